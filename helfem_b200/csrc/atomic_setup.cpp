@@ -1,0 +1,320 @@
+// Host-side setup of the atomic (l,m) x radial-FE basis: element structure,
+// cross-element radial integrals and the in-element two-electron kernel in
+// pivoted-Cholesky form.  Produces the BasisTables the J/K engine consumes.
+//
+// Reference behaviour: src/atomic/TwoDBasis.cpp:66-94 (ctor), :708-735
+// (compute_tei), src/atomic/basis.cpp:179-203 (angular ordering),
+// libhelfemqc/include/CoulombExchangeFE.h:180-217 (disjoint factors),
+// libhelfem/src/RadialBasis.cpp:245-257,643-716 and
+// libhelfem/src/quadrature.cpp:37-161 (nested quadrature for r_<^L/r_>^(L+1)).
+#include <cmath>
+#include <map>
+#include <memory>
+
+#include "fem.h"
+#include "tables.h"
+
+namespace hfq {
+
+namespace {
+
+constexpr int kOrderCap = 512;
+constexpr double kCholTol = 1e-12;  // absolute, src/atomic/TwoDBasis.h:118-119
+
+// B/r on element iel (analytic deflation on the first element).
+Mat radial_bf(const FEBasis &fe, const std::vector<double> &x, int iel) {
+  if (iel == 0) return fe.eval_over_r(x, 0, iel);
+  Mat v = fe.eval_dnf(x, 0, iel);
+  const std::vector<double> r = fe.coord(x, iel);
+  for (int j = 0; j < v.cols; j++)
+    for (int q = 0; q < v.rows; q++) v(q, j) /= r[q];
+  return v;
+}
+
+// sum_q w_q scale f(r_q) lh(q,i) rh(q,j) on element iel
+Mat element_integral(const FEBasis &fe, int iel, const std::function<Mat(const std::vector<double> &, int)> &ev,
+                     const std::vector<double> &x, const std::vector<double> &w, const std::function<double(double)> &f) {
+  const std::vector<double> r = fe.coord(x, iel);
+  std::vector<double> wp(x.size());
+  for (size_t q = 0; q < x.size(); q++) {
+    wp[q] = w[q] * fe.scale(iel);
+    if (f) {
+      const double fv = f(r[q]);
+      wp[q] = std::isfinite(fv) ? wp[q] * fv : 0.0;
+    }
+  }
+  const Mat bf = ev(x, iel);
+  return weighted_gram(bf, wp, bf);
+}
+
+// Auto-converging Gauss-Lobatto element integral (FiniteElementBasis.cpp:557-604).
+Mat element_integral_auto(const FEBasis &fe, int iel, const std::function<Mat(const std::vector<double> &, int)> &ev,
+                          const std::function<double(double)> &f, int poly_degree_f) {
+  const int basisdeg = std::max(0, fe.nnodes() - 1);
+  const int deg = 2 * basisdeg + std::max(0, poly_degree_f);
+  const int nstart = std::max(5, (deg + 4) / 2 + 2);
+  return converge_block(
+      [&](int n) {
+        std::vector<double> x, w;
+        lobatto_rule(n, x, w);
+        return element_integral(fe, iel, ev, x, w, f);
+      },
+      nstart, kOrderCap);
+}
+
+// Element data for the in-element kernel that depend only on (element, rule).
+struct NestedRule {
+  std::vector<double> x, w, r;   // outer rule and radii
+  Mat bf;                        // outer B values (n x nbf)
+  std::vector<Mat> subbf;        // B at the points of sub-interval ip
+  std::vector<std::vector<double>> subr;
+  std::vector<double> sublen;
+  bool empty_first = false;
+};
+
+NestedRule make_nested_rule(const FEBasis &fe, int iel, int n) {
+  NestedRule nr;
+  lobatto_rule(n, nr.x, nr.w);
+  const double rmin = fe.begin(iel), rmax = fe.end(iel);
+  const double rmid = 0.5 * (rmax + rmin), rlen = 0.5 * (rmax - rmin);
+  nr.r.resize(n);
+  for (int q = 0; q < n; q++) nr.r[q] = rmid + rlen * nr.x[q];
+  const std::vector<int> en = fe.enabled(iel);
+  auto eval = [&](const std::vector<double> &xp) {
+    const Mat prim = lip_eval(xp, fe.nodes(), 0);
+    Mat out((int)xp.size(), (int)en.size());
+    for (size_t k = 0; k < en.size(); k++)
+      for (size_t q = 0; q < xp.size(); q++) out((int)q, (int)k) = prim((int)q, en[k]);
+    return out;
+  };
+  nr.bf = eval(nr.x);
+  nr.empty_first = (nr.r[0] == rmin);
+  nr.subbf.resize(n);
+  nr.subr.resize(n);
+  nr.sublen.assign(n, 0.0);
+  for (int ip = 0; ip < n; ip++) {
+    if (ip == 0 && nr.empty_first) continue;
+    const double a = (ip == 0) ? rmin : nr.r[ip - 1], b = nr.r[ip];
+    const double smid = 0.5 * (b + a), slen = 0.5 * (b - a);
+    std::vector<double> rs(n), xp(n);
+    for (int q = 0; q < n; q++) {
+      rs[q] = smid + slen * nr.x[q];
+      xp[q] = (rs[q] - rmid) / rlen;
+    }
+    nr.subbf[ip] = eval(xp);
+    nr.subr[ip] = rs;
+    nr.sublen[ip] = slen;
+  }
+  return nr;
+}
+
+// In-element tensor T[(ij),(kl)] = int int B_i B_j(r) r_<^L / r_>^(L+1) B_k B_l(r')
+// at a fixed rule (quadrature.cpp:77-161): cumulative inner integral, rescaled
+// by (r_{ip-1}/r_ip)^(L+1) between neighbouring outer points.
+Mat twoe_fixed(const FEBasis &fe, int iel, int L, const NestedRule &nr) {
+  const int n = (int)nr.x.size(), nbf = nr.bf.cols, nn = nbf * nbf;
+  const double rlen = fe.scale(iel);
+  Mat inner(n, nn);
+  std::vector<double> wp(n);
+  for (int ip = 0; ip < n; ip++) {
+    if (ip == 0 && nr.empty_first) continue;
+    const double b = nr.r[ip];
+    for (int q = 0; q < n; q++) wp[q] = nr.w[q] * (std::pow(nr.subr[ip][q] / b, L) / b) * nr.sublen[ip];
+    const Mat g = weighted_gram(nr.subbf[ip], wp, nr.subbf[ip]);
+    for (int c = 0; c < nn; c++) inner(ip, c) = g.a[c];
+  }
+  for (int ip = 1; ip < n; ip++) {
+    if (ip == 1 && nr.empty_first) continue;
+    const double fac = std::pow(nr.r[ip], -L - 1) / std::pow(nr.r[ip - 1], -L - 1);
+    for (int c = 0; c < nn; c++) inner(ip, c) += inner(ip - 1, c) * fac;
+  }
+  // outer integral: ints = (w rlen B_i B_j)^T inner, then symmetrise over r<->r'
+  Mat wbf(n, nn);
+  for (int i = 0; i < nbf; i++)
+    for (int j = 0; j < nbf; j++)
+      for (int q = 0; q < n; q++) wbf(q, i * nbf + j) = nr.bf(q, i) * nr.bf(q, j) * nr.w[q] * rlen;
+  Mat ints(nn, nn);
+  for (int c = 0; c < nn; c++) {
+    const double *ic = &inner.a[(size_t)c * n];
+    for (int rix = 0; rix < nn; rix++) {
+      const double *wr = &wbf.a[(size_t)rix * n];
+      double s = 0.0;
+      for (int q = 0; q < n; q++) s += wr[q] * ic[q];
+      ints(rix, c) = s;
+    }
+  }
+  Mat out(nn, nn);
+  for (int c = 0; c < nn; c++)
+    for (int rix = 0; rix < nn; rix++) out(rix, c) = ints(rix, c) + ints(c, rix);
+  return out;
+}
+
+// Diagonal-pivoted Cholesky, stop when the largest residual diagonal <= tol
+// (RadialBasis.cpp:670-709).  Returns (n x rank) column-major.
+void pivoted_cholesky(const Mat &A, double tol, std::vector<double> &Lout, int &rank) {
+  const int n = A.rows;
+  std::vector<double> D(n);
+  for (int i = 0; i < n; i++) D[i] = A(i, i);
+  std::vector<char> done(n, 0);
+  Lout.clear();
+  rank = 0;
+  for (int k = 0; k < n; k++) {
+    int piv = -1;
+    double pv = tol;
+    for (int i = 0; i < n; i++)
+      if (!done[i] && D[i] > pv) {
+        piv = i;
+        pv = D[i];
+      }
+    if (piv < 0) break;
+    done[piv] = 1;
+    const double sd = std::sqrt(pv);
+    Lout.resize((size_t)(rank + 1) * n);
+    double *col = &Lout[(size_t)rank * n];
+    for (int i = 0; i < n; i++) {
+      if (done[i] && i != piv) {
+        col[i] = 0.0;
+        continue;
+      }
+      double s = A(i, piv);
+      for (int j = 0; j < rank; j++) s -= Lout[(size_t)j * n + i] * Lout[(size_t)j * n + piv];
+      col[i] = s / sd;
+    }
+    col[piv] = sd;
+    for (int i = 0; i < n; i++)
+      if (!done[i]) D[i] -= col[i] * col[i];
+    rank++;
+  }
+}
+
+}  // namespace
+
+BasisTables build_atomic_tables(int Z, int lmax, int mmax, int nelem, int nnodes, double Rmax, int igrid, double zexp,
+                                int nquad) {
+  BasisTables t;
+  t.kind = BasisKind::Atomic;
+  t.nch = 1;
+  t.Z1 = Z;
+  t.nnodes = nnodes;
+  t.nquad = nquad > 0 ? nquad : 5 * nnodes;
+  t.bval = element_grid(Rmax, nelem, igrid, zexp);
+  const FEBasis fe(nnodes, t.bval, true, true);
+  t.Nrad = fe.nbf();
+  t.Nel = fe.nel();
+  for (int e = 0; e < t.Nel; e++) {
+    t.efirst.push_back(fe.first(e));
+    t.en.push_back(fe.nprim(e));
+  }
+  for (int mabs = 0; mabs <= mmax; mabs++)
+    for (int l = mabs; l <= lmax; l++) {
+      t.lval.push_back(l);
+      t.mval.push_back(mabs);
+      if (mabs > 0) {
+        t.lval.push_back(l);
+        t.mval.push_back(-mabs);
+      }
+    }
+  const int N_L = 2 * lmax + 1;
+  const double pi = std::acos(-1.0);
+  for (int L = 0; L < N_L; L++) {
+    t.lmL.push_back(L);
+    t.lmM.push_back(-1);
+    t.pref.push_back(4.0 * pi / (2 * L + 1));
+  }
+  t.sign_by_M = false;
+  t.Lext = 0;
+  t.blocks.resize((size_t)N_L * t.Nel);
+
+  auto bfR = [&](const std::vector<double> &x, int iel) { return radial_bf(fe, x, iel); };
+  const int nstart = std::min(std::max(t.nquad, 5), kOrderCap);
+
+#pragma omp parallel for schedule(dynamic)
+  for (int iel = 0; iel < t.Nel; iel++) {
+    std::map<int, std::shared_ptr<NestedRule>> rules;  // per-order cache, shared by all L
+    auto rule = [&](int n) {
+      auto it = rules.find(n);
+      if (it == rules.end()) it = rules.emplace(n, std::make_shared<NestedRule>(make_nested_rule(fe, iel, n))).first;
+      return it->second;
+    };
+    for (int L = 0; L < N_L; L++) {
+      ChannelBlock &b = t.blocks[(size_t)L * t.Nel + iel];
+      b.n = fe.nprim(iel);
+      // r^L and r^(-L-1) weighted overlaps of B/r: int (B/r)(B/r) r^(n+2) dr
+      const Mat sm = element_integral_auto(fe, iel, bfR, [L](double r) { return std::pow(r, L + 2); }, -1);
+      b.small = sm.a;
+      if (iel > 0) {  // never needed (and divergent) on the element touching r = 0
+        const Mat bg = element_integral_auto(fe, iel, bfR, [L](double r) { return std::pow(r, -L - 1 + 2); }, -1);
+        b.big = bg.a;
+      }
+      const Mat tei = converge_block([&](int n) { return twoe_fixed(fe, iel, L, *rule(n)); }, nstart, kOrderCap);
+      pivoted_cholesky(tei, kCholTol, b.B, b.rank);
+      b.sigma.assign(b.rank, 1.0);
+    }
+  }
+  return t;
+}
+
+// ---------------------------------------------------------------------------
+// shared BasisTables helpers
+// ---------------------------------------------------------------------------
+
+int BasisTables::Nbf() const {
+  int n = 0;
+  for (size_t i = 0; i < mval.size(); i++) n += Nrad - ((drop_first_m_nonzero && mval[i] != 0) ? 1 : 0);
+  return n;
+}
+
+std::vector<int64_t> BasisTables::pure_idx() const {
+  std::vector<int64_t> idx;
+  for (size_t i = 0; i < mval.size(); i++) {
+    const int skip = (drop_first_m_nonzero && mval[i] != 0) ? 1 : 0;
+    for (int j = skip; j < Nrad; j++) idx.push_back((int64_t)i * Nrad + j);
+  }
+  return idx;
+}
+
+int BasisTables::channel(int L, int Mabs) const {
+  for (size_t i = 0; i < lmL.size(); i++)
+    if (lmL[i] == L && (lmM[i] < 0 || lmM[i] == Mabs)) return (int)i;
+  return -1;
+}
+
+// One-electron matrices for the atomic basis (TwoDBasis.cpp:320-375).
+void atomic_one_electron(const BasisTables &t, std::vector<double> &S, std::vector<double> &T, std::vector<double> &V) {
+  const FEBasis fe(t.nnodes, t.bval, true, true);
+  const int N = t.Nrad, na = t.Nang(), nbf = na * N;
+  auto bfR = [&](const std::vector<double> &x, int iel) { return radial_bf(fe, x, iel); };
+  auto bfB0 = [&](const std::vector<double> &x, int iel) { return fe.eval_dnf(x, 0, iel); };
+  auto bfB1 = [&](const std::vector<double> &x, int iel) { return fe.eval_dnf(x, 1, iel); };
+  Mat Srad(N, N), Trad(N, N), Tl(N, N), Vrad(N, N);
+  for (int e = 0; e < t.Nel; e++) {
+    const Mat s = element_integral_auto(fe, e, bfR, [](double r) { return r * r; }, -1);
+    const Mat k = element_integral_auto(fe, e, bfB1, nullptr, 0);
+    const Mat kl = element_integral_auto(fe, e, bfR, nullptr, -1);
+    const Mat v = element_integral_auto(fe, e, bfR, [](double r) { return r; }, -1);
+    (void)bfB0;
+    const int f = fe.first(e), n = fe.nprim(e);
+    for (int j = 0; j < n; j++)
+      for (int i = 0; i < n; i++) {
+        Srad(f + i, f + j) += s(i, j);
+        Trad(f + i, f + j) += 0.5 * k(i, j);
+        Tl(f + i, f + j) += 0.5 * kl(i, j);
+        Vrad(f + i, f + j) += v(i, j);
+      }
+  }
+  S.assign((size_t)nbf * nbf, 0.0);
+  T.assign((size_t)nbf * nbf, 0.0);
+  V.assign((size_t)nbf * nbf, 0.0);
+  for (int a = 0; a < na; a++) {
+    const double ll = (double)t.lval[a] * (t.lval[a] + 1);
+    for (int j = 0; j < N; j++)
+      for (int i = 0; i < N; i++) {
+        const size_t o = (size_t)(a * N + i) + (size_t)(a * N + j) * nbf;
+        S[o] = Srad(i, j);
+        T[o] = Trad(i, j) + ll * Tl(i, j);
+        V[o] = -(double)t.Z1 * Vrad(i, j);
+      }
+  }
+}
+
+}  // namespace hfq

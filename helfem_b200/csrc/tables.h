@@ -1,0 +1,71 @@
+// Host-side description of one basis for the J/K engine: the angular function
+// list, the radial element structure and the integral caches (cross-element
+// "disjoint" factors and the in-element low-rank factor) per multipole channel.
+//
+// The same structure describes the three reference basis types:
+//   atomic   (src/atomic/TwoDBasis.h:83-128):  nch = 1, channel index = L,
+//            small = r^L, big = r^(-L-1), factor = pivoted Cholesky, sigma = +1,
+//            prefactor 4 pi/(2L+1), couplings = Gaunt coefficients.
+//   diatomic (src/diatomic/basis.h:151-188):   nch = 2 (cos^2-modified Gaunt
+//            channel "0" and plain Gaunt channel "2"), channel index =
+//            (L,|M|), small = P0/P2, big = Q0/Q2, factor = sign-aware Cholesky
+//            of the 2-channel kernel, prefactor (-1)^M 4 pi Rh^5 (L-|M|)!/(L+|M|)!.
+// It can be filled either by this library's own setup (atomic_setup.cpp,
+// diatomic_setup.cpp) or by a caller that already owns the reference's caches
+// (hfq_create_from_tables in the C ABI).
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace hfq {
+
+enum class BasisKind : int { Atomic = 0, Diatomic = 1 };
+
+struct ChannelBlock {        // one (multipole channel, element)
+  int n = 0;                 // functions in the element (Ni)
+  int rank = 0;              // columns of the in-element factor
+  std::vector<double> small; // nch blocks of n*n, column-major
+  std::vector<double> big;   // nch blocks of n*n (may be empty on element 0)
+  std::vector<double> B;     // (nch*n*n) x rank, column-major
+  std::vector<double> sigma; // rank entries, +-1
+};
+
+struct BasisTables {
+  BasisKind kind = BasisKind::Atomic;
+  int nch = 1;
+  int Nrad = 0, Nel = 0;
+  std::vector<int> efirst, en;          // element -> first radial function, count
+  std::vector<int> lval, mval;          // angular functions, reference order
+  bool drop_first_m_nonzero = false;    // diatomic: m != 0 shells lose radial fn 0
+  // multipole channels; lmM[i] = -1 means "any M" (atomic: channel = L)
+  std::vector<int> lmL, lmM;
+  std::vector<double> pref;             // |prefactor| per channel
+  bool sign_by_M = false;               // multiply prefactor by (-1)^M
+  int Lext = 0;                         // coupling range |lj-li|-Lext .. lj+li+Lext
+  std::vector<ChannelBlock> blocks;     // [ilm*Nel + iel]
+  // basis parameters kept for bookkeeping / grid construction
+  double Rhalf = 0.0;
+  int Z1 = 0, Z2 = 0;
+  int nnodes = 0, nquad = 0;
+  std::vector<double> bval;
+
+  int Nang() const { return (int)lval.size(); }
+  int Ndummy() const { return Nang() * Nrad; }
+  int Nbf() const;                       // after boundary removal
+  std::vector<int64_t> pure_idx() const; // dense index -> dummy index
+  int channel(int L, int Mabs) const;    // -1 if absent
+};
+
+// atomic: Z, lmax, mmax, nelem, nnodes (LIP, primbas=4), Rmax, grid type, zexp, nquad (0 -> 5*nnodes)
+BasisTables build_atomic_tables(int Z, int lmax, int mmax, int nelem, int nnodes, double Rmax, int igrid, double zexp,
+                                int nquad);
+// diatomic: lmax_per_m[|m|], other arguments as src/diatomic/main.cpp:60-118
+BasisTables build_diatomic_tables(int Z1, int Z2, double Rbond, const std::vector<int> &lmax_per_m, int nelem,
+                                  int nnodes, double Rmax, int igrid, double zexp, int nquad);
+
+// One-electron matrices (overlap, kinetic, nuclear attraction), dense Nbf x Nbf
+// column-major -- setup helpers so that callers/tests can run an SCF around the
+// Fock-build path (src/atomic/TwoDBasis.cpp:320-375, src/diatomic/basis.cpp:1032-1166).
+void one_electron_matrices(const BasisTables &t, std::vector<double> &S, std::vector<double> &T, std::vector<double> &V);
+
+}  // namespace hfq
