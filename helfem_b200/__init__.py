@@ -1,0 +1,341 @@
+"""helfem_b200 -- B200-native SCF Fock builds (J, K) for HelFEM bases.
+
+Host-side mirror of the reference's operator interface for this path: the
+``TwoDBasis`` classes expose ``compute_tei()``, ``coulomb(P)``, ``exchange(P)``
+(and ``set_absm_symmetric`` for the diatomic basis) with the reference's names,
+argument meaning and error behaviour (src/atomic/TwoDBasis.h:181,223-227,
+src/diatomic/basis.h:265,300-302,344).  Everything is computed by the CUDA
+library ``libhelfemqc_b200.so`` through the C ABI in include/helfem_b200.h;
+there is no CPU fallback -- if the library or a GPU is missing, calls raise.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBPATH = os.path.join(_HERE, "libhelfemqc_b200.so")
+_lib = None
+
+_c_int_p = ctypes.POINTER(ctypes.c_int)
+_c_dbl_p = ctypes.POINTER(ctypes.c_double)
+
+
+class _TablesDesc(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int), ("nch", ctypes.c_int), ("Nrad", ctypes.c_int), ("Nel", ctypes.c_int),
+                ("Nang", ctypes.c_int), ("nlm", ctypes.c_int),
+                ("efirst", _c_int_p), ("en", _c_int_p), ("lval", _c_int_p), ("mval", _c_int_p),
+                ("lmL", _c_int_p), ("lmM", _c_int_p), ("pref", _c_dbl_p), ("rank", _c_int_p),
+                ("small_", _c_dbl_p), ("big_", _c_dbl_p), ("B", _c_dbl_p), ("sigma", _c_dbl_p),
+                ("Rhalf", ctypes.c_double)]
+
+
+class _TablesInfo(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in ("kind", "nch", "Nrad", "Nel", "Nang", "nlm", "Nbf", "Ndummy")]
+
+
+EXPORTED_SYMBOLS = [
+    "hfq_last_error", "hfq_tables_atomic", "hfq_tables_diatomic", "hfq_tables_from_arrays", "hfq_tables_get_info",
+    "hfq_tables_get_ints", "hfq_tables_get_doubles", "hfq_tables_get_block", "hfq_tables_one_electron",
+    "hfq_tables_destroy", "hfq_create", "hfq_destroy", "hfq_nbf", "hfq_set_absm_symmetric", "hfq_coulomb",
+    "hfq_exchange", "hfq_coulomb_device", "hfq_exchange_device", "hfq_last_timings",
+]
+
+
+def lib():
+    """Load libhelfemqc_b200.so (built in-tree by helfem_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIBPATH):
+        raise RuntimeError("libhelfemqc_b200.so is missing: run `python -m helfem_b200.build` "
+                           "(there is no CPU fallback for the Fock-build path)")
+    L = ctypes.CDLL(_LIBPATH)
+    L.hfq_last_error.restype = ctypes.c_char_p
+    vp, ci, cd, i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_int64
+    L.hfq_tables_atomic.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ci, ci, cd, ci, cd, ci]
+    L.hfq_tables_diatomic.argtypes = [ctypes.POINTER(vp), ci, ci, cd, _c_int_p, ci, ci, ci, cd, ci, cd, ci]
+    L.hfq_tables_from_arrays.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(_TablesDesc)]
+    L.hfq_tables_get_info.argtypes = [vp, ctypes.POINTER(_TablesInfo)]
+    L.hfq_tables_get_ints.argtypes = [vp, ci, vp, i64]
+    L.hfq_tables_get_doubles.argtypes = [vp, ci, vp, i64]
+    L.hfq_tables_get_block.argtypes = [vp, ci, ci, vp, vp, vp, vp]
+    L.hfq_tables_one_electron.argtypes = [vp, vp, vp, vp]
+    L.hfq_tables_destroy.argtypes = [vp]
+    L.hfq_tables_destroy.restype = None
+    L.hfq_create.argtypes = [ctypes.POINTER(vp), vp, ci]
+    L.hfq_destroy.argtypes = [vp]
+    L.hfq_destroy.restype = None
+    L.hfq_nbf.argtypes = [vp]
+    L.hfq_set_absm_symmetric.argtypes = [vp, ci]
+    L.hfq_coulomb.argtypes = [vp, vp, i64, vp, i64]
+    L.hfq_exchange.argtypes = [vp, vp, i64, vp, i64]
+    L.hfq_coulomb_device.argtypes = [vp, vp, i64, vp, i64, vp]
+    L.hfq_exchange_device.argtypes = [vp, vp, i64, vp, i64, ci, ci, vp]
+    L.hfq_last_timings.argtypes = [vp, vp, ci]
+    _lib = L
+    return L
+
+
+class HfqError(RuntimeError):
+    pass
+
+
+def _check(rc):
+    if rc < 0:
+        msg = lib().hfq_last_error().decode()
+        # the reference throws std::logic_error for misuse and size mismatches
+        raise (ValueError if rc == -1 else HfqError)(msg)
+    return rc
+
+
+def _fmat(a, n):
+    a = np.asarray(a, dtype=np.float64)
+    if a.shape != (n, n):
+        raise ValueError("Matrix does not have expected size! Got %s, expected %i x %i!" % (a.shape, n, n))
+    return np.asfortranarray(a)
+
+
+class Tables:
+    """Host-side basis description and integral caches (hfq_tables)."""
+
+    def __init__(self, handle):
+        self._h = handle
+        info = _TablesInfo()
+        _check(lib().hfq_tables_get_info(self._h, ctypes.byref(info)))
+        for name, _ in _TablesInfo._fields_:
+            setattr(self, name, getattr(info, name))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.hfq_tables_destroy(self._h)
+            self._h = None
+
+    @classmethod
+    def atomic(cls, Z, lmax, mmax, nelem, nnodes=15, Rmax=40.0, igrid=4, zexp=2.0, nquad=0):
+        h = ctypes.c_void_p()
+        _check(lib().hfq_tables_atomic(ctypes.byref(h), Z, lmax, mmax, nelem, nnodes, Rmax, igrid, zexp, nquad))
+        return cls(h)
+
+    @classmethod
+    def diatomic(cls, Z1, Z2, Rbond, lmax_per_m, nelem, nnodes=15, Rmax=40.0, igrid=4, zexp=1.0, nquad=0):
+        h = ctypes.c_void_p()
+        lm = (ctypes.c_int * len(lmax_per_m))(*[int(x) for x in lmax_per_m])
+        _check(lib().hfq_tables_diatomic(ctypes.byref(h), Z1, Z2, Rbond, lm, len(lmax_per_m), nelem, nnodes, Rmax,
+                                         igrid, zexp, nquad))
+        return cls(h)
+
+    @classmethod
+    def from_arrays(cls, kind, Nrad, efirst, en, lval, mval, lmL, lmM, pref, blocks, Rhalf=0.0):
+        """blocks[ilm*Nel+iel] = (small, big, B, sigma) with small/big shaped (nch, n, n)
+        (each n x n block column-major when flattened), B (nch*n*n, rank), sigma (rank,)."""
+        nch = 1 if kind == 0 else 2
+        ia = lambda v: np.ascontiguousarray(v, dtype=np.int32)
+        efirst, en, lval, mval, lmL, lmM = map(ia, (efirst, en, lval, mval, lmL, lmM))
+        pref = np.ascontiguousarray(pref, dtype=np.float64)
+        rank = ia([b[2].shape[1] for b in blocks])
+
+        def cat(parts):
+            return np.ascontiguousarray(np.concatenate([np.asarray(p, dtype=np.float64).ravel() for p in parts])
+                                        if parts else np.zeros(0))
+        small = cat([np.concatenate([np.asarray(m).ravel(order="F") for m in b[0]]) for b in blocks])
+        big = cat([np.concatenate([np.asarray(m).ravel(order="F") for m in b[1]]) for b in blocks])
+        Bc = cat([np.asarray(b[2]).ravel(order="F") for b in blocks])
+        sig = cat([np.asarray(b[3]) for b in blocks])
+        if len(sig) == 0:
+            sig = np.zeros(1)
+        if len(Bc) == 0:
+            Bc = np.zeros(1)
+        d = _TablesDesc(kind, nch, Nrad, len(en), len(lval), len(lmL),
+                        efirst.ctypes.data_as(_c_int_p), en.ctypes.data_as(_c_int_p), lval.ctypes.data_as(_c_int_p),
+                        mval.ctypes.data_as(_c_int_p), lmL.ctypes.data_as(_c_int_p), lmM.ctypes.data_as(_c_int_p),
+                        pref.ctypes.data_as(_c_dbl_p), rank.ctypes.data_as(_c_int_p), small.ctypes.data_as(_c_dbl_p),
+                        big.ctypes.data_as(_c_dbl_p), Bc.ctypes.data_as(_c_dbl_p), sig.ctypes.data_as(_c_dbl_p),
+                        float(Rhalf))
+        h = ctypes.c_void_p()
+        _check(lib().hfq_tables_from_arrays(ctypes.byref(h), ctypes.byref(d)))
+        return cls(h)
+
+    def ints(self, what, n):
+        out = np.zeros(n, dtype=np.int32)
+        _check(lib().hfq_tables_get_ints(self._h, what, out.ctypes.data, n))
+        return out
+
+    @property
+    def lval(self): return self.ints(0, self.Nang)
+    @property
+    def mval(self): return self.ints(1, self.Nang)
+    @property
+    def efirst(self): return self.ints(2, self.Nel)
+    @property
+    def en(self): return self.ints(3, self.Nel)
+    @property
+    def lmL(self): return self.ints(4, self.nlm)
+    @property
+    def lmM(self): return self.ints(5, self.nlm)
+    @property
+    def ranks(self): return self.ints(6, self.nlm * self.Nel)
+
+    @property
+    def pref(self):
+        out = np.zeros(self.nlm)
+        _check(lib().hfq_tables_get_doubles(self._h, 0, out.ctypes.data, self.nlm))
+        return out
+
+    @property
+    def bval(self):
+        out = np.zeros(self.Nel + 1)
+        _check(lib().hfq_tables_get_doubles(self._h, 1, out.ctypes.data, self.Nel + 1))
+        return out
+
+    def block(self, ilm, iel):
+        """(small, big, B, sigma): small/big (nch, n, n), B (nch*n*n, rank)."""
+        n = int(self.en[iel])
+        r = int(self.ranks[ilm * self.Nel + iel])
+        small = np.zeros(self.nch * n * n); big = np.zeros(self.nch * n * n)
+        B = np.zeros(max(1, self.nch * n * n * r)); sig = np.zeros(max(1, r))
+        _check(lib().hfq_tables_get_block(self._h, ilm, iel, small.ctypes.data, big.ctypes.data, B.ctypes.data,
+                                          sig.ctypes.data))
+        sm = np.stack([small[c * n * n:(c + 1) * n * n].reshape(n, n, order="F") for c in range(self.nch)])
+        bg = np.stack([big[c * n * n:(c + 1) * n * n].reshape(n, n, order="F") for c in range(self.nch)])
+        return sm, bg, B[:self.nch * n * n * r].reshape(self.nch * n * n, r, order="F"), sig[:r]
+
+    def one_electron(self):
+        n = self.Nbf
+        S, T, V = (np.zeros((n, n), order="F") for _ in range(3))
+        _check(lib().hfq_tables_one_electron(self._h, S.ctypes.data, T.ctypes.data, V.ctypes.data))
+        return S, T, V
+
+
+class _BasisBase:
+    """Common part of the atomic / diatomic TwoDBasis mirrors."""
+
+    def __init__(self, device=0):
+        self._tables = None
+        self._ctx = None
+        self._device = device
+        self._absm = False
+
+    def __del__(self):
+        if getattr(self, "_ctx", None) and _lib is not None:
+            _lib.hfq_destroy(self._ctx)
+            self._ctx = None
+
+    # -- reference API -------------------------------------------------------
+    def compute_tei(self, exchange=True):
+        """Build the integral caches (host) -- TwoDBasis::compute_tei."""
+        self._tables = self._make_tables()
+        return self
+
+    def Nbf(self):
+        return self.tables.Nbf
+
+    def Nrad(self):
+        return self.tables.Nrad
+
+    def Nang(self):
+        return self.tables.Nang
+
+    def coulomb(self, P):
+        ctx = self._context()
+        n = self.Nbf()
+        Pf = _fmat(P, n)
+        J = np.empty((n, n), order="F")
+        _check(lib().hfq_coulomb(ctx, Pf.ctypes.data, n, J.ctypes.data, n))
+        return J
+
+    def exchange(self, P):
+        ctx = self._context()
+        n = self.Nbf()
+        Pf = _fmat(P, n)
+        K = np.empty((n, n), order="F")
+        _check(lib().hfq_exchange(ctx, Pf.ctypes.data, n, K.ctypes.data, n))
+        return K
+
+    # -- device-resident variants (torch CUDA tensors, column-major = transposed view) ---------
+    def coulomb_device(self, dP_ptr, dJ_ptr, stream=None):
+        n = self.Nbf()
+        _check(lib().hfq_coulomb_device(self._context(), dP_ptr, n, dJ_ptr, n, stream))
+
+    def exchange_device(self, dP_ptr, dK_ptr, shard=0, nshards=1, stream=None):
+        n = self.Nbf()
+        _check(lib().hfq_exchange_device(self._context(), dP_ptr, n, dK_ptr, n, shard, nshards, stream))
+
+    def last_timings(self):
+        out = np.zeros(11)
+        _check(lib().hfq_last_timings(self._context(), out.ctypes.data, 11))
+        keys = ["ms_pack", "ms_fold", "ms_tgemm", "ms_offdiag", "ms_unpack", "ms_total", "flops_fold", "flops_tgemm",
+                "flops_offdiag", "launches", "device_bytes"]
+        return dict(zip(keys, out))
+
+    # -- helpers ---------------------------------------------------------------
+    @property
+    def tables(self):
+        if self._tables is None:
+            raise ValueError("Primitive teis have not been computed!\n")   # reference: std::logic_error
+        return self._tables
+
+    def _context(self):
+        if self._ctx is None:
+            t = self.tables
+            h = ctypes.c_void_p()
+            _check(lib().hfq_create(ctypes.byref(h), t._h, self._device))
+            self._ctx = h
+            _check(lib().hfq_set_absm_symmetric(self._ctx, int(self._absm)))
+        return self._ctx
+
+    def overlap(self):
+        return self.tables.one_electron()[0]
+
+    def kinetic(self):
+        return self.tables.one_electron()[1]
+
+    def nuclear(self):
+        return self.tables.one_electron()[2]
+
+
+class AtomicTwoDBasis(_BasisBase):
+    """helfem::atomic::basis::TwoDBasisT<double> (src/atomic/TwoDBasis.h)."""
+
+    def __init__(self, Z, lmax, mmax, nelem, nnodes=15, Rmax=40.0, igrid=4, zexp=2.0, nquad=0, device=0):
+        super().__init__(device)
+        self._args = (Z, lmax, mmax, nelem, nnodes, Rmax, igrid, zexp, nquad)
+
+    def _make_tables(self):
+        return Tables.atomic(*self._args)
+
+
+class DiatomicTwoDBasis(_BasisBase):
+    """helfem::diatomic::basis::TwoDBasis (src/diatomic/basis.h)."""
+
+    def __init__(self, Z1, Z2, Rbond, lmax_per_m, nelem, nnodes=15, Rmax=40.0, igrid=4, zexp=1.0, nquad=0,
+                 device=0):
+        super().__init__(device)
+        self._args = (Z1, Z2, Rbond, list(lmax_per_m), nelem, nnodes, Rmax, igrid, zexp, nquad)
+
+    def _make_tables(self):
+        return Tables.diatomic(*self._args)
+
+    def set_absm_symmetric(self, sym):
+        self._absm = bool(sym)
+        if self._ctx is not None:
+            _check(lib().hfq_set_absm_symmetric(self._ctx, int(self._absm)))
+
+    def is_absm_symmetric(self):
+        return self._absm
+
+
+class TablesBasis(_BasisBase):
+    """A basis whose caches were produced elsewhere (e.g. by an existing HelFEM build)."""
+
+    def __init__(self, tables, device=0):
+        super().__init__(device)
+        self._tables = tables
+
+    def _make_tables(self):
+        return self._tables
+
+    def set_absm_symmetric(self, sym):
+        self._absm = bool(sym)
+        if self._ctx is not None:
+            _check(lib().hfq_set_absm_symmetric(self._ctx, int(self._absm)))

@@ -1,0 +1,294 @@
+// C ABI of libhelfemqc_b200 (see include/helfem_b200.h).
+#include "../../include/helfem_b200.h"
+
+#include <cstring>
+#include <exception>
+#include <mutex>
+#include <new>
+#include <stdexcept>
+#include <string>
+
+#include "engine.h"
+#include "tables.h"
+
+struct hfq_tables {
+  hfq::BasisTables t;
+};
+
+struct hfq_ctx {
+  std::unique_ptr<hfq::Engine> eng;
+  std::mutex mu;  // the reference's gensap driver calls the build from several threads (src/sadatom/scf.cpp:329-334)
+};
+
+namespace {
+thread_local std::string g_err;
+
+template <typename F>
+int guarded(F &&f) {
+  try {
+    return f();
+  } catch (const std::logic_error &e) {
+    g_err = e.what();
+    return HFQ_ERR_INVALID;
+  } catch (const std::runtime_error &e) {
+    g_err = e.what();
+    return (g_err.find("CUDA") != std::string::npos) ? HFQ_ERR_CUDA : HFQ_ERR_INTERNAL;
+  } catch (const std::exception &e) {
+    g_err = e.what();
+    return HFQ_ERR_INTERNAL;
+  } catch (...) {
+    g_err = "unknown error";
+    return HFQ_ERR_INTERNAL;
+  }
+}
+
+int fail(int code, const char *msg) {
+  g_err = msg;
+  return code;
+}
+}  // namespace
+
+extern "C" {
+
+const char *hfq_last_error(void) { return g_err.c_str(); }
+
+int hfq_tables_atomic(hfq_tables **out, int Z, int lmax, int mmax, int nelem, int nnodes, double Rmax, int igrid,
+                      double zexp, int nquad) {
+  if (!out || lmax < 0 || mmax < 0 || mmax > lmax || nelem < 1 || nnodes < 2 || nnodes > 16 || !(Rmax > 0.0))
+    return fail(HFQ_ERR_INVALID, "hfq_tables_atomic: invalid argument");
+  return guarded([&] {
+    auto *h = new hfq_tables;
+    h->t = hfq::build_atomic_tables(Z, lmax, mmax, nelem, nnodes, Rmax, igrid, zexp, nquad);
+    *out = h;
+    return HFQ_OK;
+  });
+}
+
+int hfq_tables_diatomic(hfq_tables **out, int Z1, int Z2, double Rbond, const int *lmax_per_m, int nm, int nelem,
+                        int nnodes, double Rmax, int igrid, double zexp, int nquad) {
+  if (!out || !lmax_per_m || nm < 1 || nelem < 1 || nnodes < 2 || nnodes > 16 || !(Rbond > 0.0) || !(Rmax > 0.5 * Rbond))
+    return fail(HFQ_ERR_INVALID, "hfq_tables_diatomic: invalid argument");
+  for (int m = 0; m < nm; m++)
+    if (lmax_per_m[m] < m) return fail(HFQ_ERR_INVALID, "hfq_tables_diatomic: lmax(|m|) < |m|");
+  return guarded([&] {
+    auto *h = new hfq_tables;
+    h->t = hfq::build_diatomic_tables(Z1, Z2, Rbond, std::vector<int>(lmax_per_m, lmax_per_m + nm), nelem, nnodes,
+                                      Rmax, igrid, zexp, nquad);
+    *out = h;
+    return HFQ_OK;
+  });
+}
+
+int hfq_tables_from_arrays(hfq_tables **out, const hfq_tables_desc *d) {
+  if (!out || !d || !d->efirst || !d->en || !d->lval || !d->mval || !d->lmL || !d->lmM || !d->pref || !d->rank ||
+      !d->small_ || !d->big_ || !d->B || !d->sigma)
+    return fail(HFQ_ERR_INVALID, "hfq_tables_from_arrays: null argument");
+  if ((d->kind != 0 && d->kind != 1) || d->nch != (d->kind == 0 ? 1 : 2) || d->Nrad < 1 || d->Nel < 1 ||
+      d->Nang < 1 || d->nlm < 1)
+    return fail(HFQ_ERR_INVALID, "hfq_tables_from_arrays: inconsistent sizes");
+  return guarded([&] {
+    auto *h = new hfq_tables;
+    hfq::BasisTables &t = h->t;
+    t.kind = d->kind == 0 ? hfq::BasisKind::Atomic : hfq::BasisKind::Diatomic;
+    t.nch = d->nch;
+    t.Nrad = d->Nrad;
+    t.Nel = d->Nel;
+    t.efirst.assign(d->efirst, d->efirst + d->Nel);
+    t.en.assign(d->en, d->en + d->Nel);
+    t.lval.assign(d->lval, d->lval + d->Nang);
+    t.mval.assign(d->mval, d->mval + d->Nang);
+    t.lmL.assign(d->lmL, d->lmL + d->nlm);
+    t.lmM.assign(d->lmM, d->lmM + d->nlm);
+    t.pref.assign(d->pref, d->pref + d->nlm);
+    t.drop_first_m_nonzero = d->kind == 1;
+    t.sign_by_M = d->kind == 1;
+    t.Lext = d->kind == 1 ? 2 : 0;
+    t.Rhalf = d->Rhalf;
+    for (int e = 0; e < t.Nel; e++)
+      if (t.efirst[e] < 0 || t.en[e] < 1 || t.efirst[e] + t.en[e] > t.Nrad) {
+        delete h;
+        throw std::logic_error("hfq_tables_from_arrays: element outside the radial basis");
+      }
+    t.blocks.resize((size_t)d->nlm * d->Nel);
+    size_t os = 0, ob = 0, og = 0;
+    for (int ilm = 0; ilm < d->nlm; ilm++)
+      for (int e = 0; e < d->Nel; e++) {
+        hfq::ChannelBlock &b = t.blocks[(size_t)ilm * d->Nel + e];
+        b.n = t.en[e];
+        b.rank = d->rank[(size_t)ilm * d->Nel + e];
+        const size_t nn = (size_t)t.nch * b.n * b.n;
+        b.small.assign(d->small_ + os, d->small_ + os + nn);
+        b.big.assign(d->big_ + os, d->big_ + os + nn);
+        os += nn;
+        b.B.assign(d->B + ob, d->B + ob + nn * b.rank);
+        ob += nn * b.rank;
+        b.sigma.assign(d->sigma + og, d->sigma + og + b.rank);
+        og += b.rank;
+      }
+    *out = h;
+    return HFQ_OK;
+  });
+}
+
+int hfq_tables_get_info(const hfq_tables *h, hfq_tables_info *info) {
+  if (!h || !info) return fail(HFQ_ERR_INVALID, "hfq_tables_get_info: null argument");
+  const hfq::BasisTables &t = h->t;
+  info->kind = (int)t.kind;
+  info->nch = t.nch;
+  info->Nrad = t.Nrad;
+  info->Nel = t.Nel;
+  info->Nang = t.Nang();
+  info->nlm = (int)t.lmL.size();
+  info->Nbf = t.Nbf();
+  info->Ndummy = t.Ndummy();
+  return HFQ_OK;
+}
+
+int hfq_tables_get_ints(const hfq_tables *h, int what, int *out, int64_t cap) {
+  if (!h || !out) return fail(HFQ_ERR_INVALID, "hfq_tables_get_ints: null argument");
+  const hfq::BasisTables &t = h->t;
+  std::vector<int> ranks;
+  const std::vector<int> *src = nullptr;
+  switch (what) {
+    case 0: src = &t.lval; break;
+    case 1: src = &t.mval; break;
+    case 2: src = &t.efirst; break;
+    case 3: src = &t.en; break;
+    case 4: src = &t.lmL; break;
+    case 5: src = &t.lmM; break;
+    case 6:
+      for (const auto &b : t.blocks) ranks.push_back(b.rank);
+      src = &ranks;
+      break;
+    default: return fail(HFQ_ERR_INVALID, "hfq_tables_get_ints: unknown selector");
+  }
+  if ((int64_t)src->size() > cap) return fail(HFQ_ERR_INVALID, "hfq_tables_get_ints: buffer too small");
+  std::memcpy(out, src->data(), src->size() * sizeof(int));
+  return (int)src->size();
+}
+
+int hfq_tables_get_doubles(const hfq_tables *h, int what, double *out, int64_t cap) {
+  if (!h || !out) return fail(HFQ_ERR_INVALID, "hfq_tables_get_doubles: null argument");
+  const std::vector<double> *src = what == 0 ? &h->t.pref : what == 1 ? &h->t.bval : nullptr;
+  if (!src) return fail(HFQ_ERR_INVALID, "hfq_tables_get_doubles: unknown selector");
+  if ((int64_t)src->size() > cap) return fail(HFQ_ERR_INVALID, "hfq_tables_get_doubles: buffer too small");
+  std::memcpy(out, src->data(), src->size() * sizeof(double));
+  return (int)src->size();
+}
+
+int hfq_tables_get_block(const hfq_tables *h, int ilm, int iel, double *small_, double *big_, double *B,
+                         double *sigma) {
+  if (!h) return fail(HFQ_ERR_INVALID, "hfq_tables_get_block: null argument");
+  const hfq::BasisTables &t = h->t;
+  if (ilm < 0 || ilm >= (int)t.lmL.size() || iel < 0 || iel >= t.Nel)
+    return fail(HFQ_ERR_INVALID, "hfq_tables_get_block: index out of range");
+  const hfq::ChannelBlock &b = t.blocks[(size_t)ilm * t.Nel + iel];
+  const size_t nn = (size_t)t.nch * b.n * b.n;
+  if (small_) std::memcpy(small_, b.small.data(), nn * sizeof(double));
+  if (big_) {
+    if (b.big.size() == nn)
+      std::memcpy(big_, b.big.data(), nn * sizeof(double));
+    else
+      std::memset(big_, 0, nn * sizeof(double));
+  }
+  if (B) std::memcpy(B, b.B.data(), b.B.size() * sizeof(double));
+  if (sigma) std::memcpy(sigma, b.sigma.data(), b.sigma.size() * sizeof(double));
+  return HFQ_OK;
+}
+
+int hfq_tables_one_electron(const hfq_tables *h, double *S, double *T, double *V) {
+  if (!h || !S || !T || !V) return fail(HFQ_ERR_INVALID, "hfq_tables_one_electron: null argument");
+  if (h->t.bval.empty()) return fail(HFQ_ERR_STATE, "hfq_tables_one_electron: tables were not built by this library");
+  return guarded([&] {
+    std::vector<double> s, t, v;
+    hfq::one_electron_matrices(h->t, s, t, v);
+    std::memcpy(S, s.data(), s.size() * sizeof(double));
+    std::memcpy(T, t.data(), t.size() * sizeof(double));
+    std::memcpy(V, v.data(), v.size() * sizeof(double));
+    return HFQ_OK;
+  });
+}
+
+void hfq_tables_destroy(hfq_tables *h) { delete h; }
+
+int hfq_create(hfq_ctx **out, const hfq_tables *h, int device) {
+  if (!out || !h) return fail(HFQ_ERR_INVALID, "hfq_create: null argument");
+  if (h->t.blocks.empty())
+    return fail(HFQ_ERR_STATE, "Primitive teis have not been computed!");
+  return guarded([&] {
+    auto c = std::make_unique<hfq_ctx>();
+    c->eng = std::make_unique<hfq::Engine>(h->t, device);
+    *out = c.release();
+    return HFQ_OK;
+  });
+}
+
+void hfq_destroy(hfq_ctx *ctx) { delete ctx; }
+
+int hfq_nbf(const hfq_ctx *ctx) { return ctx ? ctx->eng->Nbf() : fail(HFQ_ERR_INVALID, "hfq_nbf: null context"); }
+
+int hfq_set_absm_symmetric(hfq_ctx *ctx, int flag) {
+  if (!ctx) return fail(HFQ_ERR_INVALID, "hfq_set_absm_symmetric: null context");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->eng->set_absm_symmetric(flag != 0);
+  return HFQ_OK;
+}
+
+static int check_mat(const hfq_ctx *ctx, const void *a, int64_t lda, const void *b, int64_t ldb) {
+  if (!ctx || !a || !b) return fail(HFQ_ERR_INVALID, "null argument");
+  const int64_t n = ctx->eng->Nbf();
+  if (lda < n || ldb < n) {
+    g_err = "Matrix does not have expected size! Leading dimension smaller than Nbf = " + std::to_string(n);
+    return HFQ_ERR_INVALID;
+  }
+  return HFQ_OK;
+}
+
+int hfq_coulomb(hfq_ctx *ctx, const double *P, int64_t ldP, double *J, int64_t ldJ) {
+  if (int rc = check_mat(ctx, P, ldP, J, ldJ)) return rc;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  return guarded([&] {
+    ctx->eng->coulomb(P, ldP, J, ldJ);
+    return HFQ_OK;
+  });
+}
+
+int hfq_exchange(hfq_ctx *ctx, const double *P, int64_t ldP, double *K, int64_t ldK) {
+  if (int rc = check_mat(ctx, P, ldP, K, ldK)) return rc;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  return guarded([&] {
+    ctx->eng->exchange(P, ldP, K, ldK);
+    return HFQ_OK;
+  });
+}
+
+int hfq_coulomb_device(hfq_ctx *ctx, const double *dP, int64_t ldP, double *dJ, int64_t ldJ, void *stream) {
+  if (int rc = check_mat(ctx, dP, ldP, dJ, ldJ)) return rc;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  return guarded([&] {
+    ctx->eng->coulomb_dev(dP, ldP, dJ, ldJ, stream ? (cudaStream_t)stream : ctx->eng->stream());
+    return HFQ_OK;
+  });
+}
+
+int hfq_exchange_device(hfq_ctx *ctx, const double *dP, int64_t ldP, double *dK, int64_t ldK, int shard,
+                        int nshards, void *stream) {
+  if (int rc = check_mat(ctx, dP, ldP, dK, ldK)) return rc;
+  if (nshards < 1 || shard < 0 || shard >= nshards) return fail(HFQ_ERR_INVALID, "hfq_exchange_device: bad shard");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  return guarded([&] {
+    ctx->eng->exchange_dev(dP, ldP, dK, ldK, shard, nshards, stream ? (cudaStream_t)stream : ctx->eng->stream());
+    return HFQ_OK;
+  });
+}
+
+int hfq_last_timings(const hfq_ctx *ctx, double *out, int n) {
+  if (!ctx || !out) return fail(HFQ_ERR_INVALID, "hfq_last_timings: null argument");
+  const hfq::EngineTimings &t = ctx->eng->timings();
+  const double v[11] = {t.pack, t.fold, t.tgemm, t.offdiag, t.unpack, t.total, t.flops_fold, t.flops_tgemm,
+                        t.flops_offdiag, (double)t.launches, (double)ctx->eng->device_bytes()};
+  for (int i = 0; i < n && i < 11; i++) out[i] = v[i];
+  return HFQ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,821 @@
+// Host orchestration of the J/K engine.  See engine.h / kernels.cuh.
+#include "engine.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <numeric>
+#include <stdexcept>
+
+#include "kernels.cuh"
+#include "special.h"
+
+namespace hfq {
+
+#define CK(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t err__ = (call);                                                                   \
+    if (err__ != cudaSuccess)                                                                     \
+      throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(err__) + " at " + \
+                               __FILE__ + ":" + std::to_string(__LINE__));                        \
+  } while (0)
+
+namespace {
+
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  size_t *counter = nullptr;
+  void alloc(size_t count, size_t *ctr) {
+    release();
+    n = count;
+    counter = ctr;
+    if (count) {
+      CK(cudaMalloc(&p, count * sizeof(T)));
+      if (ctr) *ctr += count * sizeof(T);
+    }
+  }
+  void upload(const std::vector<T> &h, size_t *ctr) {
+    alloc(h.size(), ctr);
+    if (!h.empty()) CK(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  }
+  void release() {
+    if (p) {
+      cudaFree(p);
+      if (counter) *counter -= n * sizeof(T);
+    }
+    p = nullptr;
+    n = 0;
+  }
+  ~DevBuf() { release(); }
+};
+
+int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+}  // namespace
+
+struct Engine::Impl {
+  BasisTables t;   // host copy (without the big factor arrays after upload)
+  // sector structure
+  int ns = 0, NP = 0, NB = 0, NT = 0, NL = 0, nab = 1, Npix = 0;
+  std::vector<int> sec_m, sec_n, sec_ang, ang_sec, ang_pos, ang_off, ang_skip;
+  std::vector<int> sec_lmin, sec_lmax;
+  int mmin = 0, mmax = 0, nM = 0;   // M = m_a - m_b range: -(mmax-mmin) .. (mmax-mmin)
+  // channels
+  std::vector<int> chan_run, chan_pos, run_nL, run_first;   // |M| runs
+  std::vector<int64_t> blk_off, B_off, sig_off;
+  std::vector<int> ranks;
+  std::vector<char> G_nonzero;      // [sp*NL + L]
+  // element-pair accumulator layout
+  std::vector<int64_t> ep_off;
+  int64_t op_stride = 0;
+  std::vector<int64_t> tperm_off;   // [Nel * nruns] offset of A_(e,run)
+  std::vector<int64_t> tperm_lda;   // [Nel * nruns]
+  // device
+  DevBuf<int> d_ang_off, d_ang_skip, d_sec_n, d_sec_ang, d_efirst, d_en, d_ang_sec, d_ang_pos;
+  DevBuf<double> d_G, d_small, d_big, d_B, d_sigma, d_tperm;
+  DevBuf<int64_t> d_blk_off, d_B_off, d_sig_off, d_ep_off;
+  DevBuf<int> d_rank, d_chan_of, d_browoff_T, d_browoff_G, d_splist, d_op_src, d_sp_active;
+  DevBuf<double> d_jfac, d_norms, d_Ppix, d_R, d_Kacc, d_Paux, d_JauxT, d_Jsec, d_P, d_O;
+  DevBuf<dev::FoldTask> d_tasks;
+  DevBuf<dev::GemmItem> d_gitems;
+  DevBuf<dev::GemmEntry> d_gentries;
+  DevBuf<dev::OffItem> d_oitems;
+  DevBuf<dev::OffEntry> d_oentries;
+  std::vector<int> browoff_T_first;  // per element: first index into d_browoff_T
+  dev::BasisDev bd{};
+  size_t r_slots = 0;                // capacity of the R buffer in task slots
+  cudaEvent_t ev[8];
+};
+
+Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(device) {
+  CK(cudaSetDevice(device));
+  CK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  Impl &s = *p_;
+  for (auto &e : s.ev) CK(cudaEventCreate(&e));
+  s.t = tin;
+  const BasisTables &t = s.t;
+  nbf_ = t.Nbf();
+  if (t.Nel > 64) throw std::runtime_error("Engine: more than 64 radial elements not supported");
+  for (int e = 0; e < t.Nel; e++)
+    if (t.en[e] > 16) throw std::runtime_error("Engine: more than 16 functions per element not supported");
+  s.nab = t.nch * t.nch;
+  s.Npix = t.Nrad * t.Nrad;
+  // ---- m sectors, in ascending m
+  const int na = t.Nang();
+  std::map<int, std::vector<int>> bym;
+  for (int a = 0; a < na; a++) bym[t.mval[a]].push_back(a);
+  s.ns = (int)bym.size();
+  int nmaxsec = 0;
+  for (auto &kv : bym) {
+    std::sort(kv.second.begin(), kv.second.end(), [&](int x, int y) { return t.lval[x] < t.lval[y]; });
+    nmaxsec = std::max(nmaxsec, (int)kv.second.size());
+  }
+  const int supported_nt[] = {1, 2, 3, 4, 6, 8};
+  s.NT = 0;
+  for (int nt : supported_nt)
+    if (nt * 8 >= nmaxsec) {
+      s.NT = nt;
+      break;
+    }
+  if (!s.NT) throw std::runtime_error("Engine: more than 64 angular functions per m sector not supported");
+  s.NP = s.NT * 8;
+  s.NB = s.NP * s.NP;
+  s.ang_sec.assign(na, 0);
+  s.ang_pos.assign(na, 0);
+  s.sec_ang.assign((size_t)s.ns * s.NP, -1);
+  {
+    int si = 0;
+    for (auto &kv : bym) {
+      s.sec_m.push_back(kv.first);
+      s.sec_n.push_back((int)kv.second.size());
+      int lmn = 1 << 30, lmx = 0;
+      for (size_t k = 0; k < kv.second.size(); k++) {
+        s.sec_ang[(size_t)si * s.NP + k] = kv.second[k];
+        s.ang_sec[kv.second[k]] = si;
+        s.ang_pos[kv.second[k]] = (int)k;
+        lmn = std::min(lmn, t.lval[kv.second[k]]);
+        lmx = std::max(lmx, t.lval[kv.second[k]]);
+      }
+      s.sec_lmin.push_back(lmn);
+      s.sec_lmax.push_back(lmx);
+      si++;
+    }
+  }
+  s.mmin = s.sec_m.front();
+  s.mmax = s.sec_m.back();
+  s.nM = 2 * (s.mmax - s.mmin) + 1;
+  s.ang_off.assign(na, 0);
+  s.ang_skip.assign(na, 0);
+  {
+    int off = 0;
+    for (int a = 0; a < na; a++) {
+      s.ang_skip[a] = (t.drop_first_m_nonzero && t.mval[a] != 0) ? 1 : 0;
+      s.ang_off[a] = off;
+      off += t.Nrad - s.ang_skip[a];
+    }
+  }
+  // ---- multipole range and coupling tables
+  int lmaxall = 0;
+  for (int l : t.lval) lmaxall = std::max(lmaxall, l);
+  s.NL = 0;
+  for (int L : t.lmL) s.NL = std::max(s.NL, L + 1);
+  {
+    const GauntTable gt(std::max(s.NL + 2, lmaxall + 2));
+    const size_t gsz = (size_t)s.ns * s.ns * s.NL * t.nch * s.NB;
+    std::vector<double> G(gsz, 0.0);
+    s.G_nonzero.assign((size_t)s.ns * s.ns * s.NL, 0);
+#pragma omp parallel for collapse(2) schedule(dynamic)
+    for (int sa = 0; sa < s.ns; sa++)
+      for (int sb = 0; sb < s.ns; sb++) {
+        const int sp = sa * s.ns + sb, ma = s.sec_m[sa], mb = s.sec_m[sb], M = ma - mb;
+        for (int L = std::abs(M); L < s.NL; L++) {
+          if (t.channel(L, std::abs(M)) < 0) continue;
+          bool any = false;
+          for (int ia = 0; ia < s.sec_n[sa]; ia++)
+            for (int ib = 0; ib < s.sec_n[sb]; ib++) {
+              const int la = t.lval[s.sec_ang[(size_t)sa * s.NP + ia]], lb = t.lval[s.sec_ang[(size_t)sb * s.NP + ib]];
+              if (L < std::max(std::abs(la - lb) - t.Lext, std::abs(M)) || L > la + lb + t.Lext) continue;
+              double *dst = &G[(((size_t)sp * s.NL + L) * t.nch) * s.NB + (size_t)ia * s.NP + ib];
+              if (t.kind == BasisKind::Atomic) {
+                dst[0] = gt.coeff(la, ma, L, M, lb);
+                any |= dst[0] != 0.0;
+              } else {
+                dst[0] = gt.mod_coeff(la, ma, L, M, lb, mb);
+                dst[s.NB] = -gt.coeff(la, ma, L, M, lb);
+                any |= dst[0] != 0.0 || dst[s.NB] != 0.0;
+              }
+            }
+          s.G_nonzero[(size_t)sp * s.NL + L] = any;
+        }
+      }
+    s.d_G.upload(G, &dev_bytes_);
+  }
+  // ---- channel runs (same |M|), flattened cache arrays
+  const int nlm = (int)t.lmL.size();
+  s.chan_run.assign(nlm, 0);
+  s.chan_pos.assign(nlm, 0);
+  for (int i = 0; i < nlm;) {
+    int j = i;
+    while (j < nlm && t.lmM[j] == t.lmM[i]) j++;
+    for (int k = i; k < j; k++) {
+      s.chan_run[k] = (int)s.run_nL.size();
+      s.chan_pos[k] = k - i;
+    }
+    s.run_first.push_back(i);
+    s.run_nL.push_back(j - i);
+    i = j;
+  }
+  {
+    std::vector<double> hsmall, hbig, hB, hsig;
+    s.blk_off.assign((size_t)nlm * t.Nel, 0);
+    s.B_off.assign((size_t)nlm * t.Nel, 0);
+    s.sig_off.assign((size_t)nlm * t.Nel, 0);
+    s.ranks.assign((size_t)nlm * t.Nel, 0);
+    for (int ilm = 0; ilm < nlm; ilm++)
+      for (int e = 0; e < t.Nel; e++) {
+        const ChannelBlock &b = t.blocks[(size_t)ilm * t.Nel + e];
+        const size_t nn = (size_t)t.nch * b.n * b.n;
+        if (b.rank > 128) throw std::runtime_error("Engine: in-element factor rank > 128");
+        s.blk_off[(size_t)ilm * t.Nel + e] = (int64_t)hsmall.size();
+        hsmall.insert(hsmall.end(), b.small.begin(), b.small.end());
+        if (b.big.size() == nn)
+          hbig.insert(hbig.end(), b.big.begin(), b.big.end());
+        else
+          hbig.insert(hbig.end(), nn, 0.0);
+        s.B_off[(size_t)ilm * t.Nel + e] = (int64_t)hB.size();
+        hB.insert(hB.end(), b.B.begin(), b.B.end());
+        s.sig_off[(size_t)ilm * t.Nel + e] = (int64_t)hsig.size();
+        hsig.insert(hsig.end(), b.sigma.begin(), b.sigma.end());
+        s.ranks[(size_t)ilm * t.Nel + e] = b.rank;
+      }
+    s.d_small.upload(hsmall, &dev_bytes_);
+    s.d_big.upload(hbig, &dev_bytes_);
+    s.d_B.upload(hB, &dev_bytes_);
+    s.d_sigma.upload(hsig, &dev_bytes_);
+    s.d_blk_off.upload(s.blk_off, &dev_bytes_);
+    s.d_B_off.upload(s.B_off, &dev_bytes_);
+    s.d_sig_off.upload(s.sig_off, &dev_bytes_);
+    s.d_rank.upload(s.ranks, &dev_bytes_);
+  }
+  // free the big host copies
+  for (auto &b : s.t.blocks) {
+    std::vector<double>().swap(b.B);
+    std::vector<double>().swap(b.small);
+    std::vector<double>().swap(b.big);
+  }
+  // ---- small index arrays
+  s.d_ang_off.upload(s.ang_off, &dev_bytes_);
+  s.d_ang_skip.upload(s.ang_skip, &dev_bytes_);
+  s.d_sec_n.upload(s.sec_n, &dev_bytes_);
+  s.d_sec_ang.upload(s.sec_ang, &dev_bytes_);
+  s.d_efirst.upload(t.efirst, &dev_bytes_);
+  s.d_en.upload(t.en, &dev_bytes_);
+  s.d_ang_sec.upload(s.ang_sec, &dev_bytes_);
+  s.d_ang_pos.upload(s.ang_pos, &dev_bytes_);
+  s.bd = dev::BasisDev{na, t.Nrad, s.Npix, s.NP, s.NB, s.ns, t.nch, s.nab, t.Nel, s.NL,
+                       s.d_ang_off.p, s.d_ang_skip.p, s.d_sec_n.p, s.d_sec_ang.p, s.d_efirst.p, s.d_en.p};
+  // ---- element-pair accumulator layout
+  s.ep_off.assign((size_t)t.Nel * t.Nel, 0);
+  {
+    int64_t off = 0;
+    for (int ei = 0; ei < t.Nel; ei++)
+      for (int ej = 0; ej < t.Nel; ej++) {
+        s.ep_off[(size_t)ei * t.Nel + ej] = off;
+        off += (int64_t)t.en[ei] * t.en[ej] * s.NB;
+      }
+    s.op_stride = off;
+  }
+  s.d_ep_off.upload(s.ep_off, &dev_bytes_);
+  // ---- dense exchange-ordered in-element kernels  A_(e,run)[(rj,rk)][pos][ab][(ri,rl)]
+  {
+    const int nruns = (int)s.run_nL.size();
+    s.tperm_off.assign((size_t)t.Nel * nruns, 0);
+    s.tperm_lda.assign((size_t)t.Nel * nruns, 0);
+    int64_t off = 0;
+    for (int e = 0; e < t.Nel; e++)
+      for (int r = 0; r < nruns; r++) {
+        const int64_t nn = (int64_t)t.en[e] * t.en[e];
+        s.tperm_off[(size_t)e * nruns + r] = off;
+        s.tperm_lda[(size_t)e * nruns + r] = (int64_t)s.run_nL[r] * s.nab * nn;
+        off += nn * s.run_nL[r] * s.nab * nn;
+      }
+    s.d_tperm.alloc((size_t)off, &dev_bytes_);
+    for (int ilm = 0; ilm < nlm; ilm++)
+      for (int e = 0; e < t.Nel; e++) {
+        const int n = t.en[e], r = s.chan_run[ilm];
+        const int64_t nn = (int64_t)n * n;
+        double *dst = s.d_tperm.p + s.tperm_off[(size_t)e * nruns + r] + (int64_t)s.chan_pos[ilm] * s.nab * nn;
+        dev::k_build_tperm<<<n * n, 256, 0, stream_>>>(
+            s.d_B.p + s.B_off[(size_t)ilm * t.Nel + e], s.d_sigma.p + s.sig_off[(size_t)ilm * t.Nel + e], n,
+            s.ranks[(size_t)ilm * t.Nel + e], t.nch, t.kind == BasisKind::Atomic ? 1 : 0, dst,
+            s.tperm_lda[(size_t)e * nruns + r]);
+      }
+    CK(cudaGetLastError());
+  }
+  // ---- B-row offset tables
+  {
+    // T-GEMM: k' = ab*n*n + ri*n + rl -> (ab*Npix + pix(ri,rl)) * NB
+    std::vector<int> bo;
+    for (int e = 0; e < t.Nel; e++) {
+      s.browoff_T_first.push_back((int)bo.size());
+      const int n = t.en[e], f = t.efirst[e];
+      for (int ab = 0; ab < s.nab; ab++)
+        for (int ri = 0; ri < n; ri++)
+          for (int rl = 0; rl < n; rl++) {
+            const int64_t v = ((int64_t)ab * s.Npix + (int64_t)(f + ri) * t.Nrad + f + rl) * s.NB;
+            if (v > 0x7fffffffLL) throw std::runtime_error("Engine: R row offset overflows int32");
+            bo.push_back((int)v);
+          }
+    }
+    s.d_browoff_T.upload(bo, &dev_bytes_);
+    // J unfold: q -> q * NB
+    std::vector<int> bg((size_t)s.NL * t.nch);
+    for (size_t q = 0; q < bg.size(); q++) bg[q] = (int)(q * s.NB);
+    s.d_browoff_G.upload(bg, &dev_bytes_);
+  }
+  // ---- J radial lookup
+  {
+    std::vector<int> chan_of((size_t)s.NL * s.nM, -1);
+    std::vector<double> jfac((size_t)s.NL * s.nM, 0.0);
+    for (int L = 0; L < s.NL; L++)
+      for (int Mi = 0; Mi < s.nM; Mi++) {
+        const int M = Mi - (s.mmax - s.mmin);
+        if (std::abs(M) > L) continue;
+        const int ilm = t.channel(L, std::abs(M));
+        if (ilm < 0) continue;
+        chan_of[(size_t)L * s.nM + Mi] = ilm;
+        jfac[(size_t)L * s.nM + Mi] = t.pref[ilm] * ((t.sign_by_M && (M & 1)) ? -1.0 : 1.0);
+      }
+    s.d_chan_of.upload(chan_of, &dev_bytes_);
+    s.d_jfac.upload(jfac, &dev_bytes_);
+  }
+  // ---- work buffers that do not depend on the density
+  s.d_norms.alloc((size_t)na * na, &dev_bytes_);
+  s.d_Ppix.alloc((size_t)s.ns * s.ns * s.Npix * s.NB, &dev_bytes_);
+  s.d_splist.alloc((size_t)s.ns * s.ns, &dev_bytes_);
+  s.d_op_src.alloc((size_t)s.ns * s.ns, &dev_bytes_);
+  s.d_sp_active.alloc((size_t)s.ns * s.ns, &dev_bytes_);
+  CK(cudaStreamSynchronize(stream_));
+  // opt-in shared memory sizes
+  CK(cudaFuncSetAttribute(dev::k_offdiag<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(dev::k_offdiag<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+}
+
+Engine::~Engine() {
+  if (p_)
+    for (auto &e : p_->ev) cudaEventDestroy(e);
+  if (stream_) cudaStreamDestroy(stream_);
+}
+
+namespace {
+
+template <int NT, int NCH>
+void launch_fold_t(const dev::BasisDev &bd, const dev::FoldTask *tasks, int ntasks, const double *G, const double *Ppix,
+                   double *R, cudaStream_t st) {
+  constexpr int NP = NT * 8, LD = NP + 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(dev::k_fold<NT, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  const size_t gbytes = (size_t)2 * NCH * NP * LD * sizeof(double);
+  const size_t slot = (size_t)(1 + NCH) * NP * LD * sizeof(double);
+  // pixel slots per group: fill ~100 KB, at least enough items for 8 warps
+  int PB = (int)std::max<size_t>(1, std::min<size_t>((100 * 1024 - gbytes) / slot, 64));
+  PB = std::min(PB, std::max(1, 32 / (NT * NCH)) * 2);
+  PB = std::max(PB, 1);
+  const size_t smem = gbytes + PB * slot;
+  // pixels per CTA: enough CTAs to fill the GPU, but amortise the table load
+  int ppc = std::max(PB, (int)(((int64_t)bd.Npix * ntasks + 148 * 8 - 1) / (148 * 8)));
+  ppc = std::min(ppc, std::max(PB * 8, 64));
+  ppc = round_up(std::min(ppc, bd.Npix), PB);
+  const dim3 grid((bd.Npix + ppc - 1) / ppc, ntasks);
+  dev::k_fold<NT, NCH><<<grid, 256, smem, st>>>(bd, tasks, G, Ppix, R, ppc, PB);
+  CK(cudaGetLastError());
+}
+
+void launch_fold(int NT, int nch, const dev::BasisDev &bd, const dev::FoldTask *tasks, int ntasks, const double *G,
+                 const double *Ppix, double *R, cudaStream_t st) {
+#define HFQ_FOLD_CASE(nt)                                                         \
+  case nt:                                                                        \
+    if (nch == 1)                                                                 \
+      launch_fold_t<nt, 1>(bd, tasks, ntasks, G, Ppix, R, st);                    \
+    else                                                                          \
+      launch_fold_t<nt, 2>(bd, tasks, ntasks, G, Ppix, R, st);                    \
+    break;
+  switch (NT) {
+    HFQ_FOLD_CASE(1)
+    HFQ_FOLD_CASE(2)
+    HFQ_FOLD_CASE(3)
+    HFQ_FOLD_CASE(4)
+    HFQ_FOLD_CASE(6)
+    HFQ_FOLD_CASE(8)
+    default:
+      throw std::runtime_error("fold: unsupported sector size");
+  }
+#undef HFQ_FOLD_CASE
+}
+
+template <bool KC>
+void launch_gemm(const dev::GemmItem *items, const dev::GemmEntry *entries, int nitems, int maxM, int maxN,
+                 cudaStream_t st) {
+  if (nitems == 0) return;
+  constexpr int BM = 64, BN = 64;
+  const dim3 grid((maxN + BN - 1) / BN, (maxM + BM - 1) / BM, nitems);
+  dev::k_gemm<BM, BN, 2, 2, KC><<<grid, 128, 0, st>>>(items, entries);
+  CK(cudaGetLastError());
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// exchange
+// ---------------------------------------------------------------------------
+void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK, int shard, int nshards,
+                          cudaStream_t st) {
+  Impl &s = *p_;
+  const BasisTables &t = s.t;
+  CK(cudaSetDevice(device_));
+  const int na = t.Nang(), ns = s.ns;
+  tm_ = EngineTimings();
+  CK(cudaEventRecord(s.ev[0], st));
+  // 1. which angular blocks of P carry density (reference: block norm >= 10 eps)
+  dev::k_block_norms<<<dim3(na, na), 128, 0, st>>>(s.bd, dP, ldP, s.d_norms.p);
+  CK(cudaGetLastError());
+  std::vector<double> norms((size_t)na * na);
+  CK(cudaMemcpyAsync(norms.data(), s.d_norms.p, norms.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const double thr = 10.0 * 2.220446049250313e-16;
+  std::vector<char> sp_nz((size_t)ns * ns, 0);
+  for (int a = 0; a < na; a++)
+    for (int b = 0; b < na; b++)
+      if (std::sqrt(norms[(size_t)a * na + b]) >= thr) sp_nz[(size_t)s.ang_sec[a] * ns + s.ang_sec[b]] = 1;
+  std::vector<int> splist;
+  for (int sp = 0; sp < ns * ns; sp++)
+    if (sp_nz[sp]) splist.push_back(sp);
+  // 2. pack the active sector pairs
+  if (!splist.empty()) {
+    CK(cudaMemcpyAsync(s.d_splist.p, splist.data(), splist.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    for (int sp : splist)
+      CK(cudaMemsetAsync(s.d_Ppix.p + (size_t)sp * s.Npix * s.NB, 0, (size_t)s.Npix * s.NB * sizeof(double), st));
+    dev::k_pack<<<dim3(t.Nrad, (unsigned)splist.size()), 256, 0, st>>>(s.bd, dP, ldP, s.d_splist.p, s.d_Ppix.p);
+    CK(cudaGetLastError());
+  }
+  CK(cudaEventRecord(s.ev[1], st));
+  // 3. task list: output pair (sj,sk) <- density pair (si,sl) with mj-mi == mk-ml, every coupled L
+  struct OpWork {
+    int op;
+    std::vector<dev::FoldTask> tasks;
+    std::vector<int> ilm;
+  };
+  std::vector<OpWork> work;
+  std::vector<int> op_src((size_t)ns * ns, -1);
+  {
+    int opcount = 0;
+    for (int sj = 0; sj < ns; sj++)
+      for (int sk = 0; sk < ns; sk++) {
+        const int mj = s.sec_m[sj], mk = s.sec_m[sk];
+        if (absm_symmetric_ && (mj < 0 || mk < 0)) continue;
+        OpWork w;
+        w.op = sj * ns + sk;
+        for (int si = 0; si < ns; si++)
+          for (int sl = 0; sl < ns; sl++) {
+            if (!sp_nz[(size_t)si * ns + sl]) continue;
+            const int mi = s.sec_m[si], ml = s.sec_m[sl];
+            if (mj - mi != mk - ml) continue;
+            const int M = mj - mi;
+            for (int L = std::abs(M); L < s.NL; L++) {
+              const int ilm = t.channel(L, std::abs(M));
+              if (ilm < 0) continue;
+              if (!s.G_nonzero[((size_t)sj * ns + si) * s.NL + L] || !s.G_nonzero[((size_t)sk * ns + sl) * s.NL + L])
+                continue;
+              dev::FoldTask ft;
+              ft.spj = sj * ns + si;
+              ft.spk = sk * ns + sl;
+              ft.spp = si * ns + sl;
+              ft.L = L;
+              ft.rslot = 0;
+              ft.pad = 0;
+              ft.fac = t.pref[ilm] * ((t.sign_by_M && (M & 1)) ? -1.0 : 1.0);
+              w.tasks.push_back(ft);
+              w.ilm.push_back(ilm);
+            }
+          }
+        if (w.tasks.empty()) continue;
+        const bool mine = (opcount % nshards) == shard;
+        opcount++;
+        if (!mine) continue;
+        op_src[w.op] = w.op;
+        work.push_back(std::move(w));
+      }
+  }
+  if (absm_symmetric_) {
+    // K(-mj,-mk) block = K(mj,mk) block (same l positions: sectors +-m hold the same l list)
+    std::map<int, int> sec_of_m;
+    for (int i = 0; i < ns; i++) sec_of_m[s.sec_m[i]] = i;
+    for (int sj = 0; sj < ns; sj++)
+      for (int sk = 0; sk < ns; sk++) {
+        const int mj = s.sec_m[sj], mk = s.sec_m[sk];
+        if (mj >= 0 || mk >= 0) continue;
+        auto pj = sec_of_m.find(-mj), pk = sec_of_m.find(-mk);
+        if (pj == sec_of_m.end() || pk == sec_of_m.end()) continue;
+        op_src[(size_t)sj * ns + sk] = op_src[(size_t)pj->second * ns + pk->second];
+      }
+  }
+  // 4. buffers
+  const size_t slot_doubles = (size_t)s.nab * s.Npix * s.NB;
+  if (s.d_Kacc.n < (size_t)ns * ns * s.op_stride) s.d_Kacc.alloc((size_t)ns * ns * s.op_stride, &dev_bytes_);
+  size_t total_tasks = 0, max_op_tasks = 0;
+  for (auto &w : work) {
+    total_tasks += w.tasks.size();
+    max_op_tasks = std::max(max_op_tasks, w.tasks.size());
+  }
+  {
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    const size_t have = s.d_R.n * sizeof(double);
+    const size_t budget = std::min<size_t>((size_t)48 << 30, (size_t)((free_b + have) * 0.6));
+    size_t want_slots = std::min<size_t>(total_tasks, std::max<size_t>(1, budget / (slot_doubles * sizeof(double))));
+    if (want_slots > s.r_slots) {
+      s.d_R.alloc(want_slots * slot_doubles, &dev_bytes_);
+      s.r_slots = want_slots;
+    }
+  }
+  if (total_tasks && s.r_slots == 0) throw std::runtime_error("Engine: no memory for the exchange work buffer");
+  // 5. batches: consecutive tasks (an output pair may span batches)
+  double fl_fold = 0, fl_tg = 0, fl_off = 0;
+  const int nruns = (int)s.run_nL.size();
+  size_t wi = 0, ti = 0;  // current op / task inside op
+  std::vector<char> op_started(work.size(), 0);
+  float ms_fold = 0, ms_tg = 0, ms_off = 0;
+  while (wi < work.size()) {
+    std::vector<dev::FoldTask> tasks;
+    std::vector<dev::GemmItem> gitems;
+    std::vector<dev::GemmEntry> gentries;
+    std::vector<dev::OffItem> oitems;
+    std::vector<dev::OffEntry> oentries;
+    while (wi < work.size() && tasks.size() < s.r_slots) {
+      OpWork &w = work[wi];
+      const size_t take = std::min(w.tasks.size() - ti, s.r_slots - tasks.size());
+      const int acc = op_started[wi] ? 1 : 0;
+      op_started[wi] = 1;
+      const size_t t0 = tasks.size();
+      for (size_t k = 0; k < take; k++) {
+        dev::FoldTask ft = w.tasks[ti + k];
+        ft.rslot = (int)(t0 + k);
+        tasks.push_back(ft);
+      }
+      double *acc_base = s.d_Kacc.p + (size_t)w.op * s.op_stride;
+      // in-element items (tensor-core GEMM against the dense exchange-ordered kernel)
+      for (int e = 0; e < t.Nel; e++) {
+        const int n = t.en[e];
+        dev::GemmItem gi{};
+        gi.C = acc_base + s.ep_off[(size_t)e * t.Nel + e];
+        gi.browoff = s.d_browoff_T.p + s.browoff_T_first[e];
+        gi.M = n * n;
+        gi.N = s.NB;
+        gi.K = s.nab * n * n;
+        gi.ent0 = (int)gentries.size();
+        for (size_t k = 0; k < take; k++) {
+          const int ilm = w.ilm[ti + k], r = s.chan_run[ilm];
+          dev::GemmEntry ge;
+          ge.A = s.d_tperm.p + s.tperm_off[(size_t)e * nruns + r] + (int64_t)s.chan_pos[ilm] * s.nab * n * n;
+          ge.lda = s.tperm_lda[(size_t)e * nruns + r];
+          ge.B = s.d_R.p + (t0 + k) * slot_doubles;
+          gentries.push_back(ge);
+        }
+        gi.ent1 = (int)gentries.size();
+        gi.accumulate = acc;
+        gi.ldb = 0;
+        gi.ldc = s.NB;
+        gi.alpha = 1.0;
+        gitems.push_back(gi);
+        fl_tg += 2.0 * gi.M * gi.N * (double)gi.K * take;
+      }
+      // cross-element items
+      const int oe0 = (int)oentries.size();
+      for (size_t k = 0; k < take; k++) oentries.push_back(dev::OffEntry{(int)(t0 + k), w.ilm[ti + k]});
+      for (int ei = 0; ei < t.Nel; ei++)
+        for (int ej = 0; ej < t.Nel; ej++) {
+          if (ei == ej) continue;
+          dev::OffItem oi{};
+          oi.C = acc_base + s.ep_off[(size_t)ei * t.Nel + ej];
+          oi.ei = ei;
+          oi.ej = ej;
+          oi.ent0 = oe0;
+          oi.ent1 = (int)oentries.size();
+          oi.accumulate = acc;
+          oitems.push_back(oi);
+          fl_off += 2.0 * t.nch * (double)s.NB * take *
+                    ((double)t.en[ei] * t.en[ej] * t.nch * t.en[ej] + (double)t.en[ei] * t.en[ej] * t.en[ei]);
+        }
+      fl_fold += 2.0 * (double)take * s.Npix * (double)s.NP * s.NP * s.NP * (t.nch + s.nab);
+      ti += take;
+      if (ti == w.tasks.size()) {
+        wi++;
+        ti = 0;
+      }
+    }
+    if (tasks.empty()) break;
+    // upload descriptors
+    auto up = [&](auto &dbuf, const auto &h) {
+      if (dbuf.n < h.size()) dbuf.alloc(h.size() * 2, &dev_bytes_);
+      if (!h.empty()) CK(cudaMemcpyAsync(dbuf.p, h.data(), h.size() * sizeof(h[0]), cudaMemcpyHostToDevice, st));
+    };
+    up(s.d_tasks, tasks);
+    up(s.d_gitems, gitems);
+    up(s.d_gentries, gentries);
+    up(s.d_oitems, oitems);
+    up(s.d_oentries, oentries);
+    CK(cudaStreamSynchronize(st));  // host vectors go out of scope below
+    CK(cudaEventRecord(s.ev[2], st));
+    launch_fold(s.NT, t.nch, s.bd, s.d_tasks.p, (int)tasks.size(), s.d_G.p, s.d_Ppix.p, s.d_R.p, st);
+    CK(cudaEventRecord(s.ev[3], st));
+    launch_gemm<false>(s.d_gitems.p, s.d_gentries.p, (int)gitems.size(), 16 * 16, s.NB, st);
+    CK(cudaEventRecord(s.ev[4], st));
+    if (!oitems.empty()) {
+      const size_t smem = (size_t)(s.nab * 2048 + t.nch * 2048 + 2 * t.nch * 256) * sizeof(double);
+      const dim3 grid(s.NB / 8, (unsigned)oitems.size());
+      if (t.nch == 1)
+        dev::k_offdiag<1><<<grid, 256, smem, st>>>(s.bd, s.d_oitems.p, s.d_oentries.p, s.d_R.p, s.d_small.p,
+                                                    s.d_big.p, s.d_blk_off.p);
+      else
+        dev::k_offdiag<2><<<grid, 256, smem, st>>>(s.bd, s.d_oitems.p, s.d_oentries.p, s.d_R.p, s.d_small.p,
+                                                    s.d_big.p, s.d_blk_off.p);
+      CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(s.ev[5], st));
+    CK(cudaStreamSynchronize(st));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, s.ev[2], s.ev[3]));
+    ms_fold += ms;
+    CK(cudaEventElapsedTime(&ms, s.ev[3], s.ev[4]));
+    ms_tg += ms;
+    CK(cudaEventElapsedTime(&ms, s.ev[4], s.ev[5]));
+    ms_off += ms;
+    tm_.launches += 2 + (oitems.empty() ? 0 : 1);
+  }
+  // 6. unpack
+  CK(cudaEventRecord(s.ev[6], st));
+  CK(cudaMemcpyAsync(s.d_op_src.p, op_src.data(), op_src.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  dev::UnpackDev u{s.d_op_src.p, s.d_ep_off.p, s.d_ang_sec.p, s.d_ang_pos.p, s.op_stride};
+  dev::k_unpack_K<<<dim3(na, na), 256, 0, st>>>(s.bd, u, s.d_Kacc.p, dK, ldK);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(s.ev[7], st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaEventElapsedTime(&tm_.pack, s.ev[0], s.ev[1]));
+  CK(cudaEventElapsedTime(&tm_.unpack, s.ev[6], s.ev[7]));
+  CK(cudaEventElapsedTime(&tm_.total, s.ev[0], s.ev[7]));
+  tm_.fold = ms_fold;
+  tm_.tgemm = ms_tg;
+  tm_.offdiag = ms_off;
+  tm_.flops_fold = fl_fold;
+  tm_.flops_tgemm = fl_tg;
+  tm_.flops_offdiag = fl_off;
+  tm_.launches += 3;
+}
+
+// ---------------------------------------------------------------------------
+// coulomb
+// ---------------------------------------------------------------------------
+void Engine::coulomb_dev(const double *dP, int64_t ldP, double *dJ, int64_t ldJ, cudaStream_t st) {
+  Impl &s = *p_;
+  const BasisTables &t = s.t;
+  CK(cudaSetDevice(device_));
+  const int na = t.Nang(), ns = s.ns, nq = s.NL * t.nch;
+  tm_ = EngineTimings();
+  CK(cudaEventRecord(s.ev[0], st));
+  dev::k_block_norms<<<dim3(na, na), 128, 0, st>>>(s.bd, dP, ldP, s.d_norms.p);
+  CK(cudaGetLastError());
+  std::vector<double> norms((size_t)na * na);
+  CK(cudaMemcpyAsync(norms.data(), s.d_norms.p, norms.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  std::vector<char> sp_nz((size_t)ns * ns, 0);
+  for (int a = 0; a < na; a++)
+    for (int b = 0; b < na; b++)
+      if (norms[(size_t)a * na + b] > 0.0) sp_nz[(size_t)s.ang_sec[a] * ns + s.ang_sec[b]] = 1;
+  std::vector<int> splist;
+  for (int sp = 0; sp < ns * ns; sp++)
+    if (sp_nz[sp]) splist.push_back(sp);
+  if (!splist.empty()) {
+    CK(cudaMemcpyAsync(s.d_splist.p, splist.data(), splist.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    for (int sp : splist)
+      CK(cudaMemsetAsync(s.d_Ppix.p + (size_t)sp * s.Npix * s.NB, 0, (size_t)s.Npix * s.NB * sizeof(double), st));
+    dev::k_pack<<<dim3(t.Nrad, (unsigned)splist.size()), 256, 0, st>>>(s.bd, dP, ldP, s.d_splist.p, s.d_Ppix.p);
+    CK(cudaGetLastError());
+  }
+  CK(cudaEventRecord(s.ev[1], st));
+  if (s.d_Paux.n == 0) {
+    s.d_Paux.alloc((size_t)s.nM * nq * s.Npix, &dev_bytes_);
+    s.d_JauxT.alloc((size_t)s.nM * nq * s.Npix, &dev_bytes_);
+    s.d_Jsec.alloc((size_t)ns * ns * s.Npix * s.NB, &dev_bytes_);
+  }
+  // fold: Paux[Mi][q][pix] = sum over sector pairs with m_a - m_b = M of G[sp][q][:] . Ppix[sp][pix][:]
+  std::vector<dev::GemmItem> items;
+  std::vector<dev::GemmEntry> entries;
+  std::vector<char> M_active(s.nM, 0);
+  for (int Mi = 0; Mi < s.nM; Mi++) {
+    const int M = Mi - (s.mmax - s.mmin);
+    dev::GemmItem gi{};
+    gi.C = s.d_Paux.p + (size_t)Mi * nq * s.Npix;
+    gi.M = nq;
+    gi.N = s.Npix;
+    gi.K = s.NB;
+    gi.ent0 = (int)entries.size();
+    for (int sp : splist) {
+      if (s.sec_m[sp / ns] - s.sec_m[sp % ns] != M) continue;
+      dev::GemmEntry ge;
+      ge.A = s.d_G.p + (size_t)sp * nq * s.NB;
+      ge.lda = s.NB;
+      ge.B = s.d_Ppix.p + (size_t)sp * s.Npix * s.NB;
+      entries.push_back(ge);
+    }
+    gi.ent1 = (int)entries.size();
+    if (gi.ent1 == gi.ent0) continue;
+    M_active[Mi] = 1;
+    gi.accumulate = 0;
+    gi.ldb = s.NB;
+    gi.ldc = s.Npix;
+    gi.alpha = 1.0;
+    items.push_back(gi);
+  }
+  auto up = [&](auto &dbuf, const auto &h) {
+    if (dbuf.n < h.size()) dbuf.alloc(h.size() * 2, &dev_bytes_);
+    if (!h.empty()) CK(cudaMemcpyAsync(dbuf.p, h.data(), h.size() * sizeof(h[0]), cudaMemcpyHostToDevice, st));
+  };
+  up(s.d_gitems, items);
+  up(s.d_gentries, entries);
+  CK(cudaStreamSynchronize(st));
+  // inactive M channels must read as zero in the radial step
+  for (int Mi = 0; Mi < s.nM; Mi++)
+    if (!M_active[Mi]) CK(cudaMemsetAsync(s.d_Paux.p + (size_t)Mi * nq * s.Npix, 0, (size_t)nq * s.Npix * sizeof(double), st));
+  launch_gemm<true>(s.d_gitems.p, s.d_gentries.p, (int)items.size(), nq, s.Npix, st);
+  CK(cudaEventRecord(s.ev[2], st));
+  // radial step
+  dev::JRadDev jr{s.d_chan_of.p, s.d_jfac.p, s.d_blk_off.p, s.d_B_off.p, s.d_sig_off.p, s.d_rank.p,
+                  s.d_small.p, s.d_big.p, s.d_B.p, s.d_sigma.p, s.nM};
+  dev::k_jradial<<<dim3(s.NL, s.nM), 256, 0, st>>>(s.bd, jr, s.d_Paux.p, s.d_JauxT.p);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(s.ev[3], st));
+  // unfold: Jsec[sp=(sj,si)][pix][j*NP+i] = sum_q JauxT[Mi][pix][q] G[sp][q][j*NP+i]
+  std::vector<dev::GemmItem> uitems;
+  std::vector<dev::GemmEntry> uentries;
+  std::vector<int> sp_active((size_t)ns * ns, 0);
+  for (int sp = 0; sp < ns * ns; sp++) {
+    const int M = s.sec_m[sp / ns] - s.sec_m[sp % ns], Mi = M + (s.mmax - s.mmin);
+    if (!M_active[Mi]) continue;
+    sp_active[sp] = 1;
+    dev::GemmItem gi{};
+    gi.C = s.d_Jsec.p + (size_t)sp * s.Npix * s.NB;
+    gi.browoff = s.d_browoff_G.p;
+    gi.M = s.Npix;
+    gi.N = s.NB;
+    gi.K = nq;
+    gi.ent0 = (int)uentries.size();
+    dev::GemmEntry ge;
+    ge.A = s.d_JauxT.p + (size_t)Mi * s.Npix * nq;
+    ge.lda = nq;
+    ge.B = s.d_G.p + (size_t)sp * nq * s.NB;
+    uentries.push_back(ge);
+    gi.ent1 = (int)uentries.size();
+    gi.accumulate = 0;
+    gi.ldc = s.NB;
+    gi.alpha = 1.0;
+    uitems.push_back(gi);
+  }
+  CK(cudaStreamSynchronize(st));  // the fold GEMM still reads the descriptor buffers
+  up(s.d_gitems, uitems);
+  up(s.d_gentries, uentries);
+  CK(cudaMemcpyAsync(s.d_sp_active.p, sp_active.data(), sp_active.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));
+  launch_gemm<false>(s.d_gitems.p, s.d_gentries.p, (int)uitems.size(), s.Npix, s.NB, st);
+  CK(cudaEventRecord(s.ev[4], st));
+  dev::k_unpack_J<<<dim3(na, na), 256, 0, st>>>(s.bd, s.d_ang_sec.p, s.d_ang_pos.p, s.d_sp_active.p, s.d_Jsec.p, dJ, ldJ);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(s.ev[5], st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaEventElapsedTime(&tm_.pack, s.ev[0], s.ev[1]));
+  CK(cudaEventElapsedTime(&tm_.fold, s.ev[1], s.ev[2]));
+  CK(cudaEventElapsedTime(&tm_.offdiag, s.ev[2], s.ev[3]));
+  CK(cudaEventElapsedTime(&tm_.tgemm, s.ev[3], s.ev[4]));
+  CK(cudaEventElapsedTime(&tm_.unpack, s.ev[4], s.ev[5]));
+  CK(cudaEventElapsedTime(&tm_.total, s.ev[0], s.ev[5]));
+  tm_.launches = 6;
+}
+
+// ---------------------------------------------------------------------------
+// host-pointer wrappers
+// ---------------------------------------------------------------------------
+void Engine::coulomb(const double *P, int64_t ldP, double *J, int64_t ldJ) {
+  Impl &s = *p_;
+  CK(cudaSetDevice(device_));
+  const size_t n = (size_t)nbf_;
+  if (s.d_P.n < n * n) s.d_P.alloc(n * n, &dev_bytes_);
+  if (s.d_O.n < n * n) s.d_O.alloc(n * n, &dev_bytes_);
+  CK(cudaMemcpy2DAsync(s.d_P.p, n * sizeof(double), P, ldP * sizeof(double), n * sizeof(double), n,
+                       cudaMemcpyHostToDevice, stream_));
+  coulomb_dev(s.d_P.p, (int64_t)n, s.d_O.p, (int64_t)n, stream_);
+  CK(cudaMemcpy2DAsync(J, ldJ * sizeof(double), s.d_O.p, n * sizeof(double), n * sizeof(double), n,
+                       cudaMemcpyDeviceToHost, stream_));
+  CK(cudaStreamSynchronize(stream_));
+}
+
+void Engine::exchange(const double *P, int64_t ldP, double *K, int64_t ldK) {
+  Impl &s = *p_;
+  CK(cudaSetDevice(device_));
+  const size_t n = (size_t)nbf_;
+  if (s.d_P.n < n * n) s.d_P.alloc(n * n, &dev_bytes_);
+  if (s.d_O.n < n * n) s.d_O.alloc(n * n, &dev_bytes_);
+  CK(cudaMemcpy2DAsync(s.d_P.p, n * sizeof(double), P, ldP * sizeof(double), n * sizeof(double), n,
+                       cudaMemcpyHostToDevice, stream_));
+  exchange_dev(s.d_P.p, (int64_t)n, s.d_O.p, (int64_t)n, 0, 1, stream_);
+  CK(cudaMemcpy2DAsync(K, ldK * sizeof(double), s.d_O.p, n * sizeof(double), n * sizeof(double), n,
+                       cudaMemcpyDeviceToHost, stream_));
+  CK(cudaStreamSynchronize(stream_));
+}
+
+}  // namespace hfq

@@ -1,0 +1,67 @@
+// J/K engine: device-resident integral caches + the CUDA Fock-build path.
+//
+// One Engine per (basis, GPU).  It owns the device copies of the integral
+// caches and coupling tables, and evaluates
+//     J = coulomb(P),  K = exchange(P)
+// for dense column-major FP64 density matrices, with the semantics of the
+// reference's TwoDBasis::coulomb / TwoDBasis::exchange
+// (src/atomic/TwoDBasis.cpp:773-999, src/diatomic/basis.cpp:1627-2089):
+// exchange() returns -K, boundary functions of m != 0 shells are removed
+// (diatomic), +-m mirroring is available through set_absm_symmetric().
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "tables.h"
+
+namespace hfq {
+
+struct EngineTimings {      // milliseconds of the last call, CUDA events
+  float pack = 0, fold = 0, tgemm = 0, offdiag = 0, unpack = 0, total = 0;
+  double flops_fold = 0, flops_tgemm = 0, flops_offdiag = 0;  // executed (padded) flops
+  double alg_flops = 0;      // algorithmic flops of the call
+  int launches = 0;
+};
+
+class Engine {
+ public:
+  Engine(const BasisTables &t, int device);
+  ~Engine();
+  Engine(const Engine &) = delete;
+  Engine &operator=(const Engine &) = delete;
+
+  int Nbf() const { return nbf_; }
+  int device() const { return device_; }
+  void set_absm_symmetric(bool s) { absm_symmetric_ = s; }
+  bool absm_symmetric() const { return absm_symmetric_; }
+
+  // Device-pointer entry points: P, J, K are Nbf x Nbf column-major on this
+  // engine's device.  shard/nshards partition the exchange output blocks over
+  // ranks (blocks owned by other shards are written as zero so that a sum
+  // over ranks gives the full matrix).
+  void coulomb_dev(const double *dP, int64_t ldP, double *dJ, int64_t ldJ, cudaStream_t stream);
+  void exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK, int shard, int nshards,
+                    cudaStream_t stream);
+  // Host-pointer entry points (copies in/out on the engine's stream).
+  void coulomb(const double *P, int64_t ldP, double *J, int64_t ldJ);
+  void exchange(const double *P, int64_t ldP, double *K, int64_t ldK);
+
+  const EngineTimings &timings() const { return tm_; }
+  cudaStream_t stream() const { return stream_; }
+  size_t device_bytes() const { return dev_bytes_; }
+
+ private:
+  struct Impl;
+  std::unique_ptr<Impl> p_;
+  int device_ = 0, nbf_ = 0;
+  bool absm_symmetric_ = false;
+  cudaStream_t stream_ = nullptr;
+  EngineTimings tm_;
+  size_t dev_bytes_ = 0;
+};
+
+}  // namespace hfq

@@ -1,0 +1,601 @@
+// CUDA kernels of the J/K engine (sm_100a).  All arithmetic is FP64; the
+// GEMM-shaped work runs on the FP64 tensor pipe (mma.sync m8n8k4 -> SASS
+// DMMA.8x8x4) with shared-memory staged operands.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace hfq {
+namespace dev {
+
+__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// ---------------------------------------------------------------------------
+// Dense <-> sector-packed layout
+//   dense:  P[(ang a, radial r), (ang b, radial c)], column-major, boundary
+//           functions of dropped shells removed (index maps ang_off/ang_skip)
+//   packed: Ppix[sp][pix = r*Nrad + c][ia][ib], sp = sector pair (sa, sb),
+//           ia/ib = position of the angular function inside its m-sector
+// ---------------------------------------------------------------------------
+
+struct BasisDev {
+  int Nang, Nrad, Npix, NP, NB, ns, nch, nab, Nel, NL;
+  const int *ang_off;    // [Nang] first dense index of angular function
+  const int *ang_skip;   // [Nang] 1 if radial function 0 is removed
+  const int *sec_n;      // [ns]
+  const int *sec_ang;    // [ns*NP] angular function index or -1
+  const int *efirst;     // [Nel]
+  const int *en;         // [Nel]
+};
+
+// sum of squares of every (ang a, ang b) block -> norms2[a*Nang+b]
+__global__ void k_block_norms(BasisDev b, const double *__restrict__ P, int64_t ld, double *__restrict__ norms2) {
+  const int a = blockIdx.x, c = blockIdx.y;
+  const int sa = b.ang_skip[a], sc = b.ang_skip[c];
+  const int na = b.Nrad - sa, nc = b.Nrad - sc;
+  const double *base = P + b.ang_off[a] + (int64_t)b.ang_off[c] * ld;
+  double s = 0.0;
+  for (int idx = threadIdx.x; idx < na * nc; idx += blockDim.x) {
+    const int i = idx % na, j = idx / na;
+    const double v = base[i + (int64_t)j * ld];
+    s += v * v;
+  }
+  __shared__ double red[32];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) norms2[a * b.Nang + c] = s;
+  }
+}
+
+// grid (Nrad [column radial c], nactive sector pairs); splist[y] = sp index
+__global__ void k_pack(BasisDev b, const double *__restrict__ P, int64_t ld, const int *__restrict__ splist,
+                       double *__restrict__ Ppix) {
+  const int c = blockIdx.x, sp = splist[blockIdx.y];
+  const int sa = sp / b.ns, sb = sp % b.ns;
+  double *dst = Ppix + (int64_t)sp * b.Npix * b.NB;
+  const int na = b.sec_n[sa], nb = b.sec_n[sb];
+  for (int ib = 0; ib < nb; ib++) {
+    const int angb = b.sec_ang[sb * b.NP + ib];
+    if (c < b.ang_skip[angb]) continue;
+    const int64_t col = b.ang_off[angb] + c - b.ang_skip[angb];
+    for (int idx = threadIdx.x; idx < na * b.Nrad; idx += blockDim.x) {
+      const int ia = idx / b.Nrad, r = idx % b.Nrad;
+      const int anga = b.sec_ang[sa * b.NP + ia];
+      if (r < b.ang_skip[anga]) continue;
+      const double v = P[b.ang_off[anga] + r - b.ang_skip[anga] + col * ld];
+      dst[((int64_t)r * b.Nrad + c) * b.NB + ia * b.NP + ib] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Exchange fold: R_ab[pix] = fac * Gj_a * P[pix] * Gk_b^T  per (task, pixel)
+// ---------------------------------------------------------------------------
+
+struct FoldTask {
+  int spj, spk, spp;   // sector pairs of the two coupling tables and of P
+  int L;               // multipole order (index into the coupling tables)
+  int rslot;           // slot in the R buffer
+  int pad;
+  double fac;          // prefactor incl. (-1)^M
+};
+
+// NT = NP/8.  Shared memory: Gj[NCH][NP][LD] Gk[NCH][NP][LD] then per pixel slot
+// P[NP][LD] Yt[NCH][NP][LD], LD = NP+4 (conflict-free DMMA fragment reads).
+template <int NT, int NCH>
+__global__ void __launch_bounds__(256)
+k_fold(BasisDev b, const FoldTask *__restrict__ tasks, const double *__restrict__ G, const double *__restrict__ Ppix,
+       double *__restrict__ R, int pix_per_cta, int PB) {
+  constexpr int NP = NT * 8, LD = NP + 4, NAB = NCH * NCH;
+  extern __shared__ double sm[];
+  const FoldTask t = tasks[blockIdx.y];
+  double *sGj = sm, *sGk = sGj + NCH * NP * LD, *sSlots = sGk + NCH * NP * LD;
+  const int slot_sz = (1 + NCH) * NP * LD;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  const int64_t gstride = (int64_t)NP * NP;
+  {
+    const double *gj = G + ((int64_t)t.spj * b.NL + t.L) * NCH * gstride;
+    const double *gk = G + ((int64_t)t.spk * b.NL + t.L) * NCH * gstride;
+    for (int idx = tid; idx < NCH * NP * NP; idx += blockDim.x) {
+      const int ch = idx / (NP * NP), rem = idx % (NP * NP), r = rem / NP, c = rem % NP;
+      sGj[(ch * NP + r) * LD + c] = gj[idx];
+      sGk[(ch * NP + r) * LD + c] = gk[idx];
+    }
+  }
+  const int pix0 = blockIdx.x * pix_per_cta;
+  const int pix1 = min(pix0 + pix_per_cta, b.Npix);
+  const double *Psrc = Ppix + (int64_t)t.spp * b.Npix * gstride;
+  double *Rdst = R + (int64_t)t.rslot * NAB * b.Npix * gstride;
+  const int lr = lane >> 2, lc = lane & 3;
+  for (int pg = pix0; pg < pix1; pg += PB) {
+    const int npx = min(PB, pix1 - pg);
+    __syncthreads();  // previous group's stage 2 is done with the slots (and G is loaded)
+    for (int idx = tid; idx < npx * NP * NP; idx += blockDim.x) {
+      const int s = idx / (NP * NP), rem = idx % (NP * NP), r = rem / NP, c = rem % NP;
+      sSlots[s * slot_sz + r * LD + c] = Psrc[(int64_t)(pg + s) * gstride + rem];
+    }
+    __syncthreads();
+    // stage 1: Yt_b[k][i] = sum_l Gk_b[k][l] P[i][l]   items: (slot, b, row tile of k)
+    for (int item = warp; item < npx * NCH * NT; item += nwarp) {
+      const int s = item / (NCH * NT), rem = item % (NCH * NT), bb = rem / NT, rt = rem % NT;
+      const double *A = sGk + (bb * NP + rt * 8 + lr) * LD + lc;
+      const double *B = sSlots + s * slot_sz + lr * LD + lc;
+      double c[NT][2];
+#pragma unroll
+      for (int n = 0; n < NT; n++) c[n][0] = c[n][1] = 0.0;
+#pragma unroll 2
+      for (int kk = 0; kk < NP; kk += 4) {
+        const double a = A[kk];
+#pragma unroll
+        for (int n = 0; n < NT; n++) dmma(c[n][0], c[n][1], a, B[n * 8 * LD + kk]);
+      }
+      double *Y = sSlots + s * slot_sz + (1 + bb) * NP * LD + (rt * 8 + lr) * LD + 2 * lc;
+#pragma unroll
+      for (int n = 0; n < NT; n++) {
+        Y[n * 8] = c[n][0];
+        Y[n * 8 + 1] = c[n][1];
+      }
+    }
+    __syncthreads();
+    // stage 2: R_ab[j][k] = fac sum_i Gj_a[j][i] Yt_b[k][i]   items: (slot, a, b, row tile of j)
+    for (int item = warp; item < npx * NAB * NT; item += nwarp) {
+      const int s = item / (NAB * NT), rem = item % (NAB * NT), ab = rem / NT, rt = rem % NT;
+      const int aa = ab / NCH, bb = ab % NCH;
+      const double *A = sGj + (aa * NP + rt * 8 + lr) * LD + lc;
+      const double *B = sSlots + s * slot_sz + (1 + bb) * NP * LD + lr * LD + lc;
+      double c[NT][2];
+#pragma unroll
+      for (int n = 0; n < NT; n++) c[n][0] = c[n][1] = 0.0;
+#pragma unroll 2
+      for (int kk = 0; kk < NP; kk += 4) {
+        const double a = A[kk];
+#pragma unroll
+        for (int n = 0; n < NT; n++) dmma(c[n][0], c[n][1], a, B[n * 8 * LD + kk]);
+      }
+      double *out = Rdst + ((int64_t)ab * b.Npix + pg + s) * gstride + (rt * 8 + lr) * NP + 2 * lc;
+#pragma unroll
+      for (int n = 0; n < NT; n++) {
+        double2 v;
+        v.x = t.fac * c[n][0];
+        v.y = t.fac * c[n][1];
+        *reinterpret_cast<double2 *>(out + n * 8) = v;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Multi-entry FP64 tensor-core GEMM:  C[M x N] (+)= alpha * sum_e A_e[M x K] B_e[K x N]
+//   A_e: row-major, row stride lda_e, K contiguous.
+//   B_e: KCONTIG = false: row k of B_e lives at B_e + browoff[k], N contiguous
+//        KCONTIG = true : B_e[n][k] row-major with stride ldb (K contiguous)
+//   C  : row-major with stride ldc
+// ---------------------------------------------------------------------------
+
+struct GemmEntry {
+  const double *A;
+  const double *B;
+  int64_t lda;
+};
+
+struct GemmItem {
+  double *C;
+  const int *browoff;  // KCONTIG=false only
+  int M, N, K;
+  int ent0, ent1;
+  int accumulate;
+  int64_t ldb;         // KCONTIG=true only
+  int64_t ldc;
+  double alpha;
+};
+
+template <int BM, int BN, int WGM, int WGN, bool KCONTIG>
+__global__ void __launch_bounds__(WGM *WGN * 32)
+k_gemm(const GemmItem *__restrict__ items, const GemmEntry *__restrict__ entries) {
+  constexpr int BK = 16, NTHR = WGM * WGN * 32;
+  constexpr int LDA_S = BK + 4;
+  constexpr int LDB_S = KCONTIG ? (BK + 4) : (BN + 4);
+  constexpr int WM = BM / WGM, WN = BN / WGN, TM = WM / 8, TN = WN / 8;
+  constexpr int A_PER = BM * BK / NTHR, B_PER = BN * BK / NTHR;
+  static_assert(BM * BK % NTHR == 0 && BN * BK % NTHR == 0, "tile/threads mismatch");
+  __shared__ double As[BM * LDA_S];
+  __shared__ double Bs[KCONTIG ? BN * LDB_S : BK * LDB_S];
+
+  const GemmItem it = items[blockIdx.z];
+  const int bm = blockIdx.y * BM, bn = blockIdx.x * BN;
+  if (bm >= it.M || bn >= it.N) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm0 = (warp / WGN) * WM, wn0 = (warp % WGN) * WN;
+  const int lr = lane >> 2, lc = lane & 3;
+
+  double acc[TM][TN][2];
+#pragma unroll
+  for (int i = 0; i < TM; i++)
+#pragma unroll
+    for (int j = 0; j < TN; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  double ra[A_PER], rb[B_PER];
+  const int nkc = (it.K + BK - 1) / BK;
+  const int nsteps = (it.ent1 - it.ent0) * nkc;
+
+  auto fetch = [&](int step) {
+    const GemmEntry e = entries[it.ent0 + step / nkc];
+    const int kc = (step % nkc) * BK;
+#pragma unroll
+    for (int u = 0; u < A_PER; u++) {
+      const int idx = tid + u * NTHR, m = idx / BK, k = idx % BK;
+      ra[u] = (bm + m < it.M && kc + k < it.K) ? __ldg(e.A + (int64_t)(bm + m) * e.lda + kc + k) : 0.0;
+    }
+    if (KCONTIG) {
+#pragma unroll
+      for (int u = 0; u < B_PER; u++) {
+        const int idx = tid + u * NTHR, n = idx / BK, k = idx % BK;
+        rb[u] = (bn + n < it.N && kc + k < it.K) ? __ldg(e.B + (int64_t)(bn + n) * it.ldb + kc + k) : 0.0;
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < B_PER; u++) {
+        const int idx = tid + u * NTHR, k = idx / BN, n = idx % BN;
+        rb[u] = (bn + n < it.N && kc + k < it.K) ? __ldg(e.B + it.browoff[kc + k] + bn + n) : 0.0;
+      }
+    }
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int u = 0; u < A_PER; u++) {
+      const int idx = tid + u * NTHR, m = idx / BK, k = idx % BK;
+      As[m * LDA_S + k] = ra[u];
+    }
+    if (KCONTIG) {
+#pragma unroll
+      for (int u = 0; u < B_PER; u++) {
+        const int idx = tid + u * NTHR, n = idx / BK, k = idx % BK;
+        Bs[n * LDB_S + k] = rb[u];
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < B_PER; u++) {
+        const int idx = tid + u * NTHR, k = idx / BN, n = idx % BN;
+        Bs[k * LDB_S + n] = rb[u];
+      }
+    }
+  };
+
+  if (nsteps > 0) fetch(0);
+  for (int step = 0; step < nsteps; step++) {
+    __syncthreads();
+    stash();
+    __syncthreads();
+    if (step + 1 < nsteps) fetch(step + 1);
+#pragma unroll
+    for (int kk = 0; kk < BK; kk += 4) {
+      double af[TM], bf[TN];
+#pragma unroll
+      for (int i = 0; i < TM; i++) af[i] = As[(wm0 + i * 8 + lr) * LDA_S + kk + lc];
+#pragma unroll
+      for (int j = 0; j < TN; j++)
+        bf[j] = KCONTIG ? Bs[(wn0 + j * 8 + lr) * LDB_S + kk + lc] : Bs[(kk + lc) * LDB_S + wn0 + j * 8 + lr];
+#pragma unroll
+      for (int i = 0; i < TM; i++)
+#pragma unroll
+        for (int j = 0; j < TN; j++) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < TM; i++) {
+    const int m = bm + wm0 + i * 8 + lr;
+    if (m >= it.M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; j++) {
+      const int n = bn + wn0 + j * 8 + 2 * lc;
+      double *c = it.C + (int64_t)m * it.ldc + n;
+      if (n < it.N) c[0] = it.alpha * acc[i][j][0] + (it.accumulate ? c[0] : 0.0);
+      if (n + 1 < it.N) c[1] = it.alpha * acc[i][j][1] + (it.accumulate ? c[1] : 0.0);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Setup: dense exchange-ordered in-element kernel from the low-rank factor
+//   T[(rj*n + rk)][ab][(ri*n + rl)] = s_ab sum_p sigma_p B[a*nn + pair1, p] B[b*nn + rk + rl*n, p]
+//   pair1 = out_fast ? rj + ri*n : ri + rj*n
+// grid (n*n rows), dst row stride = ldT
+// ---------------------------------------------------------------------------
+__global__ void k_build_tperm(const double *__restrict__ B, const double *__restrict__ sigma, int n, int rank, int nch,
+                              int out_fast, double *__restrict__ dst, int64_t ldT) {
+  const int row = blockIdx.x, rj = row / n, rk = row % n, nn = n * n;
+  for (int col = threadIdx.x; col < nch * nch * nn; col += blockDim.x) {
+    const int ab = col / nn, il = col % nn, a = ab / nch, bb = ab % nch, ri = il / n, rl = il % n;
+    const int p1 = out_fast ? (rj + ri * n) : (ri + rj * n);
+    const double *b1 = B + a * nn + p1, *b2 = B + bb * nn + rk + rl * n;
+    const int64_t ldB = (int64_t)nch * nn;
+    double s = 0.0;
+    for (int p = 0; p < rank; p++) s += sigma[p] * b1[p * ldB] * b2[p * ldB];
+    const double sgn = (nch == 2 && a != bb) ? -1.0 : 1.0;
+    dst[(int64_t)row * ldT + col] = sgn * s;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Exchange, cross-element pairs:  K_(ei,ej)(rj,rk) += sum_ab sum_(ri,rl) I_a(rj,ri) R_ab(ri,rl) J_b(rk,rl)
+// One CTA = (item = output pair x element pair, tile of BT = 8 blk columns).
+// ---------------------------------------------------------------------------
+struct OffItem {
+  double *C;        // [Ni*Nj][NB]
+  int ei, ej;
+  int ent0, ent1;   // entries: (R slot, channel)
+  int accumulate;
+  int pad;
+};
+struct OffEntry {
+  int rslot, ilm;
+};
+
+template <int NCH>
+__global__ void __launch_bounds__(256)
+k_offdiag(BasisDev b, const OffItem *__restrict__ items, const OffEntry *__restrict__ entries,
+          const double *__restrict__ R, const double *__restrict__ dsmall, const double *__restrict__ dbig,
+          const int64_t *__restrict__ blk_off /* [nlm*Nel] offset of channel block in dsmall/dbig */) {
+  constexpr int BT = 8, NAB = NCH * NCH, MAXN = 16;
+  extern __shared__ double sm[];
+  const OffItem it = items[blockIdx.y];
+  const int Ni = b.en[it.ei], Nj = b.en[it.ej], fi = b.efirst[it.ei], fj = b.efirst[it.ej];
+  const int blk0 = blockIdx.x * BT;
+  double *sR = sm;                               // [NAB][Ni*Nj][BT]
+  double *sU = sR + NAB * MAXN * MAXN * BT;      // [NCH][Ni][Nj][BT]
+  double *sI = sU + NCH * MAXN * MAXN * BT;      // [NCH][Ni(rj)][Ni(ri)]  row-major in rj
+  double *sJ = sI + NCH * MAXN * MAXN;           // [NCH][Nj(rl)][Nj(rk)]  (transposed: rk fastest)
+  const int tid = threadIdx.x;
+  const int64_t gstride = (int64_t)b.NB;
+  // stage-2 ownership: thread -> (half a, rk, blk), accumulates all rj
+  const int t_blk = tid % BT, t_rk = (tid / BT) % MAXN, t_a = tid / (BT * MAXN);
+  double acc[MAXN];
+#pragma unroll
+  for (int q = 0; q < MAXN; q++) acc[q] = 0.0;
+
+  for (int e = it.ent0; e < it.ent1; e++) {
+    const OffEntry en = entries[e];
+    const double *Rt = R + (int64_t)en.rslot * NAB * b.Npix * gstride;
+    // I = factor on the output-row element, J = factor on the output-column element
+    const double *srcI = (it.ei > it.ej ? dbig : dsmall) + blk_off[en.ilm * b.Nel + it.ei];
+    const double *srcJ = (it.ei > it.ej ? dsmall : dbig) + blk_off[en.ilm * b.Nel + it.ej];
+    __syncthreads();
+    for (int idx = tid; idx < NCH * Ni * Ni; idx += blockDim.x) {
+      const int ch = idx / (Ni * Ni), rem = idx % (Ni * Ni), ri = rem / Ni, rj = rem % Ni;  // column-major source
+      sI[(ch * MAXN + rj) * MAXN + ri] = srcI[idx];
+    }
+    for (int idx = tid; idx < NCH * Nj * Nj; idx += blockDim.x) {
+      const int ch = idx / (Nj * Nj), rem = idx % (Nj * Nj), rl = rem / Nj, rk = rem % Nj;  // J(rk,rl) column-major
+      sJ[(ch * MAXN + rl) * MAXN + rk] = srcJ[idx];
+    }
+    for (int idx = tid; idx < NAB * Ni * Nj * BT; idx += blockDim.x) {
+      const int bt = idx % BT, rem = idx / BT, rl = rem % Nj, rem2 = rem / Nj, ri = rem2 % Ni, ab = rem2 / Ni;
+      const int pix = (fi + ri) * b.Nrad + fj + rl;
+      sR[((ab * MAXN + ri) * MAXN + rl) * BT + bt] = Rt[((int64_t)ab * b.Npix + pix) * gstride + blk0 + bt];
+    }
+    __syncthreads();
+    // stage 1: U_a[ri][rk][blk] = sum_b sum_rl R_ab[ri][rl][blk] J_b[rk][rl]; thread -> (a, ri, blk), all rk
+    {
+      const int s_blk = tid % BT, s_ri = (tid / BT) % MAXN, s_a = tid / (BT * MAXN);
+      if (s_a < NCH && s_ri < Ni) {
+        double u[MAXN];
+#pragma unroll
+        for (int q = 0; q < MAXN; q++) u[q] = 0.0;
+        for (int bb = 0; bb < NCH; bb++)
+          for (int rl = 0; rl < Nj; rl++) {
+            const double r = sR[(((s_a * NCH + bb) * MAXN + s_ri) * MAXN + rl) * BT + s_blk];
+            const double *jrow = sJ + (bb * MAXN + rl) * MAXN;
+#pragma unroll
+            for (int q = 0; q < MAXN; q++) u[q] += r * jrow[q];
+          }
+#pragma unroll
+        for (int q = 0; q < MAXN; q++) sU[((s_a * MAXN + s_ri) * MAXN + q) * BT + s_blk] = u[q];
+      }
+    }
+    __syncthreads();
+    // stage 2: acc[rj] += sum_ri I_a[rj][ri] U_a[ri][rk][blk]
+    if (t_a < NCH && t_rk < Nj) {
+      for (int ri = 0; ri < Ni; ri++) {
+        const double u = sU[((t_a * MAXN + ri) * MAXN + t_rk) * BT + t_blk];
+#pragma unroll
+        for (int q = 0; q < MAXN; q++) acc[q] += sI[(t_a * MAXN + q) * MAXN + ri] * u;
+      }
+    }
+  }
+  // combine the NCH halves through shared memory and write
+  __syncthreads();
+  double *sC = sm;  // reuse: [NCH][MAXN rj][MAXN rk][BT]
+  if (t_a < NCH) {
+#pragma unroll
+    for (int q = 0; q < MAXN; q++) sC[((t_a * MAXN + q) * MAXN + t_rk) * BT + t_blk] = acc[q];
+  }
+  __syncthreads();
+  for (int idx = tid; idx < Ni * Nj * BT; idx += blockDim.x) {
+    const int bt = idx % BT, rem = idx / BT, rk = rem % Nj, rj = rem / Nj;
+    double s = 0.0;
+    for (int a = 0; a < NCH; a++) s += sC[((a * MAXN + rj) * MAXN + rk) * BT + bt];
+    double *c = it.C + (int64_t)(rj * Nj + rk) * gstride + blk0 + bt;
+    *c = s + (it.accumulate ? *c : 0.0);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Exchange unpack: dense K = - sum over element-pair blocks, boundary removal,
+// optional +-m mirror (mirror_op maps an output sector pair to the pair that
+// was actually computed).
+// grid (dense column tiles), one thread per dense element
+// ---------------------------------------------------------------------------
+struct UnpackDev {
+  const int *op_src;      // [ns*ns] sector pair whose accumulator holds this block (or -1: zero)
+  const int64_t *ep_off;  // [Nel*Nel] offset of element-pair block inside one output pair's accumulator
+  const int *ang_sec;     // [Nang] sector of angular function
+  const int *ang_pos;     // [Nang] position inside the sector
+  int64_t op_stride;      // accumulator stride per output pair
+};
+
+__global__ void k_unpack_K(BasisDev b, UnpackDev u, const double *__restrict__ Kacc, double *__restrict__ K, int64_t ld) {
+  const int angk = blockIdx.y, angj = blockIdx.x;
+  const int sj = b.ang_skip[angj], sk = b.ang_skip[angk];
+  const int nj = b.Nrad - sj, nk = b.Nrad - sk;
+  double *dst = K + b.ang_off[angj] + (int64_t)b.ang_off[angk] * ld;
+  const int op = u.ang_sec[angj] * b.ns + u.ang_sec[angk];
+  const int src = u.op_src[op];
+  const int blk = u.ang_pos[angj] * b.NP + u.ang_pos[angk];
+  for (int idx = threadIdx.x; idx < nj * nk; idx += blockDim.x) {
+    const int r = idx % nj + sj, c = idx / nj + sk;
+    double s = 0.0;
+    if (src >= 0) {
+      const double *acc = Kacc + (int64_t)src * u.op_stride;
+      for (int ei = 0; ei < b.Nel; ei++) {
+        const int ri = r - b.efirst[ei];
+        if (ri < 0 || ri >= b.en[ei]) continue;
+        for (int ej = 0; ej < b.Nel; ej++) {
+          const int rk = c - b.efirst[ej];
+          if (rk < 0 || rk >= b.en[ej]) continue;
+          s += acc[u.ep_off[ei * b.Nel + ej] + (int64_t)(ri * b.en[ej] + rk) * b.NB + blk];
+        }
+      }
+    }
+    dst[(r - sj) + (int64_t)(c - sk) * ld] = -s;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Coulomb: radial step per (L, M) channel.
+//   in : Paux[Midx][q = L*nch + ch][pix]      (fold output)
+//   out: JauxT[Midx][pix][q]
+// One CTA per (L, Midx).
+// ---------------------------------------------------------------------------
+struct JRadDev {
+  const int *chan_of;        // [NL * nM] channel index (ilm) or -1
+  const double *fac;         // [NL * nM] prefactor incl. sign
+  const int64_t *blk_off;    // [nlm*Nel] offsets into dsmall/dbig
+  const int64_t *B_off;      // [nlm*Nel] offsets into dB
+  const int64_t *sig_off;    // [nlm*Nel] offsets into dsigma
+  const int *rank;           // [nlm*Nel]
+  const double *dsmall, *dbig, *dB, *dsigma;
+  int nM;
+};
+
+__global__ void __launch_bounds__(256)
+k_jradial(BasisDev b, JRadDev jr, const double *__restrict__ Paux, double *__restrict__ JauxT) {
+  const int L = blockIdx.x, Mi = blockIdx.y, tid = threadIdx.x;
+  const int nq = b.NL * b.nch;
+  const int ilm = jr.chan_of[L * jr.nM + Mi];
+  double *out = JauxT + (int64_t)Mi * b.Npix * nq;
+  for (int ch = 0; ch < b.nch; ch++)
+    for (int pix = tid; pix < b.Npix; pix += blockDim.x) out[(int64_t)pix * nq + L * b.nch + ch] = 0.0;
+  if (ilm < 0) return;
+  const double fac = jr.fac[L * jr.nM + Mi];
+  const double *pin = Paux + ((int64_t)Mi * nq + L * b.nch) * b.Npix;  // [ch][pix]
+  __shared__ double s_js[64], s_jb[64], s_c[128], red[2][8];
+  __shared__ double s_pre[64], s_post[64];
+  const int Nel = b.Nel;
+  // traces with the cross-element factors
+  for (int e = 0; e < Nel; e++) {
+    const int n = b.en[e], f = b.efirst[e];
+    const double *sm = jr.dsmall + jr.blk_off[ilm * Nel + e];
+    const double *bg = jr.dbig + jr.blk_off[ilm * Nel + e];
+    double ts = 0.0, tb = 0.0;
+    for (int idx = tid; idx < b.nch * n * n; idx += blockDim.x) {
+      const int ch = idx / (n * n), rem = idx % (n * n), bcol = rem / n, a = rem % n;  // small(a,bcol)
+      const double p = pin[(int64_t)ch * b.Npix + (f + bcol) * b.Nrad + f + a];       // Psub(bcol,a)
+      ts += sm[idx] * p;
+      if (e > 0) tb += bg[idx] * p;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      ts += __shfl_down_sync(0xffffffffu, ts, o);
+      tb += __shfl_down_sync(0xffffffffu, tb, o);
+    }
+    if ((tid & 31) == 0) {
+      red[0][tid >> 5] = ts;
+      red[1][tid >> 5] = tb;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double a = 0, c = 0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); w++) {
+        a += red[0][w];
+        c += red[1][w];
+      }
+      s_js[e] = fac * a;
+      s_jb[e] = fac * c;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    // element e receives  (sum of big traces of outer elements) * small_e
+    //                   + (sum of small traces of inner elements) * big_e
+    double run = 0.0;
+    for (int e = 0; e < Nel; e++) {
+      s_pre[e] = run;
+      run += s_js[e];
+    }
+    run = 0.0;
+    for (int e = Nel - 1; e >= 0; e--) {
+      s_post[e] = run;
+      run += s_jb[e];
+    }
+  }
+  __syncthreads();
+  for (int e = 0; e < Nel; e++) {
+    const int n = b.en[e], f = b.efirst[e], nn = n * n;
+    const double *sm = jr.dsmall + jr.blk_off[ilm * Nel + e];
+    const double *bg = jr.dbig + jr.blk_off[ilm * Nel + e];
+    const double *Bf = jr.dB + jr.B_off[ilm * Nel + e];
+    const double *sg = jr.dsigma + jr.sig_off[ilm * Nel + e];
+    const int rank = jr.rank[ilm * Nel + e];
+    const int ldB = b.nch * nn;
+    // c_p = sigma_p sum_ch s_ch sum_ab B[ch*nn+ab,p] Psub_ch(a,b)
+    for (int p = tid >> 5; p < rank; p += blockDim.x >> 5) {
+      double s = 0.0;
+      for (int idx = tid & 31; idx < ldB; idx += 32) {
+        const int ch = idx / nn, ab = idx % nn, a = ab % n, bcol = ab / n;
+        const double sgn = (b.nch == 2 && ch == 1) ? -1.0 : 1.0;
+        s += sgn * Bf[(int64_t)p * ldB + idx] * pin[(int64_t)ch * b.Npix + (f + a) * b.Nrad + f + bcol];
+      }
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+      if ((tid & 31) == 0) s_c[p] = sg[p] * s;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < ldB; idx += blockDim.x) {
+      const int ch = idx / nn, ab = idx % nn, a = ab % n, bcol = ab / n;
+      const double sgn = (b.nch == 2 && ch == 1) ? -1.0 : 1.0;
+      double s = 0.0;
+      for (int p = 0; p < rank; p++) s += Bf[(int64_t)p * ldB + idx] * s_c[p];
+      double v = fac * sgn * s + s_post[e] * sm[idx];
+      if (e > 0) v += s_pre[e] * bg[idx];
+      out[(int64_t)((f + a) * b.Nrad + f + bcol) * nq + L * b.nch + ch] += v;
+    }
+    __syncthreads();
+  }
+}
+
+// Coulomb unpack: dense J[(ang i, r), (ang j, c)] = Jsec[sp=(sj,si)][pix=(r,c)][pos_j*NP + pos_i]
+__global__ void k_unpack_J(BasisDev b, const int *__restrict__ ang_sec, const int *__restrict__ ang_pos,
+                           const int *__restrict__ sp_active, const double *__restrict__ Jsec, double *__restrict__ J,
+                           int64_t ld) {
+  const int angi = blockIdx.x, angj = blockIdx.y;
+  const int si = b.ang_skip[angi], sj = b.ang_skip[angj];
+  const int ni = b.Nrad - si, nj = b.Nrad - sj;
+  double *dst = J + b.ang_off[angi] + (int64_t)b.ang_off[angj] * ld;
+  const int sp = ang_sec[angj] * b.ns + ang_sec[angi];
+  const bool act = sp_active[sp] != 0;
+  const double *src = Jsec + (int64_t)sp * b.Npix * b.NB + ang_pos[angj] * b.NP + ang_pos[angi];
+  for (int idx = threadIdx.x; idx < ni * nj; idx += blockDim.x) {
+    const int r = idx % ni + si, c = idx / ni + sj;
+    dst[(r - si) + (int64_t)(c - sj) * ld] = act ? src[(int64_t)(r * b.Nrad + c) * b.NB] : 0.0;
+  }
+}
+
+}  // namespace dev
+}  // namespace hfq

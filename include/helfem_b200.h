@@ -1,0 +1,129 @@
+/* libhelfemqc_b200 -- C ABI of the B200-native SCF Fock-build path (J, K).
+ *
+ * Drop-in boundary for the reference's (susilehtola/HelFEM) hot path.  The
+ * reference has no C ABI of its own; each entry point below names the C++
+ * member it replaces.  All matrices are dense FP64, column-major, caller
+ * owned, with explicit leading dimensions.  Every function returns 0 on
+ * success and a negative code on error; the message of the last error of the
+ * calling thread is available from hfq_last_error().
+ *
+ * Two object kinds:
+ *   hfq_tables  host-side basis description + integral caches
+ *               (what TwoDBasis' constructor and compute_tei() produce)
+ *   hfq_ctx     one basis bound to one GPU: device-resident caches and the
+ *               CUDA kernels behind coulomb() / exchange()
+ * There is no CPU fallback: hfq_create fails if no CUDA device is usable.
+ */
+#ifndef HELFEM_B200_H
+#define HELFEM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hfq_tables hfq_tables;
+typedef struct hfq_ctx hfq_ctx;
+
+#define HFQ_OK 0
+#define HFQ_ERR_INVALID (-1)  /* bad argument / size mismatch (reference: std::logic_error)   */
+#define HFQ_ERR_STATE (-2)    /* called before the integrals exist ("Primitive teis have not
+                                 been computed!", src/atomic/TwoDBasis.cpp:775)              */
+#define HFQ_ERR_CUDA (-3)     /* CUDA runtime failure                                         */
+#define HFQ_ERR_INTERNAL (-4)
+
+const char *hfq_last_error(void);
+
+/* ---- basis construction + compute_tei() ------------------------------------------------- */
+
+/* Atomic basis: TwoDBasisT<double> ctor + compute_tei()
+ * (src/atomic/TwoDBasis.cpp:66-94, :708-735; flags src/atomic/main.cpp:53-129).
+ * LIP primitive basis (primbas=4), point nucleus.  nquad = 0 -> 5*nnodes. */
+int hfq_tables_atomic(hfq_tables **out, int Z, int lmax, int mmax, int nelem, int nnodes, double Rmax, int igrid,
+                      double zexp, int nquad);
+
+/* Diatomic basis: diatomic::basis::TwoDBasis ctor + compute_tei()
+ * (src/diatomic/basis.cpp:525-647, :1382-1547; flags src/diatomic/main.cpp:60-118).
+ * lmax_per_m[|m|], |m| = 0..nm-1, is the --lmax list. */
+int hfq_tables_diatomic(hfq_tables **out, int Z1, int Z2, double Rbond, const int *lmax_per_m, int nm, int nelem,
+                        int nnodes, double Rmax, int igrid, double zexp, int nquad);
+
+/* Caller-supplied caches: lets an existing HelFEM build hand over the caches its own
+ * compute_tei() produced (disjoint_L/disjoint_m1L/prim_chol, src/atomic/TwoDBasis.h:83-128;
+ * disjoint_P0/P2/Q0/Q2, cd_B, cd_sigma, src/diatomic/basis.h:151-188).
+ * Block (ilm, iel), flat index ilm*Nel+iel:
+ *   small/big: nch matrices n x n column-major, concatenated (big may be all zero on element 0)
+ *   B: (nch*n*n) x rank column-major; sigma: rank entries (+-1)
+ * The per-block arrays are concatenated in flat-index order. */
+typedef struct hfq_tables_desc {
+  int kind;               /* 0 atomic, 1 diatomic */
+  int nch;                /* 1 atomic, 2 diatomic */
+  int Nrad, Nel, Nang, nlm;
+  const int *efirst;      /* [Nel] first radial function of element */
+  const int *en;          /* [Nel] functions in element */
+  const int *lval;        /* [Nang] */
+  const int *mval;        /* [Nang] */
+  const int *lmL;         /* [nlm] multipole L of channel */
+  const int *lmM;         /* [nlm] |M| of channel, -1 = any (atomic) */
+  const double *pref;     /* [nlm] |prefactor| */
+  const int *rank;        /* [nlm*Nel] */
+  const double *small_;   /* concatenated */
+  const double *big_;     /* concatenated */
+  const double *B;        /* concatenated */
+  const double *sigma;    /* concatenated */
+  double Rhalf;
+} hfq_tables_desc;
+int hfq_tables_from_arrays(hfq_tables **out, const hfq_tables_desc *desc);
+
+typedef struct hfq_tables_info {
+  int kind, nch, Nrad, Nel, Nang, nlm, Nbf, Ndummy;
+} hfq_tables_info;
+int hfq_tables_get_info(const hfq_tables *t, hfq_tables_info *info);
+/* what: 0 lval, 1 mval, 2 efirst, 3 en, 4 lmL, 5 lmM, 6 rank[nlm*Nel] */
+int hfq_tables_get_ints(const hfq_tables *t, int what, int *out, int64_t cap);
+/* what: 0 pref[nlm], 1 bval[Nel+1] */
+int hfq_tables_get_doubles(const hfq_tables *t, int what, double *out, int64_t cap);
+/* copy one cache block out (any pointer may be NULL) */
+int hfq_tables_get_block(const hfq_tables *t, int ilm, int iel, double *small_, double *big_, double *B,
+                         double *sigma);
+/* overlap / kinetic / nuclear attraction, Nbf x Nbf column-major (setup helpers,
+ * src/atomic/TwoDBasis.cpp:320-375, src/diatomic/basis.cpp:1032-1166) */
+int hfq_tables_one_electron(const hfq_tables *t, double *S, double *T, double *V);
+void hfq_tables_destroy(hfq_tables *t);
+
+/* ---- the Fock-build path ------------------------------------------------------------------- */
+
+/* Bind a basis to CUDA device `device`, upload the caches. */
+int hfq_create(hfq_ctx **out, const hfq_tables *t, int device);
+void hfq_destroy(hfq_ctx *ctx);
+int hfq_nbf(const hfq_ctx *ctx);
+
+/* diatomic::basis::TwoDBasis::set_absm_symmetric (src/diatomic/basis.cpp:913-915) */
+int hfq_set_absm_symmetric(hfq_ctx *ctx, int flag);
+
+/* J = coulomb(P): atomic src/atomic/TwoDBasis.cpp:773-877, diatomic src/diatomic/basis.cpp:1627-1816.
+ * Host buffers; copies are part of the call. */
+int hfq_coulomb(hfq_ctx *ctx, const double *P, int64_t ldP, double *J, int64_t ldJ);
+/* K = exchange(P) with the reference's sign (returns -K, added to the Fock matrix):
+ * atomic src/atomic/TwoDBasis.cpp:879-999, diatomic src/diatomic/basis.cpp:1818-2089. */
+int hfq_exchange(hfq_ctx *ctx, const double *P, int64_t ldP, double *K, int64_t ldK);
+
+/* Same with device-resident matrices on the context's GPU; `stream` is a cudaStream_t
+ * (NULL = the context's own stream).  The call returns after the work is complete.
+ * shard/nshards split the exchange output blocks across ranks: blocks owned by other
+ * shards are written as zero, so an all-reduce(sum) over ranks yields the full matrix. */
+int hfq_coulomb_device(hfq_ctx *ctx, const double *dP, int64_t ldP, double *dJ, int64_t ldJ, void *stream);
+int hfq_exchange_device(hfq_ctx *ctx, const double *dP, int64_t ldP, double *dK, int64_t ldK, int shard,
+                        int nshards, void *stream);
+
+/* Timings / work counters of the last call on this context:
+ * out[0..5] = ms {pack, fold, in-element GEMM, cross-element, unpack, total},
+ * out[6..8] = executed flops {fold, in-element GEMM, cross-element}, out[9] = kernel launches,
+ * out[10] = device bytes held by the context. */
+int hfq_last_timings(const hfq_ctx *ctx, double *out, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HELFEM_B200_H */

@@ -1,0 +1,138 @@
+"""GPU parity: the CUDA J/K path (through the C ABI) against the CPU oracle.
+
+Tolerance: 1e-12 relative Frobenius (BASELINE.json north_star); energies 1e-10 Eh.
+"""
+import numpy as np
+import pytest
+
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def _check_jk(basis, ob, P, tol=TOL):
+    J = basis.coulomb(P)
+    K = basis.exchange(P)
+    Jo = ob.coulomb(P)
+    Ko = ob.exchange(P)
+    ej, ek = cases.relerr(J, Jo), cases.relerr(K, Ko)
+    assert ej < tol, "J relative error %.3e" % ej
+    assert ek < tol, "K relative error %.3e" % ek
+    return J, K
+
+
+@pytest.mark.parametrize("lmax,mmax,nelem", [(0, 0, 5), (1, 1, 3), (2, 2, 2), (2, 1, 3)])
+def test_atomic_oracle_caches(hb, lmax, mmax, nelem):
+    """Identical caches (the oracle's) on both sides: pure kernel parity."""
+    ob = cases.oracle_atomic(4, lmax, mmax, nelem)
+    basis = hb.TablesBasis(cases.tables_from_oracle_atomic(hb, ob))
+    n = ob.Nbf()
+    # m-block-diagonal density (typical SCF) and a fully dense random one
+    P1 = cases.random_density(n, 3, 11, cases.m_blocks(ob.mval, ob.Nrad(), False))
+    _check_jk(basis, ob, P1)
+    P2 = cases.random_density(n, 5, 12)
+    _check_jk(basis, ob, P2)
+
+
+@pytest.mark.parametrize("lmax,mmax,nelem", [(0, 0, 5), (2, 2, 2)])
+def test_atomic_own_setup(hb, lmax, mmax, nelem):
+    """Product's own compute_tei + kernels against the oracle end to end."""
+    ob = cases.oracle_atomic(4, lmax, mmax, nelem)
+    basis = hb.AtomicTwoDBasis(4, lmax, mmax, nelem).compute_tei()
+    P = cases.random_density(ob.Nbf(), 4, 5, cases.m_blocks(ob.mval, ob.Nrad(), False))
+    _check_jk(basis, ob, P)
+
+
+@pytest.mark.parametrize("lmax_per_m,nelem", [((2,), 2), ((3, 2), 2), ((2, 2, 2), 2), ((4,), 3)])
+def test_diatomic_oracle_caches(hb, lmax_per_m, nelem):
+    ob = cases.oracle_diatomic(3, 1, 1.8, lmax_per_m, nelem)
+    basis = hb.TablesBasis(cases.tables_from_oracle_diatomic(hb, ob))
+    n = ob.Nbf()
+    P1 = cases.random_density(n, 3, 21, cases.m_blocks(ob.mval, ob.Nrad(), True))
+    _check_jk(basis, ob, P1)
+    P2 = cases.random_density(n, 4, 22)
+    _check_jk(basis, ob, P2)
+
+
+def test_diatomic_own_setup(hb):
+    ob = cases.oracle_diatomic(7, 7, 2.07, (3, 2), 2)
+    basis = hb.DiatomicTwoDBasis(7, 7, 2.07, [3, 2], 2).compute_tei()
+    P = cases.random_density(ob.Nbf(), 3, 31, cases.m_blocks(ob.mval, ob.Nrad(), True))
+    _check_jk(basis, ob, P)
+
+
+def test_diatomic_absm_symmetric(hb):
+    """+-m mirrored build (src/diatomic/basis.cpp:1886-1891,2067-2086) == full build for a
+    +-m symmetric density, and == the oracle's mirrored build."""
+    ob = cases.oracle_diatomic(7, 7, 2.07, (3, 3, 2), 2)
+    n = ob.Nbf()
+    blocks = cases.m_blocks(ob.mval, ob.Nrad(), True)
+    ms = sorted(set(int(m) for m in ob.mval))
+    rng = np.random.default_rng(3)
+    P = np.zeros((n, n))
+    for mabs in range(max(ms) + 1):
+        bp = blocks[ms.index(mabs)]
+        Q, _ = np.linalg.qr(rng.standard_normal((len(bp), 2)))
+        blk = 2.0 * Q @ Q.T
+        P[np.ix_(bp, bp)] = blk
+        if mabs > 0:
+            bm = blocks[ms.index(-mabs)]
+            P[np.ix_(bm, bm)] = blk
+    basis = hb.TablesBasis(cases.tables_from_oracle_diatomic(hb, ob))
+    Kfull = basis.exchange(P)
+    basis.set_absm_symmetric(True)
+    Ksym = basis.exchange(P)
+    assert cases.relerr(Ksym, Kfull) < TOL
+    ob.absm_symmetric = True
+    try:
+        Ko = ob.exchange(P)
+    finally:
+        ob.absm_symmetric = False
+    assert cases.relerr(Ksym, Ko) < TOL
+
+
+def test_linearity_and_symmetry(hb):
+    """Size-independent properties: J,K linear in P; symmetric P -> symmetric J,K."""
+    basis = hb.DiatomicTwoDBasis(7, 7, 2.07, [5, 4, 3], 3).compute_tei()
+    n = basis.Nbf()
+    t = basis.tables
+    blocks = cases.m_blocks(t.mval, t.Nrad, True)
+    Pa = cases.random_density(n, 3, 1, blocks)
+    Pb = cases.random_density(n, 2, 2, blocks)
+    Ka, Kb, Kab = basis.exchange(Pa), basis.exchange(Pb), basis.exchange(Pa + 0.5 * Pb)
+    assert cases.relerr(Kab, Ka + 0.5 * Kb) < TOL
+    Ja, Jb, Jab = basis.coulomb(Pa), basis.coulomb(Pb), basis.coulomb(Pa + 0.5 * Pb)
+    assert cases.relerr(Jab, Ja + 0.5 * Jb) < TOL
+    assert cases.relerr(Ka, Ka.T) < TOL and cases.relerr(Ja, Ja.T) < TOL
+    # zero density -> zero matrices (empty screening lists)
+    Z = np.zeros((n, n))
+    assert np.all(basis.exchange(Z) == 0.0) and np.all(basis.coulomb(Z) == 0.0)
+
+
+def test_he_scf_energy_on_gpu(hb):
+    """He RHF through the GPU J/K: total -2.8616799956 Eh (tests/refs/ci.json atomic-He-hf-r)."""
+    from oracle import scf
+    basis = hb.AtomicTwoDBasis(2, 0, 0, 5).compute_tei()
+    S, T, V = basis.tables.one_electron()
+    r = scf.rhf(S, T + V, basis.coulomb, basis.exchange, [1], [np.arange(basis.Nbf())])
+    assert abs(r["E"] - (-2.8616799956)) < 1e-9
+    assert abs(r["Coulomb"] - 2.0515380305) < 2e-6 and abs(r["Exx"] - (-1.0257690153)) < 2e-6
+
+
+def test_h2_scf_energy_on_gpu(hb):
+    """H2 RHF (diatomic-H2-hf-r): total -1.1336295702 Eh."""
+    from oracle import scf
+    basis = hb.DiatomicTwoDBasis(1, 1, 1.4, [4], 3).compute_tei()
+    S, T, V = basis.tables.one_electron()
+    r = scf.rhf(S, T + V, basis.coulomb, basis.exchange, [1], [np.arange(basis.Nbf())])
+    assert abs(r["E"] + 1.0 / 1.4 - (-1.1336295702)) < 1e-9
+
+
+def test_errors(hb):
+    b = hb.AtomicTwoDBasis(2, 0, 0, 2)
+    with pytest.raises(ValueError):      # reference: "Primitive teis have not been computed!"
+        b.coulomb(np.zeros((1, 1)))
+    b.compute_tei()
+    with pytest.raises(ValueError):      # size mismatch
+        b.exchange(np.zeros((3, 3)))
