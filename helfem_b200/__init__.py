@@ -262,10 +262,11 @@ class _BasisBase:
         _check(lib().hfq_exchange_device(self._context(), dP_ptr, n, dK_ptr, n, shard, nshards, stream))
 
     def last_timings(self):
-        out = np.zeros(11)
-        _check(lib().hfq_last_timings(self._context(), out.ctypes.data, 11))
+        out = np.zeros(17)
+        _check(lib().hfq_last_timings(self._context(), out.ctypes.data, 17))
         keys = ["ms_pack", "ms_fold", "ms_tgemm", "ms_offdiag", "ms_unpack", "ms_total", "flops_fold", "flops_tgemm",
-                "flops_offdiag", "launches", "device_bytes"]
+                "flops_offdiag", "launches", "device_bytes", "alg_fold", "alg_tgemm", "alg_offdiag",
+                "launches_fold", "launches_tgemm", "launches_offdiag"]
         return dict(zip(keys, out))
 
     # -- helpers ---------------------------------------------------------------

@@ -285,9 +285,11 @@ int hfq_exchange_device(hfq_ctx *ctx, const double *dP, int64_t ldP, double *dK,
 int hfq_last_timings(const hfq_ctx *ctx, double *out, int n) {
   if (!ctx || !out) return fail(HFQ_ERR_INVALID, "hfq_last_timings: null argument");
   const hfq::EngineTimings &t = ctx->eng->timings();
-  const double v[11] = {t.pack, t.fold, t.tgemm, t.offdiag, t.unpack, t.total, t.flops_fold, t.flops_tgemm,
-                        t.flops_offdiag, (double)t.launches, (double)ctx->eng->device_bytes()};
-  for (int i = 0; i < n && i < 11; i++) out[i] = v[i];
+  const double v[17] = {t.pack, t.fold, t.tgemm, t.offdiag, t.unpack, t.total, t.flops_fold, t.flops_tgemm,
+                        t.flops_offdiag, (double)t.launches, (double)ctx->eng->device_bytes(), t.alg_fold,
+                        t.alg_tgemm, t.alg_offdiag, (double)t.launches_fold, (double)t.launches_tgemm,
+                        (double)t.launches_offdiag};
+  for (int i = 0; i < n && i < 17; i++) out[i] = v[i];
   return HFQ_OK;
 }
 

@@ -451,11 +451,14 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
     int op;
     std::vector<dev::FoldTask> tasks;
     std::vector<int> ilm;
+    std::vector<double> alg_fold;  // unpadded flops of the fold per task
   };
   std::vector<OpWork> work;
   std::vector<int> op_src((size_t)ns * ns, -1);
   {
-    int opcount = 0;
+    // Sharding: tasks (output pair, density pair, L) are dealt round-robin to the shards, so
+    // every rank builds a partial sum of every output block and the all-reduce completes it.
+    long taskcount = 0;
     for (int sj = 0; sj < ns; sj++)
       for (int sk = 0; sk < ns; sk++) {
         const int mj = s.sec_m[sj], mk = s.sec_m[sk];
@@ -473,6 +476,7 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
               if (ilm < 0) continue;
               if (!s.G_nonzero[((size_t)sj * ns + si) * s.NL + L] || !s.G_nonzero[((size_t)sk * ns + sl) * s.NL + L])
                 continue;
+              if ((taskcount++ % nshards) != shard) continue;
               dev::FoldTask ft;
               ft.spj = sj * ns + si;
               ft.spk = sk * ns + sl;
@@ -483,12 +487,13 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
               ft.fac = t.pref[ilm] * ((t.sign_by_M && (M & 1)) ? -1.0 : 1.0);
               w.tasks.push_back(ft);
               w.ilm.push_back(ilm);
+              {
+                const double nj = s.sec_n[sj], nk = s.sec_n[sk], ni = s.sec_n[si], nl = s.sec_n[sl];
+                w.alg_fold.push_back(2.0 * s.Npix * (ni * nl * nk * t.nch + nj * ni * nk * s.nab));
+              }
             }
           }
         if (w.tasks.empty()) continue;
-        const bool mine = (opcount % nshards) == shard;
-        opcount++;
-        if (!mine) continue;
         op_src[w.op] = w.op;
         work.push_back(std::move(w));
       }
@@ -527,7 +532,7 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
   }
   if (total_tasks && s.r_slots == 0) throw std::runtime_error("Engine: no memory for the exchange work buffer");
   // 5. batches: consecutive tasks (an output pair may span batches)
-  double fl_fold = 0, fl_tg = 0, fl_off = 0;
+  double fl_fold = 0, fl_tg = 0, fl_off = 0, al_fold = 0, al_tg = 0, al_off = 0;
   const int nruns = (int)s.run_nL.size();
   size_t wi = 0, ti = 0;  // current op / task inside op
   std::vector<char> op_started(work.size(), 0);
@@ -575,6 +580,7 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
         gi.alpha = 1.0;
         gitems.push_back(gi);
         fl_tg += 2.0 * gi.M * gi.N * (double)gi.K * take;
+        al_tg += 2.0 * gi.M * (double)s.sec_n[w.op / ns] * s.sec_n[w.op % ns] * (double)gi.K * take;
       }
       // cross-element items
       const int oe0 = (int)oentries.size();
@@ -592,8 +598,11 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
           oitems.push_back(oi);
           fl_off += 2.0 * t.nch * (double)s.NB * take *
                     ((double)t.en[ei] * t.en[ej] * t.nch * t.en[ej] + (double)t.en[ei] * t.en[ej] * t.en[ei]);
+          al_off += 2.0 * t.nch * (double)s.sec_n[w.op / ns] * s.sec_n[w.op % ns] * take *
+                    ((double)t.en[ei] * t.en[ej] * t.nch * t.en[ej] + (double)t.en[ei] * t.en[ej] * t.en[ei]);
         }
       fl_fold += 2.0 * (double)take * s.Npix * (double)s.NP * s.NP * s.NP * (t.nch + s.nab);
+      for (size_t k = 0; k < take; k++) al_fold += w.alg_fold[ti + k];
       ti += take;
       if (ti == w.tasks.size()) {
         wi++;
@@ -638,6 +647,9 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
     CK(cudaEventElapsedTime(&ms, s.ev[4], s.ev[5]));
     ms_off += ms;
     tm_.launches += 2 + (oitems.empty() ? 0 : 1);
+    tm_.launches_fold++;
+    tm_.launches_tgemm++;
+    tm_.launches_offdiag += oitems.empty() ? 0 : 1;
   }
   // 6. unpack
   CK(cudaEventRecord(s.ev[6], st));
@@ -656,6 +668,9 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
   tm_.flops_fold = fl_fold;
   tm_.flops_tgemm = fl_tg;
   tm_.flops_offdiag = fl_off;
+  tm_.alg_fold = al_fold;
+  tm_.alg_tgemm = al_tg;
+  tm_.alg_offdiag = al_off;
   tm_.launches += 3;
 }
 

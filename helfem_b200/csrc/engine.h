@@ -23,8 +23,9 @@ namespace hfq {
 struct EngineTimings {      // milliseconds of the last call, CUDA events
   float pack = 0, fold = 0, tgemm = 0, offdiag = 0, unpack = 0, total = 0;
   double flops_fold = 0, flops_tgemm = 0, flops_offdiag = 0;  // executed (padded) flops
-  double alg_flops = 0;      // algorithmic flops of the call
-  int launches = 0;
+  double alg_fold = 0, alg_tgemm = 0, alg_offdiag = 0;        // algorithmic (unpadded) flops, DESIGN.md
+  int launches = 0;           // kernel launches of the call
+  int launches_fold = 0, launches_tgemm = 0, launches_offdiag = 0;
 };
 
 class Engine {

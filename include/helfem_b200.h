@@ -120,7 +120,8 @@ int hfq_exchange_device(hfq_ctx *ctx, const double *dP, int64_t ldP, double *dK,
 /* Timings / work counters of the last call on this context:
  * out[0..5] = ms {pack, fold, in-element GEMM, cross-element, unpack, total},
  * out[6..8] = executed flops {fold, in-element GEMM, cross-element}, out[9] = kernel launches,
- * out[10] = device bytes held by the context. */
+ * out[10] = device bytes held by the context, out[11..13] = algorithmic (unpadded) flops
+ * {fold, in-element GEMM, cross-element}, out[14..16] = launches of those three kernels. */
 int hfq_last_timings(const hfq_ctx *ctx, double *out, int n);
 
 #ifdef __cplusplus

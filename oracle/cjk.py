@@ -1,0 +1,141 @@
+"""ctypes front end of the C oracle (oracle/csrc/jk_oracle.c).  Test infrastructure only.
+
+Takes the integral caches as plain arrays (from the numpy oracle or exported from the
+product's tables), so the CPU baseline and the GPU path can be timed on identical inputs.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+from . import gaunt as _gaunt
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libjk_oracle.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        src = os.path.join(_HERE, "csrc", "jk_oracle.c")
+        if not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+            subprocess.check_call(["make", "-s", "-C", _HERE, os.path.join(_HERE, "_build", "libjk_oracle.so")])
+        _lib = ctypes.CDLL(_SO)
+        _lib.jk_num_threads.restype = ctypes.c_int
+    return _lib
+
+
+def num_threads():
+    return lib().jk_num_threads()
+
+
+def _ptrs(mats):
+    keep = [np.ascontiguousarray(np.asarray(m, dtype=np.float64).ravel(order="F")) for m in mats]
+    arr = (ctypes.c_void_p * len(keep))(*[k.ctypes.data for k in keep])
+    return arr, keep
+
+
+def _i(v):
+    return np.ascontiguousarray(v, dtype=np.int32)
+
+
+class DiatomicCaches:
+    """Flat caches for the C oracle.  blocks[ilm*Nel+iel] = (small(2,n,n), big(2,n,n), B, sigma)."""
+
+    def __init__(self, Nrad, efirst, en, lval, mval, lmL, lmM, pref, blocks):
+        self.Nrad, self.efirst, self.en = int(Nrad), _i(efirst), _i(en)
+        self.lval, self.mval, self.lmL, self.lmM = _i(lval), _i(mval), _i(lmL), _i(lmM)
+        self.pref = np.ascontiguousarray(pref, dtype=np.float64)
+        self.Nang, self.Nel, self.nlm = len(self.lval), len(self.en), len(self.lmL)
+        self.NL = int(self.lmL.max()) + 1
+        self.P0, self._k0 = _ptrs([b[0][0] for b in blocks])
+        self.P2, self._k1 = _ptrs([b[0][1] for b in blocks])
+        self.Q0, self._k2 = _ptrs([b[1][0] for b in blocks])
+        self.Q2, self._k3 = _ptrs([b[1][1] for b in blocks])
+        self.B, self._k4 = _ptrs([b[2] for b in blocks])
+        self.S, self._k5 = _ptrs([b[3] for b in blocks])
+        self.rank = _i([b[2].shape[1] for b in blocks])
+        g0, g2 = _gaunt.coupling_tables(self.lval, self.mval, self.NL, True)
+        self.g0 = np.ascontiguousarray(g0); self.g2 = np.ascontiguousarray(g2)
+        LM = set()
+        for i in range(self.Nang):
+            for j in range(self.Nang):
+                M = int(self.mval[j] - self.mval[i])
+                for L in range(max(abs(int(self.lval[j] - self.lval[i])) - 2, abs(M)), int(self.lval[j] + self.lval[i]) + 3):
+                    LM.add((L, M))
+        LM = sorted(LM)
+        self.LML, self.LMM = _i([p[0] for p in LM]), _i([p[1] for p in LM])
+
+    def pure_idx(self):
+        idx = []
+        for i, m in enumerate(self.mval):
+            idx += list(range(i * self.Nrad + (0 if m == 0 else 1), (i + 1) * self.Nrad))
+        return np.array(idx)
+
+    def expand(self, P):
+        nd = self.Nang * self.Nrad
+        out = np.zeros((nd, nd), order="F")
+        pi = self.pure_idx()
+        out[np.ix_(pi, pi)] = P
+        return out
+
+    def exchange_blocks(self, Pdummy, jangs, kangs):
+        """Selected output blocks K.block(jang,kang) (Nrad x Nrad each), reference sign."""
+        Pd = np.asfortranarray(Pdummy)
+        jangs, kangs = _i(jangs), _i(kangs)
+        out = np.zeros((len(jangs), self.Nrad, self.Nrad))
+        v = ctypes.c_void_p
+        lib().jk_diatomic_exchange_blocks(
+            self.Nang, self.Nrad, self.Nel, self.NL, v(self.efirst.ctypes.data), v(self.en.ctypes.data),
+            v(self.lval.ctypes.data), v(self.mval.ctypes.data), v(self.g0.ctypes.data), v(self.g2.ctypes.data),
+            self.nlm, v(self.lmL.ctypes.data), v(self.lmM.ctypes.data), v(self.pref.ctypes.data),
+            self.P0, self.P2, self.Q0, self.Q2, self.B, self.S, v(self.rank.ctypes.data), v(Pd.ctypes.data),
+            len(jangs), v(jangs.ctypes.data), v(kangs.ctypes.data), v(out.ctypes.data))
+        return np.transpose(out, (0, 2, 1))  # stored column-major per block
+
+    def exchange(self, P):
+        """Full K (boundary removed), all output blocks."""
+        Pd = self.expand(P)
+        ja, ka = np.meshgrid(np.arange(self.Nang), np.arange(self.Nang), indexing="ij")
+        blk = self.exchange_blocks(Pd, ja.ravel(), ka.ravel())
+        nd = self.Nang * self.Nrad
+        K = np.zeros((nd, nd))
+        for b, (j, k) in enumerate(zip(ja.ravel(), ka.ravel())):
+            K[j * self.Nrad:(j + 1) * self.Nrad, k * self.Nrad:(k + 1) * self.Nrad] = blk[b]
+        pi = self.pure_idx()
+        return K[np.ix_(pi, pi)]
+
+    def coulomb(self, P):
+        Pd = self.expand(P)
+        nd = self.Nang * self.Nrad
+        J = np.zeros((nd, nd), order="F")
+        v = ctypes.c_void_p
+        lib().jk_diatomic_coulomb(
+            self.Nang, self.Nrad, self.Nel, self.NL, v(self.efirst.ctypes.data), v(self.en.ctypes.data),
+            v(self.lval.ctypes.data), v(self.mval.ctypes.data), v(self.g0.ctypes.data), v(self.g2.ctypes.data),
+            self.nlm, v(self.lmL.ctypes.data), v(self.lmM.ctypes.data), v(self.pref.ctypes.data),
+            len(self.LML), v(self.LML.ctypes.data), v(self.LMM.ctypes.data),
+            self.P0, self.P2, self.Q0, self.Q2, self.B, self.S, v(self.rank.ctypes.data), v(Pd.ctypes.data),
+            v(J.ctypes.data))
+        pi = self.pure_idx()
+        return J[np.ix_(pi, pi)]
+
+    @classmethod
+    def from_oracle(cls, b):
+        Nel = b.radial.Nel()
+        blocks = []
+        for ilm in range(len(b.lm_map)):
+            for e in range(Nel):
+                i = ilm * Nel + e
+                blocks.append((np.stack([b.disjoint_P0[i], b.disjoint_P2[i]]),
+                               np.stack([b.disjoint_Q0[i], b.disjoint_Q2[i]]), b.cd_B[i], b.cd_sigma[i]))
+        return cls(b.Nrad(), [b.radial.get_idx(e)[0] for e in range(Nel)], [b.radial.fem.nprim(e) for e in range(Nel)],
+                   b.lval, b.mval, [p[0] for p in b.lm_map], [p[1] for p in b.lm_map], b.LMfac_abs(), blocks)
+
+    @classmethod
+    def from_tables(cls, T):
+        """From the product's exported tables (identical inputs for the CPU baseline)."""
+        blocks = [T.block(ilm, e) for ilm in range(T.nlm) for e in range(T.Nel)]
+        return cls(T.Nrad, T.efirst, T.en, T.lval, T.mval, T.lmL, T.lmM, T.pref, blocks)

@@ -136,3 +136,22 @@ def test_errors(hb):
     b.compute_tei()
     with pytest.raises(ValueError):      # size mismatch
         b.exchange(np.zeros((3, 3)))
+
+
+def test_exchange_shards_sum_to_full(hb):
+    """Multi-GPU protocol on one device: the per-shard partial K matrices (device API) sum to
+    the unsharded result -- what the NCCL all-reduce relies on."""
+    import torch
+    basis = hb.DiatomicTwoDBasis(7, 7, 2.07, [4, 3, 2], 2).compute_tei()
+    n = basis.Nbf()
+    t = basis.tables
+    P = cases.random_density(n, 3, 7, cases.m_blocks(t.mval, t.Nrad, True))
+    Kfull = basis.exchange(P)
+    dP = torch.from_numpy(np.ascontiguousarray(P.T)).cuda()
+    for nsh in (2, 3):
+        tot = torch.zeros_like(dP)
+        for sh in range(nsh):
+            dK = torch.empty_like(dP)
+            basis.exchange_device(dP.data_ptr(), dK.data_ptr(), sh, nsh)
+            tot += dK
+        assert cases.relerr(tot.cpu().numpy().T, Kfull) < TOL

@@ -1,0 +1,105 @@
+"""Host side of the product on CPU: the C ABI loads and exports what include/helfem_b200.h
+declares; the C++ setup (basis + compute_tei) matches the oracle; error behaviour."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from tests import cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_exports_every_declared_symbol(hb):
+    header = open(os.path.join(ROOT, "include", "helfem_b200.h")).read()
+    declared = set(re.findall(r"\b(hfq_[a-z_0-9]+)\s*\(", header))
+    declared -= {"hfq_tables_desc", "hfq_tables_info"}
+    assert len(declared) >= 19
+    L = ctypes.CDLL(os.path.join(ROOT, "helfem_b200", "libhelfemqc_b200.so"))
+    for name in sorted(declared):
+        assert hasattr(L, name), name
+    assert declared == set(hb.EXPORTED_SYMBOLS)
+
+
+def test_atomic_setup_matches_oracle(hb):
+    ob = cases.oracle_atomic(4, 1, 1, 3)
+    T = hb.Tables.atomic(4, 1, 1, 3)
+    assert (T.Nbf, T.Nrad, T.Nel, T.Nang) == (ob.Nbf(), ob.Nrad(), 3, ob.Nang())
+    assert list(T.lval) == list(ob.lval) and list(T.mval) == list(ob.mval)
+    Nel = 3
+    for L in range(T.nlm):
+        for e in range(Nel):
+            sm, bg, B, sig = T.block(L, e)
+            o_sm, o_bg, o_B = ob.disjoint_L[L * Nel + e], ob.disjoint_m1L[L * Nel + e], ob.prim_chol[L * Nel + e]
+            assert np.abs(sm[0] - o_sm).max() <= 1e-13 * np.abs(o_sm).max()
+            if e > 0:
+                assert np.abs(bg[0] - o_bg).max() <= 1e-13 * np.abs(o_bg).max()
+            assert B.shape == o_B.shape and np.all(sig == 1.0)
+            assert np.abs(B @ B.T - o_B @ o_B.T).max() <= 1e-12 * np.abs(o_B @ o_B.T).max()
+    S, Tk, V = T.one_electron()
+    assert cases.relerr(S, ob.overlap()) < 1e-13
+    assert cases.relerr(Tk, ob.kinetic()) < 1e-13
+    assert cases.relerr(V, ob.nuclear()) < 1e-13
+
+
+def test_diatomic_setup_matches_oracle(hb):
+    ob = cases.oracle_diatomic(3, 1, 1.8, (3, 2), 2)
+    T = hb.Tables.diatomic(3, 1, 1.8, [3, 2], 2)
+    assert (T.Nbf, T.Nrad, T.Nang) == (ob.Nbf(), ob.Nrad(), ob.Nang())
+    assert list(zip(T.lmL, T.lmM)) == ob.lm_map
+    assert np.allclose(T.pref, ob.LMfac_abs(), rtol=1e-15)
+    Nel = 2
+    for ilm in range(T.nlm):
+        for e in range(Nel):
+            i = ilm * Nel + e
+            sm, bg, B, sig = T.block(ilm, e)
+            for c, (os_, ob_) in enumerate([(ob.disjoint_P0[i], ob.disjoint_Q0[i]), (ob.disjoint_P2[i], ob.disjoint_Q2[i])]):
+                assert np.abs(sm[c] - os_).max() <= 1e-13 * np.abs(os_).max()
+                if e > 0:
+                    assert np.abs(bg[c] - ob_).max() <= 1e-13 * np.abs(ob_).max()
+            W = (B * sig) @ B.T
+            Wo = (ob.cd_B[i] * ob.cd_sigma[i]) @ ob.cd_B[i].T
+            assert np.abs(W - Wo).max() <= 1e-11 * np.abs(Wo).max()
+    S, Tk, V = T.one_electron()
+    assert cases.relerr(S, ob.overlap()) < 1e-13
+    assert cases.relerr(Tk, ob.kinetic()) < 1e-13
+    assert cases.relerr(V, ob.nuclear()) < 1e-13
+
+
+def test_from_arrays_round_trip(hb):
+    ob = cases.oracle_diatomic(3, 1, 1.8, (2,), 2)
+    T = cases.tables_from_oracle_diatomic(hb, ob)
+    sm, bg, B, sig = T.block(3, 1)
+    assert np.array_equal(sm[1], ob.disjoint_P2[3 * 2 + 1]) and np.array_equal(B, ob.cd_B[3 * 2 + 1])
+    assert np.array_equal(sig, ob.cd_sigma[3 * 2 + 1])
+
+
+def test_argument_errors(hb):
+    with pytest.raises(ValueError):
+        hb.Tables.atomic(2, 0, 1, 5)            # mmax > lmax
+    with pytest.raises(ValueError):
+        hb.Tables.diatomic(1, 1, 1.4, [0, 0], 2)  # lmax(|m|=1) < 1
+    b = hb.AtomicTwoDBasis(2, 0, 0, 2)
+    with pytest.raises(ValueError, match="Primitive teis"):
+        b.coulomb(np.zeros((2, 2)))
+
+
+def test_no_cpu_fallback(hb):
+    """Without a CUDA device the Fock-build path must fail loudly, not fall back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    b = hb.AtomicTwoDBasis(2, 0, 0, 2).compute_tei()
+    with pytest.raises(hb.HfqError, match="CUDA"):
+        b.coulomb(np.zeros((b.Nbf(), b.Nbf())))
+
+
+def test_product_does_not_touch_the_oracle():
+    pkg = os.path.join(ROOT, "helfem_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cpp", ".cu", ".h", ".cuh")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "oracle" not in txt.replace("the oracle", "").lower() or f == "__init__.py" and "oracle" not in txt, f

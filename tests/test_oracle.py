@@ -1,0 +1,121 @@
+"""The oracle against the reference's own golden vectors / recorded results (CPU only)."""
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import atomic as oat
+from oracle import fem as ofem
+from oracle import gaunt as og
+from oracle import legendre as oleg
+from oracle import scf
+from tests import cases
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EPS = np.finfo(float).eps
+
+
+def test_gaunt_against_reference_table():
+    """src/general/gaunt_test.cpp: 550 tabulated values at DBL_EPSILON*(1+|ref|)."""
+    ref = json.load(open(os.path.join(HERE, "golden", "gaunt_ref.json")))
+    assert len(ref) == 550
+    for e in ref:
+        v = getattr(og, e["fn"])(*e["args"])
+        assert abs(v - e["ref"]) < EPS * (1.0 + abs(e["ref"])), e
+
+
+def test_gaunt_bulk_tables_match_exact():
+    lv = np.array([0, 1, 1, 2, 2, 3, 3, 5])
+    mv = np.array([0, 1, -1, 2, -2, 1, 0, -3])
+    g0, g2 = og.coupling_tables(lv, mv, 12, True)
+    g = og.Gaunt()
+    for j in range(len(lv)):
+        for i in range(len(lv)):
+            M = int(mv[j] - mv[i])
+            for L in range(max(abs(int(lv[j] - lv[i])) - 2, abs(M)), min(int(lv[j] + lv[i]) + 3, 12)):
+                assert abs(g2[j, i, L] - g.coeff(int(lv[j]), int(mv[j]), L, M, int(lv[i]))) < 4 * EPS
+                assert abs(g0[j, i, L] - g.mod_coeff(int(lv[j]), int(mv[j]), L, M, int(lv[i]), int(mv[i]))) < 4 * EPS
+
+
+def test_legendre_against_reference_build():
+    """oracle/_ref/liblegendre_ref.so is the reference's own src/legendre/Legendre.h
+    (which passes its 32130-value Maple unit test) compiled from where it lies."""
+    so = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "liblegendre_ref.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    lib = ctypes.CDLL(so)
+    lib.ref_plm.argtypes = lib.ref_qlm.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double]
+    rng = np.random.default_rng(0)
+    for lmax, M in [(5, 0), (10, 2), (30, 6), (64, 12), (20, 1)]:
+        mu = np.concatenate([10 ** rng.uniform(-6, 0, 20), rng.uniform(0, 4.4, 30)])
+        x = np.cosh(mu)
+        x = x[x > 1]
+        P, Q = oleg.plm(lmax, M, x), oleg.qlm(lmax, M, x)
+        for i, xi in enumerate(x):
+            buf = np.zeros((M + 1) * (lmax + 1))
+            assert lib.ref_plm(buf.ctypes.data, lmax, M, xi) == 0
+            pr = buf[M * (lmax + 1):].copy()
+            assert lib.ref_qlm(buf.ctypes.data, lmax, M, xi) == 0
+            qr = buf[M * (lmax + 1):].copy()
+            assert np.allclose(P[:, i], pr, rtol=1e-14, atol=0)
+            assert np.allclose(Q[:, i], qr, rtol=1e-14, atol=0)
+
+
+def test_two_electron_exact_rationals():
+    """src/atomic/inttest.cpp:72-99: Maple values of the 2-node L=0 in-element integrals."""
+    R = 2.5
+    rb = oat.RadialBasis(ofem.FEBasis(2, [0.0, R], False, False), 10)
+    T = rb.twoe_integral(0, 0)
+    t = np.zeros((4, 4))
+    t[0, 0] = 47 / 180; t[0, 1] = t[0, 2] = 11 / 360; t[0, 3] = 1 / 90
+    t[1, 0] = 1 / 10; t[1, 1] = t[1, 2] = 1 / 40; t[1, 3] = 1 / 60
+    t[2] = t[1]; t[3, 0] = 3 / 20; t[3, 1] = t[3, 2] = 7 / 120; t[3, 3] = 1 / 15
+    ex = (t + t.T) * R
+    err = np.abs(T / ex - 1.0)
+    err[0, 0] = 0.0   # B(0) != 0 for this function: slowly convergent, never used (function is dropped)
+    assert err.max() < 1e-13
+
+
+def test_cholesky_rank_and_accuracy():
+    """src/atomic/TwoDBasis.h:96-98: rank 27-29 of 196-225, |T - LL'| at the 1e-12 threshold."""
+    ob = cases.oracle_atomic(2, 0, 0, 5)
+    ranks = [c.shape[1] for c in ob.prim_chol]
+    assert ranks == [27, 29, 29, 29, 27]
+    T = ob.radial.twoe_integral(0, 2)
+    Lf = ob.prim_chol[2]
+    assert np.abs(T - Lf @ Lf.T).max() < 1e-11
+
+
+def test_he_rhf_recorded_energy():
+    """tests/refs/ci.json atomic-He-hf-r: total -2.8616799956 (10 decimals); components are
+    recorded from a 1e-7-converged SCF, hence the looser bound on them."""
+    ob = cases.oracle_atomic(2, 0, 0, 5)
+    S, T, V = ob.overlap(), ob.kinetic(), ob.nuclear()
+    r = scf.rhf(S, T + V, ob.coulomb, ob.exchange, [1], [np.arange(ob.Nbf())])
+    assert abs(r["E"] - (-2.8616799956)) < 1e-10
+    assert abs(r["E"] - (-2.861679995612)) < 1e-10          # HF limit, src/atomic/precision.cpp:102
+    assert abs(r["Coulomb"] - 2.0515380305) < 1e-6
+    assert abs(r["Exx"] - (-1.0257690153)) < 1e-6
+    assert abs(np.sum(r["P"] * T) - 2.8616803763) < 1e-6
+    assert abs(np.sum(r["P"] * V) - (-6.7491293871)) < 2e-6
+
+
+def test_h2_rhf_recorded_energy():
+    """tests/refs/ci.json diatomic-H2-hf-r: total -1.1336295702."""
+    ob = cases.oracle_diatomic(1, 1, 1.4, (4,), 3)
+    S, T, V = ob.overlap(), ob.kinetic(), ob.nuclear()
+    r = scf.rhf(S, T + V, ob.coulomb, ob.exchange, [1], [np.arange(ob.Nbf())])
+    assert abs(r["E"] + 1.0 / 1.4 - (-1.1336295702)) < 1e-10
+    assert abs(r["Coulomb"] - 1.3171969210) < 1e-6
+    assert abs(r["Exx"] - (-0.6585984605)) < 1e-6
+
+
+def test_c_oracle_matches_numpy_oracle():
+    from oracle import cjk
+    ob = cases.oracle_diatomic(3, 1, 1.8, (2, 2, 2), 2)
+    C = cjk.DiatomicCaches.from_oracle(ob)
+    P = cases.random_density(ob.Nbf(), 4, 22)
+    assert cases.relerr(C.exchange(P), ob.exchange(P)) < 1e-13
+    assert cases.relerr(C.coulomb(P), ob.coulomb(P)) < 1e-13
