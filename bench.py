@@ -106,8 +106,11 @@ def main():
     ap.add_argument("--nelem", type=int, default=3)
     ap.add_argument("--cpu-blocks", type=int, default=24, help="exchange output blocks in the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-mode", action="store_true",
+                    help="for runs under ncu only: device-resident steps, no e2e/peak/CPU legs, prints no bench line")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "ours" and not args.profile_mode:
+        args.warmup = max(args.warmup, 3)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -225,6 +228,9 @@ def main():
     ms_step = float(tms.item()) / args.steps
     value = 1e3 / ms_step
 
+    if args.profile_mode:
+        print("profile-mode: %.2f ms/step (not a bench value)" % ms_step)
+        return
     # ---- end-to-end through the host-pointer C ABI (pinned host buffers, copies inside)
     e2e_val = None
     if world == 1:
