@@ -341,8 +341,10 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
   s.d_sp_active.alloc((size_t)s.ns * s.ns, &dev_bytes_);
   CK(cudaStreamSynchronize(stream_));
   // opt-in shared memory sizes
-  CK(cudaFuncSetAttribute(dev::k_offdiag<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  CK(cudaFuncSetAttribute(dev::k_offdiag<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(dev::k_offdiag_mma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  CK(cudaFuncSetAttribute(dev::k_offdiag_mma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  CK(cudaFuncSetAttribute(dev::k_tgemm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(dev::k_tgemm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 }
 
 Engine::~Engine() {
@@ -494,9 +496,34 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
             }
           }
         if (w.tasks.empty()) continue;
-        op_src[w.op] = w.op;
         work.push_back(std::move(w));
       }
+  }
+  // 4. buffers
+  const size_t slot_doubles = (size_t)s.nab * s.Npix * s.NB;
+  const int nactive = (int)work.size();
+  size_t total_tasks = 0;
+  for (auto &w : work) total_tasks += w.tasks.size();
+  // K-split of the in-element GEMM: each (output pair, element) item is cut into S chunks of its
+  // task list, each chunk accumulating into its own partial buffer (summed by the unpack kernel),
+  // so that the number of CTAs per launch fills whole waves of the 148 SMs.
+  int S = 1;
+  {
+    const double units = (double)nactive * t.Nel * (s.NB / 64);
+    double best = 0.0;
+    for (int c = 1; c <= 4; c++) {
+      const double u = units * c, eff = u / (std::ceil(u / 148.0) * 148.0);
+      if (eff > best + 0.02) {
+        best = eff;
+        S = c;
+      }
+    }
+  }
+  if (s.d_Kacc.n < (size_t)nactive * S * s.op_stride) s.d_Kacc.alloc((size_t)nactive * S * s.op_stride, &dev_bytes_);
+  for (int a = 0; a < nactive; a++) {
+    op_src[work[a].op] = a;
+    if (S > 1)
+      CK(cudaMemsetAsync(s.d_Kacc.p + ((size_t)a * S + 1) * s.op_stride, 0, (size_t)(S - 1) * s.op_stride * sizeof(double), st));
   }
   if (absm_symmetric_) {
     // K(-mj,-mk) block = K(mj,mk) block (same l positions: sectors +-m hold the same l list)
@@ -511,14 +538,6 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
         op_src[(size_t)sj * ns + sk] = op_src[(size_t)pj->second * ns + pk->second];
       }
   }
-  // 4. buffers
-  const size_t slot_doubles = (size_t)s.nab * s.Npix * s.NB;
-  if (s.d_Kacc.n < (size_t)ns * ns * s.op_stride) s.d_Kacc.alloc((size_t)ns * ns * s.op_stride, &dev_bytes_);
-  size_t total_tasks = 0, max_op_tasks = 0;
-  for (auto &w : work) {
-    total_tasks += w.tasks.size();
-    max_op_tasks = std::max(max_op_tasks, w.tasks.size());
-  }
   {
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
@@ -531,83 +550,98 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
     }
   }
   if (total_tasks && s.r_slots == 0) throw std::runtime_error("Engine: no memory for the exchange work buffer");
-  // 5. batches: consecutive tasks (an output pair may span batches)
+  // 5. batches: every batch takes an equal share of tasks from every active output pair, so each
+  //    launch works on all output pairs at once (grid size independent of the batch count)
   double fl_fold = 0, fl_tg = 0, fl_off = 0, al_fold = 0, al_tg = 0, al_off = 0;
   const int nruns = (int)s.run_nL.size();
-  size_t wi = 0, ti = 0;  // current op / task inside op
-  std::vector<char> op_started(work.size(), 0);
+  std::vector<size_t> done(work.size(), 0);
+  std::vector<char> started((size_t)work.size() * S, 0);
+  size_t remaining = total_tasks;
   float ms_fold = 0, ms_tg = 0, ms_off = 0;
-  while (wi < work.size()) {
+  while (remaining > 0) {
     std::vector<dev::FoldTask> tasks;
     std::vector<dev::GemmItem> gitems;
     std::vector<dev::GemmEntry> gentries;
     std::vector<dev::OffItem> oitems;
     std::vector<dev::OffEntry> oentries;
-    while (wi < work.size() && tasks.size() < s.r_slots) {
+    // shares: proportional split of the slot budget over the output pairs that still have work
+    size_t open = 0;
+    for (size_t wi = 0; wi < work.size(); wi++) open += done[wi] < work[wi].tasks.size();
+    const size_t share = std::max<size_t>(1, s.r_slots / std::max<size_t>(open, 1));
+    for (size_t wi = 0; wi < work.size() && tasks.size() < s.r_slots; wi++) {
       OpWork &w = work[wi];
-      const size_t take = std::min(w.tasks.size() - ti, s.r_slots - tasks.size());
-      const int acc = op_started[wi] ? 1 : 0;
-      op_started[wi] = 1;
+      const size_t ti = done[wi];
+      size_t take = std::min(w.tasks.size() - ti, std::min(share, s.r_slots - tasks.size()));
+      if (remaining <= s.r_slots) take = w.tasks.size() - ti;   // everything fits: finish
+      take = std::min(take, s.r_slots - tasks.size());
+      if (take == 0) continue;
       const size_t t0 = tasks.size();
       for (size_t k = 0; k < take; k++) {
         dev::FoldTask ft = w.tasks[ti + k];
         ft.rslot = (int)(t0 + k);
         tasks.push_back(ft);
       }
-      double *acc_base = s.d_Kacc.p + (size_t)w.op * s.op_stride;
-      // in-element items (tensor-core GEMM against the dense exchange-ordered kernel)
-      for (int e = 0; e < t.Nel; e++) {
-        const int n = t.en[e];
-        dev::GemmItem gi{};
-        gi.C = acc_base + s.ep_off[(size_t)e * t.Nel + e];
-        gi.browoff = s.d_browoff_T.p + s.browoff_T_first[e];
-        gi.M = n * n;
-        gi.N = s.NB;
-        gi.K = s.nab * n * n;
-        gi.ent0 = (int)gentries.size();
-        for (size_t k = 0; k < take; k++) {
-          const int ilm = w.ilm[ti + k], r = s.chan_run[ilm];
-          dev::GemmEntry ge;
-          ge.A = s.d_tperm.p + s.tperm_off[(size_t)e * nruns + r] + (int64_t)s.chan_pos[ilm] * s.nab * n * n;
-          ge.lda = s.tperm_lda[(size_t)e * nruns + r];
-          ge.B = s.d_R.p + (t0 + k) * slot_doubles;
-          gentries.push_back(ge);
+      // in-element items (tensor-core GEMM against the dense exchange-ordered kernel), S chunks
+      for (int c = 0; c < S; c++) {
+        const size_t k0 = take * c / S, k1 = take * (c + 1) / S;
+        if (k1 == k0) continue;
+        double *acc_base = s.d_Kacc.p + ((size_t)wi * S + c) * s.op_stride;
+        const int acc = started[wi * S + c] ? 1 : 0;
+        started[wi * S + c] = 1;
+        for (int e = 0; e < t.Nel; e++) {
+          const int n = t.en[e];
+          dev::GemmItem gi{};
+          gi.C = acc_base + s.ep_off[(size_t)e * t.Nel + e];
+          gi.browoff = s.d_browoff_T.p + s.browoff_T_first[e];
+          gi.M = n * n;
+          gi.N = s.NB;
+          gi.K = s.nab * n * n;
+          gi.ent0 = (int)gentries.size();
+          for (size_t k = k0; k < k1; k++) {
+            const int ilm = w.ilm[ti + k], r = s.chan_run[ilm];
+            dev::GemmEntry ge;
+            ge.A = s.d_tperm.p + s.tperm_off[(size_t)e * nruns + r] + (int64_t)s.chan_pos[ilm] * s.nab * n * n;
+            ge.lda = s.tperm_lda[(size_t)e * nruns + r];
+            ge.B = s.d_R.p + (t0 + k) * slot_doubles;
+            gentries.push_back(ge);
+          }
+          gi.ent1 = (int)gentries.size();
+          gi.accumulate = acc;
+          gi.ldb = 0;
+          gi.ldc = s.NB;
+          gi.alpha = 1.0;
+          gitems.push_back(gi);
+          fl_tg += 2.0 * gi.M * gi.N * (double)gi.K * (k1 - k0);
+          al_tg += 2.0 * gi.M * (double)s.sec_n[w.op / ns] * s.sec_n[w.op % ns] * (double)gi.K * (k1 - k0);
         }
-        gi.ent1 = (int)gentries.size();
-        gi.accumulate = acc;
-        gi.ldb = 0;
-        gi.ldc = s.NB;
-        gi.alpha = 1.0;
-        gitems.push_back(gi);
-        fl_tg += 2.0 * gi.M * gi.N * (double)gi.K * take;
-        al_tg += 2.0 * gi.M * (double)s.sec_n[w.op / ns] * s.sec_n[w.op % ns] * (double)gi.K * take;
       }
-      // cross-element items
-      const int oe0 = (int)oentries.size();
-      for (size_t k = 0; k < take; k++) oentries.push_back(dev::OffEntry{(int)(t0 + k), w.ilm[ti + k]});
-      for (int ei = 0; ei < t.Nel; ei++)
-        for (int ej = 0; ej < t.Nel; ej++) {
-          if (ei == ej) continue;
-          dev::OffItem oi{};
-          oi.C = acc_base + s.ep_off[(size_t)ei * t.Nel + ej];
-          oi.ei = ei;
-          oi.ej = ej;
-          oi.ent0 = oe0;
-          oi.ent1 = (int)oentries.size();
-          oi.accumulate = acc;
-          oitems.push_back(oi);
-          fl_off += 2.0 * t.nch * (double)s.NB * take *
-                    ((double)t.en[ei] * t.en[ej] * t.nch * t.en[ej] + (double)t.en[ei] * t.en[ej] * t.en[ei]);
-          al_off += 2.0 * t.nch * (double)s.sec_n[w.op / ns] * s.sec_n[w.op % ns] * take *
-                    ((double)t.en[ei] * t.en[ej] * t.nch * t.en[ej] + (double)t.en[ei] * t.en[ej] * t.en[ei]);
-        }
+      // cross-element items (partial buffer 0)
+      {
+        double *acc_base = s.d_Kacc.p + (size_t)wi * S * s.op_stride;
+        const int acc = ti > 0 ? 1 : 0;
+        const int oe0 = (int)oentries.size();
+        for (size_t k = 0; k < take; k++) oentries.push_back(dev::OffEntry{(int)(t0 + k), w.ilm[ti + k]});
+        for (int ei = 0; ei < t.Nel; ei++)
+          for (int ej = 0; ej < t.Nel; ej++) {
+            if (ei == ej) continue;
+            dev::OffItem oi{};
+            oi.C = acc_base + s.ep_off[(size_t)ei * t.Nel + ej];
+            oi.ei = ei;
+            oi.ej = ej;
+            oi.ent0 = oe0;
+            oi.ent1 = (int)oentries.size();
+            oi.accumulate = acc;
+            oitems.push_back(oi);
+            const double per = 2.0 * t.nch * take *
+                               ((double)t.en[ei] * t.en[ej] * t.nch * t.en[ej] + (double)t.en[ei] * t.en[ej] * t.en[ei]);
+            fl_off += per * s.NB;
+            al_off += per * s.sec_n[w.op / ns] * s.sec_n[w.op % ns];
+          }
+      }
       fl_fold += 2.0 * (double)take * s.Npix * (double)s.NP * s.NP * s.NP * (t.nch + s.nab);
       for (size_t k = 0; k < take; k++) al_fold += w.alg_fold[ti + k];
-      ti += take;
-      if (ti == w.tasks.size()) {
-        wi++;
-        ti = 0;
-      }
+      done[wi] += take;
+      remaining -= take;
     }
     if (tasks.empty()) break;
     // upload descriptors
@@ -624,16 +658,25 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
     CK(cudaEventRecord(s.ev[2], st));
     launch_fold(s.NT, t.nch, s.bd, s.d_tasks.p, (int)tasks.size(), s.d_G.p, s.d_Ppix.p, s.d_R.p, st);
     CK(cudaEventRecord(s.ev[3], st));
-    launch_gemm<false>(s.d_gitems.p, s.d_gentries.p, (int)gitems.size(), 16 * 16, s.NB, st);
+    {
+      // in-element exchange: one CTA tile covers all Ni^2 rows (R rows are read once)
+      const size_t smem = (size_t)3 * (256 * 20 + 16 * 68) * sizeof(double);
+      const dim3 grid(s.NB / 64, (unsigned)gitems.size());
+      if (s.nab % 2 == 0)
+        dev::k_tgemm<true><<<grid, 256, smem, st>>>(s.d_gitems.p, s.d_gentries.p);
+      else
+        dev::k_tgemm<false><<<grid, 256, smem, st>>>(s.d_gitems.p, s.d_gentries.p);
+      CK(cudaGetLastError());
+    }
     CK(cudaEventRecord(s.ev[4], st));
     if (!oitems.empty()) {
-      const size_t smem = (size_t)(s.nab * 2048 + t.nch * 2048 + 2 * t.nch * 256) * sizeof(double);
-      const dim3 grid(s.NB / 8, (unsigned)oitems.size());
+      const dim3 grid(s.NB / 16, (unsigned)oitems.size());
+      const size_t smem = (size_t)(t.nch * 16 * 16 * 20 + t.nch * 16 * 20 + 16 * (t.nch * 16 + 4)) * sizeof(double);
       if (t.nch == 1)
-        dev::k_offdiag<1><<<grid, 256, smem, st>>>(s.bd, s.d_oitems.p, s.d_oentries.p, s.d_R.p, s.d_small.p,
+        dev::k_offdiag_mma<1><<<grid, 256, smem, st>>>(s.bd, s.d_oitems.p, s.d_oentries.p, s.d_R.p, s.d_small.p,
                                                     s.d_big.p, s.d_blk_off.p);
       else
-        dev::k_offdiag<2><<<grid, 256, smem, st>>>(s.bd, s.d_oitems.p, s.d_oentries.p, s.d_R.p, s.d_small.p,
+        dev::k_offdiag_mma<2><<<grid, 256, smem, st>>>(s.bd, s.d_oitems.p, s.d_oentries.p, s.d_R.p, s.d_small.p,
                                                     s.d_big.p, s.d_blk_off.p);
       CK(cudaGetLastError());
     }
@@ -654,7 +697,7 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
   // 6. unpack
   CK(cudaEventRecord(s.ev[6], st));
   CK(cudaMemcpyAsync(s.d_op_src.p, op_src.data(), op_src.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-  dev::UnpackDev u{s.d_op_src.p, s.d_ep_off.p, s.d_ang_sec.p, s.d_ang_pos.p, s.op_stride};
+  dev::UnpackDev u{s.d_op_src.p, s.d_ep_off.p, s.d_ang_sec.p, s.d_ang_pos.p, s.op_stride, S};
   dev::k_unpack_K<<<dim3(na, na), 256, 0, st>>>(s.bd, u, s.d_Kacc.p, dK, ldK);
   CK(cudaGetLastError());
   CK(cudaEventRecord(s.ev[7], st));

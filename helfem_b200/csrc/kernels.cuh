@@ -429,6 +429,258 @@ k_offdiag(BasisDev b, const OffItem *__restrict__ items, const OffEntry *__restr
 }
 
 // ---------------------------------------------------------------------------
+// Exchange, cross-element pairs on the FP64 tensor pipe.
+//   K_(ei,ej)(rj,rk)[blk] += sum_a sum_ri I_a(rj,ri) U_a(ri,rk)[blk]
+//   U_a(ri,rk)[blk]        = sum_b sum_rl J_b(rk,rl) R_ab(ri,rl)[blk]
+// Element sizes are padded 15 -> 16 with zero rows/columns of I and J.
+// One CTA (8 warps) = (item, tile of 16 blk columns).  Stage 1 streams the R rows
+// straight from global memory into DMMA B fragments (every R element is used by
+// exactly one CTA), stage 2 keeps the 16x16x16 output tile of two rk values per
+// warp in registers across the whole entry loop.
+// Shared memory: U[NCH][16 rk][16 ri][LDU] + I[NCH][16][LDS] + J[NCH][16][LDJ]
+// ---------------------------------------------------------------------------
+template <int NCH>
+__global__ void __launch_bounds__(256)
+k_offdiag_mma(BasisDev b, const OffItem *__restrict__ items, const OffEntry *__restrict__ entries,
+              const double *__restrict__ R, const double *__restrict__ dsmall, const double *__restrict__ dbig,
+              const int64_t *__restrict__ blk_off) {
+  constexpr int BT = 16, LDU = BT + 4, LDI = 16 + 4, LDJ = NCH * 16 + 4, NAB = NCH * NCH;
+  extern __shared__ double sm[];
+  double *sU = sm;                          // [NCH][16 rk][16 ri][LDU]
+  double *sI = sU + NCH * 16 * 16 * LDU;    // [NCH][16 rj][LDI]
+  double *sJ = sI + NCH * 16 * LDI;         // J[rk][b*16 + rl]
+  const OffItem it = items[blockIdx.y];
+  const int Ni = b.en[it.ei], Nj = b.en[it.ej], fi = b.efirst[it.ei], fj = b.efirst[it.ej];
+  const int blk0 = blockIdx.x * BT;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lr = lane >> 2, lc = lane & 3;
+  const int64_t gstride = (int64_t)b.NB;
+  for (int idx = tid; idx < NCH * 16 * 16 * LDU; idx += 256) sU[idx] = 0.0;
+  for (int idx = tid; idx < NCH * 16 * LDI; idx += 256) sI[idx] = 0.0;
+  for (int idx = tid; idx < 16 * LDJ; idx += 256) sJ[idx] = 0.0;
+  double kacc[2][2][2][2];   // [rk slot][rj tile][blk tile][frag]
+#pragma unroll
+  for (int q = 0; q < 16; q++) (&kacc[0][0][0][0])[q] = 0.0;
+
+  for (int e = it.ent0; e < it.ent1; e++) {
+    const OffEntry en = entries[e];
+    const double *Rt = R + (int64_t)en.rslot * NAB * b.Npix * gstride + blk0;
+    const double *srcI = (it.ei > it.ej ? dbig : dsmall) + blk_off[en.ilm * b.Nel + it.ei];
+    const double *srcJ = (it.ei > it.ej ? dsmall : dbig) + blk_off[en.ilm * b.Nel + it.ej];
+    __syncthreads();   // previous stage 2 finished with sI/sU
+    for (int idx = tid; idx < NCH * Ni * Ni; idx += 256) {
+      const int ch = idx / (Ni * Ni), rem = idx % (Ni * Ni), ri = rem / Ni, rj = rem % Ni;   // I(rj,ri) column-major
+      sI[(ch * 16 + rj) * LDI + ri] = srcI[idx];
+    }
+    for (int idx = tid; idx < NCH * Nj * Nj; idx += 256) {
+      const int ch = idx / (Nj * Nj), rem = idx % (Nj * Nj), rl = rem / Nj, rk = rem % Nj;   // J(rk,rl) column-major
+      sJ[rk * LDJ + ch * 16 + rl] = srcJ[idx];
+    }
+    __syncthreads();
+    // ---- stage 1: warp -> ri = warp, warp + 8
+    for (int ri = warp; ri < Ni; ri += 8) {
+#pragma unroll
+      for (int a = 0; a < NCH; a++) {
+        double c[2][2][2];
+#pragma unroll
+        for (int q = 0; q < 8; q++) (&c[0][0][0])[q] = 0.0;
+#pragma unroll
+        for (int bb = 0; bb < NCH; bb++) {
+          const double *Rrow = Rt + ((int64_t)(a * NCH + bb) * b.Npix + (int64_t)(fi + ri) * b.Nrad + fj) * gstride;
+#pragma unroll
+          for (int ks = 0; ks < 4; ks++) {
+            const int rl = ks * 4 + lc;
+            double bf0 = 0.0, bf1 = 0.0;
+            if (rl < Nj) {
+              const double *rp = Rrow + (int64_t)rl * gstride + lr;
+              bf0 = __ldg(rp);
+              bf1 = __ldg(rp + 8);
+            }
+            const double a0 = sJ[lr * LDJ + bb * 16 + rl], a1 = sJ[(8 + lr) * LDJ + bb * 16 + rl];
+            dmma(c[0][0][0], c[0][0][1], a0, bf0);
+            dmma(c[0][1][0], c[0][1][1], a0, bf1);
+            dmma(c[1][0][0], c[1][0][1], a1, bf0);
+            dmma(c[1][1][0], c[1][1][1], a1, bf1);
+          }
+        }
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+          for (int nt = 0; nt < 2; nt++) {
+            double *u = sU + ((a * 16 + mt * 8 + lr) * 16 + ri) * LDU + nt * 8 + 2 * lc;
+            u[0] = c[mt][nt][0];
+            u[1] = c[mt][nt][1];
+          }
+      }
+    }
+    __syncthreads();
+    // ---- stage 2: warp -> rk = warp, warp + 8
+#pragma unroll
+    for (int slot = 0; slot < 2; slot++) {
+      const int rk = warp + slot * 8;
+      if (rk >= Nj) continue;
+#pragma unroll
+      for (int a = 0; a < NCH; a++) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ks++) {
+          const int ri = ks * 4 + lc;
+          const double a0 = sI[(a * 16 + lr) * LDI + ri], a1 = sI[(a * 16 + 8 + lr) * LDI + ri];
+          const double *u = sU + ((a * 16 + rk) * 16 + ri) * LDU + lr;
+          const double bf0 = u[0], bf1 = u[8];
+          dmma(kacc[slot][0][0][0], kacc[slot][0][0][1], a0, bf0);
+          dmma(kacc[slot][0][1][0], kacc[slot][0][1][1], a0, bf1);
+          dmma(kacc[slot][1][0][0], kacc[slot][1][0][1], a1, bf0);
+          dmma(kacc[slot][1][1][0], kacc[slot][1][1][1], a1, bf1);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int slot = 0; slot < 2; slot++) {
+    const int rk = warp + slot * 8;
+    if (rk >= Nj) continue;
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++) {
+      const int rj = mt * 8 + lr;
+      if (rj >= Ni) continue;
+#pragma unroll
+      for (int nt = 0; nt < 2; nt++) {
+        double *c = it.C + (int64_t)(rj * Nj + rk) * gstride + blk0 + nt * 8 + 2 * lc;
+        double2 v;
+        v.x = kacc[slot][mt][nt][0];
+        v.y = kacc[slot][mt][nt][1];
+        if (it.accumulate) {
+          const double2 o = *reinterpret_cast<const double2 *>(c);
+          v.x += o.x;
+          v.y += o.y;
+        }
+        *reinterpret_cast<double2 *>(c) = v;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// In-element exchange GEMM on the FP64 tensor pipe, one CTA tile covering ALL rows:
+//   C[M x 64-column tile] (+)= sum_entries A_e[M x K] R_e[K x N],  M = Ni^2 <= 256, K = nab*Ni^2
+// A_e rows are K-contiguous (dense exchange-ordered kernel), row k of R_e lives at
+// B_e + browoff[k].  Every R row is read exactly once per launch.  3-stage cp.async
+// pipeline, 8 warps; warp w owns row tiles {w, w+8, w+16, w+24} x all 8 column tiles.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src_bytes) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem, int src_bytes) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(sa), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+template <bool A16>
+__global__ void __launch_bounds__(256, 1)
+k_tgemm(const GemmItem *__restrict__ items, const GemmEntry *__restrict__ entries) {
+  constexpr int BK = 16, BN = 64, MAXM = 256, STAGES = 3;
+  constexpr int LDA_S = BK + 4, LDB_S = BN + 4;
+  constexpr int A_STAGE = MAXM * LDA_S, B_STAGE = BK * LDB_S;
+  extern __shared__ double sm[];
+  double *As = sm, *Bs = sm + STAGES * A_STAGE;
+  const GemmItem it = items[blockIdx.y];
+  const int bn = blockIdx.x * BN;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lr = lane >> 2, lc = lane & 3;
+  constexpr int Mpad = MAXM;   // rows >= M are zero-filled so that every warp runs the same DMMA sequence
+  const int nkc = (it.K + BK - 1) / BK;
+  const int nsteps = (it.ent1 - it.ent0) * nkc;
+
+  double acc[4][8][2];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  auto issue = [&](int step, int stage) {
+    const GemmEntry e = entries[it.ent0 + step / nkc];
+    const int kc = (step % nkc) * BK;
+    double *as = As + stage * A_STAGE, *bs = Bs + stage * B_STAGE;
+    if (A16) {
+      // A tile: Mpad rows x 16 doubles = 8 x 16-byte chunks per row
+      for (int idx = tid; idx < Mpad * 8; idx += 256) {
+        const int m = idx >> 3, ch = idx & 7, k = kc + ch * 2;
+        int bytes = 0;
+        if (m < it.M && k < it.K) bytes = (k + 1 < it.K) ? 16 : 8;
+        const double *src = e.A + (int64_t)(m < it.M ? m : 0) * e.lda + (k < it.K ? k : 0);
+        cp_async16(as + m * LDA_S + ch * 2, src, bytes);
+      }
+    } else {
+      for (int idx = tid; idx < Mpad * 16; idx += 256) {
+        const int m = idx >> 4, kk = idx & 15, k = kc + kk;
+        const int bytes = (m < it.M && k < it.K) ? 8 : 0;
+        const double *src = e.A + (int64_t)(m < it.M ? m : 0) * e.lda + (k < it.K ? k : 0);
+        cp_async8(as + m * LDA_S + kk, src, bytes);
+      }
+    }
+    // B tile: 16 rows x 64 doubles = 32 x 16-byte chunks per row
+    for (int idx = tid; idx < BK * 32; idx += 256) {
+      const int kk = idx >> 5, ch = idx & 31, k = kc + kk;
+      const int bytes = (k < it.K) ? 16 : 0;
+      const double *src = e.B + (k < it.K ? it.browoff[k] : 0) + bn + ch * 2;
+      cp_async16(bs + kk * LDB_S + ch * 2, src, bytes);
+    }
+  };
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; s++) {
+    if (s < nsteps) issue(s, s);
+    cp_async_commit();
+  }
+  for (int step = 0; step < nsteps; step++) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      const int nxt = step + STAGES - 1;
+      if (nxt < nsteps) issue(nxt, nxt % STAGES);
+      cp_async_commit();
+    }
+    const double *as = As + (step % STAGES) * A_STAGE, *bs = Bs + (step % STAGES) * B_STAGE;
+#pragma unroll
+    for (int kk = 0; kk < BK; kk += 4) {
+      double bf[8], af[4];
+#pragma unroll
+      for (int j = 0; j < 8; j++) bf[j] = bs[(kk + lc) * LDB_S + j * 8 + lr];
+#pragma unroll
+      for (int i = 0; i < 4; i++) af[i] = as[((warp + i * 8) * 8 + lr) * LDA_S + kk + lc];
+      // all four row tiles unconditionally (rows >= M are zero-filled): no divergence around the DMMAs
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+  }
+  cp_async_wait<0>();
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int m = (warp + i * 8) * 8 + lr;
+    if (m >= it.M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      double *c = it.C + (int64_t)m * it.ldc + bn + j * 8 + 2 * lc;
+      double2 v;
+      v.x = it.alpha * acc[i][j][0];
+      v.y = it.alpha * acc[i][j][1];
+      if (it.accumulate) {
+        const double2 o = *reinterpret_cast<const double2 *>(c);
+        v.x += o.x;
+        v.y += o.y;
+      }
+      *reinterpret_cast<double2 *>(c) = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Exchange unpack: dense K = - sum over element-pair blocks, boundary removal,
 // optional +-m mirror (mirror_op maps an output sector pair to the pair that
 // was actually computed).
@@ -439,7 +691,8 @@ struct UnpackDev {
   const int64_t *ep_off;  // [Nel*Nel] offset of element-pair block inside one output pair's accumulator
   const int *ang_sec;     // [Nang] sector of angular function
   const int *ang_pos;     // [Nang] position inside the sector
-  int64_t op_stride;      // accumulator stride per output pair
+  int64_t op_stride;      // accumulator stride per (output pair, partial)
+  int S;                  // partial accumulators per output pair (K-split of the in-element GEMM)
 };
 
 __global__ void k_unpack_K(BasisDev b, UnpackDev u, const double *__restrict__ Kacc, double *__restrict__ K, int64_t ld) {
@@ -454,14 +707,15 @@ __global__ void k_unpack_K(BasisDev b, UnpackDev u, const double *__restrict__ K
     const int r = idx % nj + sj, c = idx / nj + sk;
     double s = 0.0;
     if (src >= 0) {
-      const double *acc = Kacc + (int64_t)src * u.op_stride;
       for (int ei = 0; ei < b.Nel; ei++) {
         const int ri = r - b.efirst[ei];
         if (ri < 0 || ri >= b.en[ei]) continue;
         for (int ej = 0; ej < b.Nel; ej++) {
           const int rk = c - b.efirst[ej];
           if (rk < 0 || rk >= b.en[ej]) continue;
-          s += acc[u.ep_off[ei * b.Nel + ej] + (int64_t)(ri * b.en[ej] + rk) * b.NB + blk];
+          const double *acc = Kacc + (int64_t)src * u.S * u.op_stride + u.ep_off[ei * b.Nel + ej] +
+                              (int64_t)(ri * b.en[ej] + rk) * b.NB + blk;
+          for (int p = 0; p < u.S; p++) s += acc[(int64_t)p * u.op_stride];
         }
       }
     }
