@@ -61,6 +61,7 @@ struct Engine::Impl {
   BasisTables t;   // host copy (without the big factor arrays after upload)
   // sector structure
   int ns = 0, NP = 0, NB = 0, NT = 0, NL = 0, nab = 1, Npix = 0;
+  bool parity = false;              // sector positions ordered by l-parity class (halves the fold)
   std::vector<int> sec_m, sec_n, sec_ang, ang_sec, ang_pos, ang_off, ang_skip;
   std::vector<int> sec_lmin, sec_lmax;
   int mmin = 0, mmax = 0, nM = 0;   // M = m_a - m_b range: -(mmax-mmin) .. (mmax-mmin)
@@ -124,6 +125,15 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
   if (!s.NT) throw std::runtime_error("Engine: more than 64 angular functions per m sector not supported");
   s.NP = s.NT * 8;
   s.NB = s.NP * s.NP;
+  // l-parity ordering: even-l functions in positions [0, NP/2), odd-l in [NP/2, NP), if both
+  // classes of every sector fit into half of the padded size
+  s.parity = (s.NT % 2 == 0);
+  if (s.parity)
+    for (auto &kv : bym) {
+      int cnt[2] = {0, 0};
+      for (int a : kv.second) cnt[t.lval[a] & 1]++;
+      if (std::max(cnt[0], cnt[1]) > s.NP / 2) s.parity = false;
+    }
   s.ang_sec.assign(na, 0);
   s.ang_pos.assign(na, 0);
   s.sec_ang.assign((size_t)s.ns * s.NP, -1);
@@ -132,13 +142,15 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
     for (auto &kv : bym) {
       s.sec_m.push_back(kv.first);
       s.sec_n.push_back((int)kv.second.size());
-      int lmn = 1 << 30, lmx = 0;
+      int lmn = 1 << 30, lmx = 0, cnt[2] = {0, 0};
       for (size_t k = 0; k < kv.second.size(); k++) {
-        s.sec_ang[(size_t)si * s.NP + k] = kv.second[k];
-        s.ang_sec[kv.second[k]] = si;
-        s.ang_pos[kv.second[k]] = (int)k;
-        lmn = std::min(lmn, t.lval[kv.second[k]]);
-        lmx = std::max(lmx, t.lval[kv.second[k]]);
+        const int a = kv.second[k], cls = t.lval[a] & 1;
+        const int pos = s.parity ? cls * (s.NP / 2) + cnt[cls]++ : (int)k;
+        s.sec_ang[(size_t)si * s.NP + pos] = a;
+        s.ang_sec[a] = si;
+        s.ang_pos[a] = pos;
+        lmn = std::min(lmn, t.lval[a]);
+        lmx = std::max(lmx, t.lval[a]);
       }
       s.sec_lmin.push_back(lmn);
       s.sec_lmax.push_back(lmx);
@@ -175,9 +187,11 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
         for (int L = std::abs(M); L < s.NL; L++) {
           if (t.channel(L, std::abs(M)) < 0) continue;
           bool any = false;
-          for (int ia = 0; ia < s.sec_n[sa]; ia++)
-            for (int ib = 0; ib < s.sec_n[sb]; ib++) {
-              const int la = t.lval[s.sec_ang[(size_t)sa * s.NP + ia]], lb = t.lval[s.sec_ang[(size_t)sb * s.NP + ib]];
+          for (int ia = 0; ia < s.NP; ia++)
+            for (int ib = 0; ib < s.NP; ib++) {
+              const int anga = s.sec_ang[(size_t)sa * s.NP + ia], angb = s.sec_ang[(size_t)sb * s.NP + ib];
+              if (anga < 0 || angb < 0) continue;
+              const int la = t.lval[anga], lb = t.lval[angb];
               if (L < std::max(std::abs(la - lb) - t.Lext, std::abs(M)) || L > la + lb + t.Lext) continue;
               double *dst = &G[(((size_t)sp * s.NL + L) * t.nch) * s.NB + (size_t)ia * s.NP + ib];
               if (t.kind == BasisKind::Atomic) {
@@ -355,19 +369,19 @@ Engine::~Engine() {
 
 namespace {
 
-template <int NT, int NCH>
+template <int NT, int NCH, bool PAR>
 void launch_fold_t(const dev::BasisDev &bd, const dev::FoldTask *tasks, int ntasks, const double *G, const double *Ppix,
                    double *R, cudaStream_t st) {
   constexpr int NP = NT * 8, LD = NP + 4;
   static bool attr_set = false;
   if (!attr_set) {
-    CK(cudaFuncSetAttribute(dev::k_fold<NT, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(dev::k_fold<NT, NCH, PAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
   const size_t gbytes = (size_t)2 * NCH * NP * LD * sizeof(double);
-  const size_t slot = (size_t)(1 + NCH) * NP * LD * sizeof(double);
-  // pixel slots per group: fill ~100 KB, at least enough items for 8 warps
-  int PB = (int)std::max<size_t>(1, std::min<size_t>((100 * 1024 - gbytes) / slot, 64));
+  const size_t slot = (size_t)(2 + NCH) * NP * LD * sizeof(double);   // 2 P buffers + NCH Y tiles per pixel slot
+  // pixel slots per group: keep two CTAs per SM (<= ~110 KB each), enough items for 8 warps
+  int PB = (int)std::max<size_t>(1, std::min<size_t>((110 * 1024 - gbytes) / slot, 64));
   PB = std::min(PB, std::max(1, 32 / (NT * NCH)) * 2);
   PB = std::max(PB, 1);
   const size_t smem = gbytes + PB * slot;
@@ -376,29 +390,31 @@ void launch_fold_t(const dev::BasisDev &bd, const dev::FoldTask *tasks, int ntas
   ppc = std::min(ppc, std::max(PB * 8, 64));
   ppc = round_up(std::min(ppc, bd.Npix), PB);
   const dim3 grid((bd.Npix + ppc - 1) / ppc, ntasks);
-  dev::k_fold<NT, NCH><<<grid, 256, smem, st>>>(bd, tasks, G, Ppix, R, ppc, PB);
+  dev::k_fold<NT, NCH, PAR><<<grid, 256, smem, st>>>(bd, tasks, G, Ppix, R, ppc, PB);
   CK(cudaGetLastError());
 }
 
-void launch_fold(int NT, int nch, const dev::BasisDev &bd, const dev::FoldTask *tasks, int ntasks, const double *G,
-                 const double *Ppix, double *R, cudaStream_t st) {
-#define HFQ_FOLD_CASE(nt)                                                         \
-  case nt:                                                                        \
-    if (nch == 1)                                                                 \
-      launch_fold_t<nt, 1>(bd, tasks, ntasks, G, Ppix, R, st);                    \
-    else                                                                          \
-      launch_fold_t<nt, 2>(bd, tasks, ntasks, G, Ppix, R, st);                    \
-    break;
-  switch (NT) {
-    HFQ_FOLD_CASE(1)
-    HFQ_FOLD_CASE(2)
-    HFQ_FOLD_CASE(3)
-    HFQ_FOLD_CASE(4)
-    HFQ_FOLD_CASE(6)
-    HFQ_FOLD_CASE(8)
-    default:
-      throw std::runtime_error("fold: unsupported sector size");
+void launch_fold(int NT, int nch, bool par, const dev::BasisDev &bd, const dev::FoldTask *tasks, int ntasks,
+                 const double *G, const double *Ppix, double *R, cudaStream_t st) {
+#define HFQ_FOLD_CASE(nt, parity)                                                \
+  if (NT == nt && par == parity) {                                               \
+    if (nch == 1)                                                                \
+      launch_fold_t<nt, 1, parity>(bd, tasks, ntasks, G, Ppix, R, st);           \
+    else                                                                         \
+      launch_fold_t<nt, 2, parity>(bd, tasks, ntasks, G, Ppix, R, st);           \
+    return;                                                                      \
   }
+  HFQ_FOLD_CASE(1, false)
+  HFQ_FOLD_CASE(2, false)
+  HFQ_FOLD_CASE(3, false)
+  HFQ_FOLD_CASE(4, false)
+  HFQ_FOLD_CASE(6, false)
+  HFQ_FOLD_CASE(8, false)
+  HFQ_FOLD_CASE(2, true)
+  HFQ_FOLD_CASE(4, true)
+  HFQ_FOLD_CASE(6, true)
+  HFQ_FOLD_CASE(8, true)
+  throw std::runtime_error("fold: unsupported sector size");
 #undef HFQ_FOLD_CASE
 }
 
@@ -656,7 +672,7 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
     up(s.d_oentries, oentries);
     CK(cudaStreamSynchronize(st));  // host vectors go out of scope below
     CK(cudaEventRecord(s.ev[2], st));
-    launch_fold(s.NT, t.nch, s.bd, s.d_tasks.p, (int)tasks.size(), s.d_G.p, s.d_Ppix.p, s.d_R.p, st);
+    launch_fold(s.NT, t.nch, s.parity, s.bd, s.d_tasks.p, (int)tasks.size(), s.d_G.p, s.d_Ppix.p, s.d_R.p, st);
     CK(cudaEventRecord(s.ev[3], st));
     {
       // in-element exchange: one CTA tile covers all Ni^2 rows (R rows are read once)

@@ -62,15 +62,14 @@ __global__ void k_pack(BasisDev b, const double *__restrict__ P, int64_t ld, con
   const int c = blockIdx.x, sp = splist[blockIdx.y];
   const int sa = sp / b.ns, sb = sp % b.ns;
   double *dst = Ppix + (int64_t)sp * b.Npix * b.NB;
-  const int na = b.sec_n[sa], nb = b.sec_n[sb];
-  for (int ib = 0; ib < nb; ib++) {
+  for (int ib = 0; ib < b.NP; ib++) {   // sector positions may have gaps (parity-class ordering)
     const int angb = b.sec_ang[sb * b.NP + ib];
-    if (c < b.ang_skip[angb]) continue;
+    if (angb < 0 || c < b.ang_skip[angb]) continue;
     const int64_t col = b.ang_off[angb] + c - b.ang_skip[angb];
-    for (int idx = threadIdx.x; idx < na * b.Nrad; idx += blockDim.x) {
+    for (int idx = threadIdx.x; idx < b.NP * b.Nrad; idx += blockDim.x) {
       const int ia = idx / b.Nrad, r = idx % b.Nrad;
       const int anga = b.sec_ang[sa * b.NP + ia];
-      if (r < b.ang_skip[anga]) continue;
+      if (anga < 0 || r < b.ang_skip[anga]) continue;
       const double v = P[b.ang_off[anga] + r - b.ang_skip[anga] + col * ld];
       dst[((int64_t)r * b.Nrad + c) * b.NB + ia * b.NP + ib] = v;
     }
@@ -89,19 +88,49 @@ struct FoldTask {
   double fac;          // prefactor incl. (-1)^M
 };
 
-// NT = NP/8.  Shared memory: Gj[NCH][NP][LD] Gk[NCH][NP][LD] then per pixel slot
-// P[NP][LD] Yt[NCH][NP][LD], LD = NP+4 (conflict-free DMMA fragment reads).
-template <int NT, int NCH>
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src_bytes) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem, int src_bytes) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(sa), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// NT = NP/8.  Shared memory: Gj[NCH][NP][LD] Gk[NCH][NP][LD], P[2][PB][NP][LD] (cp.async double
+// buffer), Yt[PB][NCH][NP][LD]; LD = NP+4 (conflict-free DMMA fragment reads).
+// PAR: the angular functions of a sector are ordered by l-parity class (first half / second
+// half of the NP positions).  A coupling coefficient is non-zero only if l_j + l_i + L is even,
+// so every 8-row tile couples to ONE parity class of the contracted index: both contractions
+// run over NP/2 instead of NP.
+template <int NT, int NCH, bool PAR>
 __global__ void __launch_bounds__(256)
 k_fold(BasisDev b, const FoldTask *__restrict__ tasks, const double *__restrict__ G, const double *__restrict__ Ppix,
        double *__restrict__ R, int pix_per_cta, int PB) {
-  constexpr int NP = NT * 8, LD = NP + 4, NAB = NCH * NCH;
+  constexpr int NP = NT * 8, LD = NP + 4, NAB = NCH * NCH, NPH = NP / 2, NTH = NT / 2;
   extern __shared__ double sm[];
   const FoldTask t = tasks[blockIdx.y];
-  double *sGj = sm, *sGk = sGj + NCH * NP * LD, *sSlots = sGk + NCH * NP * LD;
-  const int slot_sz = (1 + NCH) * NP * LD;
+  double *sGj = sm, *sGk = sGj + NCH * NP * LD, *sP = sGk + NCH * NP * LD;
+  double *sY = sP + 2 * PB * NP * LD;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
   const int64_t gstride = (int64_t)NP * NP;
+  const int pix0 = blockIdx.x * pix_per_cta;
+  const int pix1 = min(pix0 + pix_per_cta, b.Npix);
+  const double *Psrc = Ppix + (int64_t)t.spp * b.Npix * gstride;
+  double *Rdst = R + (int64_t)t.rslot * NAB * b.Npix * gstride;
+  auto prefetch = [&](int pg, int buf) {
+    const int npx = min(PB, pix1 - pg);
+    if (npx <= 0) return;
+    for (int idx = tid; idx < npx * NP * (NP / 2); idx += blockDim.x) {
+      const int s = idx / (NP * (NP / 2)), rem = idx % (NP * (NP / 2)), r = rem / (NP / 2), c2 = rem % (NP / 2);
+      cp_async16(sP + ((buf * PB + s) * NP + r) * LD + 2 * c2, Psrc + (int64_t)(pg + s) * gstride + r * NP + 2 * c2, 16);
+    }
+  };
+  prefetch(pix0, 0);
+  cp_async_commit();
   {
     const double *gj = G + ((int64_t)t.spj * b.NL + t.L) * NCH * gstride;
     const double *gk = G + ((int64_t)t.spk * b.NL + t.L) * NCH * gstride;
@@ -111,38 +140,37 @@ k_fold(BasisDev b, const FoldTask *__restrict__ tasks, const double *__restrict_
       sGk[(ch * NP + r) * LD + c] = gk[idx];
     }
   }
-  const int pix0 = blockIdx.x * pix_per_cta;
-  const int pix1 = min(pix0 + pix_per_cta, b.Npix);
-  const double *Psrc = Ppix + (int64_t)t.spp * b.Npix * gstride;
-  double *Rdst = R + (int64_t)t.rslot * NAB * b.Npix * gstride;
   const int lr = lane >> 2, lc = lane & 3;
-  for (int pg = pix0; pg < pix1; pg += PB) {
+  const int Lpar = t.L & 1;
+  int buf = 0;
+  for (int pg = pix0; pg < pix1; pg += PB, buf ^= 1) {
     const int npx = min(PB, pix1 - pg);
-    __syncthreads();  // previous group's stage 2 is done with the slots (and G is loaded)
-    for (int idx = tid; idx < npx * NP * NP; idx += blockDim.x) {
-      const int s = idx / (NP * NP), rem = idx % (NP * NP), r = rem / NP, c = rem % NP;
-      sSlots[s * slot_sz + r * LD + c] = Psrc[(int64_t)(pg + s) * gstride + rem];
-    }
-    __syncthreads();
+    cp_async_wait<0>();
+    __syncthreads();  // P(pg) landed; previous group's stage 2 no longer reads sY; G is loaded
+    prefetch(pg + PB, buf ^ 1);
+    cp_async_commit();
     // stage 1: Yt_b[k][i] = sum_l Gk_b[k][l] P[i][l]   items: (slot, b, row tile of k)
     for (int item = warp; item < npx * NCH * NT; item += nwarp) {
       const int s = item / (NCH * NT), rem = item % (NCH * NT), bb = rem / NT, rt = rem % NT;
-      const double *A = sGk + (bb * NP + rt * 8 + lr) * LD + lc;
-      const double *B = sSlots + s * slot_sz + lr * LD + lc;
+      const int k0 = PAR ? (((rt / NTH) ^ Lpar) * NPH) : 0;
+      const double *A = sGk + (bb * NP + rt * 8 + lr) * LD + lc + k0;
+      const double *B = sP + ((buf * PB + s) * NP + lr) * LD + lc + k0;
       double c[NT][2];
 #pragma unroll
       for (int n = 0; n < NT; n++) c[n][0] = c[n][1] = 0.0;
 #pragma unroll 2
-      for (int kk = 0; kk < NP; kk += 4) {
+      for (int kk = 0; kk < (PAR ? NPH : NP); kk += 4) {
         const double a = A[kk];
 #pragma unroll
         for (int n = 0; n < NT; n++) dmma(c[n][0], c[n][1], a, B[n * 8 * LD + kk]);
       }
-      double *Y = sSlots + s * slot_sz + (1 + bb) * NP * LD + (rt * 8 + lr) * LD + 2 * lc;
+      double *Y = sY + ((s * NCH + bb) * NP + rt * 8 + lr) * LD + 2 * lc;
 #pragma unroll
       for (int n = 0; n < NT; n++) {
-        Y[n * 8] = c[n][0];
-        Y[n * 8 + 1] = c[n][1];
+        double2 v;
+        v.x = c[n][0];
+        v.y = c[n][1];
+        *reinterpret_cast<double2 *>(Y + n * 8) = v;
       }
     }
     __syncthreads();
@@ -150,13 +178,14 @@ k_fold(BasisDev b, const FoldTask *__restrict__ tasks, const double *__restrict_
     for (int item = warp; item < npx * NAB * NT; item += nwarp) {
       const int s = item / (NAB * NT), rem = item % (NAB * NT), ab = rem / NT, rt = rem % NT;
       const int aa = ab / NCH, bb = ab % NCH;
-      const double *A = sGj + (aa * NP + rt * 8 + lr) * LD + lc;
-      const double *B = sSlots + s * slot_sz + (1 + bb) * NP * LD + lr * LD + lc;
+      const int k0 = PAR ? (((rt / NTH) ^ Lpar) * NPH) : 0;
+      const double *A = sGj + (aa * NP + rt * 8 + lr) * LD + lc + k0;
+      const double *B = sY + ((s * NCH + bb) * NP + lr) * LD + lc + k0;
       double c[NT][2];
 #pragma unroll
       for (int n = 0; n < NT; n++) c[n][0] = c[n][1] = 0.0;
 #pragma unroll 2
-      for (int kk = 0; kk < NP; kk += 4) {
+      for (int kk = 0; kk < (PAR ? NPH : NP); kk += 4) {
         const double a = A[kk];
 #pragma unroll
         for (int n = 0; n < NT; n++) dmma(c[n][0], c[n][1], a, B[n * 8 * LD + kk]);
@@ -567,18 +596,6 @@ k_offdiag_mma(BasisDev b, const OffItem *__restrict__ items, const OffEntry *__r
 // B_e + browoff[k].  Every R row is read exactly once per launch.  3-stage cp.async
 // pipeline, 8 warps; warp w owns row tiles {w, w+8, w+16, w+24} x all 8 column tiles.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src_bytes) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(src_bytes));
-}
-__device__ __forceinline__ void cp_async8(void *smem, const void *gmem, int src_bytes) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(sa), "l"(gmem), "r"(src_bytes));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
-
 template <bool A16>
 __global__ void __launch_bounds__(256, 1)
 k_tgemm(const GemmItem *__restrict__ items, const GemmEntry *__restrict__ entries) {
