@@ -25,27 +25,29 @@ sys.path.insert(0, ROOT)
 
 
 def n2_density(T, seed=42):
-    """Synthetic closed-shell N2-like density: 5 doubly-occupied sigma orbitals (m=0) and one
-    doubly-occupied pi orbital in each of m=+1 and m=-1 (same coefficients: +-m symmetric)."""
-    from tests import cases
+    """Synthetic closed-shell density with the N2 ground-state structure: 3 sigma_g (even l) and
+    2 sigma_u (odd l) doubly-occupied orbitals in m=0, one pi_u orbital (odd l) in each of m=+1
+    and m=-1 (same coefficients: +-m symmetric).  Orbitals are seeded random orthonormal vectors
+    inside their (m, l-parity) subspace, like the g/u-symmetric SCF orbitals of a homonuclear
+    diatomic."""
     rng = np.random.default_rng(seed)
     n = T.Nbf
-    mval = T.mval
-    blocks = {}
+    mval, lval = T.mval, T.lval
+    sub = {}
     off = 0
-    for m in mval:
+    for m, l in zip(mval, lval):
         k = T.Nrad - (1 if m != 0 else 0)
-        blocks.setdefault(int(m), []).extend(range(off, off + k))
+        sub.setdefault((int(m), int(l) & 1), []).extend(range(off, off + k))
         off += k
     P = np.zeros((n, n), order="F")
-    occ = {0: 5, 1: 1}
-    for mabs, k in occ.items():
-        idx = np.array(blocks[mabs])
+    for (m, par, k) in ((0, 0, 3), (0, 1, 2), (1, 1, 1)):
+        idx = np.array(sub[(m, par)])
         Q, _ = np.linalg.qr(rng.standard_normal((len(idx), k)))
         blk = 2.0 * Q @ Q.T
         P[np.ix_(idx, idx)] = blk
-        if mabs:
-            P[np.ix_(np.array(blocks[-mabs]), np.array(blocks[-mabs]))] = blk
+        if m:
+            jdx = np.array(sub[(-m, par)])
+            P[np.ix_(jdx, jdx)] = blk
     return P
 
 
@@ -119,7 +121,7 @@ def main():
     import helfem_b200 as hb
     from helfem_b200 import build as hb_build
     workload = "N2 HF diatomic J+K Fock build, Rbond=2.07, lmax=%d |m|<=%d, nelem=%d x 15-node LIP" % (args.lmax, args.mmax, args.nelem)
-    config = {"workload": workload, "density": "synthetic closed-shell N2 pattern (5 sigma + pi+-), seed 42",
+    config = {"workload": workload, "density": "synthetic closed-shell N2 structure (3 sigma_g + 2 sigma_u + pi_u+-, g/u-symmetric orbitals), seed 42",
               "symmetry": "per-m (reference default --symmetry=1, absm_symmetric off)",
               "l2": "inputs larger than L2 (P/J/K 1.76 GB each, work buffers > 10 GB)",
               "sharding": "exchange output (m_j,m_k) sector pairs round-robin over ranks + one NCCL all-reduce of K; J replicated"}

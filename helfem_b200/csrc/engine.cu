@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <numeric>
@@ -62,6 +63,7 @@ struct Engine::Impl {
   // sector structure
   int ns = 0, NP = 0, NB = 0, NT = 0, NL = 0, nab = 1, Npix = 0;
   bool parity = false;              // sector positions ordered by l-parity class (halves the fold)
+  std::vector<int> sec_cls;
   std::vector<int> sec_m, sec_n, sec_ang, ang_sec, ang_pos, ang_off, ang_skip;
   std::vector<int> sec_lmin, sec_lmax;
   int mmin = 0, mmax = 0, nM = 0;   // M = m_a - m_b range: -(mmax-mmin) .. (mmax-mmin)
@@ -105,10 +107,20 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
     if (t.en[e] > 16) throw std::runtime_error("Engine: more than 16 functions per element not supported");
   s.nab = t.nch * t.nch;
   s.Npix = t.Nrad * t.Nrad;
-  // ---- m sectors, in ascending m
+  // ---- sectors: angular functions grouped by m and, for large expansions, by l-parity.
+  // A coupling coefficient vanishes unless l_j + l_i + L is even, so a (m, parity) sector pair
+  // couples through one L-parity only, and densities of homonuclear molecules (no even-odd l
+  // blocks) are screened at sector granularity exactly as the reference screens them per block.
   const int na = t.Nang();
-  std::map<int, std::vector<int>> bym;
-  for (int a = 0; a < na; a++) bym[t.mval[a]].push_back(a);
+  bool split_parity = false;
+  {
+    std::map<int, int> cnt;
+    for (int a = 0; a < na; a++) cnt[t.mval[a]]++;
+    for (auto &kv : cnt) split_parity |= kv.second > 8;
+    if (const char *env = getenv("HFQ_SECTOR_SPLIT")) split_parity = atoi(env) != 0;
+  }
+  std::map<std::pair<int, int>, std::vector<int>> bym;
+  for (int a = 0; a < na; a++) bym[{t.mval[a], split_parity ? (t.lval[a] & 1) : 0}].push_back(a);
   s.ns = (int)bym.size();
   int nmaxsec = 0;
   for (auto &kv : bym) {
@@ -127,7 +139,7 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
   s.NB = s.NP * s.NP;
   // l-parity ordering: even-l functions in positions [0, NP/2), odd-l in [NP/2, NP), if both
   // classes of every sector fit into half of the padded size
-  s.parity = (s.NT % 2 == 0);
+  s.parity = (s.NT % 2 == 0) && !split_parity;
   if (s.parity)
     for (auto &kv : bym) {
       int cnt[2] = {0, 0};
@@ -140,7 +152,8 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
   {
     int si = 0;
     for (auto &kv : bym) {
-      s.sec_m.push_back(kv.first);
+      s.sec_m.push_back(kv.first.first);
+      s.sec_cls.push_back(kv.first.second);
       s.sec_n.push_back((int)kv.second.size());
       int lmn = 1 << 30, lmx = 0, cnt[2] = {0, 0};
       for (size_t k = 0; k < kv.second.size(); k++) {
@@ -157,8 +170,8 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
       si++;
     }
   }
-  s.mmin = s.sec_m.front();
-  s.mmax = s.sec_m.back();
+  s.mmin = *std::min_element(s.sec_m.begin(), s.sec_m.end());
+  s.mmax = *std::max_element(s.sec_m.begin(), s.sec_m.end());
   s.nM = 2 * (s.mmax - s.mmin) + 1;
   s.ang_off.assign(na, 0);
   s.ang_skip.assign(na, 0);
@@ -543,13 +556,13 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
   }
   if (absm_symmetric_) {
     // K(-mj,-mk) block = K(mj,mk) block (same l positions: sectors +-m hold the same l list)
-    std::map<int, int> sec_of_m;
-    for (int i = 0; i < ns; i++) sec_of_m[s.sec_m[i]] = i;
+    std::map<std::pair<int, int>, int> sec_of_m;
+    for (int i = 0; i < ns; i++) sec_of_m[{s.sec_m[i], s.sec_cls[i]}] = i;
     for (int sj = 0; sj < ns; sj++)
       for (int sk = 0; sk < ns; sk++) {
         const int mj = s.sec_m[sj], mk = s.sec_m[sk];
         if (mj >= 0 || mk >= 0) continue;
-        auto pj = sec_of_m.find(-mj), pk = sec_of_m.find(-mk);
+        auto pj = sec_of_m.find({-mj, s.sec_cls[sj]}), pk = sec_of_m.find({-mk, s.sec_cls[sk]});
         if (pj == sec_of_m.end() || pk == sec_of_m.end()) continue;
         op_src[(size_t)sj * ns + sk] = op_src[(size_t)pj->second * ns + pk->second];
       }
