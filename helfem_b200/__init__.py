@@ -38,7 +38,7 @@ EXPORTED_SYMBOLS = [
     "hfq_last_error", "hfq_tables_atomic", "hfq_tables_diatomic", "hfq_tables_from_arrays", "hfq_tables_get_info",
     "hfq_tables_get_ints", "hfq_tables_get_doubles", "hfq_tables_get_block", "hfq_tables_one_electron",
     "hfq_tables_destroy", "hfq_create", "hfq_destroy", "hfq_nbf", "hfq_set_absm_symmetric", "hfq_coulomb",
-    "hfq_exchange", "hfq_coulomb_device", "hfq_exchange_device", "hfq_last_timings",
+    "hfq_exchange", "hfq_coulomb_device", "hfq_exchange_device", "hfq_last_timings", "hfq_exchange_output_pattern",
 ]
 
 
@@ -73,6 +73,7 @@ def lib():
     L.hfq_coulomb_device.argtypes = [vp, vp, i64, vp, i64, vp]
     L.hfq_exchange_device.argtypes = [vp, vp, i64, vp, i64, ci, ci, vp]
     L.hfq_last_timings.argtypes = [vp, vp, ci]
+    L.hfq_exchange_output_pattern.argtypes = [vp, vp, i64, vp, i64]
     _lib = L
     return L
 
@@ -260,6 +261,15 @@ class _BasisBase:
     def exchange_device(self, dP_ptr, dK_ptr, shard=0, nshards=1, stream=None):
         n = self.Nbf()
         _check(lib().hfq_exchange_device(self._context(), dP_ptr, n, dK_ptr, n, shard, nshards, stream))
+
+    def exchange_output_pattern(self):
+        """(bf_sector[Nbf], [(row sector, col sector), ...]) of the last exchange result."""
+        n = self.Nbf()
+        bs = np.zeros(n, dtype=np.int32)
+        cap = 4 * self.tables.Nang ** 2 + 16
+        pr = np.zeros(cap, dtype=np.int32)
+        k = _check(lib().hfq_exchange_output_pattern(self._context(), bs.ctypes.data, n, pr.ctypes.data, cap))
+        return bs, [(int(pr[2 * i]), int(pr[2 * i + 1])) for i in range(k)]
 
     def last_timings(self):
         out = np.zeros(17)

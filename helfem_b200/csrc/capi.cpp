@@ -282,6 +282,17 @@ int hfq_exchange_device(hfq_ctx *ctx, const double *dP, int64_t ldP, double *dK,
   });
 }
 
+int hfq_exchange_output_pattern(const hfq_ctx *ctx, int *bf_sector, int64_t cap_bf, int *pairs, int64_t cap_pairs) {
+  if (!ctx || !bf_sector || !pairs) return fail(HFQ_ERR_INVALID, "hfq_exchange_output_pattern: null argument");
+  std::vector<int> bs, pr;
+  ctx->eng->output_pattern(bs, pr);
+  if ((int64_t)bs.size() > cap_bf || (int64_t)pr.size() > cap_pairs)
+    return fail(HFQ_ERR_INVALID, "hfq_exchange_output_pattern: buffer too small");
+  std::memcpy(bf_sector, bs.data(), bs.size() * sizeof(int));
+  std::memcpy(pairs, pr.data(), pr.size() * sizeof(int));
+  return (int)(pr.size() / 2);
+}
+
 int hfq_last_timings(const hfq_ctx *ctx, double *out, int n) {
   if (!ctx || !out) return fail(HFQ_ERR_INVALID, "hfq_last_timings: null argument");
   const hfq::EngineTimings &t = ctx->eng->timings();

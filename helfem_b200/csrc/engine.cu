@@ -374,11 +374,6 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
   CK(cudaFuncSetAttribute(dev::k_tgemm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 }
 
-Engine::~Engine() {
-  if (p_)
-    for (auto &e : p_->ev) cudaEventDestroy(e);
-  if (stream_) cudaStreamDestroy(stream_);
-}
 
 namespace {
 
@@ -446,6 +441,30 @@ void launch_gemm(const dev::GemmItem *items, const dev::GemmEntry *entries, int 
 // ---------------------------------------------------------------------------
 // exchange
 // ---------------------------------------------------------------------------
+// A plan is everything about an exchange call that depends only on WHICH sector pairs of the
+// density are non-zero (plus sharding and the +-m flag): the task list, its split into batches
+// and the device-resident kernel descriptors.  SCF iterations reuse it.
+struct ExchangeBatch {
+  DevBuf<dev::FoldTask> tasks;
+  DevBuf<dev::GemmItem> gitems;
+  DevBuf<dev::GemmEntry> gentries;
+  DevBuf<dev::OffItem> oitems;
+  DevBuf<dev::OffEntry> oentries;
+  int ntasks = 0, ngitems = 0, noitems = 0;
+};
+struct ExchangePlan {
+  std::string key;
+  std::vector<std::unique_ptr<ExchangeBatch>> batches;
+  std::vector<int> splist, op_src;
+  int nactive = 0, S = 1;
+  double fl_fold = 0, fl_tg = 0, fl_off = 0, al_fold = 0, al_tg = 0, al_off = 0;
+  const double *R_base = nullptr, *K_base = nullptr;   // buffers the descriptors point into
+};
+
+struct Engine::PlanCache {
+  std::vector<std::unique_ptr<ExchangePlan>> plans;
+};
+
 void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK, int shard, int nshards,
                           cudaStream_t st) {
   Impl &s = *p_;
@@ -453,6 +472,7 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
   CK(cudaSetDevice(device_));
   const int na = t.Nang(), ns = s.ns;
   tm_ = EngineTimings();
+  if (!plans_) plans_.reset(new PlanCache);
   CK(cudaEventRecord(s.ev[0], st));
   // 1. which angular blocks of P carry density (reference: block norm >= 10 eps)
   dev::k_block_norms<<<dim3(na, na), 128, 0, st>>>(s.bd, dP, ldP, s.d_norms.p);
@@ -460,35 +480,37 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
   std::vector<double> norms((size_t)na * na);
   CK(cudaMemcpyAsync(norms.data(), s.d_norms.p, norms.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  const double thr = 10.0 * 2.220446049250313e-16;
-  std::vector<char> sp_nz((size_t)ns * ns, 0);
+  const double thr2 = std::pow(10.0 * 2.220446049250313e-16, 2);
+  std::string key((size_t)ns * ns + 3, '0');
   for (int a = 0; a < na; a++)
     for (int b = 0; b < na; b++)
-      if (std::sqrt(norms[(size_t)a * na + b]) >= thr) sp_nz[(size_t)s.ang_sec[a] * ns + s.ang_sec[b]] = 1;
-  std::vector<int> splist;
-  for (int sp = 0; sp < ns * ns; sp++)
-    if (sp_nz[sp]) splist.push_back(sp);
-  // 2. pack the active sector pairs
-  if (!splist.empty()) {
-    CK(cudaMemcpyAsync(s.d_splist.p, splist.data(), splist.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-    for (int sp : splist)
-      CK(cudaMemsetAsync(s.d_Ppix.p + (size_t)sp * s.Npix * s.NB, 0, (size_t)s.Npix * s.NB * sizeof(double), st));
-    dev::k_pack<<<dim3(t.Nrad, (unsigned)splist.size()), 256, 0, st>>>(s.bd, dP, ldP, s.d_splist.p, s.d_Ppix.p);
-    CK(cudaGetLastError());
-  }
-  CK(cudaEventRecord(s.ev[1], st));
-  // 3. task list: output pair (sj,sk) <- density pair (si,sl) with mj-mi == mk-ml, every coupled L
-  struct OpWork {
-    int op;
-    std::vector<dev::FoldTask> tasks;
-    std::vector<int> ilm;
-    std::vector<double> alg_fold;  // unpadded flops of the fold per task
-  };
-  std::vector<OpWork> work;
-  std::vector<int> op_src((size_t)ns * ns, -1);
-  {
-    // Sharding: tasks (output pair, density pair, L) are dealt round-robin to the shards, so
-    // every rank builds a partial sum of every output block and the all-reduce completes it.
+      if (norms[(size_t)a * na + b] >= thr2) key[(size_t)s.ang_sec[a] * ns + s.ang_sec[b]] = '1';
+  key[(size_t)ns * ns] = absm_symmetric_ ? 'S' : 'N';
+  key[(size_t)ns * ns + 1] = (char)('0' + shard);
+  key[(size_t)ns * ns + 2] = (char)('0' + nshards);
+  ExchangePlan *plan = nullptr;
+  for (auto &pl : plans_->plans)
+    if (pl->key == key && pl->R_base == s.d_R.p && pl->K_base == s.d_Kacc.p) plan = pl.get();
+  if (!plan) {
+    // ---------------- build the plan ----------------
+    auto np = std::make_unique<ExchangePlan>();
+    np->key = key;
+    std::vector<char> sp_nz((size_t)ns * ns, 0);
+    for (int sp = 0; sp < ns * ns; sp++) {
+      sp_nz[sp] = key[sp] == '1';
+      if (sp_nz[sp]) np->splist.push_back(sp);
+    }
+    struct OpWork {
+      int op;
+      std::vector<dev::FoldTask> tasks;
+      std::vector<int> ilm;
+      std::vector<double> alg_fold;  // unpadded flops of the fold per task
+    };
+    std::vector<OpWork> work;
+    np->op_src.assign((size_t)ns * ns, -1);
+    // Task list: output pair (sj,sk) <- density pair (si,sl) with mj-mi == mk-ml, every coupled L.
+    // Sharding: tasks are dealt round-robin to the shards, so every rank builds a partial sum of
+    // every output block and the all-reduce completes it.
     long taskcount = 0;
     for (int sj = 0; sj < ns; sj++)
       for (int sk = 0; sk < ns; sk++) {
@@ -518,194 +540,211 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
               ft.fac = t.pref[ilm] * ((t.sign_by_M && (M & 1)) ? -1.0 : 1.0);
               w.tasks.push_back(ft);
               w.ilm.push_back(ilm);
-              {
-                const double nj = s.sec_n[sj], nk = s.sec_n[sk], ni = s.sec_n[si], nl = s.sec_n[sl];
-                w.alg_fold.push_back(2.0 * s.Npix * (ni * nl * nk * t.nch + nj * ni * nk * s.nab));
-              }
+              const double nj = s.sec_n[sj], nk = s.sec_n[sk], ni = s.sec_n[si], nl = s.sec_n[sl];
+              w.alg_fold.push_back(2.0 * s.Npix * (ni * nl * nk * t.nch + nj * ni * nk * s.nab));
             }
           }
-        if (w.tasks.empty()) continue;
-        work.push_back(std::move(w));
+        if (!w.tasks.empty()) work.push_back(std::move(w));
       }
-  }
-  // 4. buffers
-  const size_t slot_doubles = (size_t)s.nab * s.Npix * s.NB;
-  const int nactive = (int)work.size();
-  size_t total_tasks = 0;
-  for (auto &w : work) total_tasks += w.tasks.size();
-  // K-split of the in-element GEMM: each (output pair, element) item is cut into S chunks of its
-  // task list, each chunk accumulating into its own partial buffer (summed by the unpack kernel),
-  // so that the number of CTAs per launch fills whole waves of the 148 SMs.
-  int S = 1;
-  {
-    const double units = (double)nactive * t.Nel * (s.NB / 64);
-    double best = 0.0;
-    for (int c = 1; c <= 4; c++) {
-      const double u = units * c, eff = u / (std::ceil(u / 148.0) * 148.0);
-      if (eff > best + 0.02) {
-        best = eff;
-        S = c;
-      }
-    }
-  }
-  if (s.d_Kacc.n < (size_t)nactive * S * s.op_stride) s.d_Kacc.alloc((size_t)nactive * S * s.op_stride, &dev_bytes_);
-  for (int a = 0; a < nactive; a++) {
-    op_src[work[a].op] = a;
-    if (S > 1)
-      CK(cudaMemsetAsync(s.d_Kacc.p + ((size_t)a * S + 1) * s.op_stride, 0, (size_t)(S - 1) * s.op_stride * sizeof(double), st));
-  }
-  if (absm_symmetric_) {
-    // K(-mj,-mk) block = K(mj,mk) block (same l positions: sectors +-m hold the same l list)
-    std::map<std::pair<int, int>, int> sec_of_m;
-    for (int i = 0; i < ns; i++) sec_of_m[{s.sec_m[i], s.sec_cls[i]}] = i;
-    for (int sj = 0; sj < ns; sj++)
-      for (int sk = 0; sk < ns; sk++) {
-        const int mj = s.sec_m[sj], mk = s.sec_m[sk];
-        if (mj >= 0 || mk >= 0) continue;
-        auto pj = sec_of_m.find({-mj, s.sec_cls[sj]}), pk = sec_of_m.find({-mk, s.sec_cls[sk]});
-        if (pj == sec_of_m.end() || pk == sec_of_m.end()) continue;
-        op_src[(size_t)sj * ns + sk] = op_src[(size_t)pj->second * ns + pk->second];
-      }
-  }
-  {
-    size_t free_b = 0, total_b = 0;
-    CK(cudaMemGetInfo(&free_b, &total_b));
-    const size_t have = s.d_R.n * sizeof(double);
-    const size_t budget = std::min<size_t>((size_t)48 << 30, (size_t)((free_b + have) * 0.6));
-    size_t want_slots = std::min<size_t>(total_tasks, std::max<size_t>(1, budget / (slot_doubles * sizeof(double))));
-    if (want_slots > s.r_slots) {
-      s.d_R.alloc(want_slots * slot_doubles, &dev_bytes_);
-      s.r_slots = want_slots;
-    }
-  }
-  if (total_tasks && s.r_slots == 0) throw std::runtime_error("Engine: no memory for the exchange work buffer");
-  // 5. batches: every batch takes an equal share of tasks from every active output pair, so each
-  //    launch works on all output pairs at once (grid size independent of the batch count)
-  double fl_fold = 0, fl_tg = 0, fl_off = 0, al_fold = 0, al_tg = 0, al_off = 0;
-  const int nruns = (int)s.run_nL.size();
-  std::vector<size_t> done(work.size(), 0);
-  std::vector<char> started((size_t)work.size() * S, 0);
-  size_t remaining = total_tasks;
-  float ms_fold = 0, ms_tg = 0, ms_off = 0;
-  while (remaining > 0) {
-    std::vector<dev::FoldTask> tasks;
-    std::vector<dev::GemmItem> gitems;
-    std::vector<dev::GemmEntry> gentries;
-    std::vector<dev::OffItem> oitems;
-    std::vector<dev::OffEntry> oentries;
-    // shares: proportional split of the slot budget over the output pairs that still have work
-    size_t open = 0;
-    for (size_t wi = 0; wi < work.size(); wi++) open += done[wi] < work[wi].tasks.size();
-    const size_t share = std::max<size_t>(1, s.r_slots / std::max<size_t>(open, 1));
-    for (size_t wi = 0; wi < work.size() && tasks.size() < s.r_slots; wi++) {
-      OpWork &w = work[wi];
-      const size_t ti = done[wi];
-      size_t take = std::min(w.tasks.size() - ti, std::min(share, s.r_slots - tasks.size()));
-      if (remaining <= s.r_slots) take = w.tasks.size() - ti;   // everything fits: finish
-      take = std::min(take, s.r_slots - tasks.size());
-      if (take == 0) continue;
-      const size_t t0 = tasks.size();
-      for (size_t k = 0; k < take; k++) {
-        dev::FoldTask ft = w.tasks[ti + k];
-        ft.rslot = (int)(t0 + k);
-        tasks.push_back(ft);
-      }
-      // in-element items (tensor-core GEMM against the dense exchange-ordered kernel), S chunks
-      for (int c = 0; c < S; c++) {
-        const size_t k0 = take * c / S, k1 = take * (c + 1) / S;
-        if (k1 == k0) continue;
-        double *acc_base = s.d_Kacc.p + ((size_t)wi * S + c) * s.op_stride;
-        const int acc = started[wi * S + c] ? 1 : 0;
-        started[wi * S + c] = 1;
-        for (int e = 0; e < t.Nel; e++) {
-          const int n = t.en[e];
-          dev::GemmItem gi{};
-          gi.C = acc_base + s.ep_off[(size_t)e * t.Nel + e];
-          gi.browoff = s.d_browoff_T.p + s.browoff_T_first[e];
-          gi.M = n * n;
-          gi.N = s.NB;
-          gi.K = s.nab * n * n;
-          gi.ent0 = (int)gentries.size();
-          for (size_t k = k0; k < k1; k++) {
-            const int ilm = w.ilm[ti + k], r = s.chan_run[ilm];
-            dev::GemmEntry ge;
-            ge.A = s.d_tperm.p + s.tperm_off[(size_t)e * nruns + r] + (int64_t)s.chan_pos[ilm] * s.nab * n * n;
-            ge.lda = s.tperm_lda[(size_t)e * nruns + r];
-            ge.B = s.d_R.p + (t0 + k) * slot_doubles;
-            gentries.push_back(ge);
-          }
-          gi.ent1 = (int)gentries.size();
-          gi.accumulate = acc;
-          gi.ldb = 0;
-          gi.ldc = s.NB;
-          gi.alpha = 1.0;
-          gitems.push_back(gi);
-          fl_tg += 2.0 * gi.M * gi.N * (double)gi.K * (k1 - k0);
-          al_tg += 2.0 * gi.M * (double)s.sec_n[w.op / ns] * s.sec_n[w.op % ns] * (double)gi.K * (k1 - k0);
+    const size_t slot_doubles = (size_t)s.nab * s.Npix * s.NB;
+    const int nactive = (int)work.size();
+    np->nactive = nactive;
+    size_t total_tasks = 0;
+    for (auto &w : work) total_tasks += w.tasks.size();
+    // K-split of the in-element GEMM: each (output pair, element) item is cut into S chunks of its
+    // task list, each chunk accumulating into its own partial buffer (summed by the unpack kernel),
+    // so that the number of CTAs per launch fills whole waves of the 148 SMs.
+    int S = 1;
+    {
+      const double units = (double)nactive * t.Nel * (s.NB / 64);
+      double best = 0.0;
+      for (int c = 1; c <= 4; c++) {
+        const double u = units * c, eff = u / (std::ceil(u / 148.0) * 148.0);
+        if (eff > best + 0.02) {
+          best = eff;
+          S = c;
         }
       }
-      // cross-element items (partial buffer 0)
-      {
-        double *acc_base = s.d_Kacc.p + (size_t)wi * S * s.op_stride;
-        const int acc = ti > 0 ? 1 : 0;
-        const int oe0 = (int)oentries.size();
-        for (size_t k = 0; k < take; k++) oentries.push_back(dev::OffEntry{(int)(t0 + k), w.ilm[ti + k]});
-        for (int ei = 0; ei < t.Nel; ei++)
-          for (int ej = 0; ej < t.Nel; ej++) {
-            if (ei == ej) continue;
-            dev::OffItem oi{};
-            oi.C = acc_base + s.ep_off[(size_t)ei * t.Nel + ej];
-            oi.ei = ei;
-            oi.ej = ej;
-            oi.ent0 = oe0;
-            oi.ent1 = (int)oentries.size();
-            oi.accumulate = acc;
-            oitems.push_back(oi);
-            const double per = 2.0 * t.nch * take *
-                               ((double)t.en[ei] * t.en[ej] * t.nch * t.en[ej] + (double)t.en[ei] * t.en[ej] * t.en[ei]);
-            fl_off += per * s.NB;
-            al_off += per * s.sec_n[w.op / ns] * s.sec_n[w.op % ns];
-          }
-      }
-      fl_fold += 2.0 * (double)take * s.Npix * (double)s.NP * s.NP * s.NP * (t.nch + s.nab);
-      for (size_t k = 0; k < take; k++) al_fold += w.alg_fold[ti + k];
-      done[wi] += take;
-      remaining -= take;
     }
-    if (tasks.empty()) break;
-    // upload descriptors
-    auto up = [&](auto &dbuf, const auto &h) {
-      if (dbuf.n < h.size()) dbuf.alloc(h.size() * 2, &dev_bytes_);
-      if (!h.empty()) CK(cudaMemcpyAsync(dbuf.p, h.data(), h.size() * sizeof(h[0]), cudaMemcpyHostToDevice, st));
-    };
-    up(s.d_tasks, tasks);
-    up(s.d_gitems, gitems);
-    up(s.d_gentries, gentries);
-    up(s.d_oitems, oitems);
-    up(s.d_oentries, oentries);
-    CK(cudaStreamSynchronize(st));  // host vectors go out of scope below
+    np->S = S;
+    if (s.d_Kacc.n < (size_t)nactive * S * s.op_stride) {
+      CK(cudaStreamSynchronize(st));
+      s.d_Kacc.alloc((size_t)nactive * S * s.op_stride, &dev_bytes_);
+    }
+    for (int a = 0; a < nactive; a++) np->op_src[work[a].op] = a;
+    if (absm_symmetric_) {
+      // K(-mj,-mk) block = K(mj,mk) block (sectors +-m of one parity class hold the same l list)
+      std::map<std::pair<int, int>, int> sec_of_m;
+      for (int i = 0; i < ns; i++) sec_of_m[{s.sec_m[i], s.sec_cls[i]}] = i;
+      for (int sj = 0; sj < ns; sj++)
+        for (int sk = 0; sk < ns; sk++) {
+          const int mj = s.sec_m[sj], mk = s.sec_m[sk];
+          if (mj >= 0 || mk >= 0) continue;
+          auto pj = sec_of_m.find({-mj, s.sec_cls[sj]}), pk = sec_of_m.find({-mk, s.sec_cls[sk]});
+          if (pj == sec_of_m.end() || pk == sec_of_m.end()) continue;
+          np->op_src[(size_t)sj * ns + sk] = np->op_src[(size_t)pj->second * ns + pk->second];
+        }
+    }
+    {
+      size_t free_b = 0, total_b = 0;
+      CK(cudaMemGetInfo(&free_b, &total_b));
+      const size_t have = s.d_R.n * sizeof(double);
+      const size_t budget = std::min<size_t>((size_t)48 << 30, (size_t)((free_b + have) * 0.6));
+      size_t want_slots = std::min<size_t>(total_tasks, std::max<size_t>(1, budget / (slot_doubles * sizeof(double))));
+      if (want_slots > s.r_slots) {
+        CK(cudaStreamSynchronize(st));
+        s.d_R.alloc(want_slots * slot_doubles, &dev_bytes_);
+        s.r_slots = want_slots;
+      }
+    }
+    if (total_tasks && s.r_slots == 0) throw std::runtime_error("Engine: no memory for the exchange work buffer");
+    np->R_base = s.d_R.p;
+    np->K_base = s.d_Kacc.p;
+    // Batches: every batch takes an equal share of tasks from every active output pair, so each
+    // launch works on all output pairs at once (grid size independent of the batch count).
+    const int nruns = (int)s.run_nL.size();
+    std::vector<size_t> done(work.size(), 0);
+    std::vector<char> started((size_t)work.size() * S, 0);
+    size_t remaining = total_tasks;
+    while (remaining > 0) {
+      std::vector<dev::FoldTask> tasks;
+      std::vector<dev::GemmItem> gitems;
+      std::vector<dev::GemmEntry> gentries;
+      std::vector<dev::OffItem> oitems;
+      std::vector<dev::OffEntry> oentries;
+      size_t open = 0;
+      for (size_t wi = 0; wi < work.size(); wi++) open += done[wi] < work[wi].tasks.size();
+      const size_t share = std::max<size_t>(1, s.r_slots / std::max<size_t>(open, 1));
+      for (size_t wi = 0; wi < work.size() && tasks.size() < s.r_slots; wi++) {
+        OpWork &w = work[wi];
+        const size_t ti = done[wi];
+        size_t take = std::min(w.tasks.size() - ti, std::min(share, s.r_slots - tasks.size()));
+        if (remaining <= s.r_slots) take = w.tasks.size() - ti;   // everything fits: finish
+        take = std::min(take, s.r_slots - tasks.size());
+        if (take == 0) continue;
+        const size_t t0 = tasks.size();
+        for (size_t k = 0; k < take; k++) {
+          dev::FoldTask ft = w.tasks[ti + k];
+          ft.rslot = (int)(t0 + k);
+          tasks.push_back(ft);
+        }
+        // in-element items (tensor-core GEMM against the dense exchange-ordered kernel), S chunks
+        for (int c = 0; c < S; c++) {
+          const size_t k0 = take * c / S, k1 = take * (c + 1) / S;
+          if (k1 == k0) continue;
+          double *acc_base = s.d_Kacc.p + ((size_t)wi * S + c) * s.op_stride;
+          const int acc = started[wi * S + c] ? 1 : 0;
+          started[wi * S + c] = 1;
+          for (int e = 0; e < t.Nel; e++) {
+            const int n = t.en[e];
+            dev::GemmItem gi{};
+            gi.C = acc_base + s.ep_off[(size_t)e * t.Nel + e];
+            gi.browoff = s.d_browoff_T.p + s.browoff_T_first[e];
+            gi.M = n * n;
+            gi.N = s.NB;
+            gi.K = s.nab * n * n;
+            gi.ent0 = (int)gentries.size();
+            for (size_t k = k0; k < k1; k++) {
+              const int ilm = w.ilm[ti + k], r = s.chan_run[ilm];
+              dev::GemmEntry ge;
+              ge.A = s.d_tperm.p + s.tperm_off[(size_t)e * nruns + r] + (int64_t)s.chan_pos[ilm] * s.nab * n * n;
+              ge.lda = s.tperm_lda[(size_t)e * nruns + r];
+              ge.B = s.d_R.p + (t0 + k) * slot_doubles;
+              gentries.push_back(ge);
+            }
+            gi.ent1 = (int)gentries.size();
+            gi.accumulate = acc;
+            gi.ldb = 0;
+            gi.ldc = s.NB;
+            gi.alpha = 1.0;
+            gitems.push_back(gi);
+            np->fl_tg += 2.0 * gi.M * gi.N * (double)gi.K * (k1 - k0);
+            np->al_tg += 2.0 * gi.M * (double)s.sec_n[w.op / ns] * s.sec_n[w.op % ns] * (double)gi.K * (k1 - k0);
+          }
+        }
+        // cross-element items (partial buffer 0)
+        {
+          double *acc_base = s.d_Kacc.p + (size_t)wi * S * s.op_stride;
+          const int acc = ti > 0 ? 1 : 0;
+          const int oe0 = (int)oentries.size();
+          for (size_t k = 0; k < take; k++) oentries.push_back(dev::OffEntry{(int)(t0 + k), w.ilm[ti + k]});
+          for (int ei = 0; ei < t.Nel; ei++)
+            for (int ej = 0; ej < t.Nel; ej++) {
+              if (ei == ej) continue;
+              dev::OffItem oi{};
+              oi.C = acc_base + s.ep_off[(size_t)ei * t.Nel + ej];
+              oi.ei = ei;
+              oi.ej = ej;
+              oi.ent0 = oe0;
+              oi.ent1 = (int)oentries.size();
+              oi.accumulate = acc;
+              oitems.push_back(oi);
+              const double per = 2.0 * t.nch * take *
+                                 ((double)t.en[ei] * t.en[ej] * t.nch * t.en[ej] + (double)t.en[ei] * t.en[ej] * t.en[ei]);
+              np->fl_off += per * s.NB;
+              np->al_off += per * s.sec_n[w.op / ns] * s.sec_n[w.op % ns];
+            }
+        }
+        np->fl_fold += 2.0 * (double)take * s.Npix * (double)s.NP * s.NP * s.NP * (t.nch + s.nab) * (s.parity ? 0.5 : 1.0);
+        for (size_t k = 0; k < take; k++) np->al_fold += w.alg_fold[ti + k];
+        done[wi] += take;
+        remaining -= take;
+      }
+      if (tasks.empty()) break;
+      auto bt = std::make_unique<ExchangeBatch>();
+      bt->tasks.upload(tasks, &dev_bytes_);
+      bt->gitems.upload(gitems, &dev_bytes_);
+      bt->gentries.upload(gentries, &dev_bytes_);
+      bt->oitems.upload(oitems, &dev_bytes_);
+      bt->oentries.upload(oentries, &dev_bytes_);
+      bt->ntasks = (int)tasks.size();
+      bt->ngitems = (int)gitems.size();
+      bt->noitems = (int)oitems.size();
+      np->batches.push_back(std::move(bt));
+    }
+    if (plans_->plans.size() >= 4) plans_->plans.erase(plans_->plans.begin());
+    plans_->plans.push_back(std::move(np));
+    plan = plans_->plans.back().get();
+  }
+  // ---------------- run the plan ----------------
+  // 2. pack the active sector pairs
+  if (!plan->splist.empty()) {
+    CK(cudaMemcpyAsync(s.d_splist.p, plan->splist.data(), plan->splist.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    for (int sp : plan->splist)
+      CK(cudaMemsetAsync(s.d_Ppix.p + (size_t)sp * s.Npix * s.NB, 0, (size_t)s.Npix * s.NB * sizeof(double), st));
+    dev::k_pack<<<dim3(t.Nrad, (unsigned)plan->splist.size()), 256, 0, st>>>(s.bd, dP, ldP, s.d_splist.p, s.d_Ppix.p);
+    CK(cudaGetLastError());
+  }
+  const int S = plan->S;
+  if (S > 1)
+    for (int a = 0; a < plan->nactive; a++)
+      CK(cudaMemsetAsync(s.d_Kacc.p + ((size_t)a * S + 1) * s.op_stride, 0, (size_t)(S - 1) * s.op_stride * sizeof(double), st));
+  CK(cudaEventRecord(s.ev[1], st));
+  float ms_fold = 0, ms_tg = 0, ms_off = 0;
+  for (auto &btp : plan->batches) {
+    ExchangeBatch &bt = *btp;
     CK(cudaEventRecord(s.ev[2], st));
-    launch_fold(s.NT, t.nch, s.parity, s.bd, s.d_tasks.p, (int)tasks.size(), s.d_G.p, s.d_Ppix.p, s.d_R.p, st);
+    launch_fold(s.NT, t.nch, s.parity, s.bd, bt.tasks.p, bt.ntasks, s.d_G.p, s.d_Ppix.p, s.d_R.p, st);
     CK(cudaEventRecord(s.ev[3], st));
     {
       // in-element exchange: one CTA tile covers all Ni^2 rows (R rows are read once)
       const size_t smem = (size_t)3 * (256 * 20 + 16 * 68) * sizeof(double);
-      const dim3 grid(s.NB / 64, (unsigned)gitems.size());
+      const dim3 grid(s.NB / 64, (unsigned)bt.ngitems);
       if (s.nab % 2 == 0)
-        dev::k_tgemm<true><<<grid, 256, smem, st>>>(s.d_gitems.p, s.d_gentries.p);
+        dev::k_tgemm<true><<<grid, 256, smem, st>>>(bt.gitems.p, bt.gentries.p);
       else
-        dev::k_tgemm<false><<<grid, 256, smem, st>>>(s.d_gitems.p, s.d_gentries.p);
+        dev::k_tgemm<false><<<grid, 256, smem, st>>>(bt.gitems.p, bt.gentries.p);
       CK(cudaGetLastError());
     }
     CK(cudaEventRecord(s.ev[4], st));
-    if (!oitems.empty()) {
-      const dim3 grid(s.NB / 16, (unsigned)oitems.size());
+    if (bt.noitems) {
+      const dim3 grid(s.NB / 16, (unsigned)bt.noitems);
       const size_t smem = (size_t)(t.nch * 16 * 16 * 20 + t.nch * 16 * 20 + 16 * (t.nch * 16 + 4)) * sizeof(double);
       if (t.nch == 1)
-        dev::k_offdiag_mma<1><<<grid, 256, smem, st>>>(s.bd, s.d_oitems.p, s.d_oentries.p, s.d_R.p, s.d_small.p,
+        dev::k_offdiag_mma<1><<<grid, 256, smem, st>>>(s.bd, bt.oitems.p, bt.oentries.p, s.d_R.p, s.d_small.p,
                                                     s.d_big.p, s.d_blk_off.p);
       else
-        dev::k_offdiag_mma<2><<<grid, 256, smem, st>>>(s.bd, s.d_oitems.p, s.d_oentries.p, s.d_R.p, s.d_small.p,
+        dev::k_offdiag_mma<2><<<grid, 256, smem, st>>>(s.bd, bt.oitems.p, bt.oentries.p, s.d_R.p, s.d_small.p,
                                                     s.d_big.p, s.d_blk_off.p);
       CK(cudaGetLastError());
     }
@@ -718,14 +757,14 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
     ms_tg += ms;
     CK(cudaEventElapsedTime(&ms, s.ev[4], s.ev[5]));
     ms_off += ms;
-    tm_.launches += 2 + (oitems.empty() ? 0 : 1);
+    tm_.launches += 2 + (bt.noitems ? 1 : 0);
     tm_.launches_fold++;
     tm_.launches_tgemm++;
-    tm_.launches_offdiag += oitems.empty() ? 0 : 1;
+    tm_.launches_offdiag += bt.noitems ? 1 : 0;
   }
   // 6. unpack
   CK(cudaEventRecord(s.ev[6], st));
-  CK(cudaMemcpyAsync(s.d_op_src.p, op_src.data(), op_src.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(s.d_op_src.p, plan->op_src.data(), plan->op_src.size() * sizeof(int), cudaMemcpyHostToDevice, st));
   dev::UnpackDev u{s.d_op_src.p, s.d_ep_off.p, s.d_ang_sec.p, s.d_ang_pos.p, s.op_stride, S};
   dev::k_unpack_K<<<dim3(na, na), 256, 0, st>>>(s.bd, u, s.d_Kacc.p, dK, ldK);
   CK(cudaGetLastError());
@@ -737,13 +776,37 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
   tm_.fold = ms_fold;
   tm_.tgemm = ms_tg;
   tm_.offdiag = ms_off;
-  tm_.flops_fold = fl_fold;
-  tm_.flops_tgemm = fl_tg;
-  tm_.flops_offdiag = fl_off;
-  tm_.alg_fold = al_fold;
-  tm_.alg_tgemm = al_tg;
-  tm_.alg_offdiag = al_off;
+  tm_.flops_fold = plan->fl_fold;
+  tm_.flops_tgemm = plan->fl_tg;
+  tm_.flops_offdiag = plan->fl_off;
+  tm_.alg_fold = plan->al_fold;
+  tm_.alg_tgemm = plan->al_tg;
+  tm_.alg_offdiag = plan->al_off;
   tm_.launches += 3;
+  // which dense blocks of K can be non-zero (for compact collectives): angular pairs (j,k)
+  last_active_ops_.assign(plan->op_src.begin(), plan->op_src.end());
+}
+
+Engine::~Engine() {
+  plans_.reset();
+  if (p_)
+    for (auto &e : p_->ev) cudaEventDestroy(e);
+  if (stream_) cudaStreamDestroy(stream_);
+}
+
+// sector of every dense basis function and the list of output sector pairs written by the last
+// exchange call (everything else in K is exactly zero)
+void Engine::output_pattern(std::vector<int> &bf_sector, std::vector<int> &pairs) const {
+  const Impl &s = *p_;
+  bf_sector.clear();
+  for (int a = 0; a < s.t.Nang(); a++)
+    for (int r = s.ang_skip[a]; r < s.t.Nrad; r++) bf_sector.push_back(s.ang_sec[a]);
+  pairs.clear();
+  for (size_t op = 0; op < last_active_ops_.size(); op++)
+    if (last_active_ops_[op] >= 0) {
+      pairs.push_back((int)(op / s.ns));
+      pairs.push_back((int)(op % s.ns));
+    }
 }
 
 // ---------------------------------------------------------------------------

@@ -51,13 +51,20 @@ class Engine {
   void coulomb(const double *P, int64_t ldP, double *J, int64_t ldJ);
   void exchange(const double *P, int64_t ldP, double *K, int64_t ldK);
 
+  // Non-zero structure of the last exchange result: sector id of every dense basis function and
+  // the (row sector, column sector) pairs that were written; all other blocks of K are zero.
+  void output_pattern(std::vector<int> &bf_sector, std::vector<int> &pairs) const;
+
   const EngineTimings &timings() const { return tm_; }
   cudaStream_t stream() const { return stream_; }
   size_t device_bytes() const { return dev_bytes_; }
 
  private:
   struct Impl;
+  struct PlanCache;
   std::unique_ptr<Impl> p_;
+  std::unique_ptr<PlanCache> plans_;
+  std::vector<int> last_active_ops_;
   int device_ = 0, nbf_ = 0;
   bool absm_symmetric_ = false;
   cudaStream_t stream_ = nullptr;

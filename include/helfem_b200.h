@@ -117,6 +117,11 @@ int hfq_coulomb_device(hfq_ctx *ctx, const double *dP, int64_t ldP, double *dJ, 
 int hfq_exchange_device(hfq_ctx *ctx, const double *dP, int64_t ldP, double *dK, int64_t ldK, int shard,
                         int nshards, void *stream);
 
+/* Non-zero structure of the last hfq_exchange* result, for compact collectives / copies:
+ * bf_sector[Nbf] = sector id of every basis function; pairs = (row sector, column sector) of the
+ * blocks that were written (everything else in K is exactly zero).  Returns the number of pairs. */
+int hfq_exchange_output_pattern(const hfq_ctx *ctx, int *bf_sector, int64_t cap_bf, int *pairs, int64_t cap_pairs);
+
 /* Timings / work counters of the last call on this context:
  * out[0..5] = ms {pack, fold, in-element GEMM, cross-element, unpack, total},
  * out[6..8] = executed flops {fold, in-element GEMM, cross-element}, out[9] = kernel launches,
