@@ -728,7 +728,7 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
     CK(cudaEventRecord(s.ev[3], st));
     {
       // in-element exchange: one CTA tile covers all Ni^2 rows (R rows are read once)
-      const size_t smem = (size_t)3 * (256 * 20 + 16 * 68) * sizeof(double);
+      const size_t smem = (size_t)2 * (256 * 36 + 32 * 68) * sizeof(double);
       const dim3 grid(s.NB / 64, (unsigned)bt.ngitems);
       if (s.nab % 2 == 0)
         dev::k_tgemm<true><<<grid, 256, smem, st>>>(bt.gitems.p, bt.gentries.p);

@@ -599,16 +599,16 @@ k_offdiag_mma(BasisDev b, const OffItem *__restrict__ items, const OffEntry *__r
 template <bool A16>
 __global__ void __launch_bounds__(256, 1)
 k_tgemm(const GemmItem *__restrict__ items, const GemmEntry *__restrict__ entries) {
-  constexpr int BK = 16, BN = 64, MAXM = 256, STAGES = 3;
+  constexpr int BK = 32, BN = 64, MAXM = 256, STAGES = 2;
   constexpr int LDA_S = BK + 4, LDB_S = BN + 4;
   constexpr int A_STAGE = MAXM * LDA_S, B_STAGE = BK * LDB_S;
+  constexpr int CPR = BK / 2;   // 16-byte chunks per A row
   extern __shared__ double sm[];
   double *As = sm, *Bs = sm + STAGES * A_STAGE;
   const GemmItem it = items[blockIdx.y];
   const int bn = blockIdx.x * BN;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lr = lane >> 2, lc = lane & 3;
-  constexpr int Mpad = MAXM;   // rows >= M are zero-filled so that every warp runs the same DMMA sequence
   const int nkc = (it.K + BK - 1) / BK;
   const int nsteps = (it.ent1 - it.ent0) * nkc;
 
@@ -618,29 +618,31 @@ k_tgemm(const GemmItem *__restrict__ items, const GemmEntry *__restrict__ entrie
 #pragma unroll
     for (int j = 0; j < 8; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+  // rows >= M are zero-filled so that every warp runs the same DMMA sequence (no divergence)
   auto issue = [&](int step, int stage) {
     const GemmEntry e = entries[it.ent0 + step / nkc];
     const int kc = (step % nkc) * BK;
     double *as = As + stage * A_STAGE, *bs = Bs + stage * B_STAGE;
     if (A16) {
-      // A tile: Mpad rows x 16 doubles = 8 x 16-byte chunks per row
-      for (int idx = tid; idx < Mpad * 8; idx += 256) {
-        const int m = idx >> 3, ch = idx & 7, k = kc + ch * 2;
+#pragma unroll 4
+      for (int idx = tid; idx < MAXM * CPR; idx += 256) {
+        const int m = idx / CPR, ch = idx % CPR, k = kc + ch * 2;
         int bytes = 0;
         if (m < it.M && k < it.K) bytes = (k + 1 < it.K) ? 16 : 8;
         const double *src = e.A + (int64_t)(m < it.M ? m : 0) * e.lda + (k < it.K ? k : 0);
         cp_async16(as + m * LDA_S + ch * 2, src, bytes);
       }
     } else {
-      for (int idx = tid; idx < Mpad * 16; idx += 256) {
-        const int m = idx >> 4, kk = idx & 15, k = kc + kk;
+#pragma unroll 4
+      for (int idx = tid; idx < MAXM * BK; idx += 256) {
+        const int m = idx / BK, kk = idx % BK, k = kc + kk;
         const int bytes = (m < it.M && k < it.K) ? 8 : 0;
         const double *src = e.A + (int64_t)(m < it.M ? m : 0) * e.lda + (k < it.K ? k : 0);
         cp_async8(as + m * LDA_S + kk, src, bytes);
       }
     }
-    // B tile: 16 rows x 64 doubles = 32 x 16-byte chunks per row
-    for (int idx = tid; idx < BK * 32; idx += 256) {
+#pragma unroll 4
+    for (int idx = tid; idx < BK * 32; idx += 256) {   // B tile: BK rows x 32 chunks of 16 bytes
       const int kk = idx >> 5, ch = idx & 31, k = kc + kk;
       const int bytes = (k < it.K) ? 16 : 0;
       const double *src = e.B + (k < it.K ? it.browoff[k] : 0) + bn + ch * 2;
@@ -648,32 +650,33 @@ k_tgemm(const GemmItem *__restrict__ items, const GemmEntry *__restrict__ entrie
     }
   };
 
-#pragma unroll
-  for (int s = 0; s < STAGES - 1; s++) {
-    if (s < nsteps) issue(s, s);
-    cp_async_commit();
-  }
+  if (nsteps > 0) issue(0, 0);
+  cp_async_commit();
   for (int step = 0; step < nsteps; step++) {
-    cp_async_wait<STAGES - 2>();
-    __syncthreads();
-    {
-      const int nxt = step + STAGES - 1;
-      if (nxt < nsteps) issue(nxt, nxt % STAGES);
-      cp_async_commit();
-    }
-    const double *as = As + (step % STAGES) * A_STAGE, *bs = Bs + (step % STAGES) * B_STAGE;
+    cp_async_wait<0>();
+    __syncthreads();   // stage (step&1) landed; everyone is done reading stage ((step+1)&1)
+    if (step + 1 < nsteps) issue(step + 1, (step + 1) & 1);
+    cp_async_commit();
+    const double *as = As + (step & 1) * A_STAGE + lr * LDA_S + lc, *bs = Bs + (step & 1) * B_STAGE + lc * LDB_S + lr;
+    // software-pipelined fragments: load k-step kk+4 while the DMMAs of kk issue
+    double bf[2][8], af[2][4];
 #pragma unroll
-    for (int kk = 0; kk < BK; kk += 4) {
-      double bf[8], af[4];
+    for (int j = 0; j < 8; j++) bf[0][j] = bs[j * 8];
 #pragma unroll
-      for (int j = 0; j < 8; j++) bf[j] = bs[(kk + lc) * LDB_S + j * 8 + lr];
+    for (int i = 0; i < 4; i++) af[0][i] = as[(warp + i * 8) * 8 * LDA_S];
 #pragma unroll
-      for (int i = 0; i < 4; i++) af[i] = as[((warp + i * 8) * 8 + lr) * LDA_S + kk + lc];
-      // all four row tiles unconditionally (rows >= M are zero-filled): no divergence around the DMMAs
+    for (int ks = 0; ks < BK / 4; ks++) {
+      const int cur = ks & 1, nxt = cur ^ 1;
+      if (ks + 1 < BK / 4) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) bf[nxt][j] = bs[(ks + 1) * 4 * LDB_S + j * 8];
+#pragma unroll
+        for (int i = 0; i < 4; i++) af[nxt][i] = as[(warp + i * 8) * 8 * LDA_S + (ks + 1) * 4];
+      }
 #pragma unroll
       for (int i = 0; i < 4; i++)
 #pragma unroll
-        for (int j = 0; j < 8; j++) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        for (int j = 0; j < 8; j++) dmma(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
     }
   }
   cp_async_wait<0>();
