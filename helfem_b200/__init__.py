@@ -39,6 +39,7 @@ EXPORTED_SYMBOLS = [
     "hfq_tables_get_ints", "hfq_tables_get_doubles", "hfq_tables_get_block", "hfq_tables_one_electron",
     "hfq_tables_destroy", "hfq_create", "hfq_destroy", "hfq_nbf", "hfq_set_absm_symmetric", "hfq_coulomb",
     "hfq_exchange", "hfq_coulomb_device", "hfq_exchange_device", "hfq_last_timings", "hfq_exchange_output_pattern",
+    "hfq_grid_attach", "hfq_grid_npoints", "hfq_grid_density", "hfq_grid_fxc", "hfq_eval_fxc",
 ]
 
 
@@ -74,6 +75,12 @@ def lib():
     L.hfq_exchange_device.argtypes = [vp, vp, i64, vp, i64, ci, ci, vp]
     L.hfq_last_timings.argtypes = [vp, vp, ci]
     L.hfq_exchange_output_pattern.argtypes = [vp, vp, i64, vp, i64]
+    L.hfq_grid_attach.argtypes = [vp, ci, ci]
+    L.hfq_grid_npoints.argtypes = [vp]
+    L.hfq_grid_npoints.restype = i64
+    L.hfq_grid_density.argtypes = [vp, vp, i64, vp, i64, ci, vp, vp, vp, vp, vp, vp, vp]
+    L.hfq_grid_fxc.argtypes = [vp, ci, ci, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp]
+    L.hfq_eval_fxc.argtypes = [vp, ci, ci, vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, ci, cd]
     _lib = L
     return L
 
@@ -350,3 +357,68 @@ class TablesBasis(_BasisBase):
         self._absm = bool(sym)
         if self._ctx is not None:
             _check(lib().hfq_set_absm_symmetric(self._ctx, int(self._absm)))
+
+
+class AtomicDFTGrid:
+    """helfem::atomic::dftgrid::DFTGrid (src/atomic/dftgrid.h:139-160) on the GPU.
+
+    ``eval_Fxc`` has the reference's argument order; functionals other than the built-in Slater
+    exchange are evaluated by the caller between ``density`` and ``fxc`` (libxc layout)."""
+
+    GRAD, TAU, LAPL = 1, 2, 4
+
+    def __init__(self, basis, lang, mang):
+        self.basis = basis
+        _check(lib().hfq_grid_attach(basis._context(), lang, mang))
+        self.N = int(lib().hfq_grid_npoints(basis._context()))
+
+    def density(self, Pa, Pb=None, flags=0):
+        n = self.basis.Nbf()
+        Pa = _fmat(Pa, n)
+        pol = Pb is not None
+        if pol:
+            Pb = _fmat(Pb, n)
+        ns = 2 if pol else 1
+        out = {"rho": np.zeros((self.N, ns)), "w": np.zeros(self.N)}
+        if flags & 1:
+            out["sigma"] = np.zeros((self.N, 3 if pol else 1))
+        if flags & 6:
+            out["tau"] = np.zeros((self.N, ns))
+        if flags & 4:
+            out["lapl"] = np.zeros((self.N, ns))
+        nel, ekin = ctypes.c_double(), ctypes.c_double()
+        ptr = lambda k: out[k].ctypes.data if k in out else None
+        _check(lib().hfq_grid_density(self.basis._context(), Pa.ctypes.data, n, Pb.ctypes.data if pol else None, n, flags,
+                                      ptr("rho"), ptr("sigma"), ptr("tau"), ptr("lapl"), ptr("w"), ctypes.byref(nel),
+                                      ctypes.byref(ekin)))
+        out["Nel"], out["Ekin"] = nel.value, ekin.value
+        self._pol = pol
+        return out
+
+    def fxc(self, exc, vrho, vsigma=None, vtau=None, vlapl=None, beta=True):
+        n = self.basis.Nbf()
+        Ha = np.zeros((n, n), order="F")
+        Hb = np.zeros((n, n), order="F") if self._pol else None
+        c = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+        exc, vrho, vsigma, vtau, vlapl = map(c, (exc, vrho, vsigma, vtau, vlapl))
+        p = lambda a: None if a is None else a.ctypes.data
+        flags = (1 if vsigma is not None else 0) | (2 if vtau is not None else 0) | (4 if vlapl is not None else 0)
+        e = ctypes.c_double()
+        _check(lib().hfq_grid_fxc(self.basis._context(), flags, int(beta), p(exc), p(vrho), p(vsigma), p(vtau), p(vlapl),
+                                  Ha.ctypes.data, n, p(Hb), n, ctypes.byref(e)))
+        return Ha, Hb, e.value
+
+    def eval_Fxc(self, x_func, c_func, P, Pb=None, beta=True, thr=1e-12):
+        """Returns (H or (Ha, Hb), Exc, Nel, Ekin)."""
+        n = self.basis.Nbf()
+        Pa = _fmat(P, n)
+        pol = Pb is not None
+        if pol:
+            Pb = _fmat(Pb, n)
+        Ha = np.zeros((n, n), order="F")
+        Hb = np.zeros((n, n), order="F") if pol else None
+        exc, nel, ekin = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+        _check(lib().hfq_eval_fxc(self.basis._context(), x_func, c_func, Pa.ctypes.data, n, Pb.ctypes.data if pol else None,
+                                  n, Ha.ctypes.data, n, Hb.ctypes.data if pol else None, n, ctypes.byref(exc),
+                                  ctypes.byref(nel), ctypes.byref(ekin), int(beta), thr))
+        return ((Ha, Hb) if pol else Ha), exc.value, nel.value, ekin.value

@@ -1,7 +1,9 @@
 // C ABI of libhelfemqc_b200 (see include/helfem_b200.h).
 #include "../../include/helfem_b200.h"
 
+#include <cmath>
 #include <cstring>
+#include <vector>
 #include <exception>
 #include <mutex>
 #include <new>
@@ -9,6 +11,7 @@
 #include <string>
 
 #include "engine.h"
+#include "grid.h"
 #include "tables.h"
 
 struct hfq_tables {
@@ -17,6 +20,7 @@ struct hfq_tables {
 
 struct hfq_ctx {
   std::unique_ptr<hfq::Engine> eng;
+  std::unique_ptr<hfq::GridEngine> grid;
   std::mutex mu;  // the reference's gensap driver calls the build from several threads (src/sadatom/scf.cpp:329-334)
 };
 
@@ -291,6 +295,90 @@ int hfq_exchange_output_pattern(const hfq_ctx *ctx, int *bf_sector, int64_t cap_
   std::memcpy(bf_sector, bs.data(), bs.size() * sizeof(int));
   std::memcpy(pairs, pr.data(), pr.size() * sizeof(int));
   return (int)(pr.size() / 2);
+}
+
+int hfq_grid_attach(hfq_ctx *ctx, int lang, int mang) {
+  if (!ctx || lang < 1 || mang < 1) return fail(HFQ_ERR_INVALID, "hfq_grid_attach: invalid argument");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  return guarded([&] {
+    const hfq::GridTables g = hfq::build_atomic_grid(ctx->eng->tables(), lang, mang);
+    ctx->grid = std::make_unique<hfq::GridEngine>(ctx->eng->tables(), g, ctx->eng->device(), ctx->eng->stream());
+    return HFQ_OK;
+  });
+}
+
+int64_t hfq_grid_npoints(const hfq_ctx *ctx) {
+  if (!ctx || !ctx->grid) return fail(HFQ_ERR_STATE, "hfq_grid_npoints: no grid attached");
+  return ctx->grid->npoints();
+}
+
+int hfq_grid_density(hfq_ctx *ctx, const double *Pa, int64_t ldPa, const double *Pb, int64_t ldPb, int flags,
+                     double *rho, double *sigma, double *tau, double *lapl, double *weights, double *Nel, double *Ekin) {
+  if (!ctx || !ctx->grid) return fail(HFQ_ERR_STATE, "hfq_grid_density: no grid attached");
+  if (!Pa) return fail(HFQ_ERR_INVALID, "Error - density matrix is empty!");   // src/atomic/dftgrid.cpp:53-55
+  const int64_t n = ctx->eng->Nbf();
+  if (ldPa < n || (Pb && ldPb < n)) return fail(HFQ_ERR_INVALID, "hfq_grid_density: leading dimension smaller than Nbf");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  return guarded([&] {
+    ctx->grid->density(Pa, ldPa, Pb, ldPb, flags, rho, sigma, tau, lapl, weights, Nel, Ekin);
+    return HFQ_OK;
+  });
+}
+
+int hfq_grid_fxc(hfq_ctx *ctx, int flags, int beta, const double *exc, const double *vrho, const double *vsigma,
+                 const double *vtau, const double *vlapl, double *Ha, int64_t ldHa, double *Hb, int64_t ldHb, double *Exc) {
+  if (!ctx || !ctx->grid) return fail(HFQ_ERR_STATE, "hfq_grid_fxc: no grid attached");
+  if (!vrho || !Ha) return fail(HFQ_ERR_INVALID, "hfq_grid_fxc: null argument");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  return guarded([&] {
+    ctx->grid->fxc(flags, beta != 0, exc, vrho, vsigma, vtau, vlapl, Ha, ldHa, Hb, ldHb, Exc);
+    return HFQ_OK;
+  });
+}
+
+// Slater exchange, libxc id 1 (XC_LDA_X): e_x per particle and v_x; spin-scaling relation for the polarised case.
+static void lda_x(int64_t N, int nspin, const double *rho, double thr, double *exc, double *vrho) {
+  const double pi = std::acos(-1.0);
+  const double cx = -0.75 * std::cbrt(3.0 / pi);
+  for (int64_t p = 0; p < N; p++) {
+    if (nspin == 1) {
+      const double n = rho[p];
+      if (n < thr) { exc[p] = 0.0; vrho[p] = 0.0; continue; }
+      const double n13 = std::cbrt(n);
+      exc[p] = cx * n13;
+      vrho[p] = 4.0 / 3.0 * cx * n13;
+    } else {
+      const double na = rho[2 * p], nb = rho[2 * p + 1], n = na + nb;
+      if (n < thr) { exc[p] = 0.0; vrho[2 * p] = vrho[2 * p + 1] = 0.0; continue; }
+      // E_x[na,nb] = (E_x[2na] + E_x[2nb]) / 2
+      const double ea = na > 0 ? cx * std::cbrt(2.0 * na) * na : 0.0, eb = nb > 0 ? cx * std::cbrt(2.0 * nb) * nb : 0.0;
+      exc[p] = (ea + eb) / n;
+      vrho[2 * p] = na > 0 ? 4.0 / 3.0 * cx * std::cbrt(2.0 * na) : 0.0;
+      vrho[2 * p + 1] = nb > 0 ? 4.0 / 3.0 * cx * std::cbrt(2.0 * nb) : 0.0;
+    }
+  }
+}
+
+int hfq_eval_fxc(hfq_ctx *ctx, int x_func, int c_func, const double *Pa, int64_t ldPa, const double *Pb, int64_t ldPb,
+                 double *Ha, int64_t ldHa, double *Hb, int64_t ldHb, double *Exc, double *Nel, double *Ekin, int beta,
+                 double thr) {
+  if (!ctx || !ctx->grid) return fail(HFQ_ERR_STATE, "hfq_eval_fxc: no grid attached");
+  if (!Pa || !Ha) return fail(HFQ_ERR_INVALID, "Error - density matrix is empty!");
+  if (c_func > 0 || (x_func > 0 && x_func != 1))
+    return fail(HFQ_ERR_INVALID,
+                "hfq_eval_fxc: only the Slater exchange (libxc id 1) is built in; evaluate other functionals with libxc "
+                "between hfq_grid_density and hfq_grid_fxc");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  return guarded([&] {
+    const int64_t N = ctx->grid->npoints();
+    const int nspin = Pb ? 2 : 1;
+    std::vector<double> rho((size_t)N * nspin), exc((size_t)N, 0.0), vrho((size_t)N * nspin, 0.0);
+    ctx->grid->density(Pa, ldPa, Pb, ldPb, 0, rho.data(), nullptr, nullptr, nullptr, nullptr, Nel, Ekin);
+    if (Ekin) *Ekin = 0.0;   // tau is not evaluated for an LDA (src/general/dftgrid_common.cpp compute_Ekin)
+    if (x_func == 1) lda_x(N, nspin, rho.data(), thr, exc.data(), vrho.data());
+    ctx->grid->fxc(0, beta != 0, exc.data(), vrho.data(), nullptr, nullptr, nullptr, Ha, ldHa, Hb, ldHb, Exc);
+    return HFQ_OK;
+  });
 }
 
 int hfq_last_timings(const hfq_ctx *ctx, double *out, int n) {

@@ -787,6 +787,8 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
   last_active_ops_.assign(plan->op_src.begin(), plan->op_src.end());
 }
 
+const BasisTables &Engine::tables() const { return p_->t; }
+
 Engine::~Engine() {
   plans_.reset();
   if (p_)

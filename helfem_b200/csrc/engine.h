@@ -36,6 +36,7 @@ class Engine {
   Engine &operator=(const Engine &) = delete;
 
   int Nbf() const { return nbf_; }
+  const BasisTables &tables() const;   // host description (integral blocks released after upload)
   int device() const { return device_; }
   void set_absm_symmetric(bool s) { absm_symmetric_ = s; }
   bool absm_symmetric() const { return absm_symmetric_; }

@@ -1,0 +1,509 @@
+// Device engine of the atomic DFT grid (see grid.h).  All contractions are small FP64 GEMMs on
+// pair tables, run through the multi-entry DMMA GEMM kernel of kernels.cuh:
+//   density  : Q[(a,b)][(type,ir)] = Pe[(a,b)][(r,c)] . RR[(r,c)][(type,ir)]
+//              D_j[ia][ir]          = YY_j^T[ia][(a,b)] . Q[(a,b)][(type_j, ir)]
+//   assembly : T_j[ia][(r,c)]       = c_j[ia][ir] . RR_j^T[ir][(r,c)]
+//              H_e[(a,b)][(r,c)]   += YY_j[(a,b)][ia] . T_j[ia][(r,c)]
+#include "grid.h"
+
+#include <cmath>
+#include <stdexcept>
+#include <string>
+
+#include "kernels.cuh"
+
+namespace hfq {
+
+#define CK(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t err__ = (call);                                                                   \
+    if (err__ != cudaSuccess)                                                                     \
+      throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(err__) + " at " + \
+                               __FILE__ + ":" + std::to_string(__LINE__));                        \
+  } while (0)
+
+namespace {
+
+template <typename T>
+struct Buf {
+  T *p = nullptr;
+  size_t n = 0;
+  void alloc(size_t c) {
+    if (c <= n) return;
+    if (p) cudaFree(p);
+    CK(cudaMalloc(&p, c * sizeof(T)));
+    n = c;
+  }
+  void upload(const std::vector<T> &h) {
+    alloc(h.size());
+    if (!h.empty()) CK(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  }
+  ~Buf() {
+    if (p) cudaFree(p);
+  }
+};
+
+constexpr int NCOMBO = 8;   // 00, 10, 20, 30, 11, 22, 33, L0
+constexpr int NRR = 5;      // FF, DF, DD, LF, 2F
+constexpr int NYY = 6;      // YY, ThY, PhY, ThTh, PhPh, YlY
+
+struct GridDev {
+  int Nel, Nang, NA2, NI, NN, nang, nrad, Nrad;
+  int64_t npe;   // points per element
+  const int *efirst, *en;
+  const double *w;       // [Nel][nang][nrad] total quadrature weight
+  const double *rr;      // [Nel][nrad] radius
+  const double *sth;     // [nang] sin(theta)
+};
+
+// Pe[e][(a,b)][(r,c)] = P[(a, f+r), (b, f+c)]     grid (Nel, NA2)
+__global__ void k_grid_pack(GridDev g, const double *__restrict__ P, int64_t ld, double *__restrict__ Pe) {
+  const int e = blockIdx.x, ab = blockIdx.y, a = ab / g.Nang, b = ab % g.Nang;
+  const int f = g.efirst[e], n = g.en[e];
+  double *dst = Pe + ((int64_t)e * g.NA2 + ab) * g.NN;
+  for (int idx = threadIdx.x; idx < g.NN; idx += blockDim.x) {
+    const int r = idx / g.NI, c = idx % g.NI;
+    dst[idx] = (r < n && c < n) ? P[(int64_t)a * g.Nrad + f + r + ((int64_t)b * g.Nrad + f + c) * ld] : 0.0;
+  }
+}
+
+// point quantities from the contracted tables D[j][p], p = (e*nang + ia)*nrad + ir
+// out: rho[p], grho[3][p], tau[p], lapl[p]; sums[0] += w rho, sums[1] += w tau
+__global__ void k_grid_points(GridDev g, const double *__restrict__ D, int flags, double *__restrict__ rho,
+                              double *__restrict__ grho, double *__restrict__ tau, double *__restrict__ lapl,
+                              double *__restrict__ sums) {
+  const int64_t N = (int64_t)g.Nel * g.npe;
+  double sn = 0.0, sk = 0.0;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < N; p += (int64_t)gridDim.x * blockDim.x) {
+    const int ir = (int)(p % g.nrad), ia = (int)((p / g.nrad) % g.nang), e = (int)(p / g.npe);
+    const double r = g.rr[e * g.nrad + ir], st = r, sp = r * g.sth[ia], w = g.w[p];
+    const double d0 = D[p];
+    rho[p] = d0;
+    sn += w * d0;
+    if (flags & GRID_GRAD) {
+      grho[p] = 2.0 * D[N + p];
+      grho[N + p] = 2.0 * D[2 * N + p] / st;
+      grho[2 * N + p] = 2.0 * D[3 * N + p] / sp;
+    }
+    if (flags & (GRID_TAU | GRID_LAPL)) {
+      const double kin = D[4 * N + p] + D[5 * N + p] / (st * st) + D[6 * N + p] / (sp * sp);
+      tau[p] = 0.5 * kin;
+      sk += w * 0.5 * kin;
+      if (flags & GRID_LAPL) lapl[p] = 2.0 * (kin + D[7 * N + p]);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    sn += __shfl_down_sync(0xffffffffu, sn, o);
+    sk += __shfl_down_sync(0xffffffffu, sk, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(sums, sn);
+    atomicAdd(sums + 1, sk);
+  }
+}
+
+// assembly weights c_j[p] for one spin channel
+//   vr: v_rho, vs_same/vs_ab: v_sigma(ss), v_sigma(ab) (vs_ab == nullptr: restricted, factor 2 on vs_same only),
+//   g_same/g_other: gradients [3][N]
+__global__ void k_grid_weights(GridDev g, int flags, const double *__restrict__ vr, const double *__restrict__ vs_same,
+                               const double *__restrict__ vs_ab, const double *__restrict__ vt,
+                               const double *__restrict__ vl, const double *__restrict__ g_same,
+                               const double *__restrict__ g_other, int use_vtl, double *__restrict__ C) {
+  const int64_t N = (int64_t)g.Nel * g.npe;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < N; p += (int64_t)gridDim.x * blockDim.x) {
+    const int ir = (int)(p % g.nrad), ia = (int)((p / g.nrad) % g.nang), e = (int)(p / g.npe);
+    const double r = g.rr[e * g.nrad + ir], st = r, sp = r * g.sth[ia], w = g.w[p];
+    C[p] = w * vr[p];
+    if (flags & GRID_GRAD) {
+      const double sc[3] = {1.0, st, sp};
+      for (int c = 0; c < 3; c++) {
+        double gv = 2.0 * vs_same[p] * g_same[c * N + p];
+        if (vs_ab) gv += vs_ab[p] * g_other[c * N + p];
+        C[(1 + c) * N + p] = w * gv / sc[c];
+      }
+    }
+    if (use_vtl) {
+      double vtl = 0.0;
+      if (vt) vtl += 0.5 * vt[p];
+      if (vl) vtl += 2.0 * vl[p];
+      vtl *= w;
+      C[4 * N + p] = vtl;
+      C[5 * N + p] = vtl / (st * st);
+      C[6 * N + p] = vtl / (sp * sp);
+    }
+    if (vl) C[7 * N + p] = w * vl[p];
+  }
+}
+
+// H[(a,f+r),(b,f+c)] = sum over elements containing both radial functions of
+//   Hs[e][(a,b)][(r,c)] + Hx[e][(a,b)][(r,c)] + Hx[e][(b,a)][(c,r)]        grid (Nang, Nang)
+__global__ void k_grid_unpack(GridDev g, const double *__restrict__ Hs, const double *__restrict__ Hx,
+                              double *__restrict__ H, int64_t ld) {
+  const int a = blockIdx.x, b = blockIdx.y;
+  for (int idx = threadIdx.x; idx < g.Nrad * g.Nrad; idx += blockDim.x) {
+    const int R = idx % g.Nrad, Cc = idx / g.Nrad;
+    double s = 0.0;
+    for (int e = 0; e < g.Nel; e++) {
+      const int r = R - g.efirst[e], c = Cc - g.efirst[e];
+      if (r < 0 || c < 0 || r >= g.en[e] || c >= g.en[e]) continue;
+      const int64_t eb = (int64_t)e * g.NA2;
+      s += Hs[(eb + a * g.Nang + b) * g.NN + r * g.NI + c] + Hx[(eb + a * g.Nang + b) * g.NN + r * g.NI + c] +
+           Hx[(eb + b * g.Nang + a) * g.NN + c * g.NI + r];
+    }
+    H[(int64_t)a * g.Nrad + R + ((int64_t)b * g.Nrad + Cc) * ld] = s;
+  }
+}
+
+// interleave spin components: out[p*nc + c] = in[c][p]
+__global__ void k_interleave(const double *__restrict__ a, const double *__restrict__ b, const double *__restrict__ c,
+                             int nc, int64_t N, double *__restrict__ out) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < N; p += (int64_t)gridDim.x * blockDim.x) {
+    out[p * nc] = a[p];
+    if (nc > 1) out[p * nc + 1] = b[p];
+    if (nc > 2) out[p * nc + 2] = c[p];
+  }
+}
+// sigma components from gradients
+__global__ void k_sigma(const double *__restrict__ ga, const double *__restrict__ gb, int64_t N, double *__restrict__ saa,
+                        double *__restrict__ sab, double *__restrict__ sbb) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < N; p += (int64_t)gridDim.x * blockDim.x) {
+    const double a0 = ga[p], a1 = ga[N + p], a2 = ga[2 * N + p];
+    saa[p] = a0 * a0 + a1 * a1 + a2 * a2;
+    if (gb) {
+      const double b0 = gb[p], b1 = gb[N + p], b2 = gb[2 * N + p];
+      sab[p] = a0 * b0 + a1 * b1 + a2 * b2;
+      sbb[p] = b0 * b0 + b1 * b1 + b2 * b2;
+    }
+  }
+}
+// de-interleave: out[c][p] = in[p*nc + c]
+__global__ void k_deinterleave(const double *__restrict__ in, int nc, int c, int64_t N, double *__restrict__ out) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < N; p += (int64_t)gridDim.x * blockDim.x)
+    out[p] = in[p * nc + c];
+}
+// Exc = sum w exc (rho_a + rho_b)
+__global__ void k_exc(const double *__restrict__ w, const double *__restrict__ exc, const double *__restrict__ ra,
+                      const double *__restrict__ rb, int64_t N, double *__restrict__ sum) {
+  double s = 0.0;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < N; p += (int64_t)gridDim.x * blockDim.x)
+    s += w[p] * exc[p] * (ra[p] + (rb ? rb[p] : 0.0));
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(sum, s);
+}
+
+}  // namespace
+
+struct GridEngine::Impl {
+  int device = 0;
+  cudaStream_t st = nullptr;
+  GridDev gd{};
+  int nbf = 0;
+  int64_t N = 0;
+  Buf<int> d_efirst, d_en, d_bo_q, d_bo_t;
+  Buf<double> d_w, d_rr, d_sth, d_RR, d_RRT, d_YY, d_YYT;
+  Buf<double> d_P, d_Pe, d_Q, d_D, d_dens, d_C, d_T, d_Hs, d_Hx, d_H, d_sums, d_io, d_v;
+  Buf<dev::GemmItem> d_items;
+  Buf<dev::GemmEntry> d_entries;
+  bool polarized = false;
+  int dens_flags = 0;
+  // dens layout per spin s: rho [N], grho [3N], tau [N], lapl [N]  -> 6N
+  double *dens(int s, int which) { return d_dens.p + ((size_t)s * 6 + which) * N; }
+
+  void gemm(const std::vector<dev::GemmItem> &items, const std::vector<dev::GemmEntry> &entries, int maxM, int maxN) {
+    if (items.empty()) return;
+    d_items.alloc(items.size());
+    d_entries.alloc(entries.size());
+    CK(cudaMemcpyAsync(d_items.p, items.data(), items.size() * sizeof(items[0]), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_entries.p, entries.data(), entries.size() * sizeof(entries[0]), cudaMemcpyHostToDevice, st));
+    const dim3 grid((maxN + 63) / 64, (maxM + 63) / 64, (unsigned)items.size());
+    dev::k_gemm<64, 64, 2, 2, false><<<grid, 128, 0, st>>>(d_items.p, d_entries.p);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));   // descriptor buffers are reused by the next stage
+  }
+};
+
+GridEngine::GridEngine(const BasisTables &t, const GridTables &g, int device, cudaStream_t stream) : p_(new Impl) {
+  Impl &s = *p_;
+  s.device = device;
+  s.st = stream;
+  CK(cudaSetDevice(device));
+  const int NA = g.Nang, NA2 = NA * NA, NI = g.NI, NN = NI * NI, nang = g.nang, nrad = g.nrad, Nel = g.Nel;
+  s.nbf = t.Nbf();
+  s.N = (int64_t)Nel * nang * nrad;
+  s.d_efirst.upload(t.efirst);
+  s.d_en.upload(t.en);
+  std::vector<double> w((size_t)s.N), sth(nang);
+  for (int ia = 0; ia < nang; ia++) sth[ia] = std::sqrt(1.0 - g.cth[ia] * g.cth[ia]);
+  for (int e = 0; e < Nel; e++)
+    for (int ia = 0; ia < nang; ia++)
+      for (int ir = 0; ir < nrad; ir++) {
+        const double r = g.r[(size_t)e * nrad + ir];
+        w[((size_t)e * nang + ia) * nrad + ir] = g.wang[ia] * g.wrad[(size_t)e * nrad + ir] * r * r;
+      }
+  s.d_w.upload(w);
+  s.d_rr.upload(g.r);
+  s.d_sth.upload(sth);
+  // radial pair tables: RR[e][(r,c)][type*nrad + ir] and RRT[e][type][ir][(r,c)]
+  {
+    std::vector<double> RR((size_t)Nel * NN * NRR * nrad, 0.0), RRT((size_t)Nel * NRR * nrad * NN, 0.0);
+    const std::vector<double> *rowt[NRR] = {&g.F, &g.D, &g.D, &g.L1, &g.F2};
+    const std::vector<double> *colt[NRR] = {&g.F, &g.F, &g.D, &g.F, &g.F};
+    for (int e = 0; e < Nel; e++)
+      for (int ty = 0; ty < NRR; ty++)
+        for (int r = 0; r < NI; r++)
+          for (int c = 0; c < NI; c++)
+            for (int ir = 0; ir < nrad; ir++) {
+              const double v = (*rowt[ty])[((size_t)e * NI + r) * nrad + ir] * (*colt[ty])[((size_t)e * NI + c) * nrad + ir];
+              RR[((size_t)e * NN + r * NI + c) * NRR * nrad + ty * nrad + ir] = v;
+              RRT[(((size_t)e * NRR + ty) * nrad + ir) * NN + r * NI + c] = v;
+            }
+    s.d_RR.upload(RR);
+    s.d_RRT.upload(RRT);
+  }
+  // angular pair tables: YY[type][(a,b)][ia], YYT[type][ia][(a,b)]
+  {
+    std::vector<double> YY((size_t)NYY * NA2 * nang), YYT((size_t)NYY * nang * NA2);
+    for (int a = 0; a < NA; a++)
+      for (int b = 0; b < NA; b++)
+        for (int ia = 0; ia < nang; ia++) {
+          const std::complex<double> ya = g.Y[(size_t)a * nang + ia], yb = g.Y[(size_t)b * nang + ia];
+          const std::complex<double> ta = g.Th[(size_t)a * nang + ia], tb = g.Th[(size_t)b * nang + ia];
+          const double ma = t.mval[a], mb = t.mval[b], la = t.lval[a];
+          const std::complex<double> cyy = std::conj(ya) * yb;
+          const double v[NYY] = {cyy.real(), (std::conj(ta) * yb).real(), ma * cyy.imag(), (std::conj(ta) * tb).real(),
+                                 ma * mb * cyy.real(), -la * (la + 1.0) * cyy.real()};
+          for (int ty = 0; ty < NYY; ty++) {
+            YY[((size_t)ty * NA2 + a * NA + b) * nang + ia] = v[ty];
+            YYT[((size_t)ty * nang + ia) * NA2 + a * NA + b] = v[ty];
+          }
+        }
+    s.d_YY.upload(YY);
+    s.d_YYT.upload(YYT);
+  }
+  {
+    std::vector<int> boq(std::max(NA2, NN)), bot(std::max(nang, nrad));
+    for (size_t k = 0; k < boq.size(); k++) boq[k] = (int)(k * NRR * nrad);
+    for (size_t k = 0; k < bot.size(); k++) bot[k] = (int)(k * NN);
+    s.d_bo_q.upload(boq);
+    s.d_bo_t.upload(bot);
+  }
+  s.gd = GridDev{Nel, NA, NA2, NI, NN, nang, nrad, t.Nrad, (int64_t)nang * nrad, s.d_efirst.p, s.d_en.p,
+                 s.d_w.p, s.d_rr.p, s.d_sth.p};
+  s.d_P.alloc((size_t)2 * s.nbf * s.nbf);
+  s.d_H.alloc((size_t)s.nbf * s.nbf);
+  s.d_Pe.alloc((size_t)2 * Nel * NA2 * NN);
+  s.d_Q.alloc((size_t)2 * Nel * NA2 * NRR * nrad);
+  s.d_D.alloc((size_t)NCOMBO * s.N);
+  s.d_dens.alloc((size_t)2 * 6 * s.N);
+  s.d_C.alloc((size_t)NCOMBO * s.N);
+  s.d_T.alloc((size_t)(NCOMBO + 1) * Nel * nang * NN);
+  s.d_Hs.alloc((size_t)Nel * NA2 * NN);
+  s.d_Hx.alloc((size_t)Nel * NA2 * NN);
+  s.d_sums.alloc(4);
+  s.d_io.alloc((size_t)3 * s.N);
+  s.d_v.alloc((size_t)12 * s.N);
+}
+
+GridEngine::~GridEngine() {}
+int64_t GridEngine::npoints() const { return p_->N; }
+
+void GridEngine::density(const double *Pa, int64_t ldPa, const double *Pb, int64_t ldPb, int flags, double *rho,
+                         double *sigma, double *tau, double *lapl, double *weights, double *Nel, double *Ekin) {
+  Impl &s = *p_;
+  CK(cudaSetDevice(s.device));
+  const GridDev &g = s.gd;
+  const int nspin = Pb ? 2 : 1;
+  const size_t n = (size_t)s.nbf;
+  const int64_t N = s.N;
+  s.polarized = Pb != nullptr;
+  s.dens_flags = flags;
+  CK(cudaMemsetAsync(s.d_sums.p, 0, 4 * sizeof(double), s.st));
+  // combos: (yy type, rr type) per D_j; the Laplacian combo has two entries
+  static const int yyt[NCOMBO + 1] = {0, 0, 1, 2, 0, 3, 4, 0, 5}, rrt[NCOMBO + 1] = {0, 1, 0, 0, 2, 0, 0, 3, 4};
+  for (int sp = 0; sp < nspin; sp++) {
+    const double *P = sp ? Pb : Pa;
+    const int64_t ld = sp ? ldPb : ldPa;
+    double *dP = s.d_P.p + (size_t)sp * n * n;
+    CK(cudaMemcpy2DAsync(dP, n * sizeof(double), P, ld * sizeof(double), n * sizeof(double), n, cudaMemcpyHostToDevice, s.st));
+    double *Pe = s.d_Pe.p + (size_t)sp * g.Nel * g.NA2 * g.NN;
+    k_grid_pack<<<dim3(g.Nel, g.NA2), 128, 0, s.st>>>(g, dP, (int64_t)n, Pe);
+    CK(cudaGetLastError());
+    // stage 1: Q[e] = Pe[e] . RR[e]
+    double *Q = s.d_Q.p + (size_t)sp * g.Nel * g.NA2 * NRR * g.nrad;
+    std::vector<dev::GemmItem> items;
+    std::vector<dev::GemmEntry> entries;
+    for (int e = 0; e < g.Nel; e++) {
+      dev::GemmItem it{};
+      it.C = Q + (size_t)e * g.NA2 * NRR * g.nrad;
+      it.browoff = s.d_bo_q.p;
+      it.M = g.NA2;
+      it.N = NRR * g.nrad;
+      it.K = g.NN;
+      it.ent0 = (int)entries.size();
+      entries.push_back(dev::GemmEntry{Pe + (size_t)e * g.NA2 * g.NN, s.d_RR.p + (size_t)e * g.NN * NRR * g.nrad, g.NN});
+      it.ent1 = (int)entries.size();
+      it.accumulate = 0;
+      it.ldc = NRR * g.nrad;
+      it.alpha = 1.0;
+      items.push_back(it);
+    }
+    s.gemm(items, entries, g.NA2, NRR * g.nrad);
+    // stage 2: D_j[e][ia][ir] = YYT_j . Q[e][:, type_j]
+    items.clear();
+    entries.clear();
+    for (int j = 0; j < NCOMBO; j++) {
+      const bool need = j == 0 || ((flags & GRID_GRAD) && j >= 1 && j <= 3) ||
+                        ((flags & (GRID_TAU | GRID_LAPL)) && j >= 4 && j <= 6) || ((flags & GRID_LAPL) && j == 7);
+      if (!need) continue;
+      for (int e = 0; e < g.Nel; e++) {
+        dev::GemmItem it{};
+        it.C = s.d_D.p + (size_t)j * N + (size_t)e * g.npe;
+        it.browoff = s.d_bo_q.p;
+        it.M = g.nang;
+        it.N = g.nrad;
+        it.K = g.NA2;
+        it.ent0 = (int)entries.size();
+        const double *Qe = Q + (size_t)e * g.NA2 * NRR * g.nrad;
+        entries.push_back(dev::GemmEntry{s.d_YYT.p + (size_t)yyt[j] * g.nang * g.NA2, Qe + rrt[j] * g.nrad, g.NA2});
+        if (j == 7) entries.push_back(dev::GemmEntry{s.d_YYT.p + (size_t)yyt[8] * g.nang * g.NA2, Qe + rrt[8] * g.nrad, g.NA2});
+        it.ent1 = (int)entries.size();
+        it.accumulate = 0;
+        it.ldc = g.nrad;
+        it.alpha = 1.0;
+        items.push_back(it);
+      }
+    }
+    s.gemm(items, entries, g.nang, g.nrad);
+    k_grid_points<<<592, 256, 0, s.st>>>(g, s.d_D.p, flags, s.dens(sp, 0), s.dens(sp, 1), s.dens(sp, 4), s.dens(sp, 5),
+                                         s.d_sums.p);
+    CK(cudaGetLastError());
+  }
+  // outputs in libxc layout
+  auto out = [&](double *host, const double *a, const double *b, const double *c, int nc) {
+    if (!host) return;
+    k_interleave<<<592, 256, 0, s.st>>>(a, b, c, nc, N, s.d_io.p);
+    CK(cudaMemcpyAsync(host, s.d_io.p, (size_t)nc * N * sizeof(double), cudaMemcpyDeviceToHost, s.st));
+    CK(cudaStreamSynchronize(s.st));
+  };
+  out(rho, s.dens(0, 0), s.dens(1, 0), nullptr, nspin);
+  if ((flags & GRID_GRAD) && sigma) {
+    double *saa = s.d_v.p, *sab = saa + N, *sbb = sab + N;
+    k_sigma<<<592, 256, 0, s.st>>>(s.dens(0, 1), nspin == 2 ? s.dens(1, 1) : nullptr, N, saa, sab, sbb);
+    out(sigma, saa, sab, sbb, nspin == 2 ? 3 : 1);
+  }
+  if ((flags & (GRID_TAU | GRID_LAPL)) && tau) out(tau, s.dens(0, 4), s.dens(1, 4), nullptr, nspin);
+  if ((flags & GRID_LAPL) && lapl) out(lapl, s.dens(0, 5), s.dens(1, 5), nullptr, nspin);
+  if (weights) CK(cudaMemcpyAsync(weights, s.d_w.p, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, s.st));
+  double sums[4];
+  CK(cudaMemcpyAsync(sums, s.d_sums.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, s.st));
+  CK(cudaStreamSynchronize(s.st));
+  if (Nel) *Nel = sums[0];
+  if (Ekin) *Ekin = sums[1];
+}
+
+void GridEngine::fxc(int flags, bool beta, const double *exc, const double *vrho, const double *vsigma, const double *vtau,
+                     const double *vlapl, double *Ha, int64_t ldHa, double *Hb, int64_t ldHb, double *Exc) {
+  Impl &s = *p_;
+  CK(cudaSetDevice(s.device));
+  const GridDev &g = s.gd;
+  const int64_t N = s.N;
+  const int nspin = s.polarized ? 2 : 1;
+  const size_t n = (size_t)s.nbf;
+  const bool gga = (flags & GRID_GRAD) && vsigma;
+  if (gga && !(s.dens_flags & GRID_GRAD)) throw std::logic_error("hfq_grid_fxc: gradient was not computed by hfq_grid_density");
+  // device copies of the functional output, de-interleaved: v[0..1] vrho, v[2..4] vsigma, v[5..6] vtau, v[7..8] vlapl, v[9] exc
+  auto put = [&](const double *host, int nc, int slot0) {
+    if (!host) return;
+    CK(cudaMemcpyAsync(s.d_io.p, host, (size_t)nc * N * sizeof(double), cudaMemcpyHostToDevice, s.st));
+    for (int c = 0; c < nc; c++) k_deinterleave<<<592, 256, 0, s.st>>>(s.d_io.p, nc, c, N, s.d_v.p + (size_t)(slot0 + c) * N);
+    CK(cudaStreamSynchronize(s.st));
+  };
+  put(vrho, nspin, 0);
+  if (gga) put(vsigma, nspin == 2 ? 3 : 1, 2);
+  if (vtau) put(vtau, nspin, 5);
+  if (vlapl) put(vlapl, nspin, 7);
+  if (exc) {
+    put(exc, 1, 9);
+    CK(cudaMemsetAsync(s.d_sums.p + 2, 0, sizeof(double), s.st));
+    k_exc<<<592, 256, 0, s.st>>>(s.d_w.p, s.d_v.p + 9 * N, s.dens(0, 0), nspin == 2 ? s.dens(1, 0) : nullptr, N, s.d_sums.p + 2);
+  }
+  static const int yyt[NCOMBO + 1] = {0, 0, 1, 2, 0, 3, 4, 0, 5}, rrt[NCOMBO + 1] = {0, 1, 0, 0, 2, 0, 0, 3, 4};
+  for (int sp = 0; sp < nspin; sp++) {
+    if (sp == 1 && !beta) continue;
+    double *v = s.d_v.p;
+    const double *vr = v + (size_t)sp * N;
+    const double *vs_same = gga ? v + (size_t)(2 + (nspin == 2 ? 2 * sp : 0)) * N : nullptr;
+    const double *vs_ab = (gga && nspin == 2) ? v + 3 * N : nullptr;
+    const double *vt = vtau ? v + (size_t)(5 + sp) * N : nullptr;
+    const double *vl = vlapl ? v + (size_t)(7 + sp) * N : nullptr;
+    // reference quirk: the unrestricted branch applies the tau/laplacian kinetic term only when tau is present
+    const int use_vtl = (nspin == 2) ? (vt != nullptr) : (vt != nullptr || vl != nullptr);
+    k_grid_weights<<<592, 256, 0, s.st>>>(g, gga ? GRID_GRAD : 0, vr, vs_same, vs_ab, vt, vl, s.dens(sp, 1),
+                                          s.dens(1 - sp, 1), use_vtl, s.d_C.p);
+    CK(cudaGetLastError());
+    // stage 1: T_j[e][ia][(r,c)] = C_j[e][ia][ir] . RRT[e][type_j][ir][(r,c)]
+    std::vector<int> combos = {0};
+    if (gga) { combos.push_back(1); combos.push_back(2); combos.push_back(3); }
+    if (use_vtl) { combos.push_back(4); combos.push_back(5); combos.push_back(6); }
+    if (vl) { combos.push_back(7); combos.push_back(8); }
+    std::vector<dev::GemmItem> items;
+    std::vector<dev::GemmEntry> entries;
+    const size_t tsz = (size_t)g.Nel * g.nang * g.NN;
+    for (int j : combos)
+      for (int e = 0; e < g.Nel; e++) {
+        dev::GemmItem it{};
+        it.C = s.d_T.p + (size_t)j * tsz + (size_t)e * g.nang * g.NN;
+        it.browoff = s.d_bo_t.p;
+        it.M = g.nang;
+        it.N = g.NN;
+        it.K = g.nrad;
+        it.ent0 = (int)entries.size();
+        const int cj = j == 8 ? 7 : j;
+        entries.push_back(dev::GemmEntry{s.d_C.p + (size_t)cj * N + (size_t)e * g.npe,
+                                         s.d_RRT.p + ((size_t)e * NRR + rrt[j]) * g.nrad * g.NN, g.nrad});
+        it.ent1 = (int)entries.size();
+        it.accumulate = 0;
+        it.ldc = g.NN;
+        it.alpha = 1.0;
+        items.push_back(it);
+      }
+    s.gemm(items, entries, g.nang, g.NN);
+    // stage 2: Hs / Hx [e][(a,b)][(r,c)] = sum_j YY_j . T_j[e]
+    items.clear();
+    entries.clear();
+    for (int grp = 0; grp < 2; grp++)
+      for (int e = 0; e < g.Nel; e++) {
+        dev::GemmItem it{};
+        it.C = (grp ? s.d_Hx.p : s.d_Hs.p) + (size_t)e * g.NA2 * g.NN;
+        it.browoff = s.d_bo_t.p;
+        it.M = g.NA2;
+        it.N = g.NN;
+        it.K = g.nang;
+        it.ent0 = (int)entries.size();
+        for (int j : combos) {
+          const bool sym = (j == 0 || (j >= 4 && j <= 6));
+          if (sym != (grp == 0)) continue;
+          entries.push_back(dev::GemmEntry{s.d_YY.p + (size_t)yyt[j] * g.NA2 * g.nang,
+                                           s.d_T.p + (size_t)j * tsz + (size_t)e * g.nang * g.NN, g.nang});
+        }
+        it.ent1 = (int)entries.size();
+        it.accumulate = 0;
+        it.ldc = g.NN;
+        it.alpha = 1.0;
+        items.push_back(it);   // an item without entries writes zeros
+      }
+    s.gemm(items, entries, g.NA2, g.NN);
+    k_grid_unpack<<<dim3(g.Nang, g.Nang), 256, 0, s.st>>>(g, s.d_Hs.p, s.d_Hx.p, s.d_H.p, (int64_t)n);
+    CK(cudaGetLastError());
+    double *H = sp ? Hb : Ha;
+    const int64_t ld = sp ? ldHb : ldHa;
+    CK(cudaMemcpy2DAsync(H, ld * sizeof(double), s.d_H.p, n * sizeof(double), n * sizeof(double), n, cudaMemcpyDeviceToHost, s.st));
+    CK(cudaStreamSynchronize(s.st));
+  }
+  if (exc && Exc) {
+    CK(cudaMemcpyAsync(Exc, s.d_sums.p + 2, sizeof(double), cudaMemcpyDeviceToHost, s.st));
+    CK(cudaStreamSynchronize(s.st));
+  }
+}
+
+}  // namespace hfq

@@ -1,0 +1,108 @@
+// Host tables of the atomic DFT grid: radial functions (B/r and its derivatives) at the
+// modified Gauss-Chebyshev nodes of every element, the theta x phi compound rule and the
+// spherical harmonics with their theta derivatives.
+// Reference behaviour: libhelfem/src/RadialBasis.cpp:868-926 (get_bf/get_df/get_lf),
+// src/general/angular.cpp:21-69, src/general/spherical_harmonics.cpp:20-35,
+// src/atomic/TwoDBasis.cpp:1133-1235 (eval_bf/eval_df/eval_lf).
+#include <cmath>
+#include <stdexcept>
+
+#include "fem.h"
+#include "grid.h"
+
+namespace hfq {
+
+static std::complex<double> ylm(int l, int m, double cth, double phi) {
+  if (m < 0) {
+    const std::complex<double> v = std::conj(ylm(l, -m, cth, phi));
+    return ((-m) & 1) ? -v : v;
+  }
+  if (m > l) return 0.0;
+  // std::sph_legendre: normalised associated Legendre function incl. the Condon-Shortley phase
+  return std::polar(1.0, m * phi) * std::sph_legendre((unsigned)l, (unsigned)m, std::acos(cth));
+}
+
+GridTables build_atomic_grid(const BasisTables &t, int lang, int mang) {
+  if (t.kind != BasisKind::Atomic) throw std::logic_error("build_atomic_grid: atomic basis required");
+  if (t.bval.empty()) throw std::logic_error("build_atomic_grid: basis was not built by this library");
+  GridTables g;
+  g.lang = lang;
+  g.mang = mang;
+  g.nang = lang * mang;
+  g.nrad = t.nquad;
+  g.Nel = t.Nel;
+  g.Nang = t.Nang();
+  g.NI = 0;
+  for (int n : t.en) g.NI = std::max(g.NI, n);
+  // angular rule: Chebyshev in cos(theta) x uniform phi
+  std::vector<double> xl, wl;
+  chebyshev_rule(lang, xl, wl);
+  const double dphi = 2.0 * std::acos(-1.0) / mang;
+  for (int i = 0; i < lang; i++)
+    for (int j = 0; j < mang; j++) {
+      g.cth.push_back(xl[i]);
+      g.phi.push_back(j * dphi);
+      g.wang.push_back(wl[i] * dphi);
+    }
+  // angular functions
+  g.Y.assign((size_t)g.Nang * g.nang, 0.0);
+  g.Th.assign((size_t)g.Nang * g.nang, 0.0);
+  for (int a = 0; a < g.Nang; a++) {
+    const int l = t.lval[a], m = t.mval[a];
+    for (int ia = 0; ia < g.nang; ia++) {
+      const double c = g.cth[ia], p = g.phi[ia];
+      const double sinth = std::sqrt(std::max((1.0 - c) * (1.0 + c), 0.0));
+      const double cot = sinth > 0.0 ? c / sinth : 0.0;
+      const std::complex<double> y = ylm(l, m, c, p);
+      std::complex<double> ang = (double)m * cot * y;
+      if (m < l) ang += std::sqrt((double)(l - m) * (l + m + 1)) * std::polar(1.0, -p) * ylm(l, m + 1, c, p);
+      g.Y[(size_t)a * g.nang + ia] = y;
+      g.Th[(size_t)a * g.nang + ia] = ang;
+    }
+  }
+  // radial functions
+  const FEBasis fe(t.nnodes, t.bval, true, true);
+  std::vector<double> xq, wq;
+  chebyshev_rule(g.nrad, xq, wq);
+  const size_t tsz = (size_t)g.Nel * g.NI * g.nrad;
+  g.F.assign(tsz, 0.0);
+  g.D.assign(tsz, 0.0);
+  g.L1.assign(tsz, 0.0);
+  g.F2.assign(tsz, 0.0);
+  for (int e = 0; e < g.Nel; e++) {
+    const std::vector<double> r = fe.coord(xq, e);
+    for (int q = 0; q < g.nrad; q++) {
+      g.r.push_back(r[q]);
+      g.wrad.push_back(wq[q] * fe.scale(e));
+    }
+    Mat f, d, l2;
+    if (e == 0) {
+      f = fe.eval_over_r(xq, 0, e);
+      d = fe.eval_over_r(xq, 1, e);
+      l2 = fe.eval_over_r(xq, 2, e);
+    } else {
+      const Mat B0 = fe.eval_dnf(xq, 0, e), B1 = fe.eval_dnf(xq, 1, e), B2 = fe.eval_dnf(xq, 2, e);
+      f = B0;
+      d = B0;
+      l2 = B0;
+      for (int j = 0; j < B0.cols; j++)
+        for (int q = 0; q < g.nrad; q++) {
+          const double ir = 1.0 / r[q];
+          f(q, j) = B0(q, j) * ir;
+          d(q, j) = (-B0(q, j) * ir + B1(q, j)) * ir;
+          l2(q, j) = ((2.0 * B0(q, j) * ir - 2.0 * B1(q, j)) * ir + B2(q, j)) * ir;
+        }
+    }
+    for (int j = 0; j < f.cols; j++)
+      for (int q = 0; q < g.nrad; q++) {
+        const size_t o = ((size_t)e * g.NI + j) * g.nrad + q;
+        g.F[o] = f(q, j);
+        g.D[o] = d(q, j);
+        g.L1[o] = l2(q, j) + 2.0 * d(q, j) / r[q];
+        g.F2[o] = f(q, j) / (r[q] * r[q]);
+      }
+  }
+  return g;
+}
+
+}  // namespace hfq

@@ -34,7 +34,7 @@ struct BasisDev {
 };
 
 // sum of squares of every (ang a, ang b) block -> norms2[a*Nang+b]
-__global__ void k_block_norms(BasisDev b, const double *__restrict__ P, int64_t ld, double *__restrict__ norms2) {
+static __global__ void k_block_norms(BasisDev b, const double *__restrict__ P, int64_t ld, double *__restrict__ norms2) {
   const int a = blockIdx.x, c = blockIdx.y;
   const int sa = b.ang_skip[a], sc = b.ang_skip[c];
   const int na = b.Nrad - sa, nc = b.Nrad - sc;
@@ -57,7 +57,7 @@ __global__ void k_block_norms(BasisDev b, const double *__restrict__ P, int64_t 
 }
 
 // grid (Nrad [column radial c], nactive sector pairs); splist[y] = sp index
-__global__ void k_pack(BasisDev b, const double *__restrict__ P, int64_t ld, const int *__restrict__ splist,
+static __global__ void k_pack(BasisDev b, const double *__restrict__ P, int64_t ld, const int *__restrict__ splist,
                        double *__restrict__ Ppix) {
   const int c = blockIdx.x, sp = splist[blockIdx.y];
   const int sa = sp / b.ns, sb = sp % b.ns;
@@ -339,7 +339,7 @@ k_gemm(const GemmItem *__restrict__ items, const GemmEntry *__restrict__ entries
 //   pair1 = out_fast ? rj + ri*n : ri + rj*n
 // grid (n*n rows), dst row stride = ldT
 // ---------------------------------------------------------------------------
-__global__ void k_build_tperm(const double *__restrict__ B, const double *__restrict__ sigma, int n, int rank, int nch,
+static __global__ void k_build_tperm(const double *__restrict__ B, const double *__restrict__ sigma, int n, int rank, int nch,
                               int out_fast, double *__restrict__ dst, int64_t ldT) {
   const int row = blockIdx.x, rj = row / n, rk = row % n, nn = n * n;
   for (int col = threadIdx.x; col < nch * nch * nn; col += blockDim.x) {
@@ -715,7 +715,7 @@ struct UnpackDev {
   int S;                  // partial accumulators per output pair (K-split of the in-element GEMM)
 };
 
-__global__ void k_unpack_K(BasisDev b, UnpackDev u, const double *__restrict__ Kacc, double *__restrict__ K, int64_t ld) {
+static __global__ void k_unpack_K(BasisDev b, UnpackDev u, const double *__restrict__ Kacc, double *__restrict__ K, int64_t ld) {
   const int angk = blockIdx.y, angj = blockIdx.x;
   const int sj = b.ang_skip[angj], sk = b.ang_skip[angk];
   const int nj = b.Nrad - sj, nk = b.Nrad - sk;
@@ -760,7 +760,7 @@ struct JRadDev {
   int nM;
 };
 
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 k_jradial(BasisDev b, JRadDev jr, const double *__restrict__ Paux, double *__restrict__ JauxT) {
   const int L = blockIdx.x, Mi = blockIdx.y, tid = threadIdx.x;
   const int nq = b.NL * b.nch;
@@ -855,7 +855,7 @@ k_jradial(BasisDev b, JRadDev jr, const double *__restrict__ Paux, double *__res
 }
 
 // Coulomb unpack: dense J[(ang i, r), (ang j, c)] = Jsec[sp=(sj,si)][pix=(r,c)][pos_j*NP + pos_i]
-__global__ void k_unpack_J(BasisDev b, const int *__restrict__ ang_sec, const int *__restrict__ ang_pos,
+static __global__ void k_unpack_J(BasisDev b, const int *__restrict__ ang_sec, const int *__restrict__ ang_pos,
                            const int *__restrict__ sp_active, const double *__restrict__ Jsec, double *__restrict__ J,
                            int64_t ld) {
   const int angi = blockIdx.x, angj = blockIdx.y;

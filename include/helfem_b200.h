@@ -117,6 +117,31 @@ int hfq_coulomb_device(hfq_ctx *ctx, const double *dP, int64_t ldP, double *dJ, 
 int hfq_exchange_device(hfq_ctx *ctx, const double *dP, int64_t ldP, double *dK, int64_t ldK, int shard,
                         int nshards, void *stream);
 
+/* ---- DFT quadrature grid: DFTGrid::eval_Fxc of the atomic basis --------------------------------
+ * (src/atomic/dftgrid.h:156,159; worker src/atomic/dftgrid.cpp:51-242, :304-465, :470-576).
+ * The functional evaluation itself stays on libxc's definitions: the GPU produces the densities in
+ * libxc's layout, the caller (or hfq_eval_fxc for the built-in Slater exchange) evaluates the
+ * functional, the GPU assembles the matrix.  Point p = (element, angular point, radial point);
+ * spin components are interleaved per point exactly as libxc expects them
+ * (src/general/dftgrid_common.cpp:60-73): rho[p*ns + s], sigma[p*3 + {aa,ab,bb}] (1 component if
+ * restricted), tau, lapl like rho.  flags: 1 gradient, 2 tau, 4 Laplacian. */
+int hfq_grid_attach(hfq_ctx *ctx, int lang, int mang);      /* DFTGrid(&basis, ldft, mdft) */
+int64_t hfq_grid_npoints(const hfq_ctx *ctx);
+/* DFTGridWorker::update_density + compute_Nel/compute_Ekin over all elements.  Pb == NULL: restricted.
+ * Output pointers may be NULL.  weights[p] = w_ang w_rad r^2. */
+int hfq_grid_density(hfq_ctx *ctx, const double *Pa, int64_t ldPa, const double *Pb, int64_t ldPb, int flags,
+                     double *rho, double *sigma, double *tau, double *lapl, double *weights, double *Nel, double *Ekin);
+/* DFTGridWorker::eval_Fxc + eval_Exc for the densities of the last hfq_grid_density call.
+ * vsigma/vtau/vlapl/exc may be NULL; Hb is written only if the density was polarised and beta != 0. */
+int hfq_grid_fxc(hfq_ctx *ctx, int flags, int beta, const double *exc, const double *vrho, const double *vsigma,
+                 const double *vtau, const double *vlapl, double *Ha, int64_t ldHa, double *Hb, int64_t ldHb, double *Exc);
+/* DFTGrid::eval_Fxc(x_func, .., c_func, .., P[a,b] -> H[a,b], Exc, Nel, Ekin, beta, thr) for the
+ * functionals built into this library (x_func = 1: Slater exchange, x_func <= 0: none -- the HF
+ * drivers still call eval_Fxc to integrate Nel).  Other ids return HFQ_ERR_INVALID. */
+int hfq_eval_fxc(hfq_ctx *ctx, int x_func, int c_func, const double *Pa, int64_t ldPa, const double *Pb, int64_t ldPb,
+                 double *Ha, int64_t ldHa, double *Hb, int64_t ldHb, double *Exc, double *Nel, double *Ekin, int beta,
+                 double thr);
+
 /* Non-zero structure of the last hfq_exchange* result, for compact collectives / copies:
  * bf_sector[Nbf] = sector id of every basis function; pairs = (row sector, column sector) of the
  * blocks that were written (everything else in K is exactly zero).  Returns the number of pairs. */
