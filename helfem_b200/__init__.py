@@ -359,15 +359,17 @@ class TablesBasis(_BasisBase):
             _check(lib().hfq_set_absm_symmetric(self._ctx, int(self._absm)))
 
 
-class AtomicDFTGrid:
-    """helfem::atomic::dftgrid::DFTGrid (src/atomic/dftgrid.h:139-160) on the GPU.
+class DFTGrid:
+    """DFT quadrature grid on the GPU: helfem::atomic::dftgrid::DFTGrid (src/atomic/dftgrid.h:139-160)
+    for an atomic basis, helfem::diatomic::dftgrid_purem::PureMDFTGrid
+    (src/diatomic/dftgrid_purem.h:140-160) for a diatomic basis (mang is ignored there).
 
     ``eval_Fxc`` has the reference's argument order; functionals other than the built-in Slater
     exchange are evaluated by the caller between ``density`` and ``fxc`` (libxc layout)."""
 
     GRAD, TAU, LAPL = 1, 2, 4
 
-    def __init__(self, basis, lang, mang):
+    def __init__(self, basis, lang, mang=1):
         self.basis = basis
         _check(lib().hfq_grid_attach(basis._context(), lang, mang))
         self.N = int(lib().hfq_grid_npoints(basis._context()))
@@ -422,3 +424,7 @@ class AtomicDFTGrid:
                                   n, Ha.ctypes.data, n, Hb.ctypes.data if pol else None, n, ctypes.byref(exc),
                                   ctypes.byref(nel), ctypes.byref(ekin), int(beta), thr))
         return ((Ha, Hb) if pol else Ha), exc.value, nel.value, ekin.value
+
+
+AtomicDFTGrid = DFTGrid
+PureMDFTGrid = DFTGrid

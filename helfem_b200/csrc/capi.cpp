@@ -301,7 +301,10 @@ int hfq_grid_attach(hfq_ctx *ctx, int lang, int mang) {
   if (!ctx || lang < 1 || mang < 1) return fail(HFQ_ERR_INVALID, "hfq_grid_attach: invalid argument");
   std::lock_guard<std::mutex> lk(ctx->mu);
   return guarded([&] {
-    const hfq::GridTables g = hfq::build_atomic_grid(ctx->eng->tables(), lang, mang);
+    const hfq::BasisTables &bt = ctx->eng->tables();
+    // atomic: 3D grid; diatomic: the pure-m grid the reference uses at --symmetry >= 1 (mang ignored)
+    const hfq::GridTables g = bt.kind == hfq::BasisKind::Atomic ? hfq::build_atomic_grid(bt, lang, mang)
+                                                                 : hfq::build_diatomic_purem_grid(bt, lang);
     ctx->grid = std::make_unique<hfq::GridEngine>(ctx->eng->tables(), g, ctx->eng->device(), ctx->eng->stream());
     return HFQ_OK;
   });

@@ -44,26 +44,30 @@ struct Buf {
 };
 
 constexpr int NCOMBO = 8;   // 00, 10, 20, 30, 11, 22, 33, L0
-constexpr int NRR = 5;      // FF, DF, DD, LF, 2F
-constexpr int NYY = 6;      // YY, ThY, PhY, ThTh, PhPh, YlY
+constexpr int NRR = 6;      // FF, DF, DD, LF, 2F, 3F
+constexpr int NYY = 7;      // YY, ThY, PhY, ThTh, PhPh, YlY, Ym2Y
 
 struct GridDev {
-  int Nel, Nang, NA2, NI, NN, nang, nrad, Nrad;
+  int Nel, Nang, NA2, NI, NN, nang, nrad, Nrad;   // NA2 = number of coupled angular pairs
   int64_t npe;   // points per element
   const int *efirst, *en;
-  const double *w;       // [Nel][nang][nrad] total quadrature weight
-  const double *rr;      // [Nel][nrad] radius
-  const double *sth;     // [nang] sin(theta)
+  const int *pair_a, *pair_b;   // [NA2]
+  const int *pair_of;           // [Nang*Nang] pair index or -1
+  const int *ang_off, *ang_skip;   // dense index map (boundary functions of dropped shells removed)
+  const double *w;       // [N] total quadrature weight
+  const double *sc;      // [3][N] scale factors of the three orthogonal directions
+  const double *lfac;    // [N] prefactor of the Laplacian
 };
 
 // Pe[e][(a,b)][(r,c)] = P[(a, f+r), (b, f+c)]     grid (Nel, NA2)
 __global__ void k_grid_pack(GridDev g, const double *__restrict__ P, int64_t ld, double *__restrict__ Pe) {
-  const int e = blockIdx.x, ab = blockIdx.y, a = ab / g.Nang, b = ab % g.Nang;
-  const int f = g.efirst[e], n = g.en[e];
+  const int e = blockIdx.x, ab = blockIdx.y, a = g.pair_a[ab], b = g.pair_b[ab];
+  const int f = g.efirst[e], n = g.en[e], sa = g.ang_skip[a], sb = g.ang_skip[b];
   double *dst = Pe + ((int64_t)e * g.NA2 + ab) * g.NN;
   for (int idx = threadIdx.x; idx < g.NN; idx += blockDim.x) {
     const int r = idx / g.NI, c = idx % g.NI;
-    dst[idx] = (r < n && c < n) ? P[(int64_t)a * g.Nrad + f + r + ((int64_t)b * g.Nrad + f + c) * ld] : 0.0;
+    const bool ok = r < n && c < n && f + r >= sa && f + c >= sb;
+    dst[idx] = ok ? P[(int64_t)g.ang_off[a] + f + r - sa + ((int64_t)g.ang_off[b] + f + c - sb) * ld] : 0.0;
   }
 }
 
@@ -75,21 +79,20 @@ __global__ void k_grid_points(GridDev g, const double *__restrict__ D, int flags
   const int64_t N = (int64_t)g.Nel * g.npe;
   double sn = 0.0, sk = 0.0;
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < N; p += (int64_t)gridDim.x * blockDim.x) {
-    const int ir = (int)(p % g.nrad), ia = (int)((p / g.nrad) % g.nang), e = (int)(p / g.npe);
-    const double r = g.rr[e * g.nrad + ir], st = r, sp = r * g.sth[ia], w = g.w[p];
+    const double s0 = g.sc[p], st = g.sc[N + p], sp = g.sc[2 * N + p], w = g.w[p];
     const double d0 = D[p];
     rho[p] = d0;
     sn += w * d0;
     if (flags & GRID_GRAD) {
-      grho[p] = 2.0 * D[N + p];
+      grho[p] = 2.0 * D[N + p] / s0;
       grho[N + p] = 2.0 * D[2 * N + p] / st;
       grho[2 * N + p] = 2.0 * D[3 * N + p] / sp;
     }
     if (flags & (GRID_TAU | GRID_LAPL)) {
-      const double kin = D[4 * N + p] + D[5 * N + p] / (st * st) + D[6 * N + p] / (sp * sp);
+      const double kin = D[4 * N + p] / (s0 * s0) + D[5 * N + p] / (st * st) + D[6 * N + p] / (sp * sp);
       tau[p] = 0.5 * kin;
       sk += w * 0.5 * kin;
-      if (flags & GRID_LAPL) lapl[p] = 2.0 * (kin + D[7 * N + p]);
+      if (flags & GRID_LAPL) lapl[p] = 2.0 * (kin + g.lfac[p] * D[7 * N + p]);
     }
   }
   for (int o = 16; o > 0; o >>= 1) {
@@ -111,11 +114,10 @@ __global__ void k_grid_weights(GridDev g, int flags, const double *__restrict__ 
                                const double *__restrict__ g_other, int use_vtl, double *__restrict__ C) {
   const int64_t N = (int64_t)g.Nel * g.npe;
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < N; p += (int64_t)gridDim.x * blockDim.x) {
-    const int ir = (int)(p % g.nrad), ia = (int)((p / g.nrad) % g.nang), e = (int)(p / g.npe);
-    const double r = g.rr[e * g.nrad + ir], st = r, sp = r * g.sth[ia], w = g.w[p];
+    const double s0 = g.sc[p], st = g.sc[N + p], sp = g.sc[2 * N + p], w = g.w[p];
     C[p] = w * vr[p];
     if (flags & GRID_GRAD) {
-      const double sc[3] = {1.0, st, sp};
+      const double sc[3] = {s0, st, sp};
       for (int c = 0; c < 3; c++) {
         double gv = 2.0 * vs_same[p] * g_same[c * N + p];
         if (vs_ab) gv += vs_ab[p] * g_other[c * N + p];
@@ -127,11 +129,11 @@ __global__ void k_grid_weights(GridDev g, int flags, const double *__restrict__ 
       if (vt) vtl += 0.5 * vt[p];
       if (vl) vtl += 2.0 * vl[p];
       vtl *= w;
-      C[4 * N + p] = vtl;
+      C[4 * N + p] = vtl / (s0 * s0);
       C[5 * N + p] = vtl / (st * st);
       C[6 * N + p] = vtl / (sp * sp);
     }
-    if (vl) C[7 * N + p] = w * vl[p];
+    if (vl) C[7 * N + p] = w * vl[p] * g.lfac[p];
   }
 }
 
@@ -140,17 +142,21 @@ __global__ void k_grid_weights(GridDev g, int flags, const double *__restrict__ 
 __global__ void k_grid_unpack(GridDev g, const double *__restrict__ Hs, const double *__restrict__ Hx,
                               double *__restrict__ H, int64_t ld) {
   const int a = blockIdx.x, b = blockIdx.y;
+  const int sa = g.ang_skip[a], sb = g.ang_skip[b];
+  const int pab = g.pair_of[a * g.Nang + b], pba = g.pair_of[b * g.Nang + a];
   for (int idx = threadIdx.x; idx < g.Nrad * g.Nrad; idx += blockDim.x) {
     const int R = idx % g.Nrad, Cc = idx / g.Nrad;
+    if (R < sa || Cc < sb) continue;
     double s = 0.0;
-    for (int e = 0; e < g.Nel; e++) {
-      const int r = R - g.efirst[e], c = Cc - g.efirst[e];
-      if (r < 0 || c < 0 || r >= g.en[e] || c >= g.en[e]) continue;
-      const int64_t eb = (int64_t)e * g.NA2;
-      s += Hs[(eb + a * g.Nang + b) * g.NN + r * g.NI + c] + Hx[(eb + a * g.Nang + b) * g.NN + r * g.NI + c] +
-           Hx[(eb + b * g.Nang + a) * g.NN + c * g.NI + r];
-    }
-    H[(int64_t)a * g.Nrad + R + ((int64_t)b * g.Nrad + Cc) * ld] = s;
+    if (pab >= 0)
+      for (int e = 0; e < g.Nel; e++) {
+        const int r = R - g.efirst[e], c = Cc - g.efirst[e];
+        if (r < 0 || c < 0 || r >= g.en[e] || c >= g.en[e]) continue;
+        const int64_t eb = (int64_t)e * g.NA2;
+        s += Hs[(eb + pab) * g.NN + r * g.NI + c] + Hx[(eb + pab) * g.NN + r * g.NI + c] +
+             Hx[(eb + pba) * g.NN + c * g.NI + r];
+      }
+    H[(int64_t)g.ang_off[a] + R - sa + ((int64_t)g.ang_off[b] + Cc - sb) * ld] = s;
   }
 }
 
@@ -199,12 +205,12 @@ struct GridEngine::Impl {
   GridDev gd{};
   int nbf = 0;
   int64_t N = 0;
-  Buf<int> d_efirst, d_en, d_bo_q, d_bo_t;
-  Buf<double> d_w, d_rr, d_sth, d_RR, d_RRT, d_YY, d_YYT;
+  Buf<int> d_efirst, d_en, d_bo_q, d_bo_t, d_pa, d_pb, d_pof, d_aoff, d_askip;
+  Buf<double> d_w, d_sc, d_lfac, d_RR, d_RRT, d_YY, d_YYT;
   Buf<double> d_P, d_Pe, d_Q, d_D, d_dens, d_C, d_T, d_Hs, d_Hx, d_H, d_sums, d_io, d_v;
   Buf<dev::GemmItem> d_items;
   Buf<dev::GemmEntry> d_entries;
-  bool polarized = false;
+  bool polarized = false, pure_m = false;
   int dens_flags = 0;
   // dens layout per spin s: rho [N], grho [3N], tau [N], lapl [N]  -> 6N
   double *dens(int s, int which) { return d_dens.p + ((size_t)s * 6 + which) * N; }
@@ -227,27 +233,47 @@ GridEngine::GridEngine(const BasisTables &t, const GridTables &g, int device, cu
   s.device = device;
   s.st = stream;
   CK(cudaSetDevice(device));
-  const int NA = g.Nang, NA2 = NA * NA, NI = g.NI, NN = NI * NI, nang = g.nang, nrad = g.nrad, Nel = g.Nel;
+  const int NA = g.Nang, NI = g.NI, NN = NI * NI, nang = g.nang, nrad = g.nrad, Nel = g.Nel;
   s.nbf = t.Nbf();
+  s.pure_m = g.pure_m;
   s.N = (int64_t)Nel * nang * nrad;
   s.d_efirst.upload(t.efirst);
   s.d_en.upload(t.en);
-  std::vector<double> w((size_t)s.N), sth(nang);
-  for (int ia = 0; ia < nang; ia++) sth[ia] = std::sqrt(1.0 - g.cth[ia] * g.cth[ia]);
-  for (int e = 0; e < Nel; e++)
-    for (int ia = 0; ia < nang; ia++)
-      for (int ir = 0; ir < nrad; ir++) {
-        const double r = g.r[(size_t)e * nrad + ir];
-        w[((size_t)e * nang + ia) * nrad + ir] = g.wang[ia] * g.wrad[(size_t)e * nrad + ir] * r * r;
+  // coupled angular pairs: all of them (3D grid) or same-m only (phi integrated analytically)
+  std::vector<int> pa, pb, pof((size_t)NA * NA, -1), aoff(NA), askip(NA);
+  for (int a = 0; a < NA; a++)
+    for (int b = 0; b < NA; b++)
+      if (!g.pure_m || t.mval[a] == t.mval[b]) {
+        pof[(size_t)a * NA + b] = (int)pa.size();
+        pa.push_back(a);
+        pb.push_back(b);
       }
-  s.d_w.upload(w);
-  s.d_rr.upload(g.r);
-  s.d_sth.upload(sth);
+  const int NA2 = (int)pa.size();
+  {
+    int off = 0;
+    for (int a = 0; a < NA; a++) {
+      askip[a] = (t.drop_first_m_nonzero && t.mval[a] != 0) ? 1 : 0;
+      aoff[a] = off;
+      off += t.Nrad - askip[a];
+    }
+  }
+  s.d_pa.upload(pa);
+  s.d_pb.upload(pb);
+  s.d_pof.upload(pof);
+  s.d_aoff.upload(aoff);
+  s.d_askip.upload(askip);
+  s.d_w.upload(g.wtot);
+  {
+    std::vector<double> sc;
+    for (int c = 0; c < 3; c++) sc.insert(sc.end(), g.scale[c].begin(), g.scale[c].end());
+    s.d_sc.upload(sc);
+  }
+  s.d_lfac.upload(g.lfac);
   // radial pair tables: RR[e][(r,c)][type*nrad + ir] and RRT[e][type][ir][(r,c)]
   {
     std::vector<double> RR((size_t)Nel * NN * NRR * nrad, 0.0), RRT((size_t)Nel * NRR * nrad * NN, 0.0);
-    const std::vector<double> *rowt[NRR] = {&g.F, &g.D, &g.D, &g.L1, &g.F2};
-    const std::vector<double> *colt[NRR] = {&g.F, &g.F, &g.D, &g.F, &g.F};
+    const std::vector<double> *rowt[NRR] = {&g.F, &g.D, &g.D, &g.L1, &g.F2, &g.F3};
+    const std::vector<double> *colt[NRR] = {&g.F, &g.F, &g.D, &g.F, &g.F, &g.F};
     for (int e = 0; e < Nel; e++)
       for (int ty = 0; ty < NRR; ty++)
         for (int r = 0; r < NI; r++)
@@ -263,20 +289,21 @@ GridEngine::GridEngine(const BasisTables &t, const GridTables &g, int device, cu
   // angular pair tables: YY[type][(a,b)][ia], YYT[type][ia][(a,b)]
   {
     std::vector<double> YY((size_t)NYY * NA2 * nang), YYT((size_t)NYY * nang * NA2);
-    for (int a = 0; a < NA; a++)
-      for (int b = 0; b < NA; b++)
-        for (int ia = 0; ia < nang; ia++) {
-          const std::complex<double> ya = g.Y[(size_t)a * nang + ia], yb = g.Y[(size_t)b * nang + ia];
-          const std::complex<double> ta = g.Th[(size_t)a * nang + ia], tb = g.Th[(size_t)b * nang + ia];
-          const double ma = t.mval[a], mb = t.mval[b], la = t.lval[a];
-          const std::complex<double> cyy = std::conj(ya) * yb;
-          const double v[NYY] = {cyy.real(), (std::conj(ta) * yb).real(), ma * cyy.imag(), (std::conj(ta) * tb).real(),
-                                 ma * mb * cyy.real(), -la * (la + 1.0) * cyy.real()};
-          for (int ty = 0; ty < NYY; ty++) {
-            YY[((size_t)ty * NA2 + a * NA + b) * nang + ia] = v[ty];
-            YYT[((size_t)ty * nang + ia) * NA2 + a * NA + b] = v[ty];
-          }
+    for (int ab = 0; ab < NA2; ab++) {
+      const int a = pa[ab], b = pb[ab];
+      for (int ia = 0; ia < nang; ia++) {
+        const std::complex<double> ya = g.Y[(size_t)a * nang + ia], yb = g.Y[(size_t)b * nang + ia];
+        const std::complex<double> ta = g.Th[(size_t)a * nang + ia], tb = g.Th[(size_t)b * nang + ia];
+        const double ma = t.mval[a], mb = t.mval[b], la = t.lval[a];
+        const std::complex<double> cyy = std::conj(ya) * yb;
+        const double v[NYY] = {cyy.real(), (std::conj(ta) * yb).real(), ma * cyy.imag(), (std::conj(ta) * tb).real(),
+                               ma * mb * cyy.real(), -la * (la + 1.0) * cyy.real(), -ma * ma * cyy.real()};
+        for (int ty = 0; ty < NYY; ty++) {
+          YY[((size_t)ty * NA2 + ab) * nang + ia] = v[ty];
+          YYT[((size_t)ty * nang + ia) * NA2 + ab] = v[ty];
         }
+      }
+    }
     s.d_YY.upload(YY);
     s.d_YYT.upload(YYT);
   }
@@ -288,7 +315,7 @@ GridEngine::GridEngine(const BasisTables &t, const GridTables &g, int device, cu
     s.d_bo_t.upload(bot);
   }
   s.gd = GridDev{Nel, NA, NA2, NI, NN, nang, nrad, t.Nrad, (int64_t)nang * nrad, s.d_efirst.p, s.d_en.p,
-                 s.d_w.p, s.d_rr.p, s.d_sth.p};
+                 s.d_pa.p, s.d_pb.p, s.d_pof.p, s.d_aoff.p, s.d_askip.p, s.d_w.p, s.d_sc.p, s.d_lfac.p};
   s.d_P.alloc((size_t)2 * s.nbf * s.nbf);
   s.d_H.alloc((size_t)s.nbf * s.nbf);
   s.d_Pe.alloc((size_t)2 * Nel * NA2 * NN);
@@ -296,7 +323,7 @@ GridEngine::GridEngine(const BasisTables &t, const GridTables &g, int device, cu
   s.d_D.alloc((size_t)NCOMBO * s.N);
   s.d_dens.alloc((size_t)2 * 6 * s.N);
   s.d_C.alloc((size_t)NCOMBO * s.N);
-  s.d_T.alloc((size_t)(NCOMBO + 1) * Nel * nang * NN);
+  s.d_T.alloc((size_t)(NCOMBO + 2) * Nel * nang * NN);
   s.d_Hs.alloc((size_t)Nel * NA2 * NN);
   s.d_Hx.alloc((size_t)Nel * NA2 * NN);
   s.d_sums.alloc(4);
@@ -319,7 +346,7 @@ void GridEngine::density(const double *Pa, int64_t ldPa, const double *Pb, int64
   s.dens_flags = flags;
   CK(cudaMemsetAsync(s.d_sums.p, 0, 4 * sizeof(double), s.st));
   // combos: (yy type, rr type) per D_j; the Laplacian combo has two entries
-  static const int yyt[NCOMBO + 1] = {0, 0, 1, 2, 0, 3, 4, 0, 5}, rrt[NCOMBO + 1] = {0, 1, 0, 0, 2, 0, 0, 3, 4};
+  static const int yyt[NCOMBO + 2] = {0, 0, 1, 2, 0, 3, 4, 0, 5, 6}, rrt[NCOMBO + 2] = {0, 1, 0, 0, 2, 0, 0, 3, 4, 5};
   for (int sp = 0; sp < nspin; sp++) {
     const double *P = sp ? Pb : Pa;
     const int64_t ld = sp ? ldPb : ldPa;
@@ -365,7 +392,9 @@ void GridEngine::density(const double *Pa, int64_t ldPa, const double *Pb, int64
         it.ent0 = (int)entries.size();
         const double *Qe = Q + (size_t)e * g.NA2 * NRR * g.nrad;
         entries.push_back(dev::GemmEntry{s.d_YYT.p + (size_t)yyt[j] * g.nang * g.NA2, Qe + rrt[j] * g.nrad, g.NA2});
-        if (j == 7) entries.push_back(dev::GemmEntry{s.d_YYT.p + (size_t)yyt[8] * g.nang * g.NA2, Qe + rrt[8] * g.nrad, g.NA2});
+        if (j == 7)
+          for (int x = 8; x <= 9; x++)
+            entries.push_back(dev::GemmEntry{s.d_YYT.p + (size_t)yyt[x] * g.nang * g.NA2, Qe + rrt[x] * g.nrad, g.NA2});
         it.ent1 = (int)entries.size();
         it.accumulate = 0;
         it.ldc = g.nrad;
@@ -427,7 +456,7 @@ void GridEngine::fxc(int flags, bool beta, const double *exc, const double *vrho
     CK(cudaMemsetAsync(s.d_sums.p + 2, 0, sizeof(double), s.st));
     k_exc<<<592, 256, 0, s.st>>>(s.d_w.p, s.d_v.p + 9 * N, s.dens(0, 0), nspin == 2 ? s.dens(1, 0) : nullptr, N, s.d_sums.p + 2);
   }
-  static const int yyt[NCOMBO + 1] = {0, 0, 1, 2, 0, 3, 4, 0, 5}, rrt[NCOMBO + 1] = {0, 1, 0, 0, 2, 0, 0, 3, 4};
+  static const int yyt[NCOMBO + 2] = {0, 0, 1, 2, 0, 3, 4, 0, 5, 6}, rrt[NCOMBO + 2] = {0, 1, 0, 0, 2, 0, 0, 3, 4, 5};
   for (int sp = 0; sp < nspin; sp++) {
     if (sp == 1 && !beta) continue;
     double *v = s.d_v.p;
@@ -436,8 +465,9 @@ void GridEngine::fxc(int flags, bool beta, const double *exc, const double *vrho
     const double *vs_ab = (gga && nspin == 2) ? v + 3 * N : nullptr;
     const double *vt = vtau ? v + (size_t)(5 + sp) * N : nullptr;
     const double *vl = vlapl ? v + (size_t)(7 + sp) * N : nullptr;
-    // reference quirk: the unrestricted branch applies the tau/laplacian kinetic term only when tau is present
-    const int use_vtl = (nspin == 2) ? (vt != nullptr) : (vt != nullptr || vl != nullptr);
+    // reference quirk: the unrestricted branch of the ATOMIC worker applies the tau/laplacian kinetic
+    // term only when tau is present (src/atomic/dftgrid.cpp:426); the pure-m worker tests both (:521)
+    const int use_vtl = (nspin == 2 && !s.pure_m) ? (vt != nullptr) : (vt != nullptr || vl != nullptr);
     k_grid_weights<<<592, 256, 0, s.st>>>(g, gga ? GRID_GRAD : 0, vr, vs_same, vs_ab, vt, vl, s.dens(sp, 1),
                                           s.dens(1 - sp, 1), use_vtl, s.d_C.p);
     CK(cudaGetLastError());
@@ -445,7 +475,7 @@ void GridEngine::fxc(int flags, bool beta, const double *exc, const double *vrho
     std::vector<int> combos = {0};
     if (gga) { combos.push_back(1); combos.push_back(2); combos.push_back(3); }
     if (use_vtl) { combos.push_back(4); combos.push_back(5); combos.push_back(6); }
-    if (vl) { combos.push_back(7); combos.push_back(8); }
+    if (vl) { combos.push_back(7); combos.push_back(8); combos.push_back(9); }
     std::vector<dev::GemmItem> items;
     std::vector<dev::GemmEntry> entries;
     const size_t tsz = (size_t)g.Nel * g.nang * g.NN;
@@ -458,7 +488,7 @@ void GridEngine::fxc(int flags, bool beta, const double *exc, const double *vrho
         it.N = g.NN;
         it.K = g.nrad;
         it.ent0 = (int)entries.size();
-        const int cj = j == 8 ? 7 : j;
+        const int cj = j >= 8 ? 7 : j;
         entries.push_back(dev::GemmEntry{s.d_C.p + (size_t)cj * N + (size_t)e * g.npe,
                                          s.d_RRT.p + ((size_t)e * NRR + rrt[j]) * g.nrad * g.NN, g.nrad});
         it.ent1 = (int)entries.size();

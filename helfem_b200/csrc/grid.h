@@ -17,17 +17,26 @@
 
 namespace hfq {
 
+// Point p = (element e, angular point ia, radial point ir), p = (e*nang + ia)*nrad + ir.
+// Basis function (a, r) at p:  value conj(Y_a(ia)) F_r(ir); derivatives along the three
+// orthogonal directions conj(Y_a) D_r / s0, conj(Th_a) F_r / s1, conj(i m_a Y_a) F_r / s2;
+// Laplacian lfac(p) * conj(Y_a) [ L1_r - l_a(l_a+1) F2_r - m_a^2 F3_r ].
 struct GridTables {
   int lang = 0, mang = 0, nang = 0, nrad = 0, Nel = 0, Nang = 0, NI = 0;
+  bool pure_m = false;                             // only same-m pairs couple (phi integrated analytically)
   std::vector<double> cth, phi, wang;              // [nang]
   std::vector<double> r, wrad;                     // [Nel*nrad]
+  std::vector<double> wtot, scale[3], lfac;        // [N] per point
   // radial tables per element, [Nel][NI][nrad] (zero rows for missing functions)
-  std::vector<double> F, D, L1, F2;
+  std::vector<double> F, D, L1, F2, F3;
   // angular tables [Nang][nang]
   std::vector<std::complex<double>> Y, Th;
 };
 
+// atomic 3D grid (src/atomic/dftgrid.cpp), r x theta x phi
 GridTables build_atomic_grid(const BasisTables &t, int lang, int mang);
+// diatomic pure-m 2D grid (src/diatomic/dftgrid_purem.cpp), mu x nu, phi analytic
+GridTables build_diatomic_purem_grid(const BasisTables &t, int lang);
 
 enum GridFlags { GRID_GRAD = 1, GRID_TAU = 2, GRID_LAPL = 4 };
 

@@ -69,6 +69,7 @@ GridTables build_atomic_grid(const BasisTables &t, int lang, int mang) {
   g.D.assign(tsz, 0.0);
   g.L1.assign(tsz, 0.0);
   g.F2.assign(tsz, 0.0);
+  g.F3.assign(tsz, 0.0);
   for (int e = 0; e < g.Nel; e++) {
     const std::vector<double> r = fe.coord(xq, e);
     for (int q = 0; q < g.nrad; q++) {
@@ -102,6 +103,106 @@ GridTables build_atomic_grid(const BasisTables &t, int lang, int mang) {
         g.F2[o] = f(q, j) / (r[q] * r[q]);
       }
   }
+  // per-point weights and scale factors (1, r, r sin(theta)); src/atomic/dftgrid.cpp:486-512
+  const size_t N = (size_t)g.Nel * g.nang * g.nrad;
+  g.wtot.assign(N, 0.0);
+  g.lfac.assign(N, 1.0);
+  for (auto &sc : g.scale) sc.assign(N, 1.0);
+  for (int e = 0; e < g.Nel; e++)
+    for (int ia = 0; ia < g.nang; ia++) {
+      const double sth = std::sqrt(1.0 - g.cth[ia] * g.cth[ia]);
+      for (int q = 0; q < g.nrad; q++) {
+        const size_t p = ((size_t)e * g.nang + ia) * g.nrad + q;
+        const double r = g.r[(size_t)e * g.nrad + q];
+        g.wtot[p] = g.wang[ia] * g.wrad[(size_t)e * g.nrad + q] * r * r;
+        g.scale[1][p] = r;
+        g.scale[2][p] = r * sth;
+      }
+    }
+  return g;
+}
+
+// Pure-m diatomic grid: real Y_l^m(cos nu) at phi = 0, Gauss-Chebyshev in cos(nu), the FE
+// functions B, B', B'' at the mu quadrature nodes; weight 2 pi w_nu w_mu Rh^3 sinh(mu)
+// (sinh^2 mu + sin^2 nu); scale factors h_mu = h_nu = Rh sqrt(sinh^2 mu + sin^2 nu),
+// h_phi = Rh sinh(mu) sin(nu); Laplacian = (1/h^2) [R'' + coth(mu) R' - (l(l+1) + m^2/sinh^2 mu) R] Y.
+// Reference: src/diatomic/dftgrid_purem.cpp:30-200.
+GridTables build_diatomic_purem_grid(const BasisTables &t, int lang) {
+  if (t.kind != BasisKind::Diatomic) throw std::logic_error("build_diatomic_purem_grid: diatomic basis required");
+  if (t.bval.empty()) throw std::logic_error("build_diatomic_purem_grid: basis was not built by this library");
+  GridTables g;
+  g.pure_m = true;
+  g.lang = lang;
+  g.mang = 1;
+  g.nang = lang;
+  g.nrad = t.nquad;
+  g.Nel = t.Nel;
+  g.Nang = t.Nang();
+  for (int n : t.en) g.NI = std::max(g.NI, n);
+  chebyshev_rule(lang, g.cth, g.wang);
+  g.phi.assign(lang, 0.0);
+  g.Y.assign((size_t)g.Nang * g.nang, 0.0);
+  g.Th.assign((size_t)g.Nang * g.nang, 0.0);
+  for (int a = 0; a < g.Nang; a++) {
+    const int l = t.lval[a], m = t.mval[a];
+    for (int ia = 0; ia < g.nang; ia++) {
+      const double c = g.cth[ia];
+      const double sth = std::sqrt(std::max((1.0 - c) * (1.0 + c), 0.0));
+      const double cot = sth > 0.0 ? c / sth : 0.0;
+      const double y = ylm(l, m, c, 0.0).real();
+      double dy = m * cot * y;
+      if (m < l) dy += std::sqrt((double)(l - m) * (double)(l + m + 1)) * ylm(l, m + 1, c, 0.0).real();
+      g.Y[(size_t)a * g.nang + ia] = y;
+      g.Th[(size_t)a * g.nang + ia] = dy;
+    }
+  }
+  const FEBasis fe(t.nnodes, t.bval, false, true);
+  std::vector<double> xq, wq;
+  chebyshev_rule(g.nrad, xq, wq);
+  const size_t tsz = (size_t)g.Nel * g.NI * g.nrad;
+  g.F.assign(tsz, 0.0);
+  g.D.assign(tsz, 0.0);
+  g.L1.assign(tsz, 0.0);
+  g.F2.assign(tsz, 0.0);
+  g.F3.assign(tsz, 0.0);
+  for (int e = 0; e < g.Nel; e++) {
+    const std::vector<double> mu = fe.coord(xq, e);
+    const Mat B0 = fe.eval_dnf(xq, 0, e), B1 = fe.eval_dnf(xq, 1, e), B2 = fe.eval_dnf(xq, 2, e);
+    for (int q = 0; q < g.nrad; q++) {
+      g.r.push_back(mu[q]);
+      g.wrad.push_back(wq[q] * fe.scale(e));
+    }
+    for (int j = 0; j < B0.cols; j++)
+      for (int q = 0; q < g.nrad; q++) {
+        const double sh = std::sinh(mu[q]), coth = sh > 0.0 ? std::cosh(mu[q]) / sh : 0.0;
+        const size_t o = ((size_t)e * g.NI + j) * g.nrad + q;
+        g.F[o] = B0(q, j);
+        g.D[o] = B1(q, j);
+        g.L1[o] = B2(q, j) + coth * B1(q, j);
+        g.F2[o] = B0(q, j);
+        g.F3[o] = sh > 0.0 ? B0(q, j) / (sh * sh) : 0.0;
+      }
+  }
+  const size_t N = (size_t)g.Nel * g.nang * g.nrad;
+  g.wtot.assign(N, 0.0);
+  g.lfac.assign(N, 0.0);
+  for (auto &sc : g.scale) sc.assign(N, 1.0);
+  const double pi = std::acos(-1.0), Rh = t.Rhalf;
+  for (int e = 0; e < g.Nel; e++)
+    for (int ia = 0; ia < g.nang; ia++) {
+      const double c = g.cth[ia];
+      const double sth = std::sqrt(std::max((1.0 - c) * (1.0 + c), 0.0));
+      for (int q = 0; q < g.nrad; q++) {
+        const size_t p = ((size_t)e * g.nang + ia) * g.nrad + q;
+        const double sh = std::sinh(g.r[(size_t)e * g.nrad + q]);
+        const double h = Rh * std::sqrt(sh * sh + sth * sth), hphi = Rh * sh * sth;
+        g.wtot[p] = 2.0 * pi * g.wang[ia] * g.wrad[(size_t)e * g.nrad + q] * Rh * Rh * Rh * sh * (sh * sh + sth * sth);
+        g.scale[0][p] = h;
+        g.scale[1][p] = h;
+        g.scale[2][p] = hphi;
+        g.lfac[p] = h > 0.0 ? 1.0 / (h * h) : 0.0;
+      }
+    }
   return g;
 }
 

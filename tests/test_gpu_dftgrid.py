@@ -106,3 +106,77 @@ def test_eval_fxc_slater_exchange(hb):
     assert np.all(H0 == 0.0) and Exc0 == 0.0 and abs(Nel0 - o["Nel"]) < 1e-11
     with pytest.raises(ValueError):
         gg.eval_Fxc(101, 130, P)     # PBE is not built in: use density + libxc + fxc
+
+
+# ---------------------------------------------------------------------------------------------
+# diatomic pure-m grid (src/diatomic/dftgrid_purem.cpp)
+# ---------------------------------------------------------------------------------------------
+def _setup_purem(hb, lmax_per_m, nelem, Z1=7, Z2=7, R=2.07):
+    from oracle import dftgrid_purem as dp
+    ob = cases.oracle_diatomic(Z1, Z2, R, tuple(lmax_per_m), nelem)
+    basis = hb.DiatomicTwoDBasis(Z1, Z2, R, list(lmax_per_m), nelem).compute_tei()
+    lang = 4 * max(lmax_per_m) + 12        # src/diatomic/main.cpp: ldft = 4*lmax+12
+    return ob, basis, dp.PureMDFTGrid(ob, lang), hb.PureMDFTGrid(basis, lang)
+
+
+def test_purem_density(hb):
+    ob, basis, og, gg = _setup_purem(hb, (3, 2), 2)
+    n = ob.Nbf()
+    blocks = cases.m_blocks(ob.mval, ob.Nrad(), True)
+    P = cases.random_density(n, 3, 5, blocks)
+    o = og.eval_density(P, None, True, True, True)
+    g = gg.density(P, None, 7)
+    assert gg.N == og.npoints()
+    for k in ("rho", "sigma", "tau", "lapl"):
+        assert _rel(g[k], o[k]) < TOL, k
+    assert _rel(g["w"], o["w"]) < 1e-14
+    S, T, _ = basis.tables.one_electron()
+    assert abs(g["Nel"] - np.sum(P * S)) < 1e-8 * abs(np.sum(P * S))
+    assert abs(g["Ekin"] - np.sum(P * T)) < 1e-6 * abs(np.sum(P * T))
+    # unrestricted
+    Pb = cases.random_density(n, 2, 6, blocks)
+    o = og.eval_density(P, Pb, True, True, True)
+    g = gg.density(P, Pb, 7)
+    for k in ("rho", "sigma", "tau", "lapl"):
+        assert g[k].shape == o[k].shape and _rel(g[k], o[k]) < TOL, k
+
+
+@pytest.mark.parametrize("kind", ["lda", "gga", "mgga_tl"])
+def test_purem_fxc(hb, kind):
+    ob, basis, og, gg = _setup_purem(hb, (3, 2), 2)
+    n = ob.Nbf()
+    blocks = cases.m_blocks(ob.mval, ob.Nrad(), True)
+    P = cases.random_density(n, 3, 5, blocks)
+    og.eval_density(P, None, True, True, True)
+    gg.density(P, None, 7)
+    rng = np.random.default_rng(17)
+    N = gg.N
+    exc = rng.uniform(-1, 0, N); vrho = rng.uniform(-1, 0, (N, 1))
+    vsigma = rng.uniform(0, 1e-2, (N, 1)) if kind != "lda" else None
+    vtau = rng.uniform(0, 1e-2, (N, 1)) if kind == "mgga_tl" else None
+    vlapl = rng.uniform(0, 1e-2, (N, 1)) if kind == "mgga_tl" else None
+    Ho, _, Eo = og.eval_fxc(exc, vrho, vsigma, vtau, vlapl)
+    Hg, _, Eg = gg.fxc(exc, vrho, vsigma, vtau, vlapl)
+    assert cases.relerr(Hg, Ho) < TOL and abs(Eg - Eo) < 1e-12 * abs(Eo)
+    # the pure-m matrix is m-block diagonal
+    for i, bi in enumerate(blocks):
+        for j, bj in enumerate(blocks):
+            if i != j:
+                assert np.all(Hg[np.ix_(bi, bj)] == 0.0)
+
+
+def test_purem_fxc_unrestricted(hb):
+    ob, basis, og, gg = _setup_purem(hb, (2, 2), 2)
+    n = ob.Nbf()
+    blocks = cases.m_blocks(ob.mval, ob.Nrad(), True)
+    Pa = cases.random_density(n, 3, 5, blocks); Pb = cases.random_density(n, 2, 6, blocks)
+    og.eval_density(Pa, Pb, True, True, True)
+    gg.density(Pa, Pb, 7)
+    rng = np.random.default_rng(18)
+    N = gg.N
+    exc = rng.uniform(-1, 0, N)
+    vrho = rng.uniform(-1, 0, (N, 2)); vsigma = rng.uniform(0, 1e-2, (N, 3))
+    vtau = rng.uniform(0, 1e-2, (N, 2)); vlapl = rng.uniform(0, 1e-2, (N, 2))
+    Hao, Hbo, Eo = og.eval_fxc(exc, vrho, vsigma, vtau, vlapl, polarized=True)
+    Hag, Hbg, Eg = gg.fxc(exc, vrho, vsigma, vtau, vlapl)
+    assert cases.relerr(Hag, Hao) < TOL and cases.relerr(Hbg, Hbo) < TOL and abs(Eg - Eo) < 1e-12 * abs(Eo)
