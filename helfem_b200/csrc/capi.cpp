@@ -298,13 +298,14 @@ int hfq_exchange_output_pattern(const hfq_ctx *ctx, int *bf_sector, int64_t cap_
 }
 
 int hfq_grid_attach(hfq_ctx *ctx, int lang, int mang) {
-  if (!ctx || lang < 1 || mang < 1) return fail(HFQ_ERR_INVALID, "hfq_grid_attach: invalid argument");
+  if (!ctx || lang < 1) return fail(HFQ_ERR_INVALID, "hfq_grid_attach: invalid argument");
   std::lock_guard<std::mutex> lk(ctx->mu);
   return guarded([&] {
     const hfq::BasisTables &bt = ctx->eng->tables();
-    // atomic: 3D grid; diatomic: the pure-m grid the reference uses at --symmetry >= 1 (mang ignored)
+    // atomic: 3D grid; diatomic: mang <= 1 selects the pure-m grid the reference uses at --symmetry >= 1,
+    // mang >= 2 the general 3D grid of --symmetry=0
     const hfq::GridTables g = bt.kind == hfq::BasisKind::Atomic ? hfq::build_atomic_grid(bt, lang, mang)
-                                                                 : hfq::build_diatomic_purem_grid(bt, lang);
+                                                                 : hfq::build_diatomic_grid(bt, lang, mang);
     ctx->grid = std::make_unique<hfq::GridEngine>(ctx->eng->tables(), g, ctx->eng->device(), ctx->eng->stream());
     return HFQ_OK;
   });

@@ -78,7 +78,7 @@ struct Engine::Impl {
   std::vector<int64_t> tperm_off;   // [Nel * nruns] offset of A_(e,run)
   std::vector<int64_t> tperm_lda;   // [Nel * nruns]
   // device
-  DevBuf<int> d_ang_off, d_ang_skip, d_sec_n, d_sec_ang, d_efirst, d_en, d_ang_sec, d_ang_pos;
+  DevBuf<int> d_ang_off, d_ang_skip, d_sec_n, d_sec_ang, d_efirst, d_en, d_ang_sec, d_ang_pos, d_rad_e0, d_rad_e1;
   DevBuf<double> d_G, d_small, d_big, d_B, d_sigma, d_tperm;
   DevBuf<int64_t> d_blk_off, d_B_off, d_sig_off, d_ep_off;
   DevBuf<int> d_rank, d_chan_of, d_browoff_T, d_browoff_G, d_splist, d_op_src, d_sp_active;
@@ -283,8 +283,19 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
   s.d_en.upload(t.en, &dev_bytes_);
   s.d_ang_sec.upload(s.ang_sec, &dev_bytes_);
   s.d_ang_pos.upload(s.ang_pos, &dev_bytes_);
+  {
+    std::vector<int> e0(t.Nrad, t.Nel), e1(t.Nrad, -1);
+    for (int e = 0; e < t.Nel; e++)
+      for (int r = t.efirst[e]; r < t.efirst[e] + t.en[e]; r++) {
+        e0[r] = std::min(e0[r], e);
+        e1[r] = std::max(e1[r], e);
+      }
+    s.d_rad_e0.upload(e0, &dev_bytes_);
+    s.d_rad_e1.upload(e1, &dev_bytes_);
+  }
   s.bd = dev::BasisDev{na, t.Nrad, s.Npix, s.NP, s.NB, s.ns, t.nch, s.nab, t.Nel, s.NL,
-                       s.d_ang_off.p, s.d_ang_skip.p, s.d_sec_n.p, s.d_sec_ang.p, s.d_efirst.p, s.d_en.p};
+                       s.d_ang_off.p, s.d_ang_skip.p, s.d_sec_n.p, s.d_sec_ang.p, s.d_efirst.p, s.d_en.p,
+                       s.d_rad_e0.p, s.d_rad_e1.p};
   // ---- element-pair accumulator layout
   s.ep_off.assign((size_t)t.Nel * t.Nel, 0);
   {

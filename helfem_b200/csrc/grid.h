@@ -35,8 +35,9 @@ struct GridTables {
 
 // atomic 3D grid (src/atomic/dftgrid.cpp), r x theta x phi
 GridTables build_atomic_grid(const BasisTables &t, int lang, int mang);
-// diatomic pure-m 2D grid (src/diatomic/dftgrid_purem.cpp), mu x nu, phi analytic
-GridTables build_diatomic_purem_grid(const BasisTables &t, int lang);
+// diatomic grids: mang <= 1 -> pure-m 2D grid (src/diatomic/dftgrid_purem.cpp, mu x nu, phi analytic),
+// mang >= 2 -> general 3D grid (src/diatomic/dftgrid.cpp)
+GridTables build_diatomic_grid(const BasisTables &t, int lang, int mang);
 
 enum GridFlags { GRID_GRAD = 1, GRID_TAU = 2, GRID_LAPL = 4 };
 

@@ -127,33 +127,53 @@ GridTables build_atomic_grid(const BasisTables &t, int lang, int mang) {
 // (sinh^2 mu + sin^2 nu); scale factors h_mu = h_nu = Rh sqrt(sinh^2 mu + sin^2 nu),
 // h_phi = Rh sinh(mu) sin(nu); Laplacian = (1/h^2) [R'' + coth(mu) R' - (l(l+1) + m^2/sinh^2 mu) R] Y.
 // Reference: src/diatomic/dftgrid_purem.cpp:30-200.
-GridTables build_diatomic_purem_grid(const BasisTables &t, int lang) {
-  if (t.kind != BasisKind::Diatomic) throw std::logic_error("build_diatomic_purem_grid: diatomic basis required");
-  if (t.bval.empty()) throw std::logic_error("build_diatomic_purem_grid: basis was not built by this library");
+// mang <= 1: pure-m grid (phi analytic, real harmonics at phi = 0, weight 2 pi w_nu);
+// mang >= 2: the general 3D grid of src/diatomic/dftgrid.cpp:414-518 (complex harmonics on the
+// theta x phi compound rule, every (a,b) pair couples, no Laplacian in the reference).
+GridTables build_diatomic_grid(const BasisTables &t, int lang, int mang) {
+  if (t.kind != BasisKind::Diatomic) throw std::logic_error("build_diatomic_grid: diatomic basis required");
+  if (t.bval.empty()) throw std::logic_error("build_diatomic_grid: basis was not built by this library");
   GridTables g;
-  g.pure_m = true;
+  g.pure_m = mang <= 1;
   g.lang = lang;
-  g.mang = 1;
-  g.nang = lang;
+  g.mang = g.pure_m ? 1 : mang;
+  g.nang = lang * g.mang;
   g.nrad = t.nquad;
   g.Nel = t.Nel;
   g.Nang = t.Nang();
   for (int n : t.en) g.NI = std::max(g.NI, n);
-  chebyshev_rule(lang, g.cth, g.wang);
-  g.phi.assign(lang, 0.0);
+  {
+    std::vector<double> xl, wl;
+    chebyshev_rule(lang, xl, wl);
+    const double dphi = 2.0 * std::acos(-1.0) / g.mang;
+    for (int i = 0; i < lang; i++)
+      for (int j = 0; j < g.mang; j++) {
+        g.cth.push_back(xl[i]);
+        g.phi.push_back(g.pure_m ? 0.0 : j * dphi);
+        g.wang.push_back(g.pure_m ? 2.0 * std::acos(-1.0) * wl[i] : wl[i] * dphi);
+      }
+  }
   g.Y.assign((size_t)g.Nang * g.nang, 0.0);
   g.Th.assign((size_t)g.Nang * g.nang, 0.0);
   for (int a = 0; a < g.Nang; a++) {
     const int l = t.lval[a], m = t.mval[a];
     for (int ia = 0; ia < g.nang; ia++) {
-      const double c = g.cth[ia];
+      const double c = g.cth[ia], ph = g.phi[ia];
       const double sth = std::sqrt(std::max((1.0 - c) * (1.0 + c), 0.0));
       const double cot = sth > 0.0 ? c / sth : 0.0;
-      const double y = ylm(l, m, c, 0.0).real();
-      double dy = m * cot * y;
-      if (m < l) dy += std::sqrt((double)(l - m) * (double)(l + m + 1)) * ylm(l, m + 1, c, 0.0).real();
-      g.Y[(size_t)a * g.nang + ia] = y;
-      g.Th[(size_t)a * g.nang + ia] = dy;
+      if (g.pure_m) {
+        const double y = ylm(l, m, c, 0.0).real();
+        double dy = m * cot * y;
+        if (m < l) dy += std::sqrt((double)(l - m) * (double)(l + m + 1)) * ylm(l, m + 1, c, 0.0).real();
+        g.Y[(size_t)a * g.nang + ia] = y;
+        g.Th[(size_t)a * g.nang + ia] = dy;
+      } else {
+        const std::complex<double> y = ylm(l, m, c, ph);
+        std::complex<double> ang = (double)m * cot * y;
+        if (m < l) ang += std::sqrt((double)(l - m) * (l + m + 1)) * std::polar(1.0, -ph) * ylm(l, m + 1, c, ph);
+        g.Y[(size_t)a * g.nang + ia] = y;
+        g.Th[(size_t)a * g.nang + ia] = ang;
+      }
     }
   }
   const FEBasis fe(t.nnodes, t.bval, false, true);
@@ -187,7 +207,7 @@ GridTables build_diatomic_purem_grid(const BasisTables &t, int lang) {
   g.wtot.assign(N, 0.0);
   g.lfac.assign(N, 0.0);
   for (auto &sc : g.scale) sc.assign(N, 1.0);
-  const double pi = std::acos(-1.0), Rh = t.Rhalf;
+  const double Rh = t.Rhalf;
   for (int e = 0; e < g.Nel; e++)
     for (int ia = 0; ia < g.nang; ia++) {
       const double c = g.cth[ia];
@@ -196,7 +216,7 @@ GridTables build_diatomic_purem_grid(const BasisTables &t, int lang) {
         const size_t p = ((size_t)e * g.nang + ia) * g.nrad + q;
         const double sh = std::sinh(g.r[(size_t)e * g.nrad + q]);
         const double h = Rh * std::sqrt(sh * sh + sth * sth), hphi = Rh * sh * sth;
-        g.wtot[p] = 2.0 * pi * g.wang[ia] * g.wrad[(size_t)e * g.nrad + q] * Rh * Rh * Rh * sh * (sh * sh + sth * sth);
+        g.wtot[p] = g.wang[ia] * g.wrad[(size_t)e * g.nrad + q] * Rh * Rh * Rh * sh * (sh * sh + sth * sth);
         g.scale[0][p] = h;
         g.scale[1][p] = h;
         g.scale[2][p] = hphi;

@@ -31,6 +31,8 @@ struct BasisDev {
   const int *sec_ang;    // [ns*NP] angular function index or -1
   const int *efirst;     // [Nel]
   const int *en;         // [Nel]
+  const int *rad_e0;     // [Nrad] first element containing the radial function
+  const int *rad_e1;     // [Nrad] last element containing it (elements overlap by one function)
 };
 
 // sum of squares of every (ang a, ang b) block -> norms2[a*Nang+b]
@@ -727,12 +729,10 @@ static __global__ void k_unpack_K(BasisDev b, UnpackDev u, const double *__restr
     const int r = idx % nj + sj, c = idx / nj + sk;
     double s = 0.0;
     if (src >= 0) {
-      for (int ei = 0; ei < b.Nel; ei++) {
+      for (int ei = b.rad_e0[r]; ei <= b.rad_e1[r]; ei++) {
         const int ri = r - b.efirst[ei];
-        if (ri < 0 || ri >= b.en[ei]) continue;
-        for (int ej = 0; ej < b.Nel; ej++) {
+        for (int ej = b.rad_e0[c]; ej <= b.rad_e1[c]; ej++) {
           const int rk = c - b.efirst[ej];
-          if (rk < 0 || rk >= b.en[ej]) continue;
           const double *acc = Kacc + (int64_t)src * u.S * u.op_stride + u.ep_off[ei * b.Nel + ej] +
                               (int64_t)(ri * b.en[ej] + rk) * b.NB + blk;
           for (int p = 0; p < u.S; p++) s += acc[(int64_t)p * u.op_stride];

@@ -125,7 +125,10 @@ int hfq_exchange_device(hfq_ctx *ctx, const double *dP, int64_t ldP, double *dK,
  * spin components are interleaved per point exactly as libxc expects them
  * (src/general/dftgrid_common.cpp:60-73): rho[p*ns + s], sigma[p*3 + {aa,ab,bb}] (1 component if
  * restricted), tau, lapl like rho.  flags: 1 gradient, 2 tau, 4 Laplacian. */
-int hfq_grid_attach(hfq_ctx *ctx, int lang, int mang);      /* DFTGrid(&basis, ldft, mdft) */
+/* atomic basis: DFTGrid(&basis, ldft, mdft) (src/atomic/dftgrid.h:139).  Diatomic basis: mang <= 1 ->
+ * PureMDFTGrid(&basis, ldft) (src/diatomic/dftgrid_purem.h, phi analytic, used at --symmetry >= 1);
+ * mang >= 2 -> the general 3D DFTGrid(&basis, ldft, mdft) of src/diatomic/dftgrid.h (no Laplacian). */
+int hfq_grid_attach(hfq_ctx *ctx, int lang, int mang);
 int64_t hfq_grid_npoints(const hfq_ctx *ctx);
 /* DFTGridWorker::update_density + compute_Nel/compute_Ekin over all elements.  Pb == NULL: restricted.
  * Output pointers may be NULL.  weights[p] = w_ang w_rad r^2. */

@@ -212,3 +212,55 @@ class AtomicDFTGrid:
                         vtl = 0.5 * vtau[sl, spin] + (2.0 * vlapl[sl, spin] if vlapl is not None else 0.0)
                     H[idx] += self.fxc_block(vrho[sl, spin], gn, vtl, vlapl[sl, spin] if vlapl is not None else None)
         return Ha, Hb, Exc
+
+
+class Diatomic3DGrid(AtomicDFTGrid):
+    """General 3D diatomic grid (symmetry=0 path), src/diatomic/dftgrid.cpp:414-518 with
+    eval_bf/eval_df of src/diatomic/basis.cpp:2120-2243: FE functions B(mu) (not B/r), scale
+    factors h_mu = h_nu = Rh sqrt(sinh^2 mu + sin^2 nu), h_phi = Rh sinh mu sin nu, weight
+    w_ang w_mu Rh^3 sinh mu (sinh^2 mu + sin^2 nu).  No Laplacian in the reference."""
+
+    def compute_bf(self, iel):
+        b = self.b
+        lv, mv = b.lval, b.mval
+        rb = b.radial
+        xq = rb.xq
+        mu = rb.fem.coord(xq, iel)
+        wrad = rb.wq * rb.fem.scale(iel)
+        f, d = rb.fem.eval_dnf(xq, 0, iel), rb.fem.eval_dnf(xq, 1, iel)
+        nrad, nang, Nr = len(mu), len(self.wang), f.shape[1]
+        a0, _ = rb.get_idx(iel)
+        N = b.Nrad()
+        self.bf_ind = np.array([N * ia + a0 + j for ia in range(len(lv)) for j in range(Nr)])
+        sth = np.sqrt(1.0 - self.cth ** 2)
+        sh = np.sinh(mu)
+        h = (b.Rhalf * np.sqrt(sh[None, :] ** 2 + sth[:, None] ** 2)).ravel()
+        self.scale = np.stack([h, h, (b.Rhalf * sh[None, :] * sth[:, None]).ravel()])
+        self.wtot = (self.wang[:, None] * (wrad * b.Rhalf ** 3 * sh)[None, :] * (sh[None, :] ** 2 + sth[:, None] ** 2)).ravel()
+        nbf = len(self.bf_ind)
+        bf = np.zeros((nbf, nang * nrad), complex); dr = np.zeros_like(bf); dth = np.zeros_like(bf); dph = np.zeros_like(bf)
+        for ia, (c, p) in enumerate(zip(self.cth, self.phi)):
+            sinth = np.sqrt(max((1.0 - c) * (1.0 + c), 0.0))
+            cot = c / sinth if sinth > 0 else 0.0
+            for i, (l, m) in enumerate(zip(lv, mv)):
+                y = sph_harm(int(l), int(m), c, p)
+                ang = m * cot * y
+                if m < l:
+                    ang = ang + np.sqrt((l - m) * (l + m + 1)) * np.exp(-1j * p) * sph_harm(int(l), int(m) + 1, c, p)
+                rows = slice(i * Nr, (i + 1) * Nr); cols = slice(ia * nrad, (ia + 1) * nrad)
+                bf[rows, cols] = np.conj(y * f).T
+                dr[rows, cols] = np.conj(y * d).T
+                dph[rows, cols] = np.conj(1j * m * y * f).T
+                dth[rows, cols] = np.conj(ang * f).T
+        self.t = {"f": bf, "r": dr, "t": dth, "p": dph, "l": np.zeros_like(bf)}
+
+    def eval_density(self, Pa, Pb=None, grad=False, tau=False, lapl=False):
+        if lapl:
+            raise ValueError("Laplacian not implemented.")   # src/diatomic/dftgrid.cpp:503-505
+        ex = self.b.expand_boundaries
+        return super().eval_density(ex(Pa), None if Pb is None else ex(Pb), grad, tau, False)
+
+    def eval_fxc(self, exc, vrho, vsigma=None, vtau=None, polarized=False, beta=True):
+        Ha, Hb, E = super().eval_fxc(self.b.Ndummy(), exc, vrho, vsigma, vtau, None, polarized, beta)
+        rb = self.b.remove_boundaries
+        return rb(Ha), (rb(Hb) if Hb is not None else None), E

@@ -180,3 +180,33 @@ def test_purem_fxc_unrestricted(hb):
     Hao, Hbo, Eo = og.eval_fxc(exc, vrho, vsigma, vtau, vlapl, polarized=True)
     Hag, Hbg, Eg = gg.fxc(exc, vrho, vsigma, vtau, vlapl)
     assert cases.relerr(Hag, Hao) < TOL and cases.relerr(Hbg, Hbo) < TOL and abs(Eg - Eo) < 1e-12 * abs(Eo)
+
+
+def test_diatomic_3d_grid(hb):
+    """General 3D diatomic grid (--symmetry=0): m-mixing density, GGA + tau, restricted and unrestricted."""
+    from oracle import dftgrid_atomic as dg
+    ob = cases.oracle_diatomic(3, 1, 1.8, (2, 2), 2)
+    basis = hb.DiatomicTwoDBasis(3, 1, 1.8, [2, 2], 2).compute_tei()
+    lang = mang = 4 * 2 + 12
+    og, gg = dg.Diatomic3DGrid(ob, lang, mang), hb.DFTGrid(basis, lang, mang)
+    n = ob.Nbf()
+    Pa = cases.random_density(n, 3, 5); Pb = cases.random_density(n, 2, 6)     # dense: couples different m
+    o = og.eval_density(Pa, Pb, True, True)
+    g = gg.density(Pa, Pb, 3)
+    for k in ("rho", "sigma", "tau"):
+        assert _rel(g[k], o[k]) < TOL, k
+    S, T, _ = basis.tables.one_electron()
+    assert abs(g["Nel"] - np.sum((Pa + Pb) * S)) < 1e-8 * abs(np.sum((Pa + Pb) * S))
+    rng = np.random.default_rng(27)
+    N = gg.N
+    exc = rng.uniform(-1, 0, N)
+    vrho = rng.uniform(-1, 0, (N, 2)); vsigma = rng.uniform(0, 1e-2, (N, 3)); vtau = rng.uniform(0, 1e-2, (N, 2))
+    Hao, Hbo, Eo = og.eval_fxc(exc, vrho, vsigma, vtau, polarized=True)
+    Hag, Hbg, Eg = gg.fxc(exc, vrho, vsigma, vtau)
+    assert cases.relerr(Hag, Hao) < TOL and cases.relerr(Hbg, Hbo) < TOL and abs(Eg - Eo) < 1e-12 * abs(Eo)
+    # purem on == off for an m-diagonal density (invariant of tests/cases.json)
+    Pm = cases.random_density(n, 3, 9, cases.m_blocks(ob.mval, ob.Nrad(), True))
+    d3 = gg.density(Pm, None, 3)
+    gp = hb.DFTGrid(basis, lang)          # pure-m grid on the same context replaces the 3D one
+    dp_ = gp.density(Pm, None, 3)
+    assert abs(d3["Nel"] - dp_["Nel"]) < 1e-9 * abs(dp_["Nel"]) and abs(d3["Ekin"] - dp_["Ekin"]) < 1e-9 * abs(dp_["Ekin"])
