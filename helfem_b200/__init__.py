@@ -35,7 +35,7 @@ class _TablesInfo(ctypes.Structure):
 
 
 EXPORTED_SYMBOLS = [
-    "hfq_last_error", "hfq_tables_atomic", "hfq_tables_diatomic", "hfq_tables_from_arrays", "hfq_tables_get_info",
+    "hfq_last_error", "hfq_tables_atomic", "hfq_tables_sadatom", "hfq_tables_diatomic", "hfq_tables_from_arrays", "hfq_tables_get_info",
     "hfq_tables_get_ints", "hfq_tables_get_doubles", "hfq_tables_get_block", "hfq_tables_one_electron",
     "hfq_tables_destroy", "hfq_create", "hfq_destroy", "hfq_nbf", "hfq_set_absm_symmetric", "hfq_coulomb",
     "hfq_exchange", "hfq_coulomb_device", "hfq_exchange_device", "hfq_last_timings", "hfq_exchange_output_pattern",
@@ -55,6 +55,7 @@ def lib():
     L.hfq_last_error.restype = ctypes.c_char_p
     vp, ci, cd, i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_int64
     L.hfq_tables_atomic.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ci, ci, cd, ci, cd, ci]
+    L.hfq_tables_sadatom.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ci, cd, ci, cd, ci]
     L.hfq_tables_diatomic.argtypes = [ctypes.POINTER(vp), ci, ci, cd, _c_int_p, ci, ci, ci, cd, ci, cd, ci]
     L.hfq_tables_from_arrays.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(_TablesDesc)]
     L.hfq_tables_get_info.argtypes = [vp, ctypes.POINTER(_TablesInfo)]
@@ -126,6 +127,12 @@ class Tables:
         return cls(h)
 
     @classmethod
+    def sadatom(cls, Z, lmax, nelem, nnodes=15, Rmax=40.0, igrid=4, zexp=2.0, nquad=0):
+        h = ctypes.c_void_p()
+        _check(lib().hfq_tables_sadatom(ctypes.byref(h), Z, lmax, nelem, nnodes, Rmax, igrid, zexp, nquad))
+        return cls(h)
+
+    @classmethod
     def diatomic(cls, Z1, Z2, Rbond, lmax_per_m, nelem, nnodes=15, Rmax=40.0, igrid=4, zexp=1.0, nquad=0):
         h = ctypes.c_void_p()
         lm = (ctypes.c_int * len(lmax_per_m))(*[int(x) for x in lmax_per_m])
@@ -137,7 +144,7 @@ class Tables:
     def from_arrays(cls, kind, Nrad, efirst, en, lval, mval, lmL, lmM, pref, blocks, Rhalf=0.0):
         """blocks[ilm*Nel+iel] = (small, big, B, sigma) with small/big shaped (nch, n, n)
         (each n x n block column-major when flattened), B (nch*n*n, rank), sigma (rank,)."""
-        nch = 1 if kind == 0 else 2
+        nch = 2 if kind == 1 else 1
         ia = lambda v: np.ascontiguousarray(v, dtype=np.int32)
         efirst, en, lval, mval, lmL, lmM = map(ia, (efirst, en, lval, mval, lmL, lmM))
         pref = np.ascontiguousarray(pref, dtype=np.float64)
@@ -341,6 +348,45 @@ class DiatomicTwoDBasis(_BasisBase):
 
     def is_absm_symmetric(self):
         return self._absm
+
+
+class SadatomTwoDBasis:
+    """helfem::sadatom::basis::TwoDBasis (src/sadatom/basis.h:72,110-114): spherically averaged atom.
+    ``coulomb(Prad)`` takes the radial density matrix, ``exchange(cube)`` a list of per-l matrices."""
+
+    def __init__(self, Z, lmax, nelem, nnodes=15, Rmax=40.0, igrid=4, zexp=2.0, nquad=0, device=0):
+        self._args = (Z, lmax, nelem, nnodes, Rmax, igrid, zexp, nquad)
+        self.lmax = lmax
+        self._k = _BasisBase(device)
+        self._j = _BasisBase(device)
+
+    def compute_tei(self, exchange=True):
+        Z, lmax, nelem, nnodes, Rmax, igrid, zexp, nquad = self._args
+        self._k._tables = Tables.sadatom(*self._args)
+        self._j._tables = Tables.atomic(Z, 0, 0, nelem, nnodes, Rmax, igrid, zexp, nquad)
+        return self
+
+    def Nrad(self):
+        return self._k.tables.Nrad
+
+    def coulomb(self, Prad):
+        """J(P_in) = 4 pi J_0(P_in), src/sadatom/basis.cpp:186-207."""
+        return 4.0 * np.pi * self._j.coulomb(Prad)
+
+    def exchange(self, cube):
+        """Per-l exchange blocks (reference sign, -K), src/sadatom/basis.cpp:209-312."""
+        N = self.Nrad()
+        if len(cube) != self.lmax + 1:
+            raise ValueError("Density matrix am does not match basis set!")
+        n = (self.lmax + 1) * N
+        P = np.zeros((n, n), order="F")
+        for l, Pl in enumerate(cube):
+            Pl = np.asarray(Pl)
+            if Pl.shape != (N, N):
+                raise ValueError("Density matrix does not match basis set!")
+            P[l * N:(l + 1) * N, l * N:(l + 1) * N] = Pl
+        K = self._k.exchange(P)
+        return [np.array(K[l * N:(l + 1) * N, l * N:(l + 1) * N]) for l in range(self.lmax + 1)]
 
 
 class TablesBasis(_BasisBase):

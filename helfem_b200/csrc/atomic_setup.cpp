@@ -254,6 +254,14 @@ BasisTables build_atomic_tables(int Z, int lmax, int mmax, int nelem, int nnodes
   return t;
 }
 
+BasisTables build_sadatom_tables(int Z, int lmax, int nelem, int nnodes, double Rmax, int igrid, double zexp,
+                                 int nquad) {
+  // identical radial caches; the angular list is l = 0..lmax with m = 0
+  BasisTables t = build_atomic_tables(Z, lmax, 0, nelem, nnodes, Rmax, igrid, zexp, nquad);
+  t.kind = BasisKind::Sadatom;
+  return t;
+}
+
 // ---------------------------------------------------------------------------
 // shared BasisTables helpers
 // ---------------------------------------------------------------------------

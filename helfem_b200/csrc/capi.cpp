@@ -68,6 +68,18 @@ int hfq_tables_atomic(hfq_tables **out, int Z, int lmax, int mmax, int nelem, in
   });
 }
 
+int hfq_tables_sadatom(hfq_tables **out, int Z, int lmax, int nelem, int nnodes, double Rmax, int igrid, double zexp,
+                       int nquad) {
+  if (!out || lmax < 0 || nelem < 1 || nnodes < 2 || nnodes > 16 || !(Rmax > 0.0))
+    return fail(HFQ_ERR_INVALID, "hfq_tables_sadatom: invalid argument");
+  return guarded([&] {
+    auto *h = new hfq_tables;
+    h->t = hfq::build_sadatom_tables(Z, lmax, nelem, nnodes, Rmax, igrid, zexp, nquad);
+    *out = h;
+    return HFQ_OK;
+  });
+}
+
 int hfq_tables_diatomic(hfq_tables **out, int Z1, int Z2, double Rbond, const int *lmax_per_m, int nm, int nelem,
                         int nnodes, double Rmax, int igrid, double zexp, int nquad) {
   if (!out || !lmax_per_m || nm < 1 || nelem < 1 || nnodes < 2 || nnodes > 16 || !(Rbond > 0.0) || !(Rmax > 0.5 * Rbond))
@@ -87,13 +99,13 @@ int hfq_tables_from_arrays(hfq_tables **out, const hfq_tables_desc *d) {
   if (!out || !d || !d->efirst || !d->en || !d->lval || !d->mval || !d->lmL || !d->lmM || !d->pref || !d->rank ||
       !d->small_ || !d->big_ || !d->B || !d->sigma)
     return fail(HFQ_ERR_INVALID, "hfq_tables_from_arrays: null argument");
-  if ((d->kind != 0 && d->kind != 1) || d->nch != (d->kind == 0 ? 1 : 2) || d->Nrad < 1 || d->Nel < 1 ||
+  if ((d->kind != 0 && d->kind != 1 && d->kind != 2) || d->nch != (d->kind == 1 ? 2 : 1) || d->Nrad < 1 || d->Nel < 1 ||
       d->Nang < 1 || d->nlm < 1)
     return fail(HFQ_ERR_INVALID, "hfq_tables_from_arrays: inconsistent sizes");
   return guarded([&] {
     auto *h = new hfq_tables;
     hfq::BasisTables &t = h->t;
-    t.kind = d->kind == 0 ? hfq::BasisKind::Atomic : hfq::BasisKind::Diatomic;
+    t.kind = d->kind == 0 ? hfq::BasisKind::Atomic : d->kind == 1 ? hfq::BasisKind::Diatomic : hfq::BasisKind::Sadatom;
     t.nch = d->nch;
     t.Nrad = d->Nrad;
     t.Nel = d->Nel;

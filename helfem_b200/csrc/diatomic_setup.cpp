@@ -484,7 +484,7 @@ void diatomic_one_electron(const BasisTables &t, std::vector<double> &S, std::ve
 void atomic_one_electron(const BasisTables &t, std::vector<double> &S, std::vector<double> &T, std::vector<double> &V);
 
 void one_electron_matrices(const BasisTables &t, std::vector<double> &S, std::vector<double> &T, std::vector<double> &V) {
-  if (t.kind == BasisKind::Atomic)
+  if (t.kind != BasisKind::Diatomic)
     atomic_one_electron(t, S, T, V);
   else
     diatomic_one_electron(t, S, T, V);

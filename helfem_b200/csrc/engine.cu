@@ -120,7 +120,13 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
     if (const char *env = getenv("HFQ_SECTOR_SPLIT")) split_parity = atoi(env) != 0;
   }
   std::map<std::pair<int, int>, std::vector<int>> bym;
-  for (int a = 0; a < na; a++) bym[{t.mval[a], split_parity ? (t.lval[a] & 1) : 0}].push_back(a);
+  if (t.kind == BasisKind::Sadatom) {
+    // spherically averaged atom: every l is its own sector and only l-diagonal blocks exist
+    split_parity = false;
+    for (int a = 0; a < na; a++) bym[{0, t.lval[a]}].push_back(a);
+  } else {
+    for (int a = 0; a < na; a++) bym[{t.mval[a], split_parity ? (t.lval[a] & 1) : 0}].push_back(a);
+  }
   s.ns = (int)bym.size();
   int nmaxsec = 0;
   for (auto &kv : bym) {
@@ -209,6 +215,17 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
               double *dst = &G[(((size_t)sp * s.NL + L) * t.nch) * s.NB + (size_t)ia * s.NP + ib];
               if (t.kind == BasisKind::Atomic) {
                 dst[0] = gt.coeff(la, ma, L, M, lb);
+                any |= dst[0] != 0.0;
+              } else if (t.kind == BasisKind::Sadatom) {
+                // sqrt of the m-averaged squared coupling: both fold factors carry the same entry, so
+                // their product is sum_{m,m'} G(la,m,L,m-m',lb)^2 / (2 la + 1)  (src/sadatom/basis.cpp:248-259)
+                double tot = 0.0;
+                for (int mo = -la; mo <= la; mo++)
+                  for (int mi = -lb; mi <= lb; mi++) {
+                    const double c = gt.coeff(la, mo, L, mo - mi, lb);
+                    tot += c * c;
+                  }
+                dst[0] = std::sqrt(tot / (2 * la + 1));
                 any |= dst[0] != 0.0;
               } else {
                 dst[0] = gt.mod_coeff(la, ma, L, M, lb, mb);
@@ -527,6 +544,7 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
       for (int sk = 0; sk < ns; sk++) {
         const int mj = s.sec_m[sj], mk = s.sec_m[sk];
         if (absm_symmetric_ && (mj < 0 || mk < 0)) continue;
+        if (t.kind == BasisKind::Sadatom && sj != sk) continue;   // l-diagonal outputs only
         OpWork w;
         w.op = sj * ns + sk;
         for (int si = 0; si < ns; si++)

@@ -19,7 +19,7 @@
 
 namespace hfq {
 
-enum class BasisKind : int { Atomic = 0, Diatomic = 1 };
+enum class BasisKind : int { Atomic = 0, Diatomic = 1, Sadatom = 2 };
 
 struct ChannelBlock {        // one (multipole channel, element)
   int n = 0;                 // functions in the element (Ni)
@@ -59,6 +59,10 @@ struct BasisTables {
 // atomic: Z, lmax, mmax, nelem, nnodes (LIP, primbas=4), Rmax, grid type, zexp, nquad (0 -> 5*nnodes)
 BasisTables build_atomic_tables(int Z, int lmax, int mmax, int nelem, int nnodes, double Rmax, int igrid, double zexp,
                                 int nquad);
+// spherically averaged atom (src/sadatom/basis.{h,cpp}): one angular function per l (m summed
+// out), same radial caches as the atomic basis; exchange couples density block l_in to output
+// block l_out through the m-averaged squared Gaunt coefficient (src/sadatom/basis.cpp:209-312)
+BasisTables build_sadatom_tables(int Z, int lmax, int nelem, int nnodes, double Rmax, int igrid, double zexp, int nquad);
 // diatomic: lmax_per_m[|m|], other arguments as src/diatomic/main.cpp:60-118
 BasisTables build_diatomic_tables(int Z1, int Z2, double Rbond, const std::vector<int> &lmax_per_m, int nelem,
                                   int nnodes, double Rmax, int igrid, double zexp, int nquad);

@@ -43,6 +43,15 @@ const char *hfq_last_error(void);
 int hfq_tables_atomic(hfq_tables **out, int Z, int lmax, int mmax, int nelem, int nnodes, double Rmax, int igrid,
                       double zexp, int nquad);
 
+/* Spherically averaged atom: sadatom::basis::TwoDBasis ctor + compute_tei()
+ * (src/sadatom/basis.cpp:50-184).  One angular function per l = 0..lmax; matrices passed to
+ * hfq_exchange are the block-diagonal dense form of the reference's per-l Cube
+ * (block l at rows/cols [l*Nrad, (l+1)*Nrad)); exchange = src/sadatom/basis.cpp:209-312.
+ * The Coulomb matrix of the spherical density (src/sadatom/basis.cpp:186-207) is
+ * 4*pi * hfq_coulomb of an lmax = 0 atomic context over the same radial basis. */
+int hfq_tables_sadatom(hfq_tables **out, int Z, int lmax, int nelem, int nnodes, double Rmax, int igrid, double zexp,
+                       int nquad);
+
 /* Diatomic basis: diatomic::basis::TwoDBasis ctor + compute_tei()
  * (src/diatomic/basis.cpp:525-647, :1382-1547; flags src/diatomic/main.cpp:60-118).
  * lmax_per_m[|m|], |m| = 0..nm-1, is the --lmax list. */
@@ -57,8 +66,8 @@ int hfq_tables_diatomic(hfq_tables **out, int Z1, int Z2, double Rbond, const in
  *   B: (nch*n*n) x rank column-major; sigma: rank entries (+-1)
  * The per-block arrays are concatenated in flat-index order. */
 typedef struct hfq_tables_desc {
-  int kind;               /* 0 atomic, 1 diatomic */
-  int nch;                /* 1 atomic, 2 diatomic */
+  int kind;               /* 0 atomic, 1 diatomic, 2 sadatom */
+  int nch;                /* 2 diatomic, 1 otherwise */
   int Nrad, Nel, Nang, nlm;
   const int *efirst;      /* [Nel] first radial function of element */
   const int *en;          /* [Nel] functions in element */

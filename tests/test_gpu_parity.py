@@ -155,3 +155,27 @@ def test_exchange_shards_sum_to_full(hb):
             basis.exchange_device(dP.data_ptr(), dK.data_ptr(), sh, nsh)
             tot += dK
         assert cases.relerr(tot.cpu().numpy().T, Kfull) < TOL
+
+
+def test_sadatom_coulomb_exchange(hb):
+    """Spherically averaged atom (gensap path, src/sadatom/basis.cpp:186-312)."""
+    from oracle import sadatom as osad
+    lmax = 2
+    ob = cases.oracle_atomic(10, lmax, 0, 3)          # radial caches L = 0..2*lmax, m = 0 angular list
+    so = osad.SadatomBasis(ob, lmax)
+    sb = hb.SadatomTwoDBasis(10, lmax, 3).compute_tei()
+    N = ob.Nrad()
+    rng = np.random.default_rng(4)
+    cube = []
+    for l in range(lmax + 1):
+        Q, _ = np.linalg.qr(rng.standard_normal((N, 2)))
+        cube.append((2 * l + 1) * Q @ Q.T)
+    cube[1] = np.zeros((N, N))                        # an empty shell is skipped (P[lin].norm()==0)
+    Ko = so.exchange(cube)
+    Kg = sb.exchange(cube)
+    for l in range(lmax + 1):
+        assert cases.relerr(Kg[l], Ko[l]) < TOL, l
+    Prad = sum(cube) / (4 * np.pi)
+    assert cases.relerr(sb.coulomb(Prad), so.coulomb(Prad)) < TOL
+    with pytest.raises(ValueError):
+        sb.exchange(cube[:2])
