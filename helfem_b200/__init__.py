@@ -39,7 +39,8 @@ EXPORTED_SYMBOLS = [
     "hfq_tables_get_ints", "hfq_tables_get_doubles", "hfq_tables_get_block", "hfq_tables_one_electron",
     "hfq_tables_destroy", "hfq_create", "hfq_destroy", "hfq_nbf", "hfq_set_absm_symmetric", "hfq_coulomb",
     "hfq_exchange", "hfq_coulomb_device", "hfq_exchange_device", "hfq_last_timings", "hfq_exchange_output_pattern",
-    "hfq_grid_attach", "hfq_grid_npoints", "hfq_grid_density", "hfq_grid_fxc", "hfq_eval_fxc",
+    "hfq_coulomb_output_pattern",
+    "hfq_coulomb_exchange", "hfq_coulomb_exchange_device", "hfq_grid_attach", "hfq_grid_npoints", "hfq_grid_density", "hfq_grid_fxc", "hfq_eval_fxc",
 ]
 
 
@@ -76,6 +77,9 @@ def lib():
     L.hfq_exchange_device.argtypes = [vp, vp, i64, vp, i64, ci, ci, vp]
     L.hfq_last_timings.argtypes = [vp, vp, ci]
     L.hfq_exchange_output_pattern.argtypes = [vp, vp, i64, vp, i64]
+    L.hfq_coulomb_output_pattern.argtypes = [vp, vp, i64, vp, i64]
+    L.hfq_coulomb_exchange.argtypes = [vp, vp, i64, cd, vp, i64, vp, i64]
+    L.hfq_coulomb_exchange_device.argtypes = [vp, vp, i64, cd, vp, i64, vp, i64, ci, ci, vp]
     L.hfq_grid_attach.argtypes = [vp, ci, ci]
     L.hfq_grid_npoints.argtypes = [vp]
     L.hfq_grid_npoints.restype = i64
@@ -267,6 +271,21 @@ class _BasisBase:
         _check(lib().hfq_exchange(ctx, Pf.ctypes.data, n, K.ctypes.data, n))
         return K
 
+    def coulomb_exchange(self, P, kscale=1.0):
+        """(J, K) = (coulomb(P), exchange(kscale * P)) in one call (one upload, overlapped copies)."""
+        ctx = self._context()
+        n = self.Nbf()
+        Pf = _fmat(P, n)
+        J = np.empty((n, n), order="F")
+        K = np.empty((n, n), order="F")
+        _check(lib().hfq_coulomb_exchange(ctx, Pf.ctypes.data, n, kscale, J.ctypes.data, n, K.ctypes.data, n))
+        return J, K
+
+    def coulomb_exchange_device(self, dP_ptr, dJ_ptr, dK_ptr, kscale=1.0, shard=0, nshards=1, stream=None):
+        n = self.Nbf()
+        _check(lib().hfq_coulomb_exchange_device(self._context(), dP_ptr, n, kscale, dJ_ptr, n, dK_ptr, n, shard, nshards,
+                                                 stream))
+
     # -- device-resident variants (torch CUDA tensors, column-major = transposed view) ---------
     def coulomb_device(self, dP_ptr, dJ_ptr, stream=None):
         n = self.Nbf()
@@ -276,13 +295,14 @@ class _BasisBase:
         n = self.Nbf()
         _check(lib().hfq_exchange_device(self._context(), dP_ptr, n, dK_ptr, n, shard, nshards, stream))
 
-    def exchange_output_pattern(self):
-        """(bf_sector[Nbf], [(row sector, col sector), ...]) of the last exchange result."""
+    def exchange_output_pattern(self, coulomb=False):
+        """(bf_sector[Nbf], [(row sector, col sector), ...]) of the last exchange (or coulomb) result."""
         n = self.Nbf()
         bs = np.zeros(n, dtype=np.int32)
         cap = 4 * self.tables.Nang ** 2 + 16
         pr = np.zeros(cap, dtype=np.int32)
-        k = _check(lib().hfq_exchange_output_pattern(self._context(), bs.ctypes.data, n, pr.ctypes.data, cap))
+        fn = lib().hfq_coulomb_output_pattern if coulomb else lib().hfq_exchange_output_pattern
+        k = _check(fn(self._context(), bs.ctypes.data, n, pr.ctypes.data, cap))
         return bs, [(int(pr[2 * i]), int(pr[2 * i + 1])) for i in range(k)]
 
     def last_timings(self):

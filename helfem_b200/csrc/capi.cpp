@@ -282,7 +282,7 @@ int hfq_coulomb_device(hfq_ctx *ctx, const double *dP, int64_t ldP, double *dJ, 
   if (int rc = check_mat(ctx, dP, ldP, dJ, ldJ)) return rc;
   std::lock_guard<std::mutex> lk(ctx->mu);
   return guarded([&] {
-    ctx->eng->coulomb_dev(dP, ldP, dJ, ldJ, stream ? (cudaStream_t)stream : ctx->eng->stream());
+    ctx->eng->coulomb_dev(dP, ldP, dJ, ldJ, 0, 1, stream ? (cudaStream_t)stream : ctx->eng->stream());
     return HFQ_OK;
   });
 }
@@ -298,10 +298,43 @@ int hfq_exchange_device(hfq_ctx *ctx, const double *dP, int64_t ldP, double *dK,
   });
 }
 
+int hfq_coulomb_exchange(hfq_ctx *ctx, const double *P, int64_t ldP, double kscale, double *J, int64_t ldJ, double *K,
+                         int64_t ldK) {
+  if (int rc = check_mat(ctx, P, ldP, J, ldJ)) return rc;
+  if (int rc = check_mat(ctx, P, ldP, K, ldK)) return rc;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  return guarded([&] {
+    ctx->eng->coulomb_exchange(P, ldP, kscale, J, ldJ, K, ldK);
+    return HFQ_OK;
+  });
+}
+
+int hfq_coulomb_exchange_device(hfq_ctx *ctx, const double *dP, int64_t ldP, double kscale, double *dJ, int64_t ldJ,
+                                double *dK, int64_t ldK, int shard, int nshards, void *stream) {
+  if (int rc = check_mat(ctx, dP, ldP, dJ, ldJ)) return rc;
+  if (int rc = check_mat(ctx, dP, ldP, dK, ldK)) return rc;
+  if (nshards < 1 || shard < 0 || shard >= nshards) return fail(HFQ_ERR_INVALID, "hfq_coulomb_exchange_device: bad shard");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  return guarded([&] {
+    ctx->eng->jk_dev(dP, ldP, kscale, dJ, ldJ, dK, ldK, shard, nshards, stream ? (cudaStream_t)stream : ctx->eng->stream());
+    return HFQ_OK;
+  });
+}
+
+static int output_pattern(const hfq_ctx *ctx, bool coulomb, int *bf_sector, int64_t cap_bf, int *pairs, int64_t cap_pairs);
+
 int hfq_exchange_output_pattern(const hfq_ctx *ctx, int *bf_sector, int64_t cap_bf, int *pairs, int64_t cap_pairs) {
-  if (!ctx || !bf_sector || !pairs) return fail(HFQ_ERR_INVALID, "hfq_exchange_output_pattern: null argument");
+  return output_pattern(ctx, false, bf_sector, cap_bf, pairs, cap_pairs);
+}
+
+int hfq_coulomb_output_pattern(const hfq_ctx *ctx, int *bf_sector, int64_t cap_bf, int *pairs, int64_t cap_pairs) {
+  return output_pattern(ctx, true, bf_sector, cap_bf, pairs, cap_pairs);
+}
+
+static int output_pattern(const hfq_ctx *ctx, bool coulomb, int *bf_sector, int64_t cap_bf, int *pairs, int64_t cap_pairs) {
+  if (!ctx || !bf_sector || !pairs) return fail(HFQ_ERR_INVALID, "hfq_*_output_pattern: null argument");
   std::vector<int> bs, pr;
-  ctx->eng->output_pattern(bs, pr);
+  ctx->eng->output_pattern(bs, pr, coulomb);
   if ((int64_t)bs.size() > cap_bf || (int64_t)pr.size() > cap_pairs)
     return fail(HFQ_ERR_INVALID, "hfq_exchange_output_pattern: buffer too small");
   std::memcpy(bf_sector, bs.data(), bs.size() * sizeof(int));

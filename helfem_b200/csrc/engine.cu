@@ -82,7 +82,7 @@ struct Engine::Impl {
   DevBuf<double> d_G, d_small, d_big, d_B, d_sigma, d_tperm;
   DevBuf<int64_t> d_blk_off, d_B_off, d_sig_off, d_ep_off;
   DevBuf<int> d_rank, d_chan_of, d_browoff_T, d_browoff_G, d_splist, d_op_src, d_sp_active;
-  DevBuf<double> d_jfac, d_norms, d_Ppix, d_R, d_Kacc, d_Paux, d_JauxT, d_Jsec, d_P, d_O;
+  DevBuf<double> d_jfac, d_norms, d_Ppix, d_R, d_Kacc, d_Paux, d_JauxT, d_Jsec, d_P, d_O, d_O2;
   DevBuf<dev::FoldTask> d_tasks;
   DevBuf<dev::GemmItem> d_gitems;
   DevBuf<dev::GemmEntry> d_gentries;
@@ -91,6 +91,13 @@ struct Engine::Impl {
   std::vector<int> browoff_T_first;  // per element: first index into d_browoff_T
   dev::BasisDev bd{};
   size_t r_slots = 0;                // capacity of the R buffer in task slots
+  // density packed by pack_density(): shared by coulomb and exchange in a fused build
+  std::vector<double> norms_host;
+  std::vector<int> packed_splist;
+  bool packed_valid = false;
+  double kscale = 1.0;               // exchange(kscale * P) = kscale * exchange(P)
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_j = nullptr, ev_jcopied = nullptr;
   cudaEvent_t ev[8];
 };
 
@@ -469,6 +476,57 @@ void launch_gemm(const dev::GemmItem *items, const dev::GemmEntry *entries, int 
 // ---------------------------------------------------------------------------
 // exchange
 // ---------------------------------------------------------------------------
+// Block norms of P (the reference's screening quantity) and the sector-packed copy of every
+// sector pair that carries density.  Shared by coulomb and exchange inside a fused build.
+void Engine::pack_density(const double *dP, int64_t ldP, cudaStream_t st) {
+  Impl &s = *p_;
+  const BasisTables &t = s.t;
+  const int na = t.Nang(), ns = s.ns;
+  dev::k_block_norms<<<dim3(na, na), 128, 0, st>>>(s.bd, dP, ldP, s.d_norms.p);
+  CK(cudaGetLastError());
+  s.norms_host.resize((size_t)na * na);
+  CK(cudaMemcpyAsync(s.norms_host.data(), s.d_norms.p, s.norms_host.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  std::vector<char> sp_nz((size_t)ns * ns, 0);
+  for (int a = 0; a < na; a++)
+    for (int b = 0; b < na; b++)
+      if (s.norms_host[(size_t)a * na + b] > 0.0) sp_nz[(size_t)s.ang_sec[a] * ns + s.ang_sec[b]] = 1;
+  s.packed_splist.clear();
+  for (int sp = 0; sp < ns * ns; sp++)
+    if (sp_nz[sp]) s.packed_splist.push_back(sp);
+  if (!s.packed_splist.empty()) {
+    CK(cudaMemcpyAsync(s.d_splist.p, s.packed_splist.data(), s.packed_splist.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    for (int sp : s.packed_splist)
+      CK(cudaMemsetAsync(s.d_Ppix.p + (size_t)sp * s.Npix * s.NB, 0, (size_t)s.Npix * s.NB * sizeof(double), st));
+    dev::k_pack<<<dim3(t.Nrad, (unsigned)s.packed_splist.size()), 256, 0, st>>>(s.bd, dP, ldP, s.d_splist.p, s.d_Ppix.p);
+    CK(cudaGetLastError());
+  }
+}
+
+// Fused Fock-build step: J = coulomb(P), K = exchange(kscale * P) from ONE packed copy of P.
+void Engine::jk_dev(const double *dP, int64_t ldP, double kscale, double *dJ, int64_t ldJ, double *dK, int64_t ldK,
+                    int shard, int nshards, cudaStream_t st) {
+  Impl &s = *p_;
+  CK(cudaSetDevice(device_));
+  pack_density(dP, ldP, st);
+  s.packed_valid = true;
+  try {
+    coulomb_dev(dP, ldP, dJ, ldJ, shard, nshards, st);
+    const EngineTimings tj = tm_;
+    if (s.ev_j) CK(cudaEventRecord(s.ev_j, st));
+    s.kscale = kscale;
+    exchange_dev(dP, ldP, dK, ldK, shard, nshards, st);
+    tm_.launches += tj.launches;
+    tm_.total += tj.total;
+  } catch (...) {
+    s.packed_valid = false;
+    s.kscale = 1.0;
+    throw;
+  }
+  s.packed_valid = false;
+  s.kscale = 1.0;
+}
+
 // A plan is everything about an exchange call that depends only on WHICH sector pairs of the
 // density are non-zero (plus sharding and the +-m flag): the task list, its split into batches
 // and the device-resident kernel descriptors.  SCF iterations reuse it.
@@ -503,11 +561,8 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
   if (!plans_) plans_.reset(new PlanCache);
   CK(cudaEventRecord(s.ev[0], st));
   // 1. which angular blocks of P carry density (reference: block norm >= 10 eps)
-  dev::k_block_norms<<<dim3(na, na), 128, 0, st>>>(s.bd, dP, ldP, s.d_norms.p);
-  CK(cudaGetLastError());
-  std::vector<double> norms((size_t)na * na);
-  CK(cudaMemcpyAsync(norms.data(), s.d_norms.p, norms.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  if (!s.packed_valid) pack_density(dP, ldP, st);
+  const std::vector<double> &norms = s.norms_host;
   const double thr2 = std::pow(10.0 * 2.220446049250313e-16, 2);
   std::string key((size_t)ns * ns + 3, '0');
   for (int a = 0; a < na; a++)
@@ -736,14 +791,6 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
     plan = plans_->plans.back().get();
   }
   // ---------------- run the plan ----------------
-  // 2. pack the active sector pairs
-  if (!plan->splist.empty()) {
-    CK(cudaMemcpyAsync(s.d_splist.p, plan->splist.data(), plan->splist.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-    for (int sp : plan->splist)
-      CK(cudaMemsetAsync(s.d_Ppix.p + (size_t)sp * s.Npix * s.NB, 0, (size_t)s.Npix * s.NB * sizeof(double), st));
-    dev::k_pack<<<dim3(t.Nrad, (unsigned)plan->splist.size()), 256, 0, st>>>(s.bd, dP, ldP, s.d_splist.p, s.d_Ppix.p);
-    CK(cudaGetLastError());
-  }
   const int S = plan->S;
   if (S > 1)
     for (int a = 0; a < plan->nactive; a++)
@@ -794,7 +841,7 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
   // 6. unpack
   CK(cudaEventRecord(s.ev[6], st));
   CK(cudaMemcpyAsync(s.d_op_src.p, plan->op_src.data(), plan->op_src.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-  dev::UnpackDev u{s.d_op_src.p, s.d_ep_off.p, s.d_ang_sec.p, s.d_ang_pos.p, s.op_stride, S};
+  dev::UnpackDev u{s.d_op_src.p, s.d_ep_off.p, s.d_ang_sec.p, s.d_ang_pos.p, s.op_stride, S, s.kscale};
   dev::k_unpack_K<<<dim3(na, na), 256, 0, st>>>(s.bd, u, s.d_Kacc.p, dK, ldK);
   CK(cudaGetLastError());
   CK(cudaEventRecord(s.ev[7], st));
@@ -827,12 +874,21 @@ Engine::~Engine() {
 
 // sector of every dense basis function and the list of output sector pairs written by the last
 // exchange call (everything else in K is exactly zero)
-void Engine::output_pattern(std::vector<int> &bf_sector, std::vector<int> &pairs) const {
+void Engine::output_pattern(std::vector<int> &bf_sector, std::vector<int> &pairs, bool coulomb) const {
   const Impl &s = *p_;
   bf_sector.clear();
   for (int a = 0; a < s.t.Nang(); a++)
     for (int r = s.ang_skip[a]; r < s.t.Nrad; r++) bf_sector.push_back(s.ang_sec[a]);
   pairs.clear();
+  if (coulomb) {
+    // J block (ang i, ang j) is read from Jsec[sp = (sector j, sector i)]: rows belong to sector i
+    for (size_t sp = 0; sp < last_active_j_.size(); sp++)
+      if (last_active_j_[sp]) {
+        pairs.push_back((int)(sp % s.ns));
+        pairs.push_back((int)(sp / s.ns));
+      }
+    return;
+  }
   for (size_t op = 0; op < last_active_ops_.size(); op++)
     if (last_active_ops_[op] >= 0) {
       pairs.push_back((int)(op / s.ns));
@@ -843,32 +899,19 @@ void Engine::output_pattern(std::vector<int> &bf_sector, std::vector<int> &pairs
 // ---------------------------------------------------------------------------
 // coulomb
 // ---------------------------------------------------------------------------
-void Engine::coulomb_dev(const double *dP, int64_t ldP, double *dJ, int64_t ldJ, cudaStream_t st) {
+void Engine::coulomb_dev(const double *dP, int64_t ldP, double *dJ, int64_t ldJ, int shard, int nshards,
+                         cudaStream_t st) {
   Impl &s = *p_;
   const BasisTables &t = s.t;
   CK(cudaSetDevice(device_));
   const int na = t.Nang(), ns = s.ns, nq = s.NL * t.nch;
   tm_ = EngineTimings();
   CK(cudaEventRecord(s.ev[0], st));
-  dev::k_block_norms<<<dim3(na, na), 128, 0, st>>>(s.bd, dP, ldP, s.d_norms.p);
-  CK(cudaGetLastError());
-  std::vector<double> norms((size_t)na * na);
-  CK(cudaMemcpyAsync(norms.data(), s.d_norms.p, norms.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  std::vector<char> sp_nz((size_t)ns * ns, 0);
-  for (int a = 0; a < na; a++)
-    for (int b = 0; b < na; b++)
-      if (norms[(size_t)a * na + b] > 0.0) sp_nz[(size_t)s.ang_sec[a] * ns + s.ang_sec[b]] = 1;
-  std::vector<int> splist;
-  for (int sp = 0; sp < ns * ns; sp++)
-    if (sp_nz[sp]) splist.push_back(sp);
-  if (!splist.empty()) {
-    CK(cudaMemcpyAsync(s.d_splist.p, splist.data(), splist.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-    for (int sp : splist)
-      CK(cudaMemsetAsync(s.d_Ppix.p + (size_t)sp * s.Npix * s.NB, 0, (size_t)s.Npix * s.NB * sizeof(double), st));
-    dev::k_pack<<<dim3(t.Nrad, (unsigned)splist.size()), 256, 0, st>>>(s.bd, dP, ldP, s.d_splist.p, s.d_Ppix.p);
-    CK(cudaGetLastError());
-  }
+  if (!s.packed_valid) pack_density(dP, ldP, st);
+  const std::vector<int> &splist = s.packed_splist;
+  // sharding: this rank handles the multipoles L in [L0, L1) (partial J, summed by the caller's all-reduce)
+  const int L0 = (int)((int64_t)s.NL * shard / nshards), L1 = (int)((int64_t)s.NL * (shard + 1) / nshards);
+  const int q0 = L0 * t.nch, nqs = (L1 - L0) * t.nch;
   CK(cudaEventRecord(s.ev[1], st));
   if (s.d_Paux.n == 0) {
     s.d_Paux.alloc((size_t)s.nM * nq * s.Npix, &dev_bytes_);
@@ -882,21 +925,21 @@ void Engine::coulomb_dev(const double *dP, int64_t ldP, double *dJ, int64_t ldJ,
   for (int Mi = 0; Mi < s.nM; Mi++) {
     const int M = Mi - (s.mmax - s.mmin);
     dev::GemmItem gi{};
-    gi.C = s.d_Paux.p + (size_t)Mi * nq * s.Npix;
-    gi.M = nq;
+    gi.C = s.d_Paux.p + ((size_t)Mi * nq + q0) * s.Npix;
+    gi.M = nqs;
     gi.N = s.Npix;
     gi.K = s.NB;
     gi.ent0 = (int)entries.size();
     for (int sp : splist) {
       if (s.sec_m[sp / ns] - s.sec_m[sp % ns] != M) continue;
       dev::GemmEntry ge;
-      ge.A = s.d_G.p + (size_t)sp * nq * s.NB;
+      ge.A = s.d_G.p + ((size_t)sp * nq + q0) * s.NB;
       ge.lda = s.NB;
       ge.B = s.d_Ppix.p + (size_t)sp * s.Npix * s.NB;
       entries.push_back(ge);
     }
     gi.ent1 = (int)entries.size();
-    if (gi.ent1 == gi.ent0) continue;
+    if (gi.ent1 == gi.ent0 || nqs == 0) continue;
     M_active[Mi] = 1;
     gi.accumulate = 0;
     gi.ldb = s.NB;
@@ -914,12 +957,14 @@ void Engine::coulomb_dev(const double *dP, int64_t ldP, double *dJ, int64_t ldJ,
   // inactive M channels must read as zero in the radial step
   for (int Mi = 0; Mi < s.nM; Mi++)
     if (!M_active[Mi]) CK(cudaMemsetAsync(s.d_Paux.p + (size_t)Mi * nq * s.Npix, 0, (size_t)nq * s.Npix * sizeof(double), st));
-  launch_gemm<true>(s.d_gitems.p, s.d_gentries.p, (int)items.size(), nq, s.Npix, st);
+  launch_gemm<true>(s.d_gitems.p, s.d_gentries.p, (int)items.size(), nqs, s.Npix, st);
   CK(cudaEventRecord(s.ev[2], st));
+  if (nshards > 1)   // multipoles of other shards must read as zero in the unfold
+    CK(cudaMemsetAsync(s.d_JauxT.p, 0, (size_t)s.nM * nq * s.Npix * sizeof(double), st));
   // radial step
   dev::JRadDev jr{s.d_chan_of.p, s.d_jfac.p, s.d_blk_off.p, s.d_B_off.p, s.d_sig_off.p, s.d_rank.p,
                   s.d_small.p, s.d_big.p, s.d_B.p, s.d_sigma.p, s.nM};
-  dev::k_jradial<<<dim3(s.NL, s.nM), 256, 0, st>>>(s.bd, jr, s.d_Paux.p, s.d_JauxT.p);
+  if (L1 > L0) dev::k_jradial<<<dim3(L1 - L0, s.nM), 256, 0, st>>>(s.bd, jr, L0, s.d_Paux.p, s.d_JauxT.p);
   CK(cudaGetLastError());
   CK(cudaEventRecord(s.ev[3], st));
   // unfold: Jsec[sp=(sj,si)][pix][j*NP+i] = sum_q JauxT[Mi][pix][q] G[sp][q][j*NP+i]
@@ -935,12 +980,12 @@ void Engine::coulomb_dev(const double *dP, int64_t ldP, double *dJ, int64_t ldJ,
     gi.browoff = s.d_browoff_G.p;
     gi.M = s.Npix;
     gi.N = s.NB;
-    gi.K = nq;
+    gi.K = nqs;
     gi.ent0 = (int)uentries.size();
     dev::GemmEntry ge;
-    ge.A = s.d_JauxT.p + (size_t)Mi * s.Npix * nq;
+    ge.A = s.d_JauxT.p + (size_t)Mi * s.Npix * nq + q0;
     ge.lda = nq;
-    ge.B = s.d_G.p + (size_t)sp * nq * s.NB;
+    ge.B = s.d_G.p + ((size_t)sp * nq + q0) * s.NB;
     uentries.push_back(ge);
     gi.ent1 = (int)uentries.size();
     gi.accumulate = 0;
@@ -952,6 +997,7 @@ void Engine::coulomb_dev(const double *dP, int64_t ldP, double *dJ, int64_t ldJ,
   up(s.d_gitems, uitems);
   up(s.d_gentries, uentries);
   CK(cudaMemcpyAsync(s.d_sp_active.p, sp_active.data(), sp_active.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  last_active_j_.assign(sp_active.begin(), sp_active.end());
   CK(cudaStreamSynchronize(st));
   launch_gemm<false>(s.d_gitems.p, s.d_gentries.p, (int)uitems.size(), s.Npix, s.NB, st);
   CK(cudaEventRecord(s.ev[4], st));
@@ -979,7 +1025,7 @@ void Engine::coulomb(const double *P, int64_t ldP, double *J, int64_t ldJ) {
   if (s.d_O.n < n * n) s.d_O.alloc(n * n, &dev_bytes_);
   CK(cudaMemcpy2DAsync(s.d_P.p, n * sizeof(double), P, ldP * sizeof(double), n * sizeof(double), n,
                        cudaMemcpyHostToDevice, stream_));
-  coulomb_dev(s.d_P.p, (int64_t)n, s.d_O.p, (int64_t)n, stream_);
+  coulomb_dev(s.d_P.p, (int64_t)n, s.d_O.p, (int64_t)n, 0, 1, stream_);
   CK(cudaMemcpy2DAsync(J, ldJ * sizeof(double), s.d_O.p, n * sizeof(double), n * sizeof(double), n,
                        cudaMemcpyDeviceToHost, stream_));
   CK(cudaStreamSynchronize(stream_));
@@ -997,6 +1043,48 @@ void Engine::exchange(const double *P, int64_t ldP, double *K, int64_t ldK) {
   CK(cudaMemcpy2DAsync(K, ldK * sizeof(double), s.d_O.p, n * sizeof(double), n * sizeof(double), n,
                        cudaMemcpyDeviceToHost, stream_));
   CK(cudaStreamSynchronize(stream_));
+}
+
+// Fused host entry point: one upload of P, J is copied back on a second stream while the exchange
+// kernels run, then K.
+void Engine::coulomb_exchange(const double *P, int64_t ldP, double kscale, double *J, int64_t ldJ, double *K,
+                              int64_t ldK) {
+  Impl &s = *p_;
+  CK(cudaSetDevice(device_));
+  const size_t n = (size_t)nbf_;
+  if (s.d_P.n < n * n) s.d_P.alloc(n * n, &dev_bytes_);
+  if (s.d_O.n < n * n) s.d_O.alloc(n * n, &dev_bytes_);
+  if (s.d_O2.n < n * n) s.d_O2.alloc(n * n, &dev_bytes_);
+  if (!s.copy_stream) {
+    CK(cudaStreamCreateWithFlags(&s.copy_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&s.ev_j, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&s.ev_jcopied, cudaEventDisableTiming));
+  }
+  CK(cudaMemcpy2DAsync(s.d_P.p, n * sizeof(double), P, ldP * sizeof(double), n * sizeof(double), n,
+                       cudaMemcpyHostToDevice, stream_));
+  pack_density(s.d_P.p, (int64_t)n, stream_);
+  s.packed_valid = true;
+  try {
+    coulomb_dev(s.d_P.p, (int64_t)n, s.d_O2.p, (int64_t)n, 0, 1, stream_);
+    const EngineTimings tj = tm_;
+    // J is complete (coulomb_dev synchronises): copy it out while K is being built
+    CK(cudaMemcpy2DAsync(J, ldJ * sizeof(double), s.d_O2.p, n * sizeof(double), n * sizeof(double), n,
+                         cudaMemcpyDeviceToHost, s.copy_stream));
+    s.kscale = kscale;
+    exchange_dev(s.d_P.p, (int64_t)n, s.d_O.p, (int64_t)n, 0, 1, stream_);
+    tm_.launches += tj.launches;
+    tm_.total += tj.total;
+  } catch (...) {
+    s.packed_valid = false;
+    s.kscale = 1.0;
+    throw;
+  }
+  s.packed_valid = false;
+  s.kscale = 1.0;
+  CK(cudaMemcpy2DAsync(K, ldK * sizeof(double), s.d_O.p, n * sizeof(double), n * sizeof(double), n,
+                       cudaMemcpyDeviceToHost, stream_));
+  CK(cudaStreamSynchronize(stream_));
+  CK(cudaStreamSynchronize(s.copy_stream));
 }
 
 }  // namespace hfq

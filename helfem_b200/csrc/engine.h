@@ -45,27 +45,33 @@ class Engine {
   // engine's device.  shard/nshards partition the exchange output blocks over
   // ranks (blocks owned by other shards are written as zero so that a sum
   // over ranks gives the full matrix).
-  void coulomb_dev(const double *dP, int64_t ldP, double *dJ, int64_t ldJ, cudaStream_t stream);
+  void coulomb_dev(const double *dP, int64_t ldP, double *dJ, int64_t ldJ, int shard, int nshards, cudaStream_t stream);
+  // Fused build: J = coulomb(P), K = exchange(kscale * P) from one packed copy of P.  With nshards > 1
+  // both outputs are partial sums (J over multipoles, K over tasks) to be all-reduced by the caller.
+  void jk_dev(const double *dP, int64_t ldP, double kscale, double *dJ, int64_t ldJ, double *dK, int64_t ldK, int shard,
+              int nshards, cudaStream_t stream);
   void exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK, int shard, int nshards,
                     cudaStream_t stream);
   // Host-pointer entry points (copies in/out on the engine's stream).
   void coulomb(const double *P, int64_t ldP, double *J, int64_t ldJ);
   void exchange(const double *P, int64_t ldP, double *K, int64_t ldK);
+  void coulomb_exchange(const double *P, int64_t ldP, double kscale, double *J, int64_t ldJ, double *K, int64_t ldK);
 
   // Non-zero structure of the last exchange result: sector id of every dense basis function and
   // the (row sector, column sector) pairs that were written; all other blocks of K are zero.
-  void output_pattern(std::vector<int> &bf_sector, std::vector<int> &pairs) const;
+  void output_pattern(std::vector<int> &bf_sector, std::vector<int> &pairs, bool coulomb = false) const;
 
   const EngineTimings &timings() const { return tm_; }
   cudaStream_t stream() const { return stream_; }
   size_t device_bytes() const { return dev_bytes_; }
 
  private:
+  void pack_density(const double *dP, int64_t ldP, cudaStream_t stream);
   struct Impl;
   struct PlanCache;
   std::unique_ptr<Impl> p_;
   std::unique_ptr<PlanCache> plans_;
-  std::vector<int> last_active_ops_;
+  std::vector<int> last_active_ops_, last_active_j_;
   int device_ = 0, nbf_ = 0;
   bool absm_symmetric_ = false;
   cudaStream_t stream_ = nullptr;

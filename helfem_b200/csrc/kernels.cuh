@@ -715,6 +715,7 @@ struct UnpackDev {
   const int *ang_pos;     // [Nang] position inside the sector
   int64_t op_stride;      // accumulator stride per (output pair, partial)
   int S;                  // partial accumulators per output pair (K-split of the in-element GEMM)
+  double scale;           // exchange(scale * P) = scale * exchange(P)
 };
 
 static __global__ void k_unpack_K(BasisDev b, UnpackDev u, const double *__restrict__ Kacc, double *__restrict__ K, int64_t ld) {
@@ -739,7 +740,7 @@ static __global__ void k_unpack_K(BasisDev b, UnpackDev u, const double *__restr
         }
       }
     }
-    dst[(r - sj) + (int64_t)(c - sk) * ld] = -s;
+    dst[(r - sj) + (int64_t)(c - sk) * ld] = -u.scale * s;
   }
 }
 
@@ -761,8 +762,8 @@ struct JRadDev {
 };
 
 static __global__ void __launch_bounds__(256)
-k_jradial(BasisDev b, JRadDev jr, const double *__restrict__ Paux, double *__restrict__ JauxT) {
-  const int L = blockIdx.x, Mi = blockIdx.y, tid = threadIdx.x;
+k_jradial(BasisDev b, JRadDev jr, int L0, const double *__restrict__ Paux, double *__restrict__ JauxT) {
+  const int L = L0 + blockIdx.x, Mi = blockIdx.y, tid = threadIdx.x;
   const int nq = b.NL * b.nch;
   const int ilm = jr.chan_of[L * jr.nM + Mi];
   double *out = JauxT + (int64_t)Mi * b.Npix * nq;

@@ -14,8 +14,8 @@ class CompactAllReduce:
     """All-reduce(sum) of the non-zero blocks of a column-major Nbf x Nbf device matrix held in a
     torch tensor ``dK`` of shape (Nbf, Nbf) (dK[c, r] = K[r, c])."""
 
-    def __init__(self, basis, device):
-        bf_sector, pairs = basis.exchange_output_pattern()
+    def __init__(self, basis, device, coulomb=False):
+        bf_sector, pairs = basis.exchange_output_pattern(coulomb)
         n = len(bf_sector)
         nsec = int(bf_sector.max()) + 1
         members = [np.nonzero(bf_sector == s)[0] for s in range(nsec)]

@@ -126,6 +126,15 @@ int hfq_coulomb_device(hfq_ctx *ctx, const double *dP, int64_t ldP, double *dJ, 
 int hfq_exchange_device(hfq_ctx *ctx, const double *dP, int64_t ldP, double *dK, int64_t ldK, int shard,
                         int nshards, void *stream);
 
+/* One Fock-build step as the reference's fock_builder issues it (src/diatomic/main.cpp:413-426:
+ * J = coulomb(P); K = exchange(P/2) back to back): J = coulomb(P) and K = exchange(kscale * P) from a
+ * single upload and a single packed copy of P; the host version copies J back while K is being built.
+ * With nshards > 1 (device version) J and K are partial sums to be all-reduced. */
+int hfq_coulomb_exchange(hfq_ctx *ctx, const double *P, int64_t ldP, double kscale, double *J, int64_t ldJ, double *K,
+                         int64_t ldK);
+int hfq_coulomb_exchange_device(hfq_ctx *ctx, const double *dP, int64_t ldP, double kscale, double *dJ, int64_t ldJ,
+                                double *dK, int64_t ldK, int shard, int nshards, void *stream);
+
 /* ---- DFT quadrature grid: DFTGrid::eval_Fxc of the atomic basis --------------------------------
  * (src/atomic/dftgrid.h:156,159; worker src/atomic/dftgrid.cpp:51-242, :304-465, :470-576).
  * The functional evaluation itself stays on libxc's definitions: the GPU produces the densities in
@@ -158,6 +167,8 @@ int hfq_eval_fxc(hfq_ctx *ctx, int x_func, int c_func, const double *Pa, int64_t
  * bf_sector[Nbf] = sector id of every basis function; pairs = (row sector, column sector) of the
  * blocks that were written (everything else in K is exactly zero).  Returns the number of pairs. */
 int hfq_exchange_output_pattern(const hfq_ctx *ctx, int *bf_sector, int64_t cap_bf, int *pairs, int64_t cap_pairs);
+/* the same for the last hfq_coulomb* result */
+int hfq_coulomb_output_pattern(const hfq_ctx *ctx, int *bf_sector, int64_t cap_bf, int *pairs, int64_t cap_pairs);
 
 /* Timings / work counters of the last call on this context:
  * out[0..5] = ms {pack, fold, in-element GEMM, cross-element, unpack, total},

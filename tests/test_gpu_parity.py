@@ -179,3 +179,31 @@ def test_sadatom_coulomb_exchange(hb):
     assert cases.relerr(sb.coulomb(Prad), so.coulomb(Prad)) < TOL
     with pytest.raises(ValueError):
         sb.exchange(cube[:2])
+
+
+def test_fused_coulomb_exchange(hb):
+    """hfq_coulomb_exchange == hfq_coulomb + hfq_exchange(kscale*P); sharded partial J and K sum to the full matrices."""
+    import torch
+    basis = hb.DiatomicTwoDBasis(7, 7, 2.07, [4, 3, 2], 2).compute_tei()
+    n = basis.Nbf()
+    t = basis.tables
+    P = cases.random_density(n, 3, 7, cases.m_blocks(t.mval, t.Nrad, True))
+    J0, K0 = basis.coulomb(P), basis.exchange(0.5 * P)
+    J1, K1 = basis.coulomb_exchange(P, 0.5)
+    assert cases.relerr(J1, J0) < 1e-14 and cases.relerr(K1, K0) < 1e-14
+    dP = torch.from_numpy(np.ascontiguousarray(P.T)).cuda()
+    for nsh in (1, 3):
+        tj, tk = torch.zeros_like(dP), torch.zeros_like(dP)
+        for sh in range(nsh):
+            dJ, dK = torch.empty_like(dP), torch.empty_like(dP)
+            basis.coulomb_exchange_device(dP.data_ptr(), dJ.data_ptr(), dK.data_ptr(), 0.5, sh, nsh)
+            tj += dJ
+            tk += dK
+        assert cases.relerr(tj.cpu().numpy().T, J0) < TOL and cases.relerr(tk.cpu().numpy().T, K0) < TOL
+    # non-zero patterns reported for compact collectives cover everything that is non-zero
+    for coul, M in ((False, K0), (True, J0)):
+        bs, pairs = basis.exchange_output_pattern(coul)
+        mask = np.zeros((n, n), bool)
+        for (sj, sk) in pairs:
+            mask[np.ix_(bs == sj, bs == sk)] = True
+        assert np.all(M[~mask] == 0.0)
