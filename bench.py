@@ -307,7 +307,7 @@ def main():
     nst = max(acc["n"], 1)
     nl = max(acc["launches_tgemm"], 1)
     ach = acc["alg_tgemm"] / (acc["ms_tgemm"] * 1e-3) / 1e12 if acc["ms_tgemm"] > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "k_gemm (in-element exchange, FP64 DMMA)", "achieved": ach, "peak": fp64_peak,
+    roofline = {"bound": "tensor", "kernel": "k_tgemm (in-element exchange, FP64 DMMA)", "achieved": ach, "peak": fp64_peak,
                 "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": None,
                 "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                 "alg_flops_per_launch": acc["alg_tgemm"] / nl, "ms_per_launch": acc["ms_tgemm"] / nl,

@@ -35,7 +35,7 @@ class _TablesInfo(ctypes.Structure):
 
 
 EXPORTED_SYMBOLS = [
-    "hfq_last_error", "hfq_tables_atomic", "hfq_tables_sadatom", "hfq_tables_diatomic", "hfq_tables_from_arrays", "hfq_tables_get_info",
+    "hfq_last_error", "hfq_tables_atomic", "hfq_tables_atomic_yukawa", "hfq_tables_sadatom", "hfq_tables_diatomic", "hfq_tables_from_arrays", "hfq_tables_get_info",
     "hfq_tables_get_ints", "hfq_tables_get_doubles", "hfq_tables_get_block", "hfq_tables_one_electron",
     "hfq_tables_destroy", "hfq_create", "hfq_destroy", "hfq_nbf", "hfq_set_absm_symmetric", "hfq_coulomb",
     "hfq_exchange", "hfq_coulomb_device", "hfq_exchange_device", "hfq_last_timings", "hfq_exchange_output_pattern",
@@ -56,6 +56,7 @@ def lib():
     L.hfq_last_error.restype = ctypes.c_char_p
     vp, ci, cd, i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_int64
     L.hfq_tables_atomic.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ci, ci, cd, ci, cd, ci]
+    L.hfq_tables_atomic_yukawa.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ci, ci, cd, ci, cd, ci, cd]
     L.hfq_tables_sadatom.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ci, cd, ci, cd, ci]
     L.hfq_tables_diatomic.argtypes = [ctypes.POINTER(vp), ci, ci, cd, _c_int_p, ci, ci, ci, cd, ci, cd, ci]
     L.hfq_tables_from_arrays.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(_TablesDesc)]
@@ -128,6 +129,12 @@ class Tables:
     def atomic(cls, Z, lmax, mmax, nelem, nnodes=15, Rmax=40.0, igrid=4, zexp=2.0, nquad=0):
         h = ctypes.c_void_p()
         _check(lib().hfq_tables_atomic(ctypes.byref(h), Z, lmax, mmax, nelem, nnodes, Rmax, igrid, zexp, nquad))
+        return cls(h)
+
+    @classmethod
+    def atomic_yukawa(cls, Z, lmax, mmax, nelem, nnodes=15, Rmax=40.0, igrid=4, zexp=2.0, nquad=0, lam=0.4):
+        h = ctypes.c_void_p()
+        _check(lib().hfq_tables_atomic_yukawa(ctypes.byref(h), Z, lmax, mmax, nelem, nnodes, Rmax, igrid, zexp, nquad, lam))
         return cls(h)
 
     @classmethod
@@ -348,6 +355,18 @@ class AtomicTwoDBasis(_BasisBase):
 
     def _make_tables(self):
         return Tables.atomic(*self._args)
+
+    def compute_yukawa(self, lam):
+        """TwoDBasisT::compute_yukawa (src/atomic/TwoDBasis.cpp:737-758): Yukawa-screened caches."""
+        self._rs = _BasisBase(self._device)
+        self._rs._tables = Tables.atomic_yukawa(*self._args, lam=lam)
+        return self
+
+    def rs_exchange(self, P):
+        """TwoDBasisT::rs_exchange (src/atomic/TwoDBasis.cpp:1001-1131), Yukawa kernel."""
+        if getattr(self, "_rs", None) is None:
+            raise ValueError("Primitive teis have not been computed!\n")
+        return self._rs.exchange(P)
 
 
 class DiatomicTwoDBasis(_BasisBase):

@@ -8,6 +8,7 @@
 // libhelfem/src/RadialBasis.cpp:245-257,643-716 and
 // libhelfem/src/quadrature.cpp:37-161 (nested quadrature for r_<^L/r_>^(L+1)).
 #include <cmath>
+#include <limits>
 #include <map>
 #include <memory>
 
@@ -111,7 +112,37 @@ NestedRule make_nested_rule(const FEBasis &fe, int iel, int n) {
 // In-element tensor T[(ij),(kl)] = int int B_i B_j(r) r_<^L / r_>^(L+1) B_k B_l(r')
 // at a fixed rule (quadrature.cpp:77-161): cumulative inner integral, rescaled
 // by (r_{ip-1}/r_ip)^(L+1) between neighbouring outer points.
-Mat twoe_fixed(const FEBasis &fe, int iel, int L, const NestedRule &nr) {
+// fsmallbig(r, R): kernel with r < R inside one sub-interval; fbig(r): its outer factor, used to
+// carry the cumulative integral from one outer point to the next.
+//   bare Coulomb: (r/R)^L / R and r^(-L-1);  Yukawa: i_L(lambda r) k_L(lambda R) and k_L(lambda r)
+struct RadialKernel {
+  std::function<double(double, double)> fsmallbig;
+  std::function<double(double)> fbig;
+};
+
+// Modified spherical Bessel functions (libhelfem/include/math.h:68-110)
+double bessel_il(double r, int L) {
+  const double a = std::fabs(r);
+  double val;
+  if (a < 0.5) {
+    double dfac = 1.0;
+    for (int j = 3; j <= 2 * L + 1; j += 2) dfac *= j;
+    double term = std::pow(a, L) / dfac;
+    val = term;
+    const double r2half = 0.5 * a * a, tol = std::numeric_limits<double>::epsilon() * 0.01;
+    for (int k = 1; k < 256; k++) {
+      term *= r2half / ((double)k * (2 * L + 2 * k + 1));
+      val += term;
+      if (std::fabs(term) <= tol * std::fabs(val)) break;
+    }
+  } else {
+    val = std::cyl_bessel_i(L + 0.5, a) * std::sqrt(std::acos(-1.0) / (2.0 * a));
+  }
+  return (r < 0.0 && (L & 1)) ? -val : val;
+}
+double bessel_kl(double r, int L) { return std::cyl_bessel_k(L + 0.5, r) * std::sqrt(2.0 / (std::acos(-1.0) * r)); }
+
+Mat twoe_fixed(const FEBasis &fe, int iel, const RadialKernel &ker, const NestedRule &nr) {
   const int n = (int)nr.x.size(), nbf = nr.bf.cols, nn = nbf * nbf;
   const double rlen = fe.scale(iel);
   Mat inner(n, nn);
@@ -119,13 +150,13 @@ Mat twoe_fixed(const FEBasis &fe, int iel, int L, const NestedRule &nr) {
   for (int ip = 0; ip < n; ip++) {
     if (ip == 0 && nr.empty_first) continue;
     const double b = nr.r[ip];
-    for (int q = 0; q < n; q++) wp[q] = nr.w[q] * (std::pow(nr.subr[ip][q] / b, L) / b) * nr.sublen[ip];
+    for (int q = 0; q < n; q++) wp[q] = nr.w[q] * ker.fsmallbig(nr.subr[ip][q], b) * nr.sublen[ip];
     const Mat g = weighted_gram(nr.subbf[ip], wp, nr.subbf[ip]);
     for (int c = 0; c < nn; c++) inner(ip, c) = g.a[c];
   }
   for (int ip = 1; ip < n; ip++) {
     if (ip == 1 && nr.empty_first) continue;
-    const double fac = std::pow(nr.r[ip], -L - 1) / std::pow(nr.r[ip - 1], -L - 1);
+    const double fac = ker.fbig(nr.r[ip]) / ker.fbig(nr.r[ip - 1]);
     for (int c = 0; c < nn; c++) inner(ip, c) += inner(ip - 1, c) * fac;
   }
   // outer integral: ints = (w rlen B_i B_j)^T inner, then symmetrise over r<->r'
@@ -189,8 +220,8 @@ void pivoted_cholesky(const Mat &A, double tol, std::vector<double> &Lout, int &
 
 }  // namespace
 
-BasisTables build_atomic_tables(int Z, int lmax, int mmax, int nelem, int nnodes, double Rmax, int igrid, double zexp,
-                                int nquad) {
+static BasisTables build_atomic_common(int Z, int lmax, int mmax, int nelem, int nnodes, double Rmax, int igrid,
+                                       double zexp, int nquad, bool yukawa, double lambda) {
   BasisTables t;
   t.kind = BasisKind::Atomic;
   t.nch = 1;
@@ -219,13 +250,15 @@ BasisTables build_atomic_tables(int Z, int lmax, int mmax, int nelem, int nnodes
   for (int L = 0; L < N_L; L++) {
     t.lmL.push_back(L);
     t.lmM.push_back(-1);
-    t.pref.push_back(4.0 * pi / (2 * L + 1));
+    // bare: 4 pi/(2L+1) (TwoDBasis.cpp:835,965); Yukawa: 4 pi lambda (:1082)
+    t.pref.push_back(yukawa ? 4.0 * pi * lambda : 4.0 * pi / (2 * L + 1));
   }
   t.sign_by_M = false;
   t.Lext = 0;
   t.blocks.resize((size_t)N_L * t.Nel);
 
   auto bfR = [&](const std::vector<double> &x, int iel) { return radial_bf(fe, x, iel); };
+  auto bfB = [&](const std::vector<double> &x, int iel) { return fe.eval_dnf(x, 0, iel); };
   const int nstart = std::min(std::max(t.nquad, 5), kOrderCap);
 
 #pragma omp parallel for schedule(dynamic)
@@ -239,19 +272,44 @@ BasisTables build_atomic_tables(int Z, int lmax, int mmax, int nelem, int nnodes
     for (int L = 0; L < N_L; L++) {
       ChannelBlock &b = t.blocks[(size_t)L * t.Nel + iel];
       b.n = fe.nprim(iel);
-      // r^L and r^(-L-1) weighted overlaps of B/r: int (B/r)(B/r) r^(n+2) dr
-      const Mat sm = element_integral_auto(fe, iel, bfR, [L](double r) { return std::pow(r, L + 2); }, -1);
-      b.small = sm.a;
-      if (iel > 0) {  // never needed (and divergent) on the element touching r = 0
-        const Mat bg = element_integral_auto(fe, iel, bfR, [L](double r) { return std::pow(r, -L - 1 + 2); }, -1);
-        b.big = bg.a;
+      RadialKernel ker;
+      if (!yukawa) {
+        // r^L and r^(-L-1) weighted overlaps of B/r: int (B/r)(B/r) r^(n+2) dr
+        const Mat sm = element_integral_auto(fe, iel, bfR, [L](double r) { return std::pow(r, L + 2); }, -1);
+        b.small = sm.a;
+        if (iel > 0) {  // never needed (and divergent) on the element touching r = 0
+          const Mat bg = element_integral_auto(fe, iel, bfR, [L](double r) { return std::pow(r, -L - 1 + 2); }, -1);
+          b.big = bg.a;
+        }
+        ker.fsmallbig = [L](double r, double R) { return std::pow(r / R, L) / R; };
+        ker.fbig = [L](double r) { return std::pow(r, -L - 1); };
+      } else {
+        // int B B i_L(lambda r) dr and int B B k_L(lambda r) dr (RadialBasis.cpp:320-330)
+        const Mat sm = element_integral_auto(fe, iel, bfB, [L, lambda](double r) { return bessel_il(r * lambda, L); }, -1);
+        b.small = sm.a;
+        if (iel > 0) {
+          const Mat bg = element_integral_auto(fe, iel, bfB, [L, lambda](double r) { return bessel_kl(r * lambda, L); }, -1);
+          b.big = bg.a;
+        }
+        ker.fsmallbig = [L, lambda](double r, double R) { return bessel_il(r * lambda, L) * bessel_kl(R * lambda, L); };
+        ker.fbig = [L, lambda](double r) { return bessel_kl(r * lambda, L); };
       }
-      const Mat tei = converge_block([&](int n) { return twoe_fixed(fe, iel, L, *rule(n)); }, nstart, kOrderCap);
+      const Mat tei = converge_block([&](int n) { return twoe_fixed(fe, iel, ker, *rule(n)); }, nstart, kOrderCap);
       pivoted_cholesky(tei, kCholTol, b.B, b.rank);
       b.sigma.assign(b.rank, 1.0);
     }
   }
   return t;
+}
+
+BasisTables build_atomic_tables(int Z, int lmax, int mmax, int nelem, int nnodes, double Rmax, int igrid, double zexp,
+                                int nquad) {
+  return build_atomic_common(Z, lmax, mmax, nelem, nnodes, Rmax, igrid, zexp, nquad, false, 0.0);
+}
+
+BasisTables build_atomic_yukawa_tables(int Z, int lmax, int mmax, int nelem, int nnodes, double Rmax, int igrid,
+                                       double zexp, int nquad, double lambda) {
+  return build_atomic_common(Z, lmax, mmax, nelem, nnodes, Rmax, igrid, zexp, nquad, true, lambda);
 }
 
 BasisTables build_sadatom_tables(int Z, int lmax, int nelem, int nnodes, double Rmax, int igrid, double zexp,

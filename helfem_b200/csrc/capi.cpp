@@ -68,6 +68,18 @@ int hfq_tables_atomic(hfq_tables **out, int Z, int lmax, int mmax, int nelem, in
   });
 }
 
+int hfq_tables_atomic_yukawa(hfq_tables **out, int Z, int lmax, int mmax, int nelem, int nnodes, double Rmax, int igrid,
+                             double zexp, int nquad, double lambda) {
+  if (!out || lmax < 0 || mmax < 0 || mmax > lmax || nelem < 1 || nnodes < 2 || nnodes > 16 || !(Rmax > 0.0) || !(lambda > 0.0))
+    return fail(HFQ_ERR_INVALID, "hfq_tables_atomic_yukawa: invalid argument");
+  return guarded([&] {
+    auto *h = new hfq_tables;
+    h->t = hfq::build_atomic_yukawa_tables(Z, lmax, mmax, nelem, nnodes, Rmax, igrid, zexp, nquad, lambda);
+    *out = h;
+    return HFQ_OK;
+  });
+}
+
 int hfq_tables_sadatom(hfq_tables **out, int Z, int lmax, int nelem, int nnodes, double Rmax, int igrid, double zexp,
                        int nquad) {
   if (!out || lmax < 0 || nelem < 1 || nnodes < 2 || nnodes > 16 || !(Rmax > 0.0))

@@ -405,8 +405,8 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
   // opt-in shared memory sizes
   CK(cudaFuncSetAttribute(dev::k_offdiag_mma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
   CK(cudaFuncSetAttribute(dev::k_offdiag_mma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-  CK(cudaFuncSetAttribute(dev::k_tgemm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  CK(cudaFuncSetAttribute(dev::k_tgemm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(dev::k_tgemm<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(dev::k_tgemm<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 }
 
 
@@ -807,9 +807,9 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
       const size_t smem = (size_t)2 * (256 * 36 + 32 * 68) * sizeof(double);
       const dim3 grid(s.NB / 64, (unsigned)bt.ngitems);
       if (s.nab % 2 == 0)
-        dev::k_tgemm<true><<<grid, 256, smem, st>>>(bt.gitems.p, bt.gentries.p);
+        dev::k_tgemm<true, 8><<<grid, 256, smem, st>>>(bt.gitems.p, bt.gentries.p);
       else
-        dev::k_tgemm<false><<<grid, 256, smem, st>>>(bt.gitems.p, bt.gentries.p);
+        dev::k_tgemm<false, 8><<<grid, 256, smem, st>>>(bt.gitems.p, bt.gentries.p);
       CK(cudaGetLastError());
     }
     CK(cudaEventRecord(s.ev[4], st));

@@ -595,13 +595,14 @@ k_offdiag_mma(BasisDev b, const OffItem *__restrict__ items, const OffEntry *__r
 // In-element exchange GEMM on the FP64 tensor pipe, one CTA tile covering ALL rows:
 //   C[M x 64-column tile] (+)= sum_entries A_e[M x K] R_e[K x N],  M = Ni^2 <= 256, K = nab*Ni^2
 // A_e rows are K-contiguous (dense exchange-ordered kernel), row k of R_e lives at
-// B_e + browoff[k].  Every R row is read exactly once per launch.  3-stage cp.async
-// pipeline, 8 warps; warp w owns row tiles {w, w+8, w+16, w+24} x all 8 column tiles.
+// B_e + browoff[k].  Every R row is read exactly once per launch.  2-stage cp.async
+// pipeline, NW warps; warp w owns row tiles {w, w+NW, ...} x all 8 column tiles (NW = 8 is the
+// measured optimum: 16 warps gave 38.5 ms vs 38.1 ms on the N2 workload).
 // ---------------------------------------------------------------------------
-template <bool A16>
-__global__ void __launch_bounds__(256, 1)
+template <bool A16, int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
 k_tgemm(const GemmItem *__restrict__ items, const GemmEntry *__restrict__ entries) {
-  constexpr int BK = 32, BN = 64, MAXM = 256, STAGES = 2;
+  constexpr int BK = 32, BN = 64, MAXM = 256, STAGES = 2, NTHR = NW * 32, MT = 32 / NW;
   constexpr int LDA_S = BK + 4, LDB_S = BN + 4;
   constexpr int A_STAGE = MAXM * LDA_S, B_STAGE = BK * LDB_S;
   constexpr int CPR = BK / 2;   // 16-byte chunks per A row
@@ -614,9 +615,9 @@ k_tgemm(const GemmItem *__restrict__ items, const GemmEntry *__restrict__ entrie
   const int nkc = (it.K + BK - 1) / BK;
   const int nsteps = (it.ent1 - it.ent0) * nkc;
 
-  double acc[4][8][2];
+  double acc[MT][8][2];
 #pragma unroll
-  for (int i = 0; i < 4; i++)
+  for (int i = 0; i < MT; i++)
 #pragma unroll
     for (int j = 0; j < 8; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
@@ -627,7 +628,7 @@ k_tgemm(const GemmItem *__restrict__ items, const GemmEntry *__restrict__ entrie
     double *as = As + stage * A_STAGE, *bs = Bs + stage * B_STAGE;
     if (A16) {
 #pragma unroll 4
-      for (int idx = tid; idx < MAXM * CPR; idx += 256) {
+      for (int idx = tid; idx < MAXM * CPR; idx += NTHR) {
         const int m = idx / CPR, ch = idx % CPR, k = kc + ch * 2;
         int bytes = 0;
         if (m < it.M && k < it.K) bytes = (k + 1 < it.K) ? 16 : 8;
@@ -636,7 +637,7 @@ k_tgemm(const GemmItem *__restrict__ items, const GemmEntry *__restrict__ entrie
       }
     } else {
 #pragma unroll 4
-      for (int idx = tid; idx < MAXM * BK; idx += 256) {
+      for (int idx = tid; idx < MAXM * BK; idx += NTHR) {
         const int m = idx / BK, kk = idx % BK, k = kc + kk;
         const int bytes = (m < it.M && k < it.K) ? 8 : 0;
         const double *src = e.A + (int64_t)(m < it.M ? m : 0) * e.lda + (k < it.K ? k : 0);
@@ -644,7 +645,7 @@ k_tgemm(const GemmItem *__restrict__ items, const GemmEntry *__restrict__ entrie
       }
     }
 #pragma unroll 4
-    for (int idx = tid; idx < BK * 32; idx += 256) {   // B tile: BK rows x 32 chunks of 16 bytes
+    for (int idx = tid; idx < BK * 32; idx += NTHR) {   // B tile: BK rows x 32 chunks of 16 bytes
       const int kk = idx >> 5, ch = idx & 31, k = kc + kk;
       const int bytes = (k < it.K) ? 16 : 0;
       const double *src = e.B + (k < it.K ? it.browoff[k] : 0) + bn + ch * 2;
@@ -661,11 +662,11 @@ k_tgemm(const GemmItem *__restrict__ items, const GemmEntry *__restrict__ entrie
     cp_async_commit();
     const double *as = As + (step & 1) * A_STAGE + lr * LDA_S + lc, *bs = Bs + (step & 1) * B_STAGE + lc * LDB_S + lr;
     // software-pipelined fragments: load k-step kk+4 while the DMMAs of kk issue
-    double bf[2][8], af[2][4];
+    double bf[2][8], af[2][MT];
 #pragma unroll
     for (int j = 0; j < 8; j++) bf[0][j] = bs[j * 8];
 #pragma unroll
-    for (int i = 0; i < 4; i++) af[0][i] = as[(warp + i * 8) * 8 * LDA_S];
+    for (int i = 0; i < MT; i++) af[0][i] = as[(warp + i * NW) * 8 * LDA_S];
 #pragma unroll
     for (int ks = 0; ks < BK / 4; ks++) {
       const int cur = ks & 1, nxt = cur ^ 1;
@@ -673,18 +674,18 @@ k_tgemm(const GemmItem *__restrict__ items, const GemmEntry *__restrict__ entrie
 #pragma unroll
         for (int j = 0; j < 8; j++) bf[nxt][j] = bs[(ks + 1) * 4 * LDB_S + j * 8];
 #pragma unroll
-        for (int i = 0; i < 4; i++) af[nxt][i] = as[(warp + i * 8) * 8 * LDA_S + (ks + 1) * 4];
+        for (int i = 0; i < MT; i++) af[nxt][i] = as[(warp + i * NW) * 8 * LDA_S + (ks + 1) * 4];
       }
 #pragma unroll
-      for (int i = 0; i < 4; i++)
+      for (int i = 0; i < MT; i++)
 #pragma unroll
         for (int j = 0; j < 8; j++) dmma(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
     }
   }
   cp_async_wait<0>();
 #pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const int m = (warp + i * 8) * 8 + lr;
+  for (int i = 0; i < MT; i++) {
+    const int m = (warp + i * NW) * 8 + lr;
     if (m >= it.M) continue;
 #pragma unroll
     for (int j = 0; j < 8; j++) {

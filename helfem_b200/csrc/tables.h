@@ -59,6 +59,11 @@ struct BasisTables {
 // atomic: Z, lmax, mmax, nelem, nnodes (LIP, primbas=4), Rmax, grid type, zexp, nquad (0 -> 5*nnodes)
 BasisTables build_atomic_tables(int Z, int lmax, int mmax, int nelem, int nnodes, double Rmax, int igrid, double zexp,
                                 int nquad);
+// Yukawa-screened caches of the same basis (TwoDBasis::compute_yukawa, src/atomic/TwoDBasis.cpp:737-758):
+// exchange() on these tables is the reference's rs_exchange() for a Yukawa range separation
+// (:1001-1131): i_L / k_L weighted cross-element factors, Yukawa in-element kernel, prefactor 4 pi lambda
+BasisTables build_atomic_yukawa_tables(int Z, int lmax, int mmax, int nelem, int nnodes, double Rmax, int igrid,
+                                       double zexp, int nquad, double lambda);
 // spherically averaged atom (src/sadatom/basis.{h,cpp}): one angular function per l (m summed
 // out), same radial caches as the atomic basis; exchange couples density block l_in to output
 // block l_out through the m-averaged squared Gaunt coefficient (src/sadatom/basis.cpp:209-312)

@@ -43,6 +43,12 @@ const char *hfq_last_error(void);
 int hfq_tables_atomic(hfq_tables **out, int Z, int lmax, int mmax, int nelem, int nnodes, double Rmax, int igrid,
                       double zexp, int nquad);
 
+/* Range-separated exchange, Yukawa kernel: TwoDBasisT::compute_yukawa(lambda) (src/atomic/TwoDBasis.cpp:737-758).
+ * hfq_exchange on a context created from these tables is TwoDBasisT::rs_exchange(P) (:1001-1131, Yukawa branch).
+ * (The erfc kernel of compute_erfc is not built yet.) */
+int hfq_tables_atomic_yukawa(hfq_tables **out, int Z, int lmax, int mmax, int nelem, int nnodes, double Rmax, int igrid,
+                             double zexp, int nquad, double lambda);
+
 /* Spherically averaged atom: sadatom::basis::TwoDBasis ctor + compute_tei()
  * (src/sadatom/basis.cpp:50-184).  One angular function per l = 0..lmax; matrices passed to
  * hfq_exchange are the block-diagonal dense form of the reference's per-l Cube

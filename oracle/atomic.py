@@ -23,6 +23,37 @@ def angular_basis(lmax, mmax):
     return np.array(lval), np.array(mval)
 
 
+def bessel_il(x, L):
+    """Modified spherical Bessel function i_L; power series below 0.5 as libhelfem/include/math.h:68-91."""
+    from scipy.special import iv
+    x = np.atleast_1d(np.asarray(x, dtype=float))
+    out = np.zeros_like(x)
+    small = np.abs(x) < 0.5
+    if small.any():
+        a = np.abs(x[small])
+        dfac = 1.0
+        for j in range(3, 2 * L + 2, 2):
+            dfac *= j
+        term = a ** L / dfac
+        val = term.copy()
+        for k in range(1, 256):
+            term = term * (0.5 * a * a) / (k * (2 * L + 2 * k + 1))
+            val += term
+        out[small] = val
+    if (~small).any():
+        a = np.abs(x[~small])
+        out[~small] = iv(L + 0.5, a) * np.sqrt(np.pi / (2 * a))
+    return out if out.size > 1 else float(out[0])
+
+
+def bessel_kl(x, L):
+    """k_L(x) = sqrt(2/(pi x)) K_(L+1/2)(x); libhelfem/include/math.h:101-105."""
+    from scipy.special import kv
+    x = np.asarray(x, dtype=float)
+    with np.errstate(all="ignore"):
+        return kv(L + 0.5, x) * np.sqrt(2 / (np.pi * x))
+
+
 def pivoted_cholesky(A, tol):
     """Diagonal-pivoted Cholesky, absolute tolerance on the residual diagonal;
     libhelfem/src/RadialBasis.cpp:670-709."""
@@ -94,7 +125,7 @@ class RadialBasis:
         return self.assemble(lambda iel: -self.fem.matrix_element_auto(iel, self.get_bf, self.get_bf, lambda r: r))
 
     # ---- two-electron in-element integrals: libhelfem/src/quadrature.cpp:37-161
-    def _twoe_fixed(self, iel, L, x, wx):
+    def _twoe_fixed(self, iel, L, x, wx, fsb=None, fbig=None):
         rmin, rmax = self.fem.begin(iel), self.fem.end(iel)
         en = self.fem.enabled(iel)
         x0 = self.fem.x0
@@ -108,8 +139,8 @@ class RadialBasis:
             # quadrature.cpp:37-75 with fsmallbig(r,R)=(r/R)^L/R
             smid, slen = 0.5 * (b + a), 0.5 * (b - a)
             rs = smid + slen * x
-            fsb = (rs / b) ** L / b
-            wp = wx * fsb * slen
+            fv = (rs / b) ** L / b if fsb is None else fsb(rs, b)
+            wp = wx * fv * slen
             xpoly = (rs - rmid) / rlen
             bf = fem.lip_eval(xpoly, x0, 0)[:, en]
             return ((bf * wp[:, None]).T @ bf).reshape(-1, order="F")
@@ -122,7 +153,10 @@ class RadialBasis:
         for ip in range(1, nq):
             if ip == 1 and empty_first:
                 continue
-            inner[ip] += inner[ip - 1] * (r[ip] ** float(-L - 1) / r[ip - 1] ** float(-L - 1))
+            if fbig is None:
+                inner[ip] += inner[ip - 1] * (r[ip] ** float(-L - 1) / r[ip - 1] ** float(-L - 1))
+            else:
+                inner[ip] += inner[ip - 1] * (fbig(r[ip]) / fbig(r[ip - 1]))
         bf = fem.lip_eval(x, x0, 0)[:, en]
         bfprod = (bf[:, :, None] * bf[:, None, :]).reshape(nq, nbf * nbf)
         bfprod = bfprod * (wx * rlen)[:, None]
@@ -133,6 +167,23 @@ class RadialBasis:
         """RadialBasis.cpp:643-663 (order-doubling Gauss-Lobatto)."""
         nstart = min(max(len(self.xq), 5), 512)
         return fem.converge(lambda n: self._twoe_fixed(iel, L, *fem.lobatto(n)), nstart, 512)
+
+    # ---- Yukawa kernel: libhelfem/src/quadrature.cpp:164-201, libhelfem/include/math.h:68-110
+    def yukawa_integral(self, L, lam, iel):
+        il = lambda x: bessel_il(x, L)
+        kl = lambda x: bessel_kl(x, L)
+        nstart = min(max(len(self.xq), 5), 512)
+        return fem.converge(lambda n: self._twoe_fixed(iel, L, *fem.lobatto(n),
+                                                       fsb=lambda r, R: il(r * lam) * kl(R * lam), fbig=lambda r: kl(r * lam)),
+                            nstart, 512)
+
+    def bessel_integral(self, which, L, lam, iel):
+        """int B B i_L(lam r) dr / int B B k_L(lam r) dr; RadialBasis.cpp:320-330."""
+        if which == "i":
+            f = lambda r: bessel_il(r * lam, L)
+        else:
+            f = lambda r: bessel_kl(r * lam, L)
+        return self.fem.matrix_element_auto(iel, self._B(0), self._B(0), f)
 
     def twoe_integral_cholesky(self, L, iel, tol=1e-12):
         return pivoted_cholesky(self.twoe_integral(L, iel), tol)
@@ -187,6 +238,29 @@ class TwoDBasis:
                 if iel > 0:
                     self.disjoint_m1L[L * Nel + iel] = self.radial.radial_integral(-L - 1, iel)
                 self.prim_chol[L * Nel + iel] = self.radial.twoe_integral_cholesky(L, iel)
+
+    def compute_yukawa(self, lam):
+        """TwoDBasis.cpp:737-758."""
+        N_L = 2 * int(self.lval.max()) + 1
+        Nel = self.radial.Nel()
+        self.lam = lam
+        self.disjoint_iL = [None] * (N_L * Nel); self.disjoint_kL = [None] * (N_L * Nel); self.rs_chol = [None] * (N_L * Nel)
+        for L in range(N_L):
+            for iel in range(Nel):
+                self.disjoint_iL[L * Nel + iel] = self.radial.bessel_integral("i", L, lam, iel)
+                if iel > 0:
+                    self.disjoint_kL[L * Nel + iel] = self.radial.bessel_integral("k", L, lam, iel)
+                self.rs_chol[L * Nel + iel] = pivoted_cholesky(self.radial.yukawa_integral(L, lam, iel), 1e-12)
+
+    def rs_exchange(self, P):
+        """TwoDBasis.cpp:1001-1131, Yukawa branch: same loops as exchange() with the screened caches
+        and prefactor 4 pi lambda."""
+        save = (self.disjoint_L, self.disjoint_m1L, self.prim_chol)
+        self.disjoint_L, self.disjoint_m1L, self.prim_chol = self.disjoint_iL, self.disjoint_kL, self.rs_chol
+        try:
+            return self.exchange(P, Lfac=lambda L: 4.0 * np.pi * self.lam)
+        finally:
+            self.disjoint_L, self.disjoint_m1L, self.prim_chol = save
 
     # ---- FE assemblers, CoulombExchangeFE.h:432-530
     def _assemble_J(self, L, P):
@@ -258,7 +332,7 @@ class TwoDBasis:
                         J[i * N:(i + 1) * N, j * N:(j + 1) * N] += cpl * Jaux[(L, M)]
         return J
 
-    def exchange(self, P):
+    def exchange(self, P, Lfac=None):
         """TwoDBasis.cpp:879-999; returns -K like the reference."""
         if self.prim_chol is None:
             raise RuntimeError("Primitive teis have not been computed!")
@@ -282,8 +356,8 @@ class TwoDBasis:
                             cpl = g.coeff(lv[j], mv[j], L, M, lv[i]) * g.coeff(lv[k], mv[k], L, M, lv[l])
                             if cpl == 0.0:
                                 continue
-                            Lfac = 4.0 * np.pi / (2 * L + 1)
-                            R[L] = R.get(L, 0.0) + (Lfac * cpl) * P[i * N:(i + 1) * N, l * N:(l + 1) * N]
+                            lf = 4.0 * np.pi / (2 * L + 1) if Lfac is None else Lfac(L)
+                            R[L] = R.get(L, 0.0) + (lf * cpl) * P[i * N:(i + 1) * N, l * N:(l + 1) * N]
                 Kb = np.zeros((N, N))
                 for L, RL in sorted(R.items()):
                     Kb += self._assemble_K(L, RL)

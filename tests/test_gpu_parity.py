@@ -207,3 +207,29 @@ def test_fused_coulomb_exchange(hb):
         for (sj, sk) in pairs:
             mask[np.ix_(bs == sj, bs == sk)] = True
         assert np.all(M[~mask] == 0.0)
+
+
+def test_atomic_rs_exchange_yukawa(hb):
+    """Range-separated exchange with the Yukawa kernel (CAMY-type functionals):
+    compute_yukawa + rs_exchange, src/atomic/TwoDBasis.cpp:737-758, :1001-1131."""
+    lam = 0.34
+    ob = cases.oracle_atomic(4, 1, 1, 2)
+    ob.compute_yukawa(lam)
+    basis = hb.AtomicTwoDBasis(4, 1, 1, 2).compute_tei().compute_yukawa(lam)
+    n = ob.Nbf()
+    P = cases.random_density(n, 3, 41, cases.m_blocks(ob.mval, ob.Nrad(), False))
+    Ko = ob.rs_exchange(P)
+    Kg = basis.rs_exchange(P)
+    assert cases.relerr(Kg, Ko) < 1e-11       # Bessel functions come from two libraries (libstdc++ vs scipy)
+    # the screened exchange is weaker than the bare one, and tends to it for small lambda
+    K0 = basis.exchange(P)
+    assert np.linalg.norm(Kg) < np.linalg.norm(K0)
+    # host setup parity of the screened caches
+    Ty = basis._rs.tables
+    Nel = 2
+    for L in range(Ty.nlm):
+        for e in range(Nel):
+            sm, bg, B, _ = Ty.block(L, e)
+            assert np.abs(sm[0] - ob.disjoint_iL[L * Nel + e]).max() <= 1e-12 * np.abs(sm[0]).max()
+            W, Wo = B @ B.T, ob.rs_chol[L * Nel + e] @ ob.rs_chol[L * Nel + e].T
+            assert np.abs(W - Wo).max() <= 1e-10 * np.abs(Wo).max()
