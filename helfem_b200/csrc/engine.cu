@@ -75,11 +75,12 @@ struct Engine::Impl {
   // element-pair accumulator layout
   std::vector<int64_t> ep_off;
   int64_t op_stride = 0;
-  std::vector<int64_t> tperm_off;   // [Nel * nruns] offset of A_(e,run)
-  std::vector<int64_t> tperm_lda;   // [Nel * nruns]
+  std::vector<int64_t> tperm_off;   // [nlm * Nel] offset of the tiled in-element kernel A_(ilm,e)
   // device
   DevBuf<int> d_ang_off, d_ang_skip, d_sec_n, d_sec_ang, d_efirst, d_en, d_ang_sec, d_ang_pos, d_rad_e0, d_rad_e1;
-  DevBuf<double> d_G, d_small, d_big, d_B, d_sigma, d_tperm;
+  int tg_stages = 2, tg_maxM = 0;
+  size_t tg_smem = 0;
+  DevBuf<double> d_G, d_small, d_big, d_B, d_sigma, d_tperm, d_zrow;
   DevBuf<int64_t> d_blk_off, d_B_off, d_sig_off, d_ep_off;
   DevBuf<int> d_rank, d_chan_of, d_browoff_T, d_browoff_G, d_splist, d_op_src, d_sp_active;
   DevBuf<double> d_jfac, d_norms, d_Ppix, d_R, d_Kacc, d_Paux, d_JauxT, d_Jsec, d_P, d_O, d_O2;
@@ -332,29 +333,26 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
     s.op_stride = off;
   }
   s.d_ep_off.upload(s.ep_off, &dev_bytes_);
-  // ---- dense exchange-ordered in-element kernels  A_(e,run)[(rj,rk)][pos][ab][(ri,rl)]
+  // ---- dense exchange-ordered in-element kernels, one per (multipole channel, element), stored as
+  //      the pre-swizzled k-chunk tiles k_tgemm_ws bulk-copies (kernels.cuh: tperm_index)
   {
-    const int nruns = (int)s.run_nL.size();
-    s.tperm_off.assign((size_t)t.Nel * nruns, 0);
-    s.tperm_lda.assign((size_t)t.Nel * nruns, 0);
+    s.tperm_off.assign((size_t)nlm * t.Nel, 0);
     int64_t off = 0;
-    for (int e = 0; e < t.Nel; e++)
-      for (int r = 0; r < nruns; r++) {
-        const int64_t nn = (int64_t)t.en[e] * t.en[e];
-        s.tperm_off[(size_t)e * nruns + r] = off;
-        s.tperm_lda[(size_t)e * nruns + r] = (int64_t)s.run_nL[r] * s.nab * nn;
-        off += nn * s.run_nL[r] * s.nab * nn;
-      }
-    s.d_tperm.alloc((size_t)off, &dev_bytes_);
     for (int ilm = 0; ilm < nlm; ilm++)
       for (int e = 0; e < t.Nel; e++) {
-        const int n = t.en[e], r = s.chan_run[ilm];
-        const int64_t nn = (int64_t)n * n;
-        double *dst = s.d_tperm.p + s.tperm_off[(size_t)e * nruns + r] + (int64_t)s.chan_pos[ilm] * s.nab * nn;
+        const int nn = t.en[e] * t.en[e];
+        s.tperm_off[(size_t)ilm * t.Nel + e] = off;
+        off += dev::tperm_doubles(nn, s.nab * nn);
+      }
+    s.d_tperm.alloc((size_t)off, &dev_bytes_);
+    CK(cudaMemsetAsync(s.d_tperm.p, 0, (size_t)off * sizeof(double), stream_));
+    for (int ilm = 0; ilm < nlm; ilm++)
+      for (int e = 0; e < t.Nel; e++) {
+        const int n = t.en[e];
         dev::k_build_tperm<<<n * n, 256, 0, stream_>>>(
             s.d_B.p + s.B_off[(size_t)ilm * t.Nel + e], s.d_sigma.p + s.sig_off[(size_t)ilm * t.Nel + e], n,
-            s.ranks[(size_t)ilm * t.Nel + e], t.nch, t.kind == BasisKind::Atomic ? 1 : 0, dst,
-            s.tperm_lda[(size_t)e * nruns + r]);
+            s.ranks[(size_t)ilm * t.Nel + e], t.nch, t.kind == BasisKind::Atomic ? 1 : 0,
+            s.d_tperm.p + s.tperm_off[(size_t)ilm * t.Nel + e]);
       }
     CK(cudaGetLastError());
   }
@@ -405,8 +403,17 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
   // opt-in shared memory sizes
   CK(cudaFuncSetAttribute(dev::k_offdiag_mma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
   CK(cudaFuncSetAttribute(dev::k_offdiag_mma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-  CK(cudaFuncSetAttribute(dev::k_tgemm<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  CK(cudaFuncSetAttribute(dev::k_tgemm<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  {
+    // stages of the in-element GEMM ring: as many as fit in the 227 KB of shared memory, at most 4
+    s.tg_maxM = 0;
+    for (int e = 0; e < t.Nel; e++) s.tg_maxM = std::max(s.tg_maxM, t.en[e] * t.en[e]);
+    if (s.tg_maxM > 256) throw std::runtime_error("elements with more than 16 radial functions are not supported");
+    s.tg_stages = 4;
+    while (s.tg_stages > 2 && dev::tgemm_ws_smem(s.tg_maxM, s.tg_stages) > 227 * 1024) s.tg_stages--;
+    s.tg_smem = dev::tgemm_ws_smem(s.tg_maxM, s.tg_stages);
+    CK(cudaFuncSetAttribute(dev::k_tgemm_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.tg_smem));
+  }
+  s.d_zrow.upload(std::vector<double>(64, 0.0), &dev_bytes_);
 }
 
 
@@ -686,7 +693,6 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
     np->K_base = s.d_Kacc.p;
     // Batches: every batch takes an equal share of tasks from every active output pair, so each
     // launch works on all output pairs at once (grid size independent of the batch count).
-    const int nruns = (int)s.run_nL.size();
     std::vector<size_t> done(work.size(), 0);
     std::vector<char> started((size_t)work.size() * S, 0);
     size_t remaining = total_tasks;
@@ -729,10 +735,10 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
             gi.K = s.nab * n * n;
             gi.ent0 = (int)gentries.size();
             for (size_t k = k0; k < k1; k++) {
-              const int ilm = w.ilm[ti + k], r = s.chan_run[ilm];
+              const int ilm = w.ilm[ti + k];
               dev::GemmEntry ge;
-              ge.A = s.d_tperm.p + s.tperm_off[(size_t)e * nruns + r] + (int64_t)s.chan_pos[ilm] * s.nab * n * n;
-              ge.lda = s.tperm_lda[(size_t)e * nruns + r];
+              ge.A = s.d_tperm.p + s.tperm_off[(size_t)ilm * t.Nel + e];
+              ge.lda = 0;
               ge.B = s.d_R.p + (t0 + k) * slot_doubles;
               gentries.push_back(ge);
             }
@@ -804,12 +810,8 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
     CK(cudaEventRecord(s.ev[3], st));
     {
       // in-element exchange: one CTA tile covers all Ni^2 rows (R rows are read once)
-      const size_t smem = (size_t)2 * (256 * 36 + 32 * 68) * sizeof(double);
       const dim3 grid(s.NB / 64, (unsigned)bt.ngitems);
-      if (s.nab % 2 == 0)
-        dev::k_tgemm<true, 8><<<grid, 256, smem, st>>>(bt.gitems.p, bt.gentries.p);
-      else
-        dev::k_tgemm<false, 8><<<grid, 256, smem, st>>>(bt.gitems.p, bt.gentries.p);
+      dev::k_tgemm_ws<<<grid, 288, s.tg_smem, st>>>(bt.gitems.p, bt.gentries.p, s.d_zrow.p, s.tg_stages, s.tg_maxM);
       CK(cudaGetLastError());
     }
     CK(cudaEventRecord(s.ev[4], st));

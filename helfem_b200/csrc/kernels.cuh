@@ -336,13 +336,27 @@ k_gemm(const GemmItem *__restrict__ items, const GemmEntry *__restrict__ entries
 }
 
 // ---------------------------------------------------------------------------
+// Storage of one dense exchange-ordered in-element kernel A[(rj,rk)][K] (K = nab*n*n):
+// k-chunks of TP_BK columns, each chunk a dense [n*n rows][TP_BK] tile that is the exact
+// shared-memory image the GEMM wants (one bulk copy per tile).  Within a row the 4-double groups
+// are XOR-swizzled with (row & 7) so that the DMMA A-fragment reads (8 rows x 4 consecutive k)
+// hit every bank exactly twice (= the 2-wavefront minimum for 256 bytes).  Columns >= K are zero.
+// ---------------------------------------------------------------------------
+constexpr int TP_BK = 32;
+__host__ __device__ inline int64_t tperm_tile_doubles(int nn) { return (int64_t)nn * TP_BK; }
+__host__ __device__ inline int64_t tperm_doubles(int nn, int K) { return (int64_t)((K + TP_BK - 1) / TP_BK) * nn * TP_BK; }
+__host__ __device__ inline int64_t tperm_index(int row, int col, int nn) {
+  return (int64_t)(col / TP_BK) * nn * TP_BK + (int64_t)row * TP_BK + ((col % TP_BK) ^ (4 * (row & 7)));
+}
+
+// ---------------------------------------------------------------------------
 // Setup: dense exchange-ordered in-element kernel from the low-rank factor
 //   T[(rj*n + rk)][ab][(ri*n + rl)] = s_ab sum_p sigma_p B[a*nn + pair1, p] B[b*nn + rk + rl*n, p]
 //   pair1 = out_fast ? rj + ri*n : ri + rj*n
-// grid (n*n rows), dst row stride = ldT
+// grid (n*n rows); stored at tperm_index(row, ab*nn + ri*n + rl, nn)
 // ---------------------------------------------------------------------------
 static __global__ void k_build_tperm(const double *__restrict__ B, const double *__restrict__ sigma, int n, int rank, int nch,
-                              int out_fast, double *__restrict__ dst, int64_t ldT) {
+                              int out_fast, double *__restrict__ dst) {
   const int row = blockIdx.x, rj = row / n, rk = row % n, nn = n * n;
   for (int col = threadIdx.x; col < nch * nch * nn; col += blockDim.x) {
     const int ab = col / nn, il = col % nn, a = ab / nch, bb = ab % nch, ri = il / n, rl = il % n;
@@ -352,7 +366,7 @@ static __global__ void k_build_tperm(const double *__restrict__ B, const double 
     double s = 0.0;
     for (int p = 0; p < rank; p++) s += sigma[p] * b1[p * ldB] * b2[p * ldB];
     const double sgn = (nch == 2 && a != bb) ? -1.0 : 1.0;
-    dst[(int64_t)row * ldT + col] = sgn * s;
+    dst[tperm_index(row, col, nn)] = sgn * s;
   }
 }
 
@@ -592,97 +606,148 @@ k_offdiag_mma(BasisDev b, const OffItem *__restrict__ items, const OffEntry *__r
 }
 
 // ---------------------------------------------------------------------------
-// In-element exchange GEMM on the FP64 tensor pipe, one CTA tile covering ALL rows:
-//   C[M x 64-column tile] (+)= sum_entries A_e[M x K] R_e[K x N],  M = Ni^2 <= 256, K = nab*Ni^2
-// A_e rows are K-contiguous (dense exchange-ordered kernel), row k of R_e lives at
-// B_e + browoff[k].  Every R row is read exactly once per launch.  2-stage cp.async
-// pipeline, NW warps; warp w owns row tiles {w, w+NW, ...} x all 8 column tiles (NW = 8 is the
-// measured optimum: 16 warps gave 38.5 ms vs 38.1 ms on the N2 workload).
+// mbarrier / bulk-copy helpers (sm_90+ PTX; SASS UBLKCP + SYNCS)
 // ---------------------------------------------------------------------------
-template <bool A16, int NW>
-__global__ void __launch_bounds__(NW * 32, 1)
-k_tgemm(const GemmItem *__restrict__ items, const GemmEntry *__restrict__ entries) {
-  constexpr int BK = 32, BN = 64, MAXM = 256, STAGES = 2, NTHR = NW * 32, MT = 32 / NW;
-  constexpr int LDA_S = BK + 4, LDB_S = BN + 4;
-  constexpr int A_STAGE = MAXM * LDA_S, B_STAGE = BK * LDB_S;
-  constexpr int CPR = BK / 2;   // 16-byte chunks per A row
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---------------------------------------------------------------------------
+// In-element exchange GEMM, warp-specialised (same item/entry tables as k_tgemm):
+//   C[M x 64-column tile] (+)= sum_entries A_e[M x K] R_e[K x N],  M = Ni^2 <= 256, K = nab*Ni^2
+// A_e is stored as pre-swizzled [k-chunk][M][TP_BK] tiles (tperm_index), so the producer warp moves
+// a whole A stage with ONE cp.async.bulk (<= 64 KB) plus one 512-byte bulk copy per R row, all
+// counted on the stage's "full" mbarrier; the 8 DMMA warps wait on it, run their k-steps and
+// release the stage through an "empty" mbarrier.  No CTA-wide barrier in the main loop, so the
+// FP64 tensor pipe is fed by whichever warps hold data while others wait.  Row tiles past M read
+// stale shared memory; they only feed accumulator rows >= M, which are never stored.  A columns
+// >= K are zero in the tiles and R rows past K come from a zero row.  Warp w owns row tiles
+// {w, w+8, w+16, w+24} x all 8 column tiles.  NS = stages that fit (3 for the 15-node elements).
+// ---------------------------------------------------------------------------
+__host__ __device__ inline size_t tgemm_ws_smem(int M, int ns) {
+  // ns stages of (A tile [M][TP_BK] + R tile [TP_BK][68]); slack so that the row tiles past M that
+  // the last stage's warps still read stay inside the allocation; 2*ns mbarriers
+  return ((size_t)ns * ((size_t)M * TP_BK + TP_BK * 68) + (size_t)(256 - M) * TP_BK) * sizeof(double) + 16 * ns;
+}
+
+static __global__ void __launch_bounds__(288, 1)
+k_tgemm_ws(const GemmItem *__restrict__ items, const GemmEntry *__restrict__ entries, const double *__restrict__ zrow,
+           int NS, int maxM) {
+  constexpr int BK = TP_BK, BN = 64, NW = 8, MT = 4;
+  constexpr int LDB_S = BN + 4, B_STAGE = BK * LDB_S;
   extern __shared__ double sm[];
-  double *As = sm, *Bs = sm + STAGES * A_STAGE;
   const GemmItem it = items[blockIdx.y];
+  const int A_STAGE = maxM * BK;   // stage stride (largest M of the launch); rows >= it.M hold stale data
+  double *Bs = sm, *As = sm + NS * B_STAGE;
+  uint64_t *full = reinterpret_cast<uint64_t *>(As + (size_t)NS * A_STAGE + (256 - maxM) * BK), *empty = full + NS;
   const int bn = blockIdx.x * BN;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int lr = lane >> 2, lc = lane & 3;
   const int nkc = (it.K + BK - 1) / BK;
   const int nsteps = (it.ent1 - it.ent0) * nkc;
 
+  if (tid == 0) {
+    for (int s = 0; s < NS; s++) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, NW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+
+  if (warp == NW) {
+    // ---- producer ----
+    const uint32_t abytes = (uint32_t)(it.M * BK * 8);
+    int stage = 0, phase = 1, ent = it.ent0, kci = 0;
+    GemmEntry e = entries[ent];
+    for (int step = 0; step < nsteps; step++) {
+      mbar_wait(empty + stage, phase);
+      const int kc = kci * BK;
+      if (lane == 0) {
+        mbar_expect_tx(full + stage, abytes + BK * BN * 8);
+        bulk_g2s(As + (size_t)stage * A_STAGE, e.A + (int64_t)kci * it.M * BK, abytes, full + stage);
+      }
+      __syncwarp();
+      const double *src = (kc + lane < it.K) ? e.B + it.browoff[kc + lane] + bn : zrow;
+      bulk_g2s(Bs + stage * B_STAGE + lane * LDB_S, src, BN * 8, full + stage);
+      if (++kci == nkc) {
+        kci = 0;
+        if (++ent < it.ent1) e = entries[ent];
+      }
+      if (++stage == NS) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    return;
+  }
+
+  // ---- consumers ----
+  const int lr = lane >> 2, lc = lane & 3;
   double acc[MT][8][2];
 #pragma unroll
   for (int i = 0; i < MT; i++)
 #pragma unroll
     for (int j = 0; j < 8; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  // rows >= M are zero-filled so that every warp runs the same DMMA sequence (no divergence)
-  auto issue = [&](int step, int stage) {
-    const GemmEntry e = entries[it.ent0 + step / nkc];
-    const int kc = (step % nkc) * BK;
-    double *as = As + stage * A_STAGE, *bs = Bs + stage * B_STAGE;
-    if (A16) {
-#pragma unroll 4
-      for (int idx = tid; idx < MAXM * CPR; idx += NTHR) {
-        const int m = idx / CPR, ch = idx % CPR, k = kc + ch * 2;
-        int bytes = 0;
-        if (m < it.M && k < it.K) bytes = (k + 1 < it.K) ? 16 : 8;
-        const double *src = e.A + (int64_t)(m < it.M ? m : 0) * e.lda + (k < it.K ? k : 0);
-        cp_async16(as + m * LDA_S + ch * 2, src, bytes);
-      }
-    } else {
-#pragma unroll 4
-      for (int idx = tid; idx < MAXM * BK; idx += NTHR) {
-        const int m = idx / BK, kk = idx % BK, k = kc + kk;
-        const int bytes = (m < it.M && k < it.K) ? 8 : 0;
-        const double *src = e.A + (int64_t)(m < it.M ? m : 0) * e.lda + (k < it.K ? k : 0);
-        cp_async8(as + m * LDA_S + kk, src, bytes);
-      }
-    }
-#pragma unroll 4
-    for (int idx = tid; idx < BK * 32; idx += NTHR) {   // B tile: BK rows x 32 chunks of 16 bytes
-      const int kk = idx >> 5, ch = idx & 31, k = kc + kk;
-      const int bytes = (k < it.K) ? 16 : 0;
-      const double *src = e.B + (k < it.K ? it.browoff[k] : 0) + bn + ch * 2;
-      cp_async16(bs + kk * LDB_S + ch * 2, src, bytes);
-    }
-  };
-
-  if (nsteps > 0) issue(0, 0);
-  cp_async_commit();
+  int stage = 0, phase = 0;
   for (int step = 0; step < nsteps; step++) {
-    cp_async_wait<0>();
-    __syncthreads();   // stage (step&1) landed; everyone is done reading stage ((step+1)&1)
-    if (step + 1 < nsteps) issue(step + 1, (step + 1) & 1);
-    cp_async_commit();
-    const double *as = As + (step & 1) * A_STAGE + lr * LDA_S + lc, *bs = Bs + (step & 1) * B_STAGE + lc * LDB_S + lr;
-    // software-pipelined fragments: load k-step kk+4 while the DMMAs of kk issue
+    mbar_wait(full + stage, phase);
+    // A fragment of k-step ks sits at row*BK + lc + 4*(ks ^ lr)   (tperm_index swizzle)
+    const double *as = As + (size_t)stage * A_STAGE + (warp * 8 + lr) * BK + lc, *bs = Bs + stage * B_STAGE + lc * LDB_S + lr;
     double bf[2][8], af[2][MT];
 #pragma unroll
     for (int j = 0; j < 8; j++) bf[0][j] = bs[j * 8];
 #pragma unroll
-    for (int i = 0; i < MT; i++) af[0][i] = as[(warp + i * NW) * 8 * LDA_S];
+    for (int i = 0; i < MT; i++) af[0][i] = as[i * NW * 8 * BK + 4 * lr];
 #pragma unroll
     for (int ks = 0; ks < BK / 4; ks++) {
       const int cur = ks & 1, nxt = cur ^ 1;
       if (ks + 1 < BK / 4) {
+        const int ko = 4 * ((ks + 1) ^ lr);
 #pragma unroll
         for (int j = 0; j < 8; j++) bf[nxt][j] = bs[(ks + 1) * 4 * LDB_S + j * 8];
 #pragma unroll
-        for (int i = 0; i < MT; i++) af[nxt][i] = as[(warp + i * NW) * 8 * LDA_S + (ks + 1) * 4];
+        for (int i = 0; i < MT; i++) af[nxt][i] = as[i * NW * 8 * BK + ko];
       }
 #pragma unroll
       for (int i = 0; i < MT; i++)
 #pragma unroll
         for (int j = 0; j < 8; j++) dmma(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + stage);
+    if (++stage == NS) {
+      stage = 0;
+      phase ^= 1;
+    }
   }
-  cp_async_wait<0>();
 #pragma unroll
   for (int i = 0; i < MT; i++) {
     const int m = (warp + i * NW) * 8 + lr;
