@@ -64,6 +64,7 @@ struct Engine::Impl {
   int ns = 0, NP = 0, NB = 0, NT = 0, NL = 0, nab = 1, Npix = 0;
   bool parity = false;              // sector positions ordered by l-parity class (halves the fold)
   std::vector<int> sec_cls;
+  std::vector<int> sec_span;   // 1 + largest occupied position of a sector (= sec_n unless parity-ordered)
   std::vector<int> sec_m, sec_n, sec_ang, ang_sec, ang_pos, ang_off, ang_skip;
   std::vector<int> sec_lmin, sec_lmax;
   int mmin = 0, mmax = 0, nM = 0;   // M = m_a - m_b range: -(mmax-mmin) .. (mmax-mmin)
@@ -169,16 +170,18 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
       s.sec_m.push_back(kv.first.first);
       s.sec_cls.push_back(kv.first.second);
       s.sec_n.push_back((int)kv.second.size());
-      int lmn = 1 << 30, lmx = 0, cnt[2] = {0, 0};
+      int lmn = 1 << 30, lmx = 0, cnt[2] = {0, 0}, span = 0;
       for (size_t k = 0; k < kv.second.size(); k++) {
         const int a = kv.second[k], cls = t.lval[a] & 1;
         const int pos = s.parity ? cls * (s.NP / 2) + cnt[cls]++ : (int)k;
         s.sec_ang[(size_t)si * s.NP + pos] = a;
         s.ang_sec[a] = si;
         s.ang_pos[a] = pos;
+        span = std::max(span, pos + 1);
         lmn = std::min(lmn, t.lval[a]);
         lmx = std::max(lmx, t.lval[a]);
       }
+      s.sec_span.push_back(span);
       s.sec_lmin.push_back(lmn);
       s.sec_lmax.push_back(lmx);
       si++;
@@ -731,7 +734,7 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
             gi.C = acc_base + s.ep_off[(size_t)e * t.Nel + e];
             gi.browoff = s.d_browoff_T.p + s.browoff_T_first[e];
             gi.M = n * n;
-            gi.N = s.NB;
+            gi.N = s.sec_span[w.op / ns] * s.NP;   // columns (pos_j, pos_k) with pos_j past the sector are padding
             gi.K = s.nab * n * n;
             gi.ent0 = (int)gentries.size();
             for (size_t k = k0; k < k1; k++) {

@@ -647,9 +647,40 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 // release the stage through an "empty" mbarrier.  No CTA-wide barrier in the main loop, so the
 // FP64 tensor pipe is fed by whichever warps hold data while others wait.  Row tiles past M read
 // stale shared memory; they only feed accumulator rows >= M, which are never stored.  A columns
-// >= K are zero in the tiles and R rows past K come from a zero row.  Warp w owns row tiles
-// {w, w+8, w+16, w+24} x all 8 column tiles.  NS = stages that fit (3 for the 15-node elements).
+// >= K are zero in the tiles and R rows past K come from a zero row.  it.N (a multiple of 8) may be
+// smaller than the padded column count: column tiles past it are skipped.  NS = stages that fit
+// (3 for the 15-node elements).
 // ---------------------------------------------------------------------------
+// k-steps of one stage for one consumer warp of k_tgemm_ws: up to 8 row tiles x NCJ column tiles.
+// Fragments of k-step ks+1 are fetched while the DMMAs of ks issue.
+template <int NCJ>
+__device__ __forceinline__ void tgemm_ws_ksteps(double (&acc)[8][4][2], const double *__restrict__ as,
+                                                const double *__restrict__ bs, int nrt, int lr) {
+  constexpr int BK = TP_BK, LDB_S = 68;
+  double bf[2][NCJ], af[2][8];
+#pragma unroll
+  for (int j = 0; j < NCJ; j++) bf[0][j] = bs[j * 8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) af[0][i] = as[i * 32 * BK + 4 * lr];
+#pragma unroll
+  for (int ks = 0; ks < BK / 4; ks++) {
+    const int cur = ks & 1, nxt = cur ^ 1;
+    if (ks + 1 < BK / 4) {
+      const int ko = 4 * ((ks + 1) ^ lr);
+#pragma unroll
+      for (int j = 0; j < NCJ; j++) bf[nxt][j] = bs[(ks + 1) * 4 * LDB_S + j * 8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) af[nxt][i] = as[i * 32 * BK + ko];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+      if (i < nrt) {
+#pragma unroll
+        for (int j = 0; j < NCJ; j++) dmma(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
+      }
+  }
+}
+
 __host__ __device__ inline size_t tgemm_ws_smem(int M, int ns) {
   // ns stages of (A tile [M][TP_BK] + R tile [TP_BK][68]); slack so that the row tiles past M that
   // the last stage's warps still read stay inside the allocation; 2*ns mbarriers
@@ -659,7 +690,7 @@ __host__ __device__ inline size_t tgemm_ws_smem(int M, int ns) {
 static __global__ void __launch_bounds__(288, 1)
 k_tgemm_ws(const GemmItem *__restrict__ items, const GemmEntry *__restrict__ entries, const double *__restrict__ zrow,
            int NS, int maxM) {
-  constexpr int BK = TP_BK, BN = 64, NW = 8, MT = 4;
+  constexpr int BK = TP_BK, BN = 64, NW = 8, TG_MT = 8;   // row tiles per warp (M <= 256)
   constexpr int LDB_S = BN + 4, B_STAGE = BK * LDB_S;
   extern __shared__ double sm[];
   const GemmItem it = items[blockIdx.y];
@@ -667,6 +698,7 @@ k_tgemm_ws(const GemmItem *__restrict__ items, const GemmEntry *__restrict__ ent
   double *Bs = sm, *As = sm + NS * B_STAGE;
   uint64_t *full = reinterpret_cast<uint64_t *>(As + (size_t)NS * A_STAGE + (256 - maxM) * BK), *empty = full + NS;
   const int bn = blockIdx.x * BN;
+  if (bn >= it.N) return;   // column tile holds padding only
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nkc = (it.K + BK - 1) / BK;
   const int nsteps = (it.ent1 - it.ent0) * nkc;
@@ -709,37 +741,32 @@ k_tgemm_ws(const GemmItem *__restrict__ items, const GemmEntry *__restrict__ ent
   }
 
   // ---- consumers ----
+  // Work split: warp w owns column tiles 4*(w/4) .. +3 (8 columns each) and every 4th row tile
+  // starting at r0.  No DMMA is issued for row tiles past M or for column tiles past N.  The two
+  // warps that share a scheduler partition (w and w+4) start at row tiles that differ by 2, so with
+  // 29 row tiles (M = 225) the partitions carry 60/56/60/56 of the 232 units.
   const int lr = lane >> 2, lc = lane & 3;
-  double acc[MT][8][2];
+  const int cg = warp >> 2;
+  const int r0 = (warp + 2 * cg) & 3;
+  const int nrt = (((it.M + 7) >> 3) - r0 + 3) >> 2;   // row tiles of this warp
+  const int ncj = min(4, ((it.N - bn) >> 3) - 4 * cg);   // column tiles of this warp (<= 0: idle)
+  double acc[TG_MT][4][2];
 #pragma unroll
-  for (int i = 0; i < MT; i++)
+  for (int i = 0; i < TG_MT; i++)
 #pragma unroll
-    for (int j = 0; j < 8; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   int stage = 0, phase = 0;
   for (int step = 0; step < nsteps; step++) {
     mbar_wait(full + stage, phase);
-    // A fragment of k-step ks sits at row*BK + lc + 4*(ks ^ lr)   (tperm_index swizzle)
-    const double *as = As + (size_t)stage * A_STAGE + (warp * 8 + lr) * BK + lc, *bs = Bs + stage * B_STAGE + lc * LDB_S + lr;
-    double bf[2][8], af[2][MT];
-#pragma unroll
-    for (int j = 0; j < 8; j++) bf[0][j] = bs[j * 8];
-#pragma unroll
-    for (int i = 0; i < MT; i++) af[0][i] = as[i * NW * 8 * BK + 4 * lr];
-#pragma unroll
-    for (int ks = 0; ks < BK / 4; ks++) {
-      const int cur = ks & 1, nxt = cur ^ 1;
-      if (ks + 1 < BK / 4) {
-        const int ko = 4 * ((ks + 1) ^ lr);
-#pragma unroll
-        for (int j = 0; j < 8; j++) bf[nxt][j] = bs[(ks + 1) * 4 * LDB_S + j * 8];
-#pragma unroll
-        for (int i = 0; i < MT; i++) af[nxt][i] = as[i * NW * 8 * BK + ko];
-      }
-#pragma unroll
-      for (int i = 0; i < MT; i++)
-#pragma unroll
-        for (int j = 0; j < 8; j++) dmma(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
+    if (ncj > 0) {
+      // A fragment of k-step ks sits at row*BK + lc + 4*(ks ^ lr)   (tperm_index swizzle)
+      const double *as = As + (size_t)stage * A_STAGE + (r0 * 8 + lr) * BK + lc;
+      const double *bs = Bs + stage * B_STAGE + lc * LDB_S + cg * 32 + lr;
+      if (ncj > 2)
+        tgemm_ws_ksteps<4>(acc, as, bs, nrt, lr);
+      else
+        tgemm_ws_ksteps<2>(acc, as, bs, nrt, lr);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(empty + stage);
@@ -749,12 +776,13 @@ k_tgemm_ws(const GemmItem *__restrict__ items, const GemmEntry *__restrict__ ent
     }
   }
 #pragma unroll
-  for (int i = 0; i < MT; i++) {
-    const int m = (warp + i * NW) * 8 + lr;
+  for (int i = 0; i < TG_MT; i++) {
+    const int m = (r0 + 4 * i) * 8 + lr;
     if (m >= it.M) continue;
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-      double *c = it.C + (int64_t)m * it.ldc + bn + j * 8 + 2 * lc;
+    for (int j = 0; j < 4; j++) {
+      if (j >= ncj) break;
+      double *c = it.C + (int64_t)m * it.ldc + bn + cg * 32 + j * 8 + 2 * lc;
       double2 v;
       v.x = it.alpha * acc[i][j][0];
       v.y = it.alpha * acc[i][j][1];
