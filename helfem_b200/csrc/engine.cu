@@ -771,6 +771,7 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
               oi.ent0 = oe0;
               oi.ent1 = (int)oentries.size();
               oi.accumulate = acc;
+              oi.ncol = s.sec_span[w.op / ns] * s.NP;
               oitems.push_back(oi);
               const double per = 2.0 * t.nch * take *
                                  ((double)t.en[ei] * t.en[ej] * t.nch * t.en[ej] + (double)t.en[ei] * t.en[ej] * t.en[ei]);
@@ -820,7 +821,7 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
     CK(cudaEventRecord(s.ev[4], st));
     if (bt.noitems) {
       const dim3 grid(s.NB / 16, (unsigned)bt.noitems);
-      const size_t smem = (size_t)(t.nch * 16 * 16 * 20 + t.nch * 16 * 20 + 16 * (t.nch * 16 + 4)) * sizeof(double);
+      const size_t smem = (size_t)(t.nch * 16 * (16 * 20 + 4) + t.nch * 16 * 20 + 16 * (t.nch * 16 + 4)) * sizeof(double);
       if (t.nch == 1)
         dev::k_offdiag_mma<1><<<grid, 256, smem, st>>>(s.bd, bt.oitems.p, bt.oentries.p, s.d_R.p, s.d_small.p,
                                                     s.d_big.p, s.d_blk_off.p);

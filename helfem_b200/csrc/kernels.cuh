@@ -379,7 +379,7 @@ struct OffItem {
   int ei, ej;
   int ent0, ent1;   // entries: (R slot, channel)
   int accumulate;
-  int pad;
+  int ncol;         // blk columns >= ncol are padding (multiple of 16)
 };
 struct OffEntry {
   int rslot, ilm;
@@ -482,34 +482,54 @@ k_offdiag(BasisDev b, const OffItem *__restrict__ items, const OffEntry *__restr
 // straight from global memory into DMMA B fragments (every R element is used by
 // exactly one CTA), stage 2 keeps the 16x16x16 output tile of two rk values per
 // warp in registers across the whole entry loop.
-// Shared memory: U[NCH][16 rk][16 ri][LDU] + I[NCH][16][LDS] + J[NCH][16][LDJ]
+// Shared memory: U[NCH][16 rk][16 ri x LDU (+4)] + I[NCH][16][LDS] + J[NCH][16][LDJ]
 // ---------------------------------------------------------------------------
 template <int NCH>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 k_offdiag_mma(BasisDev b, const OffItem *__restrict__ items, const OffEntry *__restrict__ entries,
               const double *__restrict__ R, const double *__restrict__ dsmall, const double *__restrict__ dbig,
               const int64_t *__restrict__ blk_off) {
-  constexpr int BT = 16, LDU = BT + 4, LDI = 16 + 4, LDJ = NCH * 16 + 4, NAB = NCH * NCH;
+  constexpr int BT = 16, LDU = BT + 4, LDK = 16 * LDU + 4, LDI = 16 + 4, LDJ = NCH * 16 + 4, NAB = NCH * NCH;
+  constexpr int NCHUNK = 2 * NAB;   // chunks (ri slot, a, b) of one warp per entry
   extern __shared__ double sm[];
-  double *sU = sm;                          // [NCH][16 rk][16 ri][LDU]
-  double *sI = sU + NCH * 16 * 16 * LDU;    // [NCH][16 rj][LDI]
+  double *sU = sm;                          // [NCH][16 rk][LDK: 16 ri x LDU]
+  double *sI = sU + NCH * 16 * LDK;         // [NCH][16 rj][LDI]
   double *sJ = sI + NCH * 16 * LDI;         // J[rk][b*16 + rl]
   const OffItem it = items[blockIdx.y];
   const int Ni = b.en[it.ei], Nj = b.en[it.ej], fi = b.efirst[it.ei], fj = b.efirst[it.ej];
   const int blk0 = blockIdx.x * BT;
+  if (blk0 >= it.ncol) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lr = lane >> 2, lc = lane & 3;
   const int64_t gstride = (int64_t)b.NB;
-  for (int idx = tid; idx < NCH * 16 * 16 * LDU; idx += 256) sU[idx] = 0.0;
+  for (int idx = tid; idx < NCH * 16 * LDK; idx += 256) sU[idx] = 0.0;
   for (int idx = tid; idx < NCH * 16 * LDI; idx += 256) sI[idx] = 0.0;
   for (int idx = tid; idx < 16 * LDJ; idx += 256) sJ[idx] = 0.0;
   double kacc[2][2][2][2];   // [rk slot][rj tile][blk tile][frag]
 #pragma unroll
   for (int q = 0; q < 16; q++) (&kacc[0][0][0][0])[q] = 0.0;
 
+  // Stage-1 operand stream.  Chunk q = (slot, a, bb) of entry e is the 16 (rl) x 16 (blk) block
+  // R_ab(ri = warp + 8*slot, :)[blk0..+16).  A lane holds, for k-step ks, the two columns
+  // (2*lr, 2*lr+1) of row rl = 4*ks + lc as one 16-byte load: DMMA column tile nt therefore maps to
+  // the blk columns 2*n + nt.  The next chunk is fetched into registers while the current one
+  // feeds the tensor pipe (nothing else hides the HBM latency of this stream).
+  auto fetch = [&](int e, int q, double2 (&pf)[4]) {
+    const int slot = q / NAB, ab = q % NAB, ri = warp + 8 * slot;
+    const bool ok = e < it.ent1 && ri < Ni;
+    const double *row = R + ((int64_t)(ok ? entries[e].rslot : 0) * NAB * b.Npix + (int64_t)ab * b.Npix +
+                             (int64_t)(fi + (ok ? ri : 0)) * b.Nrad + fj) * gstride + blk0 + 2 * lr;
+#pragma unroll
+    for (int ks = 0; ks < 4; ks++) {
+      const int rl = ks * 4 + lc;
+      pf[ks] = (ok && rl < Nj) ? __ldg(reinterpret_cast<const double2 *>(row + (int64_t)rl * gstride)) : make_double2(0.0, 0.0);
+    }
+  };
+  double2 pf[4];
+  fetch(it.ent0, 0, pf);
+
   for (int e = it.ent0; e < it.ent1; e++) {
     const OffEntry en = entries[e];
-    const double *Rt = R + (int64_t)en.rslot * NAB * b.Npix * gstride + blk0;
     const double *srcI = (it.ei > it.ej ? dbig : dsmall) + blk_off[en.ilm * b.Nel + it.ei];
     const double *srcJ = (it.ei > it.ej ? dsmall : dbig) + blk_off[en.ilm * b.Nel + it.ej];
     __syncthreads();   // previous stage 2 finished with sI/sU
@@ -523,7 +543,9 @@ k_offdiag_mma(BasisDev b, const OffItem *__restrict__ items, const OffEntry *__r
     }
     __syncthreads();
     // ---- stage 1: warp -> ri = warp, warp + 8
-    for (int ri = warp; ri < Ni; ri += 8) {
+#pragma unroll
+    for (int slot = 0; slot < 2; slot++) {
+      const int ri = warp + 8 * slot;
 #pragma unroll
       for (int a = 0; a < NCH; a++) {
         double c[2][2][2];
@@ -531,31 +553,35 @@ k_offdiag_mma(BasisDev b, const OffItem *__restrict__ items, const OffEntry *__r
         for (int q = 0; q < 8; q++) (&c[0][0][0])[q] = 0.0;
 #pragma unroll
         for (int bb = 0; bb < NCH; bb++) {
-          const double *Rrow = Rt + ((int64_t)(a * NCH + bb) * b.Npix + (int64_t)(fi + ri) * b.Nrad + fj) * gstride;
+          double2 cur[4];
 #pragma unroll
-          for (int ks = 0; ks < 4; ks++) {
-            const int rl = ks * 4 + lc;
-            double bf0 = 0.0, bf1 = 0.0;
-            if (rl < Nj) {
-              const double *rp = Rrow + (int64_t)rl * gstride + lr;
-              bf0 = __ldg(rp);
-              bf1 = __ldg(rp + 8);
+          for (int ks = 0; ks < 4; ks++) cur[ks] = pf[ks];
+          const int q = (slot * NCH + a) * NCH + bb + 1;
+          if (q < NCHUNK)
+            fetch(e, q, pf);
+          else
+            fetch(e + 1, 0, pf);
+          if (ri < Ni) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ks++) {
+              const int rl = ks * 4 + lc;
+              const double a0 = sJ[lr * LDJ + bb * 16 + rl], a1 = sJ[(8 + lr) * LDJ + bb * 16 + rl];
+              dmma(c[0][0][0], c[0][0][1], a0, cur[ks].x);
+              dmma(c[0][1][0], c[0][1][1], a0, cur[ks].y);
+              dmma(c[1][0][0], c[1][0][1], a1, cur[ks].x);
+              dmma(c[1][1][0], c[1][1][1], a1, cur[ks].y);
             }
-            const double a0 = sJ[lr * LDJ + bb * 16 + rl], a1 = sJ[(8 + lr) * LDJ + bb * 16 + rl];
-            dmma(c[0][0][0], c[0][0][1], a0, bf0);
-            dmma(c[0][1][0], c[0][1][1], a0, bf1);
-            dmma(c[1][0][0], c[1][0][1], a1, bf0);
-            dmma(c[1][1][0], c[1][1][1], a1, bf1);
           }
         }
+        if (ri < Ni) {
+          // fragment (row lr, tile columns 2lc, 2lc+1 of tiles 0/1) = blk columns 4lc .. 4lc+3
 #pragma unroll
-        for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-          for (int nt = 0; nt < 2; nt++) {
-            double *u = sU + ((a * 16 + mt * 8 + lr) * 16 + ri) * LDU + nt * 8 + 2 * lc;
-            u[0] = c[mt][nt][0];
-            u[1] = c[mt][nt][1];
+          for (int mt = 0; mt < 2; mt++) {
+            double *u = sU + (a * 16 + mt * 8 + lr) * LDK + ri * LDU + 4 * lc;
+            *reinterpret_cast<double2 *>(u) = make_double2(c[mt][0][0], c[mt][1][0]);
+            *reinterpret_cast<double2 *>(u + 2) = make_double2(c[mt][0][1], c[mt][1][1]);
           }
+        }
       }
     }
     __syncthreads();
@@ -570,7 +596,7 @@ k_offdiag_mma(BasisDev b, const OffItem *__restrict__ items, const OffEntry *__r
         for (int ks = 0; ks < 4; ks++) {
           const int ri = ks * 4 + lc;
           const double a0 = sI[(a * 16 + lr) * LDI + ri], a1 = sI[(a * 16 + 8 + lr) * LDI + ri];
-          const double *u = sU + ((a * 16 + rk) * 16 + ri) * LDU + lr;
+          const double *u = sU + (a * 16 + rk) * LDK + ri * LDU + lr;
           const double bf0 = u[0], bf1 = u[8];
           dmma(kacc[slot][0][0][0], kacc[slot][0][0][1], a0, bf0);
           dmma(kacc[slot][0][1][0], kacc[slot][0][1][1], a0, bf1);
