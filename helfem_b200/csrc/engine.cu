@@ -426,6 +426,22 @@ template <int NT, int NCH, bool PAR>
 void launch_fold_t(const dev::BasisDev &bd, const dev::FoldTask *tasks, int ntasks, const double *G, const double *Ppix,
                    double *R, cudaStream_t st) {
   constexpr int NP = NT * 8, LD = NP + 4;
+  if constexpr (NT <= 2 && !PAR) {
+    // register-resident two-stage fold, one pixel per warp
+    constexpr int LDJ = (NP % 16 == 0) ? NP + 8 : NP + 16;
+    const size_t smem = (size_t)(NCH * NP * LD + NCH * NP * LDJ + 8 * 2 * NP * LD) * sizeof(double);
+    static bool attr_reg = false;
+    if (!attr_reg) {
+      CK(cudaFuncSetAttribute(dev::k_fold_reg<NT, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_reg = true;
+    }
+    int ppc = std::max(8, (int)(((int64_t)bd.Npix * ntasks + 148 * 8 - 1) / (148 * 8)));
+    ppc = round_up(std::min(std::min(ppc, 64), bd.Npix), 8);
+    const dim3 grid((bd.Npix + ppc - 1) / ppc, ntasks);
+    dev::k_fold_reg<NT, NCH><<<grid, 256, smem, st>>>(bd, tasks, G, Ppix, R, ppc);
+    CK(cudaGetLastError());
+    return;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     CK(cudaFuncSetAttribute(dev::k_fold<NT, NCH, PAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

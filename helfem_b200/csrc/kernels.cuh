@@ -205,6 +205,116 @@ k_fold(BasisDev b, const FoldTask *__restrict__ tasks, const double *__restrict_
 }
 
 // ---------------------------------------------------------------------------
+// Exchange fold for sectors of <= 16 functions (NT <= 2, no parity ordering): one warp = one pixel,
+// both contractions back to back in registers.
+//   stage 1: Yt_b[k][i] = sum_l Gk_b[k][l] P[i][l]        (accumulator fragments c1)
+//   stage 2: R_ab[j][k] = fac sum_i Gj_a[j][i] Yt_b[k][i]
+// A DMMA accumulator fragment holds Yt[row lr][cols 2lc, 2lc+1] and a B fragment wants
+// B[k = lc][n = lr]: the same row, so c1 IS the stage-2 B operand if the contraction index i is
+// visited in the order (8n + 2lc + f) instead of (4q + lc) -- only the A operand (Gj, read from shared
+// memory as one 16-byte load per two k-steps) has to follow that order.  No shared-memory round
+// trip for Yt, no CTA barrier in the pixel loop: every warp runs its own cp.async double buffer of
+// P tiles.  Shared memory: Gk[NCH][NP][NP+4], Gj[NCH][NP][LDJ], P[8 warps][2][NP][NP+4].
+// ---------------------------------------------------------------------------
+template <int NT, int NCH>
+__global__ void __launch_bounds__(256)
+k_fold_reg(BasisDev b, const FoldTask *__restrict__ tasks, const double *__restrict__ G, const double *__restrict__ Ppix,
+           double *__restrict__ R, int pix_per_cta) {
+  constexpr int NP = NT * 8, LDP = NP + 4, LDK = NP + 4, LDJ = (NP % 16 == 0) ? NP + 8 : NP + 16, NAB = NCH * NCH;
+  extern __shared__ double sm[];
+  double *sGk = sm, *sGj = sGk + NCH * NP * LDK, *sP = sGj + NCH * NP * LDJ;
+  const FoldTask t = tasks[blockIdx.y];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lr = lane >> 2, lc = lane & 3;
+  constexpr int64_t gstride = (int64_t)NP * NP;
+  const int pix0 = blockIdx.x * pix_per_cta;
+  const int pix1 = min(pix0 + pix_per_cta, b.Npix);
+  const double *Psrc = Ppix + (int64_t)t.spp * b.Npix * gstride;
+  double *Rdst = R + (int64_t)t.rslot * NAB * b.Npix * gstride;
+  double *myP = sP + warp * 2 * NP * LDP;
+  auto prefetch = [&](int pix, int buf) {
+    if (pix < pix1) {
+#pragma unroll
+      for (int idx = lane; idx < NP * (NP / 2); idx += 32) {
+        const int r = idx / (NP / 2), c2 = idx % (NP / 2);
+        cp_async16(myP + (buf * NP + r) * LDP + 2 * c2, Psrc + (int64_t)pix * gstride + r * NP + 2 * c2, 16);
+      }
+    }
+  };
+  prefetch(pix0 + warp, 0);
+  cp_async_commit();
+  {
+    const double *gj = G + ((int64_t)t.spj * b.NL + t.L) * NCH * gstride;
+    const double *gk = G + ((int64_t)t.spk * b.NL + t.L) * NCH * gstride;
+    for (int idx = tid; idx < NCH * NP * NP; idx += 256) {
+      const int ch = idx / (NP * NP), rem = idx % (NP * NP), r = rem / NP, c = rem % NP;
+      sGj[(ch * NP + r) * LDJ + c] = gj[idx];
+      sGk[(ch * NP + r) * LDK + c] = gk[idx];
+    }
+  }
+  __syncthreads();
+  int buf = 0;
+  for (int pix = pix0 + warp; pix < pix1; pix += 8, buf ^= 1) {
+    __syncwarp();   // every lane is done reading the buffer the next prefetch overwrites
+    prefetch(pix + 8, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncwarp();
+    const double *P = myP + buf * NP * LDP + lr * LDP + lc;
+    // ---- stage 1
+    double c1[NCH][NT][NT][2];
+#pragma unroll
+    for (int q = 0; q < NCH * NT * NT * 2; q++) (&c1[0][0][0][0])[q] = 0.0;
+#pragma unroll
+    for (int kk = 0; kk < NP; kk += 4) {
+      double bp[NT];
+#pragma unroll
+      for (int n = 0; n < NT; n++) bp[n] = P[n * 8 * LDP + kk];
+#pragma unroll
+      for (int bb = 0; bb < NCH; bb++)
+#pragma unroll
+        for (int rt = 0; rt < NT; rt++) {
+          const double a = sGk[(bb * NP + rt * 8 + lr) * LDK + lc + kk];
+#pragma unroll
+          for (int n = 0; n < NT; n++) dmma(c1[bb][rt][n][0], c1[bb][rt][n][1], a, bp[n]);
+        }
+    }
+    // ---- stage 2
+#pragma unroll
+    for (int aa = 0; aa < NCH; aa++) {
+      double2 ga[NT][NT];   // Gj_a[j = rtj*8 + lr][i = 8*ni + 2*lc + {0,1}]
+#pragma unroll
+      for (int rtj = 0; rtj < NT; rtj++)
+#pragma unroll
+        for (int ni = 0; ni < NT; ni++)
+          ga[rtj][ni] = *reinterpret_cast<const double2 *>(sGj + (aa * NP + rtj * 8 + lr) * LDJ + 8 * ni + 2 * lc);
+#pragma unroll
+      for (int bb = 0; bb < NCH; bb++) {
+        double c2[NT][NT][2];
+#pragma unroll
+        for (int q = 0; q < NT * NT * 2; q++) (&c2[0][0][0])[q] = 0.0;
+#pragma unroll
+        for (int ni = 0; ni < NT; ni++)
+#pragma unroll
+          for (int rtj = 0; rtj < NT; rtj++)
+#pragma unroll
+            for (int rtk = 0; rtk < NT; rtk++) {
+              dmma(c2[rtj][rtk][0], c2[rtj][rtk][1], ga[rtj][ni].x, c1[bb][rtk][ni][0]);
+              dmma(c2[rtj][rtk][0], c2[rtj][rtk][1], ga[rtj][ni].y, c1[bb][rtk][ni][1]);
+            }
+        double *out = Rdst + ((int64_t)(aa * NCH + bb) * b.Npix + pix) * gstride + lr * NP + 2 * lc;
+#pragma unroll
+        for (int rtj = 0; rtj < NT; rtj++)
+#pragma unroll
+          for (int rtk = 0; rtk < NT; rtk++)
+            *reinterpret_cast<double2 *>(out + rtj * 8 * NP + rtk * 8) =
+                make_double2(t.fac * c2[rtj][rtk][0], t.fac * c2[rtj][rtk][1]);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Multi-entry FP64 tensor-core GEMM:  C[M x N] (+)= alpha * sum_e A_e[M x K] B_e[K x N]
 //   A_e: row-major, row stride lda_e, K contiguous.
 //   B_e: KCONTIG = false: row k of B_e lives at B_e + browoff[k], N contiguous
