@@ -208,7 +208,7 @@ k_fold(BasisDev b, const FoldTask *__restrict__ tasks, const double *__restrict_
 // Exchange fold for sectors of <= 16 functions (NT <= 2, no parity ordering): one warp = one pixel,
 // both contractions back to back in registers.
 //   stage 1: Yt_b[k][i] = sum_l Gk_b[k][l] P[i][l]        (accumulator fragments c1)
-//   stage 2: R_ab[j][k] = fac sum_i Gj_a[j][i] Yt_b[k][i]
+//   stage 2: R_ab[j][k] = sum_i (fac Gj_a[j][i]) Yt_b[k][i]
 // A DMMA accumulator fragment holds Yt[row lr][cols 2lc, 2lc+1] and a B fragment wants
 // B[k = lc][n = lr]: the same row, so c1 IS the stage-2 B operand if the contraction index i is
 // visited in the order (8n + 2lc + f) instead of (4q + lc) -- only the A operand (Gj, read from shared
@@ -248,7 +248,7 @@ k_fold_reg(BasisDev b, const FoldTask *__restrict__ tasks, const double *__restr
     const double *gk = G + ((int64_t)t.spk * b.NL + t.L) * NCH * gstride;
     for (int idx = tid; idx < NCH * NP * NP; idx += 256) {
       const int ch = idx / (NP * NP), rem = idx % (NP * NP), r = rem / NP, c = rem % NP;
-      sGj[(ch * NP + r) * LDJ + c] = gj[idx];
+      sGj[(ch * NP + r) * LDJ + c] = t.fac * gj[idx];   // prefactor folded into the table (no DMUL per output)
       sGk[(ch * NP + r) * LDK + c] = gk[idx];
     }
   }
@@ -308,7 +308,7 @@ k_fold_reg(BasisDev b, const FoldTask *__restrict__ tasks, const double *__restr
 #pragma unroll
           for (int rtk = 0; rtk < NT; rtk++)
             *reinterpret_cast<double2 *>(out + rtj * 8 * NP + rtk * 8) =
-                make_double2(t.fac * c2[rtj][rtk][0], t.fac * c2[rtj][rtk][1]);
+                make_double2(c2[rtj][rtk][0], c2[rtj][rtk][1]);
       }
     }
   }
@@ -787,17 +787,18 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 // smaller than the padded column count: column tiles past it are skipped.  NS = stages that fit
 // (3 for the 15-node elements).
 // ---------------------------------------------------------------------------
-// k-steps of one stage for one consumer warp of k_tgemm_ws: up to 8 row tiles x NCJ column tiles.
-// Fragments of k-step ks+1 are fetched while the DMMAs of ks issue.
-template <int NCJ>
+// k-steps of one stage for one consumer warp of k_tgemm_ws: NRT row tiles x NCJ column tiles.
+// Fragments of k-step ks+1 are fetched while the DMMAs of ks issue.  The tile counts are template
+// parameters because a predicated-off DMMA still occupies the tensor pipe (measured: ncu r01d).
+template <int NCJ, int NRT>
 __device__ __forceinline__ void tgemm_ws_ksteps(double (&acc)[8][4][2], const double *__restrict__ as,
-                                                const double *__restrict__ bs, int nrt, int lr) {
+                                                const double *__restrict__ bs, int lr) {
   constexpr int BK = TP_BK, LDB_S = 68;
-  double bf[2][NCJ], af[2][8];
+  double bf[2][NCJ], af[2][NRT];
 #pragma unroll
   for (int j = 0; j < NCJ; j++) bf[0][j] = bs[j * 8];
 #pragma unroll
-  for (int i = 0; i < 8; i++) af[0][i] = as[i * 32 * BK + 4 * lr];
+  for (int i = 0; i < NRT; i++) af[0][i] = as[i * 32 * BK + 4 * lr];
 #pragma unroll
   for (int ks = 0; ks < BK / 4; ks++) {
     const int cur = ks & 1, nxt = cur ^ 1;
@@ -806,14 +807,28 @@ __device__ __forceinline__ void tgemm_ws_ksteps(double (&acc)[8][4][2], const do
 #pragma unroll
       for (int j = 0; j < NCJ; j++) bf[nxt][j] = bs[(ks + 1) * 4 * LDB_S + j * 8];
 #pragma unroll
-      for (int i = 0; i < 8; i++) af[nxt][i] = as[i * 32 * BK + ko];
+      for (int i = 0; i < NRT; i++) af[nxt][i] = as[i * 32 * BK + ko];
     }
 #pragma unroll
-    for (int i = 0; i < 8; i++)
-      if (i < nrt) {
+    for (int i = 0; i < NRT; i++)
 #pragma unroll
-        for (int j = 0; j < NCJ; j++) dmma(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
-      }
+      for (int j = 0; j < NCJ; j++) dmma(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
+  }
+}
+
+template <int NCJ>
+__device__ __forceinline__ void tgemm_ws_rows(double (&acc)[8][4][2], const double *__restrict__ as,
+                                              const double *__restrict__ bs, int nrt, int lr) {
+  switch (nrt) {
+    case 8: tgemm_ws_ksteps<NCJ, 8>(acc, as, bs, lr); break;
+    case 7: tgemm_ws_ksteps<NCJ, 7>(acc, as, bs, lr); break;
+    case 6: tgemm_ws_ksteps<NCJ, 6>(acc, as, bs, lr); break;
+    case 5: tgemm_ws_ksteps<NCJ, 5>(acc, as, bs, lr); break;
+    case 4: tgemm_ws_ksteps<NCJ, 4>(acc, as, bs, lr); break;
+    case 3: tgemm_ws_ksteps<NCJ, 3>(acc, as, bs, lr); break;
+    case 2: tgemm_ws_ksteps<NCJ, 2>(acc, as, bs, lr); break;
+    case 1: tgemm_ws_ksteps<NCJ, 1>(acc, as, bs, lr); break;
+    default: break;
   }
 }
 
@@ -900,9 +915,9 @@ k_tgemm_ws(const GemmItem *__restrict__ items, const GemmEntry *__restrict__ ent
       const double *as = As + (size_t)stage * A_STAGE + (r0 * 8 + lr) * BK + lc;
       const double *bs = Bs + stage * B_STAGE + lc * LDB_S + cg * 32 + lr;
       if (ncj > 2)
-        tgemm_ws_ksteps<4>(acc, as, bs, nrt, lr);
+        tgemm_ws_rows<4>(acc, as, bs, nrt, lr);
       else
-        tgemm_ws_ksteps<2>(acc, as, bs, nrt, lr);
+        tgemm_ws_rows<2>(acc, as, bs, nrt, lr);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(empty + stage);
