@@ -266,7 +266,7 @@ class _BasisBase:
         ctx = self._context()
         n = self.Nbf()
         Pf = _fmat(P, n)
-        J = np.empty((n, n), order="F")
+        J = np.full((n, n), np.nan, order="F")   # every element must be defined by the call
         _check(lib().hfq_coulomb(ctx, Pf.ctypes.data, n, J.ctypes.data, n))
         return J
 
@@ -274,7 +274,7 @@ class _BasisBase:
         ctx = self._context()
         n = self.Nbf()
         Pf = _fmat(P, n)
-        K = np.empty((n, n), order="F")
+        K = np.full((n, n), np.nan, order="F")   # every element must be defined by the call
         _check(lib().hfq_exchange(ctx, Pf.ctypes.data, n, K.ctypes.data, n))
         return K
 
@@ -283,8 +283,8 @@ class _BasisBase:
         ctx = self._context()
         n = self.Nbf()
         Pf = _fmat(P, n)
-        J = np.empty((n, n), order="F")
-        K = np.empty((n, n), order="F")
+        J = np.full((n, n), np.nan, order="F")   # every element must be defined by the call
+        K = np.full((n, n), np.nan, order="F")   # every element must be defined by the call
         _check(lib().hfq_coulomb_exchange(ctx, Pf.ctypes.data, n, kscale, J.ctypes.data, n, K.ctypes.data, n))
         return J, K
 
@@ -313,11 +313,11 @@ class _BasisBase:
         return bs, [(int(pr[2 * i]), int(pr[2 * i + 1])) for i in range(k)]
 
     def last_timings(self):
-        out = np.zeros(17)
-        _check(lib().hfq_last_timings(self._context(), out.ctypes.data, 17))
+        out = np.zeros(19)
+        _check(lib().hfq_last_timings(self._context(), out.ctypes.data, 19))
         keys = ["ms_pack", "ms_fold", "ms_tgemm", "ms_offdiag", "ms_unpack", "ms_total", "flops_fold", "flops_tgemm",
                 "flops_offdiag", "launches", "device_bytes", "alg_fold", "alg_tgemm", "alg_offdiag",
-                "launches_fold", "launches_tgemm", "launches_offdiag"]
+                "launches_fold", "launches_tgemm", "launches_offdiag", "h2d_bytes", "d2h_bytes"]
         return dict(zip(keys, out))
 
     # -- helpers ---------------------------------------------------------------

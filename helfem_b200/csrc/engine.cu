@@ -9,6 +9,7 @@
 #include <map>
 #include <numeric>
 #include <stdexcept>
+#include <thread>
 
 #include "kernels.cuh"
 #include "special.h"
@@ -816,6 +817,9 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
     plans_->plans.push_back(std::move(np));
     plan = plans_->plans.back().get();
   }
+  // which dense blocks of K can be non-zero (for compact collectives and host copies)
+  last_active_ops_.assign(plan->op_src.begin(), plan->op_src.end());
+  if (plan_hook_) plan_hook_();
   // ---------------- run the plan ----------------
   const int S = plan->S;
   if (S > 1)
@@ -881,8 +885,6 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
   tm_.alg_tgemm = plan->al_tg;
   tm_.alg_offdiag = plan->al_off;
   tm_.launches += 3;
-  // which dense blocks of K can be non-zero (for compact collectives): angular pairs (j,k)
-  last_active_ops_.assign(plan->op_src.begin(), plan->op_src.end());
 }
 
 const BasisTables &Engine::tables() const { return p_->t; }
@@ -1039,6 +1041,75 @@ void Engine::coulomb_dev(const double *dP, int64_t ldP, double *dJ, int64_t ldJ,
 // ---------------------------------------------------------------------------
 // host-pointer wrappers
 // ---------------------------------------------------------------------------
+Engine::HostRanges Engine::host_ranges(bool coulomb) const {
+  std::vector<int> bfsec, pairs;
+  output_pattern(bfsec, pairs, coulomb);
+  const int n = nbf_, ns = p_->ns;
+  std::vector<int> smin(ns, n), smax(ns, -1);
+  for (int i = 0; i < n; i++) {
+    smin[bfsec[i]] = std::min(smin[bfsec[i]], i);
+    smax[bfsec[i]] = std::max(smax[bfsec[i]], i);
+  }
+  // bounding row range of the active row sectors of every column sector
+  std::vector<int> cmin(ns, n), cmax(ns, 0);
+  for (size_t k = 0; k + 1 < pairs.size(); k += 2) {
+    const int sr = pairs[k], sc = pairs[k + 1];
+    if (smax[sr] < 0) continue;
+    cmin[sc] = std::min(cmin[sc], smin[sr]);
+    cmax[sc] = std::max(cmax[sc], smax[sr] + 1);
+  }
+  HostRanges hr;
+  hr.r0.resize(n);
+  hr.r1.resize(n);
+  for (int c = 0; c < n; c++) {
+    const int sc = bfsec[c];
+    hr.r0[c] = cmin[sc] < cmax[sc] ? cmin[sc] : 0;
+    hr.r1[c] = cmin[sc] < cmax[sc] ? cmax[sc] : 0;
+  }
+  return hr;
+}
+
+double Engine::copy_ranges_async(double *H, int64_t ldH, const double *D, const HostRanges &hr, cudaStream_t st) const {
+  const int n = nbf_;
+  double bytes = 0.0;
+  if ((int)hr.r0.size() != n) return 0.0;
+  for (int c0 = 0; c0 < n;) {
+    int c1 = c0 + 1;
+    while (c1 < n && hr.r0[c1] == hr.r0[c0] && hr.r1[c1] == hr.r1[c0]) c1++;
+    const int r0 = hr.r0[c0], r1 = hr.r1[c0];
+    bytes += (double)(r1 - r0) * (c1 - c0) * sizeof(double);
+    if (r1 > r0)
+      CK(cudaMemcpy2DAsync(H + (int64_t)c0 * ldH + r0, ldH * sizeof(double), D + (int64_t)c0 * n + r0, (size_t)n * sizeof(double),
+                           (size_t)(r1 - r0) * sizeof(double), (size_t)(c1 - c0), cudaMemcpyDeviceToHost, st));
+    c0 = c1;
+  }
+  return bytes;
+}
+
+void Engine::zero_outside(double *H, int64_t ldH, int n, const HostRanges &hr) {
+  const bool none = (int)hr.r0.size() != n;   // no pattern: everything is zero
+#pragma omp parallel for schedule(static)
+  for (int c = 0; c < n; c++) {
+    double *col = H + (int64_t)c * ldH;
+    if (none) {
+      std::memset(col, 0, (size_t)n * sizeof(double));
+      continue;
+    }
+    if (hr.r0[c] > 0) std::memset(col, 0, (size_t)hr.r0[c] * sizeof(double));
+    if (hr.r1[c] < n) std::memset(col + hr.r1[c], 0, (size_t)(n - hr.r1[c]) * sizeof(double));
+  }
+}
+
+namespace {
+// joins on scope exit so that an exception cannot leave a worker writing into the caller's buffer
+struct Joiner {
+  std::thread t;
+  ~Joiner() {
+    if (t.joinable()) t.join();
+  }
+};
+}  // namespace
+
 void Engine::coulomb(const double *P, int64_t ldP, double *J, int64_t ldJ) {
   Impl &s = *p_;
   CK(cudaSetDevice(device_));
@@ -1048,8 +1119,10 @@ void Engine::coulomb(const double *P, int64_t ldP, double *J, int64_t ldJ) {
   CK(cudaMemcpy2DAsync(s.d_P.p, n * sizeof(double), P, ldP * sizeof(double), n * sizeof(double), n,
                        cudaMemcpyHostToDevice, stream_));
   coulomb_dev(s.d_P.p, (int64_t)n, s.d_O.p, (int64_t)n, 0, 1, stream_);
-  CK(cudaMemcpy2DAsync(J, ldJ * sizeof(double), s.d_O.p, n * sizeof(double), n * sizeof(double), n,
-                       cudaMemcpyDeviceToHost, stream_));
+  const HostRanges hr = host_ranges(true);
+  tm_.h2d_bytes = (double)n * n * sizeof(double);
+  tm_.d2h_bytes = copy_ranges_async(J, ldJ, s.d_O.p, hr, stream_);
+  zero_outside(J, ldJ, nbf_, hr);
   CK(cudaStreamSynchronize(stream_));
 }
 
@@ -1061,14 +1134,27 @@ void Engine::exchange(const double *P, int64_t ldP, double *K, int64_t ldK) {
   if (s.d_O.n < n * n) s.d_O.alloc(n * n, &dev_bytes_);
   CK(cudaMemcpy2DAsync(s.d_P.p, n * sizeof(double), P, ldP * sizeof(double), n * sizeof(double), n,
                        cudaMemcpyHostToDevice, stream_));
-  exchange_dev(s.d_P.p, (int64_t)n, s.d_O.p, (int64_t)n, 0, 1, stream_);
-  CK(cudaMemcpy2DAsync(K, ldK * sizeof(double), s.d_O.p, n * sizeof(double), n * sizeof(double), n,
-                       cudaMemcpyDeviceToHost, stream_));
+  HostRanges hr;
+  Joiner zero;
+  plan_hook_ = [&]() {
+    hr = host_ranges(false);
+    zero.t = std::thread([&]() { zero_outside(K, ldK, nbf_, hr); });
+  };
+  try {
+    exchange_dev(s.d_P.p, (int64_t)n, s.d_O.p, (int64_t)n, 0, 1, stream_);
+  } catch (...) {
+    plan_hook_ = nullptr;
+    throw;
+  }
+  plan_hook_ = nullptr;
+  tm_.h2d_bytes = (double)n * n * sizeof(double);
+  tm_.d2h_bytes = copy_ranges_async(K, ldK, s.d_O.p, hr, stream_);
   CK(cudaStreamSynchronize(stream_));
 }
 
-// Fused host entry point: one upload of P, J is copied back on a second stream while the exchange
-// kernels run, then K.
+// Fused host entry point: one upload of P; the non-zero row ranges of J are copied back on a second
+// stream while the exchange kernels run, then those of K; host threads zero-fill the rest of both
+// result matrices in the meantime.
 void Engine::coulomb_exchange(const double *P, int64_t ldP, double kscale, double *J, int64_t ldJ, double *K,
                               int64_t ldK) {
   Impl &s = *p_;
@@ -1086,25 +1172,37 @@ void Engine::coulomb_exchange(const double *P, int64_t ldP, double kscale, doubl
                        cudaMemcpyHostToDevice, stream_));
   pack_density(s.d_P.p, (int64_t)n, stream_);
   s.packed_valid = true;
+  HostRanges hrj, hrk;
+  double jbytes = 0.0;
+  Joiner zero;
   try {
     coulomb_dev(s.d_P.p, (int64_t)n, s.d_O2.p, (int64_t)n, 0, 1, stream_);
     const EngineTimings tj = tm_;
     // J is complete (coulomb_dev synchronises): copy it out while K is being built
-    CK(cudaMemcpy2DAsync(J, ldJ * sizeof(double), s.d_O2.p, n * sizeof(double), n * sizeof(double), n,
-                         cudaMemcpyDeviceToHost, s.copy_stream));
+    hrj = host_ranges(true);
+    jbytes = copy_ranges_async(J, ldJ, s.d_O2.p, hrj, s.copy_stream);
     s.kscale = kscale;
+    plan_hook_ = [&]() {
+      hrk = host_ranges(false);
+      zero.t = std::thread([&]() {
+        zero_outside(J, ldJ, nbf_, hrj);
+        zero_outside(K, ldK, nbf_, hrk);
+      });
+    };
     exchange_dev(s.d_P.p, (int64_t)n, s.d_O.p, (int64_t)n, 0, 1, stream_);
     tm_.launches += tj.launches;
     tm_.total += tj.total;
   } catch (...) {
+    plan_hook_ = nullptr;
     s.packed_valid = false;
     s.kscale = 1.0;
     throw;
   }
+  plan_hook_ = nullptr;
   s.packed_valid = false;
   s.kscale = 1.0;
-  CK(cudaMemcpy2DAsync(K, ldK * sizeof(double), s.d_O.p, n * sizeof(double), n * sizeof(double), n,
-                       cudaMemcpyDeviceToHost, stream_));
+  tm_.h2d_bytes = (double)n * n * sizeof(double);
+  tm_.d2h_bytes = jbytes + copy_ranges_async(K, ldK, s.d_O.p, hrk, stream_);
   CK(cudaStreamSynchronize(stream_));
   CK(cudaStreamSynchronize(s.copy_stream));
 }

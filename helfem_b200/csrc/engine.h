@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <functional>
 #include <memory>
 #include <string>
 #include <vector>
@@ -26,6 +27,7 @@ struct EngineTimings {      // milliseconds of the last call, CUDA events
   double alg_fold = 0, alg_tgemm = 0, alg_offdiag = 0;        // algorithmic (unpadded) flops, DESIGN.md
   int launches = 0;           // kernel launches of the call
   int launches_fold = 0, launches_tgemm = 0, launches_offdiag = 0;
+  double h2d_bytes = 0, d2h_bytes = 0;   // host-pointer entry points: bytes moved over PCIe by the call
 };
 
 class Engine {
@@ -67,6 +69,16 @@ class Engine {
 
  private:
   void pack_density(const double *dP, int64_t ldP, cudaStream_t stream);
+  // Host-pointer results: only the bounding row range of the blocks that can be non-zero is copied
+  // back per column (grouped into rectangles); the rest of the caller's matrix is zero-filled by
+  // host threads while the GPU is still computing.
+  struct HostRanges {
+    std::vector<int> r0, r1;   // per dense column: rows [r0, r1) are copied, the rest is zero
+  };
+  HostRanges host_ranges(bool coulomb) const;
+  double copy_ranges_async(double *H, int64_t ldH, const double *D, const HostRanges &hr, cudaStream_t st) const;   // returns bytes
+  static void zero_outside(double *H, int64_t ldH, int n, const HostRanges &hr);
+  std::function<void()> plan_hook_;   // called by exchange_dev once the output pattern is known
   struct Impl;
   struct PlanCache;
   std::unique_ptr<Impl> p_;

@@ -180,7 +180,9 @@ int hfq_coulomb_output_pattern(const hfq_ctx *ctx, int *bf_sector, int64_t cap_b
  * out[0..5] = ms {pack, fold, in-element GEMM, cross-element, unpack, total},
  * out[6..8] = executed flops {fold, in-element GEMM, cross-element}, out[9] = kernel launches,
  * out[10] = device bytes held by the context, out[11..13] = algorithmic (unpadded) flops
- * {fold, in-element GEMM, cross-element}, out[14..16] = launches of those three kernels. */
+ * {fold, in-element GEMM, cross-element}, out[14..16] = launches of those three kernels,
+ * out[17..18] = bytes copied host->device / device->host by the last host-pointer call (the
+ * result copies skip the rows outside the non-zero blocks; those are zero-filled on the host). */
 int hfq_last_timings(const hfq_ctx *ctx, double *out, int n);
 
 #ifdef __cplusplus
