@@ -78,13 +78,15 @@ struct Engine::Impl {
   std::vector<int64_t> ep_off;
   int64_t op_stride = 0;
   std::vector<int64_t> tperm_off;   // [nlm * Nel] offset of the tiled in-element kernel A_(ilm,e)
+  std::vector<int64_t> tperm_tri_off;   // the same for the rows rj <= rk only (symmetric densities)
+  bool p_symmetric = false;   // set by pack_density: P == P^T to 1e-14 of its largest element
   // device
   DevBuf<int> d_ang_off, d_ang_skip, d_sec_n, d_sec_ang, d_efirst, d_en, d_ang_sec, d_ang_pos, d_rad_e0, d_rad_e1;
-  int tg_stages = 2, tg_maxM = 0;
-  size_t tg_smem = 0;
-  DevBuf<double> d_G, d_small, d_big, d_B, d_sigma, d_tperm, d_zrow;
+  int tg_maxM = 0;
+  double tri_pix_frac = 1.0;   // share of the pixels (ri, rl) with el(ri) <= el(rl)
+  DevBuf<double> d_G, d_small, d_big, d_B, d_sigma, d_tperm, d_tperm_tri, d_zrow;
   DevBuf<int64_t> d_blk_off, d_B_off, d_sig_off, d_ep_off;
-  DevBuf<int> d_rank, d_chan_of, d_browoff_T, d_browoff_G, d_splist, d_op_src, d_sp_active;
+  DevBuf<int> d_rank, d_chan_of, d_browoff_T, d_browoff_G, d_splist, d_op_src, d_op_tri, d_sp_active;
   DevBuf<double> d_jfac, d_norms, d_Ppix, d_R, d_Kacc, d_Paux, d_JauxT, d_Jsec, d_P, d_O, d_O2;
   DevBuf<dev::FoldTask> d_tasks;
   DevBuf<dev::GemmItem> d_gitems;
@@ -321,6 +323,10 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
       }
     s.d_rad_e0.upload(e0, &dev_bytes_);
     s.d_rad_e1.upload(e1, &dev_bytes_);
+    int64_t keep = 0;
+    for (int r = 0; r < t.Nrad; r++)
+      for (int c = 0; c < t.Nrad; c++) keep += e0[r] <= e1[c];
+    s.tri_pix_frac = (double)keep / ((double)t.Nrad * t.Nrad);
   }
   s.bd = dev::BasisDev{na, t.Nrad, s.Npix, s.NP, s.NB, s.ns, t.nch, s.nab, t.Nel, s.NL,
                        s.d_ang_off.p, s.d_ang_skip.p, s.d_sec_n.p, s.d_sec_ang.p, s.d_efirst.p, s.d_en.p,
@@ -339,24 +345,26 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
   s.d_ep_off.upload(s.ep_off, &dev_bytes_);
   // ---- dense exchange-ordered in-element kernels, one per (multipole channel, element), stored as
   //      the pre-swizzled k-chunk tiles k_tgemm_ws bulk-copies (kernels.cuh: tperm_index)
-  {
-    s.tperm_off.assign((size_t)nlm * t.Nel, 0);
+  for (int tri = 0; tri < 2; tri++) {
+    std::vector<int64_t> &offs = tri ? s.tperm_tri_off : s.tperm_off;
+    DevBuf<double> &buf = tri ? s.d_tperm_tri : s.d_tperm;
+    offs.assign((size_t)nlm * t.Nel, 0);
     int64_t off = 0;
     for (int ilm = 0; ilm < nlm; ilm++)
       for (int e = 0; e < t.Nel; e++) {
-        const int nn = t.en[e] * t.en[e];
-        s.tperm_off[(size_t)ilm * t.Nel + e] = off;
-        off += dev::tperm_doubles(nn, s.nab * nn);
+        const int n = t.en[e], rows = tri ? n * (n + 1) / 2 : n * n;
+        offs[(size_t)ilm * t.Nel + e] = off;
+        off += dev::tperm_doubles(rows, s.nab * n * n);
       }
-    s.d_tperm.alloc((size_t)off, &dev_bytes_);
-    CK(cudaMemsetAsync(s.d_tperm.p, 0, (size_t)off * sizeof(double), stream_));
+    buf.alloc((size_t)off, &dev_bytes_);
+    CK(cudaMemsetAsync(buf.p, 0, (size_t)off * sizeof(double), stream_));
     for (int ilm = 0; ilm < nlm; ilm++)
       for (int e = 0; e < t.Nel; e++) {
-        const int n = t.en[e];
-        dev::k_build_tperm<<<n * n, 256, 0, stream_>>>(
+        const int n = t.en[e], rows = tri ? n * (n + 1) / 2 : n * n;
+        dev::k_build_tperm<<<rows, 256, 0, stream_>>>(
             s.d_B.p + s.B_off[(size_t)ilm * t.Nel + e], s.d_sigma.p + s.sig_off[(size_t)ilm * t.Nel + e], n,
-            s.ranks[(size_t)ilm * t.Nel + e], t.nch, t.kind == BasisKind::Atomic ? 1 : 0,
-            s.d_tperm.p + s.tperm_off[(size_t)ilm * t.Nel + e]);
+            s.ranks[(size_t)ilm * t.Nel + e], t.nch, t.kind == BasisKind::Atomic ? 1 : 0, tri,
+            buf.p + offs[(size_t)ilm * t.Nel + e]);
       }
     CK(cudaGetLastError());
   }
@@ -398,24 +406,21 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
     s.d_jfac.upload(jfac, &dev_bytes_);
   }
   // ---- work buffers that do not depend on the density
-  s.d_norms.alloc((size_t)na * na, &dev_bytes_);
+  s.d_norms.alloc((size_t)3 * na * na, &dev_bytes_);
   s.d_Ppix.alloc((size_t)s.ns * s.ns * s.Npix * s.NB, &dev_bytes_);
   s.d_splist.alloc((size_t)s.ns * s.ns, &dev_bytes_);
   s.d_op_src.alloc((size_t)s.ns * s.ns, &dev_bytes_);
+  s.d_op_tri.alloc((size_t)s.ns * s.ns, &dev_bytes_);
   s.d_sp_active.alloc((size_t)s.ns * s.ns, &dev_bytes_);
   CK(cudaStreamSynchronize(stream_));
   // opt-in shared memory sizes
   CK(cudaFuncSetAttribute(dev::k_offdiag_mma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
   CK(cudaFuncSetAttribute(dev::k_offdiag_mma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
   {
-    // stages of the in-element GEMM ring: as many as fit in the 227 KB of shared memory, at most 4
     s.tg_maxM = 0;
     for (int e = 0; e < t.Nel; e++) s.tg_maxM = std::max(s.tg_maxM, t.en[e] * t.en[e]);
     if (s.tg_maxM > 256) throw std::runtime_error("elements with more than 16 radial functions are not supported");
-    s.tg_stages = 4;
-    while (s.tg_stages > 2 && dev::tgemm_ws_smem(s.tg_maxM, s.tg_stages) > 227 * 1024) s.tg_stages--;
-    s.tg_smem = dev::tgemm_ws_smem(s.tg_maxM, s.tg_stages);
-    CK(cudaFuncSetAttribute(dev::k_tgemm_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.tg_smem));
+    CK(cudaFuncSetAttribute(dev::k_tgemm_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   }
   s.d_zrow.upload(std::vector<double>(64, 0.0), &dev_bytes_);
 }
@@ -511,9 +516,20 @@ void Engine::pack_density(const double *dP, int64_t ldP, cudaStream_t st) {
   const int na = t.Nang(), ns = s.ns;
   dev::k_block_norms<<<dim3(na, na), 128, 0, st>>>(s.bd, dP, ldP, s.d_norms.p);
   CK(cudaGetLastError());
-  s.norms_host.resize((size_t)na * na);
+  s.norms_host.resize((size_t)3 * na * na);
   CK(cudaMemcpyAsync(s.norms_host.data(), s.d_norms.p, s.norms_host.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  {
+    // symmetric density (every SCF density is): the exchange builds half of each diagonal output pair
+    double asym = 0.0, amax = 0.0;
+    const size_t nn = (size_t)na * na;
+    for (size_t k = 0; k < nn; k++) {
+      asym = std::max(asym, s.norms_host[nn + k]);
+      amax = std::max(amax, s.norms_host[2 * nn + k]);
+    }
+    static const bool allow = !(getenv("HFQ_NO_SYMMETRY") && atoi(getenv("HFQ_NO_SYMMETRY")));
+    s.p_symmetric = allow && asym <= 1e-14 * amax;
+  }
   std::vector<char> sp_nz((size_t)ns * ns, 0);
   for (int a = 0; a < na; a++)
     for (int b = 0; b < na; b++)
@@ -568,8 +584,8 @@ struct ExchangeBatch {
 struct ExchangePlan {
   std::string key;
   std::vector<std::unique_ptr<ExchangeBatch>> batches;
-  std::vector<int> splist, op_src;
-  int nactive = 0, S = 1;
+  std::vector<int> splist, op_src, op_tri;
+  int nactive = 0, S = 1, maxM = 8;
   double fl_fold = 0, fl_tg = 0, fl_off = 0, al_fold = 0, al_tg = 0, al_off = 0;
   const double *R_base = nullptr, *K_base = nullptr;   // buffers the descriptors point into
 };
@@ -595,7 +611,7 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
   for (int a = 0; a < na; a++)
     for (int b = 0; b < na; b++)
       if (norms[(size_t)a * na + b] >= thr2) key[(size_t)s.ang_sec[a] * ns + s.ang_sec[b]] = '1';
-  key[(size_t)ns * ns] = absm_symmetric_ ? 'S' : 'N';
+  key[(size_t)ns * ns] = (char)((absm_symmetric_ ? 'S' : 'N') + (s.p_symmetric ? 1 : 0));
   key[(size_t)ns * ns + 1] = (char)('0' + shard);
   key[(size_t)ns * ns + 2] = (char)('0' + nshards);
   ExchangePlan *plan = nullptr;
@@ -612,6 +628,7 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
     }
     struct OpWork {
       int op;
+      bool tri = false;   // diagonal output pair of a symmetric density: half storage
       std::vector<dev::FoldTask> tasks;
       std::vector<int> ilm;
       std::vector<double> alg_fold;  // unpadded flops of the fold per task
@@ -629,6 +646,7 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
         if (t.kind == BasisKind::Sadatom && sj != sk) continue;   // l-diagonal outputs only
         OpWork w;
         w.op = sj * ns + sk;
+        w.tri = s.p_symmetric && sj == sk;
         for (int si = 0; si < ns; si++)
           for (int sl = 0; sl < ns; sl++) {
             if (!sp_nz[(size_t)si * ns + sl]) continue;
@@ -647,12 +665,13 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
               ft.spp = si * ns + sl;
               ft.L = L;
               ft.rslot = 0;
-              ft.pad = 0;
+              ft.tri = w.tri ? 1 : 0;
               ft.fac = t.pref[ilm] * ((t.sign_by_M && (M & 1)) ? -1.0 : 1.0);
               w.tasks.push_back(ft);
               w.ilm.push_back(ilm);
               const double nj = s.sec_n[sj], nk = s.sec_n[sk], ni = s.sec_n[si], nl = s.sec_n[sl];
-              w.alg_fold.push_back(2.0 * s.Npix * (ni * nl * nk * t.nch + nj * ni * nk * s.nab));
+              w.alg_fold.push_back((w.tri ? s.tri_pix_frac : 1.0) * 2.0 * s.Npix *
+                                   (ni * nl * nk * t.nch + nj * ni * nk * s.nab));
             }
           }
         if (!w.tasks.empty()) work.push_back(std::move(w));
@@ -683,6 +702,8 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
       s.d_Kacc.alloc((size_t)nactive * S * s.op_stride, &dev_bytes_);
     }
     for (int a = 0; a < nactive; a++) np->op_src[work[a].op] = a;
+    np->op_tri.assign((size_t)ns * ns, 0);
+    for (int a = 0; a < nactive; a++) np->op_tri[a] = work[a].tri ? 1 : 0;
     if (absm_symmetric_) {
       // K(-mj,-mk) block = K(mj,mk) block (sectors +-m of one parity class hold the same l list)
       std::map<std::pair<int, int>, int> sec_of_m;
@@ -750,14 +771,16 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
             dev::GemmItem gi{};
             gi.C = acc_base + s.ep_off[(size_t)e * t.Nel + e];
             gi.browoff = s.d_browoff_T.p + s.browoff_T_first[e];
-            gi.M = n * n;
+            gi.M = w.tri ? n * (n + 1) / 2 : n * n;
+            np->maxM = std::max(np->maxM, gi.M);
             gi.N = s.sec_span[w.op / ns] * s.NP;   // columns (pos_j, pos_k) with pos_j past the sector are padding
             gi.K = s.nab * n * n;
             gi.ent0 = (int)gentries.size();
             for (size_t k = k0; k < k1; k++) {
               const int ilm = w.ilm[ti + k];
               dev::GemmEntry ge;
-              ge.A = s.d_tperm.p + s.tperm_off[(size_t)ilm * t.Nel + e];
+              ge.A = w.tri ? s.d_tperm_tri.p + s.tperm_tri_off[(size_t)ilm * t.Nel + e]
+                           : s.d_tperm.p + s.tperm_off[(size_t)ilm * t.Nel + e];
               ge.lda = 0;
               ge.B = s.d_R.p + (t0 + k) * slot_doubles;
               gentries.push_back(ge);
@@ -780,7 +803,7 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
           for (size_t k = 0; k < take; k++) oentries.push_back(dev::OffEntry{(int)(t0 + k), w.ilm[ti + k]});
           for (int ei = 0; ei < t.Nel; ei++)
             for (int ej = 0; ej < t.Nel; ej++) {
-              if (ei == ej) continue;
+              if (ei == ej || (w.tri && ei > ej)) continue;
               dev::OffItem oi{};
               oi.C = acc_base + s.ep_off[(size_t)ei * t.Nel + ej];
               oi.ei = ei;
@@ -835,7 +858,11 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
     {
       // in-element exchange: one CTA tile covers all Ni^2 rows (R rows are read once)
       const dim3 grid(s.NB / 64, (unsigned)bt.ngitems);
-      dev::k_tgemm_ws<<<grid, 288, s.tg_smem, st>>>(bt.gitems.p, bt.gentries.p, s.d_zrow.p, s.tg_stages, s.tg_maxM);
+      // stages of the shared-memory ring: as many as fit in 227 KB for the largest A tile of the plan, at most 4
+      int stages = 4;
+      while (stages > 2 && dev::tgemm_ws_smem(plan->maxM, stages) > 227 * 1024) stages--;
+      dev::k_tgemm_ws<<<grid, 288, dev::tgemm_ws_smem(plan->maxM, stages), st>>>(bt.gitems.p, bt.gentries.p, s.d_zrow.p,
+                                                                                 stages, plan->maxM);
       CK(cudaGetLastError());
     }
     CK(cudaEventRecord(s.ev[4], st));
@@ -867,7 +894,8 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
   // 6. unpack
   CK(cudaEventRecord(s.ev[6], st));
   CK(cudaMemcpyAsync(s.d_op_src.p, plan->op_src.data(), plan->op_src.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-  dev::UnpackDev u{s.d_op_src.p, s.d_ep_off.p, s.d_ang_sec.p, s.d_ang_pos.p, s.op_stride, S, s.kscale};
+  CK(cudaMemcpyAsync(s.d_op_tri.p, plan->op_tri.data(), plan->op_tri.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  dev::UnpackDev u{s.d_op_src.p, s.d_op_tri.p, s.d_ep_off.p, s.d_ang_sec.p, s.d_ang_pos.p, s.op_stride, S, s.kscale};
   dev::k_unpack_K<<<dim3(na, na), 256, 0, st>>>(s.bd, u, s.d_Kacc.p, dK, ldK);
   CK(cudaGetLastError());
   CK(cudaEventRecord(s.ev[7], st));

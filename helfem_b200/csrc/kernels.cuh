@@ -35,26 +35,50 @@ struct BasisDev {
   const int *rad_e1;     // [Nrad] last element containing it (elements overlap by one function)
 };
 
-// sum of squares of every (ang a, ang b) block -> norms2[a*Nang+b]
-static __global__ void k_block_norms(BasisDev b, const double *__restrict__ P, int64_t ld, double *__restrict__ norms2) {
+// per (ang a, ang c) block: sum of squares -> out[a*Nang+c], max |P_ac(i,j) - P_ca(j,i)| ->
+// out[Nang^2 + ..], max |P_ac(i,j)| -> out[2 Nang^2 + ..]  (screening + symmetry test of the density)
+static __global__ void k_block_norms(BasisDev b, const double *__restrict__ P, int64_t ld, double *__restrict__ out) {
   const int a = blockIdx.x, c = blockIdx.y;
   const int sa = b.ang_skip[a], sc = b.ang_skip[c];
   const int na = b.Nrad - sa, nc = b.Nrad - sc;
   const double *base = P + b.ang_off[a] + (int64_t)b.ang_off[c] * ld;
-  double s = 0.0;
+  const double *mirr = P + b.ang_off[c] + (int64_t)b.ang_off[a] * ld;
+  double s = 0.0, d = 0.0, m = 0.0;
   for (int idx = threadIdx.x; idx < na * nc; idx += blockDim.x) {
     const int i = idx % na, j = idx / na;
     const double v = base[i + (int64_t)j * ld];
     s += v * v;
+    d = fmax(d, fabs(v - mirr[j + (int64_t)i * ld]));
+    m = fmax(m, fabs(v));
   }
-  __shared__ double red[32];
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __shared__ double red[3][32];
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_down_sync(0xffffffffu, s, o);
+    d = fmax(d, __shfl_down_sync(0xffffffffu, d, o));
+    m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = s;
+    red[1][threadIdx.x >> 5] = d;
+    red[2][threadIdx.x >> 5] = m;
+  }
   __syncthreads();
   if (threadIdx.x < 32) {
-    s = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-    if (threadIdx.x == 0) norms2[a * b.Nang + c] = s;
+    const bool in = threadIdx.x < (blockDim.x >> 5);
+    s = in ? red[0][threadIdx.x] : 0.0;
+    d = in ? red[1][threadIdx.x] : 0.0;
+    m = in ? red[2][threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_down_sync(0xffffffffu, s, o);
+      d = fmax(d, __shfl_down_sync(0xffffffffu, d, o));
+      m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
+    }
+    if (threadIdx.x == 0) {
+      const int64_t nn = (int64_t)b.Nang * b.Nang;
+      out[a * b.Nang + c] = s;
+      out[nn + a * b.Nang + c] = d;
+      out[2 * nn + a * b.Nang + c] = m;
+    }
   }
 }
 
@@ -86,7 +110,7 @@ struct FoldTask {
   int spj, spk, spp;   // sector pairs of the two coupling tables and of P
   int L;               // multipole order (index into the coupling tables)
   int rslot;           // slot in the R buffer
-  int pad;
+  int tri;             // 1: symmetric-density diagonal output pair -- only pixels (ri, rl) with el(ri) <= el(rl) are needed
   double fac;          // prefactor incl. (-1)^M
 };
 
@@ -260,6 +284,7 @@ k_fold_reg(BasisDev b, const FoldTask *__restrict__ tasks, const double *__restr
     cp_async_commit();
     cp_async_wait<1>();
     __syncwarp();
+    if (t.tri && b.rad_e0[pix / b.Nrad] > b.rad_e1[pix % b.Nrad]) continue;   // mirrored by the unpack
     const double *P = myP + buf * NP * LDP + lr * LDP + lc;
     // ---- stage 1
     double c1[NCH][NT][NT][2];
@@ -463,11 +488,22 @@ __host__ __device__ inline int64_t tperm_index(int row, int col, int nn) {
 // Setup: dense exchange-ordered in-element kernel from the low-rank factor
 //   T[(rj*n + rk)][ab][(ri*n + rl)] = s_ab sum_p sigma_p B[a*nn + pair1, p] B[b*nn + rk + rl*n, p]
 //   pair1 = out_fast ? rj + ri*n : ri + rj*n
-// grid (n*n rows); stored at tperm_index(row, ab*nn + ri*n + rl, nn)
+// grid (rows); stored at tperm_index(row, ab*nn + ri*n + rl, rows)
 // ---------------------------------------------------------------------------
 static __global__ void k_build_tperm(const double *__restrict__ B, const double *__restrict__ sigma, int n, int rank, int nch,
-                              int out_fast, double *__restrict__ dst) {
-  const int row = blockIdx.x, rj = row / n, rk = row % n, nn = n * n;
+                              int out_fast, int tri, double *__restrict__ dst) {
+  // tri: rows are the pairs rj <= rk only, row t = rk (rk + 1) / 2 + rj (symmetric densities)
+  const int row = blockIdx.x, nn = n * n;
+  int rj, rk;
+  if (tri) {
+    rk = 0;
+    while ((rk + 1) * (rk + 2) / 2 <= row) rk++;
+    rj = row - rk * (rk + 1) / 2;
+  } else {
+    rj = row / n;
+    rk = row % n;
+  }
+  const int nrows = tri ? n * (n + 1) / 2 : nn;
   for (int col = threadIdx.x; col < nch * nch * nn; col += blockDim.x) {
     const int ab = col / nn, il = col % nn, a = ab / nch, bb = ab % nch, ri = il / n, rl = il % n;
     const int p1 = out_fast ? (rj + ri * n) : (ri + rj * n);
@@ -476,7 +512,7 @@ static __global__ void k_build_tperm(const double *__restrict__ B, const double 
     double s = 0.0;
     for (int p = 0; p < rank; p++) s += sigma[p] * b1[p * ldB] * b2[p * ldB];
     const double sgn = (nch == 2 && a != bb) ? -1.0 : 1.0;
-    dst[tperm_index(row, col, nn)] = sgn * s;
+    dst[tperm_index(row, col, nrows)] = sgn * s;
   }
 }
 
@@ -955,6 +991,7 @@ k_tgemm_ws(const GemmItem *__restrict__ items, const GemmEntry *__restrict__ ent
 // ---------------------------------------------------------------------------
 struct UnpackDev {
   const int *op_src;      // [ns*ns] sector pair whose accumulator holds this block (or -1: zero)
+  const int *op_tri;      // [active op] 1: symmetric storage (see below)
   const int64_t *ep_off;  // [Nel*Nel] offset of element-pair block inside one output pair's accumulator
   const int *ang_sec;     // [Nang] sector of angular function
   const int *ang_pos;     // [Nang] position inside the sector
@@ -963,6 +1000,9 @@ struct UnpackDev {
   double scale;           // exchange(scale * P) = scale * exchange(P)
 };
 
+// Symmetric storage (diagonal output pairs of a symmetric density): K(j rj, k rk) = K(k rk, j rj), so
+// only element pairs ei <= ej were computed, and of an in-element block only the rows rj <= rk
+// (row t = rk (rk+1)/2 + rj); the other half is read from the mirrored entry, column (pos_k, pos_j).
 static __global__ void k_unpack_K(BasisDev b, UnpackDev u, const double *__restrict__ Kacc, double *__restrict__ K, int64_t ld) {
   const int angk = blockIdx.y, angj = blockIdx.x;
   const int sj = b.ang_skip[angj], sk = b.ang_skip[angk];
@@ -971,6 +1011,8 @@ static __global__ void k_unpack_K(BasisDev b, UnpackDev u, const double *__restr
   const int op = u.ang_sec[angj] * b.ns + u.ang_sec[angk];
   const int src = u.op_src[op];
   const int blk = u.ang_pos[angj] * b.NP + u.ang_pos[angk];
+  const int blkT = u.ang_pos[angk] * b.NP + u.ang_pos[angj];
+  const bool tri = src >= 0 && u.op_tri[src];
   for (int idx = threadIdx.x; idx < nj * nk; idx += blockDim.x) {
     const int r = idx % nj + sj, c = idx / nj + sk;
     double s = 0.0;
@@ -979,8 +1021,16 @@ static __global__ void k_unpack_K(BasisDev b, UnpackDev u, const double *__restr
         const int ri = r - b.efirst[ei];
         for (int ej = b.rad_e0[c]; ej <= b.rad_e1[c]; ej++) {
           const int rk = c - b.efirst[ej];
-          const double *acc = Kacc + (int64_t)src * u.S * u.op_stride + u.ep_off[ei * b.Nel + ej] +
-                              (int64_t)(ri * b.en[ej] + rk) * b.NB + blk;
+          int64_t off;
+          if (!tri || ei < ej)
+            off = u.ep_off[ei * b.Nel + ej] + (int64_t)(ri * b.en[ej] + rk) * b.NB + blk;
+          else if (ei > ej)
+            off = u.ep_off[ej * b.Nel + ei] + (int64_t)(rk * b.en[ei] + ri) * b.NB + blkT;
+          else if (ri <= rk)
+            off = u.ep_off[ei * b.Nel + ei] + (int64_t)(rk * (rk + 1) / 2 + ri) * b.NB + blk;
+          else
+            off = u.ep_off[ei * b.Nel + ei] + (int64_t)(ri * (ri + 1) / 2 + rk) * b.NB + blkT;
+          const double *acc = Kacc + (int64_t)src * u.S * u.op_stride + off;
           for (int p = 0; p < u.S; p++) s += acc[(int64_t)p * u.op_stride];
         }
       }

@@ -92,6 +92,33 @@ def test_diatomic_absm_symmetric(hb):
     assert cases.relerr(Ksym, Ko) < TOL
 
 
+def test_nonsymmetric_density(hb):
+    """The reference's J/K are defined for any P (TwoDBasis.cpp:879-999, basis.cpp:1818-2089).  A symmetric
+    P takes the half-storage exchange path, a non-symmetric one the general path; both must match the oracle
+    and K[P]^T == K[P^T]."""
+    rng = np.random.default_rng(77)
+    ob = cases.oracle_diatomic(3, 1, 1.8, (3, 2), 2)
+    basis = hb.TablesBasis(cases.tables_from_oracle_diatomic(hb, ob))
+    n = ob.Nbf()
+    blocks = cases.m_blocks(ob.mval, ob.Nrad(), True)
+    P = np.zeros((n, n))
+    for b in blocks:
+        P[np.ix_(b, b)] = rng.standard_normal((len(b), len(b)))
+    Kg = basis.exchange(P)
+    assert cases.relerr(Kg, ob.exchange(P)) < TOL
+    assert cases.relerr(basis.exchange(P.T), Kg.T) < TOL
+    assert cases.relerr(basis.coulomb(P), ob.coulomb(P)) < TOL
+    Ps = P + P.T
+    Ks = basis.exchange(Ps)
+    assert cases.relerr(Ks, ob.exchange(Ps)) < TOL
+    assert cases.relerr(Ks, Kg + Kg.T) < TOL
+    oa = cases.oracle_atomic(4, 2, 1, 3)
+    ba = hb.TablesBasis(cases.tables_from_oracle_atomic(hb, oa))
+    Pa = rng.standard_normal((oa.Nbf(), oa.Nbf()))
+    assert cases.relerr(ba.exchange(Pa), oa.exchange(Pa)) < TOL
+    assert cases.relerr(ba.exchange(Pa + Pa.T), oa.exchange(Pa + Pa.T)) < TOL
+
+
 def test_linearity_and_symmetry(hb):
     """Size-independent properties: J,K linear in P; symmetric P -> symmetric J,K."""
     basis = hb.DiatomicTwoDBasis(7, 7, 2.07, [5, 4, 3], 3).compute_tei()
