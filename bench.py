@@ -245,7 +245,7 @@ def main():
         return
     # ---- end-to-end through the host-pointer C ABI (pinned host buffers, copies inside)
     e2e_val = None
-    h2d_bytes, d2h_bytes = n * n * 8, 2 * n * n * 8
+    h2d_bytes, d2h_bytes, spec_hits = n * n * 8, 2 * n * n * 8, None
     if world == 1:
         hJ.fill_(float("nan"))   # the call must define every element (copied blocks + host zero-fill)
         hK.fill_(float("nan"))
@@ -258,6 +258,7 @@ def main():
         e2e_val = args.steps / (time.perf_counter() - t0)
         tm = basis.last_timings()
         h2d_bytes, d2h_bytes = int(tm["h2d_bytes"]), int(tm["d2h_bytes"])
+        spec_hits = int(tm["speculative_hits"])
         ek = float((hK.cuda() - dK).abs().max() / dK.abs().max())
         ej = float((hJ.cuda() - dJ).abs().max() / dJ.abs().max())
         assert ek < 1e-12 and ej < 1e-12, "host and device paths disagree: %g %g" % (ek, ej)
@@ -335,10 +336,14 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "e2e": {"value": e2e_val, "unit": "builds/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                    "call": "hfq_coulomb_exchange (one dense upload of P; of J and K only the row ranges of the non-zero "
-                            "blocks cross PCIe, the rest of the dense host matrices is zero-filled by host threads "
-                            "while the GPU computes)" if world == 1 else
+                    "call": "hfq_coulomb_exchange, dense pinned host matrices in and out. P: the row ranges that were non-zero in "
+                            "the previous call are uploaded first and the build starts on them while the complete matrix "
+                            "follows on another stream and is compared bit-for-bit on the device (mismatch = rebuild from "
+                            "the full upload; speculative_hits counts the calls that did not need it). J, K: only the row "
+                            "ranges of the non-zero blocks cross PCIe, the rest of the host matrices is zero-filled by host "
+                            "threads while the GPU computes" if world == 1 else
                             "rank 0 host buffers -> broadcast P -> sharded build -> all-reduce -> copy back",
+                    "speculative_hits": spec_hits,
                     "separate_calls_value": e2e_sep if world == 1 else None,
                     "separate_calls_note": "hfq_coulomb + hfq_exchange issued separately (2 uploads, no overlap)"},
             "gpu_launches": int(acc["launches"]), "roofline": roofline, "cpu_baseline": cpu_baseline,

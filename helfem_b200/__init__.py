@@ -313,11 +313,11 @@ class _BasisBase:
         return bs, [(int(pr[2 * i]), int(pr[2 * i + 1])) for i in range(k)]
 
     def last_timings(self):
-        out = np.zeros(19)
-        _check(lib().hfq_last_timings(self._context(), out.ctypes.data, 19))
+        out = np.zeros(20)
+        _check(lib().hfq_last_timings(self._context(), out.ctypes.data, 20))
         keys = ["ms_pack", "ms_fold", "ms_tgemm", "ms_offdiag", "ms_unpack", "ms_total", "flops_fold", "flops_tgemm",
                 "flops_offdiag", "launches", "device_bytes", "alg_fold", "alg_tgemm", "alg_offdiag",
-                "launches_fold", "launches_tgemm", "launches_offdiag", "h2d_bytes", "d2h_bytes"]
+                "launches_fold", "launches_tgemm", "launches_offdiag", "h2d_bytes", "d2h_bytes", "speculative_hits"]
         return dict(zip(keys, out))
 
     # -- helpers ---------------------------------------------------------------

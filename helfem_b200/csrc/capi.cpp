@@ -445,11 +445,11 @@ int hfq_eval_fxc(hfq_ctx *ctx, int x_func, int c_func, const double *Pa, int64_t
 int hfq_last_timings(const hfq_ctx *ctx, double *out, int n) {
   if (!ctx || !out) return fail(HFQ_ERR_INVALID, "hfq_last_timings: null argument");
   const hfq::EngineTimings &t = ctx->eng->timings();
-  const double v[19] = {t.pack, t.fold, t.tgemm, t.offdiag, t.unpack, t.total, t.flops_fold, t.flops_tgemm,
+  const double v[20] = {t.pack, t.fold, t.tgemm, t.offdiag, t.unpack, t.total, t.flops_fold, t.flops_tgemm,
                         t.flops_offdiag, (double)t.launches, (double)ctx->eng->device_bytes(), t.alg_fold,
                         t.alg_tgemm, t.alg_offdiag, (double)t.launches_fold, (double)t.launches_tgemm,
-                        (double)t.launches_offdiag, t.h2d_bytes, t.d2h_bytes};
-  for (int i = 0; i < n && i < 19; i++) out[i] = v[i];
+                        (double)t.launches_offdiag, t.h2d_bytes, t.d2h_bytes, (double)ctx->eng->speculative_hits()};
+  for (int i = 0; i < n && i < 20; i++) out[i] = v[i];
   return HFQ_OK;
 }
 

@@ -58,6 +58,7 @@ class Engine {
   void coulomb(const double *P, int64_t ldP, double *J, int64_t ldJ);
   void exchange(const double *P, int64_t ldP, double *K, int64_t ldK);
   void coulomb_exchange(const double *P, int64_t ldP, double kscale, double *J, int64_t ldJ, double *K, int64_t ldK);
+  int speculative_hits() const { return spec_hits_; }   // fused host calls that ran on a predicted sparse upload
 
   // Non-zero structure of the last exchange result: sector id of every dense basis function and
   // the (row sector, column sector) pairs that were written; all other blocks of K are zero.
@@ -78,6 +79,9 @@ class Engine {
   HostRanges host_ranges(bool coulomb) const;
   double copy_ranges_async(double *H, int64_t ldH, const double *D, const HostRanges &hr, cudaStream_t st) const;   // returns bytes
   static void zero_outside(double *H, int64_t ldH, int n, const HostRanges &hr);
+  bool fused_host(const double *P, int64_t ldP, double kscale, double *J, int64_t ldJ, double *K, int64_t ldK, bool spec);
+  HostRanges density_ranges() const;   // bounding non-zero row range per column of the density packed last
+  int spec_hits_ = 0;
   std::function<void()> plan_hook_;   // called by exchange_dev once the output pattern is known
   struct Impl;
   struct PlanCache;

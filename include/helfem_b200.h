@@ -182,7 +182,9 @@ int hfq_coulomb_output_pattern(const hfq_ctx *ctx, int *bf_sector, int64_t cap_b
  * out[10] = device bytes held by the context, out[11..13] = algorithmic (unpadded) flops
  * {fold, in-element GEMM, cross-element}, out[14..16] = launches of those three kernels,
  * out[17..18] = bytes copied host->device / device->host by the last host-pointer call (the
- * result copies skip the rows outside the non-zero blocks; those are zero-filled on the host). */
+ * result copies skip the rows outside the non-zero blocks; those are zero-filled on the host),
+ * out[19] = number of hfq_coulomb_exchange calls on this context that ran on a predicted sparse
+ * upload of P (pinned host buffers only; verified bit-for-bit against the full upload). */
 int hfq_last_timings(const hfq_ctx *ctx, double *out, int n);
 
 #ifdef __cplusplus

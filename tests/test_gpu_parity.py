@@ -260,3 +260,37 @@ def test_atomic_rs_exchange_yukawa(hb):
             assert np.abs(sm[0] - ob.disjoint_iL[L * Nel + e]).max() <= 1e-12 * np.abs(sm[0]).max()
             W, Wo = B @ B.T, ob.rs_chol[L * Nel + e] @ ob.rs_chol[L * Nel + e].T
             assert np.abs(W - Wo).max() <= 1e-10 * np.abs(Wo).max()
+
+
+def test_fused_host_speculative_upload(hb):
+    """hfq_coulomb_exchange with page-locked buffers: the second call with the same block structure runs on
+    the predicted sparse upload (verified against the full one on the device), a call whose structure grew
+    falls back to the full upload; all three match the oracle (include/helfem_b200.h, out[19])."""
+    import ctypes
+    import torch
+    ob = cases.oracle_diatomic(3, 1, 1.8, (3, 2), 2)
+    basis = hb.TablesBasis(cases.tables_from_oracle_diatomic(hb, ob))
+    n = ob.Nbf()
+    blocks = cases.m_blocks(ob.mval, ob.Nrad(), True)
+    hP = torch.zeros((n, n), dtype=torch.float64).pin_memory()
+    hJ = torch.empty((n, n), dtype=torch.float64).pin_memory()
+    hK = torch.empty((n, n), dtype=torch.float64).pin_memory()
+
+    def run(P):
+        hP.copy_(torch.from_numpy(np.ascontiguousarray(P.T)))   # column-major for the C ABI
+        hJ.fill_(float("nan"))
+        hK.fill_(float("nan"))
+        hb._check(hb.lib().hfq_coulomb_exchange(basis._context(), hP.data_ptr(), n, 0.5, hJ.data_ptr(), n,
+                                                hK.data_ptr(), n))
+        return hJ.numpy().T.copy(), hK.numpy().T.copy(), int(basis.last_timings()["speculative_hits"])
+
+    P1 = cases.random_density(n, 2, 5, blocks[:1])          # only the first m block
+    P2 = cases.random_density(n, 3, 6, blocks[:1])          # same structure, other values
+    P3 = cases.random_density(n, 3, 7, blocks)              # structure grows: prediction fails
+    hits = []
+    for P in (P1, P2, P3, P3):
+        J, K, h = run(P)
+        hits.append(h)
+        assert cases.relerr(J, ob.coulomb(P)) < TOL
+        assert cases.relerr(K, ob.exchange(0.5 * P)) < TOL
+    assert hits == [0, 1, 1, 2]
