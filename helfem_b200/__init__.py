@@ -35,7 +35,8 @@ class _TablesInfo(ctypes.Structure):
 
 
 EXPORTED_SYMBOLS = [
-    "hfq_last_error", "hfq_tables_atomic", "hfq_tables_atomic_yukawa", "hfq_tables_sadatom", "hfq_tables_diatomic", "hfq_tables_from_arrays", "hfq_tables_get_info",
+    "hfq_last_error", "hfq_tables_atomic", "hfq_tables_atomic_yukawa", "hfq_tables_atomic_erfc",
+    "hfq_tables_set_pair_tensors", "hfq_tables_get_pair_tensor", "hfq_erfc_phi", "hfq_tables_sadatom", "hfq_tables_diatomic", "hfq_tables_from_arrays", "hfq_tables_get_info",
     "hfq_tables_get_ints", "hfq_tables_get_doubles", "hfq_tables_get_block", "hfq_tables_one_electron",
     "hfq_tables_destroy", "hfq_create", "hfq_destroy", "hfq_nbf", "hfq_set_absm_symmetric", "hfq_coulomb",
     "hfq_exchange", "hfq_coulomb_device", "hfq_exchange_device", "hfq_last_timings", "hfq_exchange_output_pattern",
@@ -57,6 +58,12 @@ def lib():
     vp, ci, cd, i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_int64
     L.hfq_tables_atomic.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ci, ci, cd, ci, cd, ci]
     L.hfq_tables_atomic_yukawa.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ci, ci, cd, ci, cd, ci, cd]
+    L.hfq_tables_atomic_erfc.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ci, ci, cd, ci, cd, ci, cd]
+    L.hfq_tables_set_pair_tensors.argtypes = [vp, vp, i64]
+    L.hfq_tables_get_pair_tensor.argtypes = [vp, ci, ci, ci, vp, i64]
+    L.hfq_tables_get_pair_tensor.restype = i64
+    L.hfq_erfc_phi.argtypes = [ci, cd, cd]
+    L.hfq_erfc_phi.restype = cd
     L.hfq_tables_sadatom.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ci, cd, ci, cd, ci]
     L.hfq_tables_diatomic.argtypes = [ctypes.POINTER(vp), ci, ci, cd, _c_int_p, ci, ci, ci, cd, ci, cd, ci]
     L.hfq_tables_from_arrays.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(_TablesDesc)]
@@ -136,6 +143,28 @@ class Tables:
         h = ctypes.c_void_p()
         _check(lib().hfq_tables_atomic_yukawa(ctypes.byref(h), Z, lmax, mmax, nelem, nnodes, Rmax, igrid, zexp, nquad, lam))
         return cls(h)
+
+    @classmethod
+    def atomic_erfc(cls, Z, lmax, mmax, nelem, nnodes=15, Rmax=40.0, igrid=4, zexp=2.0, nquad=0, mu=0.3):
+        h = ctypes.c_void_p()
+        _check(lib().hfq_tables_atomic_erfc(ctypes.byref(h), Z, lmax, mmax, nelem, nnodes, Rmax, igrid, zexp, nquad, mu))
+        return cls(h)
+
+    def set_pair_tensors(self, ktei_list):
+        """Attach the reference's rs_ktei cache: list over (L*Nel + iel)*Nel + jel of (Ni*Nj) x (Ni*Nj) matrices
+        ktei[kk*Ni + jj, ll*Ni + ii] (src/atomic/TwoDBasis.h, utils::exchange_tei)."""
+        flat = np.concatenate([np.asarray(k, dtype=np.float64).reshape(-1, order="F") for k in ktei_list])
+        _check(lib().hfq_tables_set_pair_tensors(self._h, flat.ctypes.data, flat.size))
+        return self
+
+    def pair_tensor(self, L, iel, jel):
+        n = _check(lib().hfq_tables_get_pair_tensor(self._h, L, iel, jel, None, 0))
+        if n == 0:
+            return None
+        out = np.empty(n)
+        _check(lib().hfq_tables_get_pair_tensor(self._h, L, iel, jel, out.ctypes.data, n))
+        m = int(round(np.sqrt(n)))
+        return out.reshape(m, m, order="F")
 
     @classmethod
     def sadatom(cls, Z, lmax, nelem, nnodes=15, Rmax=40.0, igrid=4, zexp=2.0, nquad=0):
@@ -362,8 +391,15 @@ class AtomicTwoDBasis(_BasisBase):
         self._rs._tables = Tables.atomic_yukawa(*self._args, lam=lam)
         return self
 
+    def compute_erfc(self, mu):
+        """TwoDBasisT::compute_erfc (src/atomic/TwoDBasis.cpp:762-771): erfc-attenuated pair tensors."""
+        self._rs = _BasisBase(self._device)
+        self._rs._tables = Tables.atomic_erfc(*self._args, mu=mu)
+        return self
+
     def rs_exchange(self, P):
-        """TwoDBasisT::rs_exchange (src/atomic/TwoDBasis.cpp:1001-1131), Yukawa kernel."""
+        """TwoDBasisT::rs_exchange (src/atomic/TwoDBasis.cpp:1001-1131), kernel of the last compute_yukawa /
+        compute_erfc call."""
         if getattr(self, "_rs", None) is None:
             raise ValueError("Primitive teis have not been computed!\n")
         return self._rs.exchange(P)

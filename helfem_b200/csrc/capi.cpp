@@ -80,6 +80,79 @@ int hfq_tables_atomic_yukawa(hfq_tables **out, int Z, int lmax, int mmax, int ne
   });
 }
 
+int hfq_tables_atomic_erfc(hfq_tables **out, int Z, int lmax, int mmax, int nelem, int nnodes, double Rmax, int igrid,
+                           double zexp, int nquad, double mu) {
+  if (!out || lmax < 0 || mmax < 0 || mmax > lmax || nelem < 1 || nnodes < 2 || nnodes > 16 || !(Rmax > 0.0) || !(mu > 0.0))
+    return fail(HFQ_ERR_INVALID, "hfq_tables_atomic_erfc: invalid argument");
+  return guarded([&] {
+    auto *h = new hfq_tables;
+    h->t = hfq::build_atomic_erfc_tables(Z, lmax, mmax, nelem, nnodes, Rmax, igrid, zexp, nquad, mu);
+    *out = h;
+    return HFQ_OK;
+  });
+}
+
+int hfq_tables_set_pair_tensors(hfq_tables *h, const double *ktei, int64_t count) {
+  if (!h || !ktei) return fail(HFQ_ERR_INVALID, "hfq_tables_set_pair_tensors: null argument");
+  hfq::BasisTables &t = h->t;
+  if (t.nch != 1) return fail(HFQ_ERR_INVALID, "hfq_tables_set_pair_tensors: one-channel (atomic) tables only");
+  const int nlm = (int)t.lmL.size(), Nel = t.Nel;
+  int64_t need = 0;
+  for (int ei = 0; ei < Nel; ei++)
+    for (int ej = 0; ej < Nel; ej++) need += (int64_t)t.en[ei] * t.en[ej] * t.en[ei] * t.en[ej];
+  need *= nlm;
+  if (count != need) return fail(HFQ_ERR_INVALID, "hfq_tables_set_pair_tensors: unexpected size");
+  return guarded([&] {
+    t.pair.assign((size_t)nlm * Nel * Nel, {});
+    const double *src = ktei;
+    for (int L = 0; L < nlm; L++)
+      for (int ei = 0; ei < Nel; ei++)
+        for (int ej = 0; ej < Nel; ej++) {
+          const int Ni = t.en[ei], Nj = t.en[ej];
+          const size_t M = (size_t)Ni * Nj;
+          std::vector<double> &A = t.pair[((size_t)L * Nel + ei) * Nel + ej];
+          A.resize(M * M);
+          // reference: ktei(rk*Ni + rj, rl*Ni + ri), column-major  ->  A[(rj*Nj + rk)][(ri*Nj + rl)]
+          for (int rj = 0; rj < Ni; rj++)
+            for (int rk = 0; rk < Nj; rk++)
+              for (int ri = 0; ri < Ni; ri++)
+                for (int rl = 0; rl < Nj; rl++)
+                  A[((size_t)rj * Nj + rk) * M + (size_t)ri * Nj + rl] = src[((size_t)rk * Ni + rj) + ((size_t)rl * Ni + ri) * M];
+          src += M * M;
+        }
+    return HFQ_OK;
+  });
+}
+
+int64_t hfq_tables_get_pair_tensor(const hfq_tables *h, int L, int iel, int jel, double *out, int64_t cap) {
+  if (!h) return fail(HFQ_ERR_INVALID, "hfq_tables_get_pair_tensor: null argument");
+  const hfq::BasisTables &t = h->t;
+  if (!t.pairwise()) return 0;
+  const int nlm = (int)t.lmL.size(), Nel = t.Nel;
+  if (L < 0 || L >= nlm || iel < 0 || iel >= Nel || jel < 0 || jel >= Nel)
+    return fail(HFQ_ERR_INVALID, "hfq_tables_get_pair_tensor: index out of range");
+  const int Ni = t.en[iel], Nj = t.en[jel];
+  const size_t M = (size_t)Ni * Nj;
+  if (!out) return (int64_t)(M * M);
+  if (cap < (int64_t)(M * M)) return fail(HFQ_ERR_INVALID, "hfq_tables_get_pair_tensor: buffer too small");
+  const std::vector<double> &A = t.pair[((size_t)L * Nel + iel) * Nel + jel];
+  for (int rj = 0; rj < Ni; rj++)
+    for (int rk = 0; rk < Nj; rk++)
+      for (int ri = 0; ri < Ni; ri++)
+        for (int rl = 0; rl < Nj; rl++)
+          out[((size_t)rk * Ni + rj) + ((size_t)rl * Ni + ri) * M] = A[((size_t)rj * Nj + rk) * M + (size_t)ri * Nj + rl];
+  return (int64_t)(M * M);
+}
+
+double hfq_erfc_phi(int L, double Xi, double xi) {
+  try {
+    return hfq::erfc_phi(L, Xi, xi);
+  } catch (const std::exception &e) {
+    fail(HFQ_ERR_INTERNAL, e.what());
+    return std::nan("");
+  }
+}
+
 int hfq_tables_sadatom(hfq_tables **out, int Z, int lmax, int nelem, int nnodes, double Rmax, int igrid, double zexp,
                        int nquad) {
   if (!out || lmax < 0 || nelem < 1 || nnodes < 2 || nnodes > 16 || !(Rmax > 0.0))

@@ -89,7 +89,7 @@ struct Engine::Impl {
   double tri_pix_frac = 1.0;   // share of the pixels (ri, rl) with el(ri) <= el(rl)
   DevBuf<double> d_G, d_small, d_big, d_B, d_sigma, d_tperm, d_tperm_tri, d_zrow;
   DevBuf<int64_t> d_blk_off, d_B_off, d_sig_off, d_ep_off;
-  DevBuf<int> d_rank, d_chan_of, d_browoff_T, d_browoff_G, d_splist, d_op_src, d_op_tri, d_sp_active;
+  DevBuf<int> d_rank, d_chan_of, d_browoff_T, d_browoff_P, d_browoff_G, d_splist, d_op_src, d_op_tri, d_sp_active;
   DevBuf<double> d_jfac, d_norms, d_Ppix, d_R, d_Kacc, d_Paux, d_JauxT, d_Jsec, d_P, d_O, d_O2;
   DevBuf<dev::FoldTask> d_tasks;
   DevBuf<dev::GemmItem> d_gitems;
@@ -97,6 +97,8 @@ struct Engine::Impl {
   DevBuf<dev::OffItem> d_oitems;
   DevBuf<dev::OffEntry> d_oentries;
   std::vector<int> browoff_T_first;  // per element: first index into d_browoff_T
+  std::vector<int> browoff_P_first;  // pair-tensor tables: per element pair, first index into d_browoff_P
+  std::vector<int64_t> tpair_off, tpair_tri_off;   // [(ilm*Nel + ei)*Nel + ej] offsets of the tiled pair tensors (-1: absent)
   dev::BasisDev bd{};
   size_t r_slots = 0;                // capacity of the R buffer in task slots
   // density packed by pack_density(): shared by coulomb and exchange in a fused build
@@ -352,6 +354,45 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
   s.d_ep_off.upload(s.ep_off, &dev_bytes_);
   // ---- dense exchange-ordered in-element kernels, one per (multipole channel, element), stored as
   //      the pre-swizzled k-chunk tiles k_tgemm_ws bulk-copies (kernels.cuh: tperm_index)
+  if (t.pairwise()) {
+    // dense pair tensors (erfc): tile + swizzle on the host, every element pair; the symmetric-density
+    // variant keeps the rows rj <= rk of in-element blocks and the pairs ei < ej
+    if (t.nch != 1) throw std::runtime_error("Engine: pair tensors need a one-channel basis");
+    for (int tri = 0; tri < 2; tri++) {
+      std::vector<int64_t> &offs = tri ? s.tpair_tri_off : s.tpair_off;
+      DevBuf<double> &buf = tri ? s.d_tperm_tri : s.d_tperm;
+      offs.assign((size_t)nlm * t.Nel * t.Nel, -1);
+      int64_t off = 0;
+      for (int ilm = 0; ilm < nlm; ilm++)
+        for (int ei = 0; ei < t.Nel; ei++)
+          for (int ej = 0; ej < t.Nel; ej++) {
+            if (tri && ei > ej) continue;
+            const int Ni = t.en[ei], Nj = t.en[ej];
+            const int rows = (tri && ei == ej) ? Ni * (Ni + 1) / 2 : Ni * Nj;
+            offs[((size_t)ilm * t.Nel + ei) * t.Nel + ej] = off;
+            off += dev::tperm_doubles(rows, Ni * Nj);
+          }
+      std::vector<double> h((size_t)off, 0.0);
+      for (int ilm = 0; ilm < nlm; ilm++)
+        for (int ei = 0; ei < t.Nel; ei++)
+          for (int ej = 0; ej < t.Nel; ej++) {
+            const int64_t o = offs[((size_t)ilm * t.Nel + ei) * t.Nel + ej];
+            if (o < 0) continue;
+            const int Ni = t.en[ei], Nj = t.en[ej], K = Ni * Nj;
+            const bool half = tri && ei == ej;
+            const int rows = half ? Ni * (Ni + 1) / 2 : K;
+            const std::vector<double> &A = t.pair[((size_t)ilm * t.Nel + ei) * t.Nel + ej];
+            for (int rj = 0; rj < Ni; rj++)
+              for (int rk = 0; rk < Nj; rk++) {
+                if (half && rj > rk) continue;
+                const int row = half ? rk * (rk + 1) / 2 + rj : rj * Nj + rk;
+                for (int col = 0; col < K; col++)
+                  h[o + dev::tperm_index(row, col, rows)] = A[((size_t)rj * Nj + rk) * K + col];
+              }
+          }
+      buf.upload(h, &dev_bytes_);
+    }
+  } else
   for (int tri = 0; tri < 2; tri++) {
     std::vector<int64_t> &offs = tri ? s.tperm_tri_off : s.tperm_off;
     DevBuf<double> &buf = tri ? s.d_tperm_tri : s.d_tperm;
@@ -391,6 +432,21 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
           }
     }
     s.d_browoff_T.upload(bo, &dev_bytes_);
+    if (t.pairwise()) {
+      // pair tensors: k' = ri*Nj + rl -> pix(ri in ei, rl in ej) * NB
+      std::vector<int> bp;
+      for (int ei = 0; ei < t.Nel; ei++)
+        for (int ej = 0; ej < t.Nel; ej++) {
+          s.browoff_P_first.push_back((int)bp.size());
+          for (int ri = 0; ri < t.en[ei]; ri++)
+            for (int rl = 0; rl < t.en[ej]; rl++) {
+              const int64_t v = ((int64_t)(t.efirst[ei] + ri) * t.Nrad + t.efirst[ej] + rl) * s.NB;
+              if (v > 0x7fffffffLL) throw std::runtime_error("Engine: R row offset overflows int32");
+              bp.push_back((int)v);
+            }
+        }
+      s.d_browoff_P.upload(bp, &dev_bytes_);
+    }
     // J unfold: q -> q * NB
     std::vector<int> bg((size_t)s.NL * t.nch);
     for (size_t q = 0; q < bg.size(); q++) bg[q] = (int)(q * s.NB);
@@ -773,37 +829,48 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
           double *acc_base = s.d_Kacc.p + ((size_t)wi * S + c) * s.op_stride;
           const int acc = started[wi * S + c] ? 1 : 0;
           started[wi * S + c] = 1;
-          for (int e = 0; e < t.Nel; e++) {
-            const int n = t.en[e];
-            dev::GemmItem gi{};
-            gi.C = acc_base + s.ep_off[(size_t)e * t.Nel + e];
-            gi.browoff = s.d_browoff_T.p + s.browoff_T_first[e];
-            gi.M = w.tri ? n * (n + 1) / 2 : n * n;
-            np->maxM = std::max(np->maxM, gi.M);
-            gi.N = s.sec_span[w.op / ns] * s.NP;   // columns (pos_j, pos_k) with pos_j past the sector are padding
-            gi.K = s.nab * n * n;
-            gi.ent0 = (int)gentries.size();
-            for (size_t k = k0; k < k1; k++) {
-              const int ilm = w.ilm[ti + k];
-              dev::GemmEntry ge;
-              ge.A = w.tri ? s.d_tperm_tri.p + s.tperm_tri_off[(size_t)ilm * t.Nel + e]
-                           : s.d_tperm.p + s.tperm_off[(size_t)ilm * t.Nel + e];
-              ge.lda = 0;
-              ge.B = s.d_R.p + (t0 + k) * slot_doubles;
-              gentries.push_back(ge);
+          // element pairs handled by the GEMM: the diagonal ones, plus -- for pair-tensor tables (erfc) --
+          // every other pair (only ei < ej for a symmetric density)
+          for (int ei = 0; ei < t.Nel; ei++)
+            for (int ej = 0; ej < t.Nel; ej++) {
+              if (ei != ej && (!t.pairwise() || (w.tri && ei > ej))) continue;
+              const int Ni = t.en[ei], Nj = t.en[ej];
+              const bool half = w.tri && ei == ej;
+              dev::GemmItem gi{};
+              gi.C = acc_base + s.ep_off[(size_t)ei * t.Nel + ej];
+              gi.browoff = t.pairwise() ? s.d_browoff_P.p + s.browoff_P_first[(size_t)ei * t.Nel + ej]
+                                        : s.d_browoff_T.p + s.browoff_T_first[ei];
+              gi.M = half ? Ni * (Ni + 1) / 2 : Ni * Nj;
+              np->maxM = std::max(np->maxM, gi.M);
+              gi.N = s.sec_span[w.op / ns] * s.NP;   // columns (pos_j, pos_k) with pos_j past the sector are padding
+              gi.K = s.nab * Ni * Nj;
+              gi.ent0 = (int)gentries.size();
+              for (size_t k = k0; k < k1; k++) {
+                const int ilm = w.ilm[ti + k];
+                dev::GemmEntry ge;
+                if (t.pairwise()) {
+                  const size_t pi = ((size_t)ilm * t.Nel + ei) * t.Nel + ej;
+                  ge.A = w.tri ? s.d_tperm_tri.p + s.tpair_tri_off[pi] : s.d_tperm.p + s.tpair_off[pi];
+                } else {
+                  ge.A = w.tri ? s.d_tperm_tri.p + s.tperm_tri_off[(size_t)ilm * t.Nel + ei]
+                               : s.d_tperm.p + s.tperm_off[(size_t)ilm * t.Nel + ei];
+                }
+                ge.lda = 0;
+                ge.B = s.d_R.p + (t0 + k) * slot_doubles;
+                gentries.push_back(ge);
+              }
+              gi.ent1 = (int)gentries.size();
+              gi.accumulate = acc;
+              gi.ldb = 0;
+              gi.ldc = s.NB;
+              gi.alpha = 1.0;
+              gitems.push_back(gi);
+              np->fl_tg += 2.0 * gi.M * gi.N * (double)gi.K * (k1 - k0);
+              np->al_tg += 2.0 * gi.M * (double)s.sec_n[w.op / ns] * s.sec_n[w.op % ns] * (double)gi.K * (k1 - k0);
             }
-            gi.ent1 = (int)gentries.size();
-            gi.accumulate = acc;
-            gi.ldb = 0;
-            gi.ldc = s.NB;
-            gi.alpha = 1.0;
-            gitems.push_back(gi);
-            np->fl_tg += 2.0 * gi.M * gi.N * (double)gi.K * (k1 - k0);
-            np->al_tg += 2.0 * gi.M * (double)s.sec_n[w.op / ns] * s.sec_n[w.op % ns] * (double)gi.K * (k1 - k0);
-          }
         }
-        // cross-element items (partial buffer 0)
-        {
+        // cross-element items (partial buffer 0); pair-tensor tables went through the GEMM above
+        if (!t.pairwise()) {
           double *acc_base = s.d_Kacc.p + (size_t)wi * S * s.op_stride;
           const int acc = ti > 0 ? 1 : 0;
           const int oe0 = (int)oentries.size();
@@ -962,6 +1029,8 @@ void Engine::coulomb_dev(const double *dP, int64_t ldP, double *dJ, int64_t ldJ,
                          cudaStream_t st) {
   Impl &s = *p_;
   const BasisTables &t = s.t;
+  if (t.pairwise())
+    throw std::logic_error("coulomb is not available on range-separated (erfc pair-tensor) tables\n");
   CK(cudaSetDevice(device_));
   const int na = t.Nang(), ns = s.ns, nq = s.NL * t.nch;
   tm_ = EngineTimings();

@@ -43,6 +43,13 @@ struct BasisTables {
   bool sign_by_M = false;               // multiply prefactor by (-1)^M
   int Lext = 0;                         // coupling range |lj-li|-Lext .. lj+li+Lext
   std::vector<ChannelBlock> blocks;     // [ilm*Nel + iel]
+  // Optional dense pair tensors (kernels that do not factorise across elements: erfc attenuation,
+  // src/atomic/TwoDBasis.h rs_ktei).  pair[(ilm*Nel + ei)*Nel + ej] is the exchange-ordered matrix
+  // A[(rj*Nj + rk)][(ri*Nj + rl)] (row-major, Ni*Nj square), rj, ri in element ei, rk, rl in ej:
+  // K_(ei,ej)(rj, rk) += sum A R(ri, rl).  When present, exchange() uses them for EVERY element pair
+  // and coulomb() is unavailable (the reference has no range-separated Coulomb build either).
+  std::vector<std::vector<double>> pair;
+  bool pairwise() const { return !pair.empty(); }
   // basis parameters kept for bookkeeping / grid construction
   double Rhalf = 0.0;
   int Z1 = 0, Z2 = 0;
@@ -64,6 +71,14 @@ BasisTables build_atomic_tables(int Z, int lmax, int mmax, int nelem, int nnodes
 // (:1001-1131): i_L / k_L weighted cross-element factors, Yukawa in-element kernel, prefactor 4 pi lambda
 BasisTables build_atomic_yukawa_tables(int Z, int lmax, int mmax, int nelem, int nnodes, double Rmax, int igrid,
                                        double zexp, int nquad, double lambda);
+// erfc-attenuated exchange caches (TwoDBasis::compute_erfc, src/atomic/TwoDBasis.cpp:762-771,
+// CoulombExchangeFE.h:275-297, RadialBasis.cpp:742-810, quadrature.cpp:201-249, erfc_expn.cpp):
+// dense pair tensors of the Green's function Phi_L(mu r, mu r'), prefactor 4 pi mu/(2L+1) (:1083).
+// exchange() on these tables is the reference's rs_exchange() for erfc range separation.
+BasisTables build_atomic_erfc_tables(int Z, int lmax, int mmax, int nelem, int nnodes, double Rmax, int igrid,
+                                     double zexp, int nquad, double mu);
+// Phi_L(Xi, xi) of the erfc expansion (exported for tests)
+double erfc_phi(int n, double Xi, double xi);
 // spherically averaged atom (src/sadatom/basis.{h,cpp}): one angular function per l (m summed
 // out), same radial caches as the atomic basis; exchange couples density block l_in to output
 // block l_out through the m-averaged squared Gaunt coefficient (src/sadatom/basis.cpp:209-312)

@@ -45,9 +45,24 @@ int hfq_tables_atomic(hfq_tables **out, int Z, int lmax, int mmax, int nelem, in
 
 /* Range-separated exchange, Yukawa kernel: TwoDBasisT::compute_yukawa(lambda) (src/atomic/TwoDBasis.cpp:737-758).
  * hfq_exchange on a context created from these tables is TwoDBasisT::rs_exchange(P) (:1001-1131, Yukawa branch).
- * (The erfc kernel of compute_erfc is not built yet.) */
+ */
 int hfq_tables_atomic_yukawa(hfq_tables **out, int Z, int lmax, int mmax, int nelem, int nnodes, double Rmax, int igrid,
                              double zexp, int nquad, double lambda);
+
+/* Range-separated exchange, erfc kernel: TwoDBasisT::compute_erfc(mu) (src/atomic/TwoDBasis.cpp:762-771,
+ * CoulombExchangeFE.h:275-297): dense pair tensors rs_ktei for every element pair, prefactor 4 pi mu/(2L+1).
+ * hfq_exchange on a context created from these tables is TwoDBasisT::rs_exchange(P) (:1001-1131, erfc branch);
+ * hfq_coulomb on it fails (the reference has no range-separated Coulomb build). */
+int hfq_tables_atomic_erfc(hfq_tables **out, int Z, int lmax, int mmax, int nelem, int nnodes, double Rmax, int igrid,
+                           double zexp, int nquad, double mu);
+/* Hand over the reference's own rs_ktei cache (src/atomic/TwoDBasis.h): for flat index (L*Nel + iel)*Nel + jel a
+ * column-major (Ni*Nj) x (Ni*Nj) matrix ktei(kk*Ni + jj, ll*Ni + ii) (utils::exchange_tei), concatenated in flat
+ * order; count = total number of doubles.  pref[L] of the tables must already be 4 pi mu/(2L+1). */
+int hfq_tables_set_pair_tensors(hfq_tables *t, const double *ktei, int64_t count);
+/* copy one pair tensor out in the same layout; returns its number of doubles (0 if the tables have none) */
+int64_t hfq_tables_get_pair_tensor(const hfq_tables *t, int L, int iel, int jel, double *out, int64_t cap);
+/* Phi_L(Xi, xi) of the erfc expansion (erfc_expn::Phi, libhelfem/src/erfc_expn.cpp:225-235) */
+double hfq_erfc_phi(int L, double Xi, double xi);
 
 /* Spherically averaged atom: sadatom::basis::TwoDBasis ctor + compute_tei()
  * (src/sadatom/basis.cpp:50-184).  One angular function per l = 0..lmax; matrices passed to

@@ -185,6 +185,39 @@ class RadialBasis:
             f = lambda r: bessel_kl(r * lam, L)
         return self.fem.matrix_element_auto(iel, self._B(0), self._B(0), f)
 
+    def erfc_integral(self, L, mu, iel, kel):
+        """RadialBasis.cpp:742-810 + quadrature.cpp:201-249: dense (pair in iel) x (pair in kel) tensor of the
+        erfc Green's function Phi_L(mu r, mu r'); fixed rule, Nq sub-intervals in r' across the cusp when
+        iel == kel, symmetrised there.  Pair index fi*N+fj (make_bfprod, quadrature.cpp:126-133)."""
+        from . import erfc as erfc_mod
+        x0 = self.fem.x0
+        Nq = len(self.xq)
+        xi, wi = fem.chebyshev(Nq)
+        Nint = Nq if iel == kel else 1
+        xk = np.empty(Nq * Nint); wk = np.empty(Nq * Nint)
+        for ii in range(Nint):
+            istart = ii * 2.0 / Nint - 1.0
+            iend = (ii + 1) * 2.0 / Nint - 1.0
+            imid, ilen = 0.5 * (iend + istart), 0.5 * (iend - istart)
+            xk[ii * Nq:(ii + 1) * Nq] = imid + xi * ilen
+            wk[ii * Nq:(ii + 1) * Nq] = wi * ilen
+        ibf = fem.lip_eval(xi, x0, 0)[:, self.fem.enabled(iel)]
+        kbf = fem.lip_eval(xk, x0, 0)[:, self.fem.enabled(kel)]
+        rmini, rmaxi = self.fem.begin(iel), self.fem.end(iel)
+        rmink, rmaxk = self.fem.begin(kel), self.fem.end(kel)
+        rmidi, rleni = 0.5 * (rmaxi + rmini), 0.5 * (rmaxi - rmini)
+        rmidk, rlenk = 0.5 * (rmaxk + rmink), 0.5 * (rmaxk - rmink)
+        ri = rmidi + rleni * xi
+        rk = rmidk + rlenk * xk
+        Fn = erfc_mod.Phi(L, mu * ri[:, None], mu * rk[None, :])
+        ni, nk = ibf.shape[1], kbf.shape[1]
+        bpi = (ibf[:, :, None] * ibf[:, None, :]).reshape(len(xi), ni * ni) * (wi * rleni)[:, None]
+        bpk = (kbf[:, :, None] * kbf[:, None, :]).reshape(len(xk), nk * nk) * (wk * rlenk)[:, None]
+        tei = bpi.T @ Fn @ bpk
+        if iel == kel:
+            tei = 0.5 * (tei + tei.T)
+        return tei
+
     def twoe_integral_cholesky(self, L, iel, tol=1e-12):
         return pivoted_cholesky(self.twoe_integral(L, iel), tol)
 
@@ -244,6 +277,7 @@ class TwoDBasis:
         N_L = 2 * int(self.lval.max()) + 1
         Nel = self.radial.Nel()
         self.lam = lam
+        self.yukawa = True
         self.disjoint_iL = [None] * (N_L * Nel); self.disjoint_kL = [None] * (N_L * Nel); self.rs_chol = [None] * (N_L * Nel)
         for L in range(N_L):
             for iel in range(Nel):
@@ -252,9 +286,49 @@ class TwoDBasis:
                     self.disjoint_kL[L * Nel + iel] = self.radial.bessel_integral("k", L, lam, iel)
                 self.rs_chol[L * Nel + iel] = pivoted_cholesky(self.radial.yukawa_integral(L, lam, iel), 1e-12)
 
+    def compute_erfc(self, mu):
+        """TwoDBasis.cpp:762-771 + CoulombExchangeFE.h:275-297: dense exchange-ordered pair tensors
+        rs_ktei[L*Nel*Nel + iel*Nel + jel] = exchange_tei(erfc_integral(L, mu, iel, jel)) (utils.cpp:55-80:
+        ktei[kk*Ni + jj, ll*Ni + ii] = tei[jj*Ni + ii, ll*Nj + kk])."""
+        N_L = 2 * int(self.lval.max()) + 1
+        Nel = self.radial.Nel()
+        self.lam = mu
+        self.yukawa = False
+        self.rs_ktei = [None] * (N_L * Nel * Nel)
+        for L in range(N_L):
+            for iel in range(Nel):
+                Ni = self.radial.Nprim(iel)
+                for jel in range(Nel):
+                    Nj = self.radial.Nprim(jel)
+                    tei = self.radial.erfc_integral(L, mu, iel, jel).reshape(Ni, Ni, Nj, Nj)   # [jj, ii, ll, kk]
+                    # ktei[(kk, jj), (ll, ii)], row index kk*Ni + jj, column index ll*Ni + ii
+                    self.rs_ktei[(L * Nel + iel) * Nel + jel] = tei.transpose(3, 0, 2, 1).reshape(Nj * Ni, Nj * Ni)
+
+    def _assemble_K_pairwise(self, L, P):
+        """CoulombExchangeFE.h:396-422."""
+        Nel = self.radial.Nel()
+        K = np.zeros_like(P)
+        for iel in range(Nel):
+            a, b = self.radial.get_idx(iel)
+            Ni = b - a + 1
+            for jel in range(Nel):
+                c, d = self.radial.get_idx(jel)
+                Nj = d - c + 1
+                Psub = P[a:b + 1, c:d + 1]
+                Kv = self.rs_ktei[(L * Nel + iel) * Nel + jel] @ Psub.reshape(-1, order="F")
+                K[a:b + 1, c:d + 1] += Kv.reshape(Ni, Nj, order="F")
+        return K
+
     def rs_exchange(self, P):
-        """TwoDBasis.cpp:1001-1131, Yukawa branch: same loops as exchange() with the screened caches
-        and prefactor 4 pi lambda."""
+        """TwoDBasis.cpp:1001-1131.  Yukawa branch: same loops as exchange() with the screened caches and
+        prefactor 4 pi lambda; erfc branch: prefactor 4 pi mu / (2L+1) and the pairwise assembler."""
+        if getattr(self, "yukawa", True) is False:
+            save_K = self._assemble_K
+            self._assemble_K = self._assemble_K_pairwise
+            try:
+                return self.exchange(P, Lfac=lambda L: 4.0 * np.pi * self.lam / (2 * L + 1))
+            finally:
+                self._assemble_K = save_K
         save = (self.disjoint_L, self.disjoint_m1L, self.prim_chol)
         self.disjoint_L, self.disjoint_m1L, self.prim_chol = self.disjoint_iL, self.disjoint_kL, self.rs_chol
         try:

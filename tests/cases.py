@@ -27,7 +27,7 @@ def oracle_diatomic(Z1, Z2, Rbond, lmax_per_m, nelem, nnodes=15, Rmax=40.0, igri
     return b
 
 
-def tables_from_oracle_atomic(hb, b):
+def tables_from_oracle_atomic(hb, b, pref=None):
     """Hand the ORACLE's caches to the product through hfq_tables_from_arrays."""
     Nel = b.radial.Nel()
     blocks = []
@@ -41,7 +41,8 @@ def tables_from_oracle_atomic(hb, b):
             blocks.append(([sm], [bg], Bf, np.ones(Bf.shape[1])))
     efirst = [b.radial.get_idx(e)[0] for e in range(Nel)]
     en = [b.radial.Nprim(e) for e in range(Nel)]
-    pref = [4 * np.pi / (2 * L + 1) for L in range(b.N_L)]
+    if pref is None:
+        pref = [4 * np.pi / (2 * L + 1) for L in range(b.N_L)]
     return hb.Tables.from_arrays(0, b.Nrad(), efirst, en, b.lval, b.mval, list(range(b.N_L)), [-1] * b.N_L, pref, blocks)
 
 

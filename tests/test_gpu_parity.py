@@ -262,6 +262,41 @@ def test_atomic_rs_exchange_yukawa(hb):
             assert np.abs(W - Wo).max() <= 1e-10 * np.abs(Wo).max()
 
 
+def test_atomic_rs_exchange_erfc(hb):
+    """Range-separated exchange with the erfc kernel (CAM / omega-B97 type functionals): compute_erfc +
+    rs_exchange, src/atomic/TwoDBasis.cpp:762-771, :1001-1131 (erfc branch), dense pair tensors for every
+    element pair (CoulombExchangeFE.h:275-297, :396-422)."""
+    mu = 0.3
+    ob = cases.oracle_atomic(4, 2, 1, 3)
+    ob.compute_erfc(mu)
+    n = ob.Nbf()
+    Nel = ob.radial.Nel()
+    rng = np.random.default_rng(8)
+    Psym = cases.random_density(n, 3, 43, cases.m_blocks(ob.mval, ob.Nrad(), False))
+    Pdense = cases.random_density(n, 4, 44)
+    Pgen = rng.standard_normal((n, n))                       # non-symmetric: general (full storage) path
+    # (a) the oracle's rs_ktei handed over: isolates the GPU contraction
+    pref = [4 * np.pi * mu / (2 * L + 1) for L in range(ob.N_L)]
+    T = cases.tables_from_oracle_atomic(hb, ob, pref=pref).set_pair_tensors(ob.rs_ktei)
+    basis = hb.TablesBasis(T)
+    for P in (Psym, Pdense, Pgen):
+        assert cases.relerr(basis.exchange(P), ob.rs_exchange(P)) < TOL
+    with pytest.raises(ValueError):
+        basis.coulomb(Psym)                                  # no range-separated Coulomb build in the reference
+    # (b) the product's own compute_erfc (Phi, quadrature, pair tensors) end to end
+    own = hb.AtomicTwoDBasis(4, 2, 1, 3).compute_tei().compute_erfc(mu)
+    To = own._rs.tables
+    for L in range(ob.N_L):
+        for ie in range(Nel):
+            for je in range(Nel):
+                a, b = To.pair_tensor(L, ie, je), ob.rs_ktei[(L * Nel + ie) * Nel + je]
+                assert np.abs(a - b).max() <= 1e-12 * np.abs(b).max()
+    for P in (Psym, Pgen):
+        assert cases.relerr(own.rs_exchange(P), ob.rs_exchange(P)) < 1e-11
+    # attenuated exchange is weaker than the bare one
+    assert np.linalg.norm(own.rs_exchange(Psym)) < np.linalg.norm(own.exchange(Psym))
+
+
 def test_fused_host_speculative_upload(hb):
     """hfq_coulomb_exchange with page-locked buffers: the second call with the same block structure runs on
     the predicted sparse upload (verified against the full one on the device), a call whose structure grew

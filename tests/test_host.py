@@ -103,3 +103,25 @@ def test_product_does_not_touch_the_oracle():
             if f.endswith((".py", ".cpp", ".cu", ".h", ".cuh")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "oracle" not in txt.replace("the oracle", "").lower() or f == "__init__.py" and "oracle" not in txt, f
+
+
+def test_erfc_host_setup_matches_oracle(hb):
+    """Product's Phi and compute_erfc pair tensors (host C++) against the oracle."""
+    from oracle import erfc
+    rng = np.random.default_rng(3)
+    L = hb.lib()
+    for n in range(5):
+        for scale in (0.05, 0.5, 2.0, 6.0):
+            Xi, xi = rng.uniform(0, scale, 200), rng.uniform(0, scale, 200)
+            got = np.array([L.hfq_erfc_phi(n, float(a), float(b)) for a, b in zip(Xi, xi)])
+            ref = erfc.Phi(n, Xi, xi)
+            assert np.all(np.abs(got - ref) <= 1e-13 * np.abs(ref) + 2e-12)
+    ob = cases.oracle_atomic(4, 1, 1, 2)
+    ob.compute_erfc(0.3)
+    T = hb.Tables.atomic_erfc(4, 1, 1, 2, mu=0.3)
+    Nel = 2
+    for Lq in range(3):
+        for ie in range(Nel):
+            for je in range(Nel):
+                a, b = T.pair_tensor(Lq, ie, je), ob.rs_ktei[(Lq * Nel + ie) * Nel + je]
+                assert np.abs(a - b).max() <= 1e-12 * np.abs(b).max()

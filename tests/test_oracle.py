@@ -119,3 +119,62 @@ def test_c_oracle_matches_numpy_oracle():
     P = cases.random_density(ob.Nbf(), 4, 22)
     assert cases.relerr(C.exchange(P), ob.exchange(P)) < 1e-13
     assert cases.relerr(C.coulomb(P), ob.coulomb(P)) < 1e-13
+
+
+def _phi_tolerance(ref):
+    # the closed form cancels catastrophically next to the switch-over (x ~ 0.4, large X, high L): libm
+    # (reference) and numpy/scipy (oracle) exp/erfc differ by an ulp there, amplified ~1e7 x
+    return 1e-13 * np.abs(ref) + 2e-12
+
+
+def test_erfc_phi_against_reference_values():
+    """oracle.erfc.Phi against golden values produced by the reference's own erfc_expn.cpp
+    (tests/golden/make_erfc_golden.py), including the reference's binomial convention in the small-argument
+    series (erfc_expn.cpp:42-64), which differs from the exact expansion by ~2e-5."""
+    from oracle import erfc
+    g = json.load(open(os.path.join(HERE, "golden", "erfc_phi_ref.json")))
+    rows = g["rows"]
+    assert len(rows) >= 600
+    for n in sorted(set(r[0] for r in rows)):
+        sel = [r for r in rows if r[0] == n]
+        Xi = np.array([float.fromhex(r[1]) for r in sel])
+        xi = np.array([float.fromhex(r[2]) for r in sel])
+        ref = np.array([float.fromhex(r[3]) for r in sel])
+        got = erfc.Phi(n, Xi, xi)
+        assert np.all(np.abs(got - ref) <= _phi_tolerance(ref)), n
+        well = (np.minimum(Xi, xi) < 0.39) | (np.maximum(Xi, xi) < 1.0)     # series branch / benign closed form
+        assert np.all(np.abs(got - ref)[well] <= 1e-13 * np.abs(ref[well]) + 1e-300), n
+
+
+def test_erfc_phi_against_reference_build():
+    so = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "liberfc_ref.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    import ctypes
+    from oracle import erfc
+    lib = ctypes.CDLL(so)
+    rng = np.random.default_rng(5)
+    vp = ctypes.c_void_p
+    for n in range(5):
+        Xi, xi = rng.uniform(0, 3.0, 2000), rng.uniform(0, 3.0, 2000)
+        ref = np.empty_like(Xi)
+        assert lib.ref_erfc_phi(ref.ctypes.data_as(vp), ctypes.c_uint(n), Xi.ctypes.data_as(vp), xi.ctypes.data_as(vp),
+                                ctypes.c_long(len(Xi))) == 0
+        assert np.all(np.abs(erfc.Phi(n, Xi, xi) - ref) <= _phi_tolerance(ref))
+
+
+def test_erfc_exchange_small_mu_limit():
+    """erfc(mu r)/r = 1/r - 2 mu/sqrt(pi) + O(mu^3 r^2): the oracle's erfc rs_exchange tends to the bare
+    exchange plus (2 mu/sqrt(pi)) S P S (exchange() returns -K).  Ties Phi, the cusp quadrature
+    (RadialBasis.cpp:742-810) and the pairwise assembler together against the independently pinned bare K."""
+    from tests import cases
+    ob = cases.oracle_atomic(4, 1, 1, 2)
+    n = ob.Nbf()
+    P = cases.random_density(n, 3, 41, cases.m_blocks(ob.mval, ob.Nrad(), False))
+    K0 = ob.exchange(P)
+    S = ob.overlap()
+    mu = 1e-4
+    ob.compute_erfc(mu)
+    K1 = ob.rs_exchange(P)
+    resid = K1 - K0 - 2 * mu / np.sqrt(np.pi) * S @ P @ S
+    assert np.abs(resid).max() < 2e-6 * np.abs(K0).max()
