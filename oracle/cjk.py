@@ -139,3 +139,47 @@ class DiatomicCaches:
         """From the product's exported tables (identical inputs for the CPU baseline)."""
         blocks = [T.block(ilm, e) for ilm in range(T.nlm) for e in range(T.Nel)]
         return cls(T.Nrad, T.efirst, T.en, T.lval, T.mval, T.lmL, T.lmM, T.pref, blocks)
+
+
+class AtomicCaches:
+    """Flat caches of the atomic basis for the C oracle (jk_atomic_exchange_blocks: TwoDBasis.cpp:879-999,
+    CoulombExchangeFE.h:484-530).  blocks[L*Nel+iel] = (small(1,n,n), big(1,n,n), chol, sigma)."""
+
+    def __init__(self, Nrad, efirst, en, lval, mval, blocks):
+        self.Nrad, self.efirst, self.en = int(Nrad), _i(efirst), _i(en)
+        self.lval, self.mval = _i(lval), _i(mval)
+        self.Nang, self.Nel = len(self.lval), len(self.en)
+        self.NL = len(blocks) // self.Nel
+        self.small, self._k0 = _ptrs([b[0][0] for b in blocks])
+        self.big, self._k1 = _ptrs([b[1][0] for b in blocks])
+        self.chol, self._k2 = _ptrs([b[2] for b in blocks])
+        self.rank = _i([b[2].shape[1] for b in blocks])
+        _, g2 = _gaunt.coupling_tables(self.lval, self.mval, self.NL, False)
+        self.g2 = np.ascontiguousarray(g2)
+
+    @classmethod
+    def from_tables(cls, T):
+        blocks = [T.block(L, e) for L in range(T.nlm) for e in range(T.Nel)]
+        return cls(T.Nrad, T.efirst, T.en, T.lval, T.mval, blocks)
+
+    def exchange_blocks(self, P, jangs, kangs):
+        Pd = np.asfortranarray(P)
+        jangs, kangs = _i(jangs), _i(kangs)
+        out = np.zeros((len(jangs), self.Nrad, self.Nrad))
+        v = ctypes.c_void_p
+        lib().jk_atomic_exchange_blocks(
+            self.Nang, self.Nrad, self.Nel, self.NL, v(self.efirst.ctypes.data), v(self.en.ctypes.data),
+            v(self.lval.ctypes.data), v(self.mval.ctypes.data), v(self.g2.ctypes.data), self.small, self.big, self.chol,
+            v(self.rank.ctypes.data), v(Pd.ctypes.data), len(jangs), v(jangs.ctypes.data), v(kangs.ctypes.data),
+            v(out.ctypes.data))
+        return np.transpose(out, (0, 2, 1))
+
+    def exchange(self, P):
+        na, N = self.Nang, self.Nrad
+        ja = [j for j in range(na) for k in range(na)]
+        ka = [k for j in range(na) for k in range(na)]
+        blk = self.exchange_blocks(P, ja, ka)
+        K = np.zeros((na * N, na * N))
+        for b, (j, k) in enumerate(zip(ja, ka)):
+            K[j * N:(j + 1) * N, k * N:(k + 1) * N] = blk[b]
+        return K
