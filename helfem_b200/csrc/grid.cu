@@ -351,7 +351,7 @@ void GridEngine::density(const double *Pa, int64_t ldPa, const double *Pb, int64
     const double *P = sp ? Pb : Pa;
     const int64_t ld = sp ? ldPb : ldPa;
     double *dP = s.d_P.p + (size_t)sp * n * n;
-    CK(cudaMemcpy2DAsync(dP, n * sizeof(double), P, ld * sizeof(double), n * sizeof(double), n, cudaMemcpyHostToDevice, s.st));
+    CK(cudaMemcpy2DAsync(dP, n * sizeof(double), P, ld * sizeof(double), n * sizeof(double), n, cudaMemcpyDefault, s.st));
     double *Pe = s.d_Pe.p + (size_t)sp * g.Nel * g.NA2 * g.NN;
     k_grid_pack<<<dim3(g.Nel, g.NA2), 128, 0, s.st>>>(g, dP, (int64_t)n, Pe);
     CK(cudaGetLastError());
@@ -411,7 +411,7 @@ void GridEngine::density(const double *Pa, int64_t ldPa, const double *Pb, int64
   auto out = [&](double *host, const double *a, const double *b, const double *c, int nc) {
     if (!host) return;
     k_interleave<<<592, 256, 0, s.st>>>(a, b, c, nc, N, s.d_io.p);
-    CK(cudaMemcpyAsync(host, s.d_io.p, (size_t)nc * N * sizeof(double), cudaMemcpyDeviceToHost, s.st));
+    CK(cudaMemcpyAsync(host, s.d_io.p, (size_t)nc * N * sizeof(double), cudaMemcpyDefault, s.st));
     CK(cudaStreamSynchronize(s.st));
   };
   out(rho, s.dens(0, 0), s.dens(1, 0), nullptr, nspin);
@@ -422,7 +422,7 @@ void GridEngine::density(const double *Pa, int64_t ldPa, const double *Pb, int64
   }
   if ((flags & (GRID_TAU | GRID_LAPL)) && tau) out(tau, s.dens(0, 4), s.dens(1, 4), nullptr, nspin);
   if ((flags & GRID_LAPL) && lapl) out(lapl, s.dens(0, 5), s.dens(1, 5), nullptr, nspin);
-  if (weights) CK(cudaMemcpyAsync(weights, s.d_w.p, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, s.st));
+  if (weights) CK(cudaMemcpyAsync(weights, s.d_w.p, (size_t)N * sizeof(double), cudaMemcpyDefault, s.st));
   double sums[4];
   CK(cudaMemcpyAsync(sums, s.d_sums.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, s.st));
   CK(cudaStreamSynchronize(s.st));
@@ -443,7 +443,7 @@ void GridEngine::fxc(int flags, bool beta, const double *exc, const double *vrho
   // device copies of the functional output, de-interleaved: v[0..1] vrho, v[2..4] vsigma, v[5..6] vtau, v[7..8] vlapl, v[9] exc
   auto put = [&](const double *host, int nc, int slot0) {
     if (!host) return;
-    CK(cudaMemcpyAsync(s.d_io.p, host, (size_t)nc * N * sizeof(double), cudaMemcpyHostToDevice, s.st));
+    CK(cudaMemcpyAsync(s.d_io.p, host, (size_t)nc * N * sizeof(double), cudaMemcpyDefault, s.st));
     for (int c = 0; c < nc; c++) k_deinterleave<<<592, 256, 0, s.st>>>(s.d_io.p, nc, c, N, s.d_v.p + (size_t)(slot0 + c) * N);
     CK(cudaStreamSynchronize(s.st));
   };
@@ -527,7 +527,7 @@ void GridEngine::fxc(int flags, bool beta, const double *exc, const double *vrho
     CK(cudaGetLastError());
     double *H = sp ? Hb : Ha;
     const int64_t ld = sp ? ldHb : ldHa;
-    CK(cudaMemcpy2DAsync(H, ld * sizeof(double), s.d_H.p, n * sizeof(double), n * sizeof(double), n, cudaMemcpyDeviceToHost, s.st));
+    CK(cudaMemcpy2DAsync(H, ld * sizeof(double), s.d_H.p, n * sizeof(double), n * sizeof(double), n, cudaMemcpyDefault, s.st));
     CK(cudaStreamSynchronize(s.st));
   }
   if (exc && Exc) {

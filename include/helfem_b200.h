@@ -163,7 +163,10 @@ int hfq_coulomb_exchange_device(hfq_ctx *ctx, const double *dP, int64_t ldP, dou
  * functional, the GPU assembles the matrix.  Point p = (element, angular point, radial point);
  * spin components are interleaved per point exactly as libxc expects them
  * (src/general/dftgrid_common.cpp:60-73): rho[p*ns + s], sigma[p*3 + {aa,ab,bb}] (1 component if
- * restricted), tau, lapl like rho.  flags: 1 gradient, 2 tau, 4 Laplacian. */
+ * restricted), tau, lapl like rho.  flags: 1 gradient, 2 tau, 4 Laplacian.
+ * The matrix and per-point array arguments (P, H, rho .. weights, exc .. vlapl) may be host OR device
+ * pointers (copies use cudaMemcpyDefault): with P and H resident on the device a call moves no matrix
+ * over PCIe.  Scalars (Nel, Ekin, Exc) are host pointers. */
 /* atomic basis: DFTGrid(&basis, ldft, mdft) (src/atomic/dftgrid.h:139).  Diatomic basis: mang <= 1 ->
  * PureMDFTGrid(&basis, ldft) (src/diatomic/dftgrid_purem.h, phi analytic, used at --symmetry >= 1);
  * mang >= 2 -> the general 3D DFTGrid(&basis, ldft, mdft) of src/diatomic/dftgrid.h (no Laplacian). */

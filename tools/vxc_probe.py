@@ -33,3 +33,15 @@ for flags, name in ((0, "LDA"), (1, "GGA"), (7, "meta-GGA+lapl")):
                                  p(vl) if flags & 4 else None, p(hH), n, None, n, ctypes.byref(Exc)))
         t2 = time.perf_counter()
     print("%s: Nbf %d points %d  density %.1f ms  fxc %.1f ms  Nel %.6f" % (name, n, N, 1e3 * (t1 - t0), 1e3 * (t2 - t1), nel.value))
+    # the same with every matrix / point array resident on the device
+    dP, dH = hP.cuda(), torch.empty((n, n), dtype=torch.float64, device="cuda")
+    d = {k: v.cuda() for k, v in dict(rho=rho, sig=sig, tau=tau, lap=lap, w=w, exc=exc, vrho=vrho, vs=vs, vt=vt, vl=vl).items()}
+    for it in range(4):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        hb._check(L.hfq_grid_density(ctx, p(dP), n, None, n, flags, p(d["rho"]), p(d["sig"]), p(d["tau"]), p(d["lap"]), p(d["w"]), ctypes.byref(nel), ctypes.byref(ekin)))
+        t1 = time.perf_counter()
+        hb._check(L.hfq_grid_fxc(ctx, flags, 1, p(d["exc"]), p(d["vrho"]), p(d["vs"]) if flags & 1 else None, p(d["vt"]) if flags & 2 else None,
+                                 p(d["vl"]) if flags & 4 else None, p(dH), n, None, n, ctypes.byref(Exc)))
+        torch.cuda.synchronize(); t2 = time.perf_counter()
+    err = float((dH.cpu() - hH).abs().max() / hH.abs().max())
+    print("   device-resident: density %.2f ms  fxc %.2f ms  (H vs host-path %.1e)" % (1e3 * (t1 - t0), 1e3 * (t2 - t1), err))
