@@ -464,6 +464,43 @@ class SadatomTwoDBasis:
         return [np.array(K[l * N:(l + 1) * N, l * N:(l + 1) * N]) for l in range(self.lmax + 1)]
 
 
+class SadatomDFTGrid:
+    """helfem::sadatom::dftgrid::DFTGrid (src/sadatom/dftgrid.h:124,127): radial-only quadrature of the spherically
+    averaged atom.  Densities and Fock matrices are per-l cubes (lists of Nrad x Nrad matrices)."""
+
+    def __init__(self, basis):
+        self.basis = basis
+        self._g = DFTGrid(basis._k, 1, 1)
+        self.N = self._g.N
+
+    def _dense(self, cube):
+        N, L = self.basis.Nrad(), self.basis.lmax + 1
+        if len(cube) != L:
+            raise ValueError("Density matrix am does not match basis set!")
+        P = np.zeros((L * N, L * N), order="F")
+        for l, Pl in enumerate(cube):
+            P[l * N:(l + 1) * N, l * N:(l + 1) * N] = np.asarray(Pl)
+        return P
+
+    def _cube(self, H):
+        N, L = self.basis.Nrad(), self.basis.lmax + 1
+        return [np.array(H[l * N:(l + 1) * N, l * N:(l + 1) * N]) for l in range(L)]
+
+    def density(self, Pa, Pb=None, flags=0):
+        return self._g.density(self._dense(Pa), None if Pb is None else self._dense(Pb), flags)
+
+    def fxc(self, exc, vrho, vsigma=None, vtau=None, vlapl=None, beta=True):
+        Ha, Hb, e = self._g.fxc(exc, vrho, vsigma, vtau, vlapl, beta)
+        return self._cube(Ha), (None if Hb is None else self._cube(Hb)), e
+
+    def eval_Fxc(self, x_func, c_func, P, Pb=None, beta=True, thr=1e-12):
+        """(H cube or (Ha, Hb), Exc, Nel) as src/sadatom/dftgrid.cpp:505-653 (built-in Slater exchange only)."""
+        H, exc, nel, _ = self._g.eval_Fxc(x_func, c_func, self._dense(P), None if Pb is None else self._dense(Pb), beta, thr)
+        if Pb is None:
+            return self._cube(H), exc, nel
+        return (self._cube(H[0]), self._cube(H[1])), exc, nel
+
+
 class TablesBasis(_BasisBase):
     """A basis whose caches were produced elsewhere (e.g. by an existing HelFEM build)."""
 

@@ -434,8 +434,9 @@ int hfq_grid_attach(hfq_ctx *ctx, int lang, int mang) {
     const hfq::BasisTables &bt = ctx->eng->tables();
     // atomic: 3D grid; diatomic: mang <= 1 selects the pure-m grid the reference uses at --symmetry >= 1,
     // mang >= 2 the general 3D grid of --symmetry=0
-    const hfq::GridTables g = bt.kind == hfq::BasisKind::Atomic ? hfq::build_atomic_grid(bt, lang, mang)
-                                                                 : hfq::build_diatomic_grid(bt, lang, mang);
+    const hfq::GridTables g = bt.kind == hfq::BasisKind::Atomic    ? hfq::build_atomic_grid(bt, lang, mang)
+                              : bt.kind == hfq::BasisKind::Sadatom ? hfq::build_sadatom_grid(bt)
+                                                                   : hfq::build_diatomic_grid(bt, lang, mang);
     ctx->grid = std::make_unique<hfq::GridEngine>(ctx->eng->tables(), g, ctx->eng->device(), ctx->eng->stream());
     return HFQ_OK;
   });

@@ -57,6 +57,7 @@ struct GridDev {
   const double *w;       // [N] total quadrature weight
   const double *sc;      // [3][N] scale factors of the three orthogonal directions
   const double *lfac;    // [N] prefactor of the Laplacian
+  int clamp1;            // tau: theta-direction term clamped at zero (spherically averaged atom)
 };
 
 // Pe[e][(a,b)][(r,c)] = P[(a, f+r), (b, f+c)]     grid (Nel, NA2)
@@ -89,10 +90,16 @@ __global__ void k_grid_points(GridDev g, const double *__restrict__ D, int flags
       grho[2 * N + p] = 2.0 * D[3 * N + p] / sp;
     }
     if (flags & (GRID_TAU | GRID_LAPL)) {
-      const double kin = D[4 * N + p] / (s0 * s0) + D[5 * N + p] / (st * st) + D[6 * N + p] / (sp * sp);
-      tau[p] = 0.5 * kin;
-      sk += w * 0.5 * kin;
-      if (flags & GRID_LAPL) lapl[p] = 2.0 * (kin + g.lfac[p] * D[7 * N + p]);
+      const double kth = D[5 * N + p] / (st * st);
+      const double krest = D[4 * N + p] / (s0 * s0) + D[6 * N + p] / (sp * sp);
+      const double kin = krest + kth;
+      // sadatom: tau = (radial term + max(l(l+1) rho_l / r^2, 0)) / 2 (src/sadatom/dftgrid.cpp:100-107); the
+      // l(l+1) parts of the Laplacian cancel identically in the spherical average and are left out on both
+      // sides (kinetic part here, -l(l+1) f/r^2 in the angular pair table), as in the reference (:110-123)
+      const double kt = g.clamp1 ? krest + fmax(kth, 0.0) : kin;
+      tau[p] = 0.5 * kt;
+      sk += w * 0.5 * kt;
+      if (flags & GRID_LAPL) lapl[p] = 2.0 * ((g.clamp1 ? krest : kin) + g.lfac[p] * D[7 * N + p]);
     }
   }
   for (int o = 16; o > 0; o >>= 1) {
@@ -130,7 +137,8 @@ __global__ void k_grid_weights(GridDev g, int flags, const double *__restrict__ 
       if (vl) vtl += 2.0 * vl[p];
       vtl *= w;
       C[4 * N + p] = vtl / (s0 * s0);
-      C[5 * N + p] = vtl / (st * st);
+      // sadatom: the l(l+1) matrix takes the tau potential only (src/sadatom/dftgrid.cpp:311-315)
+      C[5 * N + p] = (g.clamp1 ? (vt ? 0.5 * vt[p] * w : 0.0) : vtl) / (st * st);
       C[6 * N + p] = vtl / (sp * sp);
     }
     if (vl) C[7 * N + p] = w * vl[p] * g.lfac[p];
@@ -243,7 +251,7 @@ GridEngine::GridEngine(const BasisTables &t, const GridTables &g, int device, cu
   std::vector<int> pa, pb, pof((size_t)NA * NA, -1), aoff(NA), askip(NA);
   for (int a = 0; a < NA; a++)
     for (int b = 0; b < NA; b++)
-      if (!g.pure_m || t.mval[a] == t.mval[b]) {
+      if ((!g.pure_m || t.mval[a] == t.mval[b]) && (!g.same_l_only || a == b)) {
         pof[(size_t)a * NA + b] = (int)pa.size();
         pa.push_back(a);
         pb.push_back(b);
@@ -297,7 +305,8 @@ GridEngine::GridEngine(const BasisTables &t, const GridTables &g, int device, cu
         const double ma = t.mval[a], mb = t.mval[b], la = t.lval[a];
         const std::complex<double> cyy = std::conj(ya) * yb;
         const double v[NYY] = {cyy.real(), (std::conj(ta) * yb).real(), ma * cyy.imag(), (std::conj(ta) * tb).real(),
-                               ma * mb * cyy.real(), -la * (la + 1.0) * cyy.real(), -ma * ma * cyy.real()};
+                               ma * mb * cyy.real(), g.same_l_only ? 0.0 : -la * (la + 1.0) * cyy.real(),
+                               -ma * ma * cyy.real()};
         for (int ty = 0; ty < NYY; ty++) {
           YY[((size_t)ty * NA2 + ab) * nang + ia] = v[ty];
           YYT[((size_t)ty * nang + ia) * NA2 + ab] = v[ty];
@@ -315,7 +324,8 @@ GridEngine::GridEngine(const BasisTables &t, const GridTables &g, int device, cu
     s.d_bo_t.upload(bot);
   }
   s.gd = GridDev{Nel, NA, NA2, NI, NN, nang, nrad, t.Nrad, (int64_t)nang * nrad, s.d_efirst.p, s.d_en.p,
-                 s.d_pa.p, s.d_pb.p, s.d_pof.p, s.d_aoff.p, s.d_askip.p, s.d_w.p, s.d_sc.p, s.d_lfac.p};
+                 s.d_pa.p, s.d_pb.p, s.d_pof.p, s.d_aoff.p, s.d_askip.p, s.d_w.p, s.d_sc.p, s.d_lfac.p,
+                 g.clamp_theta_kin ? 1 : 0};
   s.d_P.alloc((size_t)2 * s.nbf * s.nbf);
   s.d_H.alloc((size_t)s.nbf * s.nbf);
   s.d_Pe.alloc((size_t)2 * Nel * NA2 * NN);

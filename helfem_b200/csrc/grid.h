@@ -24,6 +24,8 @@ namespace hfq {
 struct GridTables {
   int lang = 0, mang = 0, nang = 0, nrad = 0, Nel = 0, Nang = 0, NI = 0;
   bool pure_m = false;                             // only same-m pairs couple (phi integrated analytically)
+  bool same_l_only = false;                        // only a == b couples (spherically averaged atom: per-l cube)
+  bool clamp_theta_kin = false;                    // tau: max(theta-direction term, 0) (src/sadatom/dftgrid.cpp:106)
   std::vector<double> cth, phi, wang;              // [nang]
   std::vector<double> r, wrad;                     // [Nel*nrad]
   std::vector<double> wtot, scale[3], lfac;        // [N] per point
@@ -35,6 +37,11 @@ struct GridTables {
 
 // atomic 3D grid (src/atomic/dftgrid.cpp), r x theta x phi
 GridTables build_atomic_grid(const BasisTables &t, int lang, int mang);
+// spherically averaged atom (src/sadatom/dftgrid.cpp:45-125, :256-328, :464-486): radial points only, weight
+// 4 pi w_r r^2, one "angular function" per l with Y = 1 and a theta-direction table i sqrt(l(l+1)), which
+// reproduces the l(l+1) rho_l / r^2 term of tau and its Fock contribution while adding nothing to grad rho;
+// the l(l+1) parts of the Laplacian cancel identically, as they do in the reference's formula
+GridTables build_sadatom_grid(const BasisTables &t);
 // diatomic grids: mang <= 1 -> pure-m 2D grid (src/diatomic/dftgrid_purem.cpp, mu x nu, phi analytic),
 // mang >= 2 -> general 3D grid (src/diatomic/dftgrid.cpp)
 GridTables build_diatomic_grid(const BasisTables &t, int lang, int mang);

@@ -22,44 +22,9 @@ static std::complex<double> ylm(int l, int m, double cth, double phi) {
   return std::polar(1.0, m * phi) * std::sph_legendre((unsigned)l, (unsigned)m, std::acos(cth));
 }
 
-GridTables build_atomic_grid(const BasisTables &t, int lang, int mang) {
-  if (t.kind != BasisKind::Atomic) throw std::logic_error("build_atomic_grid: atomic basis required");
-  if (t.bval.empty()) throw std::logic_error("build_atomic_grid: basis was not built by this library");
-  GridTables g;
-  g.lang = lang;
-  g.mang = mang;
-  g.nang = lang * mang;
-  g.nrad = t.nquad;
-  g.Nel = t.Nel;
-  g.Nang = t.Nang();
-  g.NI = 0;
-  for (int n : t.en) g.NI = std::max(g.NI, n);
-  // angular rule: Chebyshev in cos(theta) x uniform phi
-  std::vector<double> xl, wl;
-  chebyshev_rule(lang, xl, wl);
-  const double dphi = 2.0 * std::acos(-1.0) / mang;
-  for (int i = 0; i < lang; i++)
-    for (int j = 0; j < mang; j++) {
-      g.cth.push_back(xl[i]);
-      g.phi.push_back(j * dphi);
-      g.wang.push_back(wl[i] * dphi);
-    }
-  // angular functions
-  g.Y.assign((size_t)g.Nang * g.nang, 0.0);
-  g.Th.assign((size_t)g.Nang * g.nang, 0.0);
-  for (int a = 0; a < g.Nang; a++) {
-    const int l = t.lval[a], m = t.mval[a];
-    for (int ia = 0; ia < g.nang; ia++) {
-      const double c = g.cth[ia], p = g.phi[ia];
-      const double sinth = std::sqrt(std::max((1.0 - c) * (1.0 + c), 0.0));
-      const double cot = sinth > 0.0 ? c / sinth : 0.0;
-      const std::complex<double> y = ylm(l, m, c, p);
-      std::complex<double> ang = (double)m * cot * y;
-      if (m < l) ang += std::sqrt((double)(l - m) * (l + m + 1)) * std::polar(1.0, -p) * ylm(l, m + 1, c, p);
-      g.Y[(size_t)a * g.nang + ia] = y;
-      g.Th[(size_t)a * g.nang + ia] = ang;
-    }
-  }
+// radial tables of the atomic / sadatom basis at the Chebyshev nodes (RadialBasis.cpp:868-926): B/r, its first
+// derivative, radial Laplacian f'' + 2 f'/r, and f/r^2
+static void fill_atomic_radial(const BasisTables &t, GridTables &g) {
   // radial functions
   const FEBasis fe(t.nnodes, t.bval, true, true);
   std::vector<double> xq, wq;
@@ -103,6 +68,47 @@ GridTables build_atomic_grid(const BasisTables &t, int lang, int mang) {
         g.F2[o] = f(q, j) / (r[q] * r[q]);
       }
   }
+}
+
+GridTables build_atomic_grid(const BasisTables &t, int lang, int mang) {
+  if (t.kind != BasisKind::Atomic) throw std::logic_error("build_atomic_grid: atomic basis required");
+  if (t.bval.empty()) throw std::logic_error("build_atomic_grid: basis was not built by this library");
+  GridTables g;
+  g.lang = lang;
+  g.mang = mang;
+  g.nang = lang * mang;
+  g.nrad = t.nquad;
+  g.Nel = t.Nel;
+  g.Nang = t.Nang();
+  g.NI = 0;
+  for (int n : t.en) g.NI = std::max(g.NI, n);
+  // angular rule: Chebyshev in cos(theta) x uniform phi
+  std::vector<double> xl, wl;
+  chebyshev_rule(lang, xl, wl);
+  const double dphi = 2.0 * std::acos(-1.0) / mang;
+  for (int i = 0; i < lang; i++)
+    for (int j = 0; j < mang; j++) {
+      g.cth.push_back(xl[i]);
+      g.phi.push_back(j * dphi);
+      g.wang.push_back(wl[i] * dphi);
+    }
+  // angular functions
+  g.Y.assign((size_t)g.Nang * g.nang, 0.0);
+  g.Th.assign((size_t)g.Nang * g.nang, 0.0);
+  for (int a = 0; a < g.Nang; a++) {
+    const int l = t.lval[a], m = t.mval[a];
+    for (int ia = 0; ia < g.nang; ia++) {
+      const double c = g.cth[ia], p = g.phi[ia];
+      const double sinth = std::sqrt(std::max((1.0 - c) * (1.0 + c), 0.0));
+      const double cot = sinth > 0.0 ? c / sinth : 0.0;
+      const std::complex<double> y = ylm(l, m, c, p);
+      std::complex<double> ang = (double)m * cot * y;
+      if (m < l) ang += std::sqrt((double)(l - m) * (l + m + 1)) * std::polar(1.0, -p) * ylm(l, m + 1, c, p);
+      g.Y[(size_t)a * g.nang + ia] = y;
+      g.Th[(size_t)a * g.nang + ia] = ang;
+    }
+  }
+  fill_atomic_radial(t, g);
   // per-point weights and scale factors (1, r, r sin(theta)); src/atomic/dftgrid.cpp:486-512
   const size_t N = (size_t)g.Nel * g.nang * g.nrad;
   g.wtot.assign(N, 0.0);
@@ -130,6 +136,40 @@ GridTables build_atomic_grid(const BasisTables &t, int lang, int mang) {
 // mang <= 1: pure-m grid (phi analytic, real harmonics at phi = 0, weight 2 pi w_nu);
 // mang >= 2: the general 3D grid of src/diatomic/dftgrid.cpp:414-518 (complex harmonics on the
 // theta x phi compound rule, every (a,b) pair couples, no Laplacian in the reference).
+GridTables build_sadatom_grid(const BasisTables &t) {
+  if (t.kind != BasisKind::Sadatom) throw std::logic_error("build_sadatom_grid: sadatom basis required");
+  if (t.bval.empty()) throw std::logic_error("build_sadatom_grid: basis was not built by this library");
+  GridTables g;
+  g.lang = g.mang = g.nang = 1;
+  g.nrad = t.nquad;
+  g.Nel = t.Nel;
+  g.Nang = t.Nang();
+  g.NI = 0;
+  for (int n : t.en) g.NI = std::max(g.NI, n);
+  g.pure_m = true;           // both kinetic potentials enter the same term (src/sadatom/dftgrid.cpp:303, :406)
+  g.same_l_only = true;
+  g.clamp_theta_kin = true;
+  const double pi = std::acos(-1.0);
+  g.cth.push_back(1.0);
+  g.phi.push_back(0.0);
+  g.wang.push_back(4.0 * pi);
+  g.Y.assign((size_t)g.Nang, 1.0);
+  g.Th.assign((size_t)g.Nang, 0.0);
+  for (int a = 0; a < g.Nang; a++) g.Th[a] = std::complex<double>(0.0, std::sqrt((double)t.lval[a] * (t.lval[a] + 1)));
+  fill_atomic_radial(t, g);
+  const size_t N = (size_t)g.Nel * g.nrad;
+  g.wtot.resize(N);
+  for (int c = 0; c < 3; c++) g.scale[c].resize(N);
+  g.lfac.assign(N, 1.0);
+  for (size_t p = 0; p < N; p++) {
+    g.wtot[p] = 4.0 * pi * g.wrad[p] * g.r[p] * g.r[p];
+    g.scale[0][p] = 1.0;
+    g.scale[1][p] = g.r[p];
+    g.scale[2][p] = g.r[p];
+  }
+  return g;
+}
+
 GridTables build_diatomic_grid(const BasisTables &t, int lang, int mang) {
   if (t.kind != BasisKind::Diatomic) throw std::logic_error("build_diatomic_grid: diatomic basis required");
   if (t.bval.empty()) throw std::logic_error("build_diatomic_grid: basis was not built by this library");

@@ -169,7 +169,10 @@ int hfq_coulomb_exchange_device(hfq_ctx *ctx, const double *dP, int64_t ldP, dou
  * over PCIe.  Scalars (Nel, Ekin, Exc) are host pointers. */
 /* atomic basis: DFTGrid(&basis, ldft, mdft) (src/atomic/dftgrid.h:139).  Diatomic basis: mang <= 1 ->
  * PureMDFTGrid(&basis, ldft) (src/diatomic/dftgrid_purem.h, phi analytic, used at --symmetry >= 1);
- * mang >= 2 -> the general 3D DFTGrid(&basis, ldft, mdft) of src/diatomic/dftgrid.h (no Laplacian). */
+ * mang >= 2 -> the general 3D DFTGrid(&basis, ldft, mdft) of src/diatomic/dftgrid.h (no Laplacian).
+ * Sadatom basis (hfq_tables_sadatom): the radial-only grid of src/sadatom/dftgrid.h:124,127 (lang, mang ignored);
+ * matrices are the per-l cube laid out block-diagonally, (lmax+1)*Nrad square, and only the diagonal blocks
+ * of H are meaningful (src/sadatom/dftgrid.cpp:45-125, :256-328, :464-486, :505-653). */
 int hfq_grid_attach(hfq_ctx *ctx, int lang, int mang);
 int64_t hfq_grid_npoints(const hfq_ctx *ctx);
 /* DFTGridWorker::update_density + compute_Nel/compute_Ekin over all elements.  Pb == NULL: restricted.

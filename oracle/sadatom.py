@@ -40,3 +40,117 @@ class SadatomBasis:
             for L, PL in sorted(Prad.items()):
                 K[lout] -= self.b._assemble_K(L, PL)
         return K
+
+
+class SadatomDFTGrid:
+    """Radial-only DFT quadrature of the spherically averaged atom: oracle restatement of
+    src/sadatom/dftgrid.cpp (compute_bf :464-486, update_density :45-125 restricted / :127-241 unrestricted,
+    eval_Fxc :256-328 / :330-460, DFTGrid::eval_Fxc :505-653).  Densities and Fock matrices are per-l cubes
+    (lists of Nrad x Nrad matrices); point index = iel*nquad + iquad; libxc layout (point-major, spins
+    interleaved) for the per-point arrays."""
+
+    def __init__(self, atomic_basis, lmax):
+        from .dftgrid_atomic import AtomicDFTGrid
+        self.b = atomic_basis
+        self._nl = lmax + 1
+        self._rad = AtomicDFTGrid(atomic_basis, 1, 1)._radial      # RadialBasis.cpp:868-926 tables
+
+    def _el(self, iel):
+        r, wrad, f, d, l2 = self._rad(iel)
+        a, b = self.b.radial.get_idx(iel)
+        return r, wrad, 4.0 * np.pi * wrad * r * r, f.T, d.T, l2.T, a, b     # tables nbf_el x npts
+
+    def npoints(self):
+        return self.b.radial.Nel() * len(self.b.radial.xq)
+
+    def eval_density(self, Pa, Pb=None, grad=False, tau=False, lapl=False):
+        pol = Pb is not None
+        cubes = [Pa, Pb] if pol else [Pa]
+        ns = len(cubes)
+        N = self.npoints()
+        out = {"rho": np.zeros((N, ns)), "w": np.zeros(N)}
+        g = np.zeros((N, ns))
+        if tau:
+            out["tau"] = np.zeros((N, ns))
+        if lapl:
+            out["lapl"] = np.zeros((N, ns))
+            out["lapl_scale"] = np.zeros((N, ns))     # sum of |summands|: conditioning of the Laplacian sum
+        npt = len(self.b.radial.xq)
+        for iel in range(self.b.radial.Nel()):
+            r, wrad, wtot, bf, bfr, bfr2, a, b = self._el(iel)
+            sl = slice(iel * npt, (iel + 1) * npt)
+            out["w"][sl] = wtot
+            for s, cube in enumerate(cubes):
+                Pc = [np.asarray(Pl)[a:b + 1, a:b + 1] for Pl in cube]
+                P = sum(Pc)
+                Plm = sum(l * (l + 1) * Pc[l] for l in range(len(Pc)))
+                Pv = P @ bf
+                out["rho"][sl, s] = np.sum(Pv * bf, axis=0)
+                if grad:
+                    g[sl, s] = 2.0 * np.sum(Pv * bfr, axis=0)
+                if tau or lapl:
+                    Pvp = P @ bfr
+                    t1 = np.sum(Pvp * bfr, axis=0)
+                    if tau:
+                        t2 = np.sum((Plm @ bf) * bf, axis=0) / (r * r)
+                        out["tau"][sl, s] = 0.5 * (t1 + np.maximum(t2, 0.0))
+                    if lapl:
+                        t2l, t3l = 2.0 * np.sum(Pv * bfr2, axis=0), 4.0 * np.sum(Pv * bfr, axis=0) / r
+                        out["lapl"][sl, s] = 2.0 * t1 + t2l + t3l
+                        aP = np.abs(P)
+                        out["lapl_scale"][sl, s] = (2.0 * np.sum((aP @ np.abs(bfr)) * np.abs(bfr), axis=0)
+                                                    + 2.0 * np.sum((aP @ np.abs(bf)) * np.abs(bfr2), axis=0)
+                                                    + 4.0 * np.sum((aP @ np.abs(bf)) * np.abs(bfr), axis=0) / r)
+        if grad:
+            out["grho"] = g
+            out["sigma"] = (np.stack([g[:, 0] ** 2, g[:, 0] * g[:, 1], g[:, 1] ** 2], axis=1) if pol else g ** 2)
+        out["Nel"] = float(np.sum(out["w"] * out["rho"].sum(axis=1)))
+        self._g, self._pol, self._rho, self._w = g, pol, out["rho"], out["w"]
+        return out
+
+    def eval_fxc(self, exc, vrho, vsigma=None, vtau=None, vlapl=None, beta=True):
+        """Returns (Ha cube, Hb cube or None, Exc); uses the density and gradient of the last eval_density
+        call.  exc: energy density per particle, Exc = sum_p w exc rho_total (DFTGridWorkerBase::eval_Exc)."""
+        pol = self._pol
+        N = self.b.Nrad()
+        L = self._nl
+        Ha = [np.zeros((N, N)) for _ in range(L)]
+        Hb = [np.zeros((N, N)) for _ in range(L)] if (pol and beta) else None
+        npt = len(self.b.radial.xq)
+        vrho = np.asarray(vrho).reshape(self.npoints(), -1)
+        rs = lambda v: None if v is None else np.asarray(v).reshape(self.npoints(), -1)
+        vsigma, vtau, vlapl = rs(vsigma), rs(vtau), rs(vlapl)
+        for iel in range(self.b.radial.Nel()):
+            r, wrad, wtot, bf, bfr, bfr2, a, b = self._el(iel)
+            sl = slice(iel * npt, (iel + 1) * npt)
+            for s, Hc in enumerate([Ha, Hb] if pol else [Ha]):
+                if Hc is None:
+                    continue
+                H = (bf * (vrho[sl, s] * wtot)) @ bf.T
+                Hl = np.zeros_like(H)
+                if vsigma is not None:
+                    if pol:
+                        gs, go = self._g[sl, s], self._g[sl, 1 - s]
+                        gr = wtot * (2.0 * vsigma[sl, 2 * s] * gs + vsigma[sl, 1] * go)
+                    else:
+                        gr = 2.0 * wtot * vsigma[sl, 0] * self._g[sl, 0]
+                    if vlapl is not None:
+                        gr = gr + 2.0 * vlapl[sl, s] * r * (wrad * 4.0 * np.pi)
+                    X = (bfr * gr) @ bf.T            # increment_gga: H += X + X^T
+                    H += X + X.T
+                if vtau is not None or vlapl is not None:
+                    vtl = np.zeros(npt)
+                    if vtau is not None:
+                        vtl = vtl + 0.5 * vtau[sl, s]
+                    if vlapl is not None:
+                        vtl = vtl + 2.0 * vlapl[sl, s]
+                    H += (bfr * (vtl * wtot)) @ bfr.T
+                    if vtau is not None:
+                        Hl += (bf * (vtau[sl, s] * 0.5 * wrad * 4.0 * np.pi)) @ bf.T
+                    if vlapl is not None:
+                        Y = (bf * (vlapl[sl, s] * wtot)) @ bfr2.T      # increment_mgga_lapl: H += Y + Y^T
+                        H += Y + Y.T
+                for l in range(L):
+                    Hc[l][a:b + 1, a:b + 1] += H + l * (l + 1) * Hl
+        Exc = float(np.sum(self._w * np.asarray(exc).reshape(-1) * self._rho.sum(axis=1))) if exc is not None else 0.0
+        return Ha, Hb, Exc

@@ -210,3 +210,81 @@ def test_diatomic_3d_grid(hb):
     gp = hb.DFTGrid(basis, lang)          # pure-m grid on the same context replaces the 3D one
     dp_ = gp.density(Pm, None, 3)
     assert abs(d3["Nel"] - dp_["Nel"]) < 1e-9 * abs(dp_["Nel"]) and abs(d3["Ekin"] - dp_["Ekin"]) < 1e-9 * abs(dp_["Ekin"])
+
+
+def _sad_setup(hb, lmax=2, nelem=3):
+    from oracle import sadatom as osad
+    ob = cases.oracle_atomic(10, lmax, 0, nelem)          # radial caches only: angular list irrelevant for the grid
+    basis = hb.SadatomTwoDBasis(10, lmax, nelem).compute_tei()
+    return ob, basis, osad.SadatomDFTGrid(ob, lmax), hb.SadatomDFTGrid(basis)
+
+
+def _sad_cube(N, lmax, seed, nocc=2):
+    rng = np.random.default_rng(seed)
+    cube = []
+    for l in range(lmax + 1):
+        Q, _ = np.linalg.qr(rng.standard_normal((N, nocc)))
+        cube.append((2 * l + 1) * Q @ Q.T)
+    return cube
+
+
+@pytest.mark.parametrize("pol", [False, True])
+def test_sadatom_grid_density(hb, pol):
+    """Radial-only grid of the spherically averaged atom, src/sadatom/dftgrid.cpp:45-241, :464-486."""
+    ob, basis, og, gg = _sad_setup(hb)
+    N = ob.Nrad()
+    Pa, Pb = _sad_cube(N, 2, 1), (_sad_cube(N, 2, 2, 1) if pol else None)
+    o = og.eval_density(Pa, Pb, True, True, True)
+    g = gg.density(Pa, Pb, 7)
+    assert gg.N == og.npoints()
+    for k in ("rho", "sigma", "tau"):
+        assert g[k].shape == o[k].shape and _rel(g[k], o[k]) < TOL, k
+    # the Laplacian sum over basis-function pairs cancels by ~5 digits next to the nucleus for these
+    # unphysical random densities (f_u f_v'' of alternating sign): parity is measured against the sum of the
+    # absolute values of the summands, the quantity any summation order is accurate to
+    assert g["lapl"].shape == o["lapl"].shape
+    assert np.all(np.abs(g["lapl"] - o["lapl"]) <= TOL * o["lapl_scale"] + 1e-300)
+    assert _rel(g["w"], o["w"]) < 1e-14
+    assert abs(g["Nel"] - o["Nel"]) < 1e-11 * abs(o["Nel"])
+
+
+@pytest.mark.parametrize("kind,pol", [("lda", False), ("gga", False), ("mgga_t", False), ("mgga_tl", False),
+                                      ("gga", True), ("mgga_tl", True)])
+def test_sadatom_grid_fxc(hb, kind, pol):
+    """Fock-cube assembly incl. the l(l+1) tau term and the Laplacian cross terms, src/sadatom/dftgrid.cpp:256-460."""
+    ob, basis, og, gg = _sad_setup(hb)
+    N = ob.Nrad()
+    Pa, Pb = _sad_cube(N, 2, 3), (_sad_cube(N, 2, 4, 1) if pol else None)
+    og.eval_density(Pa, Pb, True, True, True)
+    gg.density(Pa, Pb, 7)
+    rng = np.random.default_rng(11)
+    Np, ns = gg.N, (2 if pol else 1)
+    exc = rng.uniform(-1, 0, Np)
+    vrho = rng.uniform(-1, 0, (Np, ns))
+    vs = rng.uniform(0, 1e-2, (Np, 3 if pol else 1)) if kind != "lda" else None
+    vt = rng.uniform(0, 1e-2, (Np, ns)) if kind.startswith("mgga") else None
+    vl = rng.uniform(0, 1e-2, (Np, ns)) if kind == "mgga_tl" else None
+    Hao, Hbo, Eo = og.eval_fxc(exc, vrho, vs, vt, vl)
+    Hag, Hbg, Eg = gg.fxc(exc, vrho, vs, vt, vl)
+    for l in range(3):
+        assert _rel(Hag[l], Hao[l]) < TOL, l
+        if pol:
+            assert _rel(Hbg[l], Hbo[l]) < TOL, l
+    assert abs(Eg - Eo) < 1e-11 * abs(Eo)
+
+
+def test_sadatom_eval_fxc_slater(hb):
+    """DFTGrid::eval_Fxc with LDA exchange (the SAP functional, src/general/sap.h:40-43) for the sadatom cube."""
+    ob, basis, og, gg = _sad_setup(hb)
+    N = ob.Nrad()
+    P = _sad_cube(N, 2, 5)
+    H, Exc, Nel = gg.eval_Fxc(1, 0, P)
+    o = og.eval_density(P)
+    rho = o["rho"][:, 0]
+    cx = -0.75 * (3.0 / np.pi) ** (1.0 / 3.0)
+    exc = np.where(rho > 1e-12, cx * np.cbrt(np.maximum(rho, 0)), 0.0)
+    vrho = np.where(rho > 1e-12, 4.0 / 3.0 * cx * np.cbrt(np.maximum(rho, 0)), 0.0)
+    Ho, _, Eo = og.eval_fxc(exc, vrho[:, None])
+    assert abs(Nel - o["Nel"]) < 1e-11 * abs(o["Nel"]) and abs(Exc - Eo) < 1e-11 * abs(Eo)
+    for l in range(3):
+        assert _rel(H[l], Ho[l]) < 1e-11, l
