@@ -36,7 +36,7 @@ class _TablesInfo(ctypes.Structure):
 
 EXPORTED_SYMBOLS = [
     "hfq_last_error", "hfq_tables_atomic", "hfq_tables_atomic_yukawa", "hfq_tables_atomic_erfc",
-    "hfq_tables_set_pair_tensors", "hfq_tables_get_pair_tensor", "hfq_erfc_phi", "hfq_tables_sadatom", "hfq_tables_diatomic", "hfq_tables_from_arrays", "hfq_tables_get_info",
+    "hfq_tables_set_pair_tensors", "hfq_tables_get_pair_tensor", "hfq_erfc_phi", "hfq_tables_sadatom", "hfq_tables_sadatom_rs", "hfq_tables_diatomic", "hfq_tables_from_arrays", "hfq_tables_get_info",
     "hfq_tables_get_ints", "hfq_tables_get_doubles", "hfq_tables_get_block", "hfq_tables_one_electron",
     "hfq_tables_destroy", "hfq_create", "hfq_destroy", "hfq_nbf", "hfq_set_absm_symmetric", "hfq_coulomb",
     "hfq_exchange", "hfq_coulomb_device", "hfq_exchange_device", "hfq_last_timings", "hfq_exchange_output_pattern",
@@ -65,6 +65,7 @@ def lib():
     L.hfq_erfc_phi.argtypes = [ci, cd, cd]
     L.hfq_erfc_phi.restype = cd
     L.hfq_tables_sadatom.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ci, cd, ci, cd, ci]
+    L.hfq_tables_sadatom_rs.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ci, cd, ci, cd, ci, ci, cd]
     L.hfq_tables_diatomic.argtypes = [ctypes.POINTER(vp), ci, ci, cd, _c_int_p, ci, ci, ci, cd, ci, cd, ci]
     L.hfq_tables_from_arrays.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(_TablesDesc)]
     L.hfq_tables_get_info.argtypes = [vp, ctypes.POINTER(_TablesInfo)]
@@ -170,6 +171,12 @@ class Tables:
     def sadatom(cls, Z, lmax, nelem, nnodes=15, Rmax=40.0, igrid=4, zexp=2.0, nquad=0):
         h = ctypes.c_void_p()
         _check(lib().hfq_tables_sadatom(ctypes.byref(h), Z, lmax, nelem, nnodes, Rmax, igrid, zexp, nquad))
+        return cls(h)
+
+    @classmethod
+    def sadatom_rs(cls, Z, lmax, nelem, nnodes=15, Rmax=40.0, igrid=4, zexp=2.0, nquad=0, rs=1, param=0.4):
+        h = ctypes.c_void_p()
+        _check(lib().hfq_tables_sadatom_rs(ctypes.byref(h), Z, lmax, nelem, nnodes, Rmax, igrid, zexp, nquad, rs, param))
         return cls(h)
 
     @classmethod
@@ -448,7 +455,25 @@ class SadatomTwoDBasis:
         """J(P_in) = 4 pi J_0(P_in), src/sadatom/basis.cpp:186-207."""
         return 4.0 * np.pi * self._j.coulomb(Prad)
 
-    def exchange(self, cube):
+    def compute_yukawa(self, lam):
+        """src/sadatom/basis.cpp:154-173."""
+        self._rs = _BasisBase(self._k._device)
+        self._rs._tables = Tables.sadatom_rs(*self._args, rs=1, param=lam)
+        return self
+
+    def compute_erfc(self, mu):
+        """src/sadatom/basis.cpp:175-184."""
+        self._rs = _BasisBase(self._k._device)
+        self._rs._tables = Tables.sadatom_rs(*self._args, rs=2, param=mu)
+        return self
+
+    def rs_exchange(self, cube):
+        """src/sadatom/basis.cpp:314-420."""
+        if getattr(self, "_rs", None) is None:
+            raise ValueError("Primitive teis have not been computed!\n")
+        return self.exchange(cube, _eng=self._rs)
+
+    def exchange(self, cube, _eng=None):
         """Per-l exchange blocks (reference sign, -K), src/sadatom/basis.cpp:209-312."""
         N = self.Nrad()
         if len(cube) != self.lmax + 1:
@@ -460,7 +485,7 @@ class SadatomTwoDBasis:
             if Pl.shape != (N, N):
                 raise ValueError("Density matrix does not match basis set!")
             P[l * N:(l + 1) * N, l * N:(l + 1) * N] = Pl
-        K = self._k.exchange(P)
+        K = (_eng or self._k).exchange(P)
         return [np.array(K[l * N:(l + 1) * N, l * N:(l + 1) * N]) for l in range(self.lmax + 1)]
 
 

@@ -505,6 +505,14 @@ BasisTables build_sadatom_tables(int Z, int lmax, int nelem, int nnodes, double 
   return t;
 }
 
+BasisTables build_sadatom_rs_tables(int Z, int lmax, int nelem, int nnodes, double Rmax, int igrid, double zexp,
+                                    int nquad, int rs, double param) {
+  BasisTables t = rs == 1 ? build_atomic_yukawa_tables(Z, lmax, 0, nelem, nnodes, Rmax, igrid, zexp, nquad, param)
+                          : build_atomic_erfc_tables(Z, lmax, 0, nelem, nnodes, Rmax, igrid, zexp, nquad, param);
+  t.kind = BasisKind::Sadatom;
+  return t;
+}
+
 // ---------------------------------------------------------------------------
 // shared BasisTables helpers
 // ---------------------------------------------------------------------------

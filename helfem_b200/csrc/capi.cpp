@@ -165,6 +165,18 @@ int hfq_tables_sadatom(hfq_tables **out, int Z, int lmax, int nelem, int nnodes,
   });
 }
 
+int hfq_tables_sadatom_rs(hfq_tables **out, int Z, int lmax, int nelem, int nnodes, double Rmax, int igrid, double zexp,
+                          int nquad, int rs, double param) {
+  if (!out || lmax < 0 || nelem < 1 || nnodes < 2 || nnodes > 16 || !(Rmax > 0.0) || (rs != 1 && rs != 2) || !(param > 0.0))
+    return fail(HFQ_ERR_INVALID, "hfq_tables_sadatom_rs: invalid argument");
+  return guarded([&] {
+    auto *h = new hfq_tables;
+    h->t = hfq::build_sadatom_rs_tables(Z, lmax, nelem, nnodes, Rmax, igrid, zexp, nquad, rs, param);
+    *out = h;
+    return HFQ_OK;
+  });
+}
+
 int hfq_tables_diatomic(hfq_tables **out, int Z1, int Z2, double Rbond, const int *lmax_per_m, int nm, int nelem,
                         int nnodes, double Rmax, int igrid, double zexp, int nquad) {
   if (!out || !lmax_per_m || nm < 1 || nelem < 1 || nnodes < 2 || nnodes > 16 || !(Rbond > 0.0) || !(Rmax > 0.5 * Rbond))

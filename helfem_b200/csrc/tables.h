@@ -83,6 +83,10 @@ double erfc_phi(int n, double Xi, double xi);
 // out), same radial caches as the atomic basis; exchange couples density block l_in to output
 // block l_out through the m-averaged squared Gaunt coefficient (src/sadatom/basis.cpp:209-312)
 BasisTables build_sadatom_tables(int Z, int lmax, int nelem, int nnodes, double Rmax, int igrid, double zexp, int nquad);
+// range-separated caches of the spherically averaged atom (src/sadatom/basis.cpp:154-184): rs = 1 Yukawa
+// (param = lambda), rs = 2 erfc (param = mu); exchange() on them is sadatom rs_exchange (:314-420)
+BasisTables build_sadatom_rs_tables(int Z, int lmax, int nelem, int nnodes, double Rmax, int igrid, double zexp, int nquad,
+                                    int rs, double param);
 // diatomic: lmax_per_m[|m|], other arguments as src/diatomic/main.cpp:60-118
 BasisTables build_diatomic_tables(int Z1, int Z2, double Rbond, const std::vector<int> &lmax_per_m, int nelem,
                                   int nnodes, double Rmax, int igrid, double zexp, int nquad);

@@ -73,6 +73,12 @@ double hfq_erfc_phi(int L, double Xi, double xi);
 int hfq_tables_sadatom(hfq_tables **out, int Z, int lmax, int nelem, int nnodes, double Rmax, int igrid, double zexp,
                        int nquad);
 
+/* Range-separated caches of the spherically averaged atom: sadatom TwoDBasis::compute_yukawa(lambda) (rs = 1)
+ * or compute_erfc(mu) (rs = 2), src/sadatom/basis.cpp:154-184; hfq_exchange on a context created from these
+ * tables is sadatom rs_exchange(cube) (:314-420). */
+int hfq_tables_sadatom_rs(hfq_tables **out, int Z, int lmax, int nelem, int nnodes, double Rmax, int igrid, double zexp,
+                          int nquad, int rs, double param);
+
 /* Diatomic basis: diatomic::basis::TwoDBasis ctor + compute_tei()
  * (src/diatomic/basis.cpp:525-647, :1382-1547; flags src/diatomic/main.cpp:60-118).
  * lmax_per_m[|m|], |m| = 0..nm-1, is the --lmax list. */

@@ -15,8 +15,23 @@ class SadatomBasis:
     def coulomb(self, P_in):
         return 4.0 * np.pi * self.b._assemble_J(0, P_in)
 
-    def exchange(self, P):
+    def rs_exchange(self, P):
+        """src/sadatom/basis.cpp:314-420: same loops with the range-separated caches of the atomic oracle
+        (compute_yukawa / compute_erfc) and prefactor 4 pi lambda (Yukawa) or 4 pi mu/(2L+1) (erfc), :385."""
+        b = self.b
+        if getattr(b, "yukawa", True) is False:
+            return self.exchange(P, Lfac=lambda L: 4.0 * np.pi * b.lam / (2 * L + 1), assemble=b._assemble_K_pairwise)
+        save = (b.disjoint_L, b.disjoint_m1L, b.prim_chol)
+        b.disjoint_L, b.disjoint_m1L, b.prim_chol = b.disjoint_iL, b.disjoint_kL, b.rs_chol
+        try:
+            return self.exchange(P, Lfac=lambda L: 4.0 * np.pi * b.lam)
+        finally:
+            b.disjoint_L, b.disjoint_m1L, b.prim_chol = save
+
+    def exchange(self, P, Lfac=None, assemble=None):
         g = Gaunt()
+        assemble = assemble or self.b._assemble_K
+        Lfac = Lfac or (lambda L: 4.0 * np.pi / (2 * L + 1))
         gmax = self.lmax
         N = self.b.Nrad()
         K = [np.zeros((N, N)) for _ in range(gmax + 1)]
@@ -36,9 +51,9 @@ class SadatomBasis:
                 for L in range(Lmin, Lmax + 1):
                     if tot[L] == 0.0:
                         continue
-                    Prad[L] = Prad.get(L, 0.0) + (4.0 * np.pi / (2 * L + 1) * tot[L]) * P[lin]
+                    Prad[L] = Prad.get(L, 0.0) + (Lfac(L) * tot[L]) * P[lin]
             for L, PL in sorted(Prad.items()):
-                K[lout] -= self.b._assemble_K(L, PL)
+                K[lout] -= assemble(L, PL)
         return K
 
 

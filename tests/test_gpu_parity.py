@@ -208,6 +208,33 @@ def test_sadatom_coulomb_exchange(hb):
         sb.exchange(cube[:2])
 
 
+@pytest.mark.parametrize("kind", ["yukawa", "erfc"])
+def test_sadatom_rs_exchange(hb, kind):
+    """Range-separated exchange of the spherically averaged atom, src/sadatom/basis.cpp:154-184, :314-420."""
+    from oracle import sadatom as osad
+    lmax, par = 1, 0.37
+    ob = cases.oracle_atomic(10, lmax, 0, 2)
+    sb = hb.SadatomTwoDBasis(10, lmax, 2).compute_tei()
+    if kind == "yukawa":
+        ob.compute_yukawa(par)
+        sb.compute_yukawa(par)
+    else:
+        ob.compute_erfc(par)
+        sb.compute_erfc(par)
+    so = osad.SadatomBasis(ob, lmax)
+    N = ob.Nrad()
+    rng = np.random.default_rng(14)
+    cube = []
+    for l in range(lmax + 1):
+        Q, _ = np.linalg.qr(rng.standard_normal((N, 2)))
+        cube.append((2 * l + 1) * Q @ Q.T)
+    Ko, Kg = so.rs_exchange(cube), sb.rs_exchange(cube)
+    K0 = sb.exchange(cube)
+    for l in range(lmax + 1):
+        assert cases.relerr(Kg[l], Ko[l]) < 1e-11, l
+        assert np.linalg.norm(Kg[l]) < np.linalg.norm(K0[l])
+
+
 def test_fused_coulomb_exchange(hb):
     """hfq_coulomb_exchange == hfq_coulomb + hfq_exchange(kscale*P); sharded partial J and K sum to the full matrices."""
     import torch
