@@ -577,7 +577,7 @@ void Engine::pack_density(const double *dP, int64_t ldP, cudaStream_t st) {
   Impl &s = *p_;
   const BasisTables &t = s.t;
   const int na = t.Nang(), ns = s.ns;
-  dev::k_block_norms<<<dim3(na, na), 128, 0, st>>>(s.bd, dP, ldP, s.d_norms.p);
+  dev::k_block_norms<<<dim3(na, na), 256, 0, st>>>(s.bd, dP, ldP, s.d_norms.p);
   CK(cudaGetLastError());
   s.norms_host.resize((size_t)3 * na * na);
   CK(cudaMemcpyAsync(s.norms_host.data(), s.d_norms.p, s.norms_host.size() * sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -41,44 +41,52 @@ static __global__ void k_block_norms(BasisDev b, const double *__restrict__ P, i
   const int a = blockIdx.x, c = blockIdx.y;
   const int sa = b.ang_skip[a], sc = b.ang_skip[c];
   const int na = b.Nrad - sa, nc = b.Nrad - sc;
-  const double *base = P + b.ang_off[a] + (int64_t)b.ang_off[c] * ld;
-  const double *mirr = P + b.ang_off[c] + (int64_t)b.ang_off[a] * ld;
+  const double *base = P + b.ang_off[a] + (int64_t)b.ang_off[c] * ld;   // block (a, c): na x nc
+  const double *mirr = P + b.ang_off[c] + (int64_t)b.ang_off[a] * ld;   // block (c, a): nc x na
+  // 32 x 32 tiles; the mirrored tile goes through shared memory so that both reads are coalesced
+  __shared__ double tm[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8 threads
   double s = 0.0, d = 0.0, m = 0.0;
-  for (int idx = threadIdx.x; idx < na * nc; idx += blockDim.x) {
-    const int i = idx % na, j = idx / na;
-    const double v = base[i + (int64_t)j * ld];
-    s += v * v;
-    d = fmax(d, fabs(v - mirr[j + (int64_t)i * ld]));
-    m = fmax(m, fabs(v));
-  }
-  __shared__ double red[3][32];
+  for (int j0 = 0; j0 < nc; j0 += 32)
+    for (int i0 = 0; i0 < na; i0 += 32) {
+      __syncthreads();
+      for (int k = ty; k < 32; k += 8) {   // mirror element (j0 + tx, i0 + k) of block (c, a)
+        const int jj = j0 + tx, ii = i0 + k;
+        tm[k][tx] = (jj < nc && ii < na) ? mirr[jj + (int64_t)ii * ld] : 0.0;
+      }
+      __syncthreads();
+      for (int k = ty; k < 32; k += 8) {   // element (i0 + tx, j0 + k) of block (a, c)
+        const int ii = i0 + tx, jj = j0 + k;
+        if (ii < na && jj < nc) {
+          const double v = base[ii + (int64_t)jj * ld];
+          s += v * v;
+          d = fmax(d, fabs(v - tm[tx][k]));
+          m = fmax(m, fabs(v));
+        }
+      }
+    }
+  __shared__ double red[3][8];
   for (int o = 16; o > 0; o >>= 1) {
     s += __shfl_down_sync(0xffffffffu, s, o);
     d = fmax(d, __shfl_down_sync(0xffffffffu, d, o));
     m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
   }
-  if ((threadIdx.x & 31) == 0) {
-    red[0][threadIdx.x >> 5] = s;
-    red[1][threadIdx.x >> 5] = d;
-    red[2][threadIdx.x >> 5] = m;
+  if (tx == 0) {
+    red[0][ty] = s;
+    red[1][ty] = d;
+    red[2][ty] = m;
   }
   __syncthreads();
-  if (threadIdx.x < 32) {
-    const bool in = threadIdx.x < (blockDim.x >> 5);
-    s = in ? red[0][threadIdx.x] : 0.0;
-    d = in ? red[1][threadIdx.x] : 0.0;
-    m = in ? red[2][threadIdx.x] : 0.0;
-    for (int o = 16; o > 0; o >>= 1) {
-      s += __shfl_down_sync(0xffffffffu, s, o);
-      d = fmax(d, __shfl_down_sync(0xffffffffu, d, o));
-      m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < 8; k++) {
+      s += red[0][k];
+      d = fmax(d, red[1][k]);
+      m = fmax(m, red[2][k]);
     }
-    if (threadIdx.x == 0) {
-      const int64_t nn = (int64_t)b.Nang * b.Nang;
-      out[a * b.Nang + c] = s;
-      out[nn + a * b.Nang + c] = d;
-      out[2 * nn + a * b.Nang + c] = m;
-    }
+    const int64_t nn = (int64_t)b.Nang * b.Nang;
+    out[a * b.Nang + c] = s;
+    out[nn + a * b.Nang + c] = d;
+    out[2 * nn + a * b.Nang + c] = m;
   }
 }
 
