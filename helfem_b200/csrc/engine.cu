@@ -106,7 +106,17 @@ struct Engine::Impl {
   std::vector<int> packed_splist;
   bool packed_valid = false;
   double kscale = 1.0;               // exchange(kscale * P) = kscale * exchange(P)
-  cudaStream_t copy_stream = nullptr, up_stream = nullptr;
+  struct JPlan {   // cached Coulomb descriptors (see coulomb_dev)
+    bool valid = false;
+    std::vector<int> splist, sp_active;
+    std::vector<char> M_active;
+    int shard = 0, nshards = 1, nfold = 0, nunfold = 0, nblocks = 0;
+    DevBuf<dev::GemmItem> d_items, d_uitems;
+    DevBuf<dev::GemmEntry> d_entries, d_uentries;
+    DevBuf<int> d_blocks;
+  } jplan;
+  cudaStream_t copy_stream = nullptr, up_stream = nullptr, j_stream = nullptr;
+  cudaEvent_t ev_packed = nullptr, ev_jdone = nullptr;
   cudaEvent_t ev_up = nullptr;
   DevBuf<double> d_Pfull;
   DevBuf<int> d_flag;
@@ -469,7 +479,7 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
     s.d_jfac.upload(jfac, &dev_bytes_);
   }
   // ---- work buffers that do not depend on the density
-  s.d_norms.alloc((size_t)3 * na * na, &dev_bytes_);
+  s.d_norms.alloc((size_t)na * na + 2, &dev_bytes_);
   s.d_Ppix.alloc((size_t)s.ns * s.ns * s.Npix * s.NB, &dev_bytes_);
   s.d_splist.alloc((size_t)s.ns * s.ns, &dev_bytes_);
   s.d_op_src.alloc((size_t)s.ns * s.ns, &dev_bytes_);
@@ -577,19 +587,22 @@ void Engine::pack_density(const double *dP, int64_t ldP, cudaStream_t st) {
   Impl &s = *p_;
   const BasisTables &t = s.t;
   const int na = t.Nang(), ns = s.ns;
+  const size_t nn = (size_t)na * na;
+  if (s.norms_host.size() != nn + 2) {
+    // page-locked once: the per-call read-back is then a plain DMA instead of a staged pageable copy
+    if (!s.norms_host.empty()) cudaHostUnregister(s.norms_host.data());
+    s.norms_host.assign(nn + 2, 0.0);
+    if (cudaHostRegister(s.norms_host.data(), s.norms_host.size() * sizeof(double), cudaHostRegisterDefault) != cudaSuccess)
+      cudaGetLastError();   // stays pageable: slower, still correct
+  }
+  CK(cudaMemsetAsync(s.d_norms.p + nn, 0, 2 * sizeof(double), st));
   dev::k_block_norms<<<dim3(na, na), 256, 0, st>>>(s.bd, dP, ldP, s.d_norms.p);
   CK(cudaGetLastError());
-  s.norms_host.resize((size_t)3 * na * na);
   CK(cudaMemcpyAsync(s.norms_host.data(), s.d_norms.p, s.norms_host.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   {
     // symmetric density (every SCF density is): the exchange builds half of each diagonal output pair
-    double asym = 0.0, amax = 0.0;
-    const size_t nn = (size_t)na * na;
-    for (size_t k = 0; k < nn; k++) {
-      asym = std::max(asym, s.norms_host[nn + k]);
-      amax = std::max(amax, s.norms_host[2 * nn + k]);
-    }
+    const double asym = s.norms_host[nn], amax = s.norms_host[nn + 1];
     static const bool allow = !(getenv("HFQ_NO_SYMMETRY") && atoi(getenv("HFQ_NO_SYMMETRY")));
     s.p_symmetric = allow && asym <= 1e-14 * amax;
   }
@@ -614,19 +627,40 @@ void Engine::jk_dev(const double *dP, int64_t ldP, double kscale, double *dJ, in
                     int shard, int nshards, cudaStream_t st) {
   Impl &s = *p_;
   CK(cudaSetDevice(device_));
+  static const bool trace = getenv("HFQ_TRACE") && atoi(getenv("HFQ_TRACE"));
+  const auto t0 = std::chrono::steady_clock::now();
+  auto ms_since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
   pack_density(dP, ldP, st);
+  const double t_pack = ms_since();
   s.packed_valid = true;
+  if (!s.j_stream) {
+    CK(cudaStreamCreateWithFlags(&s.j_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&s.ev_packed, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&s.ev_jdone, cudaEventDisableTiming));
+  }
   try {
-    coulomb_dev(dP, ldP, dJ, ldJ, shard, nshards, st);
-    const EngineTimings tj = tm_;
-    if (s.ev_j) CK(cudaEventRecord(s.ev_j, st));
+    // the Coulomb chain (~1 ms of small kernels) runs on its own stream and fills the tails of the
+    // exchange kernels instead of preceding them
+    CK(cudaEventRecord(s.ev_packed, st));
+    CK(cudaStreamWaitEvent(s.j_stream, s.ev_packed, 0));
+    coulomb_run(dP, ldP, dJ, ldJ, shard, nshards, s.j_stream, true);
+    CK(cudaEventRecord(s.ev_jdone, s.j_stream));
+    EngineTimings tj;
+    tj.launches = 6;
+    const double t_j = ms_since();
     s.kscale = kscale;
     exchange_dev(dP, ldP, dK, ldK, shard, nshards, st);
+    CK(cudaStreamWaitEvent(st, s.ev_jdone, 0));   // work queued on st by the caller sees J complete
+    CK(cudaStreamSynchronize(s.j_stream));
+    if (trace)
+      fprintf(stderr, "[hfq] jk_dev: pack %.2f  J %.2f (gpu %.2f)  K %.2f (gpu %.2f: fold %.2f gemm %.2f off %.2f unpack %.2f) ms\n",
+              t_pack, t_j - t_pack, tj.total, ms_since() - t_j, tm_.total, tm_.fold, tm_.tgemm, tm_.offdiag, tm_.unpack);
     tm_.launches += tj.launches;
     tm_.total += tj.total;
   } catch (...) {
     s.packed_valid = false;
     s.kscale = 1.0;
+    cudaStreamSynchronize(s.j_stream);
     throw;
   }
   s.packed_valid = false;
@@ -648,6 +682,8 @@ struct ExchangePlan {
   std::string key;
   std::vector<std::unique_ptr<ExchangeBatch>> batches;
   std::vector<int> splist, op_src, op_tri;
+  DevBuf<int> d_op_src, d_op_tri, d_blocks;   // device copies + angular blocks (j | k << 16) that can be non-zero
+  int nblocks = 0;
   int nactive = 0, S = 1, maxM = 8;
   double fl_fold = 0, fl_tg = 0, fl_off = 0, al_fold = 0, al_tg = 0, al_off = 0;
   const double *R_base = nullptr, *K_base = nullptr;   // buffers the descriptors point into
@@ -779,6 +815,17 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
           if (pj == sec_of_m.end() || pk == sec_of_m.end()) continue;
           np->op_src[(size_t)sj * ns + sk] = np->op_src[(size_t)pj->second * ns + pk->second];
         }
+    }
+    {
+      if (na > 0xffff) throw std::runtime_error("Engine: more than 65535 angular functions");
+      std::vector<int> blocks;
+      for (int aj = 0; aj < na; aj++)
+        for (int ak = 0; ak < na; ak++)
+          if (np->op_src[(size_t)s.ang_sec[aj] * ns + s.ang_sec[ak]] >= 0) blocks.push_back(aj | (ak << 16));
+      np->nblocks = (int)blocks.size();
+      np->d_blocks.upload(blocks, &dev_bytes_);
+      np->d_op_src.upload(np->op_src, &dev_bytes_);
+      np->d_op_tri.upload(np->op_tri, &dev_bytes_);
     }
     {
       size_t free_b = 0, total_b = 0;
@@ -967,11 +1014,15 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
   }
   // 6. unpack
   CK(cudaEventRecord(s.ev[6], st));
-  CK(cudaMemcpyAsync(s.d_op_src.p, plan->op_src.data(), plan->op_src.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(s.d_op_tri.p, plan->op_tri.data(), plan->op_tri.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-  dev::UnpackDev u{s.d_op_src.p, s.d_op_tri.p, s.d_ep_off.p, s.d_ang_sec.p, s.d_ang_pos.p, s.op_stride, S, s.kscale};
-  dev::k_unpack_K<<<dim3(na, na), 256, 0, st>>>(s.bd, u, s.d_Kacc.p, dK, ldK);
-  CK(cudaGetLastError());
+  // everything outside the computed sector pairs is exactly zero: clear K at memset speed, then unpack
+  // only the angular blocks that can be non-zero
+  CK(cudaMemset2DAsync(dK, (size_t)ldK * sizeof(double), 0, (size_t)nbf_ * sizeof(double), (size_t)nbf_, st));
+  if (plan->nblocks) {
+    dev::UnpackDev u{plan->d_op_src.p, plan->d_op_tri.p, plan->d_blocks.p, s.d_ep_off.p, s.d_ang_sec.p, s.d_ang_pos.p,
+                     s.op_stride, S, s.kscale};
+    dev::k_unpack_K<<<plan->nblocks, 256, 0, st>>>(s.bd, u, s.d_Kacc.p, dK, ldK);
+    CK(cudaGetLastError());
+  }
   CK(cudaEventRecord(s.ev[7], st));
   CK(cudaStreamSynchronize(st));
   CK(cudaEventElapsedTime(&tm_.pack, s.ev[0], s.ev[1]));
@@ -993,8 +1044,10 @@ const BasisTables &Engine::tables() const { return p_->t; }
 
 Engine::~Engine() {
   plans_.reset();
-  if (p_)
+  if (p_) {
     for (auto &e : p_->ev) cudaEventDestroy(e);
+    if (!p_->norms_host.empty()) cudaHostUnregister(p_->norms_host.data());
+  }
   if (stream_) cudaStreamDestroy(stream_);
 }
 
@@ -1027,66 +1080,115 @@ void Engine::output_pattern(std::vector<int> &bf_sector, std::vector<int> &pairs
 // ---------------------------------------------------------------------------
 void Engine::coulomb_dev(const double *dP, int64_t ldP, double *dJ, int64_t ldJ, int shard, int nshards,
                          cudaStream_t st) {
+  coulomb_run(dP, ldP, dJ, ldJ, shard, nshards, st, false);
+}
+
+// async: no timing events (they are shared with the exchange path) and no final synchronisation -- used by
+// jk_dev to run the Coulomb chain on a second stream next to the exchange kernels.
+void Engine::coulomb_run(const double *dP, int64_t ldP, double *dJ, int64_t ldJ, int shard, int nshards,
+                         cudaStream_t st, bool async) {
   Impl &s = *p_;
   const BasisTables &t = s.t;
   if (t.pairwise())
     throw std::logic_error("coulomb is not available on range-separated (erfc pair-tensor) tables\n");
   CK(cudaSetDevice(device_));
   const int na = t.Nang(), ns = s.ns, nq = s.NL * t.nch;
-  tm_ = EngineTimings();
-  CK(cudaEventRecord(s.ev[0], st));
+  if (!async) tm_ = EngineTimings();
+  if (!async) CK(cudaEventRecord(s.ev[0], st));
   if (!s.packed_valid) pack_density(dP, ldP, st);
   const std::vector<int> &splist = s.packed_splist;
   // sharding: this rank handles the multipoles L in [L0, L1) (partial J, summed by the caller's all-reduce)
   const int L0 = (int)((int64_t)s.NL * shard / nshards), L1 = (int)((int64_t)s.NL * (shard + 1) / nshards);
   const int q0 = L0 * t.nch, nqs = (L1 - L0) * t.nch;
-  CK(cudaEventRecord(s.ev[1], st));
+  if (!async) CK(cudaEventRecord(s.ev[1], st));
   if (s.d_Paux.n == 0) {
     s.d_Paux.alloc((size_t)s.nM * nq * s.Npix, &dev_bytes_);
     s.d_JauxT.alloc((size_t)s.nM * nq * s.Npix, &dev_bytes_);
     s.d_Jsec.alloc((size_t)ns * ns * s.Npix * s.NB, &dev_bytes_);
   }
-  // fold: Paux[Mi][q][pix] = sum over sector pairs with m_a - m_b = M of G[sp][q][:] . Ppix[sp][pix][:]
-  std::vector<dev::GemmItem> items;
-  std::vector<dev::GemmEntry> entries;
-  std::vector<char> M_active(s.nM, 0);
-  for (int Mi = 0; Mi < s.nM; Mi++) {
-    const int M = Mi - (s.mmax - s.mmin);
-    dev::GemmItem gi{};
-    gi.C = s.d_Paux.p + ((size_t)Mi * nq + q0) * s.Npix;
-    gi.M = nqs;
-    gi.N = s.Npix;
-    gi.K = s.NB;
-    gi.ent0 = (int)entries.size();
-    for (int sp : splist) {
-      if (s.sec_m[sp / ns] - s.sec_m[sp % ns] != M) continue;
-      dev::GemmEntry ge;
-      ge.A = s.d_G.p + ((size_t)sp * nq + q0) * s.NB;
-      ge.lda = s.NB;
-      ge.B = s.d_Ppix.p + (size_t)sp * s.Npix * s.NB;
-      entries.push_back(ge);
+  // The descriptors depend only on which sector pairs carry density (and on the shard): cached like
+  // the exchange plan, so an SCF iteration issues no host->device descriptor traffic and no mid-call sync.
+  Impl::JPlan &jp = s.jplan;
+  if (!jp.valid || jp.splist != splist || jp.shard != shard || jp.nshards != nshards) {
+    CK(cudaStreamSynchronize(st));   // a previous call may still read the descriptor buffers
+    jp.valid = true;
+    jp.splist = splist;
+    jp.shard = shard;
+    jp.nshards = nshards;
+    // fold: Paux[Mi][q][pix] = sum over sector pairs with m_a - m_b = M of G[sp][q][:] . Ppix[sp][pix][:]
+    std::vector<dev::GemmItem> items, uitems;
+    std::vector<dev::GemmEntry> entries, uentries;
+    jp.M_active.assign(s.nM, 0);
+    for (int Mi = 0; Mi < s.nM; Mi++) {
+      const int M = Mi - (s.mmax - s.mmin);
+      dev::GemmItem gi{};
+      gi.C = s.d_Paux.p + ((size_t)Mi * nq + q0) * s.Npix;
+      gi.M = nqs;
+      gi.N = s.Npix;
+      gi.K = s.NB;
+      gi.ent0 = (int)entries.size();
+      for (int sp : splist) {
+        if (s.sec_m[sp / ns] - s.sec_m[sp % ns] != M) continue;
+        dev::GemmEntry ge;
+        ge.A = s.d_G.p + ((size_t)sp * nq + q0) * s.NB;
+        ge.lda = s.NB;
+        ge.B = s.d_Ppix.p + (size_t)sp * s.Npix * s.NB;
+        entries.push_back(ge);
+      }
+      gi.ent1 = (int)entries.size();
+      if (gi.ent1 == gi.ent0 || nqs == 0) continue;
+      jp.M_active[Mi] = 1;
+      gi.accumulate = 0;
+      gi.ldb = s.NB;
+      gi.ldc = s.Npix;
+      gi.alpha = 1.0;
+      items.push_back(gi);
     }
-    gi.ent1 = (int)entries.size();
-    if (gi.ent1 == gi.ent0 || nqs == 0) continue;
-    M_active[Mi] = 1;
-    gi.accumulate = 0;
-    gi.ldb = s.NB;
-    gi.ldc = s.Npix;
-    gi.alpha = 1.0;
-    items.push_back(gi);
+    // unfold: Jsec[sp=(sj,si)][pix][j*NP+i] = sum_q JauxT[Mi][pix][q] G[sp][q][j*NP+i]
+    jp.sp_active.assign((size_t)ns * ns, 0);
+    for (int sp = 0; sp < ns * ns; sp++) {
+      const int M = s.sec_m[sp / ns] - s.sec_m[sp % ns], Mi = M + (s.mmax - s.mmin);
+      if (!jp.M_active[Mi]) continue;
+      jp.sp_active[sp] = 1;
+      dev::GemmItem gi{};
+      gi.C = s.d_Jsec.p + (size_t)sp * s.Npix * s.NB;
+      gi.browoff = s.d_browoff_G.p;
+      gi.M = s.Npix;
+      gi.N = s.NB;
+      gi.K = nqs;
+      gi.ent0 = (int)uentries.size();
+      dev::GemmEntry ge;
+      ge.A = s.d_JauxT.p + (size_t)Mi * s.Npix * nq + q0;
+      ge.lda = nq;
+      ge.B = s.d_G.p + ((size_t)sp * nq + q0) * s.NB;
+      uentries.push_back(ge);
+      gi.ent1 = (int)uentries.size();
+      gi.accumulate = 0;
+      gi.ldc = s.NB;
+      gi.alpha = 1.0;
+      uitems.push_back(gi);
+    }
+    // dense blocks (ang i, ang j) that read an active sector pair sp = (sector j, sector i)
+    if (na > 0xffff) throw std::runtime_error("Engine: more than 65535 angular functions");
+    std::vector<int> blocks;
+    for (int ai = 0; ai < na; ai++)
+      for (int aj = 0; aj < na; aj++)
+        if (jp.sp_active[(size_t)s.ang_sec[aj] * ns + s.ang_sec[ai]]) blocks.push_back(ai | (aj << 16));
+    jp.nfold = (int)items.size();
+    jp.nunfold = (int)uitems.size();
+    jp.nblocks = (int)blocks.size();
+    jp.d_items.upload(items, &dev_bytes_);
+    jp.d_entries.upload(entries, &dev_bytes_);
+    jp.d_uitems.upload(uitems, &dev_bytes_);
+    jp.d_uentries.upload(uentries, &dev_bytes_);
+    jp.d_blocks.upload(blocks, &dev_bytes_);
   }
-  auto up = [&](auto &dbuf, const auto &h) {
-    if (dbuf.n < h.size()) dbuf.alloc(h.size() * 2, &dev_bytes_);
-    if (!h.empty()) CK(cudaMemcpyAsync(dbuf.p, h.data(), h.size() * sizeof(h[0]), cudaMemcpyHostToDevice, st));
-  };
-  up(s.d_gitems, items);
-  up(s.d_gentries, entries);
-  CK(cudaStreamSynchronize(st));
+  last_active_j_.assign(jp.sp_active.begin(), jp.sp_active.end());
   // inactive M channels must read as zero in the radial step
   for (int Mi = 0; Mi < s.nM; Mi++)
-    if (!M_active[Mi]) CK(cudaMemsetAsync(s.d_Paux.p + (size_t)Mi * nq * s.Npix, 0, (size_t)nq * s.Npix * sizeof(double), st));
-  launch_gemm<true>(s.d_gitems.p, s.d_gentries.p, (int)items.size(), nqs, s.Npix, st);
-  CK(cudaEventRecord(s.ev[2], st));
+    if (!jp.M_active[Mi]) CK(cudaMemsetAsync(s.d_Paux.p + (size_t)Mi * nq * s.Npix, 0, (size_t)nq * s.Npix * sizeof(double), st));
+  launch_gemm<true>(jp.d_items.p, jp.d_entries.p, jp.nfold, nqs, s.Npix, st);
+  if (!async) CK(cudaEventRecord(s.ev[2], st));
   if (nshards > 1)   // multipoles of other shards must read as zero in the unfold
     CK(cudaMemsetAsync(s.d_JauxT.p, 0, (size_t)s.nM * nq * s.Npix * sizeof(double), st));
   // radial step
@@ -1094,44 +1196,17 @@ void Engine::coulomb_dev(const double *dP, int64_t ldP, double *dJ, int64_t ldJ,
                   s.d_small.p, s.d_big.p, s.d_B.p, s.d_sigma.p, s.nM};
   if (L1 > L0) dev::k_jradial<<<dim3(L1 - L0, s.nM), 256, 0, st>>>(s.bd, jr, L0, s.d_Paux.p, s.d_JauxT.p);
   CK(cudaGetLastError());
-  CK(cudaEventRecord(s.ev[3], st));
-  // unfold: Jsec[sp=(sj,si)][pix][j*NP+i] = sum_q JauxT[Mi][pix][q] G[sp][q][j*NP+i]
-  std::vector<dev::GemmItem> uitems;
-  std::vector<dev::GemmEntry> uentries;
-  std::vector<int> sp_active((size_t)ns * ns, 0);
-  for (int sp = 0; sp < ns * ns; sp++) {
-    const int M = s.sec_m[sp / ns] - s.sec_m[sp % ns], Mi = M + (s.mmax - s.mmin);
-    if (!M_active[Mi]) continue;
-    sp_active[sp] = 1;
-    dev::GemmItem gi{};
-    gi.C = s.d_Jsec.p + (size_t)sp * s.Npix * s.NB;
-    gi.browoff = s.d_browoff_G.p;
-    gi.M = s.Npix;
-    gi.N = s.NB;
-    gi.K = nqs;
-    gi.ent0 = (int)uentries.size();
-    dev::GemmEntry ge;
-    ge.A = s.d_JauxT.p + (size_t)Mi * s.Npix * nq + q0;
-    ge.lda = nq;
-    ge.B = s.d_G.p + ((size_t)sp * nq + q0) * s.NB;
-    uentries.push_back(ge);
-    gi.ent1 = (int)uentries.size();
-    gi.accumulate = 0;
-    gi.ldc = s.NB;
-    gi.alpha = 1.0;
-    uitems.push_back(gi);
+  if (!async) CK(cudaEventRecord(s.ev[3], st));
+  launch_gemm<false>(jp.d_uitems.p, jp.d_uentries.p, jp.nunfold, s.Npix, s.NB, st);
+  if (!async) CK(cudaEventRecord(s.ev[4], st));
+  // clear J at memset speed, then unpack only the angular blocks of active sector pairs
+  CK(cudaMemset2DAsync(dJ, (size_t)ldJ * sizeof(double), 0, (size_t)nbf_ * sizeof(double), (size_t)nbf_, st));
+  if (jp.nblocks) {
+    dev::k_unpack_J<<<jp.nblocks, 256, 0, st>>>(s.bd, s.d_ang_sec.p, s.d_ang_pos.p, jp.d_blocks.p, s.d_Jsec.p, dJ, ldJ);
+    CK(cudaGetLastError());
   }
-  CK(cudaStreamSynchronize(st));  // the fold GEMM still reads the descriptor buffers
-  up(s.d_gitems, uitems);
-  up(s.d_gentries, uentries);
-  CK(cudaMemcpyAsync(s.d_sp_active.p, sp_active.data(), sp_active.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-  last_active_j_.assign(sp_active.begin(), sp_active.end());
-  CK(cudaStreamSynchronize(st));
-  launch_gemm<false>(s.d_gitems.p, s.d_gentries.p, (int)uitems.size(), s.Npix, s.NB, st);
-  CK(cudaEventRecord(s.ev[4], st));
-  dev::k_unpack_J<<<dim3(na, na), 256, 0, st>>>(s.bd, s.d_ang_sec.p, s.d_ang_pos.p, s.d_sp_active.p, s.d_Jsec.p, dJ, ldJ);
-  CK(cudaGetLastError());
-  CK(cudaEventRecord(s.ev[5], st));
+  if (!async) CK(cudaEventRecord(s.ev[5], st));
+  if (async) return;
   CK(cudaStreamSynchronize(st));
   CK(cudaEventElapsedTime(&tm_.pack, s.ev[0], s.ev[1]));
   CK(cudaEventElapsedTime(&tm_.fold, s.ev[1], s.ev[2]));
@@ -1269,7 +1344,7 @@ Engine::HostRanges Engine::density_ranges() const {
   for (int c = 0; c < na; c++) {
     int lo = n, hi = 0;
     for (int a = 0; a < na; a++)
-      if (s.norms_host[2 * nn + (size_t)a * na + c] > 0.0) {   // block (a, c): rows of a, columns of c
+      if (s.norms_host[(size_t)a * na + c] > 0.0) {   // block (a, c): rows of a, columns of c
         lo = std::min(lo, s.ang_off[a]);
         hi = std::max(hi, s.ang_off[a] + s.t.Nrad - s.ang_skip[a]);
       }

@@ -70,6 +70,8 @@ class Engine {
 
  private:
   void pack_density(const double *dP, int64_t ldP, cudaStream_t stream);
+  void coulomb_run(const double *dP, int64_t ldP, double *dJ, int64_t ldJ, int shard, int nshards, cudaStream_t stream,
+                   bool async);
   // Host-pointer results: only the bounding row range of the blocks that can be non-zero is copied
   // back per column (grouped into rectangles); the rest of the caller's matrix is zero-filled by
   // host threads while the GPU is still computing.

@@ -35,8 +35,8 @@ struct BasisDev {
   const int *rad_e1;     // [Nrad] last element containing it (elements overlap by one function)
 };
 
-// per (ang a, ang c) block: sum of squares -> out[a*Nang+c], max |P_ac(i,j) - P_ca(j,i)| ->
-// out[Nang^2 + ..], max |P_ac(i,j)| -> out[2 Nang^2 + ..]  (screening + symmetry test of the density)
+// per (ang a, ang c) block: sum of squares -> out[a*Nang+c]; over the whole matrix max |P(i,j) - P(j,i)| ->
+// out[Nang^2] and max |P(i,j)| -> out[Nang^2 + 1] (zeroed by the caller; screening + symmetry test)
 static __global__ void k_block_norms(BasisDev b, const double *__restrict__ P, int64_t ld, double *__restrict__ out) {
   const int a = blockIdx.x, c = blockIdx.y;
   const int sa = b.ang_skip[a], sc = b.ang_skip[c];
@@ -85,8 +85,10 @@ static __global__ void k_block_norms(BasisDev b, const double *__restrict__ P, i
     }
     const int64_t nn = (int64_t)b.Nang * b.Nang;
     out[a * b.Nang + c] = s;
-    out[nn + a * b.Nang + c] = d;
-    out[2 * nn + a * b.Nang + c] = m;
+    // non-negative doubles order like their bit patterns: global maxima through integer atomicMax
+    unsigned long long *mx = reinterpret_cast<unsigned long long *>(out + nn);
+    atomicMax(mx, (unsigned long long)__double_as_longlong(d));
+    atomicMax(mx + 1, (unsigned long long)__double_as_longlong(m));
   }
 }
 
@@ -1009,6 +1011,7 @@ k_tgemm_ws(const GemmItem *__restrict__ items, const GemmEntry *__restrict__ ent
 struct UnpackDev {
   const int *op_src;      // [ns*ns] sector pair whose accumulator holds this block (or -1: zero)
   const int *op_tri;      // [active op] 1: symmetric storage (see below)
+  const int *blocks;      // angular blocks (j | k << 16) whose sector pair was computed
   const int64_t *ep_off;  // [Nel*Nel] offset of element-pair block inside one output pair's accumulator
   const int *ang_sec;     // [Nang] sector of angular function
   const int *ang_pos;     // [Nang] position inside the sector
@@ -1020,8 +1023,9 @@ struct UnpackDev {
 // Symmetric storage (diagonal output pairs of a symmetric density): K(j rj, k rk) = K(k rk, j rj), so
 // only element pairs ei <= ej were computed, and of an in-element block only the rows rj <= rk
 // (row t = rk (rk+1)/2 + rj); the other half is read from the mirrored entry, column (pos_k, pos_j).
+// One CTA per angular block that can be non-zero (u.blocks[] = angj | angk << 16); the caller zero-fills K first.
 static __global__ void k_unpack_K(BasisDev b, UnpackDev u, const double *__restrict__ Kacc, double *__restrict__ K, int64_t ld) {
-  const int angk = blockIdx.y, angj = blockIdx.x;
+  const int angj = u.blocks[blockIdx.x] & 0xffff, angk = u.blocks[blockIdx.x] >> 16;
   const int sj = b.ang_skip[angj], sk = b.ang_skip[angk];
   const int nj = b.Nrad - sj, nk = b.Nrad - sk;
   double *dst = K + b.ang_off[angj] + (int64_t)b.ang_off[angk] * ld;
@@ -1167,20 +1171,20 @@ k_jradial(BasisDev b, JRadDev jr, int L0, const double *__restrict__ Paux, doubl
   }
 }
 
-// Coulomb unpack: dense J[(ang i, r), (ang j, c)] = Jsec[sp=(sj,si)][pix=(r,c)][pos_j*NP + pos_i]
+// Coulomb unpack: dense J[(ang i, r), (ang j, c)] = Jsec[sp=(sj,si)][pix=(r,c)][pos_j*NP + pos_i].
+// One CTA per ACTIVE angular block (list blocks[] = angi | angj << 16); the caller zero-fills J first.
 static __global__ void k_unpack_J(BasisDev b, const int *__restrict__ ang_sec, const int *__restrict__ ang_pos,
-                           const int *__restrict__ sp_active, const double *__restrict__ Jsec, double *__restrict__ J,
+                           const int *__restrict__ blocks, const double *__restrict__ Jsec, double *__restrict__ J,
                            int64_t ld) {
-  const int angi = blockIdx.x, angj = blockIdx.y;
+  const int angi = blocks[blockIdx.x] & 0xffff, angj = blocks[blockIdx.x] >> 16;
   const int si = b.ang_skip[angi], sj = b.ang_skip[angj];
   const int ni = b.Nrad - si, nj = b.Nrad - sj;
   double *dst = J + b.ang_off[angi] + (int64_t)b.ang_off[angj] * ld;
   const int sp = ang_sec[angj] * b.ns + ang_sec[angi];
-  const bool act = sp_active[sp] != 0;
   const double *src = Jsec + (int64_t)sp * b.Npix * b.NB + ang_pos[angj] * b.NP + ang_pos[angi];
   for (int idx = threadIdx.x; idx < ni * nj; idx += blockDim.x) {
     const int r = idx % ni + si, c = idx / ni + sj;
-    dst[(r - si) + (int64_t)(c - sj) * ld] = act ? src[(int64_t)(r * b.Nrad + c) * b.NB] : 0.0;
+    dst[(r - si) + (int64_t)(c - sj) * ld] = src[(int64_t)(r * b.Nrad + c) * b.NB];
   }
 }
 
