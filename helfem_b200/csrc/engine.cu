@@ -946,6 +946,11 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
         remaining -= take;
       }
       if (tasks.empty()) break;
+      // longest items first: CTAs are dispatched in block-index order, so the tail of the launch is made of
+      // the cheapest items (accumulating items of one output block never share a launch, order is free)
+      std::stable_sort(gitems.begin(), gitems.end(), [](const dev::GemmItem &a, const dev::GemmItem &b) {
+        return (double)a.M * a.N * a.K * (a.ent1 - a.ent0) > (double)b.M * b.N * b.K * (b.ent1 - b.ent0);
+      });
       auto bt = std::make_unique<ExchangeBatch>();
       bt->tasks.upload(tasks, &dev_bytes_);
       bt->gitems.upload(gitems, &dev_bytes_);
