@@ -83,6 +83,7 @@ def cpu_sample(T, P, nblocks, jrows):
     """Reference algorithm (C oracle, OpenMP) on a bounded sample; returns seconds per full
     build extrapolated, and the sample description."""
     from oracle import cjk
+    cjk.use_all_cores()
     C = cjk.DiatomicCaches.from_tables(T)
     Pd = C.expand(P)
     na = C.Nang

@@ -31,6 +31,13 @@ def num_threads():
     return lib().jk_num_threads()
 
 
+def use_all_cores():
+    """Use every core this process may run on (torchrun exports OMP_NUM_THREADS=1).  Returns the count."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().jk_set_num_threads(int(n))
+    return num_threads()
+
+
 def _ptrs(mats):
     keep = [np.ascontiguousarray(np.asarray(m, dtype=np.float64).ravel(order="F")) for m in mats]
     arr = (ctypes.c_void_p * len(keep))(*[k.ctypes.data for k in keep])

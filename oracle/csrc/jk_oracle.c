@@ -40,6 +40,15 @@ int jk_num_threads(void) {
 #endif
 }
 
+/* launchers such as torchrun export OMP_NUM_THREADS=1; the timed CPU arm asks for the cores it may use */
+void jk_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* C(m x n) += alpha * op(A) * op(B); tiny dense kernels, column-major */
 static void gemm_nn(int m, int n, int k, double alpha, const double *A, int lda, const double *B, int ldb, double *C,
                     int ldc) {
