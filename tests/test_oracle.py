@@ -102,6 +102,19 @@ def test_he_rhf_recorded_energy():
     assert abs(np.sum(r["P"] * V) - (-6.7491293871)) < 2e-6
 
 
+def test_be_rhf_recorded_energy():
+    """tests/refs/ci.json atomic-Be-hf-r: total -14.5730231683, Exx -2.6669131299 (two doubly occupied s orbitals:
+    the 2s-1s exchange exercises cross-element blocks of K that He does not)."""
+    ob = cases.oracle_atomic(4, 0, 0, 5)
+    S, T, V = ob.overlap(), ob.kinetic(), ob.nuclear()
+    r = scf.rhf(S, T + V, ob.coulomb, ob.exchange, [2], [np.arange(ob.Nbf())])
+    assert abs(r["E"] - (-14.5730231683)) < 1e-10
+    assert abs(r["Coulomb"] - 7.1560551636) < 1e-5
+    assert abs(r["Exx"] - (-2.6669131299)) < 1e-5
+    assert abs(np.sum(r["P"] * T) - 14.573021084) < 1e-5
+    assert abs(np.sum(r["P"] * V) - (-33.635186286)) < 1e-5
+
+
 def test_h2_rhf_recorded_energy():
     """tests/refs/ci.json diatomic-H2-hf-r: total -1.1336295702."""
     ob = cases.oracle_diatomic(1, 1, 1.4, (4,), 3)
