@@ -125,3 +125,21 @@ def test_erfc_host_setup_matches_oracle(hb):
             for je in range(Nel):
                 a, b = T.pair_tensor(Lq, ie, je), ob.rs_ktei[(Lq * Nel + ie) * Nel + je]
                 assert np.abs(a - b).max() <= 1e-12 * np.abs(b).max()
+
+
+def test_pair_tensor_round_trip(hb):
+    """hfq_tables_set_pair_tensors / hfq_tables_get_pair_tensor keep the reference's rs_ktei layout
+    (ktei[kk*Ni + jj, ll*Ni + ii], column-major) and reject inconsistent sizes."""
+    ob = cases.oracle_atomic(4, 1, 1, 2)
+    ob.compute_erfc(0.25)
+    pref = [4 * np.pi * 0.25 / (2 * L + 1) for L in range(ob.N_L)]
+    T = cases.tables_from_oracle_atomic(hb, ob, pref=pref)
+    assert T.pair_tensor(0, 0, 0) is None
+    T.set_pair_tensors(ob.rs_ktei)
+    Nel = ob.radial.Nel()
+    for L in range(ob.N_L):
+        for ie in range(Nel):
+            for je in range(Nel):
+                assert np.array_equal(T.pair_tensor(L, ie, je), ob.rs_ktei[(L * Nel + ie) * Nel + je])
+    with pytest.raises(ValueError):
+        T.set_pair_tensors(ob.rs_ktei[:-1])
