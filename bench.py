@@ -315,8 +315,13 @@ def main():
     nst = max(acc["n"], 1)
     nl = max(acc["launches_tgemm"], 1)
     ach = acc["alg_tgemm"] / (acc["ms_tgemm"] * 1e-3) / 1e12 if acc["ms_tgemm"] > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "k_tgemm (in-element exchange, FP64 DMMA)", "achieved": ach, "peak": fp64_peak,
-                "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": None,
+    # DRAM traffic of the dominant kernel is a profiler number, not measurable here: the value of the last
+    # committed ncu --set full capture of this workload (1 GPU, symmetric density) is reported with its source
+    traffic = 26.72e9 if (world == 1 and args.lmax == 30 and args.mmax == 6 and args.nelem == 3) else None
+    roofline = {"bound": "tensor", "kernel": "k_tgemm_ws (in-element exchange, FP64 DMMA)", "achieved": ach, "peak": fp64_peak,
+                "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": traffic,
+                "traffic_note": "bytes per launch, dram__bytes_read.sum + dram__bytes_write.sum of profiles/r01f_ncu_full_summary.txt "
+                                "(26.65 GB read: R rows of the in-element pixels + the kernel tiles streamed once per item; 0.07 GB written)",
                 "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                 "alg_flops_per_launch": acc["alg_tgemm"] / nl, "ms_per_launch": acc["ms_tgemm"] / nl,
                 "executed_tflops": acc["flops_tgemm"] / (acc["ms_tgemm"] * 1e-3) / 1e12 if acc["ms_tgemm"] > 0 else 0.0,
