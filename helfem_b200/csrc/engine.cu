@@ -73,7 +73,6 @@ struct Engine::Impl {
   std::vector<int> sec_lmin, sec_lmax;
   int mmin = 0, mmax = 0, nM = 0;   // M = m_a - m_b range: -(mmax-mmin) .. (mmax-mmin)
   // channels
-  std::vector<int> chan_run, chan_pos, run_nL, run_first;   // |M| runs
   std::vector<int64_t> blk_off, B_off, sig_off;
   std::vector<int> ranks;
   std::vector<char> G_nonzero;      // [sp*NL + L]
@@ -89,7 +88,7 @@ struct Engine::Impl {
   double tri_pix_frac = 1.0;   // share of the pixels (ri, rl) with el(ri) <= el(rl)
   DevBuf<double> d_G, d_small, d_big, d_B, d_sigma, d_tperm, d_tperm_tri, d_zrow;
   DevBuf<int64_t> d_blk_off, d_B_off, d_sig_off, d_ep_off;
-  DevBuf<int> d_rank, d_chan_of, d_browoff_T, d_browoff_P, d_browoff_G, d_splist, d_op_src, d_op_tri, d_sp_active;
+  DevBuf<int> d_rank, d_chan_of, d_browoff_T, d_browoff_P, d_browoff_G, d_splist, d_sp_active;
   DevBuf<double> d_jfac, d_norms, d_Ppix, d_R, d_Kacc, d_Paux, d_JauxT, d_Jsec, d_P, d_O, d_O2;
   DevBuf<dev::FoldTask> d_tasks;
   DevBuf<dev::GemmItem> d_gitems;
@@ -271,21 +270,8 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
       }
     s.d_G.upload(G, &dev_bytes_);
   }
-  // ---- channel runs (same |M|), flattened cache arrays
+  // ---- flattened cache arrays
   const int nlm = (int)t.lmL.size();
-  s.chan_run.assign(nlm, 0);
-  s.chan_pos.assign(nlm, 0);
-  for (int i = 0; i < nlm;) {
-    int j = i;
-    while (j < nlm && t.lmM[j] == t.lmM[i]) j++;
-    for (int k = i; k < j; k++) {
-      s.chan_run[k] = (int)s.run_nL.size();
-      s.chan_pos[k] = k - i;
-    }
-    s.run_first.push_back(i);
-    s.run_nL.push_back(j - i);
-    i = j;
-  }
   {
     std::vector<double> hsmall, hbig, hB, hsig;
     s.blk_off.assign((size_t)nlm * t.Nel, 0);
@@ -482,8 +468,6 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
   s.d_norms.alloc((size_t)na * na + 2, &dev_bytes_);
   s.d_Ppix.alloc((size_t)s.ns * s.ns * s.Npix * s.NB, &dev_bytes_);
   s.d_splist.alloc((size_t)s.ns * s.ns, &dev_bytes_);
-  s.d_op_src.alloc((size_t)s.ns * s.ns, &dev_bytes_);
-  s.d_op_tri.alloc((size_t)s.ns * s.ns, &dev_bytes_);
   s.d_sp_active.alloc((size_t)s.ns * s.ns, &dev_bytes_);
   CK(cudaStreamSynchronize(stream_));
   // opt-in shared memory sizes

@@ -540,7 +540,7 @@ static __global__ void k_build_tperm(const double *__restrict__ B, const double 
 
 // ---------------------------------------------------------------------------
 // Exchange, cross-element pairs:  K_(ei,ej)(rj,rk) += sum_ab sum_(ri,rl) I_a(rj,ri) R_ab(ri,rl) J_b(rk,rl)
-// One CTA = (item = output pair x element pair, tile of BT = 8 blk columns).
+// Work descriptors of k_offdiag_mma: item = output pair x element pair, entries = (R slot, channel).
 // ---------------------------------------------------------------------------
 struct OffItem {
   double *C;        // [Ni*Nj][NB]
@@ -552,94 +552,6 @@ struct OffItem {
 struct OffEntry {
   int rslot, ilm;
 };
-
-template <int NCH>
-__global__ void __launch_bounds__(256)
-k_offdiag(BasisDev b, const OffItem *__restrict__ items, const OffEntry *__restrict__ entries,
-          const double *__restrict__ R, const double *__restrict__ dsmall, const double *__restrict__ dbig,
-          const int64_t *__restrict__ blk_off /* [nlm*Nel] offset of channel block in dsmall/dbig */) {
-  constexpr int BT = 8, NAB = NCH * NCH, MAXN = 16;
-  extern __shared__ double sm[];
-  const OffItem it = items[blockIdx.y];
-  const int Ni = b.en[it.ei], Nj = b.en[it.ej], fi = b.efirst[it.ei], fj = b.efirst[it.ej];
-  const int blk0 = blockIdx.x * BT;
-  double *sR = sm;                               // [NAB][Ni*Nj][BT]
-  double *sU = sR + NAB * MAXN * MAXN * BT;      // [NCH][Ni][Nj][BT]
-  double *sI = sU + NCH * MAXN * MAXN * BT;      // [NCH][Ni(rj)][Ni(ri)]  row-major in rj
-  double *sJ = sI + NCH * MAXN * MAXN;           // [NCH][Nj(rl)][Nj(rk)]  (transposed: rk fastest)
-  const int tid = threadIdx.x;
-  const int64_t gstride = (int64_t)b.NB;
-  // stage-2 ownership: thread -> (half a, rk, blk), accumulates all rj
-  const int t_blk = tid % BT, t_rk = (tid / BT) % MAXN, t_a = tid / (BT * MAXN);
-  double acc[MAXN];
-#pragma unroll
-  for (int q = 0; q < MAXN; q++) acc[q] = 0.0;
-
-  for (int e = it.ent0; e < it.ent1; e++) {
-    const OffEntry en = entries[e];
-    const double *Rt = R + (int64_t)en.rslot * NAB * b.Npix * gstride;
-    // I = factor on the output-row element, J = factor on the output-column element
-    const double *srcI = (it.ei > it.ej ? dbig : dsmall) + blk_off[en.ilm * b.Nel + it.ei];
-    const double *srcJ = (it.ei > it.ej ? dsmall : dbig) + blk_off[en.ilm * b.Nel + it.ej];
-    __syncthreads();
-    for (int idx = tid; idx < NCH * Ni * Ni; idx += blockDim.x) {
-      const int ch = idx / (Ni * Ni), rem = idx % (Ni * Ni), ri = rem / Ni, rj = rem % Ni;  // column-major source
-      sI[(ch * MAXN + rj) * MAXN + ri] = srcI[idx];
-    }
-    for (int idx = tid; idx < NCH * Nj * Nj; idx += blockDim.x) {
-      const int ch = idx / (Nj * Nj), rem = idx % (Nj * Nj), rl = rem / Nj, rk = rem % Nj;  // J(rk,rl) column-major
-      sJ[(ch * MAXN + rl) * MAXN + rk] = srcJ[idx];
-    }
-    for (int idx = tid; idx < NAB * Ni * Nj * BT; idx += blockDim.x) {
-      const int bt = idx % BT, rem = idx / BT, rl = rem % Nj, rem2 = rem / Nj, ri = rem2 % Ni, ab = rem2 / Ni;
-      const int pix = (fi + ri) * b.Nrad + fj + rl;
-      sR[((ab * MAXN + ri) * MAXN + rl) * BT + bt] = Rt[((int64_t)ab * b.Npix + pix) * gstride + blk0 + bt];
-    }
-    __syncthreads();
-    // stage 1: U_a[ri][rk][blk] = sum_b sum_rl R_ab[ri][rl][blk] J_b[rk][rl]; thread -> (a, ri, blk), all rk
-    {
-      const int s_blk = tid % BT, s_ri = (tid / BT) % MAXN, s_a = tid / (BT * MAXN);
-      if (s_a < NCH && s_ri < Ni) {
-        double u[MAXN];
-#pragma unroll
-        for (int q = 0; q < MAXN; q++) u[q] = 0.0;
-        for (int bb = 0; bb < NCH; bb++)
-          for (int rl = 0; rl < Nj; rl++) {
-            const double r = sR[(((s_a * NCH + bb) * MAXN + s_ri) * MAXN + rl) * BT + s_blk];
-            const double *jrow = sJ + (bb * MAXN + rl) * MAXN;
-#pragma unroll
-            for (int q = 0; q < MAXN; q++) u[q] += r * jrow[q];
-          }
-#pragma unroll
-        for (int q = 0; q < MAXN; q++) sU[((s_a * MAXN + s_ri) * MAXN + q) * BT + s_blk] = u[q];
-      }
-    }
-    __syncthreads();
-    // stage 2: acc[rj] += sum_ri I_a[rj][ri] U_a[ri][rk][blk]
-    if (t_a < NCH && t_rk < Nj) {
-      for (int ri = 0; ri < Ni; ri++) {
-        const double u = sU[((t_a * MAXN + ri) * MAXN + t_rk) * BT + t_blk];
-#pragma unroll
-        for (int q = 0; q < MAXN; q++) acc[q] += sI[(t_a * MAXN + q) * MAXN + ri] * u;
-      }
-    }
-  }
-  // combine the NCH halves through shared memory and write
-  __syncthreads();
-  double *sC = sm;  // reuse: [NCH][MAXN rj][MAXN rk][BT]
-  if (t_a < NCH) {
-#pragma unroll
-    for (int q = 0; q < MAXN; q++) sC[((t_a * MAXN + q) * MAXN + t_rk) * BT + t_blk] = acc[q];
-  }
-  __syncthreads();
-  for (int idx = tid; idx < Ni * Nj * BT; idx += blockDim.x) {
-    const int bt = idx % BT, rem = idx / BT, rk = rem % Nj, rj = rem / Nj;
-    double s = 0.0;
-    for (int a = 0; a < NCH; a++) s += sC[((a * MAXN + rj) * MAXN + rk) * BT + bt];
-    double *c = it.C + (int64_t)(rj * Nj + rk) * gstride + blk0 + bt;
-    *c = s + (it.accumulate ? *c : 0.0);
-  }
-}
 
 // ---------------------------------------------------------------------------
 // Exchange, cross-element pairs on the FP64 tensor pipe.
