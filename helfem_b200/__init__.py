@@ -36,7 +36,7 @@ class _TablesInfo(ctypes.Structure):
 
 EXPORTED_SYMBOLS = [
     "hfq_last_error", "hfq_tables_atomic", "hfq_tables_atomic_yukawa", "hfq_tables_atomic_erfc",
-    "hfq_tables_set_pair_tensors", "hfq_tables_get_pair_tensor", "hfq_erfc_phi", "hfq_tables_sadatom", "hfq_tables_sadatom_rs", "hfq_tables_diatomic", "hfq_tables_from_arrays", "hfq_tables_get_info",
+    "hfq_tables_set_pair_tensors", "hfq_sap_table", "hfq_tables_get_pair_tensor", "hfq_erfc_phi", "hfq_tables_sadatom", "hfq_tables_sadatom_rs", "hfq_tables_diatomic", "hfq_tables_from_arrays", "hfq_tables_get_info",
     "hfq_tables_get_ints", "hfq_tables_get_doubles", "hfq_tables_get_block", "hfq_tables_one_electron",
     "hfq_tables_destroy", "hfq_create", "hfq_destroy", "hfq_nbf", "hfq_set_absm_symmetric", "hfq_coulomb",
     "hfq_exchange", "hfq_coulomb_device", "hfq_exchange_device", "hfq_last_timings", "hfq_exchange_output_pattern",
@@ -64,6 +64,8 @@ def lib():
     L.hfq_tables_get_pair_tensor.restype = i64
     L.hfq_erfc_phi.argtypes = [ci, cd, cd]
     L.hfq_erfc_phi.restype = cd
+    L.hfq_sap_table.argtypes = [vp, vp, vp, ci, ci, vp, i64]
+    L.hfq_sap_table.restype = i64
     L.hfq_tables_sadatom.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ci, cd, ci, cd, ci]
     L.hfq_tables_sadatom_rs.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ci, cd, ci, cd, ci, ci, cd]
     L.hfq_tables_diatomic.argtypes = [ctypes.POINTER(vp), ci, ci, cd, _c_int_p, ci, ci, ci, cd, ci, cd, ci]
@@ -466,6 +468,25 @@ class SadatomTwoDBasis:
         self._rs = _BasisBase(self._k._device)
         self._rs._tables = Tables.sadatom_rs(*self._args, rs=2, param=mu)
         return self
+
+    def sap_table(self, Pl_a, Pl_b=None, x_func=1):
+        """effective_potential_table (src/sadatom/main.cpp:55-107): rows (nucleus, then element x node), columns
+        r, rho, grad rho, lapl rho, tau, v_coul, v_xc, weight, Z_eff.  Host-side post-processing."""
+        t = self._k.tables
+        N = t.Nrad
+        pack = lambda cube: np.ascontiguousarray(np.stack([np.asfortranarray(np.asarray(c, dtype=np.float64)).T
+                                                          for c in cube]))
+        if len(Pl_a) != self.lmax + 1 or (Pl_b is not None and len(Pl_b) != self.lmax + 1):
+            raise ValueError("Density matrix am does not match basis set!")
+        a = pack(Pl_a)
+        if a.shape != (len(Pl_a), N, N):
+            raise ValueError("Density matrix does not match basis set!")
+        b = None if Pl_b is None else pack(Pl_b)
+        need = int(_check(lib().hfq_sap_table(t._h, None, None, 0, 0, None, 0)))
+        out = np.empty(need)
+        rows = int(_check(lib().hfq_sap_table(t._h, a.ctypes.data, None if b is None else b.ctypes.data, len(Pl_a),
+                                              x_func, out.ctypes.data, need)))
+        return out.reshape(9, rows).T
 
     def rs_exchange(self, cube):
         """src/sadatom/basis.cpp:314-420."""

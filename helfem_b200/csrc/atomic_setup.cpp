@@ -514,6 +514,144 @@ BasisTables build_sadatom_rs_tables(int Z, int lmax, int nelem, int nnodes, doub
 }
 
 // ---------------------------------------------------------------------------
+// SAP table (see tables.h).  Points: the nucleus, then (element, Chebyshev node).
+// ---------------------------------------------------------------------------
+std::vector<double> sap_table(const BasisTables &t, const double *Pl_a, const double *Pl_b, int nl, int x_func) {
+  if (t.kind == BasisKind::Diatomic || t.bval.empty()) throw std::logic_error("sap_table: atomic basis built by this library required");
+  if (!Pl_a || nl < 1) throw std::logic_error("Error - density matrix is empty!\n");
+  const FEBasis fe(t.nnodes, t.bval, true, true);
+  const int Nel = t.Nel, N = t.Nrad, nq = t.nquad, npts = Nel * nq + 1;
+  const double pi = std::acos(-1.0);
+  const size_t NN = (size_t)N * N;
+  // total, spin and l(l+1)-weighted radial density matrices
+  std::vector<double> P(NN, 0.0), Pa(NN, 0.0), Pb(NN, 0.0), Plw(NN, 0.0);
+  for (int l = 0; l < nl; l++)
+    for (size_t k = 0; k < NN; k++) {
+      const double a = Pl_a[(size_t)l * NN + k], b = Pl_b ? Pl_b[(size_t)l * NN + k] : 0.0;
+      Pa[k] += a;
+      Pb[k] += b;
+      P[k] += a + b;
+      Plw[k] += l * (l + 1.0) * (a + b);
+    }
+  if (!Pl_b)   // restricted: both spin channels hold half of the density (basis.cpp:1019-1022)
+    for (size_t k = 0; k < NN; k++) Pa[k] = Pb[k] = 0.5 * P[k];
+  std::vector<double> xq, wq;
+  chebyshev_rule(nq, xq, wq);
+  std::vector<double> out((size_t)npts * 9, 0.0);
+  auto col = [&](int c) { return out.data() + (size_t)c * npts; };
+  auto sub = [&](const std::vector<double> &M, int f, int i, int j) { return M[(size_t)(f + i) + (size_t)(f + j) * N]; };
+  // quadratic form sum_ij M_ij u_i v_j over the element block
+  auto qform = [&](const std::vector<double> &M, int f, int n, const Mat &U, const Mat &V, int q) {
+    double s = 0.0;
+    for (int j = 0; j < n; j++) {
+      double c = 0.0;
+      for (int i = 0; i < n; i++) c += U(q, i) * sub(M, f, i, j);
+      s += c * V(q, j);
+    }
+    return s;
+  };
+  // cross-element parts of the Hartree potential: traces with r^0 and r^-1 weighted overlaps of B/r
+  auto bfR = [&](const std::vector<double> &x, int iel) { return radial_bf(fe, x, iel); };
+  std::vector<double> zero(Nel, 0.0), minusone(Nel, 0.0);
+  for (int e = 0; e < Nel; e++) {
+    const int f = fe.first(e), n = fe.nprim(e);
+    const Mat m0 = element_integral_auto(fe, e, bfR, [](double r) { return r * r; }, -1);
+    const Mat m1 = element_integral_auto(fe, e, bfR, [](double r) { return r; }, -1);
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j < n; j++) {
+        zero[e] += sub(P, f, i, j) * m0(j, i);
+        minusone[e] += sub(P, f, i, j) * m1(j, i);
+      }
+  }
+  for (int e = 1; e < Nel; e++) zero[e] += zero[e - 1];
+  for (int e = Nel - 2; e >= 0; e--) minusone[e] += minusone[e + 1];
+  // nucleus: rho(0) = P_uv B_u'(0) B_v'(0) (RadialBasis.cpp:962-977); the other columns stay zero there
+  {
+    const Mat der = fe.eval_dnf(std::vector<double>{-1.0}, 1, 0);
+    col(1)[0] = qform(P, fe.first(0), fe.nprim(0), der, der, 0);
+  }
+  for (int e = 0; e < Nel; e++) {
+    const int f = fe.first(e), n = fe.nprim(e);
+    const std::vector<double> r = fe.coord(xq, e);
+    // B/r and its first two derivatives at the nodes (RadialBasis.cpp:868-926)
+    Mat bf, df, lf;
+    if (e == 0) {
+      bf = fe.eval_over_r(xq, 0, e);
+      df = fe.eval_over_r(xq, 1, e);
+      lf = fe.eval_over_r(xq, 2, e);
+    } else {
+      const Mat B0 = fe.eval_dnf(xq, 0, e), B1 = fe.eval_dnf(xq, 1, e), B2 = fe.eval_dnf(xq, 2, e);
+      bf = B0, df = B0, lf = B0;
+      for (int j = 0; j < n; j++)
+        for (int q = 0; q < nq; q++) {
+          const double ir = 1.0 / r[q];
+          bf(q, j) = B0(q, j) * ir;
+          df(q, j) = (-B0(q, j) * ir + B1(q, j)) * ir;
+          lf(q, j) = ((2.0 * B0(q, j) * ir - 2.0 * B1(q, j)) * ir + B2(q, j)) * ir;
+        }
+    }
+    // in-element Hartree potential (quadrature.cpp:251-292): for node ip
+    //   V = (1/r_ip) int_rmin^r_ip B_i B_j dr + int_r_ip^rmax B_i B_j / r dr, contracted with P
+    const double rmin = fe.begin(e), rmax = fe.end(e), rmid0 = fe.mid(e), rlen0 = fe.scale(e);
+    auto seg = [&](double lo, double hi, bool inv_r) {   // sum_ij P_ij int_lo^hi B_i B_j w(r) dr, w = 1/hi or 1/r
+      const double mid = 0.5 * (hi + lo), len = 0.5 * (hi - lo);
+      std::vector<double> xp(nq);
+      for (int q = 0; q < nq; q++) xp[q] = (mid + len * xq[q] - rmid0) / rlen0;
+      const Mat prim = lip_eval(xp, fe.nodes(), 0);
+      const std::vector<int> en = fe.enabled(e);
+      double s = 0.0;
+      for (int q = 0; q < nq; q++) {
+        const double rs = mid + len * xq[q], w = wq[q] * len * (inv_r ? 1.0 / rs : 1.0 / hi);
+        double v = 0.0;
+        for (int j = 0; j < n; j++) {
+          double c = 0.0;
+          for (int i = 0; i < n; i++) c += prim(q, en[i]) * sub(P, f, i, j);
+          v += c * prim(q, en[j]);
+        }
+        s += w * v;
+      }
+      return s;
+    };
+    std::vector<double> zin(nq), mout(nq);
+    for (int ip = 0; ip < nq; ip++) {
+      zin[ip] = seg(ip ? r[ip - 1] : rmin, r[ip], false);
+      mout[ip] = seg(r[ip], ip < nq - 1 ? r[ip + 1] : rmax, true);
+    }
+    for (int ip = 0; ip < nq; ip++) {
+      const int p = 1 + e * nq + ip;
+      double V = 0.0;
+      for (int jp = 0; jp <= ip; jp++) V += zin[jp] * r[jp];
+      V /= r[ip];
+      for (int jp = ip; jp < nq; jp++) V += mout[jp];
+      if (e > 0) V += zero[e - 1] / r[ip];
+      if (e != Nel - 1) V += minusone[e + 1];
+      const double rho = qform(P, f, n, bf, bf, ip), fd = qform(P, f, n, bf, df, ip), dd = qform(P, f, n, df, df, ip);
+      col(0)[p] = r[ip];
+      col(1)[p] = rho;
+      col(2)[p] = 2.0 * fd;
+      col(3)[p] = 2.0 * (dd + qform(P, f, n, bf, lf, ip)) + 4.0 * fd / r[ip];
+      col(4)[p] = 0.5 * (dd + std::max(qform(Plw, f, n, bf, bf, ip) / (r[ip] * r[ip]), 0.0));
+      col(5)[p] = V * r[ip];
+      if (x_func == 1) {
+        // LDA exchange, spin-polarised: v_sigma = -(6 rho_sigma / pi)^(1/3) on rho / (4 pi) (basis.cpp:1025-1027),
+        // libxc's default density threshold of XC_LDA_X; averaged over the spin channels (main.cpp:73-87)
+        double v = 0.0;
+        for (const std::vector<double> *Ps : {&Pa, &Pb}) {
+          const double rs = qform(*Ps, f, n, bf, bf, ip) / (4.0 * pi);
+          if (rs > 1e-24) v += -std::cbrt(6.0 * rs / pi);
+        }
+        col(6)[p] = 0.5 * v * r[ip];
+      } else if (x_func > 1) {
+        throw std::logic_error("sap_table: only LDA exchange (id 1) is built in");
+      }
+      col(7)[p] = wq[ip] * fe.scale(e);
+    }
+  }
+  for (int p = 0; p < npts; p++) col(8)[p] = t.Z1 - (col(5)[p] + col(6)[p]);
+  return out;
+}
+
+// ---------------------------------------------------------------------------
 // shared BasisTables helpers
 // ---------------------------------------------------------------------------
 

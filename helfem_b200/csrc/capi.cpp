@@ -243,6 +243,19 @@ int hfq_tables_from_arrays(hfq_tables **out, const hfq_tables_desc *d) {
   });
 }
 
+int64_t hfq_sap_table(const hfq_tables *h, const double *Pl_a, const double *Pl_b, int nl, int x_func, double *out,
+                      int64_t cap) {
+  if (!h) return fail(HFQ_ERR_INVALID, "hfq_sap_table: null argument");
+  const int64_t need = ((int64_t)h->t.Nel * h->t.nquad + 1) * 9;
+  if (!out) return need;
+  if (cap < need) return fail(HFQ_ERR_INVALID, "hfq_sap_table: buffer too small");
+  return guarded([&] {
+    const std::vector<double> v = hfq::sap_table(h->t, Pl_a, Pl_b, nl, x_func);
+    std::memcpy(out, v.data(), v.size() * sizeof(double));
+    return (int)(v.size() / 9);
+  });
+}
+
 int hfq_tables_get_info(const hfq_tables *h, hfq_tables_info *info) {
   if (!h || !info) return fail(HFQ_ERR_INVALID, "hfq_tables_get_info: null argument");
   const hfq::BasisTables &t = h->t;

@@ -91,6 +91,15 @@ BasisTables build_sadatom_rs_tables(int Z, int lmax, int nelem, int nnodes, doub
 BasisTables build_diatomic_tables(int Z1, int Z2, double Rbond, const std::vector<int> &lmax_per_m, int nelem,
                                   int nnodes, double Rmax, int igrid, double zexp, int nquad);
 
+// Radial effective-potential ("SAP") table of the spherically averaged atom after an SCF
+// (effective_potential_table, src/sadatom/main.cpp:55-107, with coulomb_screening / xc_screening /
+// electron_density* / kinetic_energy_density of src/sadatom/basis.cpp).  Pl_a / Pl_b: nl per-l radial density
+// matrices (Nrad x Nrad, column-major, concatenated); Pl_b == nullptr: restricted, Pl_a is the total density.
+// x_func: 1 = LDA exchange (the SAP functional), <= 0 = no xc screening.  Returns (Nel*nquad + 1) rows x 9
+// columns, column-major: r, rho, grad rho, lapl rho, tau, v_coul, v_xc, quadrature weight, Z_eff.
+// Host-side post-processing (once per atom), like the reference's.
+std::vector<double> sap_table(const BasisTables &t, const double *Pl_a, const double *Pl_b, int nl, int x_func);
+
 // One-electron matrices (overlap, kinetic, nuclear attraction), dense Nbf x Nbf
 // column-major -- setup helpers so that callers/tests can run an SCF around the
 // Fock-build path (src/atomic/TwoDBasis.cpp:320-375, src/diatomic/basis.cpp:1032-1166).

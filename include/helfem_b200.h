@@ -126,6 +126,17 @@ int hfq_tables_get_block(const hfq_tables *t, int ilm, int iel, double *small_, 
 /* overlap / kinetic / nuclear attraction, Nbf x Nbf column-major (setup helpers,
  * src/atomic/TwoDBasis.cpp:320-375, src/diatomic/basis.cpp:1032-1166) */
 int hfq_tables_one_electron(const hfq_tables *t, double *S, double *T, double *V);
+/* Radial effective-potential (SAP) table of a spherically averaged atom after an SCF:
+ * effective_potential_table (src/sadatom/main.cpp:55-107) = radii, electron_density{,_gradient,_laplacian},
+ * kinetic_energy_density, coulomb_screening, xc_screening, quadrature_weights of src/sadatom/basis.cpp.
+ * Pl_a / Pl_b: nl per-l radial density matrices (Nrad x Nrad column-major, concatenated); Pl_b == NULL:
+ * restricted (Pl_a holds the total per-l density).  x_func = 1: LDA exchange (the SAP functional,
+ * src/general/sap.h:40-43), <= 0: no xc screening.  out: (Nel*nquad + 1) x 9 column-major -- r, rho, grad rho,
+ * lapl rho, tau, v_coul, v_xc, weight, Z_eff = Z - (v_coul + v_xc).  Returns the number of rows; with
+ * out == NULL the number of doubles needed.  Host-side post-processing, no GPU involved (as in the reference:
+ * once per atom, after the SCF). */
+int64_t hfq_sap_table(const hfq_tables *t, const double *Pl_a, const double *Pl_b, int nl, int x_func, double *out,
+                      int64_t cap);
 void hfq_tables_destroy(hfq_tables *t);
 
 /* ---- the Fock-build path ------------------------------------------------------------------- */

@@ -3,6 +3,7 @@ src/sadatom/basis.cpp:186-207 (coulomb, L = 0 only) and :209-312 (exchange with 
 squared Gaunt coupling).  Radial caches are those of the atomic oracle.  Test infrastructure only."""
 import numpy as np
 
+from . import fem as fem_mod
 from .gaunt import Gaunt
 
 
@@ -169,3 +170,141 @@ class SadatomDFTGrid:
                     Hc[l][a:b + 1, a:b + 1] += H + l * (l + 1) * Hl
         Exc = float(np.sum(self._w * np.asarray(exc).reshape(-1) * self._rho.sum(axis=1))) if exc is not None else 0.0
         return Ha, Hb, Exc
+
+
+class SapTable:
+    """Radial effective-potential ("SAP") table of the spherically averaged atom: oracle restatement of
+    src/sadatom/main.cpp:55-107 (effective_potential_table) and the pieces it calls in src/sadatom/basis.cpp:
+    radii :564-578, quadrature_weights :486-499, electron_density :683-718 (nucleus value via
+    libhelfem/src/RadialBasis.cpp:962-977), electron_density_gradient :912-936, electron_density_laplacian
+    :938-964, kinetic_energy_density :966-1017, coulomb_screening :501-562 (in-element potential
+    libhelfem/src/quadrature.cpp:251-292), xc_screening :1019-1179 for LDA exchange (the SAP functional,
+    src/general/sap.h:40-43).  Point 0 is the nucleus; points 1.. are (element, quadrature node).
+    Columns: r, rho, grad rho, lapl rho, tau, v_coul, v_xc, quadrature weight, Z_eff = Z - (v_coul + v_xc).
+    Test infrastructure only."""
+
+    LDA_X_DENS_THRESHOLD = 1e-24    # libxc's default density threshold of XC_LDA_X
+
+    def __init__(self, atomic_basis, Z):
+        from .dftgrid_atomic import AtomicDFTGrid
+        self.b = atomic_basis
+        self.Z = Z
+        self._rad = AtomicDFTGrid(atomic_basis, 1, 1)._radial
+
+    def _blocks(self, Prad):
+        rb = self.b.radial
+        for iel in range(rb.Nel()):
+            a, b = rb.get_idx(iel)
+            r, wrad, f, d, l2 = self._rad(iel)
+            yield iel, np.asarray(Prad)[a:b + 1, a:b + 1], r, wrad, f, d, l2
+
+    def _assemble(self, per_el, first=0.0):
+        return np.concatenate([[first]] + list(per_el))
+
+    def radii(self):
+        return self._assemble(r for _, _, r, *_ in self._blocks(np.zeros((self.b.Nrad(),) * 2)))
+
+    def quadrature_weights(self):
+        return self._assemble(w for _, _, _, w, *_ in self._blocks(np.zeros((self.b.Nrad(),) * 2)))
+
+    def nuclear_density(self, Prad):
+        """P_uv B_u'(0) B_v'(0) / (4 pi), RadialBasis.cpp:962-977, basis.cpp:479-481."""
+        rb = self.b.radial
+        der = rb.fem.eval_dnf(np.array([-1.0]), 1, 0)
+        a, b = rb.get_idx(0)
+        return (der @ np.asarray(Prad)[a:b + 1, a:b + 1] @ der.T).item() / (4.0 * np.pi)
+
+    def electron_density(self, Prad):
+        return self._assemble((np.sum((f @ P) * f, axis=1) for _, P, r, w, f, d, l2 in self._blocks(Prad)),
+                              4.0 * np.pi * self.nuclear_density(Prad))
+
+    def electron_density_gradient(self, Prad):
+        return self._assemble(2.0 * np.sum((f @ P) * d, axis=1) for _, P, r, w, f, d, l2 in self._blocks(Prad))
+
+    def electron_density_laplacian(self, Prad):
+        return self._assemble(2.0 * (np.sum((d @ P) * d, axis=1) + np.sum((f @ P) * l2, axis=1))
+                              + 4.0 * np.sum((f @ P) * d, axis=1) / r for _, P, r, w, f, d, l2 in self._blocks(Prad))
+
+    def kinetic_energy_density(self, cube):
+        P = sum(np.asarray(c) for c in cube)
+        Pl = sum(l * (l + 1) * np.asarray(c) for l, c in enumerate(cube))
+        rb = self.b.radial
+        out = []
+        for iel, Psub, r, w, f, d, l2 in self._blocks(P):
+            a, b = rb.get_idx(iel)
+            t1 = np.sum((d @ Psub) * d, axis=1)
+            t2 = np.sum((f @ Pl[a:b + 1, a:b + 1]) * f, axis=1) / (r * r)
+            out.append(0.5 * (t1 + np.maximum(t2, 0.0)))
+        return self._assemble(out)
+
+    def spherical_potential(self, iel):
+        """V[ip, (i,j)] = (1/r_ip) int_rmin^r_ip B_i B_j dr + int_r_ip^rmax B_i B_j / r dr, each sub-interval
+        integrated with the element's own rule mapped onto it (quadrature.cpp:251-292, :37-74)."""
+        rb = self.b.radial
+        x, wx = rb.xq, rb.wq
+        rmin, rmax = rb.fem.begin(iel), rb.fem.end(iel)
+        rmid0, rlen0 = 0.5 * (rmax + rmin), 0.5 * (rmax - rmin)
+        r = rmid0 + rlen0 * x
+        en = rb.fem.enabled(iel)
+        x0 = rb.fem.x0
+        nq = len(x)
+
+        def seg(lo, hi, wfun):
+            mid, ln = 0.5 * (hi + lo), 0.5 * (hi - lo)
+            rs = mid + ln * x
+            bf = fem_mod.lip_eval((rs - rmid0) / rlen0, x0, 0)[:, en]
+            wp = wx * wfun(rs, hi) * ln
+            return ((bf * wp[:, None]).T @ bf).reshape(-1, order="F")
+
+        zero = np.array([seg(r[ip - 1] if ip else rmin, r[ip], lambda rr, R: np.full_like(rr, 1.0 / R)) for ip in range(nq)])
+        minusone = np.array([seg(r[ip], r[ip + 1] if ip < nq - 1 else rmax, lambda rr, R: 1.0 / rr) for ip in range(nq)])
+        V = np.zeros_like(zero)
+        for ip in range(nq):
+            V[ip] = (zero[:ip + 1] * r[:ip + 1, None]).sum(axis=0) / r[ip] + minusone[ip:].sum(axis=0)
+        return V
+
+    def coulomb_screening(self, Prad):
+        """r * V_H(r) at the table points (0 at the nucleus), basis.cpp:501-562."""
+        rb = self.b.radial
+        Nel = rb.Nel()
+        zero, minusone = np.zeros(Nel), np.zeros(Nel)
+        for iel, Psub, *_ in self._blocks(Prad):
+            zero[iel] = np.sum(Psub * rb.radial_integral(0, iel).T)
+            minusone[iel] = np.sum(Psub * rb.radial_integral(-1, iel).T)
+        zero = np.cumsum(zero)
+        minusone = np.cumsum(minusone[::-1])[::-1]
+        out = []
+        for iel, Psub, r, *_ in self._blocks(Prad):
+            V = self.spherical_potential(iel) @ Psub.reshape(-1, order="F")
+            if iel > 0:
+                V = V + zero[iel - 1] / r
+            if iel != Nel - 1:
+                V = V + minusone[iel + 1]
+            out.append(V * r)
+        return self._assemble(out)
+
+    def xc_screening(self, Pa, Pb):
+        """r * v_x^sigma(r) for LDA exchange, spin-polarised formula v_sigma = -(6 rho_sigma / pi)^(1/3)
+        (what libxc's XC_LDA_X returns for XC_POLARIZED), densities divided by 4 pi (basis.cpp:1025-1027)."""
+        r = self.radii()
+        cols = []
+        for P in (Pa, Pb):
+            rho = self.electron_density(P) / (4.0 * np.pi)
+            v = np.where(rho > self.LDA_X_DENS_THRESHOLD, -np.cbrt(6.0 * np.maximum(rho, 0.0) / np.pi), 0.0)
+            cols.append(v * r)
+        return np.stack(cols, axis=1)
+
+    def table(self, Pl_a, Pl_b=None):
+        """effective_potential_table, main.cpp:55-107; restricted when Pl_b is None (Pl_a = total per-l density)."""
+        restricted = Pl_b is None
+        Pl = [np.asarray(c) for c in Pl_a] if restricted else [np.asarray(a) + np.asarray(b) for a, b in zip(Pl_a, Pl_b)]
+        P = sum(Pl)
+        if restricted:
+            v = self.xc_screening(P / 2, P / 2)
+            vxc = 0.5 * (v[:, 0] + v[:, 1])
+        else:
+            vxc = self.xc_screening(sum(np.asarray(c) for c in Pl_a), sum(np.asarray(c) for c in Pl_b)).mean(axis=1)
+        vcoul = self.coulomb_screening(P)
+        cols = [self.radii(), self.electron_density(P), self.electron_density_gradient(P), self.electron_density_laplacian(P),
+                self.kinetic_energy_density(Pl), vcoul, vxc, self.quadrature_weights(), self.Z - (vcoul + vxc)]
+        return np.stack(cols, axis=1)

@@ -143,3 +143,34 @@ def test_pair_tensor_round_trip(hb):
                 assert np.array_equal(T.pair_tensor(L, ie, je), ob.rs_ktei[(L * Nel + ie) * Nel + je])
     with pytest.raises(ValueError):
         T.set_pair_tensors(ob.rs_ktei[:-1])
+
+
+def test_sap_table_matches_oracle_and_physics(hb):
+    """hfq_sap_table (host-side, src/sadatom/main.cpp:55-107) against the oracle restatement, for a converged Be RHF
+    density: the reference's own printed checks hold (electron count and Coulomb energy by quadrature), Z_eff runs
+    from Z at the nucleus to Z - N + (xc tail -> 0) far out."""
+    from oracle import sadatom as osad, scf
+    Z = 4
+    ob = cases.oracle_atomic(Z, 0, 0, 5)
+    S, T, V = ob.overlap(), ob.kinetic(), ob.nuclear()
+    r = scf.rhf(S, T + V, ob.coulomb, ob.exchange, [2], [np.arange(ob.Nbf())])
+    P = r["P"]
+    st = osad.SapTable(ob, Z)
+    sb = hb.SadatomTwoDBasis(Z, 1, 5).compute_tei()
+    N = ob.Nrad()
+    Pp = 1e-3 * np.outer(np.linspace(0, 1, N) ** 2, np.linspace(0, 1, N) ** 2)       # a little l = 1 density
+    for Pa, Pb in (([P, Pp], None), ([0.6 * P, 0.5 * Pp], [0.4 * P, 0.5 * Pp])):
+        to, tg = st.table(Pa, Pb), sb.sap_table(Pa, Pb)
+        assert to.shape == tg.shape == (5 * 75 + 1, 9)
+        for c in range(9):
+            # derivative columns (grad, lapl, tau) are sums of large terms of alternating sign near the nucleus
+            tol = 1e-10 if c in (2, 3, 4) else 1e-12
+            assert np.abs(to[:, c] - tg[:, c]).max() <= tol * max(np.abs(to[:, c]).max(), 1.0), c
+    tab = sb.sap_table([P, np.zeros((N, N))])
+    rr, rho, vc, w, zeff = tab[:, 0], tab[:, 1], tab[:, 5], tab[:, 7], tab[:, 8]
+    assert abs(np.sum(w * rho * rr * rr) - 4.0) < 1e-10                       # main.cpp:101-102
+    assert abs(0.5 * np.sum(rr * rho * w * vc) - r["Coulomb"]) < 1e-9         # main.cpp:103-104
+    assert zeff[0] == Z and abs(zeff[-1]) < 1e-6 and abs(vc[-1] - 4.0) < 1e-10
+    assert np.all(np.diff(vc[1:]) > -1e-9)                                    # r V_H(r) = charge inside r grows
+    with pytest.raises(ValueError):
+        sb.sap_table([P])                                                     # wrong number of l blocks is caught below
