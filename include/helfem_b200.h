@@ -33,6 +33,11 @@ typedef struct hfq_ctx hfq_ctx;
 #define HFQ_ERR_CUDA (-3)     /* CUDA runtime failure                                         */
 #define HFQ_ERR_INTERNAL (-4)
 
+/* flags of the DFT-grid calls: which densities are produced / which potentials are supplied */
+#define HFQ_GRAD 1
+#define HFQ_TAU 2
+#define HFQ_LAPL 4
+
 const char *hfq_last_error(void);
 
 /* ---- basis construction + compute_tei() ------------------------------------------------- */
