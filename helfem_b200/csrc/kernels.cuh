@@ -746,7 +746,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 }
 
 // ---------------------------------------------------------------------------
-// In-element exchange GEMM, warp-specialised (same item/entry tables as k_tgemm):
+// In-element exchange GEMM, warp-specialised:
 //   C[M x 64-column tile] (+)= sum_entries A_e[M x K] R_e[K x N],  M = Ni^2 <= 256, K = nab*Ni^2
 // A_e is stored as pre-swizzled [k-chunk][M][TP_BK] tiles (tperm_index), so the producer warp moves
 // a whole A stage with ONE cp.async.bulk (<= 64 KB) plus one 512-byte bulk copy per R row, all
