@@ -1,7 +1,7 @@
 """Secondary measurements on BASELINE.json's other configurations: C1 Ne RHF, C2 Xe UHF, C3 Kr
 (bare K, erfc rs_exchange).  GPU: device-resident builds through the C ABI (CUDA-event timings of the library);
 CPU: the C restatement of the reference's loops (oracle/csrc/jk_oracle.c, all host cores) on the same caches.
-One JSON line per configuration.   python tools/bench_configs.py [ne xe kr]"""
+One JSON line per configuration.   python tests/measure/bench_configs.py [ne xe kr]"""
 import json, sys, time
 import numpy as np, torch
 sys.path.insert(0, '.')

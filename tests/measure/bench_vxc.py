@@ -1,7 +1,7 @@
 """Secondary measurement: DFT-grid path (density + XC-matrix assembly) on the GPU next to the
 reference algorithm (numpy oracle: materialised tables + BLAS GEMMs, as src/*/dftgrid*.cpp).
 Prints one JSON line per configuration.  Functional-independent: synthetic v arrays.
-  python tools/bench_vxc.py [kr|n2]"""
+  python tests/measure/bench_vxc.py [kr|n2]"""
 import json, sys, time
 import numpy as np
 sys.path.insert(0, '.')
