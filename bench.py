@@ -24,6 +24,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 
+class _BasisShape:
+    def __init__(self, Nrad, lval, mval):
+        self.Nrad, self.lval, self.mval = int(Nrad), np.asarray(lval), np.asarray(mval)
+        self.Nbf = int(sum(self.Nrad - (1 if m != 0 else 0) for m in self.mval))
+
+
 def n2_density(T, seed=42):
     """Synthetic closed-shell density with the N2 ground-state structure: 3 sigma_g (even l) and
     2 sigma_u (odd l) doubly-occupied orbitals in m=0, one pi_u orbital (odd l) in each of m=+1
@@ -79,23 +85,70 @@ class ClockSampler(threading.Thread):
                 "power_w_max": max(float(r[2]) for r in self.rows)}
 
 
-def cpu_sample(T, P, nblocks, jrows):
-    """Reference algorithm (C oracle, OpenMP) on a bounded sample; returns seconds per full
-    build extrapolated, and the sample description."""
+def cpu_reference_build(C, P, kscale, blocks_per_thread=8, jstride=8, threads=None):
+    """One Fock build (J = coulomb(P), K = exchange(kscale P)) of the reference algorithm on the host cores, on a
+    bounded sample, extrapolated to the full build.
+
+    K (src/diatomic/basis.cpp:1818-2089, OpenMP over output blocks): the block-norm screening runs once per build
+    and is timed in full (call with zero output blocks); then `blocks_per_thread` x threads of the output blocks that
+    receive density are computed (evenly spaced over the m-diagonal blocks, omp dynamic), and the marginal cost per
+    block is scaled to all of them: t_K = t_screen + (t_sample - t_screen) * nblocks / nsample.
+    J (basis.cpp:1627-1816, serial and unscreened in the reference): every phase is linear in the angular rows /
+    channels visited, a 1/jstride sample is timed: t_J = jstride * t_sample.
+    Returns (seconds per build, dict with the parts, the sampled K blocks for the parity check)."""
     from oracle import cjk
-    cjk.use_all_cores()
-    C = cjk.DiatomicCaches.from_tables(T)
+    nthr = cjk.use_all_cores() if threads is None else threads
+    cjk.lib().jk_set_num_threads(int(nthr))
     Pd = C.expand(P)
-    na = C.Nang
-    # output blocks that actually receive density (m-diagonal for this P), evenly sampled
+    Pk = kscale * Pd
     mv = C.mval
-    cand = [(j, k) for j in range(na) for k in range(na) if mv[j] == mv[k]]
-    step = max(1, len(cand) // nblocks)
-    sel = cand[::step][:nblocks]
+    cand = [(j, k) for j in range(C.Nang) for k in range(C.Nang) if mv[j] == mv[k]]
+    nsel = min(len(cand), max(1, blocks_per_thread * nthr))
+    pick = np.linspace(0, len(cand) - 1, nsel).astype(int)
+    sel = [cand[i] for i in pick]
     t0 = time.perf_counter()
-    C.exchange_blocks(Pd, [s[0] for s in sel], [s[1] for s in sel])
-    tK = (time.perf_counter() - t0) * len(cand) / len(sel)
-    return C, Pd, tK, len(sel), len(cand)
+    C.exchange_blocks(Pk, [], [])
+    t_screen = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    blk = C.exchange_blocks(Pk, [s[0] for s in sel], [s[1] for s in sel])
+    t_sample = time.perf_counter() - t0
+    tK = t_screen + max(t_sample - t_screen, 0.0) * len(cand) / nsel
+    tJ = jstride * C.coulomb_timing_sample(Pd, jstride)
+    parts = {"threads": int(nthr), "k_blocks_sampled": nsel, "k_blocks_total": len(cand), "k_screen_s": t_screen,
+             "k_sample_s": t_sample, "k_build_s": tK, "j_stride": jstride, "j_build_s": tJ}
+    return tK + tJ, parts, (sel, blk)
+
+
+def cpu_sample_text(parts):
+    return ("J+K of the reference algorithm (C restatement of src/diatomic/basis.cpp:1627-2089, -O3 -march=native): K = full "
+            "block-norm screening + %d of %d density-carrying output blocks (%d per thread, omp dynamic over blocks like the "
+            "reference), marginal block cost extrapolated; J (serial and unscreened in the reference) = 1/%d sample x %d"
+            % (parts["k_blocks_sampled"], parts["k_blocks_total"], parts["k_blocks_sampled"] // max(parts["threads"], 1),
+               parts["j_stride"], parts["j_stride"]))
+
+
+def parity_of_blocks(C, sel, blk, Kdense, Jdense=None, P=None):
+    """Relative Frobenius error of the GPU K on the CPU-sampled output blocks (and of J against the complete
+    single-M Coulomb build of the oracle)."""
+    pi = C.pure_idx()
+    N = C.Nrad
+    pure = np.zeros(C.Nang * N, dtype=bool)
+    pure[pi] = True
+    pos = np.cumsum(pure) - 1   # dummy index -> dense index
+    num = den = 0.0
+    for b, (j, k) in enumerate(sel):
+        rows = pos[j * N:(j + 1) * N][pure[j * N:(j + 1) * N]]
+        cols = pos[k * N:(k + 1) * N][pure[k * N:(k + 1) * N]]
+        ref = blk[b][np.ix_(pure[j * N:(j + 1) * N], pure[k * N:(k + 1) * N])]
+        got = Kdense[np.ix_(rows, cols)]
+        num += float(np.sum((got - ref) ** 2))
+        den += float(np.sum(ref ** 2))
+    out = {"max_relerr_K": (num / den) ** 0.5 if den > 0 else None, "k_blocks": len(sel)}
+    if Jdense is not None:
+        Jref = C.coulomb(P, single_M=0)
+        out["max_relerr_J"] = float(np.linalg.norm(Jdense - Jref) / np.linalg.norm(Jref))
+        out["j_blocks"] = "all (complete J of the m-diagonal density)"
+    return out
 
 
 def main():
@@ -107,7 +160,8 @@ def main():
     ap.add_argument("--lmax", type=int, default=30)
     ap.add_argument("--mmax", type=int, default=6)
     ap.add_argument("--nelem", type=int, default=3)
-    ap.add_argument("--cpu-blocks", type=int, default=24, help="exchange output blocks in the CPU sample")
+    ap.add_argument("--cpu-blocks-per-thread", type=int, default=16,
+                    help="exchange output blocks per host thread in the CPU sample (>= 4: no idle threads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-mode", action="store_true",
                     help="for runs under ncu only: device-resident steps, no e2e/peak/CPU legs, prints no bench line")
@@ -130,24 +184,32 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        T = hb.Tables.diatomic(7, 7, 2.07, [args.lmax] * (args.mmax + 1), args.nelem)
-        P = n2_density(T)
+        # Inputs: the integral caches (what compute_tei() leaves in memory) come from tools/export_caches.py run in
+        # a subprocess -- this process holds the oracle only.  See that file for why the numpy restatement is not
+        # used for them at lmax = 30.
+        import tempfile
         from oracle import cjk
-        nb = max(8, args.cpu_blocks // 2)
-        times = []
+        npz = os.path.join(tempfile.gettempdir(), "hfq_caches_%d_%d_%d.npz" % (args.lmax, args.mmax, args.nelem))
+        if not os.path.exists(npz):
+            subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "export_caches.py"), npz, "7", "7", "2.07",
+                                   str(args.lmax), str(args.mmax), str(args.nelem)])
+        C = cjk.DiatomicCaches.from_npz(npz)
+        P = n2_density(_BasisShape(C.Nrad, C.lval, C.mval))
+        # every step = one bounded sample of the build, sized so that 25 steps end within a few minutes
+        times, parts = [], None
         for it in range(args.warmup + args.steps):
-            C, Pd, tK, nsel, ncand = cpu_sample(T, 0.5 * P, nb, 0)
+            tB, parts, _ = cpu_reference_build(C, P, 0.5, blocks_per_thread=8, jstride=16)
             if it >= args.warmup:
-                times.append(tK)
-        tK = float(np.median(times)) if times else float("nan")
-        val = 1.0 / tK
+                times.append(tB)
+        tB = float(np.median(times)) if times else float("nan")
+        val = 1.0 / tB
         line = {"metric": "J+K Fock builds/s (N2 HF)", "value": val, "unit": "builds/s", "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tK, "higher_is_better": True,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tB, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
                 "config": config,
-                "cpu_baseline": {"value": val, "unit": "builds/s", "cores": cjk.num_threads(), "kind": "port",
-                                 "sample": "exchange only (dominant; coulomb <1%% of the reference build): %d of %d "
-                                           "m-diagonal output blocks per step, extrapolated linearly" % (nsel, ncand)},
+                "cpu_baseline": {"value": val, "unit": "builds/s", "cores": parts["threads"], "kind": "port",
+                                 "sample": cpu_sample_text(parts), "parts": parts,
+                                 "inputs": "integral caches written by tools/export_caches.py in a subprocess"},
                 "e2e": {"value": val, "unit": "builds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -329,13 +391,23 @@ def main():
                                "cross_element_ms": acc["ms_offdiag"] / nst, "step_ms": ms_step},
                 "alg_tflops_all_kernels": (acc["alg_fold"] + acc["alg_tgemm"] + acc["alg_offdiag"]) / nst / (ms_step * 1e-3) / 1e12}
 
-    cpu_baseline = None
+    cpu_baseline, parity = None, None
     if not args.no_cpu_baseline:
         from oracle import cjk
-        C, Pd, tK, nsel, ncand = cpu_sample(T, 0.5 * P, args.cpu_blocks, 0)
-        cpu_baseline = {"value": 1.0 / tK, "unit": "builds/s", "cores": cjk.num_threads(), "kind": "port",
-                        "sample": "exchange only (dominant): %d of %d m-diagonal output blocks, extrapolated linearly; "
-                                  "C restatement of src/diatomic/basis.cpp:1818-2089 with the reference's OpenMP axis" % (nsel, ncand)}
+        C = cjk.DiatomicCaches.from_tables(T)
+        tB, parts, (sel, blk) = cpu_reference_build(C, P, 0.5, blocks_per_thread=args.cpu_blocks_per_thread, jstride=8)
+        # the sample is also the parity check of THIS run's result at full size: the GPU K on the sampled blocks and
+        # the complete J against the oracle (1e-12, BASELINE.json north_star)
+        Kh = dK.cpu().numpy().T
+        Jh = dJ.cpu().numpy().T
+        parity = parity_of_blocks(C, sel, blk, Kh, Jh, P)
+        parity["tolerance"] = 1e-12
+        assert parity["max_relerr_K"] < 1e-12 and parity["max_relerr_J"] < 1e-12, "GPU result differs from the oracle: %s" % parity
+        # one-thread figure (the reference's own test setting, tests/cases.json defaults.env OMP_NUM_THREADS=1)
+        tB1, parts1, _ = cpu_reference_build(C, P, 0.5, blocks_per_thread=48, jstride=16, threads=1)
+        cpu_baseline = {"value": 1.0 / tB, "unit": "builds/s", "cores": parts["threads"], "kind": "port",
+                        "sample": cpu_sample_text(parts), "parts": parts,
+                        "one_thread_value": 1.0 / tB1, "one_thread_parts": parts1}
 
     nbytes = n * n * 8
     line = {"metric": "J+K Fock builds/s (N2 HF)", "value": value, "unit": "builds/s", "n_gpus": world, "steps": args.steps,
@@ -352,7 +424,7 @@ def main():
                     "speculative_hits": spec_hits,
                     "separate_calls_value": e2e_sep if world == 1 else None,
                     "separate_calls_note": "hfq_coulomb + hfq_exchange issued separately (2 uploads, no overlap)"},
-            "gpu_launches": int(acc["launches"]), "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "gpu_launches": int(acc["launches"]), "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,
             "clocks": sampler.summary(),
             "setup": {"host_compute_tei_s": t_setup, "device_upload_s": t_upload, "Nbf": n, "channels": T.nlm}}
     print(json.dumps(line))

@@ -575,10 +575,17 @@ class DFTGrid:
 
     def __init__(self, basis, lang, mang=1):
         self.basis = basis
-        _check(lib().hfq_grid_attach(basis._context(), lang, mang))
+        self.lang, self.mang = int(lang), int(mang)
+        self._select()
         self.N = int(lib().hfq_grid_npoints(basis._context()))
 
+    def _select(self):
+        # several grids may live on one basis (the reference's diatomic driver holds a 3D and a pure-m grid,
+        # src/diatomic/main.cpp:329-330): attaching an existing (lang, mang) selects it
+        _check(lib().hfq_grid_attach(self.basis._context(), self.lang, self.mang))
+
     def density(self, Pa, Pb=None, flags=0):
+        self._select()
         n = self.basis.Nbf()
         Pa = _fmat(Pa, n)
         pol = Pb is not None
@@ -602,6 +609,7 @@ class DFTGrid:
         return out
 
     def fxc(self, exc, vrho, vsigma=None, vtau=None, vlapl=None, beta=True):
+        self._select()
         n = self.basis.Nbf()
         Ha = np.zeros((n, n), order="F")
         Hb = np.zeros((n, n), order="F") if self._pol else None
@@ -616,6 +624,7 @@ class DFTGrid:
 
     def eval_Fxc(self, x_func, c_func, P, Pb=None, beta=True, thr=1e-12):
         """Returns (H or (Ha, Hb), Exc, Nel, Ekin)."""
+        self._select()
         n = self.basis.Nbf()
         Pa = _fmat(P, n)
         pol = Pb is not None

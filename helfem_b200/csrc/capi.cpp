@@ -3,6 +3,7 @@
 
 #include <cmath>
 #include <cstring>
+#include <map>
 #include <vector>
 #include <exception>
 #include <mutex>
@@ -20,7 +21,10 @@ struct hfq_tables {
 
 struct hfq_ctx {
   std::unique_ptr<hfq::Engine> eng;
-  std::unique_ptr<hfq::GridEngine> grid;
+  // every DFT grid attached to this basis, keyed by (lang, mang): the reference's diatomic driver holds a 3D
+  // DFTGrid and a PureMDFTGrid on one basis (src/diatomic/main.cpp:329-330); `grid` is the selected one
+  std::map<std::pair<int, int>, std::unique_ptr<hfq::GridEngine>> grids;
+  hfq::GridEngine *grid = nullptr;
   std::mutex mu;  // the reference's gensap driver calls the build from several threads (src/sadatom/scf.cpp:329-334)
 };
 
@@ -457,12 +461,20 @@ int hfq_grid_attach(hfq_ctx *ctx, int lang, int mang) {
   std::lock_guard<std::mutex> lk(ctx->mu);
   return guarded([&] {
     const hfq::BasisTables &bt = ctx->eng->tables();
+    if (bt.kind == hfq::BasisKind::Sadatom) lang = mang = 1;   // radial-only grid: one per basis
+    auto it = ctx->grids.find({lang, mang});
+    if (it != ctx->grids.end()) {   // already attached: select it (densities of its last call are kept)
+      ctx->grid = it->second.get();
+      return HFQ_OK;
+    }
     // atomic: 3D grid; diatomic: mang <= 1 selects the pure-m grid the reference uses at --symmetry >= 1,
     // mang >= 2 the general 3D grid of --symmetry=0
     const hfq::GridTables g = bt.kind == hfq::BasisKind::Atomic    ? hfq::build_atomic_grid(bt, lang, mang)
                               : bt.kind == hfq::BasisKind::Sadatom ? hfq::build_sadatom_grid(bt)
                                                                    : hfq::build_diatomic_grid(bt, lang, mang);
-    ctx->grid = std::make_unique<hfq::GridEngine>(ctx->eng->tables(), g, ctx->eng->device(), ctx->eng->stream());
+    auto ge = std::make_unique<hfq::GridEngine>(ctx->eng->tables(), g, ctx->eng->device(), ctx->eng->stream());
+    ctx->grid = ge.get();
+    ctx->grids[{lang, mang}] = std::move(ge);
     return HFQ_OK;
   });
 }
@@ -489,6 +501,14 @@ int hfq_grid_fxc(hfq_ctx *ctx, int flags, int beta, const double *exc, const dou
                  const double *vtau, const double *vlapl, double *Ha, int64_t ldHa, double *Hb, int64_t ldHb, double *Exc) {
   if (!ctx || !ctx->grid) return fail(HFQ_ERR_STATE, "hfq_grid_fxc: no grid attached");
   if (!vrho || !Ha) return fail(HFQ_ERR_INVALID, "hfq_grid_fxc: null argument");
+  {
+    const int64_t n = ctx->eng->Nbf();
+    if (ldHa < n) return fail(HFQ_ERR_INVALID, "hfq_grid_fxc: ldHa smaller than Nbf");
+    if (ctx->grid->polarized() && beta && (!Hb || ldHb < n))
+      return fail(HFQ_ERR_INVALID, "hfq_grid_fxc: polarised density with beta set needs Hb with ldHb >= Nbf");
+    if ((vtau && !(ctx->grid->density_flags() & HFQ_TAU)) || (vlapl && !(ctx->grid->density_flags() & HFQ_LAPL)))
+      return fail(HFQ_ERR_INVALID, "hfq_grid_fxc: vtau / vlapl given but tau / the Laplacian was not computed by hfq_grid_density");
+  }
   std::lock_guard<std::mutex> lk(ctx->mu);
   return guarded([&] {
     ctx->grid->fxc(flags, beta != 0, exc, vrho, vsigma, vtau, vlapl, Ha, ldHa, Hb, ldHb, Exc);
@@ -524,6 +544,11 @@ int hfq_eval_fxc(hfq_ctx *ctx, int x_func, int c_func, const double *Pa, int64_t
                  double thr) {
   if (!ctx || !ctx->grid) return fail(HFQ_ERR_STATE, "hfq_eval_fxc: no grid attached");
   if (!Pa || !Ha) return fail(HFQ_ERR_INVALID, "Error - density matrix is empty!");
+  {
+    const int64_t n = ctx->eng->Nbf();
+    if (ldPa < n || ldHa < n || (Pb && ldPb < n) || (Pb && beta && (!Hb || ldHb < n)))
+      return fail(HFQ_ERR_INVALID, "hfq_eval_fxc: leading dimension smaller than Nbf, or Hb missing for a polarised build");
+  }
   if (c_func > 0 || (x_func > 0 && x_func != 1))
     return fail(HFQ_ERR_INVALID,
                 "hfq_eval_fxc: only the Slater exchange (libxc id 1) is built in; evaluate other functionals with libxc "

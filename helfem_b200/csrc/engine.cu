@@ -60,6 +60,10 @@ struct DevBuf {
 
 int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+// ntasks == 0: configure the kernel (opt-in shared memory size) on the current device, launch nothing
+void launch_fold(int NT, int nch, bool par, const dev::BasisDev &bd, const dev::FoldTask *tasks, int ntasks,
+                 const double *G, const double *Ppix, double *R, cudaStream_t st);
+
 }  // namespace
 
 struct Engine::Impl {
@@ -480,6 +484,8 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
     CK(cudaFuncSetAttribute(dev::k_tgemm_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   }
   s.d_zrow.upload(std::vector<double>(64, 0.0), &dev_bytes_);
+  // opt-in shared memory of the fold kernel this basis uses (a per-device attribute: set by every engine)
+  launch_fold(s.NT, t.nch, s.parity, s.bd, nullptr, 0, nullptr, nullptr, nullptr, stream_);
 }
 
 
@@ -493,10 +499,9 @@ void launch_fold_t(const dev::BasisDev &bd, const dev::FoldTask *tasks, int ntas
     // register-resident two-stage fold, one pixel per warp
     constexpr int LDJ = (NP % 16 == 0) ? NP + 8 : NP + 16;
     const size_t smem = (size_t)(NCH * NP * LD + NCH * NP * LDJ + 8 * 2 * NP * LD) * sizeof(double);
-    static bool attr_reg = false;
-    if (!attr_reg) {
+    if (ntasks == 0) {   // configuration call from the Engine constructor: the attribute is per device
       CK(cudaFuncSetAttribute(dev::k_fold_reg<NT, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_reg = true;
+      return;
     }
     int ppc = std::max(8, (int)(((int64_t)bd.Npix * ntasks + 148 * 8 - 1) / (148 * 8)));
     ppc = round_up(std::min(std::min(ppc, 64), bd.Npix), 8);
@@ -505,10 +510,9 @@ void launch_fold_t(const dev::BasisDev &bd, const dev::FoldTask *tasks, int ntas
     CK(cudaGetLastError());
     return;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (ntasks == 0) {
     CK(cudaFuncSetAttribute(dev::k_fold<NT, NCH, PAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
+    return;
   }
   const size_t gbytes = (size_t)2 * NCH * NP * LD * sizeof(double);
   const size_t slot = (size_t)(2 + NCH) * NP * LD * sizeof(double);   // 2 P buffers + NCH Y tiles per pixel slot
@@ -593,7 +597,7 @@ void Engine::pack_density(const double *dP, int64_t ldP, cudaStream_t st) {
   std::vector<char> sp_nz((size_t)ns * ns, 0);
   for (int a = 0; a < na; a++)
     for (int b = 0; b < na; b++)
-      if (s.norms_host[(size_t)a * na + b] > 0.0) sp_nz[(size_t)s.ang_sec[a] * ns + s.ang_sec[b]] = 1;
+      if (!(s.norms_host[(size_t)a * na + b] == 0.0)) sp_nz[(size_t)s.ang_sec[a] * ns + s.ang_sec[b]] = 1;
   s.packed_splist.clear();
   for (int sp = 0; sp < ns * ns; sp++)
     if (sp_nz[sp]) s.packed_splist.push_back(sp);
@@ -693,7 +697,7 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
   std::string key((size_t)ns * ns + 3, '0');
   for (int a = 0; a < na; a++)
     for (int b = 0; b < na; b++)
-      if (norms[(size_t)a * na + b] >= thr2) key[(size_t)s.ang_sec[a] * ns + s.ang_sec[b]] = '1';
+      if (!(norms[(size_t)a * na + b] < thr2)) key[(size_t)s.ang_sec[a] * ns + s.ang_sec[b]] = '1';
   key[(size_t)ns * ns] = (char)((absm_symmetric_ ? 'S' : 'N') + (s.p_symmetric ? 1 : 0));
   key[(size_t)ns * ns + 1] = (char)('0' + shard);
   key[(size_t)ns * ns + 2] = (char)('0' + nshards);
@@ -815,7 +819,9 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
       size_t free_b = 0, total_b = 0;
       CK(cudaMemGetInfo(&free_b, &total_b));
       const size_t have = s.d_R.n * sizeof(double);
-      const size_t budget = std::min<size_t>((size_t)48 << 30, (size_t)((free_b + have) * 0.6));
+      size_t budget = std::min<size_t>((size_t)48 << 30, (size_t)((free_b + have) * 0.6));
+      if (const char *env = getenv("HFQ_R_BUDGET_MB"))   // tests: force the multi-batch path
+        budget = std::min<size_t>(budget, (size_t)std::max(1, atoi(env)) << 20);
       size_t want_slots = std::min<size_t>(total_tasks, std::max<size_t>(1, budget / (slot_doubles * sizeof(double))));
       if (want_slots > s.r_slots) {
         CK(cudaStreamSynchronize(st));
@@ -1035,6 +1041,10 @@ Engine::~Engine() {
   plans_.reset();
   if (p_) {
     for (auto &e : p_->ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : {p_->ev_packed, p_->ev_jdone, p_->ev_up, p_->ev_j, p_->ev_jcopied})
+      if (e) cudaEventDestroy(e);
+    for (cudaStream_t st : {p_->copy_stream, p_->up_stream, p_->j_stream})
+      if (st) cudaStreamDestroy(st);
     if (!p_->norms_host.empty()) cudaHostUnregister(p_->norms_host.data());
   }
   if (stream_) cudaStreamDestroy(stream_);
@@ -1333,7 +1343,7 @@ Engine::HostRanges Engine::density_ranges() const {
   for (int c = 0; c < na; c++) {
     int lo = n, hi = 0;
     for (int a = 0; a < na; a++)
-      if (s.norms_host[(size_t)a * na + c] > 0.0) {   // block (a, c): rows of a, columns of c
+      if (!(s.norms_host[(size_t)a * na + c] == 0.0)) {   // block (a, c): rows of a, columns of c
         lo = std::min(lo, s.ang_off[a]);
         hi = std::max(hi, s.ang_off[a] + s.t.Nrad - s.ang_skip[a]);
       }
@@ -1455,6 +1465,7 @@ bool Engine::fused_host(const double *P, int64_t ldP, double kscale, double *J, 
       s.packed_valid = false;
       s.kscale = 1.0;
       if (spec) cudaStreamSynchronize(s.up_stream);
+      cudaStreamSynchronize(s.copy_stream);   // the J copy-back must not write into the caller's buffer after the error return
       throw;
     }
     plan_hook_ = nullptr;

@@ -343,6 +343,8 @@ GridEngine::GridEngine(const BasisTables &t, const GridTables &g, int device, cu
 
 GridEngine::~GridEngine() {}
 int64_t GridEngine::npoints() const { return p_->N; }
+bool GridEngine::polarized() const { return p_->polarized; }
+int GridEngine::density_flags() const { return p_->dens_flags; }
 
 void GridEngine::density(const double *Pa, int64_t ldPa, const double *Pb, int64_t ldPb, int flags, double *rho,
                          double *sigma, double *tau, double *lapl, double *weights, double *Nel, double *Ekin) {

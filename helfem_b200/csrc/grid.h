@@ -53,6 +53,8 @@ class GridEngine {
   GridEngine(const BasisTables &t, const GridTables &g, int device, cudaStream_t stream);
   ~GridEngine();
   int64_t npoints() const;
+  bool polarized() const;     // the last density() call was unrestricted
+  int density_flags() const;  // GridFlags of the last density() call
   // densities in libxc layout on the host (any output pointer may be NULL); Pb == NULL: restricted
   void density(const double *Pa, int64_t ldPa, const double *Pb, int64_t ldPb, int flags, double *rho, double *sigma,
                double *tau, double *lapl, double *weights, double *Nel, double *Ekin);

@@ -12,17 +12,34 @@ import numpy as np
 from . import gaunt as _gaunt
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "_build", "libjk_oracle.so")
 _lib = None
 
 
+def _host_tag():
+    """Hash of this machine's CPU feature flags: the -march=native build is per host."""
+    import hashlib
+    flags = ""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    flags = line
+                    break
+    except OSError:
+        pass
+    return hashlib.sha1(flags.encode()).hexdigest()[:10]
+
+
 def lib():
+    """The C oracle, compiled on first use with -O3 -march=native for THIS host (the timed CPU arm must not
+    run a generic build, and a native build must not travel to a different CPU)."""
     global _lib
     if _lib is None:
         src = os.path.join(_HERE, "csrc", "jk_oracle.c")
-        if not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
-            subprocess.check_call(["make", "-s", "-C", _HERE, os.path.join(_HERE, "_build", "libjk_oracle.so")])
-        _lib = ctypes.CDLL(_SO)
+        so = os.path.join(_HERE, "_build", "libjk_oracle.%s.so" % _host_tag())
+        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+            subprocess.check_call(["make", "-s", "-C", _HERE, so])
+        _lib = ctypes.CDLL(so)
         _lib.jk_num_threads.restype = ctypes.c_int
     return _lib
 
@@ -114,11 +131,28 @@ class DiatomicCaches:
         pi = self.pure_idx()
         return K[np.ix_(pi, pi)]
 
-    def coulomb(self, P):
+    def coulomb(self, P, single_M=None):
+        """Full J (boundary removed).  single_M: the density only has blocks with m_k - m_l == single_M (checked):
+        build only those channels -- identical result, without the folds that add exact zeros."""
         Pd = self.expand(P)
         nd = self.Nang * self.Nrad
         J = np.zeros((nd, nd), order="F")
         v = ctypes.c_void_p
+        if single_M is not None:
+            N = self.Nrad
+            for k in range(self.Nang):
+                for l in range(self.Nang):
+                    if self.mval[k] - self.mval[l] != single_M and Pd[k * N:(k + 1) * N, l * N:(l + 1) * N].any():
+                        raise ValueError("density has a block with m_k - m_l != single_M")
+            lib().jk_diatomic_coulomb_single_M(
+                self.Nang, self.Nrad, self.Nel, self.NL, v(self.efirst.ctypes.data), v(self.en.ctypes.data),
+                v(self.lval.ctypes.data), v(self.mval.ctypes.data), v(self.g0.ctypes.data), v(self.g2.ctypes.data),
+                self.nlm, v(self.lmL.ctypes.data), v(self.lmM.ctypes.data), v(self.pref.ctypes.data),
+                len(self.LML), v(self.LML.ctypes.data), v(self.LMM.ctypes.data),
+                self.P0, self.P2, self.Q0, self.Q2, self.B, self.S, v(self.rank.ctypes.data), v(Pd.ctypes.data),
+                v(J.ctypes.data), int(single_M))
+            pi = self.pure_idx()
+            return J[np.ix_(pi, pi)]
         lib().jk_diatomic_coulomb(
             self.Nang, self.Nrad, self.Nel, self.NL, v(self.efirst.ctypes.data), v(self.en.ctypes.data),
             v(self.lval.ctypes.data), v(self.mval.ctypes.data), v(self.g0.ctypes.data), v(self.g2.ctypes.data),
@@ -128,6 +162,24 @@ class DiatomicCaches:
             v(J.ctypes.data))
         pi = self.pure_idx()
         return J[np.ix_(pi, pi)]
+
+    def coulomb_timing_sample(self, Pdummy, stride):
+        """Seconds of a 1/stride sample of the (serial) Coulomb build -- see jk_oracle.c; no result."""
+        import time
+        Pd = np.asfortranarray(Pdummy)
+        nd = self.Nang * self.Nrad
+        if getattr(self, "_jscratch", None) is None or self._jscratch.shape[0] != nd:
+            self._jscratch = np.zeros((nd, nd), order="F")
+        v = ctypes.c_void_p
+        t0 = time.perf_counter()
+        lib().jk_diatomic_coulomb_timing_sample(
+            self.Nang, self.Nrad, self.Nel, self.NL, v(self.efirst.ctypes.data), v(self.en.ctypes.data),
+            v(self.lval.ctypes.data), v(self.mval.ctypes.data), v(self.g0.ctypes.data), v(self.g2.ctypes.data),
+            self.nlm, v(self.lmL.ctypes.data), v(self.lmM.ctypes.data), v(self.pref.ctypes.data),
+            len(self.LML), v(self.LML.ctypes.data), v(self.LMM.ctypes.data),
+            self.P0, self.P2, self.Q0, self.Q2, self.B, self.S, v(self.rank.ctypes.data), v(Pd.ctypes.data),
+            v(self._jscratch.ctypes.data), int(stride))
+        return time.perf_counter() - t0
 
     @classmethod
     def from_oracle(cls, b):
@@ -140,6 +192,26 @@ class DiatomicCaches:
                                np.stack([b.disjoint_Q0[i], b.disjoint_Q2[i]]), b.cd_B[i], b.cd_sigma[i]))
         return cls(b.Nrad(), [b.radial.get_idx(e)[0] for e in range(Nel)], [b.radial.fem.nprim(e) for e in range(Nel)],
                    b.lval, b.mval, [p[0] for p in b.lm_map], [p[1] for p in b.lm_map], b.LMfac_abs(), blocks)
+
+    @classmethod
+    def from_npz(cls, path):
+        """From the arrays written by tools/export_caches.py (the CPU reference arm's inputs)."""
+        d = dict(np.load(path))   # NpzFile re-reads an array on every access: materialise once
+        en, ranks = d["en"], d["ranks"]
+        Nel, nlm = len(en), len(d["lmL"])
+        blocks, o1, o2 = [], 0, 0
+        so = 0
+        for ilm in range(nlm):
+            for e in range(Nel):
+                n, r = int(en[e]), int(ranks[ilm * Nel + e])
+                sm = d["small"][o1:o1 + 2 * n * n].reshape(2, n, n).transpose(0, 2, 1)
+                bg = d["big"][o1:o1 + 2 * n * n].reshape(2, n, n).transpose(0, 2, 1)
+                o1 += 2 * n * n
+                B = d["B"][o2:o2 + 2 * n * n * r].reshape(2 * n * n, r, order="F")
+                o2 += 2 * n * n * r
+                blocks.append((sm, bg, B, d["sigma"][so:so + r]))
+                so += r
+        return cls(int(d["Nrad"]), d["efirst"], en, d["lval"], d["mval"], d["lmL"], d["lmM"], d["pref"], blocks)
 
     @classmethod
     def from_tables(cls, T):

@@ -240,12 +240,21 @@ void jk_diatomic_exchange_blocks(int Nang, int Nrad, int Nel, int NL, const int 
  * Diatomic coulomb (basis.cpp:1627-1816), serial like the reference.  nLM channels (L,M)
  * given by LML/LMM; P and J are boundary-expanded Ndummy x Ndummy.
  * ---------------------------------------------------------------------------------------- */
-void jk_diatomic_coulomb(int Nang, int Nrad, int Nel, int NL, const int *efirst, const int *en, const int *lval,
+/* stride > 1: TIMING SAMPLE ONLY -- the fold visits the angular rows k = 0, stride, 2 stride .., the radial step the
+ * channels iLM = 0, stride, .., the unfold the rows i = 0, stride, ..; every one of the three phases is linear in
+ * the number of rows / channels visited, so stride * (time of the sample) estimates the time of the full build.
+ * The result of a sampled call is not a Coulomb matrix. */
+#define JK_ALL_M (1 << 30)
+static void coulomb_impl(int Nang, int Nrad, int Nel, int NL, const int *efirst, const int *en, const int *lval,
                          const int *mval, const double *g0, const double *g2, int nlm, const int *lmL, const int *lmM,
                          const double *LMfac_abs, int nLM, const int *LML, const int *LMM, const double *const *dP0,
                          const double *const *dP2, const double *const *dQ0, const double *const *dQ2,
                          const double *const *cdB, const double *const *cdS, const int *rank, const double *P,
-                         double *J) {
+                         double *J, int stride, int Monly) {
+  /* Monly != JK_ALL_M: only the channels with M == Monly are built (fold, radial step and unfold skip every
+   * other M).  For a density whose blocks all have m_k - m_l == Monly this IS the complete Coulomb matrix (all other
+   * Paux vanish identically); used by bench.py to check J at full size without the 12/13 of the fold that adds
+   * zeros.  The timed arm always runs the reference's unscreened loops (Monly = JK_ALL_M). */
   const size_t Nd = (size_t)Nang * Nrad, NN = (size_t)Nrad * Nrad;
   double *Paux0 = (double *)calloc(NN * nLM, sizeof(double)), *Paux2 = (double *)calloc(NN * nLM, sizeof(double));
   double *Jaux0 = (double *)calloc(NN * nLM, sizeof(double)), *Jaux2 = (double *)calloc(NN * nLM, sizeof(double));
@@ -258,9 +267,10 @@ void jk_diatomic_coulomb(int Nang, int Nrad, int Nel, int NL, const int *efirst,
   int *LMidx = (int *)malloc(sizeof(int) * (size_t)NL * nMv);
   for (int i = 0; i < NL * nMv; i++) LMidx[i] = -1;
   for (int i = 0; i < nLM; i++) LMidx[LML[i] * nMv + LMM[i] - Mlo] = i;
-  for (int k = 0; k < Nang; k++)
+  for (int k = 0; k < Nang; k += stride)
     for (int l = 0; l < Nang; l++) {
       const int M = mval[k] - mval[l];
+      if (Monly != JK_ALL_M && M != Monly) continue;
       const int Lmin = imax(abs(lval[k] - lval[l]) - 2, abs(M)), Lmax = lval[k] + lval[l] + 2;
       const double *Prad = P + (size_t)k * Nrad + (size_t)l * Nrad * Nd;
       for (int L = Lmin; L <= Lmax; L++) {
@@ -277,8 +287,9 @@ void jk_diatomic_coulomb(int Nang, int Nrad, int Nel, int NL, const int *efirst,
   int nmax = 0;
   for (int e = 0; e < Nel; e++) nmax = imax(nmax, en[e]);
   double *p2 = (double *)malloc(sizeof(double) * 2 * nmax * nmax), *cv = (double *)malloc(sizeof(double) * 2 * nmax * nmax);
-  for (int iLM = 0; iLM < nLM; iLM++) {
+  for (int iLM = 0; iLM < nLM; iLM += stride) {
     const int L = LML[iLM], M = LMM[iLM];
+    if (Monly != JK_ALL_M && M != Monly) continue;
     const int ilm = find_lm(nlm, lmL, lmM, L, abs(M));
     const double LMfac = ((M & 1) ? -1.0 : 1.0) * LMfac_abs[ilm];
     double *Ja0 = Jaux0 + iLM * NN, *Ja2 = Jaux2 + iLM * NN;
@@ -329,10 +340,11 @@ void jk_diatomic_coulomb(int Nang, int Nrad, int Nel, int NL, const int *efirst,
         }
     }
   }
-  memset(J, 0, sizeof(double) * Nd * Nd);
-  for (int i = 0; i < Nang; i++)
+  if (stride == 1) memset(J, 0, sizeof(double) * Nd * Nd);
+  for (int i = 0; i < Nang; i += stride)
     for (int j = 0; j < Nang; j++) {
       const int M = mval[j] - mval[i];
+      if (Monly != JK_ALL_M && M != Monly) continue;
       const int Lmin = imax(abs(lval[j] - lval[i]) - 2, abs(M)), Lmax = lval[j] + lval[i] + 2;
       double *Jb = J + (size_t)i * Nrad + (size_t)j * Nrad * Nd;
       for (int L = Lmin; L <= Lmax; L++) {
@@ -345,6 +357,38 @@ void jk_diatomic_coulomb(int Nang, int Nrad, int Nel, int NL, const int *efirst,
       }
     }
   free(Paux0); free(Paux2); free(Jaux0); free(Jaux2); free(LMidx); free(p2); free(cv);
+}
+
+void jk_diatomic_coulomb(int Nang, int Nrad, int Nel, int NL, const int *efirst, const int *en, const int *lval,
+                         const int *mval, const double *g0, const double *g2, int nlm, const int *lmL, const int *lmM,
+                         const double *LMfac_abs, int nLM, const int *LML, const int *LMM, const double *const *dP0,
+                         const double *const *dP2, const double *const *dQ0, const double *const *dQ2,
+                         const double *const *cdB, const double *const *cdS, const int *rank, const double *P,
+                         double *J) {
+  coulomb_impl(Nang, Nrad, Nel, NL, efirst, en, lval, mval, g0, g2, nlm, lmL, lmM, LMfac_abs, nLM, LML, LMM, dP0, dP2, dQ0,
+               dQ2, cdB, cdS, rank, P, J, 1, JK_ALL_M);
+}
+
+/* Coulomb matrix of a density that only has blocks with m_k - m_l == Monly (see coulomb_impl) */
+void jk_diatomic_coulomb_single_M(int Nang, int Nrad, int Nel, int NL, const int *efirst, const int *en, const int *lval,
+                                  const int *mval, const double *g0, const double *g2, int nlm, const int *lmL,
+                                  const int *lmM, const double *LMfac_abs, int nLM, const int *LML, const int *LMM,
+                                  const double *const *dP0, const double *const *dP2, const double *const *dQ0,
+                                  const double *const *dQ2, const double *const *cdB, const double *const *cdS,
+                                  const int *rank, const double *P, double *J, int Monly) {
+  coulomb_impl(Nang, Nrad, Nel, NL, efirst, en, lval, mval, g0, g2, nlm, lmL, lmM, LMfac_abs, nLM, LML, LMM, dP0, dP2, dQ0,
+               dQ2, cdB, cdS, rank, P, J, 1, Monly);
+}
+
+void jk_diatomic_coulomb_timing_sample(int Nang, int Nrad, int Nel, int NL, const int *efirst, const int *en,
+                                       const int *lval, const int *mval, const double *g0, const double *g2, int nlm,
+                                       const int *lmL, const int *lmM, const double *LMfac_abs, int nLM, const int *LML,
+                                       const int *LMM, const double *const *dP0, const double *const *dP2,
+                                       const double *const *dQ0, const double *const *dQ2, const double *const *cdB,
+                                       const double *const *cdS, const int *rank, const double *P, double *J,
+                                       int stride) {
+  coulomb_impl(Nang, Nrad, Nel, NL, efirst, en, lval, mval, g0, g2, nlm, lmL, lmM, LMfac_abs, nLM, LML, LMM, dP0, dP2, dQ0,
+               dQ2, cdB, cdS, rank, P, J, stride < 1 ? 1 : stride, JK_ALL_M);
 }
 
 /* ------------------------------------------------------------------------------------------
