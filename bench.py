@@ -179,7 +179,9 @@ def main():
     config = {"workload": workload, "density": "synthetic closed-shell N2 structure (3 sigma_g + 2 sigma_u + pi_u+-, g/u-symmetric orbitals), seed 42",
               "symmetry": "per-m (reference default --symmetry=1, absm_symmetric off)",
               "l2": "inputs larger than L2 (P/J/K 1.76 GB each, work buffers > 10 GB)",
-              "sharding": "exchange tasks (output block, density block, L) dealt round-robin over ranks, J multipoles split over ranks; NCCL all-reduce of the non-zero K and J blocks"}
+              "sharding": "owner computes: exchange units (output sector pair, radial element pair) dealt longest-first to the least "
+                          "loaded rank; ONE in-place ncclAllGather of the compact result issued by the library (hfq_comm_init); J "
+                          "replicated"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -231,6 +233,8 @@ def main():
     t0 = time.time()
     basis._context()
     t_upload = time.time() - t0
+    if world > 1:
+        basis.comm_init()   # NCCL communicator inside the library; torch.distributed only hands the id around
 
     # device-resident inputs/outputs (column-major n x n == transposed row-major torch tensors)
     dP = torch.from_numpy(np.ascontiguousarray(P.T)).cuda()
@@ -251,14 +255,8 @@ def main():
 
     def step_device(collect=False):
         # one Fock build: J = coulomb(P), K = exchange(P/2) from one packed copy of P
-        basis.coulomb_exchange_device(dP.data_ptr(), dJ.data_ptr(), dK.data_ptr(), 0.5, rank, world, stream)
-        if world > 1:
-            if "K" not in car:   # the collectives of the sharded build, on the non-zero blocks only
-                from helfem_b200.dist import CompactAllReduce
-                car["K"] = CompactAllReduce(basis, dK.device)
-                car["J"] = CompactAllReduce(basis, dJ.device, coulomb=True)
-            car["K"](dK)
-            car["J"](dJ)
+        # (with a communicator the build is sharded and completed by the library: results are whole on every rank)
+        basis.coulomb_exchange_device(dP.data_ptr(), dJ.data_ptr(), dK.data_ptr(), 0.5, 0, 1, stream)
         if collect:
             tm = basis.last_timings()
             for k in acc:

@@ -41,6 +41,7 @@ EXPORTED_SYMBOLS = [
     "hfq_tables_destroy", "hfq_create", "hfq_destroy", "hfq_nbf", "hfq_set_absm_symmetric", "hfq_coulomb",
     "hfq_exchange", "hfq_coulomb_device", "hfq_exchange_device", "hfq_last_timings", "hfq_exchange_output_pattern",
     "hfq_coulomb_output_pattern",
+    "hfq_comm_unique_id", "hfq_comm_init", "hfq_comm_size", "hfq_shard_assign",
     "hfq_coulomb_exchange", "hfq_coulomb_exchange_device", "hfq_grid_attach", "hfq_grid_npoints", "hfq_grid_density", "hfq_grid_fxc", "hfq_eval_fxc",
 ]
 
@@ -91,6 +92,10 @@ def lib():
     L.hfq_coulomb_output_pattern.argtypes = [vp, vp, i64, vp, i64]
     L.hfq_coulomb_exchange.argtypes = [vp, vp, i64, cd, vp, i64, vp, i64]
     L.hfq_coulomb_exchange_device.argtypes = [vp, vp, i64, cd, vp, i64, vp, i64, ci, ci, vp]
+    L.hfq_comm_unique_id.argtypes = [vp]
+    L.hfq_comm_init.argtypes = [vp, vp, ci, ci]
+    L.hfq_comm_size.argtypes = [vp]
+    L.hfq_shard_assign.argtypes = [vp, ci, ci, vp]
     L.hfq_grid_attach.argtypes = [vp, ci, ci]
     L.hfq_grid_npoints.argtypes = [vp]
     L.hfq_grid_npoints.restype = i64
@@ -339,6 +344,20 @@ class _BasisBase:
     def exchange_device(self, dP_ptr, dK_ptr, shard=0, nshards=1, stream=None):
         n = self.Nbf()
         _check(lib().hfq_exchange_device(self._context(), dP_ptr, n, dK_ptr, n, shard, nshards, stream))
+
+    def comm_init(self, rank=None, world=None, bcast=None):
+        """Bind the context to an NCCL communicator of `world` ranks (one process per GPU): hfq_comm_init.  The
+        128-byte id is created on rank 0 and distributed with `bcast(bytes_or_None) -> bytes`; by default through
+        torch.distributed (plumbing only: the collective of the build itself is issued by the library)."""
+        if bcast is None:
+            from . import dist as _dist
+            rank, world, bcast = _dist.torch_bcast()
+        buf = ctypes.create_string_buffer(128)
+        if rank == 0:
+            _check(lib().hfq_comm_unique_id(buf))
+        ident = bcast(buf.raw if rank == 0 else None)
+        _check(lib().hfq_comm_init(self._context(), ctypes.c_char_p(ident), rank, world))
+        return self
 
     def exchange_output_pattern(self, coulomb=False):
         """(bf_sector[Nbf], [(row sector, col sector), ...]) of the last exchange (or coulomb) result."""

@@ -12,8 +12,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhelfemqc_b200.so")
-SOURCES = ["fem.cpp", "special.cpp", "atomic_setup.cpp", "diatomic_setup.cpp", "grid_setup.cpp", "engine.cu", "grid.cu", "capi.cpp"]
-HEADERS = ["fem.h", "special.h", "tables.h", "engine.h", "grid.h", "kernels.cuh", "../../include/helfem_b200.h"]
+SOURCES = ["fem.cpp", "special.cpp", "atomic_setup.cpp", "diatomic_setup.cpp", "grid_setup.cpp", "comm.cpp", "engine.cu", "grid.cu", "capi.cpp"]
+HEADERS = ["fem.h", "special.h", "tables.h", "engine.h", "grid.h", "comm.h", "kernels.cuh", "../../include/helfem_b200.h"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
          "-Xcompiler", "-fPIC,-fopenmp,-O3", "--expt-relaxed-constexpr"]
@@ -46,7 +46,7 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed on %s:\n%s" % (src, out))
         if verbose and out.strip():
             print(out)
-    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-Xcompiler", "-fopenmp", "-lcudart", "-lgomp"]
+    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-Xcompiler", "-fopenmp", "-lcudart", "-lgomp", "-ldl"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout)

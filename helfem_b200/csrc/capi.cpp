@@ -11,6 +11,7 @@
 #include <stdexcept>
 #include <string>
 
+#include "comm.h"
 #include "engine.h"
 #include "grid.h"
 #include "tables.h"
@@ -564,6 +565,33 @@ int hfq_eval_fxc(hfq_ctx *ctx, int x_func, int c_func, const double *Pa, int64_t
     ctx->grid->fxc(0, beta != 0, exc.data(), vrho.data(), nullptr, nullptr, nullptr, Ha, ldHa, Hb, ldHb, Exc);
     return HFQ_OK;
   });
+}
+
+int hfq_comm_unique_id(void *id128) {
+  if (!id128) return fail(HFQ_ERR_INVALID, "hfq_comm_unique_id: null argument");
+  return guarded([&] {
+    hfq::Comm::unique_id(id128);
+    return HFQ_OK;
+  });
+}
+
+int hfq_comm_init(hfq_ctx *ctx, const void *id128, int rank, int nranks) {
+  if (!ctx || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(HFQ_ERR_INVALID, "hfq_comm_init: invalid argument");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  return guarded([&] {
+    ctx->eng->set_comm(id128, rank, nranks);
+    return HFQ_OK;
+  });
+}
+
+int hfq_comm_size(const hfq_ctx *ctx) { return ctx ? ctx->eng->comm_size() : 0; }
+
+int hfq_shard_assign(const double *cost, int n, int nranks, int *owner) {
+  if (!cost || !owner || n < 0 || nranks < 1) return fail(HFQ_ERR_INVALID, "hfq_shard_assign: invalid argument");
+  std::vector<int> o;
+  hfq::assign_units(std::vector<double>(cost, cost + n), nranks, o);
+  std::memcpy(owner, o.data(), (size_t)n * sizeof(int));
+  return HFQ_OK;
 }
 
 int hfq_last_timings(const hfq_ctx *ctx, double *out, int n) {

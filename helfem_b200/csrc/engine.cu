@@ -14,6 +14,7 @@
 
 #include <omp.h>
 
+#include "comm.h"
 #include "kernels.cuh"
 #include "special.h"
 
@@ -106,6 +107,10 @@ struct Engine::Impl {
   size_t r_slots = 0;                // capacity of the R buffer in task slots
   // density packed by pack_density(): shared by coulomb and exchange in a fused build
   std::vector<double> norms_host;
+  int *flags_host = nullptr;         // page-locked: per sector pair, bit 0 = not exactly zero, bit 1 = norm not below 10 eps
+  bool want_norms_host = false;      // host-pointer calls: the per-block norms are read back too (upload prediction)
+  DevBuf<int> d_spflags;
+  DevBuf<double> d_Kc;               // compact exchange result: [rank segment][unit][rows][NB]
   std::vector<int> packed_splist;
   bool packed_valid = false;
   double kscale = 1.0;               // exchange(kscale * P) = kscale * exchange(P)
@@ -571,22 +576,32 @@ void launch_gemm(const dev::GemmItem *items, const dev::GemmEntry *entries, int 
 // ---------------------------------------------------------------------------
 // Block norms of P (the reference's screening quantity) and the sector-packed copy of every
 // sector pair that carries density.  Shared by coulomb and exchange inside a fused build.
+// Only the per-sector-pair flags (a few KB) come back to the host; the per-block norms follow only when a
+// host-pointer call needs them (row ranges of the next speculative upload).
 void Engine::pack_density(const double *dP, int64_t ldP, cudaStream_t st) {
   Impl &s = *p_;
   const BasisTables &t = s.t;
   const int na = t.Nang(), ns = s.ns;
   const size_t nn = (size_t)na * na;
+  const size_t nflag = (size_t)ns * ns;
   if (s.norms_host.size() != nn + 2) {
     // page-locked once: the per-call read-back is then a plain DMA instead of a staged pageable copy
     if (!s.norms_host.empty()) cudaHostUnregister(s.norms_host.data());
     s.norms_host.assign(nn + 2, 0.0);
     if (cudaHostRegister(s.norms_host.data(), s.norms_host.size() * sizeof(double), cudaHostRegisterDefault) != cudaSuccess)
       cudaGetLastError();   // stays pageable: slower, still correct
+    if (!s.flags_host) CK(cudaMallocHost(&s.flags_host, (nflag + 4) * sizeof(int)));
+    s.d_spflags.alloc(nflag, &dev_bytes_);
   }
   CK(cudaMemsetAsync(s.d_norms.p + nn, 0, 2 * sizeof(double), st));
-  dev::k_block_norms<<<dim3(na, na), 256, 0, st>>>(s.bd, dP, ldP, s.d_norms.p);
+  CK(cudaMemsetAsync(s.d_spflags.p, 0, nflag * sizeof(int), st));
+  dev::k_block_norms<<<dim3(na, (na + 3) / 4), 128, 0, st>>>(s.bd, dP, ldP, s.d_ang_sec.p, s.d_norms.p, s.d_spflags.p);
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(s.norms_host.data(), s.d_norms.p, s.norms_host.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(s.flags_host, s.d_spflags.p, nflag * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (s.want_norms_host)
+    CK(cudaMemcpyAsync(s.norms_host.data(), s.d_norms.p, s.norms_host.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+  else
+    CK(cudaMemcpyAsync(s.norms_host.data() + nn, s.d_norms.p + nn, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   {
     // symmetric density (every SCF density is): the exchange builds half of each diagonal output pair
@@ -594,13 +609,9 @@ void Engine::pack_density(const double *dP, int64_t ldP, cudaStream_t st) {
     static const bool allow = !(getenv("HFQ_NO_SYMMETRY") && atoi(getenv("HFQ_NO_SYMMETRY")));
     s.p_symmetric = allow && asym <= 1e-14 * amax;
   }
-  std::vector<char> sp_nz((size_t)ns * ns, 0);
-  for (int a = 0; a < na; a++)
-    for (int b = 0; b < na; b++)
-      if (!(s.norms_host[(size_t)a * na + b] == 0.0)) sp_nz[(size_t)s.ang_sec[a] * ns + s.ang_sec[b]] = 1;
   s.packed_splist.clear();
   for (int sp = 0; sp < ns * ns; sp++)
-    if (sp_nz[sp]) s.packed_splist.push_back(sp);
+    if (s.flags_host[sp] & 1) s.packed_splist.push_back(sp);
   if (!s.packed_splist.empty()) {
     CK(cudaMemcpyAsync(s.d_splist.p, s.packed_splist.data(), s.packed_splist.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     for (int sp : s.packed_splist)
@@ -628,10 +639,14 @@ void Engine::jk_dev(const double *dP, int64_t ldP, double kscale, double *dJ, in
   }
   try {
     // the Coulomb chain (~1 ms of small kernels) runs on its own stream and fills the tails of the
-    // exchange kernels instead of preceding them
+    // exchange kernels instead of preceding them.  With a communicator every rank builds the complete J
+    // (replicated: cheaper than a second collective); without one the legacy shard arguments split it over L.
     CK(cudaEventRecord(s.ev_packed, st));
     CK(cudaStreamWaitEvent(s.j_stream, s.ev_packed, 0));
-    coulomb_run(dP, ldP, dJ, ldJ, shard, nshards, s.j_stream, true);
+    if (comm_)
+      coulomb_run(dP, ldP, dJ, ldJ, 0, 1, s.j_stream, true);
+    else
+      coulomb_run(dP, ldP, dJ, ldJ, shard, nshards, s.j_stream, true);
     CK(cudaEventRecord(s.ev_jdone, s.j_stream));
     EngineTimings tj;
     tj.launches = 6;
@@ -658,6 +673,14 @@ void Engine::jk_dev(const double *dP, int64_t ldP, double kscale, double *dJ, in
 // A plan is everything about an exchange call that depends only on WHICH sector pairs of the
 // density are non-zero (plus sharding and the +-m flag): the task list, its split into batches
 // and the device-resident kernel descriptors.  SCF iterations reuse it.
+//
+// Sharding (owner computes).  The unit of ownership is (output sector pair, element pair): its block of the
+// accumulator is written by exactly one rank, which folds only the pixels of that element pair, runs the
+// in-element GEMM (ei == ej) or the cross-element kernel (ei != ej) over all tasks of the output pair, and
+// reduces its K-split partials.  Units are dealt to the ranks longest-first onto the least loaded rank (costs =
+// executed flops of the three kernels); the unit blocks of a rank are contiguous in the compact buffer Kc, every
+// rank's segment has the same length, so ONE in-place ncclAllGather completes the exchange matrix on all
+// ranks; the unpack (dense K, boundary removal, mirrors) then runs everywhere.
 struct ExchangeBatch {
   DevBuf<dev::FoldTask> tasks;
   DevBuf<dev::GemmItem> gitems;
@@ -671,41 +694,75 @@ struct ExchangePlan {
   std::vector<std::unique_ptr<ExchangeBatch>> batches;
   std::vector<int> splist, op_src, op_tri;
   DevBuf<int> d_op_src, d_op_tri, d_blocks;   // device copies + angular blocks (j | k << 16) that can be non-zero
+  DevBuf<int64_t> d_unit_off;                 // [(active op * Nel + ei) * Nel + ej] offset in Kc or -1
+  DevBuf<dev::ReduceDesc> d_reduce;
+  int nreduce = 0;
+  int64_t seg = 0;                            // doubles per rank segment of Kc
+  int64_t part_stride = 0;                    // doubles per K-split partial (partials 1 .. S-1 of the own units)
   int nblocks = 0;
   int nactive = 0, S = 1, maxM = 8;
   double fl_fold = 0, fl_tg = 0, fl_off = 0, al_fold = 0, al_tg = 0, al_off = 0;
-  const double *R_base = nullptr, *K_base = nullptr;   // buffers the descriptors point into
+  const double *R_base = nullptr, *K_base = nullptr, *Kc_base = nullptr;   // buffers the descriptors point into
 };
 
 struct Engine::PlanCache {
   std::vector<std::unique_ptr<ExchangePlan>> plans;
 };
 
+int Engine::comm_size() const { return comm_ ? comm_->size() : 1; }
+
+void Engine::set_comm(const void *id128, int rank, int nranks) {
+  CK(cudaSetDevice(device_));
+  comm_.reset();
+  if (nranks > 1) comm_ = std::make_unique<Comm>(id128, rank, nranks, device_);
+  if (plans_) plans_->plans.clear();
+  p_->jplan.valid = false;
+}
+
+// Longest-processing-time assignment of n units to nranks; deterministic (ties by index), identical on every rank.
+void assign_units(const std::vector<double> &cost, int nranks, std::vector<int> &owner) {
+  const int n = (int)cost.size();
+  owner.assign(n, 0);
+  std::vector<int> order(n);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cost[x] > cost[y]; });
+  std::vector<double> load(nranks, 0.0);
+  for (int u : order) {
+    int best = 0;
+    for (int r = 1; r < nranks; r++)
+      if (load[r] < load[best]) best = r;
+    owner[u] = best;
+    load[best] += cost[u];
+  }
+}
+
 void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK, int shard, int nshards,
                           cudaStream_t st) {
   Impl &s = *p_;
   const BasisTables &t = s.t;
   CK(cudaSetDevice(device_));
-  const int na = t.Nang(), ns = s.ns;
+  const int na = t.Nang(), ns = s.ns, Nel = t.Nel;
+  if (comm_) {   // a communicator overrides the legacy shard arguments
+    shard = comm_->rank();
+    nshards = comm_->size();
+  }
   tm_ = EngineTimings();
   if (!plans_) plans_.reset(new PlanCache);
   CK(cudaEventRecord(s.ev[0], st));
-  // 1. which angular blocks of P carry density (reference: block norm >= 10 eps)
+  // 1. which sector pairs of P carry density (reference: block norm >= 10 eps)
   if (!s.packed_valid) pack_density(dP, ldP, st);
-  const std::vector<double> &norms = s.norms_host;
-  const double thr2 = std::pow(10.0 * 2.220446049250313e-16, 2);
   std::string key((size_t)ns * ns + 3, '0');
-  for (int a = 0; a < na; a++)
-    for (int b = 0; b < na; b++)
-      if (!(norms[(size_t)a * na + b] < thr2)) key[(size_t)s.ang_sec[a] * ns + s.ang_sec[b]] = '1';
+  for (int sp = 0; sp < ns * ns; sp++)
+    if (s.flags_host[sp] & 2) key[sp] = '1';
   key[(size_t)ns * ns] = (char)((absm_symmetric_ ? 'S' : 'N') + (s.p_symmetric ? 1 : 0));
   key[(size_t)ns * ns + 1] = (char)('0' + shard);
   key[(size_t)ns * ns + 2] = (char)('0' + nshards);
   ExchangePlan *plan = nullptr;
   for (auto &pl : plans_->plans)
-    if (pl->key == key && pl->R_base == s.d_R.p && pl->K_base == s.d_Kacc.p) plan = pl.get();
+    if (pl->key == key && pl->R_base == s.d_R.p && pl->K_base == s.d_Kacc.p && pl->Kc_base == s.d_Kc.p) plan = pl.get();
   if (!plan) {
     // ---------------- build the plan ----------------
+    CK(cudaStreamSynchronize(st));   // buffers may be re-allocated below
     auto np = std::make_unique<ExchangePlan>();
     np->key = key;
     std::vector<char> sp_nz((size_t)ns * ns, 0);
@@ -718,14 +775,13 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
       bool tri = false;   // diagonal output pair of a symmetric density: half storage
       std::vector<dev::FoldTask> tasks;
       std::vector<int> ilm;
-      std::vector<double> alg_fold;  // unpadded flops of the fold per task
+      std::vector<double> alg_fold;  // unpadded flops of the fold per task (all pixels)
+      unsigned long long regmask = 0;   // element pairs built by this rank
+      std::vector<int> own_pairs;       // ei * Nel + ej of those
     };
-    std::vector<OpWork> work;
+    std::vector<OpWork> work;   // every active output pair (identical on all ranks)
     np->op_src.assign((size_t)ns * ns, -1);
     // Task list: output pair (sj,sk) <- density pair (si,sl) with mj-mi == mk-ml, every coupled L.
-    // Sharding: tasks are dealt round-robin to the shards, so every rank builds a partial sum of
-    // every output block and the all-reduce completes it.
-    long taskcount = 0;
     for (int sj = 0; sj < ns; sj++)
       for (int sk = 0; sk < ns; sk++) {
         const int mj = s.sec_m[sj], mk = s.sec_m[sk];
@@ -745,7 +801,6 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
               if (ilm < 0) continue;
               if (!s.G_nonzero[((size_t)sj * ns + si) * s.NL + L] || !s.G_nonzero[((size_t)sk * ns + sl) * s.NL + L])
                 continue;
-              if ((taskcount++ % nshards) != shard) continue;
               dev::FoldTask ft;
               ft.spj = sj * ns + si;
               ft.spk = sk * ns + sl;
@@ -754,11 +809,11 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
               ft.rslot = 0;
               ft.tri = w.tri ? 1 : 0;
               ft.fac = t.pref[ilm] * ((t.sign_by_M && (M & 1)) ? -1.0 : 1.0);
+              ft.regmask = ~0ull;
               w.tasks.push_back(ft);
               w.ilm.push_back(ilm);
               const double nj = s.sec_n[sj], nk = s.sec_n[sk], ni = s.sec_n[si], nl = s.sec_n[sl];
-              w.alg_fold.push_back((w.tri ? s.tri_pix_frac : 1.0) * 2.0 * s.Npix *
-                                   (ni * nl * nk * t.nch + nj * ni * nk * s.nab));
+              w.alg_fold.push_back(2.0 * (ni * nl * nk * t.nch + nj * ni * nk * s.nab));
             }
           }
         if (!w.tasks.empty()) work.push_back(std::move(w));
@@ -766,17 +821,100 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
     const size_t slot_doubles = (size_t)s.nab * s.Npix * s.NB;
     const int nactive = (int)work.size();
     np->nactive = nactive;
-    size_t total_tasks = 0;
-    for (auto &w : work) total_tasks += w.tasks.size();
-    // K-split of the in-element GEMM: each (output pair, element) item is cut into S chunks of its
-    // task list, each chunk accumulating into its own partial buffer (summed by the unpack kernel),
-    // so that the number of CTAs per launch fills whole waves of the 148 SMs.
-    int S = 1;
+    for (int a = 0; a < nactive; a++) np->op_src[work[a].op] = a;
+    np->op_tri.assign((size_t)ns * ns, 0);
+    for (int a = 0; a < nactive; a++) np->op_tri[a] = work[a].tri ? 1 : 0;
+    // ---- units = (active output pair, element pair); ownership
+    struct Unit {
+      int a, ei, ej, rows, ncol;
+      double cost;
+      int owner = 0;
+      int64_t off = -1;   // offset in Kc
+    };
+    std::vector<Unit> units;
+    const bool by_pair = nshards > 1 && Nel <= 8;   // else whole output pairs are dealt (regmask has 64 bits)
+    for (int a = 0; a < nactive; a++) {
+      const OpWork &w = work[a];
+      const int ncol = s.sec_span[w.op / ns] * s.NP;
+      const double ntask = (double)w.tasks.size();
+      for (int ei = 0; ei < Nel; ei++)
+        for (int ej = 0; ej < Nel; ej++) {
+          if (w.tri && ei > ej) continue;
+          const int Ni = t.en[ei], Nj = t.en[ej];
+          Unit u;
+          u.a = a;
+          u.ei = ei;
+          u.ej = ej;
+          u.rows = (w.tri && ei == ej) ? Ni * (Ni + 1) / 2 : Ni * Nj;
+          u.ncol = ncol;
+          const double fold = 2.0 * Ni * Nj * (double)s.NP * s.NP * s.NP * (t.nch + s.nab) * (s.parity ? 0.5 : 1.0);
+          double body;
+          if (ei == ej || t.pairwise())
+            body = 2.0 * u.rows * (double)ncol * s.nab * Ni * Nj;
+          else   // the cross-element kernel runs at about half the flop rate of the GEMM
+            body = 2.0 * (2.0 * t.nch * ((double)Ni * Nj * t.nch * Nj + (double)Ni * Nj * Ni) * ncol);
+          u.cost = ntask * (fold + body);
+          units.push_back(u);
+        }
+    }
     {
-      const double units = (double)nactive * t.Nel * (s.NB / 64);
+      std::vector<int> owner;
+      if (by_pair) {
+        std::vector<double> cost;
+        for (auto &u : units) cost.push_back(u.cost);
+        assign_units(cost, nshards, owner);
+      } else {
+        std::vector<double> cost(nactive, 0.0);
+        for (auto &u : units) cost[u.a] += u.cost;
+        std::vector<int> oo;
+        assign_units(cost, nshards, oo);
+        for (auto &u : units) owner.push_back(oo[u.a]);
+      }
+      for (size_t i = 0; i < units.size(); i++) units[i].owner = owner[i];
+    }
+    // compact buffer Kc: [rank segment][unit][rows][NB], all segments of equal length
+    {
+      std::vector<int64_t> fill(nshards, 0);
+      for (auto &u : units) {
+        u.off = fill[u.owner];
+        fill[u.owner] += (int64_t)u.rows * s.NB;
+      }
+      np->seg = *std::max_element(fill.begin(), fill.end());
+      np->seg = (np->seg + 63) / 64 * 64;
+      for (auto &u : units) u.off += (int64_t)u.owner * np->seg;
+      const size_t need = (size_t)np->seg * nshards;
+      if (s.d_Kc.n < need) {
+        s.d_Kc.alloc(need, &dev_bytes_);
+        CK(cudaMemsetAsync(s.d_Kc.p, 0, need * sizeof(double), st));   // padding travels through the collective: keep it finite
+      }
+      std::vector<int64_t> uoff((size_t)std::max(nactive, 1) * Nel * Nel, -1);
+      for (auto &u : units)
+        if (comm_ || u.owner == shard) uoff[((size_t)u.a * Nel + u.ei) * Nel + u.ej] = u.off;
+      np->d_unit_off.upload(uoff, &dev_bytes_);
+    }
+    // own units per output pair
+    int own_gemm_ctas = 0;
+    for (auto &u : units)
+      if (u.owner == shard) {
+        OpWork &w = work[u.a];
+        w.own_pairs.push_back(u.ei * Nel + u.ej);
+        if (Nel <= 8) w.regmask |= 1ull << (u.ei * Nel + u.ej);
+        if (u.ei == u.ej || t.pairwise()) own_gemm_ctas += (u.ncol + 63) / 64;
+      }
+    if (!by_pair)
+      for (auto &w : work)
+        if (!w.own_pairs.empty()) w.regmask = ~0ull;
+    size_t total_tasks = 0;
+    for (auto &w : work)
+      if (!w.own_pairs.empty()) total_tasks += w.tasks.size();
+    // K-split of the in-element GEMM: each (unit, 64-column tile) is cut into S chunks of its task list, each
+    // chunk accumulating into its own partial buffer (partial 0 = Kc itself; the others are summed into it by
+    // k_reduce_partials), so that the CTAs of a launch fill whole waves of the 148 SMs.
+    int S = 1;
+    if (own_gemm_ctas > 0) {
       double best = 0.0;
-      for (int c = 1; c <= 4; c++) {
-        const double u = units * c, eff = u / (std::ceil(u / 148.0) * 148.0);
+      for (int c = 1; c <= 8; c++) {
+        const double u = (double)own_gemm_ctas * c, eff = u / (std::ceil(u / 148.0) * 148.0);
         if (eff > best + 0.02) {
           best = eff;
           S = c;
@@ -784,13 +922,20 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
       }
     }
     np->S = S;
-    if (s.d_Kacc.n < (size_t)nactive * S * s.op_stride) {
-      CK(cudaStreamSynchronize(st));
-      s.d_Kacc.alloc((size_t)nactive * S * s.op_stride, &dev_bytes_);
+    // partial buffers 1 .. S-1: same layout as this rank's segment of Kc
+    np->part_stride = np->seg;
+    if (S > 1 && s.d_Kacc.n < (size_t)(S - 1) * np->seg) s.d_Kacc.alloc((size_t)(S - 1) * np->seg, &dev_bytes_);
+    if (S > 1) {
+      std::vector<dev::ReduceDesc> rd;
+      for (auto &u : units)
+        if (u.owner == shard) {
+          const int64_t n = (int64_t)u.rows * s.NB;
+          for (int64_t o = 0; o < n; o += 16384)
+            rd.push_back(dev::ReduceDesc{u.off + o, u.off - (int64_t)shard * np->seg + o, (int)std::min<int64_t>(16384, n - o)});
+        }
+      np->nreduce = (int)rd.size();
+      np->d_reduce.upload(rd, &dev_bytes_);
     }
-    for (int a = 0; a < nactive; a++) np->op_src[work[a].op] = a;
-    np->op_tri.assign((size_t)ns * ns, 0);
-    for (int a = 0; a < nactive; a++) np->op_tri[a] = work[a].tri ? 1 : 0;
     if (absm_symmetric_) {
       // K(-mj,-mk) block = K(mj,mk) block (sectors +-m of one parity class hold the same l list)
       std::map<std::pair<int, int>, int> sec_of_m;
@@ -824,7 +969,6 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
         budget = std::min<size_t>(budget, (size_t)std::max(1, atoi(env)) << 20);
       size_t want_slots = std::min<size_t>(total_tasks, std::max<size_t>(1, budget / (slot_doubles * sizeof(double))));
       if (want_slots > s.r_slots) {
-        CK(cudaStreamSynchronize(st));
         s.d_R.alloc(want_slots * slot_doubles, &dev_bytes_);
         s.r_slots = want_slots;
       }
@@ -832,10 +976,19 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
     if (total_tasks && s.r_slots == 0) throw std::runtime_error("Engine: no memory for the exchange work buffer");
     np->R_base = s.d_R.p;
     np->K_base = s.d_Kacc.p;
-    // Batches: every batch takes an equal share of tasks from every active output pair, so each
-    // launch works on all output pairs at once (grid size independent of the batch count).
+    np->Kc_base = s.d_Kc.p;
+    auto unit_off = [&](int a, int pair) {
+      for (auto &u : units)
+        if (u.a == a && u.ei * Nel + u.ej == pair) return u.off;
+      return (int64_t)-1;
+    };
+    std::vector<std::vector<int64_t>> own_off(work.size());
+    for (size_t wi = 0; wi < work.size(); wi++)
+      for (int pr : work[wi].own_pairs) own_off[wi].push_back(unit_off((int)wi, pr));
+    // Batches: every batch takes an equal share of tasks from every output pair this rank works on, so each
+    // launch works on all of them at once (grid size independent of the batch count).
     std::vector<size_t> done(work.size(), 0);
-    std::vector<char> started((size_t)work.size() * S, 0);
+    std::map<std::pair<size_t, int>, char> started;   // (work index * 4096 + pair, partial) -> written before
     size_t remaining = total_tasks;
     while (remaining > 0) {
       std::vector<dev::FoldTask> tasks;
@@ -844,10 +997,11 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
       std::vector<dev::OffItem> oitems;
       std::vector<dev::OffEntry> oentries;
       size_t open = 0;
-      for (size_t wi = 0; wi < work.size(); wi++) open += done[wi] < work[wi].tasks.size();
+      for (size_t wi = 0; wi < work.size(); wi++) open += !work[wi].own_pairs.empty() && done[wi] < work[wi].tasks.size();
       const size_t share = std::max<size_t>(1, s.r_slots / std::max<size_t>(open, 1));
       for (size_t wi = 0; wi < work.size() && tasks.size() < s.r_slots; wi++) {
         OpWork &w = work[wi];
+        if (w.own_pairs.empty()) continue;
         const size_t ti = done[wi];
         size_t take = std::min(w.tasks.size() - ti, std::min(share, s.r_slots - tasks.size()));
         if (remaining <= s.r_slots) take = w.tasks.size() - ti;   // everything fits: finish
@@ -857,47 +1011,53 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
         for (size_t k = 0; k < take; k++) {
           dev::FoldTask ft = w.tasks[ti + k];
           ft.rslot = (int)(t0 + k);
+          ft.regmask = w.regmask;
           tasks.push_back(ft);
         }
-        // in-element items (tensor-core GEMM against the dense exchange-ordered kernel), S chunks
-        for (int c = 0; c < S; c++) {
-          const size_t k0 = take * c / S, k1 = take * (c + 1) / S;
-          if (k1 == k0) continue;
-          double *acc_base = s.d_Kacc.p + ((size_t)wi * S + c) * s.op_stride;
-          const int acc = started[wi * S + c] ? 1 : 0;
-          started[wi * S + c] = 1;
-          // element pairs handled by the GEMM: the diagonal ones, plus -- for pair-tensor tables (erfc) --
-          // every other pair (only ei < ej for a symmetric density)
-          for (int ei = 0; ei < t.Nel; ei++)
-            for (int ej = 0; ej < t.Nel; ej++) {
-              if (ei != ej && (!t.pairwise() || (w.tri && ei > ej))) continue;
-              const int Ni = t.en[ei], Nj = t.en[ej];
-              const bool half = w.tri && ei == ej;
+        double own_pix = 0.0;   // pixels this rank folds per task (element-pair blocks overlap in their boundary functions)
+        for (int pr : w.own_pairs) own_pix += (double)t.en[pr / Nel] * t.en[pr % Nel];
+        own_pix = std::min(own_pix, (double)s.Npix * (w.tri ? s.tri_pix_frac : 1.0));
+        for (size_t pi = 0; pi < w.own_pairs.size(); pi++) {
+          const int ei = w.own_pairs[pi] / Nel, ej = w.own_pairs[pi] % Nel;
+          const int Ni = t.en[ei], Nj = t.en[ej];
+          const int64_t koff = own_off[wi][pi];
+          const int ncol = s.sec_span[w.op / ns] * s.NP;   // columns (pos_j, pos_k) with pos_j past the sector are padding
+          if (ei == ej || t.pairwise()) {
+            // in-element item (tensor-core GEMM against the dense exchange-ordered kernel; for pair-tensor
+            // tables (erfc) every element pair), S chunks; chunk 0 always gets work
+            const bool half = w.tri && ei == ej;
+            for (int c = 0; c < S; c++) {
+              const size_t k0 = (take * c + S - 1) / S, k1 = (take * (c + 1) + S - 1) / S;
+              if (k1 == k0) continue;
+              double *C = c == 0 ? s.d_Kc.p + koff
+                                 : s.d_Kacc.p + (size_t)(c - 1) * np->part_stride + (koff - (int64_t)shard * np->seg);
+              char &st_flag = started[{wi * 4096 + (size_t)w.own_pairs[pi], c}];
               dev::GemmItem gi{};
-              gi.C = acc_base + s.ep_off[(size_t)ei * t.Nel + ej];
-              gi.browoff = t.pairwise() ? s.d_browoff_P.p + s.browoff_P_first[(size_t)ei * t.Nel + ej]
+              gi.C = C;
+              gi.browoff = t.pairwise() ? s.d_browoff_P.p + s.browoff_P_first[(size_t)ei * Nel + ej]
                                         : s.d_browoff_T.p + s.browoff_T_first[ei];
               gi.M = half ? Ni * (Ni + 1) / 2 : Ni * Nj;
               np->maxM = std::max(np->maxM, gi.M);
-              gi.N = s.sec_span[w.op / ns] * s.NP;   // columns (pos_j, pos_k) with pos_j past the sector are padding
+              gi.N = ncol;
               gi.K = s.nab * Ni * Nj;
               gi.ent0 = (int)gentries.size();
               for (size_t k = k0; k < k1; k++) {
                 const int ilm = w.ilm[ti + k];
                 dev::GemmEntry ge;
                 if (t.pairwise()) {
-                  const size_t pi = ((size_t)ilm * t.Nel + ei) * t.Nel + ej;
-                  ge.A = w.tri ? s.d_tperm_tri.p + s.tpair_tri_off[pi] : s.d_tperm.p + s.tpair_off[pi];
+                  const size_t pidx = ((size_t)ilm * Nel + ei) * Nel + ej;
+                  ge.A = w.tri ? s.d_tperm_tri.p + s.tpair_tri_off[pidx] : s.d_tperm.p + s.tpair_off[pidx];
                 } else {
-                  ge.A = w.tri ? s.d_tperm_tri.p + s.tperm_tri_off[(size_t)ilm * t.Nel + ei]
-                               : s.d_tperm.p + s.tperm_off[(size_t)ilm * t.Nel + ei];
+                  ge.A = w.tri ? s.d_tperm_tri.p + s.tperm_tri_off[(size_t)ilm * Nel + ei]
+                               : s.d_tperm.p + s.tperm_off[(size_t)ilm * Nel + ei];
                 }
                 ge.lda = 0;
                 ge.B = s.d_R.p + (t0 + k) * slot_doubles;
                 gentries.push_back(ge);
               }
               gi.ent1 = (int)gentries.size();
-              gi.accumulate = acc;
+              gi.accumulate = st_flag ? 1 : 0;
+              st_flag = 1;
               gi.ldb = 0;
               gi.ldc = s.NB;
               gi.alpha = 1.0;
@@ -905,39 +1065,33 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
               np->fl_tg += 2.0 * gi.M * gi.N * (double)gi.K * (k1 - k0);
               np->al_tg += 2.0 * gi.M * (double)s.sec_n[w.op / ns] * s.sec_n[w.op % ns] * (double)gi.K * (k1 - k0);
             }
+          } else {
+            // cross-element item (rank-1 factors), always into Kc
+            char &st_flag = started[{wi * 4096 + (size_t)w.own_pairs[pi], 0}];
+            dev::OffItem oi{};
+            oi.C = s.d_Kc.p + koff;
+            oi.ei = ei;
+            oi.ej = ej;
+            oi.ent0 = (int)oentries.size();
+            for (size_t k = 0; k < take; k++) oentries.push_back(dev::OffEntry{(int)(t0 + k), w.ilm[ti + k]});
+            oi.ent1 = (int)oentries.size();
+            oi.accumulate = st_flag ? 1 : 0;
+            st_flag = 1;
+            oi.ncol = ncol;
+            oitems.push_back(oi);
+            const double per = 2.0 * t.nch * take * ((double)Ni * Nj * t.nch * Nj + (double)Ni * Nj * Ni);
+            np->fl_off += per * s.NB;
+            np->al_off += per * s.sec_n[w.op / ns] * s.sec_n[w.op % ns];
+          }
         }
-        // cross-element items (partial buffer 0); pair-tensor tables went through the GEMM above
-        if (!t.pairwise()) {
-          double *acc_base = s.d_Kacc.p + (size_t)wi * S * s.op_stride;
-          const int acc = ti > 0 ? 1 : 0;
-          const int oe0 = (int)oentries.size();
-          for (size_t k = 0; k < take; k++) oentries.push_back(dev::OffEntry{(int)(t0 + k), w.ilm[ti + k]});
-          for (int ei = 0; ei < t.Nel; ei++)
-            for (int ej = 0; ej < t.Nel; ej++) {
-              if (ei == ej || (w.tri && ei > ej)) continue;
-              dev::OffItem oi{};
-              oi.C = acc_base + s.ep_off[(size_t)ei * t.Nel + ej];
-              oi.ei = ei;
-              oi.ej = ej;
-              oi.ent0 = oe0;
-              oi.ent1 = (int)oentries.size();
-              oi.accumulate = acc;
-              oi.ncol = s.sec_span[w.op / ns] * s.NP;
-              oitems.push_back(oi);
-              const double per = 2.0 * t.nch * take *
-                                 ((double)t.en[ei] * t.en[ej] * t.nch * t.en[ej] + (double)t.en[ei] * t.en[ej] * t.en[ei]);
-              np->fl_off += per * s.NB;
-              np->al_off += per * s.sec_n[w.op / ns] * s.sec_n[w.op % ns];
-            }
-        }
-        np->fl_fold += 2.0 * (double)take * s.Npix * (double)s.NP * s.NP * s.NP * (t.nch + s.nab) * (s.parity ? 0.5 : 1.0);
-        for (size_t k = 0; k < take; k++) np->al_fold += w.alg_fold[ti + k];
+        np->fl_fold += 2.0 * (double)take * own_pix * (double)s.NP * s.NP * s.NP * (t.nch + s.nab) * (s.parity ? 0.5 : 1.0);
+        for (size_t k = 0; k < take; k++) np->al_fold += w.alg_fold[ti + k] * own_pix;
         done[wi] += take;
         remaining -= take;
       }
       if (tasks.empty()) break;
       // longest items first: CTAs are dispatched in block-index order, so the tail of the launch is made of
-      // the cheapest items (accumulating items of one output block never share a launch, order is free)
+      // the cheapest items (accumulating items of one unit never share a launch, order is free)
       std::stable_sort(gitems.begin(), gitems.end(), [](const dev::GemmItem &a, const dev::GemmItem &b) {
         return (double)a.M * a.N * a.K * (a.ent1 - a.ent0) > (double)b.M * b.N * b.K * (b.ent1 - b.ent0);
       });
@@ -956,14 +1110,13 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
     plans_->plans.push_back(std::move(np));
     plan = plans_->plans.back().get();
   }
-  // which dense blocks of K can be non-zero (for compact collectives and host copies)
+  // which dense blocks of K can be non-zero (for compact collectives and host copies): the pattern of the
+  // COMPLETE matrix, identical on every rank
   last_active_ops_.assign(plan->op_src.begin(), plan->op_src.end());
   if (plan_hook_) plan_hook_();
   // ---------------- run the plan ----------------
   const int S = plan->S;
-  if (S > 1)
-    for (int a = 0; a < plan->nactive; a++)
-      CK(cudaMemsetAsync(s.d_Kacc.p + ((size_t)a * S + 1) * s.op_stride, 0, (size_t)(S - 1) * s.op_stride * sizeof(double), st));
+  if (S > 1) CK(cudaMemsetAsync(s.d_Kacc.p, 0, (size_t)(S - 1) * plan->part_stride * sizeof(double), st));
   CK(cudaEventRecord(s.ev[1], st));
   float ms_fold = 0, ms_tg = 0, ms_off = 0;
   for (auto &btp : plan->batches) {
@@ -971,7 +1124,7 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
     CK(cudaEventRecord(s.ev[2], st));
     launch_fold(s.NT, t.nch, s.parity, s.bd, bt.tasks.p, bt.ntasks, s.d_G.p, s.d_Ppix.p, s.d_R.p, st);
     CK(cudaEventRecord(s.ev[3], st));
-    {
+    if (bt.ngitems) {
       // in-element exchange: one CTA tile covers all Ni^2 rows (R rows are read once)
       const dim3 grid(s.NB / 64, (unsigned)bt.ngitems);
       // stages of the shared-memory ring: as many as fit in 227 KB for the largest A tile of the plan, at most 4
@@ -994,32 +1147,45 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
       CK(cudaGetLastError());
     }
     CK(cudaEventRecord(s.ev[5], st));
-    CK(cudaStreamSynchronize(st));
-    float ms;
-    CK(cudaEventElapsedTime(&ms, s.ev[2], s.ev[3]));
-    ms_fold += ms;
-    CK(cudaEventElapsedTime(&ms, s.ev[3], s.ev[4]));
-    ms_tg += ms;
-    CK(cudaEventElapsedTime(&ms, s.ev[4], s.ev[5]));
-    ms_off += ms;
-    tm_.launches += 2 + (bt.noitems ? 1 : 0);
+    if (plan->batches.size() > 1) CK(cudaStreamSynchronize(st));   // the timing events are re-used by the next batch
+    tm_.launches += 1 + (bt.ngitems ? 1 : 0) + (bt.noitems ? 1 : 0);
     tm_.launches_fold++;
-    tm_.launches_tgemm++;
+    tm_.launches_tgemm += bt.ngitems ? 1 : 0;
     tm_.launches_offdiag += bt.noitems ? 1 : 0;
+    if (plan->batches.size() > 1) {
+      float ms;
+      CK(cudaEventElapsedTime(&ms, s.ev[2], s.ev[3]));
+      ms_fold += ms;
+      CK(cudaEventElapsedTime(&ms, s.ev[3], s.ev[4]));
+      ms_tg += ms;
+      CK(cudaEventElapsedTime(&ms, s.ev[4], s.ev[5]));
+      ms_off += ms;
+    }
   }
-  // 6. unpack
+  // 6. reduce the K-split partials of the own units, complete Kc over the ranks, unpack
   CK(cudaEventRecord(s.ev[6], st));
+  if (S > 1 && plan->nreduce) {
+    dev::k_reduce_partials<<<plan->nreduce, 256, 0, st>>>(plan->d_reduce.p, s.d_Kc.p, s.d_Kacc.p, S - 1, plan->part_stride);
+    CK(cudaGetLastError());
+    tm_.launches++;
+  }
+  if (comm_ && plan->seg > 0) comm_->all_gather_inplace(s.d_Kc.p, (size_t)plan->seg, st);
   // everything outside the computed sector pairs is exactly zero: clear K at memset speed, then unpack
   // only the angular blocks that can be non-zero
   CK(cudaMemset2DAsync(dK, (size_t)ldK * sizeof(double), 0, (size_t)nbf_ * sizeof(double), (size_t)nbf_, st));
   if (plan->nblocks) {
-    dev::UnpackDev u{plan->d_op_src.p, plan->d_op_tri.p, plan->d_blocks.p, s.d_ep_off.p, s.d_ang_sec.p, s.d_ang_pos.p,
-                     s.op_stride, S, s.kscale};
-    dev::k_unpack_K<<<plan->nblocks, 256, 0, st>>>(s.bd, u, s.d_Kacc.p, dK, ldK);
+    dev::UnpackDev u{plan->d_op_src.p, plan->d_op_tri.p, plan->d_blocks.p, plan->d_unit_off.p, s.d_ang_sec.p, s.d_ang_pos.p,
+                     s.kscale};
+    dev::k_unpack_K<<<plan->nblocks, 256, 0, st>>>(s.bd, u, s.d_Kc.p, dK, ldK);
     CK(cudaGetLastError());
   }
   CK(cudaEventRecord(s.ev[7], st));
   CK(cudaStreamSynchronize(st));
+  if (plan->batches.size() == 1) {
+    CK(cudaEventElapsedTime(&ms_fold, s.ev[2], s.ev[3]));
+    CK(cudaEventElapsedTime(&ms_tg, s.ev[3], s.ev[4]));
+    CK(cudaEventElapsedTime(&ms_off, s.ev[4], s.ev[5]));
+  }
   CK(cudaEventElapsedTime(&tm_.pack, s.ev[0], s.ev[1]));
   CK(cudaEventElapsedTime(&tm_.unpack, s.ev[6], s.ev[7]));
   CK(cudaEventElapsedTime(&tm_.total, s.ev[0], s.ev[7]));
@@ -1032,7 +1198,7 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
   tm_.alg_fold = plan->al_fold;
   tm_.alg_tgemm = plan->al_tg;
   tm_.alg_offdiag = plan->al_off;
-  tm_.launches += 3;
+  tm_.launches += 2;
 }
 
 const BasisTables &Engine::tables() const { return p_->t; }
@@ -1046,7 +1212,9 @@ Engine::~Engine() {
     for (cudaStream_t st : {p_->copy_stream, p_->up_stream, p_->j_stream})
       if (st) cudaStreamDestroy(st);
     if (!p_->norms_host.empty()) cudaHostUnregister(p_->norms_host.data());
+    if (p_->flags_host) cudaFreeHost(p_->flags_host);
   }
+  comm_.reset();
   if (stream_) cudaStreamDestroy(stream_);
 }
 
@@ -1135,8 +1303,9 @@ void Engine::coulomb_run(const double *dP, int64_t ldP, double *dJ, int64_t ldJ,
         entries.push_back(ge);
       }
       gi.ent1 = (int)entries.size();
-      if (gi.ent1 == gi.ent0 || nqs == 0) continue;
-      jp.M_active[Mi] = 1;
+      if (gi.ent1 == gi.ent0) continue;
+      jp.M_active[Mi] = 1;   // pattern of the COMPLETE J: identical on every shard
+      if (nqs == 0) continue;
       gi.accumulate = 0;
       gi.ldb = s.NB;
       gi.ldc = s.Npix;
@@ -1431,7 +1600,14 @@ bool Engine::fused_host(const double *P, int64_t ldP, double kscale, double *J, 
     CK(cudaMemcpy2DAsync(s.d_P.p, n * sizeof(double), P, ldP * sizeof(double), n * sizeof(double), n,
                          cudaMemcpyHostToDevice, stream_));
   }
-  pack_density(s.d_P.p, (int64_t)n, stream_);
+  s.want_norms_host = true;   // density_ranges() below predicts the next upload from the per-block norms
+  try {
+    pack_density(s.d_P.p, (int64_t)n, stream_);
+  } catch (...) {
+    s.want_norms_host = false;
+    throw;
+  }
+  s.want_norms_host = false;
   t_pack = ms_since();
   s.packed_valid = true;
   HostRanges hrj, hrk;

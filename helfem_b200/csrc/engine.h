@@ -21,6 +21,8 @@
 
 namespace hfq {
 
+class Comm;
+
 struct EngineTimings {      // milliseconds of the last call, CUDA events
   float pack = 0, fold = 0, tgemm = 0, offdiag = 0, unpack = 0, total = 0;
   double flops_fold = 0, flops_tgemm = 0, flops_offdiag = 0;  // executed (padded) flops
@@ -29,6 +31,10 @@ struct EngineTimings {      // milliseconds of the last call, CUDA events
   int launches_fold = 0, launches_tgemm = 0, launches_offdiag = 0;
   double h2d_bytes = 0, d2h_bytes = 0;   // host-pointer entry points: bytes moved over PCIe by the call
 };
+
+// Longest-processing-time assignment of work units to ranks (owner-computes sharding of the exchange build);
+// deterministic, so every rank derives the same ownership from the same plan.
+void assign_units(const std::vector<double> &cost, int nranks, std::vector<int> &owner);
 
 class Engine {
  public:
@@ -40,6 +46,11 @@ class Engine {
   int Nbf() const { return nbf_; }
   const BasisTables &tables() const;   // host description (integral blocks released after upload)
   int device() const { return device_; }
+  // Multi-GPU build, one process per GPU: bind this engine to an NCCL communicator (id from Comm::unique_id on rank
+  // 0, distributed by the caller).  From then on exchange_dev / jk_dev shard the exchange by output block over the
+  // ranks (owner computes) and complete K with one in-place all-gather; J is built in full on every rank.
+  void set_comm(const void *id128, int rank, int nranks);
+  int comm_size() const;
   void set_absm_symmetric(bool s) { absm_symmetric_ = s; }
   bool absm_symmetric() const { return absm_symmetric_; }
 
@@ -89,6 +100,7 @@ class Engine {
   struct PlanCache;
   std::unique_ptr<Impl> p_;
   std::unique_ptr<PlanCache> plans_;
+  std::unique_ptr<Comm> comm_;
   std::vector<int> last_active_ops_, last_active_j_;
   int device_ = 0, nbf_ = 0;
   bool absm_symmetric_ = false;

@@ -35,62 +35,70 @@ struct BasisDev {
   const int *rad_e1;     // [Nrad] last element containing it (elements overlap by one function)
 };
 
-// per (ang a, ang c) block: sum of squares -> out[a*Nang+c]; over the whole matrix max |P(i,j) - P(j,i)| ->
-// out[Nang^2] and max |P(i,j)| -> out[Nang^2 + 1] (zeroed by the caller; screening + symmetry test)
-static __global__ void k_block_norms(BasisDev b, const double *__restrict__ P, int64_t ld, double *__restrict__ out) {
-  const int a = blockIdx.x, c = blockIdx.y;
+// Block norms of P (the reference's screening quantity, src/diatomic/basis.cpp:1855-1864) and the symmetry test,
+// one pass over the matrix.  One WARP per unordered pair of angular functions (a <= c): it reads block (a, c) and
+// block (c, a) once each, both coalesced (the mirrored tile goes through a warp-private shared-memory tile), and
+// produces out[a*Nang+c], out[c*Nang+a] (sums of squares), max |P(i,j) - P(j,i)| -> out[Nang^2], max |P(i,j)| ->
+// out[Nang^2 + 1] (zeroed by the caller), and the sector-pair flags the plan needs: flags[sp] |= 1 if the block is
+// not exactly zero (it must be packed), |= 2 if its norm is not below 10 eps (the reference's skip test, negated so
+// that NaN blocks are kept).  grid (Nang, ceil(Nang / 4)), 128 threads.
+static __global__ void __launch_bounds__(128)
+k_block_norms(BasisDev b, const double *__restrict__ P, int64_t ld, const int *__restrict__ ang_sec,
+              double *__restrict__ out, int *__restrict__ flags) {
+  __shared__ double tiles[4][32][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x, a = blockIdx.y * 4 + warp;
+  if (a > c || a >= b.Nang) return;
+  double(*tm)[33] = tiles[warp];
   const int sa = b.ang_skip[a], sc = b.ang_skip[c];
   const int na = b.Nrad - sa, nc = b.Nrad - sc;
   const double *base = P + b.ang_off[a] + (int64_t)b.ang_off[c] * ld;   // block (a, c): na x nc
   const double *mirr = P + b.ang_off[c] + (int64_t)b.ang_off[a] * ld;   // block (c, a): nc x na
-  // 32 x 32 tiles; the mirrored tile goes through shared memory so that both reads are coalesced
-  __shared__ double tm[32][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8 threads
-  const bool cmp = a <= c;   // the pair (a, c), (c, a) is compared once
-  double s = 0.0, d = 0.0, m = 0.0;
+  double s1 = 0.0, s2 = 0.0, d = 0.0, m = 0.0;
   for (int j0 = 0; j0 < nc; j0 += 32)
     for (int i0 = 0; i0 < na; i0 += 32) {
-      if (cmp) {   // block-uniform
-        __syncthreads();
-        for (int k = ty; k < 32; k += 8) {   // mirror element (j0 + tx, i0 + k) of block (c, a)
-          const int jj = j0 + tx, ii = i0 + k;
-          tm[k][tx] = (jj < nc && ii < na) ? mirr[jj + (int64_t)ii * ld] : 0.0;
+      __syncwarp();
+      // mirror tile: element (j0 + lane, i0 + k) of block (c, a) -> tm[k][lane]
+      for (int k = 0; k < 32; k++) {
+        const int jj = j0 + lane, ii = i0 + k;
+        const double v = (jj < nc && ii < na) ? mirr[jj + (int64_t)ii * ld] : 0.0;
+        tm[k][lane] = v;
+        if (a != c) {
+          s2 += v * v;
+          m = fmax(m, fabs(v));
         }
-        __syncthreads();
       }
-      for (int k = ty; k < 32; k += 8) {   // element (i0 + tx, j0 + k) of block (a, c)
-        const int ii = i0 + tx, jj = j0 + k;
+      __syncwarp();
+      for (int k = 0; k < 32; k++) {   // element (i0 + lane, j0 + k) of block (a, c)
+        const int ii = i0 + lane, jj = j0 + k;
         if (ii < na && jj < nc) {
           const double v = base[ii + (int64_t)jj * ld];
-          s += v * v;
-          if (cmp) d = fmax(d, fabs(v - tm[tx][k]));
+          s1 += v * v;
+          d = fmax(d, fabs(v - tm[lane][k]));
           m = fmax(m, fabs(v));
         }
       }
     }
-  __shared__ double red[3][8];
   for (int o = 16; o > 0; o >>= 1) {
-    s += __shfl_down_sync(0xffffffffu, s, o);
+    s1 += __shfl_down_sync(0xffffffffu, s1, o);
+    s2 += __shfl_down_sync(0xffffffffu, s2, o);
     d = fmax(d, __shfl_down_sync(0xffffffffu, d, o));
     m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
   }
-  if (tx == 0) {
-    red[0][ty] = s;
-    red[1][ty] = d;
-    red[2][ty] = m;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int k = 1; k < 8; k++) {
-      s += red[0][k];
-      d = fmax(d, red[1][k]);
-      m = fmax(m, red[2][k]);
-    }
+  if (lane == 0) {
     const int64_t nn = (int64_t)b.Nang * b.Nang;
-    out[a * b.Nang + c] = s;
+    const double thr2 = 100.0 * 2.220446049250313e-16 * 2.220446049250313e-16;
+    out[a * b.Nang + c] = s1;
+    int f = (!(s1 == 0.0) ? 1 : 0) | (!(s1 < thr2) ? 2 : 0);
+    if (f) atomicOr(flags + ang_sec[a] * b.ns + ang_sec[c], f);
+    if (a != c) {
+      out[c * b.Nang + a] = s2;
+      f = (!(s2 == 0.0) ? 1 : 0) | (!(s2 < thr2) ? 2 : 0);
+      if (f) atomicOr(flags + ang_sec[c] * b.ns + ang_sec[a], f);
+    }
     // non-negative doubles order like their bit patterns: global maxima through integer atomicMax
     unsigned long long *mx = reinterpret_cast<unsigned long long *>(out + nn);
-    atomicMax(mx, (unsigned long long)__double_as_longlong(d));
+    if (d > 0.0) atomicMax(mx, (unsigned long long)__double_as_longlong(d));
     atomicMax(mx + 1, (unsigned long long)__double_as_longlong(m));
   }
 }
@@ -134,7 +142,20 @@ struct FoldTask {
   int rslot;           // slot in the R buffer
   int tri;             // 1: symmetric-density diagonal output pair -- only pixels (ri, rl) with el(ri) <= el(rl) are needed
   double fac;          // prefactor incl. (-1)^M
+  unsigned long long regmask;   // bit ei*Nel+ej: the element-pair block (ei, ej) of this output pair is built by this
+                                // rank (owner-computes sharding); all ones = every block (also: Nel > 8)
 };
+
+// is the pixel (ri, rl) part of an element pair this rank builds?  (a radial function lies in one or two elements)
+__device__ __forceinline__ bool fold_pixel_needed(const BasisDev &b, const FoldTask &t, int pix) {
+  const int ri = pix / b.Nrad, rl = pix - ri * b.Nrad;
+  if (t.tri && b.rad_e0[ri] > b.rad_e1[rl]) return false;   // mirrored by the unpack
+  if (t.regmask == ~0ull) return true;
+  for (int ei = b.rad_e0[ri]; ei <= b.rad_e1[ri]; ei++)
+    for (int ej = b.rad_e0[rl]; ej <= b.rad_e1[rl]; ej++)
+      if ((t.regmask >> (ei * b.Nel + ej)) & 1ull) return true;
+  return false;
+}
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src_bytes) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
@@ -200,6 +221,7 @@ k_fold(BasisDev b, const FoldTask *__restrict__ tasks, const double *__restrict_
     // stage 1: Yt_b[k][i] = sum_l Gk_b[k][l] P[i][l]   items: (slot, b, row tile of k)
     for (int item = warp; item < npx * NCH * NT; item += nwarp) {
       const int s = item / (NCH * NT), rem = item % (NCH * NT), bb = rem / NT, rt = rem % NT;
+      if (!fold_pixel_needed(b, t, pg + s)) continue;
       const int k0 = PAR ? (((rt / NTH) ^ Lpar) * NPH) : 0;
       const double *A = sGk + (bb * NP + rt * 8 + lr) * LD + lc + k0;
       const double *B = sP + ((buf * PB + s) * NP + lr) * LD + lc + k0;
@@ -226,6 +248,7 @@ k_fold(BasisDev b, const FoldTask *__restrict__ tasks, const double *__restrict_
     for (int item = warp; item < npx * NAB * NT; item += nwarp) {
       const int s = item / (NAB * NT), rem = item % (NAB * NT), ab = rem / NT, rt = rem % NT;
       const int aa = ab / NCH, bb = ab % NCH;
+      if (!fold_pixel_needed(b, t, pg + s)) continue;
       const int k0 = PAR ? (((rt / NTH) ^ Lpar) * NPH) : 0;
       const double *A = sGj + (aa * NP + rt * 8 + lr) * LD + lc + k0;
       const double *B = sY + ((s * NCH + bb) * NP + lr) * LD + lc + k0;
@@ -306,7 +329,7 @@ k_fold_reg(BasisDev b, const FoldTask *__restrict__ tasks, const double *__restr
     cp_async_commit();
     cp_async_wait<1>();
     __syncwarp();
-    if (t.tri && b.rad_e0[pix / b.Nrad] > b.rad_e1[pix % b.Nrad]) continue;   // mirrored by the unpack
+    if (!fold_pixel_needed(b, t, pix)) continue;   // mirrored by the unpack, or built by another rank
     const double *P = myP + buf * NP * LDP + lr * LDP + lc;
     // ---- stage 1
     double c1[NCH][NT][NT][2];
@@ -925,22 +948,37 @@ k_tgemm_ws(const GemmItem *__restrict__ items, const GemmEntry *__restrict__ ent
 // grid (dense column tiles), one thread per dense element
 // ---------------------------------------------------------------------------
 struct UnpackDev {
-  const int *op_src;      // [ns*ns] sector pair whose accumulator holds this block (or -1: zero)
-  const int *op_tri;      // [active op] 1: symmetric storage (see below)
-  const int *blocks;      // angular blocks (j | k << 16) whose sector pair was computed
-  const int64_t *ep_off;  // [Nel*Nel] offset of element-pair block inside one output pair's accumulator
-  const int *ang_sec;     // [Nang] sector of angular function
-  const int *ang_pos;     // [Nang] position inside the sector
-  int64_t op_stride;      // accumulator stride per (output pair, partial)
-  int S;                  // partial accumulators per output pair (K-split of the in-element GEMM)
-  double scale;           // exchange(scale * P) = scale * exchange(P)
+  const int *op_src;        // [ns*ns] active output pair whose units hold this block (or -1: zero)
+  const int *op_tri;        // [active op] 1: symmetric storage (see below)
+  const int *blocks;        // angular blocks (j | k << 16) whose sector pair was computed
+  const int64_t *unit_off;  // [(active op * Nel + ei) * Nel + ej] offset of the unit's [rows][NB] block in Kc, -1: absent
+                            // (built by another rank and not gathered: the caller sums the partial matrices)
+  const int *ang_sec;       // [Nang] sector of angular function
+  const int *ang_pos;       // [Nang] position inside the sector
+  double scale;             // exchange(scale * P) = scale * exchange(P)
 };
+
+// Sum of the K-split partial accumulators of the units this rank built into the compact unit buffer:
+// Kc[dst + i] += sum_c part[src + c * cstride + i].  One descriptor per (unit, 16K-element slab).
+struct ReduceDesc {
+  int64_t dst, src;   // offsets in doubles into Kc / the partial buffer
+  int n;              // doubles
+};
+static __global__ void k_reduce_partials(const ReduceDesc *__restrict__ descs, double *__restrict__ Kc,
+                                         const double *__restrict__ part, int nparts, int64_t cstride) {
+  const ReduceDesc d = descs[blockIdx.x];
+  for (int i = threadIdx.x; i < d.n; i += blockDim.x) {
+    double s = Kc[d.dst + i];
+    for (int c = 0; c < nparts; c++) s += part[d.src + (int64_t)c * cstride + i];
+    Kc[d.dst + i] = s;
+  }
+}
 
 // Symmetric storage (diagonal output pairs of a symmetric density): K(j rj, k rk) = K(k rk, j rj), so
 // only element pairs ei <= ej were computed, and of an in-element block only the rows rj <= rk
 // (row t = rk (rk+1)/2 + rj); the other half is read from the mirrored entry, column (pos_k, pos_j).
 // One CTA per angular block that can be non-zero (u.blocks[] = angj | angk << 16); the caller zero-fills K first.
-static __global__ void k_unpack_K(BasisDev b, UnpackDev u, const double *__restrict__ Kacc, double *__restrict__ K, int64_t ld) {
+static __global__ void k_unpack_K(BasisDev b, UnpackDev u, const double *__restrict__ Kc, double *__restrict__ K, int64_t ld) {
   const int angj = u.blocks[blockIdx.x] & 0xffff, angk = u.blocks[blockIdx.x] >> 16;
   const int sj = b.ang_skip[angj], sk = b.ang_skip[angk];
   const int nj = b.Nrad - sj, nk = b.Nrad - sk;
@@ -950,6 +988,7 @@ static __global__ void k_unpack_K(BasisDev b, UnpackDev u, const double *__restr
   const int blk = u.ang_pos[angj] * b.NP + u.ang_pos[angk];
   const int blkT = u.ang_pos[angk] * b.NP + u.ang_pos[angj];
   const bool tri = src >= 0 && u.op_tri[src];
+  const int64_t *uo = u.unit_off + (int64_t)(src < 0 ? 0 : src) * b.Nel * b.Nel;
   for (int idx = threadIdx.x; idx < nj * nk; idx += blockDim.x) {
     const int r = idx % nj + sj, c = idx / nj + sk;
     double s = 0.0;
@@ -958,17 +997,21 @@ static __global__ void k_unpack_K(BasisDev b, UnpackDev u, const double *__restr
         const int ri = r - b.efirst[ei];
         for (int ej = b.rad_e0[c]; ej <= b.rad_e1[c]; ej++) {
           const int rk = c - b.efirst[ej];
-          int64_t off;
-          if (!tri || ei < ej)
-            off = u.ep_off[ei * b.Nel + ej] + (int64_t)(ri * b.en[ej] + rk) * b.NB + blk;
-          else if (ei > ej)
-            off = u.ep_off[ej * b.Nel + ei] + (int64_t)(rk * b.en[ei] + ri) * b.NB + blkT;
-          else if (ri <= rk)
-            off = u.ep_off[ei * b.Nel + ei] + (int64_t)(rk * (rk + 1) / 2 + ri) * b.NB + blk;
-          else
-            off = u.ep_off[ei * b.Nel + ei] + (int64_t)(ri * (ri + 1) / 2 + rk) * b.NB + blkT;
-          const double *acc = Kacc + (int64_t)src * u.S * u.op_stride + off;
-          for (int p = 0; p < u.S; p++) s += acc[(int64_t)p * u.op_stride];
+          int64_t base, off;
+          if (!tri || ei < ej) {
+            base = uo[ei * b.Nel + ej];
+            off = (int64_t)(ri * b.en[ej] + rk) * b.NB + blk;
+          } else if (ei > ej) {
+            base = uo[ej * b.Nel + ei];
+            off = (int64_t)(rk * b.en[ei] + ri) * b.NB + blkT;
+          } else if (ri <= rk) {
+            base = uo[ei * b.Nel + ei];
+            off = (int64_t)(rk * (rk + 1) / 2 + ri) * b.NB + blk;
+          } else {
+            base = uo[ei * b.Nel + ei];
+            off = (int64_t)(ri * (ri + 1) / 2 + rk) * b.NB + blkT;
+          }
+          if (base >= 0) s += Kc[base + off];
         }
       }
     }

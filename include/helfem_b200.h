@@ -163,8 +163,11 @@ int hfq_exchange(hfq_ctx *ctx, const double *P, int64_t ldP, double *K, int64_t 
 
 /* Same with device-resident matrices on the context's GPU; `stream` is a cudaStream_t
  * (NULL = the context's own stream).  The call returns after the work is complete.
- * shard/nshards split the exchange output blocks across ranks: blocks owned by other
- * shards are written as zero, so an all-reduce(sum) over ranks yields the full matrix. */
+ * shard/nshards (contexts WITHOUT a communicator, see hfq_comm_init): the exchange is split by output block
+ * -- unit = (output sector pair, radial element pair), dealt longest-first to the least loaded shard -- and each
+ * shard writes only the contributions of its own units (everything else zero), so the sum of the nshards matrices
+ * is the full K; J is split over multipoles the same way.  With a communicator the arguments are ignored: rank
+ * and size come from it and the results are complete on every rank. */
 int hfq_coulomb_device(hfq_ctx *ctx, const double *dP, int64_t ldP, double *dJ, int64_t ldJ, void *stream);
 int hfq_exchange_device(hfq_ctx *ctx, const double *dP, int64_t ldP, double *dK, int64_t ldK, int shard,
                         int nshards, void *stream);
@@ -177,6 +180,22 @@ int hfq_coulomb_exchange(hfq_ctx *ctx, const double *P, int64_t ldP, double ksca
                          int64_t ldK);
 int hfq_coulomb_exchange_device(hfq_ctx *ctx, const double *dP, int64_t ldP, double kscale, double *dJ, int64_t ldJ,
                                 double *dK, int64_t ldK, int shard, int nshards, void *stream);
+
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink (the reference's OpenMP axis over output
+ * blocks, src/diatomic/basis.cpp:1866-1875, becomes the shard axis) -----------------------------------------------
+ * hfq_comm_unique_id: ncclGetUniqueId on rank 0 (128 bytes); the caller distributes it (MPI_Bcast,
+ * torch.distributed broadcast, a file ...).  hfq_comm_init: ncclCommInitRank for the context's device -- collective
+ * over all ranks.  From then on hfq_exchange_device / hfq_coulomb_exchange_device build only the units this rank
+ * owns, complete the compact result with ONE in-place ncclAllGather issued by the library on the build stream
+ * (N2 lmax=30: 55 MB in total, each rank contributes 1/nranks), and unpack the complete K on every rank; J is built
+ * in full on every rank (0.7 ms; cheaper than a second collective).  NCCL is bound at run time (dlopen of
+ * libnccl.so.2, or $HFQ_NCCL_LIB); single-GPU users never load it.  nranks == 1 removes the communicator. */
+int hfq_comm_unique_id(void *id128);
+int hfq_comm_init(hfq_ctx *ctx, const void *id128, int rank, int nranks);
+int hfq_comm_size(const hfq_ctx *ctx);
+/* The ownership rule itself (host only, testable without a GPU): owner[i] in [0, nranks) for n work units of the
+ * given costs, longest first onto the least loaded rank, ties by index. */
+int hfq_shard_assign(const double *cost, int n, int nranks, int *owner);
 
 /* ---- DFT quadrature grid: DFTGrid::eval_Fxc of the atomic basis --------------------------------
  * (src/atomic/dftgrid.h:156,159; worker src/atomic/dftgrid.cpp:51-242, :304-465, :470-576).

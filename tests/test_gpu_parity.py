@@ -166,22 +166,72 @@ def test_errors(hb):
 
 
 def test_exchange_shards_sum_to_full(hb):
-    """Multi-GPU protocol on one device: the per-shard partial K matrices (device API) sum to
-    the unsharded result -- what the NCCL all-reduce relies on."""
+    """Owner-computes sharding on one device: every shard writes only the contributions of the units
+    (output sector pair, element pair) it owns; the per-shard partial K (and J) matrices sum to the unsharded
+    result, and the reported output pattern is the pattern of the COMPLETE matrix on every shard."""
     import torch
     basis = hb.DiatomicTwoDBasis(7, 7, 2.07, [4, 3, 2], 2).compute_tei()
     n = basis.Nbf()
     t = basis.tables
     P = cases.random_density(n, 3, 7, cases.m_blocks(t.mval, t.Nrad, True))
-    Kfull = basis.exchange(P)
+    Kfull, Jfull = basis.exchange(P), basis.coulomb(P)
     dP = torch.from_numpy(np.ascontiguousarray(P.T)).cuda()
-    for nsh in (2, 3):
+    for nsh in (2, 3, 8):
+        tot, totj = torch.zeros_like(dP), torch.zeros_like(dP)
+        patterns = set()
+        for sh in range(nsh):
+            dK, dJ = torch.empty_like(dP), torch.empty_like(dP)
+            basis.coulomb_exchange_device(dP.data_ptr(), dJ.data_ptr(), dK.data_ptr(), 1.0, sh, nsh)
+            tot += dK
+            totj += dJ
+            patterns.add((tuple(basis.exchange_output_pattern()[1]), tuple(basis.exchange_output_pattern(True)[1])))
+        assert cases.relerr(tot.cpu().numpy().T, Kfull) < TOL
+        assert cases.relerr(totj.cpu().numpy().T, Jfull) < TOL
+        assert len(patterns) == 1, "output pattern differs between shards"
+
+
+def test_shards_one_task_per_output_pair(hb):
+    """An s-only atomic density with lmax >= 1 gives ONE task per output pair: shards then own disjoint sets of
+    output pairs, yet the reported pattern (what a compact collective is built from) must be the same everywhere."""
+    import torch
+    oa = cases.oracle_atomic(4, 2, 2, 3)
+    basis = hb.TablesBasis(cases.tables_from_oracle_atomic(hb, oa))
+    n = oa.Nbf()
+    N = oa.Nrad()
+    P = np.zeros((n, n))
+    P[:N, :N] = cases.random_density(N, 2, 5)       # (l, m) = (0, 0) block only
+    Kfull = basis.exchange(P)
+    assert cases.relerr(Kfull, oa.exchange(P)) < TOL
+    dP = torch.from_numpy(np.ascontiguousarray(P.T)).cuda()
+    for nsh in (2, 4):
         tot = torch.zeros_like(dP)
+        patterns = set()
         for sh in range(nsh):
             dK = torch.empty_like(dP)
             basis.exchange_device(dP.data_ptr(), dK.data_ptr(), sh, nsh)
             tot += dK
+            patterns.add(tuple(basis.exchange_output_pattern()[1]))
         assert cases.relerr(tot.cpu().numpy().T, Kfull) < TOL
+        assert len(patterns) == 1
+
+
+def test_shards_headline_kernels(hb):
+    """Sharding by (output pair, element pair) on the NP = 16 kernels of the bench: the region mask of the fold,
+    K-split partials per shard, 8 shards."""
+    import torch
+    from tests.test_gpu_parity_large import gu_density
+    basis = hb.DiatomicTwoDBasis(7, 7, 2.07, [18, 17], 3).compute_tei()
+    t = basis.tables
+    for P in (gu_density(t, 3), cases.random_density(t.Nbf, 3, 4, cases.m_blocks(t.mval, t.Nrad, True))):
+        Kfull = basis.exchange(P)
+        dP = torch.from_numpy(np.ascontiguousarray(P.T)).cuda()
+        for nsh in (2, 8):
+            tot = torch.zeros_like(dP)
+            for sh in range(nsh):
+                dK = torch.empty_like(dP)
+                basis.exchange_device(dP.data_ptr(), dK.data_ptr(), sh, nsh)
+                tot += dK
+            assert cases.relerr(tot.cpu().numpy().T, Kfull) < TOL
 
 
 def test_sadatom_coulomb_exchange(hb):
