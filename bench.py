@@ -224,6 +224,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     hb_build.build()
 
+    hb.set_host_threads(world=world)   # torchrun exports OMP_NUM_THREADS=1: give each rank its share of the cores
     t0 = time.time()
     T = hb.Tables.diatomic(7, 7, 2.07, [args.lmax] * (args.mmax + 1), args.nelem)
     t_setup = time.time() - t0

@@ -41,7 +41,7 @@ EXPORTED_SYMBOLS = [
     "hfq_tables_destroy", "hfq_create", "hfq_destroy", "hfq_nbf", "hfq_set_absm_symmetric", "hfq_coulomb",
     "hfq_exchange", "hfq_coulomb_device", "hfq_exchange_device", "hfq_last_timings", "hfq_exchange_output_pattern",
     "hfq_coulomb_output_pattern",
-    "hfq_comm_unique_id", "hfq_comm_init", "hfq_comm_size", "hfq_shard_assign",
+    "hfq_set_host_threads", "hfq_comm_unique_id", "hfq_comm_init", "hfq_comm_size", "hfq_shard_assign",
     "hfq_coulomb_exchange", "hfq_coulomb_exchange_device", "hfq_grid_attach", "hfq_grid_npoints", "hfq_grid_density", "hfq_grid_fxc", "hfq_eval_fxc",
 ]
 
@@ -92,6 +92,7 @@ def lib():
     L.hfq_coulomb_output_pattern.argtypes = [vp, vp, i64, vp, i64]
     L.hfq_coulomb_exchange.argtypes = [vp, vp, i64, cd, vp, i64, vp, i64]
     L.hfq_coulomb_exchange_device.argtypes = [vp, vp, i64, cd, vp, i64, vp, i64, ci, ci, vp]
+    L.hfq_set_host_threads.argtypes = [ci]
     L.hfq_comm_unique_id.argtypes = [vp]
     L.hfq_comm_init.argtypes = [vp, vp, ci, ci]
     L.hfq_comm_size.argtypes = [vp]
@@ -104,6 +105,14 @@ def lib():
     L.hfq_eval_fxc.argtypes = [vp, ci, ci, vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, ci, cd]
     _lib = L
     return L
+
+
+def set_host_threads(n=None, world=1):
+    """OpenMP threads of the host-side setup; default: this process' share of the cores it may run on."""
+    if n is None:
+        n = max(1, len(os.sched_getaffinity(0)) // max(1, world))
+    _check(lib().hfq_set_host_threads(int(n)))
+    return int(n)
 
 
 class HfqError(RuntimeError):

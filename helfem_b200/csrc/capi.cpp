@@ -1,6 +1,8 @@
 // C ABI of libhelfemqc_b200 (see include/helfem_b200.h).
 #include "../../include/helfem_b200.h"
 
+#include <omp.h>
+
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -565,6 +567,12 @@ int hfq_eval_fxc(hfq_ctx *ctx, int x_func, int c_func, const double *Pa, int64_t
     ctx->grid->fxc(0, beta != 0, exc.data(), vrho.data(), nullptr, nullptr, nullptr, Ha, ldHa, Hb, ldHb, Exc);
     return HFQ_OK;
   });
+}
+
+int hfq_set_host_threads(int n) {
+  if (n < 1) return fail(HFQ_ERR_INVALID, "hfq_set_host_threads: n < 1");
+  omp_set_num_threads(n);
+  return HFQ_OK;
 }
 
 int hfq_comm_unique_id(void *id128) {

@@ -63,7 +63,8 @@ int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 // ntasks == 0: configure the kernel (opt-in shared memory size) on the current device, launch nothing
 void launch_fold(int NT, int nch, bool par, const dev::BasisDev &bd, const dev::FoldTask *tasks, int ntasks,
-                 const double *G, const double *Ppix, double *R, cudaStream_t st);
+                 const int *pixlist, int maxpix, int64_t totpix, const double *G, const double *Ppix, double *R,
+                 cudaStream_t st);
 
 }  // namespace
 
@@ -490,15 +491,17 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
   }
   s.d_zrow.upload(std::vector<double>(64, 0.0), &dev_bytes_);
   // opt-in shared memory of the fold kernel this basis uses (a per-device attribute: set by every engine)
-  launch_fold(s.NT, t.nch, s.parity, s.bd, nullptr, 0, nullptr, nullptr, nullptr, stream_);
+  launch_fold(s.NT, t.nch, s.parity, s.bd, nullptr, 0, nullptr, 0, 0, nullptr, nullptr, nullptr, stream_);
 }
 
 
 namespace {
 
+// maxpix = longest pixel list of a task, totpix = sum over the tasks: the pixel chunk per CTA is sized so that the
+// launch has a few thousand CTAs and every CTA amortises its coupling-table load over >= 8 pixels per warp
 template <int NT, int NCH, bool PAR>
-void launch_fold_t(const dev::BasisDev &bd, const dev::FoldTask *tasks, int ntasks, const double *G, const double *Ppix,
-                   double *R, cudaStream_t st) {
+void launch_fold_t(const dev::BasisDev &bd, const dev::FoldTask *tasks, int ntasks, const int *pixlist, int maxpix,
+                   int64_t totpix, const double *G, const double *Ppix, double *R, cudaStream_t st) {
   constexpr int NP = NT * 8, LD = NP + 4;
   if constexpr (NT <= 2 && !PAR) {
     // register-resident two-stage fold, one pixel per warp
@@ -508,10 +511,10 @@ void launch_fold_t(const dev::BasisDev &bd, const dev::FoldTask *tasks, int ntas
       CK(cudaFuncSetAttribute(dev::k_fold_reg<NT, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       return;
     }
-    int ppc = std::max(8, (int)(((int64_t)bd.Npix * ntasks + 148 * 8 - 1) / (148 * 8)));
-    ppc = round_up(std::min(std::min(ppc, 64), bd.Npix), 8);
-    const dim3 grid((bd.Npix + ppc - 1) / ppc, ntasks);
-    dev::k_fold_reg<NT, NCH><<<grid, 256, smem, st>>>(bd, tasks, G, Ppix, R, ppc);
+    int ppc = std::max(64, (int)((totpix + 148 * 32 - 1) / (148 * 32)));
+    ppc = round_up(std::min(std::min(ppc, 256), std::max(maxpix, 8)), 8);
+    const dim3 grid((maxpix + ppc - 1) / ppc, ntasks);
+    dev::k_fold_reg<NT, NCH><<<grid, 256, smem, st>>>(bd, tasks, pixlist, G, Ppix, R, ppc);
     CK(cudaGetLastError());
     return;
   }
@@ -527,23 +530,24 @@ void launch_fold_t(const dev::BasisDev &bd, const dev::FoldTask *tasks, int ntas
   PB = std::max(PB, 1);
   const size_t smem = gbytes + PB * slot;
   // pixels per CTA: enough CTAs to fill the GPU, but amortise the table load
-  int ppc = std::max(PB, (int)(((int64_t)bd.Npix * ntasks + 148 * 8 - 1) / (148 * 8)));
+  int ppc = std::max(PB, (int)((totpix + 148 * 8 - 1) / (148 * 8)));
   ppc = std::min(ppc, std::max(PB * 8, 64));
-  ppc = round_up(std::min(ppc, bd.Npix), PB);
-  const dim3 grid((bd.Npix + ppc - 1) / ppc, ntasks);
-  dev::k_fold<NT, NCH, PAR><<<grid, 256, smem, st>>>(bd, tasks, G, Ppix, R, ppc, PB);
+  ppc = round_up(std::min(ppc, std::max(maxpix, 1)), PB);
+  const dim3 grid((maxpix + ppc - 1) / ppc, ntasks);
+  dev::k_fold<NT, NCH, PAR><<<grid, 256, smem, st>>>(bd, tasks, pixlist, G, Ppix, R, ppc, PB);
   CK(cudaGetLastError());
 }
 
 void launch_fold(int NT, int nch, bool par, const dev::BasisDev &bd, const dev::FoldTask *tasks, int ntasks,
-                 const double *G, const double *Ppix, double *R, cudaStream_t st) {
-#define HFQ_FOLD_CASE(nt, parity)                                                \
-  if (NT == nt && par == parity) {                                               \
-    if (nch == 1)                                                                \
-      launch_fold_t<nt, 1, parity>(bd, tasks, ntasks, G, Ppix, R, st);           \
-    else                                                                         \
-      launch_fold_t<nt, 2, parity>(bd, tasks, ntasks, G, Ppix, R, st);           \
-    return;                                                                      \
+                 const int *pixlist, int maxpix, int64_t totpix, const double *G, const double *Ppix, double *R,
+                 cudaStream_t st) {
+#define HFQ_FOLD_CASE(nt, parity)                                                                        \
+  if (NT == nt && par == parity) {                                                                       \
+    if (nch == 1)                                                                                        \
+      launch_fold_t<nt, 1, parity>(bd, tasks, ntasks, pixlist, maxpix, totpix, G, Ppix, R, st);          \
+    else                                                                                                 \
+      launch_fold_t<nt, 2, parity>(bd, tasks, ntasks, pixlist, maxpix, totpix, G, Ppix, R, st);          \
+    return;                                                                                              \
   }
   HFQ_FOLD_CASE(1, false)
   HFQ_FOLD_CASE(2, false)
@@ -688,6 +692,8 @@ struct ExchangeBatch {
   DevBuf<dev::OffItem> oitems;
   DevBuf<dev::OffEntry> oentries;
   int ntasks = 0, ngitems = 0, noitems = 0;
+  int maxpix = 0;        // longest pixel list of a task
+  int64_t totpix = 0;    // pixels folded by the batch
 };
 struct ExchangePlan {
   std::string key;
@@ -696,6 +702,7 @@ struct ExchangePlan {
   DevBuf<int> d_op_src, d_op_tri, d_blocks;   // device copies + angular blocks (j | k << 16) that can be non-zero
   DevBuf<int64_t> d_unit_off;                 // [(active op * Nel + ei) * Nel + ej] offset in Kc or -1
   DevBuf<dev::ReduceDesc> d_reduce;
+  DevBuf<int> d_pixlist;                      // pixel lists of the fold tasks (one per distinct set of owned element pairs)
   int nreduce = 0;
   int64_t seg = 0;                            // doubles per rank segment of Kc
   int64_t part_stride = 0;                    // doubles per K-split partial (partials 1 .. S-1 of the own units)
@@ -776,8 +783,8 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
       std::vector<dev::FoldTask> tasks;
       std::vector<int> ilm;
       std::vector<double> alg_fold;  // unpadded flops of the fold per task (all pixels)
-      unsigned long long regmask = 0;   // element pairs built by this rank
-      std::vector<int> own_pairs;       // ei * Nel + ej of those
+      std::vector<int> own_pairs;       // ei * Nel + ej of the element pairs built by this rank
+      int pix0 = 0, npix = 0;           // its pixel list (pixels of those element pairs)
     };
     std::vector<OpWork> work;   // every active output pair (identical on all ranks)
     np->op_src.assign((size_t)ns * ns, -1);
@@ -807,9 +814,8 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
               ft.spp = si * ns + sl;
               ft.L = L;
               ft.rslot = 0;
-              ft.tri = w.tri ? 1 : 0;
+              ft.pix0 = ft.npix = 0;
               ft.fac = t.pref[ilm] * ((t.sign_by_M && (M & 1)) ? -1.0 : 1.0);
-              ft.regmask = ~0ull;
               w.tasks.push_back(ft);
               w.ilm.push_back(ilm);
               const double nj = s.sec_n[sj], nk = s.sec_n[sk], ni = s.sec_n[si], nl = s.sec_n[sl];
@@ -898,12 +904,33 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
       if (u.owner == shard) {
         OpWork &w = work[u.a];
         w.own_pairs.push_back(u.ei * Nel + u.ej);
-        if (Nel <= 8) w.regmask |= 1ull << (u.ei * Nel + u.ej);
         if (u.ei == u.ej || t.pairwise()) own_gemm_ctas += (u.ncol + 63) / 64;
       }
-    if (!by_pair)
-      for (auto &w : work)
-        if (!w.own_pairs.empty()) w.regmask = ~0ull;
+    {
+      // pixel lists: the pixels (ri, rl) of the owned element pairs of an output pair (elements overlap in their
+      // boundary functions: each pixel once), one list per distinct set
+      std::map<std::vector<int>, std::pair<int, int>> lists;
+      std::vector<int> pixlist;
+      for (auto &w : work) {
+        if (w.own_pairs.empty()) continue;
+        auto it = lists.find(w.own_pairs);
+        if (it == lists.end()) {
+          std::vector<char> need((size_t)s.Npix, 0);
+          for (int pr : w.own_pairs) {
+            const int ei = pr / Nel, ej = pr % Nel;
+            for (int ri = t.efirst[ei]; ri < t.efirst[ei] + t.en[ei]; ri++)
+              for (int rl = t.efirst[ej]; rl < t.efirst[ej] + t.en[ej]; rl++) need[(size_t)ri * t.Nrad + rl] = 1;
+          }
+          const int p0 = (int)pixlist.size();
+          for (int pix = 0; pix < s.Npix; pix++)
+            if (need[pix]) pixlist.push_back(pix);
+          it = lists.emplace(w.own_pairs, std::make_pair(p0, (int)pixlist.size() - p0)).first;
+        }
+        w.pix0 = it->second.first;
+        w.npix = it->second.second;
+      }
+      np->d_pixlist.upload(pixlist, &dev_bytes_);
+    }
     size_t total_tasks = 0;
     for (auto &w : work)
       if (!w.own_pairs.empty()) total_tasks += w.tasks.size();
@@ -977,14 +1004,9 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
     np->R_base = s.d_R.p;
     np->K_base = s.d_Kacc.p;
     np->Kc_base = s.d_Kc.p;
-    auto unit_off = [&](int a, int pair) {
-      for (auto &u : units)
-        if (u.a == a && u.ei * Nel + u.ej == pair) return u.off;
-      return (int64_t)-1;
-    };
-    std::vector<std::vector<int64_t>> own_off(work.size());
-    for (size_t wi = 0; wi < work.size(); wi++)
-      for (int pr : work[wi].own_pairs) own_off[wi].push_back(unit_off((int)wi, pr));
+    std::vector<std::vector<int64_t>> own_off(work.size());   // parallel to OpWork::own_pairs (both follow the unit order)
+    for (auto &u : units)
+      if (u.owner == shard) own_off[u.a].push_back(u.off);
     // Batches: every batch takes an equal share of tasks from every output pair this rank works on, so each
     // launch works on all of them at once (grid size independent of the batch count).
     std::vector<size_t> done(work.size(), 0);
@@ -996,6 +1018,8 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
       std::vector<dev::GemmEntry> gentries;
       std::vector<dev::OffItem> oitems;
       std::vector<dev::OffEntry> oentries;
+      int batch_maxpix = 0;
+      int64_t batch_totpix = 0;
       size_t open = 0;
       for (size_t wi = 0; wi < work.size(); wi++) open += !work[wi].own_pairs.empty() && done[wi] < work[wi].tasks.size();
       const size_t share = std::max<size_t>(1, s.r_slots / std::max<size_t>(open, 1));
@@ -1011,12 +1035,13 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
         for (size_t k = 0; k < take; k++) {
           dev::FoldTask ft = w.tasks[ti + k];
           ft.rslot = (int)(t0 + k);
-          ft.regmask = w.regmask;
+          ft.pix0 = w.pix0;
+          ft.npix = w.npix;
           tasks.push_back(ft);
         }
-        double own_pix = 0.0;   // pixels this rank folds per task (element-pair blocks overlap in their boundary functions)
-        for (int pr : w.own_pairs) own_pix += (double)t.en[pr / Nel] * t.en[pr % Nel];
-        own_pix = std::min(own_pix, (double)s.Npix * (w.tri ? s.tri_pix_frac : 1.0));
+        const double own_pix = w.npix;   // pixels this rank folds per task
+        batch_maxpix = std::max(batch_maxpix, w.npix);
+        batch_totpix += (int64_t)take * w.npix;
         for (size_t pi = 0; pi < w.own_pairs.size(); pi++) {
           const int ei = w.own_pairs[pi] / Nel, ej = w.own_pairs[pi] % Nel;
           const int Ni = t.en[ei], Nj = t.en[ej];
@@ -1104,6 +1129,8 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
       bt->ntasks = (int)tasks.size();
       bt->ngitems = (int)gitems.size();
       bt->noitems = (int)oitems.size();
+      bt->maxpix = batch_maxpix;
+      bt->totpix = batch_totpix;
       np->batches.push_back(std::move(bt));
     }
     if (plans_->plans.size() >= 4) plans_->plans.erase(plans_->plans.begin());
@@ -1122,7 +1149,8 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
   for (auto &btp : plan->batches) {
     ExchangeBatch &bt = *btp;
     CK(cudaEventRecord(s.ev[2], st));
-    launch_fold(s.NT, t.nch, s.parity, s.bd, bt.tasks.p, bt.ntasks, s.d_G.p, s.d_Ppix.p, s.d_R.p, st);
+    launch_fold(s.NT, t.nch, s.parity, s.bd, bt.tasks.p, bt.ntasks, plan->d_pixlist.p, bt.maxpix, bt.totpix, s.d_G.p,
+                s.d_Ppix.p, s.d_R.p, st);
     CK(cudaEventRecord(s.ev[3], st));
     if (bt.ngitems) {
       // in-element exchange: one CTA tile covers all Ni^2 rows (R rows are read once)

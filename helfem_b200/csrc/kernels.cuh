@@ -140,22 +140,11 @@ struct FoldTask {
   int spj, spk, spp;   // sector pairs of the two coupling tables and of P
   int L;               // multipole order (index into the coupling tables)
   int rslot;           // slot in the R buffer
-  int tri;             // 1: symmetric-density diagonal output pair -- only pixels (ri, rl) with el(ri) <= el(rl) are needed
+  int pix0, npix;      // the pixels (ri, rl) to fold: pixlist[pix0 .. pix0 + npix).  Not all of them in general: a
+                       // symmetric-density diagonal output pair needs el(ri) <= el(rl) only (mirrored by the unpack),
+                       // and under owner-computes sharding a rank folds the element pairs it builds
   double fac;          // prefactor incl. (-1)^M
-  unsigned long long regmask;   // bit ei*Nel+ej: the element-pair block (ei, ej) of this output pair is built by this
-                                // rank (owner-computes sharding); all ones = every block (also: Nel > 8)
 };
-
-// is the pixel (ri, rl) part of an element pair this rank builds?  (a radial function lies in one or two elements)
-__device__ __forceinline__ bool fold_pixel_needed(const BasisDev &b, const FoldTask &t, int pix) {
-  const int ri = pix / b.Nrad, rl = pix - ri * b.Nrad;
-  if (t.tri && b.rad_e0[ri] > b.rad_e1[rl]) return false;   // mirrored by the unpack
-  if (t.regmask == ~0ull) return true;
-  for (int ei = b.rad_e0[ri]; ei <= b.rad_e1[ri]; ei++)
-    for (int ej = b.rad_e0[rl]; ej <= b.rad_e1[rl]; ej++)
-      if ((t.regmask >> (ei * b.Nel + ej)) & 1ull) return true;
-  return false;
-}
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src_bytes) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
@@ -177,8 +166,8 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // run over NP/2 instead of NP.
 template <int NT, int NCH, bool PAR>
 __global__ void __launch_bounds__(256)
-k_fold(BasisDev b, const FoldTask *__restrict__ tasks, const double *__restrict__ G, const double *__restrict__ Ppix,
-       double *__restrict__ R, int pix_per_cta, int PB) {
+k_fold(BasisDev b, const FoldTask *__restrict__ tasks, const int *__restrict__ pixlist, const double *__restrict__ G,
+       const double *__restrict__ Ppix, double *__restrict__ R, int pix_per_cta, int PB) {
   constexpr int NP = NT * 8, LD = NP + 4, NAB = NCH * NCH, NPH = NP / 2, NTH = NT / 2;
   extern __shared__ double sm[];
   const FoldTask t = tasks[blockIdx.y];
@@ -186,8 +175,10 @@ k_fold(BasisDev b, const FoldTask *__restrict__ tasks, const double *__restrict_
   double *sY = sP + 2 * PB * NP * LD;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
   const int64_t gstride = (int64_t)NP * NP;
-  const int pix0 = blockIdx.x * pix_per_cta;
-  const int pix1 = min(pix0 + pix_per_cta, b.Npix);
+  const int pix0 = blockIdx.x * pix_per_cta;   // positions in the task's pixel list
+  const int pix1 = min(pix0 + pix_per_cta, t.npix);
+  if (pix0 >= pix1) return;
+  const int *plist = pixlist + t.pix0;
   const double *Psrc = Ppix + (int64_t)t.spp * b.Npix * gstride;
   double *Rdst = R + (int64_t)t.rslot * NAB * b.Npix * gstride;
   auto prefetch = [&](int pg, int buf) {
@@ -195,7 +186,7 @@ k_fold(BasisDev b, const FoldTask *__restrict__ tasks, const double *__restrict_
     if (npx <= 0) return;
     for (int idx = tid; idx < npx * NP * (NP / 2); idx += blockDim.x) {
       const int s = idx / (NP * (NP / 2)), rem = idx % (NP * (NP / 2)), r = rem / (NP / 2), c2 = rem % (NP / 2);
-      cp_async16(sP + ((buf * PB + s) * NP + r) * LD + 2 * c2, Psrc + (int64_t)(pg + s) * gstride + r * NP + 2 * c2, 16);
+      cp_async16(sP + ((buf * PB + s) * NP + r) * LD + 2 * c2, Psrc + (int64_t)plist[pg + s] * gstride + r * NP + 2 * c2, 16);
     }
   };
   prefetch(pix0, 0);
@@ -221,7 +212,6 @@ k_fold(BasisDev b, const FoldTask *__restrict__ tasks, const double *__restrict_
     // stage 1: Yt_b[k][i] = sum_l Gk_b[k][l] P[i][l]   items: (slot, b, row tile of k)
     for (int item = warp; item < npx * NCH * NT; item += nwarp) {
       const int s = item / (NCH * NT), rem = item % (NCH * NT), bb = rem / NT, rt = rem % NT;
-      if (!fold_pixel_needed(b, t, pg + s)) continue;
       const int k0 = PAR ? (((rt / NTH) ^ Lpar) * NPH) : 0;
       const double *A = sGk + (bb * NP + rt * 8 + lr) * LD + lc + k0;
       const double *B = sP + ((buf * PB + s) * NP + lr) * LD + lc + k0;
@@ -248,7 +238,6 @@ k_fold(BasisDev b, const FoldTask *__restrict__ tasks, const double *__restrict_
     for (int item = warp; item < npx * NAB * NT; item += nwarp) {
       const int s = item / (NAB * NT), rem = item % (NAB * NT), ab = rem / NT, rt = rem % NT;
       const int aa = ab / NCH, bb = ab % NCH;
-      if (!fold_pixel_needed(b, t, pg + s)) continue;
       const int k0 = PAR ? (((rt / NTH) ^ Lpar) * NPH) : 0;
       const double *A = sGj + (aa * NP + rt * 8 + lr) * LD + lc + k0;
       const double *B = sY + ((s * NCH + bb) * NP + lr) * LD + lc + k0;
@@ -261,7 +250,7 @@ k_fold(BasisDev b, const FoldTask *__restrict__ tasks, const double *__restrict_
 #pragma unroll
         for (int n = 0; n < NT; n++) dmma(c[n][0], c[n][1], a, B[n * 8 * LD + kk]);
       }
-      double *out = Rdst + ((int64_t)ab * b.Npix + pg + s) * gstride + (rt * 8 + lr) * NP + 2 * lc;
+      double *out = Rdst + ((int64_t)ab * b.Npix + plist[pg + s]) * gstride + (rt * 8 + lr) * NP + 2 * lc;
 #pragma unroll
       for (int n = 0; n < NT; n++) {
         double2 v;
@@ -287,8 +276,8 @@ k_fold(BasisDev b, const FoldTask *__restrict__ tasks, const double *__restrict_
 // ---------------------------------------------------------------------------
 template <int NT, int NCH>
 __global__ void __launch_bounds__(256)
-k_fold_reg(BasisDev b, const FoldTask *__restrict__ tasks, const double *__restrict__ G, const double *__restrict__ Ppix,
-           double *__restrict__ R, int pix_per_cta) {
+k_fold_reg(BasisDev b, const FoldTask *__restrict__ tasks, const int *__restrict__ pixlist, const double *__restrict__ G,
+           const double *__restrict__ Ppix, double *__restrict__ R, int pix_per_cta) {
   constexpr int NP = NT * 8, LDP = NP + 4, LDK = NP + 4, LDJ = (NP % 16 == 0) ? NP + 8 : NP + 16, NAB = NCH * NCH;
   extern __shared__ double sm[];
   double *sGk = sm, *sGj = sGk + NCH * NP * LDK, *sP = sGj + NCH * NP * LDJ;
@@ -296,17 +285,20 @@ k_fold_reg(BasisDev b, const FoldTask *__restrict__ tasks, const double *__restr
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lr = lane >> 2, lc = lane & 3;
   constexpr int64_t gstride = (int64_t)NP * NP;
-  const int pix0 = blockIdx.x * pix_per_cta;
-  const int pix1 = min(pix0 + pix_per_cta, b.Npix);
+  const int pix0 = blockIdx.x * pix_per_cta;   // positions in the task's pixel list
+  const int pix1 = min(pix0 + pix_per_cta, t.npix);
+  if (pix0 >= pix1) return;
+  const int *plist = pixlist + t.pix0;
   const double *Psrc = Ppix + (int64_t)t.spp * b.Npix * gstride;
   double *Rdst = R + (int64_t)t.rslot * NAB * b.Npix * gstride;
   double *myP = sP + warp * 2 * NP * LDP;
-  auto prefetch = [&](int pix, int buf) {
-    if (pix < pix1) {
+  auto prefetch = [&](int pos, int buf) {
+    if (pos < pix1) {
+      const int64_t pix = plist[pos];
 #pragma unroll
       for (int idx = lane; idx < NP * (NP / 2); idx += 32) {
         const int r = idx / (NP / 2), c2 = idx % (NP / 2);
-        cp_async16(myP + (buf * NP + r) * LDP + 2 * c2, Psrc + (int64_t)pix * gstride + r * NP + 2 * c2, 16);
+        cp_async16(myP + (buf * NP + r) * LDP + 2 * c2, Psrc + pix * gstride + r * NP + 2 * c2, 16);
       }
     }
   };
@@ -323,13 +315,13 @@ k_fold_reg(BasisDev b, const FoldTask *__restrict__ tasks, const double *__restr
   }
   __syncthreads();
   int buf = 0;
-  for (int pix = pix0 + warp; pix < pix1; pix += 8, buf ^= 1) {
+  for (int pos = pix0 + warp; pos < pix1; pos += 8, buf ^= 1) {
     __syncwarp();   // every lane is done reading the buffer the next prefetch overwrites
-    prefetch(pix + 8, buf ^ 1);
+    prefetch(pos + 8, buf ^ 1);
     cp_async_commit();
     cp_async_wait<1>();
     __syncwarp();
-    if (!fold_pixel_needed(b, t, pix)) continue;   // mirrored by the unpack, or built by another rank
+    const int pix = plist[pos];
     const double *P = myP + buf * NP * LDP + lr * LDP + lc;
     // ---- stage 1
     double c1[NCH][NT][NT][2];
@@ -810,19 +802,174 @@ __device__ __forceinline__ void tgemm_ws_ksteps(double (&acc)[8][4][2], const do
   }
 }
 
-template <int NCJ>
-__device__ __forceinline__ void tgemm_ws_rows(double (&acc)[8][4][2], const double *__restrict__ as,
-                                              const double *__restrict__ bs, int nrt, int lr) {
-  switch (nrt) {
-    case 8: tgemm_ws_ksteps<NCJ, 8>(acc, as, bs, lr); break;
-    case 7: tgemm_ws_ksteps<NCJ, 7>(acc, as, bs, lr); break;
-    case 6: tgemm_ws_ksteps<NCJ, 6>(acc, as, bs, lr); break;
-    case 5: tgemm_ws_ksteps<NCJ, 5>(acc, as, bs, lr); break;
-    case 4: tgemm_ws_ksteps<NCJ, 4>(acc, as, bs, lr); break;
-    case 3: tgemm_ws_ksteps<NCJ, 3>(acc, as, bs, lr); break;
-    case 2: tgemm_ws_ksteps<NCJ, 2>(acc, as, bs, lr); break;
-    case 1: tgemm_ws_ksteps<NCJ, 1>(acc, as, bs, lr); break;
-    default: break;
+// Balanced variant for warps that own all 4 column tiles of their column group.  The row tiles of the item are
+// dealt to the 4 row groups in full rounds (NF tiles per warp: rg, rg + 4, ..); the REM = (row tiles mod 4)
+// left-over row tiles are cut by COLUMN tile instead: left-over tile e goes to the warp whose local column e it
+// meets, and a warp's local column j is the actual column tile (j + rg) & 3 -- so every warp runs exactly
+// NF*4 + REM DMMAs per k-step (M = 120: 15 instead of 16/16/16/12; the four scheduler partitions stay level).
+// bsj[j] = B fragment base of local column j; ax = A fragment base of the first left-over row tile.
+template <int NF, int REM>
+__device__ __forceinline__ void tgemm_ws_ksteps_bal(double (&acc)[8][4][2], double (&ex)[4][2],
+                                                    const double *__restrict__ as, const double *__restrict__ ax,
+                                                    const double *__restrict__ bs, const int (&bcol)[4], int lr) {
+  constexpr int BK = TP_BK, LDB_S = 68, NE = REM > 0 ? REM : 1, NFF = NF > 0 ? NF : 1;
+  double bf[2][4], af[2][NFF], ae[2][NE];
+#pragma unroll
+  for (int j = 0; j < 4; j++) bf[0][j] = bs[bcol[j]];
+#pragma unroll
+  for (int i = 0; i < NF; i++) af[0][i] = as[i * 32 * BK + 4 * lr];
+#pragma unroll
+  for (int e = 0; e < REM; e++) ae[0][e] = ax[e * 8 * BK + 4 * lr];
+#pragma unroll
+  for (int ks = 0; ks < BK / 4; ks++) {
+    const int cur = ks & 1, nxt = cur ^ 1;
+    if (ks + 1 < BK / 4) {
+      const int ko = 4 * ((ks + 1) ^ lr);
+#pragma unroll
+      for (int j = 0; j < 4; j++) bf[nxt][j] = bs[(ks + 1) * 4 * LDB_S + bcol[j]];
+#pragma unroll
+      for (int i = 0; i < NF; i++) af[nxt][i] = as[i * 32 * BK + ko];
+#pragma unroll
+      for (int e = 0; e < REM; e++) ae[nxt][e] = ax[e * 8 * BK + ko];
+    }
+#pragma unroll
+    for (int i = 0; i < NF; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) dmma(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
+#pragma unroll
+    for (int e = 0; e < REM; e++) dmma(ex[e][0], ex[e][1], ae[cur][e], bf[cur][e]);
+  }
+}
+
+// The consumer loop of one warp, specialised at compile time on its tile counts (the dispatch happens once per CTA,
+// outside the stage loop, so that every variant keeps its accumulators in registers).
+//   BAL:  the warp owns 4 column tiles: NF full row tiles + REM left-over units (tgemm_ws_ksteps_bal)
+//   !BAL: the warp owns 2 column tiles (REM unused): NF row tiles rg, rg + 4, ..; NF = 0, !BAL also serves idle warps
+struct TgemmWarp {
+  const double *As, *Bs;     // stage 0 of the ring
+  uint64_t *full, *empty;
+  int NS, A_STAGE, B_STAGE, nsteps;
+  int lr, lc, cg, rg, lane;
+  int nrt_tot, ncj;
+};
+
+template <int NF, int REM, bool BAL>
+__device__ __forceinline__ void tgemm_ws_consume(const TgemmWarp &w, const GemmItem &it, int bn) {
+  constexpr int BK = TP_BK, LDB_S = 68, NFF = NF > 0 ? NF : 1;
+  double acc[NFF][4][2], ex[4][2];
+#pragma unroll
+  for (int i = 0; i < NFF; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll
+  for (int j = 0; j < 4; j++) ex[j][0] = ex[j][1] = 0.0;
+  int bcol[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) bcol[j] = BAL ? ((j + w.rg) & 3) * 8 : j * 8;
+  const int xrow = (w.nrt_tot & ~3) * 8 + w.lr;   // first left-over row tile
+  int stage = 0, phase = 0;
+  for (int step = 0; step < w.nsteps; step++) {
+    mbar_wait(w.full + stage, phase);
+    if (NF > 0 || REM > 0) {
+      // A fragment of k-step ks sits at row*BK + lc + 4*(ks ^ lr)   (tperm_index swizzle)
+      const double *as = w.As + (size_t)stage * w.A_STAGE + (w.rg * 8 + w.lr) * BK + w.lc;
+      const double *bs = w.Bs + stage * w.B_STAGE + w.lc * LDB_S + w.cg * 32 + w.lr;
+      if (BAL) {
+        const double *ax = w.As + (size_t)stage * w.A_STAGE + xrow * BK + w.lc;
+        double bf[2][4], af[2][NFF], ae[2][REM > 0 ? REM : 1];
+#pragma unroll
+        for (int j = 0; j < 4; j++) bf[0][j] = bs[bcol[j]];
+#pragma unroll
+        for (int i = 0; i < NF; i++) af[0][i] = as[i * 32 * BK + 4 * w.lr];
+#pragma unroll
+        for (int e = 0; e < REM; e++) ae[0][e] = ax[e * 8 * BK + 4 * w.lr];
+#pragma unroll
+        for (int ks = 0; ks < BK / 4; ks++) {
+          const int cur = ks & 1, nxt = cur ^ 1;
+          if (ks + 1 < BK / 4) {
+            const int ko = 4 * ((ks + 1) ^ w.lr);
+#pragma unroll
+            for (int j = 0; j < 4; j++) bf[nxt][j] = bs[(ks + 1) * 4 * LDB_S + bcol[j]];
+#pragma unroll
+            for (int i = 0; i < NF; i++) af[nxt][i] = as[i * 32 * BK + ko];
+#pragma unroll
+            for (int e = 0; e < REM; e++) ae[nxt][e] = ax[e * 8 * BK + ko];
+          }
+#pragma unroll
+          for (int i = 0; i < NF; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) dmma(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
+#pragma unroll
+          for (int e = 0; e < REM; e++) dmma(ex[e][0], ex[e][1], ae[cur][e], bf[cur][e]);
+        }
+      } else {
+        double bf[2][2], af[2][NFF];
+#pragma unroll
+        for (int j = 0; j < 2; j++) bf[0][j] = bs[j * 8];
+#pragma unroll
+        for (int i = 0; i < NF; i++) af[0][i] = as[i * 32 * BK + 4 * w.lr];
+#pragma unroll
+        for (int ks = 0; ks < BK / 4; ks++) {
+          const int cur = ks & 1, nxt = cur ^ 1;
+          if (ks + 1 < BK / 4) {
+            const int ko = 4 * ((ks + 1) ^ w.lr);
+#pragma unroll
+            for (int j = 0; j < 2; j++) bf[nxt][j] = bs[(ks + 1) * 4 * LDB_S + j * 8];
+#pragma unroll
+            for (int i = 0; i < NF; i++) af[nxt][i] = as[i * 32 * BK + ko];
+          }
+#pragma unroll
+          for (int i = 0; i < NF; i++)
+#pragma unroll
+            for (int j = 0; j < 2; j++) dmma(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
+        }
+      }
+    }
+    __syncwarp();
+    if (w.lane == 0) mbar_arrive(w.empty + stage);
+    if (++stage == w.NS) {
+      stage = 0;
+      phase ^= 1;
+    }
+  }
+  auto store = [&](int m, int col, double v0, double v1) {
+    double *c = it.C + (int64_t)m * it.ldc + bn + w.cg * 32 + col + 2 * w.lc;
+    double2 v;
+    v.x = it.alpha * v0;
+    v.y = it.alpha * v1;
+    if (it.accumulate) {
+      const double2 o = *reinterpret_cast<const double2 *>(c);
+      v.x += o.x;
+      v.y += o.y;
+    }
+    *reinterpret_cast<double2 *>(c) = v;
+  };
+#pragma unroll
+  for (int i = 0; i < NF; i++) {
+    const int m = (w.rg + 4 * i) * 8 + w.lr;
+    if (m >= it.M) continue;
+#pragma unroll
+    for (int j = 0; j < (BAL ? 4 : 2); j++) store(m, bcol[j], acc[i][j][0], acc[i][j][1]);
+  }
+#pragma unroll
+  for (int e = 0; e < REM; e++) {
+    const int m = xrow - w.lr + e * 8 + w.lr;
+    if (m < it.M) store(m, bcol[e], ex[e][0], ex[e][1]);
+  }
+}
+
+template <int REM, bool BAL>
+__device__ __forceinline__ void tgemm_ws_dispatch_nf(const TgemmWarp &w, const GemmItem &it, int bn, int nf) {
+  switch (nf) {
+    case 8: tgemm_ws_consume<8, REM, BAL>(w, it, bn); break;
+    case 7: tgemm_ws_consume<7, REM, BAL>(w, it, bn); break;
+    case 6: tgemm_ws_consume<6, REM, BAL>(w, it, bn); break;
+    case 5: tgemm_ws_consume<5, REM, BAL>(w, it, bn); break;
+    case 4: tgemm_ws_consume<4, REM, BAL>(w, it, bn); break;
+    case 3: tgemm_ws_consume<3, REM, BAL>(w, it, bn); break;
+    case 2: tgemm_ws_consume<2, REM, BAL>(w, it, bn); break;
+    case 1: tgemm_ws_consume<1, REM, BAL>(w, it, bn); break;
+    default: tgemm_ws_consume<0, REM, BAL>(w, it, bn); break;
   }
 }
 
@@ -886,58 +1033,40 @@ k_tgemm_ws(const GemmItem *__restrict__ items, const GemmEntry *__restrict__ ent
   }
 
   // ---- consumers ----
-  // Work split: warp w owns column tiles 4*(w/4) .. +3 (8 columns each) and every 4th row tile
-  // starting at r0.  No DMMA is issued for row tiles past M or for column tiles past N.  The two
-  // warps that share a scheduler partition (w and w+4) start at row tiles that differ by 2, so with
-  // 29 row tiles (M = 225) the partitions carry 60/56/60/56 of the 232 units.
-  const int lr = lane >> 2, lc = lane & 3;
-  const int cg = warp >> 2;
-  const int r0 = (warp + 2 * cg) & 3;
-  const int nrt = (((it.M + 7) >> 3) - r0 + 3) >> 2;   // row tiles of this warp
-  const int ncj = min(4, ((it.N - bn) >> 3) - 4 * cg);   // column tiles of this warp (<= 0: idle)
-  double acc[TG_MT][4][2];
-#pragma unroll
-  for (int i = 0; i < TG_MT; i++)
-#pragma unroll
-    for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-  int stage = 0, phase = 0;
-  for (int step = 0; step < nsteps; step++) {
-    mbar_wait(full + stage, phase);
-    if (ncj > 0) {
-      // A fragment of k-step ks sits at row*BK + lc + 4*(ks ^ lr)   (tperm_index swizzle)
-      const double *as = As + (size_t)stage * A_STAGE + (r0 * 8 + lr) * BK + lc;
-      const double *bs = Bs + stage * B_STAGE + lc * LDB_S + cg * 32 + lr;
-      if (ncj > 2)
-        tgemm_ws_rows<4>(acc, as, bs, nrt, lr);
-      else
-        tgemm_ws_rows<2>(acc, as, bs, nrt, lr);
+  // Work split: warp w owns the column tiles 4*(w/4) .. +3 (8 columns each) and the row group rg = w & 3.  No
+  // DMMA is issued for row tiles past M or for column tiles past N.  Warps with all 4 column tiles (the usual
+  // case) take the balanced split (tgemm_ws_consume<.., BAL = true>): the row tiles are dealt in full rounds and
+  // the (row tiles mod 4) left-over tiles are cut by column tile, so that every warp issues the same number of
+  // DMMAs per k-step (M = 120: 15 each instead of 16/16/16/12).  A warp with 2 column tiles (last tile of a sector
+  // pair whose column count is not a multiple of 64) takes every 4th row tile; one with none only keeps the ring going.
+  TgemmWarp w;
+  w.As = As;
+  w.Bs = Bs;
+  w.full = full;
+  w.empty = empty;
+  w.NS = NS;
+  w.A_STAGE = A_STAGE;
+  w.B_STAGE = B_STAGE;
+  w.nsteps = nsteps;
+  w.lane = lane;
+  w.lr = lane >> 2;
+  w.lc = lane & 3;
+  w.cg = warp >> 2;
+  w.rg = warp & 3;
+  w.nrt_tot = (it.M + 7) >> 3;
+  w.ncj = min(4, ((it.N - bn) >> 3) - 4 * w.cg);   // column tiles of this warp (<= 0: idle)
+  if (w.ncj == 4) {
+    const int nf = w.nrt_tot >> 2;
+    switch (w.nrt_tot & 3) {
+      case 3: tgemm_ws_dispatch_nf<3, true>(w, it, bn, nf); break;
+      case 2: tgemm_ws_dispatch_nf<2, true>(w, it, bn, nf); break;
+      case 1: tgemm_ws_dispatch_nf<1, true>(w, it, bn, nf); break;
+      default: tgemm_ws_dispatch_nf<0, true>(w, it, bn, nf); break;
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(empty + stage);
-    if (++stage == NS) {
-      stage = 0;
-      phase ^= 1;
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < TG_MT; i++) {
-    const int m = (r0 + 4 * i) * 8 + lr;
-    if (m >= it.M) continue;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      if (j >= ncj) break;
-      double *c = it.C + (int64_t)m * it.ldc + bn + cg * 32 + j * 8 + 2 * lc;
-      double2 v;
-      v.x = it.alpha * acc[i][j][0];
-      v.y = it.alpha * acc[i][j][1];
-      if (it.accumulate) {
-        const double2 o = *reinterpret_cast<const double2 *>(c);
-        v.x += o.x;
-        v.y += o.y;
-      }
-      *reinterpret_cast<double2 *>(c) = v;
-    }
+  } else if (w.ncj > 0) {
+    tgemm_ws_dispatch_nf<0, false>(w, it, bn, (w.nrt_tot - w.rg + 3) >> 2);
+  } else {
+    tgemm_ws_consume<0, 0, false>(w, it, bn);
   }
 }
 

@@ -39,6 +39,10 @@ typedef struct hfq_ctx hfq_ctx;
 #define HFQ_LAPL 4
 
 const char *hfq_last_error(void);
+/* OpenMP threads used by the host-side setup (compute_tei, coupling tables) and the host zero-fill / copies of the
+ * host-pointer calls.  Launchers such as torchrun export OMP_NUM_THREADS=1; a rank calls this with its share of
+ * the cores (the reference's setup loops are OpenMP too: src/diatomic/basis.cpp:1410-1454). */
+int hfq_set_host_threads(int n);
 
 /* ---- basis construction + compute_tei() ------------------------------------------------- */
 
