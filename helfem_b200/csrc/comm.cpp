@@ -79,8 +79,8 @@ void Comm::all_gather_inplace(double *buf, size_t count, cudaStream_t st) {
 void Comm::all_reduce_sum(double *buf, size_t count, cudaStream_t st) {
   check(api().AllReduce(buf, buf, count, ncclDouble, ncclSum, reinterpret_cast<ncclComm_t>(comm_), st), "ncclAllReduce");
 }
-void Comm::all_reduce_max_int(int *buf, size_t count, cudaStream_t st) {
-  check(api().AllReduce(buf, buf, count, ncclInt32, ncclMax, reinterpret_cast<ncclComm_t>(comm_), st), "ncclAllReduce");
+void Comm::all_reduce_max_u64(unsigned long long *buf, size_t count, cudaStream_t st) {
+  check(api().AllReduce(buf, buf, count, ncclUint64, ncclMax, reinterpret_cast<ncclComm_t>(comm_), st), "ncclAllReduce");
 }
 void Comm::broadcast(void *buf, size_t bytes, int root, cudaStream_t st) {
   check(api().Broadcast(buf, buf, bytes, ncclUint8, root, reinterpret_cast<ncclComm_t>(comm_), st), "ncclBroadcast");

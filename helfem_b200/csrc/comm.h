@@ -24,7 +24,7 @@ class Comm {
   // in place: every rank contributes buf[rank*count .. +count) and receives all nranks*count doubles
   void all_gather_inplace(double *buf, size_t count, cudaStream_t st);
   void all_reduce_sum(double *buf, size_t count, cudaStream_t st);
-  void all_reduce_max_int(int *buf, size_t count, cudaStream_t st);
+  void all_reduce_max_u64(unsigned long long *buf, size_t count, cudaStream_t st);
   void broadcast(void *buf, size_t bytes, int root, cudaStream_t st);
 
  private:

@@ -108,9 +108,12 @@ struct Engine::Impl {
   size_t r_slots = 0;                // capacity of the R buffer in task slots
   // density packed by pack_density(): shared by coulomb and exchange in a fused build
   std::vector<double> norms_host;
-  int *flags_host = nullptr;         // page-locked: per sector pair, bit 0 = not exactly zero, bit 1 = norm not below 10 eps
+  unsigned long long *flags_host = nullptr;   // page-locked: per sector pair, bit 0 = not exactly zero, bit 1 = norm not
+                                              // below 10 eps; then the bits of max |P - P^T| and of max |P|
   bool want_norms_host = false;      // host-pointer calls: the per-block norms are read back too (upload prediction)
-  DevBuf<int> d_spflags;
+  DevBuf<unsigned long long> d_spflags;
+  cudaStream_t aux_stream = nullptr;   // clears the output matrix while the exchange kernels run
+  cudaEvent_t ev_start = nullptr, ev_kzero = nullptr;
   DevBuf<double> d_Kc;               // compact exchange result: [rank segment][unit][rows][NB]
   std::vector<int> packed_splist;
   bool packed_valid = false;
@@ -475,7 +478,7 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
     s.d_jfac.upload(jfac, &dev_bytes_);
   }
   // ---- work buffers that do not depend on the density
-  s.d_norms.alloc((size_t)na * na + 2, &dev_bytes_);
+  s.d_norms.alloc((size_t)na * na, &dev_bytes_);
   s.d_Ppix.alloc((size_t)s.ns * s.ns * s.Npix * s.NB, &dev_bytes_);
   s.d_splist.alloc((size_t)s.ns * s.ns, &dev_bytes_);
   s.d_sp_active.alloc((size_t)s.ns * s.ns, &dev_bytes_);
@@ -588,28 +591,35 @@ void Engine::pack_density(const double *dP, int64_t ldP, cudaStream_t st) {
   const int na = t.Nang(), ns = s.ns;
   const size_t nn = (size_t)na * na;
   const size_t nflag = (size_t)ns * ns;
-  if (s.norms_host.size() != nn + 2) {
+  if (s.norms_host.size() != nn) {
     // page-locked once: the per-call read-back is then a plain DMA instead of a staged pageable copy
     if (!s.norms_host.empty()) cudaHostUnregister(s.norms_host.data());
-    s.norms_host.assign(nn + 2, 0.0);
+    s.norms_host.assign(nn, 0.0);
     if (cudaHostRegister(s.norms_host.data(), s.norms_host.size() * sizeof(double), cudaHostRegisterDefault) != cudaSuccess)
       cudaGetLastError();   // stays pageable: slower, still correct
-    if (!s.flags_host) CK(cudaMallocHost(&s.flags_host, (nflag + 4) * sizeof(int)));
-    s.d_spflags.alloc(nflag, &dev_bytes_);
+    if (!s.flags_host) CK(cudaMallocHost(&s.flags_host, (nflag + 2) * sizeof(unsigned long long)));
+    s.d_spflags.alloc(nflag + 2, &dev_bytes_);
   }
-  CK(cudaMemsetAsync(s.d_norms.p + nn, 0, 2 * sizeof(double), st));
-  CK(cudaMemsetAsync(s.d_spflags.p, 0, nflag * sizeof(int), st));
-  dev::k_block_norms<<<dim3(na, (na + 3) / 4), 128, 0, st>>>(s.bd, dP, ldP, s.d_ang_sec.p, s.d_norms.p, s.d_spflags.p);
-  CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(s.flags_host, s.d_spflags.p, nflag * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemsetAsync(s.d_spflags.p, 0, (nflag + 2) * sizeof(unsigned long long), st));
+  // multi-GPU: every rank scans 1/nranks of the columns, one all-reduce(max) of the flags completes them (the
+  // per-block norms themselves are only needed by the host-pointer calls: scanned in full there)
+  const bool split = comm_ && !s.want_norms_host;
+  const int c0 = split ? comm_->rank() : 0, cs = split ? comm_->size() : 1;
+  if (c0 < na) {
+    dev::k_block_norms<<<dim3((na - c0 + cs - 1) / cs, (na + 3) / 4), 128, 0, st>>>(s.bd, dP, ldP, s.d_ang_sec.p, s.d_norms.p,
+                                                                                   s.d_spflags.p, c0, cs);
+    CK(cudaGetLastError());
+  }
+  if (split) comm_->all_reduce_max_u64(s.d_spflags.p, nflag + 2, st);
+  CK(cudaMemcpyAsync(s.flags_host, s.d_spflags.p, (nflag + 2) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   if (s.want_norms_host)
-    CK(cudaMemcpyAsync(s.norms_host.data(), s.d_norms.p, s.norms_host.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
-  else
-    CK(cudaMemcpyAsync(s.norms_host.data() + nn, s.d_norms.p + nn, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(s.norms_host.data(), s.d_norms.p, nn * sizeof(double), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   {
     // symmetric density (every SCF density is): the exchange builds half of each diagonal output pair
-    const double asym = s.norms_host[nn], amax = s.norms_host[nn + 1];
+    double asym, amax;
+    std::memcpy(&asym, &s.flags_host[nflag], sizeof(double));
+    std::memcpy(&amax, &s.flags_host[nflag + 1], sizeof(double));
     static const bool allow = !(getenv("HFQ_NO_SYMMETRY") && atoi(getenv("HFQ_NO_SYMMETRY")));
     s.p_symmetric = allow && asym <= 1e-14 * amax;
   }
@@ -756,6 +766,17 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
   tm_ = EngineTimings();
   if (!plans_) plans_.reset(new PlanCache);
   CK(cudaEventRecord(s.ev[0], st));
+  // everything outside the computed sector pairs is exactly zero: K is cleared at memset speed on a second stream
+  // while the (tensor-pipe-bound) exchange kernels run; the unpack then writes the blocks that can be non-zero
+  if (!s.aux_stream) {
+    CK(cudaStreamCreateWithFlags(&s.aux_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&s.ev_start, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&s.ev_kzero, cudaEventDisableTiming));
+  }
+  CK(cudaEventRecord(s.ev_start, st));   // earlier work on st that still reads K must finish first
+  CK(cudaStreamWaitEvent(s.aux_stream, s.ev_start, 0));
+  CK(cudaMemset2DAsync(dK, (size_t)ldK * sizeof(double), 0, (size_t)nbf_ * sizeof(double), (size_t)nbf_, s.aux_stream));
+  CK(cudaEventRecord(s.ev_kzero, s.aux_stream));
   // 1. which sector pairs of P carry density (reference: block norm >= 10 eps)
   if (!s.packed_valid) pack_density(dP, ldP, st);
   std::string key((size_t)ns * ns + 3, '0');
@@ -1198,9 +1219,7 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
     tm_.launches++;
   }
   if (comm_ && plan->seg > 0) comm_->all_gather_inplace(s.d_Kc.p, (size_t)plan->seg, st);
-  // everything outside the computed sector pairs is exactly zero: clear K at memset speed, then unpack
-  // only the angular blocks that can be non-zero
-  CK(cudaMemset2DAsync(dK, (size_t)ldK * sizeof(double), 0, (size_t)nbf_ * sizeof(double), (size_t)nbf_, st));
+  CK(cudaStreamWaitEvent(st, s.ev_kzero, 0));
   if (plan->nblocks) {
     dev::UnpackDev u{plan->d_op_src.p, plan->d_op_tri.p, plan->d_blocks.p, plan->d_unit_off.p, s.d_ang_sec.p, s.d_ang_pos.p,
                      s.kscale};
@@ -1235,9 +1254,9 @@ Engine::~Engine() {
   plans_.reset();
   if (p_) {
     for (auto &e : p_->ev) cudaEventDestroy(e);
-    for (cudaEvent_t e : {p_->ev_packed, p_->ev_jdone, p_->ev_up, p_->ev_j, p_->ev_jcopied})
+    for (cudaEvent_t e : {p_->ev_packed, p_->ev_jdone, p_->ev_up, p_->ev_j, p_->ev_jcopied, p_->ev_start, p_->ev_kzero})
       if (e) cudaEventDestroy(e);
-    for (cudaStream_t st : {p_->copy_stream, p_->up_stream, p_->j_stream})
+    for (cudaStream_t st : {p_->copy_stream, p_->up_stream, p_->j_stream, p_->aux_stream})
       if (st) cudaStreamDestroy(st);
     if (!p_->norms_host.empty()) cudaHostUnregister(p_->norms_host.data());
     if (p_->flags_host) cudaFreeHost(p_->flags_host);

@@ -38,16 +38,19 @@ struct BasisDev {
 // Block norms of P (the reference's screening quantity, src/diatomic/basis.cpp:1855-1864) and the symmetry test,
 // one pass over the matrix.  One WARP per unordered pair of angular functions (a <= c): it reads block (a, c) and
 // block (c, a) once each, both coalesced (the mirrored tile goes through a warp-private shared-memory tile), and
-// produces out[a*Nang+c], out[c*Nang+a] (sums of squares), max |P(i,j) - P(j,i)| -> out[Nang^2], max |P(i,j)| ->
-// out[Nang^2 + 1] (zeroed by the caller), and the sector-pair flags the plan needs: flags[sp] |= 1 if the block is
-// not exactly zero (it must be packed), |= 2 if its norm is not below 10 eps (the reference's skip test, negated so
-// that NaN blocks are kept).  grid (Nang, ceil(Nang / 4)), 128 threads.
+// produces out[a*Nang+c], out[c*Nang+a] (sums of squares) and, in flags[] (zeroed by the caller), the sector-pair
+// flags the plan needs: flags[sp] |= 1 if the block is not exactly zero (it must be packed), |= 2 if its norm is not
+// below 10 eps (the reference's skip test, negated so that NaN blocks are kept); flags[ns^2] = bits of
+// max |P(i,j) - P(j,i)|, flags[ns^2 + 1] = bits of max |P(i,j)| (non-negative doubles order like their bit
+// patterns).  Every entry is combined with OR / MAX, which coincide on {0, 1, 3}: a multi-GPU build lets each rank
+// scan the columns c = c0, c0 + cstride, .. and completes the flags with one all-reduce(max).
+// grid (number of columns of this rank, ceil(Nang / 4)), 128 threads.
 static __global__ void __launch_bounds__(128)
 k_block_norms(BasisDev b, const double *__restrict__ P, int64_t ld, const int *__restrict__ ang_sec,
-              double *__restrict__ out, int *__restrict__ flags) {
+              double *__restrict__ out, unsigned long long *__restrict__ flags, int c0, int cstride) {
   __shared__ double tiles[4][32][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c = blockIdx.x, a = blockIdx.y * 4 + warp;
+  const int c = c0 + blockIdx.x * cstride, a = blockIdx.y * 4 + warp;
   if (a > c || a >= b.Nang) return;
   double(*tm)[33] = tiles[warp];
   const int sa = b.ang_skip[a], sc = b.ang_skip[c];
@@ -86,19 +89,17 @@ k_block_norms(BasisDev b, const double *__restrict__ P, int64_t ld, const int *_
     m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
   }
   if (lane == 0) {
-    const int64_t nn = (int64_t)b.Nang * b.Nang;
     const double thr2 = 100.0 * 2.220446049250313e-16 * 2.220446049250313e-16;
     out[a * b.Nang + c] = s1;
-    int f = (!(s1 == 0.0) ? 1 : 0) | (!(s1 < thr2) ? 2 : 0);
+    unsigned long long f = (!(s1 == 0.0) ? 1ull : 0ull) | (!(s1 < thr2) ? 3ull : 0ull);
     if (f) atomicOr(flags + ang_sec[a] * b.ns + ang_sec[c], f);
     if (a != c) {
       out[c * b.Nang + a] = s2;
-      f = (!(s2 == 0.0) ? 1 : 0) | (!(s2 < thr2) ? 2 : 0);
+      f = (!(s2 == 0.0) ? 1ull : 0ull) | (!(s2 < thr2) ? 3ull : 0ull);
       if (f) atomicOr(flags + ang_sec[c] * b.ns + ang_sec[a], f);
     }
-    // non-negative doubles order like their bit patterns: global maxima through integer atomicMax
-    unsigned long long *mx = reinterpret_cast<unsigned long long *>(out + nn);
-    if (d > 0.0) atomicMax(mx, (unsigned long long)__double_as_longlong(d));
+    unsigned long long *mx = flags + b.ns * b.ns;
+    if (!(d == 0.0)) atomicMax(mx, (unsigned long long)__double_as_longlong(d != d ? 1e300 : d));   // NaN: not symmetric
     atomicMax(mx + 1, (unsigned long long)__double_as_longlong(m));
   }
 }
@@ -843,8 +844,9 @@ __device__ __forceinline__ void tgemm_ws_ksteps_bal(double (&acc)[8][4][2], doub
 
 // The consumer loop of one warp, specialised at compile time on its tile counts (the dispatch happens once per CTA,
 // outside the stage loop, so that every variant keeps its accumulators in registers).
-//   BAL:  the warp owns 4 column tiles: NF full row tiles + REM left-over units (tgemm_ws_ksteps_bal)
-//   !BAL: the warp owns 2 column tiles (REM unused): NF row tiles rg, rg + 4, ..; NF = 0, !BAL also serves idle warps
+//   BAL:  the warp owns 4 column tiles: NF full row tiles + REM left-over units
+//   !BAL: the warp owns w.ncj < 4 column tiles and computes NCJ = 2 or 4 of them (columns past w.ncj are padding and
+//         are not stored; REM unused): NF row tiles rg, rg + 4, ..; NF = 0 also serves idle warps
 struct TgemmWarp {
   const double *As, *Bs;     // stage 0 of the ring
   uint64_t *full, *empty;
@@ -853,7 +855,7 @@ struct TgemmWarp {
   int nrt_tot, ncj;
 };
 
-template <int NF, int REM, bool BAL>
+template <int NF, int REM, bool BAL, int NCJ = 4>
 __device__ __forceinline__ void tgemm_ws_consume(const TgemmWarp &w, const GemmItem &it, int bn) {
   constexpr int BK = TP_BK, LDB_S = 68, NFF = NF > 0 ? NF : 1;
   double acc[NFF][4][2], ex[4][2];
@@ -903,9 +905,9 @@ __device__ __forceinline__ void tgemm_ws_consume(const TgemmWarp &w, const GemmI
           for (int e = 0; e < REM; e++) dmma(ex[e][0], ex[e][1], ae[cur][e], bf[cur][e]);
         }
       } else {
-        double bf[2][2], af[2][NFF];
+        double bf[2][NCJ], af[2][NFF];
 #pragma unroll
-        for (int j = 0; j < 2; j++) bf[0][j] = bs[j * 8];
+        for (int j = 0; j < NCJ; j++) bf[0][j] = bs[j * 8];
 #pragma unroll
         for (int i = 0; i < NF; i++) af[0][i] = as[i * 32 * BK + 4 * w.lr];
 #pragma unroll
@@ -914,14 +916,14 @@ __device__ __forceinline__ void tgemm_ws_consume(const TgemmWarp &w, const GemmI
           if (ks + 1 < BK / 4) {
             const int ko = 4 * ((ks + 1) ^ w.lr);
 #pragma unroll
-            for (int j = 0; j < 2; j++) bf[nxt][j] = bs[(ks + 1) * 4 * LDB_S + j * 8];
+            for (int j = 0; j < NCJ; j++) bf[nxt][j] = bs[(ks + 1) * 4 * LDB_S + j * 8];
 #pragma unroll
             for (int i = 0; i < NF; i++) af[nxt][i] = as[i * 32 * BK + ko];
           }
 #pragma unroll
           for (int i = 0; i < NF; i++)
 #pragma unroll
-            for (int j = 0; j < 2; j++) dmma(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
+            for (int j = 0; j < NCJ; j++) dmma(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
         }
       }
     }
@@ -949,7 +951,8 @@ __device__ __forceinline__ void tgemm_ws_consume(const TgemmWarp &w, const GemmI
     const int m = (w.rg + 4 * i) * 8 + w.lr;
     if (m >= it.M) continue;
 #pragma unroll
-    for (int j = 0; j < (BAL ? 4 : 2); j++) store(m, bcol[j], acc[i][j][0], acc[i][j][1]);
+    for (int j = 0; j < NCJ; j++)
+      if (BAL || j < w.ncj) store(m, bcol[j], acc[i][j][0], acc[i][j][1]);
   }
 #pragma unroll
   for (int e = 0; e < REM; e++) {
@@ -958,18 +961,18 @@ __device__ __forceinline__ void tgemm_ws_consume(const TgemmWarp &w, const GemmI
   }
 }
 
-template <int REM, bool BAL>
+template <int REM, bool BAL, int NCJ = 4>
 __device__ __forceinline__ void tgemm_ws_dispatch_nf(const TgemmWarp &w, const GemmItem &it, int bn, int nf) {
   switch (nf) {
-    case 8: tgemm_ws_consume<8, REM, BAL>(w, it, bn); break;
-    case 7: tgemm_ws_consume<7, REM, BAL>(w, it, bn); break;
-    case 6: tgemm_ws_consume<6, REM, BAL>(w, it, bn); break;
-    case 5: tgemm_ws_consume<5, REM, BAL>(w, it, bn); break;
-    case 4: tgemm_ws_consume<4, REM, BAL>(w, it, bn); break;
-    case 3: tgemm_ws_consume<3, REM, BAL>(w, it, bn); break;
-    case 2: tgemm_ws_consume<2, REM, BAL>(w, it, bn); break;
-    case 1: tgemm_ws_consume<1, REM, BAL>(w, it, bn); break;
-    default: tgemm_ws_consume<0, REM, BAL>(w, it, bn); break;
+    case 8: tgemm_ws_consume<8, REM, BAL, NCJ>(w, it, bn); break;
+    case 7: tgemm_ws_consume<7, REM, BAL, NCJ>(w, it, bn); break;
+    case 6: tgemm_ws_consume<6, REM, BAL, NCJ>(w, it, bn); break;
+    case 5: tgemm_ws_consume<5, REM, BAL, NCJ>(w, it, bn); break;
+    case 4: tgemm_ws_consume<4, REM, BAL, NCJ>(w, it, bn); break;
+    case 3: tgemm_ws_consume<3, REM, BAL, NCJ>(w, it, bn); break;
+    case 2: tgemm_ws_consume<2, REM, BAL, NCJ>(w, it, bn); break;
+    case 1: tgemm_ws_consume<1, REM, BAL, NCJ>(w, it, bn); break;
+    default: tgemm_ws_consume<0, REM, BAL, NCJ>(w, it, bn); break;
   }
 }
 
@@ -1063,8 +1066,10 @@ k_tgemm_ws(const GemmItem *__restrict__ items, const GemmEntry *__restrict__ ent
       case 1: tgemm_ws_dispatch_nf<1, true>(w, it, bn, nf); break;
       default: tgemm_ws_dispatch_nf<0, true>(w, it, bn, nf); break;
     }
+  } else if (w.ncj > 2) {
+    tgemm_ws_dispatch_nf<0, false, 4>(w, it, bn, (w.nrt_tot - w.rg + 3) >> 2);
   } else if (w.ncj > 0) {
-    tgemm_ws_dispatch_nf<0, false>(w, it, bn, (w.nrt_tot - w.rg + 3) >> 2);
+    tgemm_ws_dispatch_nf<0, false, 2>(w, it, bn, (w.nrt_tot - w.rg + 3) >> 2);
   } else {
     tgemm_ws_consume<0, 0, false>(w, it, bn);
   }
