@@ -1,16 +1,19 @@
 #!/usr/bin/env python
-"""bench.py -- J+K Fock builds per second for N2 HF in prolate spheroidal coordinates.
+"""bench.py -- J/K/Vxc Fock builds per second for N2 HF in prolate spheroidal coordinates.
 
 Workload (BASELINE.json metric, configs[3]): N2, Rbond 2.07, lmax=30 for |m|<=6, 3 radial
 elements x 15-node LIP (src/diatomic/main.cpp defaults, tests/cases.json diatomic-N2-hf-r
 scaled to the north-star lmax/mmax), closed-shell density with the N2 occupation pattern
-(5 sigma + pi+- doubly occupied; seeded synthetic orbitals).  One step = one Fock build:
-J = coulomb(P), K = exchange(P/2).  HF has no Vxc.
+(5 sigma + pi+- doubly occupied; seeded synthetic orbitals).  One step = one Fock build as the
+reference's fock_builder issues it (src/diatomic/main.cpp:385-426): XC = pmgrid.eval_Fxc(P) -- for
+HF (x_func = -1) the density on the pure-m grid and its integral Nel, zero XC matrix --,
+J = coulomb(P), K = exchange(P/2).
 
   python bench.py --gpus N --steps K --warmup W            our CUDA path
   python bench.py --impl reference ...                     the reference algorithm on host cores
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -127,6 +130,26 @@ def cpu_sample_text(parts):
                parts["j_stride"], parts["j_stride"]))
 
 
+def cpu_vxc_seconds(bval, lval, mval, P, lang, elements=None):
+    """The HF build's eval_Fxc on the reference's pure-m grid (src/diatomic/dftgrid_purem.cpp:87-442, 675-700:
+    materialised basis tables per element + density GEMMs; numpy/BLAS restatement oracle/dftgrid_purem.py) --
+    seconds for all elements, extrapolated from `elements` if given; also returns Nel."""
+    from oracle import diatomic as odi
+    from oracle import dftgrid_purem as dp
+    ob = odi.TwoDBasis(7, 7, 1.035, 15, 75, np.asarray(bval), np.asarray(lval), np.asarray(mval))   # grid tables only, no TEIs
+    og = dp.PureMDFTGrid(ob, lang)
+    Pd = ob.expand_boundaries(P)
+    nel_tot = ob.radial.Nel()
+    els = list(range(nel_tot)) if elements is None else list(elements)
+    t0 = time.perf_counter()
+    nel = 0.0
+    for iel in els:
+        og.compute_bf(iel)
+        d = og.density(Pd, False, False, False)
+        nel += float(np.sum(og.wtot * d["rho"]))
+    return (time.perf_counter() - t0) * nel_tot / len(els), nel
+
+
 def parity_of_blocks(C, sel, blk, Kdense, Jdense=None, P=None):
     """Relative Frobenius error of the GPU K on the CPU-sampled output blocks (and of J against the complete
     single-M Coulomb build of the oracle)."""
@@ -151,6 +174,31 @@ def parity_of_blocks(C, sel, blk, Kdense, Jdense=None, P=None):
     return out
 
 
+def make_density(kind, T):
+    if kind == "n2":
+        return n2_density(T), "synthetic closed-shell N2 structure (3 sigma_g + 2 sigma_u + pi_u+-, g/u-symmetric orbitals), seed 42"
+    rng = np.random.default_rng(42)
+    n = T.Nbf
+    P = np.zeros((n, n), order="F")
+    off = 0
+    blocks = {}
+    for m in T.mval:
+        k = T.Nrad - (1 if m != 0 else 0)
+        blocks.setdefault(int(m), []).extend(range(off, off + k))
+        off += k
+    for m, idx in blocks.items():
+        idx = np.array(idx)
+        if kind == "dense":   # dense random m-block-diagonal density (worst case of the screening)
+            Q, _ = np.linalg.qr(rng.standard_normal((len(idx), 3)))
+            P[np.ix_(idx, idx)] = 2.0 * Q @ Q.T
+        else:                 # non-symmetric: general exchange path (no half storage)
+            A = rng.standard_normal((len(idx), 3))
+            B = rng.standard_normal((len(idx), 3))
+            P[np.ix_(idx, idx)] = A @ B.T
+    return P, {"dense": "dense random symmetric m-block-diagonal density, every (m, parity) sector pair of equal m active, seed 42",
+               "nonsym": "non-symmetric random m-block-diagonal density (general exchange path), seed 42"}[kind]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -163,6 +211,8 @@ def main():
     ap.add_argument("--cpu-blocks-per-thread", type=int, default=16,
                     help="exchange output blocks per host thread in the CPU sample (>= 4: no idle threads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--density", default="n2", choices=["n2", "dense", "nonsym"],
+                    help="n2 = the headline density; dense / nonsym = secondary figures (no CPU leg)")
     ap.add_argument("--profile-mode", action="store_true",
                     help="for runs under ncu only: device-resident steps, no e2e/peak/CPU legs, prints no bench line")
     args = ap.parse_args()
@@ -172,16 +222,17 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    lang = 4 * args.lmax + 12   # pure-m grid of the reference driver (src/diatomic/main.cpp:316)
 
-    import helfem_b200 as hb
-    from helfem_b200 import build as hb_build
-    workload = "N2 HF diatomic J+K Fock build, Rbond=2.07, lmax=%d |m|<=%d, nelem=%d x 15-node LIP" % (args.lmax, args.mmax, args.nelem)
-    config = {"workload": workload, "density": "synthetic closed-shell N2 structure (3 sigma_g + 2 sigma_u + pi_u+-, g/u-symmetric orbitals), seed 42",
+    metric = "J/K/Vxc Fock builds/s (N2 HF)"
+    workload = "N2 HF diatomic Fock build (eval_Fxc on the pure-m grid [HF: density + Nel] + coulomb + exchange), Rbond=2.07, " \
+               "lmax=%d |m|<=%d, nelem=%d x 15-node LIP, grid %d nu x %d mu" % (args.lmax, args.mmax, args.nelem, lang, 75 * args.nelem)
+    config = {"workload": workload, "density": None,
               "symmetry": "per-m (reference default --symmetry=1, absm_symmetric off)",
               "l2": "inputs larger than L2 (P/J/K 1.76 GB each, work buffers > 10 GB)",
               "sharding": "owner computes: exchange units (output sector pair, radial element pair) dealt longest-first to the least "
-                          "loaded rank; ONE in-place ncclAllGather of the compact result issued by the library (hfq_comm_init); J "
-                          "replicated"}
+                          "loaded rank; ONE in-place ncclAllGather of the compact result issued by the library (hfq_comm_init); J and "
+                          "the grid density replicated"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -196,26 +247,34 @@ def main():
             subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "export_caches.py"), npz, "7", "7", "2.07",
                                    str(args.lmax), str(args.mmax), str(args.nelem)])
         C = cjk.DiatomicCaches.from_npz(npz)
-        P = n2_density(_BasisShape(C.Nrad, C.lval, C.mval))
+        bval = np.load(npz)["bval"]
+        shape = _BasisShape(C.Nrad, C.lval, C.mval)
+        P = n2_density(shape)
+        config["density"] = "synthetic closed-shell N2 structure (3 sigma_g + 2 sigma_u + pi_u+-, g/u-symmetric orbitals), seed 42"
         # every step = one bounded sample of the build, sized so that 25 steps end within a few minutes
         times, parts = [], None
         for it in range(args.warmup + args.steps):
             tB, parts, _ = cpu_reference_build(C, P, 0.5, blocks_per_thread=8, jstride=16)
+            tX, _ = cpu_vxc_seconds(bval, C.lval, C.mval, P, lang, elements=[args.nelem // 2])
+            parts["vxc_build_s"] = tX
             if it >= args.warmup:
-                times.append(tB)
+                times.append(tB + tX)
         tB = float(np.median(times)) if times else float("nan")
         val = 1.0 / tB
-        line = {"metric": "J+K Fock builds/s (N2 HF)", "value": val, "unit": "builds/s", "n_gpus": args.gpus,
+        line = {"metric": metric, "value": val, "unit": "builds/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tB, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
                 "config": config,
                 "cpu_baseline": {"value": val, "unit": "builds/s", "cores": parts["threads"], "kind": "port",
-                                 "sample": cpu_sample_text(parts), "parts": parts,
+                                 "sample": cpu_sample_text(parts) + "; Vxc (HF: grid density + Nel) = 1 of %d elements x %d, numpy/BLAS"
+                                           % (args.nelem, args.nelem), "parts": parts,
                                  "inputs": "integral caches written by tools/export_caches.py in a subprocess"},
                 "e2e": {"value": val, "unit": "builds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
 
+    import helfem_b200 as hb
+    from helfem_b200 import build as hb_build
     import torch
     import torch.distributed as dist
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
@@ -230,50 +289,66 @@ def main():
     t_setup = time.time() - t0
     basis = hb.TablesBasis(T, device=local)
     n = T.Nbf
-    P = n2_density(T)
+    P, config["density"] = make_density(args.density, T)
     t0 = time.time()
     basis._context()
     t_upload = time.time() - t0
     if world > 1:
         basis.comm_init()   # NCCL communicator inside the library; torch.distributed only hands the id around
+    hb.DFTGrid(basis, lang)
+    nel_ref = float(np.sum(P * T.one_electron()[0]))
 
     # device-resident inputs/outputs (column-major n x n == transposed row-major torch tensors)
     dP = torch.from_numpy(np.ascontiguousarray(P.T)).cuda()
-    dPh = (0.5 * dP).contiguous()
     dJ = torch.empty_like(dP)
     dK = torch.empty_like(dP)
-    hP = torch.from_numpy(np.ascontiguousarray(P.T)).pin_memory()
-    hPh = (0.5 * hP).pin_memory()
-    hJ = torch.empty((n, n), dtype=torch.float64).pin_memory()
-    hK = torch.empty((n, n), dtype=torch.float64).pin_memory()
     stream = torch.cuda.current_stream().cuda_stream
+
+    # host matrices of the end-to-end leg: one set, visible to every rank (multi-GPU: POSIX shared memory), page-locked
+    def shared_host(name, fill=None):
+        if world == 1:
+            t = torch.empty((n, n), dtype=torch.float64).pin_memory()
+        else:
+            path = "/dev/shm/hfq_bench_%s_%s" % (os.environ.get("MASTER_PORT", "0"), name)
+            if rank == 0:
+                torch.from_file(path, shared=True, size=n * n, dtype=torch.float64)   # creates the segment
+            dist.barrier()
+            t = torch.from_file(path, shared=True, size=n * n, dtype=torch.float64).view(n, n)
+            assert torch.cuda.cudart().cudaHostRegister(t.data_ptr(), n * n * 8, 0) in (0, None, torch.cuda.cudart().cudaError.success)
+        if fill is not None and rank == 0:
+            t.copy_(fill)
+        return t
+
+    hP = shared_host("P", torch.from_numpy(np.ascontiguousarray(P.T)))
+    hJ = shared_host("J")
+    hK = shared_host("K")
+    if world > 1:
+        dist.barrier()
 
     acc = {"ms_fold": 0.0, "ms_tgemm": 0.0, "ms_offdiag": 0.0, "alg_fold": 0.0, "alg_tgemm": 0.0, "alg_offdiag": 0.0,
            "launches": 0.0, "launches_tgemm": 0.0, "flops_tgemm": 0.0, "n": 0}
-    e2e_sep = None
-
-    car = {}
 
     def step_device(collect=False):
-        # one Fock build: J = coulomb(P), K = exchange(P/2) from one packed copy of P
-        # (with a communicator the build is sharded and completed by the library: results are whole on every rank)
-        basis.coulomb_exchange_device(dP.data_ptr(), dJ.data_ptr(), dK.data_ptr(), 0.5, 0, 1, stream)
+        # one Fock build: XC (HF: grid density + Nel), J = coulomb(P), K = exchange(P/2); with a communicator the
+        # exchange is sharded and completed by the library: results are whole on every rank
+        exc, nel = basis.fock_build_device(dP.data_ptr(), dJ.data_ptr(), dK.data_ptr(), 0.5, -1, 0, None, 1e-12, stream)
+        assert abs(nel - nel_ref) < 1e-9 * abs(nel_ref), (nel, nel_ref)
         if collect:
             tm = basis.last_timings()
             for k in acc:
                 if k in tm:
                     acc[k] += tm[k]
+            acc["launches"] += 4   # grid chain: pack, two GEMM stages, point kernel
             acc["n"] += 1
 
-    def step_host():
-        # the fock_builder's J = coulomb(P); K = exchange(P/2) through the fused host entry point
-        hb._check(hb.lib().hfq_coulomb_exchange(basis._context(), hP.data_ptr(), n, 0.5, hJ.data_ptr(), n, hK.data_ptr(), n))
+    nel_h, exc_h = ctypes.c_double(), ctypes.c_double()
 
-    def step_host_separate():
-        lib = hb.lib()
-        ctx = basis._context()
-        hb._check(lib.hfq_coulomb(ctx, hP.data_ptr(), n, hJ.data_ptr(), n))
-        hb._check(lib.hfq_exchange(ctx, hPh.data_ptr(), n, hK.data_ptr(), n))
+    def step_host():
+        # the fock_builder's three calls through the fused host entry point (host matrices in and out)
+        hb._check(hb.lib().hfq_fock_build(basis._context(), hP.data_ptr(), n, 0.5, hJ.data_ptr(), n, hK.data_ptr(), n, -1, 0,
+                                          None, n, ctypes.byref(exc_h), ctypes.byref(nel_h), 1e-12))
+        if world > 1:
+            dist.barrier()   # the shared matrices are complete when every rank has returned
 
     def barrier():
         torch.cuda.synchronize()
@@ -305,54 +380,36 @@ def main():
     if args.profile_mode:
         print("profile-mode: %.2f ms/step (not a bench value)" % ms_step)
         return
-    # ---- end-to-end through the host-pointer C ABI (pinned host buffers, copies inside)
-    e2e_val = None
-    h2d_bytes, d2h_bytes, spec_hits = n * n * 8, 2 * n * n * 8, None
-    if world == 1:
+    # ---- end-to-end through the host-pointer C ABI (page-locked host matrices, copies inside the timed region)
+    if rank == 0:
         hJ.fill_(float("nan"))   # the call must define every element (copied blocks + host zero-fill)
         hK.fill_(float("nan"))
+    barrier()
+    step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
         step_host()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            step_host()
-        torch.cuda.synchronize()
-        e2e_val = args.steps / (time.perf_counter() - t0)
-        tm = basis.last_timings()
-        h2d_bytes, d2h_bytes = int(tm["h2d_bytes"]), int(tm["d2h_bytes"])
-        spec_hits = int(tm["speculative_hits"])
+    torch.cuda.synchronize()
+    tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    e2e_val = args.steps / float(tt.item())
+    tm = basis.last_timings()
+    hd = torch.tensor([tm["h2d_bytes"], tm["d2h_bytes"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(hd)   # bytes moved by all ranks
+    h2d_bytes, d2h_bytes = int(hd[0].item()), int(hd[1].item())
+    spec_hits = int(tm["speculative_hits"]) if world == 1 else None
+    if rank == 0:
         ek = float((hK.cuda() - dK).abs().max() / dK.abs().max())
         ej = float((hJ.cuda() - dJ).abs().max() / dJ.abs().max())
         assert ek < 1e-12 and ej < 1e-12, "host and device paths disagree: %g %g" % (ek, ej)
-        step_host_separate()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            step_host_separate()
-        torch.cuda.synchronize()
-        e2e_sep = args.steps / (time.perf_counter() - t0)
-    else:
-        # multi-GPU e2e: rank 0 owns the host buffers; broadcast P, build, reduce K, copy back
-        def step_host_multi():
-            if rank == 0:
-                dP.copy_(hP, non_blocking=True)
-            dist.broadcast(dP, 0)
-            step_device()
-            if rank == 0:
-                hJ.copy_(dJ, non_blocking=True)
-                hK.copy_(dK, non_blocking=True)
-            torch.cuda.synchronize()
-        step_host_multi()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            step_host_multi()
-        barrier()
-        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_val = args.steps / float(tt.item())
+        assert abs(nel_h.value - nel_ref) < 1e-9 * abs(nel_ref)
 
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
 
@@ -376,14 +433,17 @@ def main():
     nst = max(acc["n"], 1)
     nl = max(acc["launches_tgemm"], 1)
     ach = acc["alg_tgemm"] / (acc["ms_tgemm"] * 1e-3) / 1e12 if acc["ms_tgemm"] > 0 else 0.0
-    # DRAM traffic of the dominant kernel is a profiler number, not measurable here: the value of the last
-    # committed ncu --set full capture of this workload (1 GPU, symmetric density) is reported with its source
-    traffic = 26.72e9 if (world == 1 and args.lmax == 30 and args.mmax == 6 and args.nelem == 3) else None
+    # DRAM traffic of the dominant kernel is a profiler number, not measurable here: it is read from the committed
+    # per-state file written from the last ncu --set full capture of this workload (1 GPU, headline density)
+    traffic, traffic_note = None, None
+    tf = os.path.join(ROOT, "profiles", "current_traffic.json")
+    if os.path.exists(tf) and world == 1 and args.density == "n2" and (args.lmax, args.mmax, args.nelem) == (30, 6, 3):
+        tj = json.load(open(tf))
+        traffic, traffic_note = tj.get("k_tgemm_ws_dram_bytes_per_launch"), tj.get("note")
     roofline = {"bound": "tensor", "kernel": "k_tgemm_ws (in-element exchange, FP64 DMMA)", "achieved": ach, "peak": fp64_peak,
-                "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": traffic,
-                "traffic_note": "bytes per launch, dram__bytes_read.sum + dram__bytes_write.sum of profiles/r01f_ncu_full_summary.txt "
-                                "(26.65 GB read: R rows of the in-element pixels + the kernel tiles streamed once per item; 0.07 GB written)",
-                "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": traffic, "traffic_note": traffic_note,
+                "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry; the DMMA "
+                               "microbenchmark of profiles/r01_fp64_peak_microbench.txt reads 37.1)",
                 "alg_flops_per_launch": acc["alg_tgemm"] / nl, "ms_per_launch": acc["ms_tgemm"] / nl,
                 "executed_tflops": acc["flops_tgemm"] / (acc["ms_tgemm"] * 1e-3) / 1e12 if acc["ms_tgemm"] > 0 else 0.0,
                 "step_share": {"fold_ms": acc["ms_fold"] / nst, "gemm_ms": acc["ms_tgemm"] / nst,
@@ -391,43 +451,49 @@ def main():
                 "alg_tflops_all_kernels": (acc["alg_fold"] + acc["alg_tgemm"] + acc["alg_offdiag"]) / nst / (ms_step * 1e-3) / 1e12}
 
     cpu_baseline, parity = None, None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and args.density == "n2":
         from oracle import cjk
         C = cjk.DiatomicCaches.from_tables(T)
         tB, parts, (sel, blk) = cpu_reference_build(C, P, 0.5, blocks_per_thread=args.cpu_blocks_per_thread, jstride=8)
-        # the sample is also the parity check of THIS run's result at full size: the GPU K on the sampled blocks and
-        # the complete J against the oracle (1e-12, BASELINE.json north_star)
+        tX, nel_cpu = cpu_vxc_seconds(T.bval, T.lval, T.mval, P, lang)
+        parts["vxc_build_s"] = tX
+        # the sample is also the parity check of THIS run's result at full size: the GPU K on the sampled blocks, the
+        # complete J and the grid integral Nel against the oracle (1e-12, BASELINE.json north_star)
         Kh = dK.cpu().numpy().T
         Jh = dJ.cpu().numpy().T
         parity = parity_of_blocks(C, sel, blk, Kh, Jh, P)
+        parity["relerr_Nel"] = abs(nel_h.value - nel_cpu) / abs(nel_cpu)
         parity["tolerance"] = 1e-12
-        assert parity["max_relerr_K"] < 1e-12 and parity["max_relerr_J"] < 1e-12, "GPU result differs from the oracle: %s" % parity
+        assert parity["max_relerr_K"] < 1e-12 and parity["max_relerr_J"] < 1e-12 and parity["relerr_Nel"] < 1e-12, \
+            "GPU result differs from the oracle: %s" % parity
         # one-thread figure (the reference's own test setting, tests/cases.json defaults.env OMP_NUM_THREADS=1)
         tB1, parts1, _ = cpu_reference_build(C, P, 0.5, blocks_per_thread=48, jstride=16, threads=1)
-        cpu_baseline = {"value": 1.0 / tB, "unit": "builds/s", "cores": parts["threads"], "kind": "port",
-                        "sample": cpu_sample_text(parts), "parts": parts,
-                        "one_thread_value": 1.0 / tB1, "one_thread_parts": parts1}
+        cpu_baseline = {"value": 1.0 / (tB + tX), "unit": "builds/s", "cores": parts["threads"], "kind": "port",
+                        "sample": cpu_sample_text(parts) + "; Vxc (HF: grid density + Nel) in full, numpy/BLAS restatement of "
+                                  "src/diatomic/dftgrid_purem.cpp", "parts": parts,
+                        "one_thread_value": 1.0 / (tB1 + tX), "one_thread_parts": parts1}
 
-    nbytes = n * n * 8
-    line = {"metric": "J+K Fock builds/s (N2 HF)", "value": value, "unit": "builds/s", "n_gpus": world, "steps": args.steps,
+    line = {"metric": metric, "value": value, "unit": "builds/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "e2e": {"value": e2e_val, "unit": "builds/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                    "call": "hfq_coulomb_exchange, dense pinned host matrices in and out. P: the row ranges that were non-zero in "
-                            "the previous call are uploaded first and the build starts on them while the complete matrix "
-                            "follows on another stream and is compared bit-for-bit on the device (mismatch = rebuild from "
-                            "the full upload; speculative_hits counts the calls that did not need it). J, K: only the row "
-                            "ranges of the non-zero blocks cross PCIe, the rest of the host matrices is zero-filled by host "
-                            "threads while the GPU computes" if world == 1 else
-                            "rank 0 host buffers -> broadcast P -> sharded build -> all-reduce -> copy back",
-                    "speculative_hits": spec_hits,
-                    "separate_calls_value": e2e_sep if world == 1 else None,
-                    "separate_calls_note": "hfq_coulomb + hfq_exchange issued separately (2 uploads, no overlap)"},
+                    "call": ("hfq_fock_build, dense page-locked host matrices in and out. P: the row ranges that were non-zero in "
+                             "the previous call are uploaded first and the build starts on them while the complete matrix "
+                             "follows on another stream and is compared bit-for-bit on the device (mismatch = rebuild from "
+                             "the full upload; speculative_hits counts the calls that did not need it). J, K: only the row "
+                             "ranges of the non-zero blocks cross PCIe, the rest of the host matrices is zero-filled by host "
+                             "threads while the GPU computes") if world == 1 else
+                            ("hfq_fock_build with a communicator: ONE set of host matrices in POSIX shared memory, page-locked by "
+                             "every rank; each rank uploads its 1/N column slice of P over its own PCIe link, one in-place "
+                             "ncclAllGather over NVLink completes P on every GPU, sharded build, each rank copies back the non-zero "
+                             "row ranges of its column slice of J and K and zero-fills the rest; host barrier at the end"),
+                    "speculative_hits": spec_hits},
             "gpu_launches": int(acc["launches"]), "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,
             "clocks": sampler.summary(),
             "setup": {"host_compute_tei_s": t_setup, "device_upload_s": t_upload, "Nbf": n, "channels": T.nlm}}
     print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

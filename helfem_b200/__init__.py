@@ -41,7 +41,7 @@ EXPORTED_SYMBOLS = [
     "hfq_tables_destroy", "hfq_create", "hfq_destroy", "hfq_nbf", "hfq_set_absm_symmetric", "hfq_coulomb",
     "hfq_exchange", "hfq_coulomb_device", "hfq_exchange_device", "hfq_last_timings", "hfq_exchange_output_pattern",
     "hfq_coulomb_output_pattern",
-    "hfq_set_host_threads", "hfq_comm_unique_id", "hfq_comm_init", "hfq_comm_size", "hfq_shard_assign",
+    "hfq_set_host_threads", "hfq_fock_build", "hfq_fock_build_device", "hfq_comm_unique_id", "hfq_comm_init", "hfq_comm_size", "hfq_shard_assign",
     "hfq_coulomb_exchange", "hfq_coulomb_exchange_device", "hfq_grid_attach", "hfq_grid_npoints", "hfq_grid_density", "hfq_grid_fxc", "hfq_eval_fxc",
 ]
 
@@ -93,6 +93,8 @@ def lib():
     L.hfq_coulomb_exchange.argtypes = [vp, vp, i64, cd, vp, i64, vp, i64]
     L.hfq_coulomb_exchange_device.argtypes = [vp, vp, i64, cd, vp, i64, vp, i64, ci, ci, vp]
     L.hfq_set_host_threads.argtypes = [ci]
+    L.hfq_fock_build.argtypes = [vp, vp, i64, cd, vp, i64, vp, i64, ci, ci, vp, i64, vp, vp, cd]
+    L.hfq_fock_build_device.argtypes = [vp, vp, i64, cd, vp, i64, vp, i64, ci, ci, vp, i64, vp, vp, cd, vp]
     L.hfq_comm_unique_id.argtypes = [vp]
     L.hfq_comm_init.argtypes = [vp, vp, ci, ci]
     L.hfq_comm_size.argtypes = [vp]
@@ -344,6 +346,15 @@ class _BasisBase:
         n = self.Nbf()
         _check(lib().hfq_coulomb_exchange_device(self._context(), dP_ptr, n, kscale, dJ_ptr, n, dK_ptr, n, shard, nshards,
                                                  stream))
+
+    def fock_build_device(self, dP_ptr, dJ_ptr, dK_ptr, kscale=0.5, x_func=-1, c_func=0, dH_ptr=None, thr=1e-12, stream=None):
+        """XC + J + K of one restricted Fock build, device-resident (hfq_fock_build_device); returns (Exc, Nel).
+        A DFT grid must be attached (DFTGrid(basis, ...))."""
+        n = self.Nbf()
+        exc, nel = ctypes.c_double(), ctypes.c_double()
+        _check(lib().hfq_fock_build_device(self._context(), dP_ptr, n, kscale, dJ_ptr, n, dK_ptr, n, x_func, c_func, dH_ptr, n,
+                                           ctypes.byref(exc), ctypes.byref(nel), thr, stream))
+        return exc.value, nel.value
 
     # -- device-resident variants (torch CUDA tensors, column-major = transposed view) ---------
     def coulomb_device(self, dP_ptr, dJ_ptr, stream=None):

@@ -519,29 +519,6 @@ int hfq_grid_fxc(hfq_ctx *ctx, int flags, int beta, const double *exc, const dou
   });
 }
 
-// Slater exchange, libxc id 1 (XC_LDA_X): e_x per particle and v_x; spin-scaling relation for the polarised case.
-static void lda_x(int64_t N, int nspin, const double *rho, double thr, double *exc, double *vrho) {
-  const double pi = std::acos(-1.0);
-  const double cx = -0.75 * std::cbrt(3.0 / pi);
-  for (int64_t p = 0; p < N; p++) {
-    if (nspin == 1) {
-      const double n = rho[p];
-      if (n < thr) { exc[p] = 0.0; vrho[p] = 0.0; continue; }
-      const double n13 = std::cbrt(n);
-      exc[p] = cx * n13;
-      vrho[p] = 4.0 / 3.0 * cx * n13;
-    } else {
-      const double na = rho[2 * p], nb = rho[2 * p + 1], n = na + nb;
-      if (n < thr) { exc[p] = 0.0; vrho[2 * p] = vrho[2 * p + 1] = 0.0; continue; }
-      // E_x[na,nb] = (E_x[2na] + E_x[2nb]) / 2
-      const double ea = na > 0 ? cx * std::cbrt(2.0 * na) * na : 0.0, eb = nb > 0 ? cx * std::cbrt(2.0 * nb) * nb : 0.0;
-      exc[p] = (ea + eb) / n;
-      vrho[2 * p] = na > 0 ? 4.0 / 3.0 * cx * std::cbrt(2.0 * na) : 0.0;
-      vrho[2 * p + 1] = nb > 0 ? 4.0 / 3.0 * cx * std::cbrt(2.0 * nb) : 0.0;
-    }
-  }
-}
-
 int hfq_eval_fxc(hfq_ctx *ctx, int x_func, int c_func, const double *Pa, int64_t ldPa, const double *Pb, int64_t ldPb,
                  double *Ha, int64_t ldHa, double *Hb, int64_t ldHb, double *Exc, double *Nel, double *Ekin, int beta,
                  double thr) {
@@ -558,13 +535,65 @@ int hfq_eval_fxc(hfq_ctx *ctx, int x_func, int c_func, const double *Pa, int64_t
                 "between hfq_grid_density and hfq_grid_fxc");
   std::lock_guard<std::mutex> lk(ctx->mu);
   return guarded([&] {
-    const int64_t N = ctx->grid->npoints();
-    const int nspin = Pb ? 2 : 1;
-    std::vector<double> rho((size_t)N * nspin), exc((size_t)N, 0.0), vrho((size_t)N * nspin, 0.0);
-    ctx->grid->density(Pa, ldPa, Pb, ldPb, 0, rho.data(), nullptr, nullptr, nullptr, nullptr, Nel, Ekin);
+    // densities, functional and assembly stay on the device; P and H may be host or device matrices
+    ctx->grid->density_launch(Pa, ldPa, Pb, ldPb, 0);
+    ctx->grid->density_collect(nullptr, nullptr, nullptr, nullptr, nullptr, Nel, Ekin);
     if (Ekin) *Ekin = 0.0;   // tau is not evaluated for an LDA (src/general/dftgrid_common.cpp compute_Ekin)
-    if (x_func == 1) lda_x(N, nspin, rho.data(), thr, exc.data(), vrho.data());
-    ctx->grid->fxc(0, beta != 0, exc.data(), vrho.data(), nullptr, nullptr, nullptr, Ha, ldHa, Hb, ldHb, Exc);
+    ctx->grid->fxc_builtin(x_func, thr, beta != 0, Ha, ldHa, Hb, ldHb, Exc);
+    return HFQ_OK;
+  });
+}
+
+int hfq_fock_build(hfq_ctx *ctx, const double *P, int64_t ldP, double kscale, double *J, int64_t ldJ, double *K, int64_t ldK,
+                   int x_func, int c_func, double *Hxc, int64_t ldH, double *Exc, double *Nel, double thr) {
+  if (!ctx || !P || !J || !K) return fail(HFQ_ERR_INVALID, "hfq_fock_build: null argument");
+  if (!ctx->grid) return fail(HFQ_ERR_STATE, "hfq_fock_build: no grid attached");
+  const int64_t n = ctx->eng->Nbf();
+  if (ldP < n || ldJ < n || ldK < n || (Hxc && ldH < n)) return fail(HFQ_ERR_INVALID, "hfq_fock_build: leading dimension smaller than Nbf");
+  if (c_func > 0 || (x_func > 0 && x_func != 1))
+    return fail(HFQ_ERR_INVALID, "hfq_fock_build: only x_func <= 0 (HF) and the Slater exchange (libxc id 1) are built in");
+  if (x_func > 0 && !Hxc) return fail(HFQ_ERR_INVALID, "hfq_fock_build: Hxc needed for a density functional");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  return guarded([&] {
+    // J, K through the host-pointer path (one upload of P, copies overlapped with the build); with a communicator
+    // the matrices are shared by all ranks and every rank moves its column slice.  The grid then works on the
+    // device copy of P that this call left behind: nothing crosses PCIe a second time.
+    if (ctx->eng->comm_size() > 1)
+      ctx->eng->jk_spmd_host(P, ldP, kscale, J, ldJ, K, ldK);
+    else
+      ctx->eng->coulomb_exchange(P, ldP, kscale, J, ldJ, K, ldK);
+    const hfq::EngineTimings tm = ctx->eng->timings();
+    double ekin = 0.0;
+    ctx->grid->density_launch(ctx->eng->device_density(), n, nullptr, 0, 0);
+    ctx->grid->density_collect(nullptr, nullptr, nullptr, nullptr, nullptr, Nel, &ekin);
+    ctx->grid->fxc_builtin(x_func, thr, true, Hxc, ldH, nullptr, 0, Exc);
+    (void)tm;
+    return HFQ_OK;
+  });
+}
+
+int hfq_fock_build_device(hfq_ctx *ctx, const double *dP, int64_t ldP, double kscale, double *dJ, int64_t ldJ, double *dK,
+                          int64_t ldK, int x_func, int c_func, double *dHxc, int64_t ldH, double *Exc, double *Nel,
+                          double thr, void *stream) {
+  if (!ctx || !dP || !dJ || !dK) return fail(HFQ_ERR_INVALID, "hfq_fock_build_device: null argument");
+  if (!ctx->grid) return fail(HFQ_ERR_STATE, "hfq_fock_build_device: no grid attached");
+  const int64_t n = ctx->eng->Nbf();
+  if (ldP < n || ldJ < n || ldK < n || (dHxc && ldH < n))
+    return fail(HFQ_ERR_INVALID, "hfq_fock_build_device: leading dimension smaller than Nbf");
+  if (c_func > 0 || (x_func > 0 && x_func != 1))
+    return fail(HFQ_ERR_INVALID, "hfq_fock_build_device: only x_func <= 0 (HF) and the Slater exchange (libxc id 1) are built in");
+  if (x_func > 0 && !dHxc) return fail(HFQ_ERR_INVALID, "hfq_fock_build_device: Hxc needed for a density functional");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  return guarded([&] {
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->eng->stream();
+    // the grid density chain (small GEMMs, bandwidth-bound) is queued first on the grid's stream and runs next to
+    // the tensor-pipe-bound J/K kernels
+    ctx->eng->fence_stream(st, ctx->grid->stream());   // P may still be written by earlier work on st
+    ctx->grid->density_launch(dP, ldP, nullptr, 0, 0);
+    ctx->eng->jk_dev(dP, ldP, kscale, dJ, ldJ, dK, ldK, 0, 1, st);
+    double ekin = 0.0;
+    ctx->grid->density_collect(nullptr, nullptr, nullptr, nullptr, nullptr, Nel, &ekin);
+    ctx->grid->fxc_builtin(x_func, thr, true, dHxc, ldH, nullptr, 0, Exc);
     return HFQ_OK;
   });
 }

@@ -113,7 +113,7 @@ struct Engine::Impl {
   bool want_norms_host = false;      // host-pointer calls: the per-block norms are read back too (upload prediction)
   DevBuf<unsigned long long> d_spflags;
   cudaStream_t aux_stream = nullptr;   // clears the output matrix while the exchange kernels run
-  cudaEvent_t ev_start = nullptr, ev_kzero = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_kzero = nullptr, ev_fence = nullptr;
   DevBuf<double> d_Kc;               // compact exchange result: [rank segment][unit][rows][NB]
   std::vector<int> packed_splist;
   bool packed_valid = false;
@@ -1250,11 +1250,19 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
 
 const BasisTables &Engine::tables() const { return p_->t; }
 
+void Engine::fence_stream(cudaStream_t on, cudaStream_t waiter) {
+  if (on == waiter) return;
+  Impl &s = *p_;
+  if (!s.ev_fence) CK(cudaEventCreateWithFlags(&s.ev_fence, cudaEventDisableTiming));
+  CK(cudaEventRecord(s.ev_fence, on));
+  CK(cudaStreamWaitEvent(waiter, s.ev_fence, 0));
+}
+
 Engine::~Engine() {
   plans_.reset();
   if (p_) {
     for (auto &e : p_->ev) cudaEventDestroy(e);
-    for (cudaEvent_t e : {p_->ev_packed, p_->ev_jdone, p_->ev_up, p_->ev_j, p_->ev_jcopied, p_->ev_start, p_->ev_kzero})
+    for (cudaEvent_t e : {p_->ev_packed, p_->ev_jdone, p_->ev_up, p_->ev_j, p_->ev_jcopied, p_->ev_start, p_->ev_kzero, p_->ev_fence})
       if (e) cudaEventDestroy(e);
     for (cudaStream_t st : {p_->copy_stream, p_->up_stream, p_->j_stream, p_->aux_stream})
       if (st) cudaStreamDestroy(st);
@@ -1463,13 +1471,15 @@ Engine::HostRanges Engine::host_ranges(bool coulomb) const {
   return hr;
 }
 
-double Engine::copy_ranges_async(double *H, int64_t ldH, const double *D, const HostRanges &hr, cudaStream_t st) const {
+double Engine::copy_ranges_async(double *H, int64_t ldH, const double *D, const HostRanges &hr, cudaStream_t st, int cb,
+                                 int ce) const {
   const int n = nbf_;
   double bytes = 0.0;
   if ((int)hr.r0.size() != n) return 0.0;
-  for (int c0 = 0; c0 < n;) {
+  if (ce < 0) ce = n;
+  for (int c0 = cb; c0 < ce;) {
     int c1 = c0 + 1;
-    while (c1 < n && hr.r0[c1] == hr.r0[c0] && hr.r1[c1] == hr.r1[c0]) c1++;
+    while (c1 < ce && hr.r0[c1] == hr.r0[c0] && hr.r1[c1] == hr.r1[c0]) c1++;
     const int r0 = hr.r0[c0], r1 = hr.r1[c0];
     bytes += (double)(r1 - r0) * (c1 - c0) * sizeof(double);
     if (r1 > r0)
@@ -1480,11 +1490,12 @@ double Engine::copy_ranges_async(double *H, int64_t ldH, const double *D, const 
   return bytes;
 }
 
-void Engine::zero_outside(double *H, int64_t ldH, int n, const HostRanges &hr) {
+void Engine::zero_outside(double *H, int64_t ldH, int n, const HostRanges &hr, int cb, int ce) {
   const bool none = (int)hr.r0.size() != n;   // no pattern: everything is zero
   const int nthr = std::max(1, omp_get_max_threads() - 2);   // leave cores to the thread that feeds the GPU
+  if (ce < 0) ce = n;
 #pragma omp parallel for schedule(static) num_threads(nthr)
-  for (int c = 0; c < n; c++) {
+  for (int c = cb; c < ce; c++) {
     double *col = H + (int64_t)c * ldH;
     if (none) {
       std::memset(col, 0, (size_t)n * sizeof(double));
@@ -1723,5 +1734,37 @@ bool Engine::fused_host(const double *P, int64_t ldP, double kscale, double *J, 
   s.pred_r1 = pr.r1;
   return true;
 }
+
+// Multi-GPU build with HOST matrices shared by all ranks (one process per GPU; P, J, K in memory every rank can
+// address, e.g. a POSIX shared-memory segment, ideally page-locked by each rank).  Every rank moves 1/nranks of the
+// bytes over ITS OWN PCIe link: it uploads its column slice of P, one in-place ncclAllGather over NVLink completes
+// the density on every GPU, the sharded build runs (jk_dev with the communicator), and every rank copies its column
+// slice of the non-zero row ranges of J and K back and zero-fills the rest of its slice.  The caller synchronises
+// the ranks afterwards (the matrices are complete when every rank has returned).
+void Engine::jk_spmd_host(const double *P, int64_t ldP, double kscale, double *J, int64_t ldJ, double *K, int64_t ldK) {
+  Impl &s = *p_;
+  if (!comm_) throw std::logic_error("hfq_coulomb_exchange_spmd needs a communicator (hfq_comm_init)");
+  CK(cudaSetDevice(device_));
+  const size_t n = (size_t)nbf_;
+  const int N = comm_->size(), r = comm_->rank();
+  const size_t chunk = (n + N - 1) / N;                 // columns per rank
+  const int cb = (int)std::min(n, r * chunk), ce = (int)std::min(n, (r + 1) * chunk);
+  if (s.d_P.n < chunk * N * n) s.d_P.alloc(chunk * N * n, &dev_bytes_);
+  if (s.d_O.n < n * n) s.d_O.alloc(n * n, &dev_bytes_);
+  if (s.d_O2.n < n * n) s.d_O2.alloc(n * n, &dev_bytes_);
+  if (ce > cb)
+    CK(cudaMemcpy2DAsync(s.d_P.p + (size_t)cb * n, n * sizeof(double), P + (int64_t)cb * ldP, ldP * sizeof(double),
+                         n * sizeof(double), (size_t)(ce - cb), cudaMemcpyHostToDevice, stream_));
+  comm_->all_gather_inplace(s.d_P.p, chunk * n, stream_);
+  jk_dev(s.d_P.p, (int64_t)n, kscale, s.d_O2.p, (int64_t)n, s.d_O.p, (int64_t)n, 0, 1, stream_);
+  const HostRanges hrj = host_ranges(true), hrk = host_ranges(false);
+  tm_.h2d_bytes = (double)(ce - cb) * n * sizeof(double);
+  tm_.d2h_bytes = copy_ranges_async(J, ldJ, s.d_O2.p, hrj, stream_, cb, ce) + copy_ranges_async(K, ldK, s.d_O.p, hrk, stream_, cb, ce);
+  zero_outside(J, ldJ, nbf_, hrj, cb, ce);
+  zero_outside(K, ldK, nbf_, hrk, cb, ce);
+  CK(cudaStreamSynchronize(stream_));
+}
+
+const double *Engine::device_density() const { return p_->d_P.p; }
 
 }  // namespace hfq

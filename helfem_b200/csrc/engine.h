@@ -69,12 +69,18 @@ class Engine {
   void coulomb(const double *P, int64_t ldP, double *J, int64_t ldJ);
   void exchange(const double *P, int64_t ldP, double *K, int64_t ldK);
   void coulomb_exchange(const double *P, int64_t ldP, double kscale, double *J, int64_t ldJ, double *K, int64_t ldK);
+  // multi-GPU, host matrices shared by all ranks: every rank moves its column slice (see engine.cu)
+  void jk_spmd_host(const double *P, int64_t ldP, double kscale, double *J, int64_t ldJ, double *K, int64_t ldK);
+  // device copy of the density of the last host-pointer call (Nbf x Nbf, ld = Nbf)
+  const double *device_density() const;
   int speculative_hits() const { return spec_hits_; }   // fused host calls that ran on a predicted sparse upload
 
   // Non-zero structure of the last exchange result: sector id of every dense basis function and
   // the (row sector, column sector) pairs that were written; all other blocks of K are zero.
   void output_pattern(std::vector<int> &bf_sector, std::vector<int> &pairs, bool coulomb = false) const;
 
+  // make `waiter` wait for everything queued on `on` so far
+  void fence_stream(cudaStream_t on, cudaStream_t waiter);
   const EngineTimings &timings() const { return tm_; }
   cudaStream_t stream() const { return stream_; }
   size_t device_bytes() const { return dev_bytes_; }
@@ -90,8 +96,10 @@ class Engine {
     std::vector<int> r0, r1;   // per dense column: rows [r0, r1) are copied, the rest is zero
   };
   HostRanges host_ranges(bool coulomb) const;
-  double copy_ranges_async(double *H, int64_t ldH, const double *D, const HostRanges &hr, cudaStream_t st) const;   // returns bytes
-  static void zero_outside(double *H, int64_t ldH, int n, const HostRanges &hr);
+  // columns [cb, ce) only (ce < 0: all)
+  double copy_ranges_async(double *H, int64_t ldH, const double *D, const HostRanges &hr, cudaStream_t st, int cb = 0,
+                           int ce = -1) const;   // returns bytes
+  static void zero_outside(double *H, int64_t ldH, int n, const HostRanges &hr, int cb = 0, int ce = -1);
   bool fused_host(const double *P, int64_t ldP, double kscale, double *J, int64_t ldJ, double *K, int64_t ldK, bool spec);
   HostRanges density_ranges() const;   // bounding non-zero row range per column of the density packed last
   int spec_hits_ = 0;

@@ -7,6 +7,8 @@
 #include "grid.h"
 
 #include <cmath>
+#include <map>
+#include <memory>
 #include <stdexcept>
 #include <string>
 
@@ -205,6 +207,33 @@ __global__ void k_exc(const double *__restrict__ w, const double *__restrict__ e
   if ((threadIdx.x & 31) == 0) atomicAdd(sum, s);
 }
 
+// Slater exchange, libxc id 1 (XC_LDA_X), on the device: exc per particle and v_rho from the densities of the last
+// density call; spin-scaling relation E_x[na, nb] = (E_x[2 na] + E_x[2 nb]) / 2 for the polarised case; zero below
+// the density threshold (xc_func_set_dens_threshold, src/general/dftgrid_common.cpp:131)
+__global__ void k_lda_x(int64_t N, const double *__restrict__ ra, const double *__restrict__ rb, double thr,
+                        double *__restrict__ exc, double *__restrict__ va, double *__restrict__ vb) {
+  const double cx = -0.75 * cbrt(3.0 / 3.14159265358979323846);
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < N; p += (int64_t)gridDim.x * blockDim.x) {
+    if (!rb) {
+      const double n = ra[p];
+      const bool ok = !(n < thr);
+      const double n13 = ok ? cbrt(n) : 0.0;
+      exc[p] = cx * n13;
+      va[p] = 4.0 / 3.0 * cx * n13;
+    } else {
+      const double na = ra[p], nb = rb[p], n = na + nb;
+      if (n < thr) {
+        exc[p] = va[p] = vb[p] = 0.0;
+        continue;
+      }
+      const double ca = na > 0 ? cbrt(2.0 * na) : 0.0, cb = nb > 0 ? cbrt(2.0 * nb) : 0.0;
+      exc[p] = cx * (ca * na + cb * nb) / n;
+      va[p] = 4.0 / 3.0 * cx * ca;
+      vb[p] = 4.0 / 3.0 * cx * cb;
+    }
+  }
+}
+
 }  // namespace
 
 struct GridEngine::Impl {
@@ -220,6 +249,35 @@ struct GridEngine::Impl {
   Buf<dev::GemmEntry> d_entries;
   bool polarized = false, pure_m = false;
   int dens_flags = 0;
+  // GEMM descriptors of the density stages depend only on (spin, flags): built once, kept on the device, so a
+  // density evaluation is a chain of launches without a host synchronisation
+  struct GemmPlan {
+    Buf<dev::GemmItem> items;
+    Buf<dev::GemmEntry> entries;
+    int n = 0, maxM = 0, maxN = 0;
+  };
+  std::map<int, std::unique_ptr<GemmPlan>> plans;
+  template <typename Build>
+  void gemm_cached(int key, int maxM, int maxN, Build build) {
+    auto it = plans.find(key);
+    if (it == plans.end()) {
+      std::vector<dev::GemmItem> items;
+      std::vector<dev::GemmEntry> entries;
+      build(items, entries);
+      auto pl = std::make_unique<GemmPlan>();
+      pl->items.upload(items);
+      pl->entries.upload(entries);
+      pl->n = (int)items.size();
+      pl->maxM = maxM;
+      pl->maxN = maxN;
+      it = plans.emplace(key, std::move(pl)).first;
+    }
+    GemmPlan &pl = *it->second;
+    if (!pl.n) return;
+    const dim3 grid((pl.maxN + 63) / 64, (pl.maxM + 63) / 64, (unsigned)pl.n);
+    dev::k_gemm<64, 64, 2, 2, false><<<grid, 128, 0, st>>>(pl.items.p, pl.entries.p);
+    CK(cudaGetLastError());
+  }
   // dens layout per spin s: rho [N], grho [3N], tau [N], lapl [N]  -> 6N
   double *dens(int s, int which) { return d_dens.p + ((size_t)s * 6 + which) * N; }
 
@@ -343,11 +401,21 @@ GridEngine::GridEngine(const BasisTables &t, const GridTables &g, int device, cu
 
 GridEngine::~GridEngine() {}
 int64_t GridEngine::npoints() const { return p_->N; }
+cudaStream_t GridEngine::stream() const { return p_->st; }
 bool GridEngine::polarized() const { return p_->polarized; }
 int GridEngine::density_flags() const { return p_->dens_flags; }
 
-void GridEngine::density(const double *Pa, int64_t ldPa, const double *Pb, int64_t ldPb, int flags, double *rho,
-                         double *sigma, double *tau, double *lapl, double *weights, double *Nel, double *Ekin) {
+static bool is_device_pointer(const void *p) {
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return attr.type == cudaMemoryTypeDevice;
+}
+
+// Asynchronous part of a density evaluation: everything is queued on the grid stream, nothing is waited for.
+void GridEngine::density_launch(const double *Pa, int64_t ldPa, const double *Pb, int64_t ldPb, int flags) {
   Impl &s = *p_;
   CK(cudaSetDevice(s.device));
   const GridDev &g = s.gd;
@@ -361,65 +429,76 @@ void GridEngine::density(const double *Pa, int64_t ldPa, const double *Pb, int64
   static const int yyt[NCOMBO + 2] = {0, 0, 1, 2, 0, 3, 4, 0, 5, 6}, rrt[NCOMBO + 2] = {0, 1, 0, 0, 2, 0, 0, 3, 4, 5};
   for (int sp = 0; sp < nspin; sp++) {
     const double *P = sp ? Pb : Pa;
-    const int64_t ld = sp ? ldPb : ldPa;
-    double *dP = s.d_P.p + (size_t)sp * n * n;
-    CK(cudaMemcpy2DAsync(dP, n * sizeof(double), P, ld * sizeof(double), n * sizeof(double), n, cudaMemcpyDefault, s.st));
+    int64_t ld = sp ? ldPb : ldPa;
+    if (!is_device_pointer(P)) {   // host matrix: stage it; a device matrix is packed where it lies
+      double *dP = s.d_P.p + (size_t)sp * n * n;
+      CK(cudaMemcpy2DAsync(dP, n * sizeof(double), P, ld * sizeof(double), n * sizeof(double), n, cudaMemcpyDefault, s.st));
+      P = dP;
+      ld = (int64_t)n;
+    }
     double *Pe = s.d_Pe.p + (size_t)sp * g.Nel * g.NA2 * g.NN;
-    k_grid_pack<<<dim3(g.Nel, g.NA2), 128, 0, s.st>>>(g, dP, (int64_t)n, Pe);
+    k_grid_pack<<<dim3(g.Nel, g.NA2), 128, 0, s.st>>>(g, P, ld, Pe);
     CK(cudaGetLastError());
     // stage 1: Q[e] = Pe[e] . RR[e]
     double *Q = s.d_Q.p + (size_t)sp * g.Nel * g.NA2 * NRR * g.nrad;
-    std::vector<dev::GemmItem> items;
-    std::vector<dev::GemmEntry> entries;
-    for (int e = 0; e < g.Nel; e++) {
-      dev::GemmItem it{};
-      it.C = Q + (size_t)e * g.NA2 * NRR * g.nrad;
-      it.browoff = s.d_bo_q.p;
-      it.M = g.NA2;
-      it.N = NRR * g.nrad;
-      it.K = g.NN;
-      it.ent0 = (int)entries.size();
-      entries.push_back(dev::GemmEntry{Pe + (size_t)e * g.NA2 * g.NN, s.d_RR.p + (size_t)e * g.NN * NRR * g.nrad, g.NN});
-      it.ent1 = (int)entries.size();
-      it.accumulate = 0;
-      it.ldc = NRR * g.nrad;
-      it.alpha = 1.0;
-      items.push_back(it);
-    }
-    s.gemm(items, entries, g.NA2, NRR * g.nrad);
-    // stage 2: D_j[e][ia][ir] = YYT_j . Q[e][:, type_j]
-    items.clear();
-    entries.clear();
-    for (int j = 0; j < NCOMBO; j++) {
-      const bool need = j == 0 || ((flags & GRID_GRAD) && j >= 1 && j <= 3) ||
-                        ((flags & (GRID_TAU | GRID_LAPL)) && j >= 4 && j <= 6) || ((flags & GRID_LAPL) && j == 7);
-      if (!need) continue;
+    s.gemm_cached(100 + sp, g.NA2, NRR * g.nrad, [&](std::vector<dev::GemmItem> &items, std::vector<dev::GemmEntry> &entries) {
       for (int e = 0; e < g.Nel; e++) {
         dev::GemmItem it{};
-        it.C = s.d_D.p + (size_t)j * N + (size_t)e * g.npe;
+        it.C = Q + (size_t)e * g.NA2 * NRR * g.nrad;
         it.browoff = s.d_bo_q.p;
-        it.M = g.nang;
-        it.N = g.nrad;
-        it.K = g.NA2;
+        it.M = g.NA2;
+        it.N = NRR * g.nrad;
+        it.K = g.NN;
         it.ent0 = (int)entries.size();
-        const double *Qe = Q + (size_t)e * g.NA2 * NRR * g.nrad;
-        entries.push_back(dev::GemmEntry{s.d_YYT.p + (size_t)yyt[j] * g.nang * g.NA2, Qe + rrt[j] * g.nrad, g.NA2});
-        if (j == 7)
-          for (int x = 8; x <= 9; x++)
-            entries.push_back(dev::GemmEntry{s.d_YYT.p + (size_t)yyt[x] * g.nang * g.NA2, Qe + rrt[x] * g.nrad, g.NA2});
+        entries.push_back(dev::GemmEntry{Pe + (size_t)e * g.NA2 * g.NN, s.d_RR.p + (size_t)e * g.NN * NRR * g.nrad, g.NN});
         it.ent1 = (int)entries.size();
         it.accumulate = 0;
-        it.ldc = g.nrad;
+        it.ldc = NRR * g.nrad;
         it.alpha = 1.0;
         items.push_back(it);
       }
-    }
-    s.gemm(items, entries, g.nang, g.nrad);
+    });
+    // stage 2: D_j[e][ia][ir] = YYT_j . Q[e][:, type_j]
+    s.gemm_cached(200 + sp * 16 + (flags & 7), g.nang, g.nrad, [&](std::vector<dev::GemmItem> &items, std::vector<dev::GemmEntry> &entries) {
+      for (int j = 0; j < NCOMBO; j++) {
+        const bool need = j == 0 || ((flags & GRID_GRAD) && j >= 1 && j <= 3) ||
+                          ((flags & (GRID_TAU | GRID_LAPL)) && j >= 4 && j <= 6) || ((flags & GRID_LAPL) && j == 7);
+        if (!need) continue;
+        for (int e = 0; e < g.Nel; e++) {
+          dev::GemmItem it{};
+          it.C = s.d_D.p + (size_t)j * N + (size_t)e * g.npe;
+          it.browoff = s.d_bo_q.p;
+          it.M = g.nang;
+          it.N = g.nrad;
+          it.K = g.NA2;
+          it.ent0 = (int)entries.size();
+          const double *Qe = Q + (size_t)e * g.NA2 * NRR * g.nrad;
+          entries.push_back(dev::GemmEntry{s.d_YYT.p + (size_t)yyt[j] * g.nang * g.NA2, Qe + rrt[j] * g.nrad, g.NA2});
+          if (j == 7)
+            for (int x = 8; x <= 9; x++)
+              entries.push_back(dev::GemmEntry{s.d_YYT.p + (size_t)yyt[x] * g.nang * g.NA2, Qe + rrt[x] * g.nrad, g.NA2});
+          it.ent1 = (int)entries.size();
+          it.accumulate = 0;
+          it.ldc = g.nrad;
+          it.alpha = 1.0;
+          items.push_back(it);
+        }
+      }
+    });
     k_grid_points<<<592, 256, 0, s.st>>>(g, s.d_D.p, flags, s.dens(sp, 0), s.dens(sp, 1), s.dens(sp, 4), s.dens(sp, 5),
                                          s.d_sums.p);
     CK(cudaGetLastError());
   }
-  // outputs in libxc layout
+}
+
+// Waits for the density chain; outputs in libxc layout (host or device pointers, any may be NULL)
+void GridEngine::density_collect(double *rho, double *sigma, double *tau, double *lapl, double *weights, double *Nel,
+                                 double *Ekin) {
+  Impl &s = *p_;
+  CK(cudaSetDevice(s.device));
+  const int64_t N = s.N;
+  const int nspin = s.polarized ? 2 : 1;
+  const int flags = s.dens_flags;
   auto out = [&](double *host, const double *a, const double *b, const double *c, int nc) {
     if (!host) return;
     k_interleave<<<592, 256, 0, s.st>>>(a, b, c, nc, N, s.d_io.p);
@@ -440,6 +519,35 @@ void GridEngine::density(const double *Pa, int64_t ldPa, const double *Pb, int64
   CK(cudaStreamSynchronize(s.st));
   if (Nel) *Nel = sums[0];
   if (Ekin) *Ekin = sums[1];
+}
+
+void GridEngine::density(const double *Pa, int64_t ldPa, const double *Pb, int64_t ldPb, int flags, double *rho,
+                         double *sigma, double *tau, double *lapl, double *weights, double *Nel, double *Ekin) {
+  density_launch(Pa, ldPa, Pb, ldPb, flags);
+  density_collect(rho, sigma, tau, lapl, weights, Nel, Ekin);
+}
+
+// Built-in functionals evaluated on the device from the densities of the last density call, then the assembly:
+// x_func = 1 Slater exchange (libxc id 1), <= 0 none (H = 0; the HF drivers call eval_Fxc only to integrate Nel).
+void GridEngine::fxc_builtin(int x_func, double thr, bool beta, double *Ha, int64_t ldHa, double *Hb, int64_t ldHb,
+                             double *Exc) {
+  Impl &s = *p_;
+  CK(cudaSetDevice(s.device));
+  const int64_t N = s.N;
+  const size_t n = (size_t)s.nbf;
+  const int nspin = s.polarized ? 2 : 1;
+  if (x_func <= 0) {
+    if (Ha) CK(cudaMemset2DAsync(Ha, (size_t)ldHa * sizeof(double), 0, n * sizeof(double), n, s.st));
+    if (Hb && nspin == 2) CK(cudaMemset2DAsync(Hb, (size_t)ldHb * sizeof(double), 0, n * sizeof(double), n, s.st));
+    CK(cudaStreamSynchronize(s.st));
+    if (Exc) *Exc = 0.0;
+    return;
+  }
+  if (x_func != 1) throw std::logic_error("only the Slater exchange (libxc id 1) is built in");
+  double *v = s.d_v.p;
+  k_lda_x<<<592, 256, 0, s.st>>>(N, s.dens(0, 0), nspin == 2 ? s.dens(1, 0) : nullptr, thr, v + 9 * N, v, v + N);
+  CK(cudaGetLastError());
+  assemble(0, beta, true, false, false, false, Ha, ldHa, Hb, ldHb, Exc);
 }
 
 void GridEngine::fxc(int flags, bool beta, const double *exc, const double *vrho, const double *vsigma, const double *vtau,
@@ -463,8 +571,21 @@ void GridEngine::fxc(int flags, bool beta, const double *exc, const double *vrho
   if (gga) put(vsigma, nspin == 2 ? 3 : 1, 2);
   if (vtau) put(vtau, nspin, 5);
   if (vlapl) put(vlapl, nspin, 7);
+  if (exc) put(exc, 1, 9);
+  assemble(flags, beta, exc != nullptr, gga, vtau != nullptr, vlapl != nullptr, Ha, ldHa, Hb, ldHb, Exc);
+}
+
+// Assembly from the de-interleaved functional output held in d_v (v[0..1] vrho, v[2..4] vsigma, v[5..6] vtau,
+// v[7..8] vlapl, v[9] exc)
+void GridEngine::assemble(int flags, bool beta, bool exc, bool gga, bool vtau, bool vlapl, double *Ha, int64_t ldHa,
+                          double *Hb, int64_t ldHb, double *Exc) {
+  Impl &s = *p_;
+  const GridDev &g = s.gd;
+  const int64_t N = s.N;
+  const int nspin = s.polarized ? 2 : 1;
+  const size_t n = (size_t)s.nbf;
+  (void)flags;
   if (exc) {
-    put(exc, 1, 9);
     CK(cudaMemsetAsync(s.d_sums.p + 2, 0, sizeof(double), s.st));
     k_exc<<<592, 256, 0, s.st>>>(s.d_w.p, s.d_v.p + 9 * N, s.dens(0, 0), nspin == 2 ? s.dens(1, 0) : nullptr, N, s.d_sums.p + 2);
   }

@@ -58,11 +58,20 @@ class GridEngine {
   // densities in libxc layout on the host (any output pointer may be NULL); Pb == NULL: restricted
   void density(const double *Pa, int64_t ldPa, const double *Pb, int64_t ldPb, int flags, double *rho, double *sigma,
                double *tau, double *lapl, double *weights, double *Nel, double *Ekin);
+  // the same in two steps: density_launch queues the whole chain on the grid stream and returns at once (so that
+  // the J/K build can be issued next to it), density_collect waits and hands the results out
+  void density_launch(const double *Pa, int64_t ldPa, const double *Pb, int64_t ldPb, int flags);
+  void density_collect(double *rho, double *sigma, double *tau, double *lapl, double *weights, double *Nel, double *Ekin);
+  // built-in functionals on the device (x_func = 1 Slater exchange, <= 0 none) + assembly; H may be device pointers
+  void fxc_builtin(int x_func, double thr, bool beta, double *Ha, int64_t ldHa, double *Hb, int64_t ldHb, double *Exc);
+  cudaStream_t stream() const;
   // assembly from functional output (host arrays, libxc layout); uses the density kept on the device
   void fxc(int flags, bool beta, const double *exc, const double *vrho, const double *vsigma, const double *vtau,
            const double *vlapl, double *Ha, int64_t ldHa, double *Hb, int64_t ldHb, double *Exc);
 
  private:
+  void assemble(int flags, bool beta, bool exc, bool gga, bool vtau, bool vlapl, double *Ha, int64_t ldHa, double *Hb,
+                int64_t ldHb, double *Exc);
   struct Impl;
   std::unique_ptr<Impl> p_;
 };

@@ -235,6 +235,25 @@ int hfq_eval_fxc(hfq_ctx *ctx, int x_func, int c_func, const double *Pa, int64_t
                  double *Ha, int64_t ldHa, double *Hb, int64_t ldHb, double *Exc, double *Nel, double *Ekin, int beta,
                  double thr);
 
+/* One complete restricted Fock build as the reference's fock_builder issues it (src/diatomic/main.cpp:385-426,
+ * src/atomic/main.cpp:385-446): XC = eval_Fxc(x_func, c_func, P), J = coulomb(P), K = exchange(kscale * P), everything
+ * device-resident.  The grid's density chain is queued first on its own stream and runs next to the J/K kernels.
+ * x_func <= 0 and c_func <= 0 (Hartree-Fock: the reference still calls eval_Fxc, which then only integrates Nel):
+ * dHxc may be NULL; if given it is zero-filled (the reference's XC matrix of an HF build).  x_func = 1: Slater
+ * exchange evaluated on the device.  Needs hfq_grid_attach.  Exc, Nel: host scalars. */
+int hfq_fock_build_device(hfq_ctx *ctx, const double *dP, int64_t ldP, double kscale, double *dJ, int64_t ldJ, double *dK,
+                          int64_t ldK, int x_func, int c_func, double *dHxc, int64_t ldH, double *Exc, double *Nel,
+                          double thr, void *stream);
+/* The same with HOST matrices, what a CPU-side SCF driver calls: J, K as hfq_coulomb_exchange (one upload of P, result
+ * copies overlapped with the build), the grid pass on the device copy of P.
+ * Multi-GPU (context with a communicator, one process per GPU): P, J, K must be memory that EVERY rank can address
+ * (one shared segment, ideally page-locked by each rank); every rank uploads its 1/nranks column slice of P over its own
+ * PCIe link, one in-place ncclAllGather over NVLink completes the density on every GPU, the build is sharded, and
+ * every rank copies back / zero-fills its column slice of J and K.  The matrices are complete when every rank has
+ * returned: the caller places a barrier after the call.  Hxc (if given) is written by every rank in full. */
+int hfq_fock_build(hfq_ctx *ctx, const double *P, int64_t ldP, double kscale, double *J, int64_t ldJ, double *K, int64_t ldK,
+                   int x_func, int c_func, double *Hxc, int64_t ldH, double *Exc, double *Nel, double thr);
+
 /* Non-zero structure of the last hfq_exchange* result, for compact collectives / copies:
  * bf_sector[Nbf] = sector id of every basis function; pairs = (row sector, column sector) of the
  * blocks that were written (everything else in K is exactly zero).  Returns the number of pairs. */

@@ -288,3 +288,29 @@ def test_sadatom_eval_fxc_slater(hb):
     assert abs(Nel - o["Nel"]) < 1e-11 * abs(o["Nel"]) and abs(Exc - Eo) < 1e-11 * abs(Eo)
     for l in range(3):
         assert _rel(H[l], Ho[l]) < 1e-11, l
+
+
+def test_fused_fock_build_device(hb):
+    """hfq_fock_build_device: XC + J + K of one restricted build, device-resident, the grid density chain running
+    next to the J/K kernels.  HF (x_func = -1): the reference's fock_builder still calls eval_Fxc, which then only
+    integrates Nel (src/diatomic/main.cpp:396-401) -> Nel = Tr(P S), zero XC matrix.  x_func = 1: Slater exchange on
+    the device == hfq_eval_fxc."""
+    import torch
+    basis = hb.DiatomicTwoDBasis(7, 7, 2.07, [6, 5, 4], 2).compute_tei()
+    t = basis.tables
+    n = basis.Nbf()
+    grid = hb.DFTGrid(basis, 4 * 6 + 12)
+    P = cases.random_density(n, 3, 17, cases.m_blocks(t.mval, t.Nrad, True))
+    S = basis.overlap()
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a.T)).cuda()
+    dP = dev(P)
+    dJ, dK, dH = torch.empty_like(dP), torch.empty_like(dP), torch.full_like(dP, float("nan"))
+    exc, nel = basis.fock_build_device(dP.data_ptr(), dJ.data_ptr(), dK.data_ptr(), 0.5, -1, 0, dH.data_ptr())
+    J, K = basis.coulomb_exchange(P, 0.5)
+    assert _rel(dJ.cpu().numpy().T, J) < 1e-13 and _rel(dK.cpu().numpy().T, K) < 1e-13
+    assert abs(nel - np.sum(P * S)) < 1e-10 * abs(nel) and exc == 0.0
+    assert not dH.cpu().numpy().any()
+    exc, nel = basis.fock_build_device(dP.data_ptr(), dJ.data_ptr(), dK.data_ptr(), 0.5, 1, 0, dH.data_ptr())
+    Href, eref, nref, _ = grid.eval_Fxc(1, 0, P)
+    assert _rel(dH.cpu().numpy().T, Href) < 1e-13 and abs(exc - eref) < 1e-12 * abs(eref) and abs(nel - nref) < 1e-12 * nref
+    assert _rel(dK.cpu().numpy().T, K) < 1e-13

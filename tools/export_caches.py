@@ -24,7 +24,7 @@ def main():
     hb_build.build()
     T = hb.Tables.diatomic(int(Z1), int(Z2), float(Rbond), [int(lmax)] * (int(mmax) + 1), int(nelem))
     d = {"Nrad": T.Nrad, "efirst": T.efirst, "en": T.en, "lval": T.lval, "mval": T.mval, "lmL": T.lmL, "lmM": T.lmM,
-         "pref": T.pref, "ranks": T.ranks}
+         "pref": T.pref, "ranks": T.ranks, "bval": T.bval}
     sm, bg, B, sg = [], [], [], []
     for ilm in range(T.nlm):
         for e in range(T.Nel):
