@@ -41,7 +41,7 @@ EXPORTED_SYMBOLS = [
     "hfq_tables_destroy", "hfq_create", "hfq_destroy", "hfq_nbf", "hfq_set_absm_symmetric", "hfq_coulomb",
     "hfq_exchange", "hfq_coulomb_device", "hfq_exchange_device", "hfq_last_timings", "hfq_exchange_output_pattern",
     "hfq_coulomb_output_pattern",
-    "hfq_set_host_threads", "hfq_fock_build", "hfq_fock_build_device", "hfq_comm_unique_id", "hfq_comm_init", "hfq_comm_size", "hfq_shard_assign",
+    "hfq_tables_sadatom_batch", "hfq_coulomb_radial_batch", "hfq_set_host_threads", "hfq_fock_build", "hfq_fock_build_device", "hfq_comm_unique_id", "hfq_comm_init", "hfq_comm_size", "hfq_shard_assign",
     "hfq_coulomb_exchange", "hfq_coulomb_exchange_device", "hfq_grid_attach", "hfq_grid_npoints", "hfq_grid_density", "hfq_grid_fxc", "hfq_eval_fxc",
 ]
 
@@ -92,6 +92,8 @@ def lib():
     L.hfq_coulomb_output_pattern.argtypes = [vp, vp, i64, vp, i64]
     L.hfq_coulomb_exchange.argtypes = [vp, vp, i64, cd, vp, i64, vp, i64]
     L.hfq_coulomb_exchange_device.argtypes = [vp, vp, i64, cd, vp, i64, vp, i64, ci, ci, vp]
+    L.hfq_tables_sadatom_batch.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ci, cd, ci, cd, ci]
+    L.hfq_coulomb_radial_batch.argtypes = [vp, vp, vp, ci, cd, vp]
     L.hfq_set_host_threads.argtypes = [ci]
     L.hfq_fock_build.argtypes = [vp, vp, i64, cd, vp, i64, vp, i64, ci, ci, vp, i64, vp, vp, cd]
     L.hfq_fock_build_device.argtypes = [vp, vp, i64, cd, vp, i64, vp, i64, ci, ci, vp, i64, vp, vp, cd, vp]
@@ -189,6 +191,12 @@ class Tables:
     def sadatom(cls, Z, lmax, nelem, nnodes=15, Rmax=40.0, igrid=4, zexp=2.0, nquad=0):
         h = ctypes.c_void_p()
         _check(lib().hfq_tables_sadatom(ctypes.byref(h), Z, lmax, nelem, nnodes, Rmax, igrid, zexp, nquad))
+        return cls(h)
+
+    @classmethod
+    def sadatom_batch(cls, lmax, nbatch, nelem, nnodes=15, Rmax=40.0, igrid=4, zexp=2.0, nquad=0):
+        h = ctypes.c_void_p()
+        _check(lib().hfq_tables_sadatom_batch(ctypes.byref(h), lmax, nbatch, nelem, nnodes, Rmax, igrid, zexp, nquad))
         return cls(h)
 
     @classmethod

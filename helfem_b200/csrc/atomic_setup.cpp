@@ -505,6 +505,22 @@ BasisTables build_sadatom_tables(int Z, int lmax, int nelem, int nnodes, double 
   return t;
 }
 
+BasisTables build_sadatom_batch_tables(int lmax, int nbatch, int nelem, int nnodes, double Rmax, int igrid, double zexp,
+                                       int nquad) {
+  // only the L = 0 radial caches are used by the batched operators: an lmax = 0 basis, angular list tiled
+  BasisTables t = build_atomic_tables(1, 0, 0, nelem, nnodes, Rmax, igrid, zexp, nquad);
+  t.kind = BasisKind::Sadatom;
+  t.batch = nbatch;
+  t.lval.clear();
+  t.mval.clear();
+  for (int a = 0; a < nbatch; a++)
+    for (int l = 0; l <= lmax; l++) {
+      t.lval.push_back(l);
+      t.mval.push_back(0);
+    }
+  return t;
+}
+
 BasisTables build_sadatom_rs_tables(int Z, int lmax, int nelem, int nnodes, double Rmax, int igrid, double zexp,
                                     int nquad, int rs, double param) {
   BasisTables t = rs == 1 ? build_atomic_yukawa_tables(Z, lmax, 0, nelem, nnodes, Rmax, igrid, zexp, nquad, param)

@@ -172,6 +172,18 @@ int hfq_tables_sadatom(hfq_tables **out, int Z, int lmax, int nelem, int nnodes,
   });
 }
 
+int hfq_tables_sadatom_batch(hfq_tables **out, int lmax, int nbatch, int nelem, int nnodes, double Rmax, int igrid,
+                             double zexp, int nquad) {
+  if (!out || lmax < 0 || nbatch < 1 || nelem < 1 || nnodes < 2 || nnodes > 16 || !(Rmax > 0.0))
+    return fail(HFQ_ERR_INVALID, "hfq_tables_sadatom_batch: invalid argument");
+  return guarded([&] {
+    auto *h = new hfq_tables;
+    h->t = hfq::build_sadatom_batch_tables(lmax, nbatch, nelem, nnodes, Rmax, igrid, zexp, nquad);
+    *out = h;
+    return HFQ_OK;
+  });
+}
+
 int hfq_tables_sadatom_rs(hfq_tables **out, int Z, int lmax, int nelem, int nnodes, double Rmax, int igrid, double zexp,
                           int nquad, int rs, double param) {
   if (!out || lmax < 0 || nelem < 1 || nnodes < 2 || nnodes > 16 || !(Rmax > 0.0) || (rs != 1 && rs != 2) || !(param > 0.0))
@@ -491,7 +503,8 @@ int hfq_grid_density(hfq_ctx *ctx, const double *Pa, int64_t ldPa, const double 
                      double *rho, double *sigma, double *tau, double *lapl, double *weights, double *Nel, double *Ekin) {
   if (!ctx || !ctx->grid) return fail(HFQ_ERR_STATE, "hfq_grid_density: no grid attached");
   if (!Pa) return fail(HFQ_ERR_INVALID, "Error - density matrix is empty!");   // src/atomic/dftgrid.cpp:53-55
-  const int64_t n = ctx->eng->Nbf();
+  // batch tables: block-compact matrices, leading dimension Nrad (include/helfem_b200.h, hfq_tables_sadatom_batch)
+  const int64_t n = ctx->eng->tables().batch > 1 ? ctx->eng->tables().Nrad : ctx->eng->Nbf();
   if (ldPa < n || (Pb && ldPb < n)) return fail(HFQ_ERR_INVALID, "hfq_grid_density: leading dimension smaller than Nbf");
   std::lock_guard<std::mutex> lk(ctx->mu);
   return guarded([&] {
@@ -505,7 +518,7 @@ int hfq_grid_fxc(hfq_ctx *ctx, int flags, int beta, const double *exc, const dou
   if (!ctx || !ctx->grid) return fail(HFQ_ERR_STATE, "hfq_grid_fxc: no grid attached");
   if (!vrho || !Ha) return fail(HFQ_ERR_INVALID, "hfq_grid_fxc: null argument");
   {
-    const int64_t n = ctx->eng->Nbf();
+    const int64_t n = ctx->eng->tables().batch > 1 ? ctx->eng->tables().Nrad : ctx->eng->Nbf();
     if (ldHa < n) return fail(HFQ_ERR_INVALID, "hfq_grid_fxc: ldHa smaller than Nbf");
     if (ctx->grid->polarized() && beta && (!Hb || ldHb < n))
       return fail(HFQ_ERR_INVALID, "hfq_grid_fxc: polarised density with beta set needs Hb with ldHb >= Nbf");
@@ -594,6 +607,16 @@ int hfq_fock_build_device(hfq_ctx *ctx, const double *dP, int64_t ldP, double ks
     double ekin = 0.0;
     ctx->grid->density_collect(nullptr, nullptr, nullptr, nullptr, nullptr, Nel, &ekin);
     ctx->grid->fxc_builtin(x_func, thr, true, dHxc, ldH, nullptr, 0, Exc);
+    return HFQ_OK;
+  });
+}
+
+int hfq_coulomb_radial_batch(hfq_ctx *ctx, const double *dP, double *dJ, int nb, double fac, void *stream) {
+  if (!ctx || !dP || !dJ || nb < 0) return fail(HFQ_ERR_INVALID, "hfq_coulomb_radial_batch: invalid argument");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  return guarded([&] {
+    const int64_t N = ctx->eng->tables().Nrad;
+    ctx->eng->coulomb_radial_batch(dP, dJ, nb, N * N, fac, stream ? (cudaStream_t)stream : ctx->eng->stream());
     return HFQ_OK;
   });
 }

@@ -87,6 +87,9 @@ struct Engine::Impl {
   int64_t op_stride = 0;
   std::vector<int64_t> tperm_off;   // [nlm * Nel] offset of the tiled in-element kernel A_(ilm,e)
   std::vector<int64_t> tperm_tri_off;   // the same for the rows rj <= rk only (symmetric densities)
+  bool radial_only = false;   // batch tables: see the constructor
+  DevBuf<int> d_bchan;        // coulomb_radial_batch: channel / prefactor per batch entry
+  DevBuf<double> d_bfac;
   bool p_symmetric = false;   // set by pack_density: P == P^T to 1e-14 of its largest element
   // device
   DevBuf<int> d_ang_off, d_ang_skip, d_sec_n, d_sec_ang, d_efirst, d_en, d_ang_sec, d_ang_pos, d_rad_e0, d_rad_e1;
@@ -150,6 +153,58 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
     if (t.en[e] > 16) throw std::runtime_error("Engine: more than 16 functions per element not supported");
   s.nab = t.nch * t.nch;
   s.Npix = t.Nrad * t.Nrad;
+  // ---- flattened cache arrays (shared by the full engine and the radial-only mode of batched atoms)
+  const int nlm = (int)t.lmL.size();
+  auto upload_caches = [&]() {
+    std::vector<double> hsmall, hbig, hB, hsig;
+    s.blk_off.assign((size_t)nlm * t.Nel, 0);
+    s.B_off.assign((size_t)nlm * t.Nel, 0);
+    s.sig_off.assign((size_t)nlm * t.Nel, 0);
+    s.ranks.assign((size_t)nlm * t.Nel, 0);
+    for (int ilm = 0; ilm < nlm; ilm++)
+      for (int e = 0; e < t.Nel; e++) {
+        const ChannelBlock &b = t.blocks[(size_t)ilm * t.Nel + e];
+        const size_t nn = (size_t)t.nch * b.n * b.n;
+        if (b.rank > 128) throw std::runtime_error("Engine: in-element factor rank > 128");
+        s.blk_off[(size_t)ilm * t.Nel + e] = (int64_t)hsmall.size();
+        hsmall.insert(hsmall.end(), b.small.begin(), b.small.end());
+        if (b.big.size() == nn)
+          hbig.insert(hbig.end(), b.big.begin(), b.big.end());
+        else
+          hbig.insert(hbig.end(), nn, 0.0);
+        s.B_off[(size_t)ilm * t.Nel + e] = (int64_t)hB.size();
+        hB.insert(hB.end(), b.B.begin(), b.B.end());
+        s.sig_off[(size_t)ilm * t.Nel + e] = (int64_t)hsig.size();
+        hsig.insert(hsig.end(), b.sigma.begin(), b.sigma.end());
+        s.ranks[(size_t)ilm * t.Nel + e] = b.rank;
+      }
+    s.d_small.upload(hsmall, &dev_bytes_);
+    s.d_big.upload(hbig, &dev_bytes_);
+    s.d_B.upload(hB, &dev_bytes_);
+    s.d_sigma.upload(hsig, &dev_bytes_);
+    s.d_blk_off.upload(s.blk_off, &dev_bytes_);
+    s.d_B_off.upload(s.B_off, &dev_bytes_);
+    s.d_sig_off.upload(s.sig_off, &dev_bytes_);
+    s.d_rank.upload(s.ranks, &dev_bytes_);
+    };
+  if (t.batch > 1) {
+    // Batch of spherically averaged atoms (BasisTables::batch): only the radial Coulomb operator of the L = 0
+    // channel is served (coulomb_radial_batch); no sectors, coupling tables or exchange kernels exist.
+    if (t.kind != BasisKind::Sadatom || t.nch != 1) throw std::logic_error("Engine: batch tables must be sadatom tables");
+    upload_caches();
+    for (auto &b : s.t.blocks) {
+      std::vector<double>().swap(b.B);
+      std::vector<double>().swap(b.small);
+      std::vector<double>().swap(b.big);
+    }
+    s.d_efirst.upload(t.efirst, &dev_bytes_);
+    s.d_en.upload(t.en, &dev_bytes_);
+    s.NL = 1;
+    s.bd = dev::BasisDev{t.Nang(), t.Nrad, s.Npix, 0, 0, 0, 1, 1, t.Nel, 1, nullptr, nullptr, nullptr, nullptr,
+                         s.d_efirst.p, s.d_en.p, nullptr, nullptr};
+    s.radial_only = true;
+    return;
+  }
   // ---- sectors: angular functions grouped by m and, for large expansions, by l-parity.
   // A coupling coefficient vanishes unless l_j + l_i + L is even, so a (m, parity) sector pair
   // couples through one L-parity only, and densities of homonuclear molecules (no even-odd l
@@ -283,40 +338,7 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
       }
     s.d_G.upload(G, &dev_bytes_);
   }
-  // ---- flattened cache arrays
-  const int nlm = (int)t.lmL.size();
-  {
-    std::vector<double> hsmall, hbig, hB, hsig;
-    s.blk_off.assign((size_t)nlm * t.Nel, 0);
-    s.B_off.assign((size_t)nlm * t.Nel, 0);
-    s.sig_off.assign((size_t)nlm * t.Nel, 0);
-    s.ranks.assign((size_t)nlm * t.Nel, 0);
-    for (int ilm = 0; ilm < nlm; ilm++)
-      for (int e = 0; e < t.Nel; e++) {
-        const ChannelBlock &b = t.blocks[(size_t)ilm * t.Nel + e];
-        const size_t nn = (size_t)t.nch * b.n * b.n;
-        if (b.rank > 128) throw std::runtime_error("Engine: in-element factor rank > 128");
-        s.blk_off[(size_t)ilm * t.Nel + e] = (int64_t)hsmall.size();
-        hsmall.insert(hsmall.end(), b.small.begin(), b.small.end());
-        if (b.big.size() == nn)
-          hbig.insert(hbig.end(), b.big.begin(), b.big.end());
-        else
-          hbig.insert(hbig.end(), nn, 0.0);
-        s.B_off[(size_t)ilm * t.Nel + e] = (int64_t)hB.size();
-        hB.insert(hB.end(), b.B.begin(), b.B.end());
-        s.sig_off[(size_t)ilm * t.Nel + e] = (int64_t)hsig.size();
-        hsig.insert(hsig.end(), b.sigma.begin(), b.sigma.end());
-        s.ranks[(size_t)ilm * t.Nel + e] = b.rank;
-      }
-    s.d_small.upload(hsmall, &dev_bytes_);
-    s.d_big.upload(hbig, &dev_bytes_);
-    s.d_B.upload(hB, &dev_bytes_);
-    s.d_sigma.upload(hsig, &dev_bytes_);
-    s.d_blk_off.upload(s.blk_off, &dev_bytes_);
-    s.d_B_off.upload(s.B_off, &dev_bytes_);
-    s.d_sig_off.upload(s.sig_off, &dev_bytes_);
-    s.d_rank.upload(s.ranks, &dev_bytes_);
-  }
+  upload_caches();
   // free the big host copies
   for (auto &b : s.t.blocks) {
     std::vector<double>().swap(b.B);
@@ -753,10 +775,39 @@ void assign_units(const std::vector<double> &cost, int nranks, std::vector<int> 
   }
 }
 
+// Radial Coulomb operator of MANY densities in one launch (batched atoms of the SAP workload):
+// J_b = fac * J_0(P_b), J_0 the L = 0 multipole of assemble_J_FE_one_multipole_cached_chol
+// (libhelfemqc/include/CoulombExchangeFE.h:432-482; sadatom coulomb = 4 pi J_0, src/sadatom/basis.cpp:186-207).
+// dP, dJ: nb matrices of Nrad x Nrad, contiguous, stride `stride` doubles (>= Nrad^2); symmetric densities.
+void Engine::coulomb_radial_batch(const double *dP, double *dJ, int nb, int64_t stride, double fac, cudaStream_t st) {
+  Impl &s = *p_;
+  const BasisTables &t = s.t;
+  if (t.kind == BasisKind::Diatomic || t.nch != 1 || t.pairwise()) throw std::logic_error("coulomb_radial_batch: atomic radial caches required");
+  if (stride != (int64_t)s.Npix) throw std::logic_error("coulomb_radial_batch: matrices must be contiguous (stride = Nrad^2)");
+  if (nb < 1) return;
+  CK(cudaSetDevice(device_));
+  const int ilm = t.channel(0, 0);
+  if (ilm < 0) throw std::logic_error("coulomb_radial_batch: no L = 0 channel");
+  if ((int)s.d_bchan.n < nb) {
+    s.d_bchan.upload(std::vector<int>(nb, ilm), &dev_bytes_);
+    s.d_bfac.upload(std::vector<double>(nb, 0.0), &dev_bytes_);
+  }
+  std::vector<double> hf(nb, fac * t.pref[ilm]);
+  CK(cudaMemcpyAsync(s.d_bfac.p, hf.data(), nb * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));   // hf goes out of scope
+  dev::BasisDev b1 = s.bd;
+  b1.NL = 1;   // one multipole: Paux[batch][pix], JauxT[batch][pix]
+  dev::JRadDev jr{s.d_bchan.p, s.d_bfac.p, s.d_blk_off.p, s.d_B_off.p, s.d_sig_off.p, s.d_rank.p,
+                  s.d_small.p, s.d_big.p, s.d_B.p, s.d_sigma.p, nb};
+  dev::k_jradial<<<dim3(1, nb), 256, 0, st>>>(b1, jr, 0, dP, dJ);
+  CK(cudaGetLastError());
+}
+
 void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK, int shard, int nshards,
                           cudaStream_t st) {
   Impl &s = *p_;
   const BasisTables &t = s.t;
+  if (s.radial_only) throw std::logic_error("exchange is not available on batch tables");
   CK(cudaSetDevice(device_));
   const int na = t.Nang(), ns = s.ns, Nel = t.Nel;
   if (comm_) {   // a communicator overrides the legacy shard arguments
@@ -1313,6 +1364,7 @@ void Engine::coulomb_run(const double *dP, int64_t ldP, double *dJ, int64_t ldJ,
   const BasisTables &t = s.t;
   if (t.pairwise())
     throw std::logic_error("coulomb is not available on range-separated (erfc pair-tensor) tables\n");
+  if (s.radial_only) throw std::logic_error("coulomb is not available on batch tables (use hfq_coulomb_radial_batch)");
   CK(cudaSetDevice(device_));
   const int na = t.Nang(), ns = s.ns, nq = s.NL * t.nch;
   if (!async) tm_ = EngineTimings();

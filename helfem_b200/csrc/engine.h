@@ -65,6 +65,8 @@ class Engine {
               int nshards, cudaStream_t stream);
   void exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK, int shard, int nshards,
                     cudaStream_t stream);
+  // batched radial Coulomb (SAP workload): J_b = fac * prefactor(L=0) * J_0(P_b), b < nb, device-resident
+  void coulomb_radial_batch(const double *dP, double *dJ, int nb, int64_t stride, double fac, cudaStream_t stream);
   // Host-pointer entry points (copies in/out on the engine's stream).
   void coulomb(const double *P, int64_t ldP, double *J, int64_t ldJ);
   void exchange(const double *P, int64_t ldP, double *K, int64_t ldK);

@@ -7,6 +7,7 @@
 #include "grid.h"
 
 #include <cmath>
+#include <cstring>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -60,6 +61,7 @@ struct GridDev {
   const double *sc;      // [3][N] scale factors of the three orthogonal directions
   const double *lfac;    // [N] prefactor of the Laplacian
   int clamp1;            // tau: theta-direction term clamped at zero (spherically averaged atom)
+  int skip_uncoupled;    // unpack: leave the blocks of uncoupled angular pairs untouched
 };
 
 // Pe[e][(a,b)][(r,c)] = P[(a, f+r), (b, f+c)]     grid (Nel, NA2)
@@ -154,6 +156,7 @@ __global__ void k_grid_unpack(GridDev g, const double *__restrict__ Hs, const do
   const int a = blockIdx.x, b = blockIdx.y;
   const int sa = g.ang_skip[a], sb = g.ang_skip[b];
   const int pab = g.pair_of[a * g.Nang + b], pba = g.pair_of[b * g.Nang + a];
+  if (pab < 0 && g.skip_uncoupled) return;   // block-compact matrices (batched atoms) hold the coupled blocks only
   for (int idx = threadIdx.x; idx < g.Nrad * g.Nrad; idx += blockDim.x) {
     const int R = idx % g.Nrad, Cc = idx / g.Nrad;
     if (R < sa || Cc < sb) continue;
@@ -383,9 +386,8 @@ GridEngine::GridEngine(const BasisTables &t, const GridTables &g, int device, cu
   }
   s.gd = GridDev{Nel, NA, NA2, NI, NN, nang, nrad, t.Nrad, (int64_t)nang * nrad, s.d_efirst.p, s.d_en.p,
                  s.d_pa.p, s.d_pb.p, s.d_pof.p, s.d_aoff.p, s.d_askip.p, s.d_w.p, s.d_sc.p, s.d_lfac.p,
-                 g.clamp_theta_kin ? 1 : 0};
-  s.d_P.alloc((size_t)2 * s.nbf * s.nbf);
-  s.d_H.alloc((size_t)s.nbf * s.nbf);
+                 g.clamp_theta_kin ? 1 : 0, t.batch > 1 ? 1 : 0};
+  // staging copies of dense host matrices (d_P, d_H) are allocated on first use: device-resident callers never need them
   s.d_Pe.alloc((size_t)2 * Nel * NA2 * NN);
   s.d_Q.alloc((size_t)2 * Nel * NA2 * NRR * nrad);
   s.d_D.alloc((size_t)NCOMBO * s.N);
@@ -431,6 +433,7 @@ void GridEngine::density_launch(const double *Pa, int64_t ldPa, const double *Pb
     const double *P = sp ? Pb : Pa;
     int64_t ld = sp ? ldPb : ldPa;
     if (!is_device_pointer(P)) {   // host matrix: stage it; a device matrix is packed where it lies
+      s.d_P.alloc((size_t)2 * n * n);
       double *dP = s.d_P.p + (size_t)sp * n * n;
       CK(cudaMemcpy2DAsync(dP, n * sizeof(double), P, ld * sizeof(double), n * sizeof(double), n, cudaMemcpyDefault, s.st));
       P = dP;
@@ -537,8 +540,16 @@ void GridEngine::fxc_builtin(int x_func, double thr, bool beta, double *Ha, int6
   const size_t n = (size_t)s.nbf;
   const int nspin = s.polarized ? 2 : 1;
   if (x_func <= 0) {
-    if (Ha) CK(cudaMemset2DAsync(Ha, (size_t)ldHa * sizeof(double), 0, n * sizeof(double), n, s.st));
-    if (Hb && nspin == 2) CK(cudaMemset2DAsync(Hb, (size_t)ldHb * sizeof(double), 0, n * sizeof(double), n, s.st));
+    auto zero = [&](double *H, int64_t ld) {
+      if (!H) return;
+      if (is_device_pointer(H)) {
+        CK(cudaMemset2DAsync(H, (size_t)ld * sizeof(double), 0, n * sizeof(double), n, s.st));
+      } else {
+        for (size_t c = 0; c < n; c++) std::memset(H + c * ld, 0, n * sizeof(double));
+      }
+    };
+    zero(Ha, ldHa);
+    if (nspin == 2) zero(Hb, ldHb);
     CK(cudaStreamSynchronize(s.st));
     if (Exc) *Exc = 0.0;
     return;
@@ -656,11 +667,17 @@ void GridEngine::assemble(int flags, bool beta, bool exc, bool gga, bool vtau, b
         items.push_back(it);   // an item without entries writes zeros
       }
     s.gemm(items, entries, g.NA2, g.NN);
-    k_grid_unpack<<<dim3(g.Nang, g.Nang), 256, 0, s.st>>>(g, s.d_Hs.p, s.d_Hx.p, s.d_H.p, (int64_t)n);
-    CK(cudaGetLastError());
     double *H = sp ? Hb : Ha;
     const int64_t ld = sp ? ldHb : ldHa;
-    CK(cudaMemcpy2DAsync(H, ld * sizeof(double), s.d_H.p, n * sizeof(double), n * sizeof(double), n, cudaMemcpyDefault, s.st));
+    if (is_device_pointer(H)) {   // device matrix: written in place, with the caller's leading dimension
+      k_grid_unpack<<<dim3(g.Nang, g.Nang), 256, 0, s.st>>>(g, s.d_Hs.p, s.d_Hx.p, H, ld);
+      CK(cudaGetLastError());
+    } else {
+      s.d_H.alloc(n * n);
+      k_grid_unpack<<<dim3(g.Nang, g.Nang), 256, 0, s.st>>>(g, s.d_Hs.p, s.d_Hx.p, s.d_H.p, (int64_t)n);
+      CK(cudaGetLastError());
+      CK(cudaMemcpy2DAsync(H, ld * sizeof(double), s.d_H.p, n * sizeof(double), n * sizeof(double), n, cudaMemcpyDefault, s.st));
+    }
     CK(cudaStreamSynchronize(s.st));
   }
   if (exc && Exc) {

@@ -140,7 +140,12 @@ GridTables build_sadatom_grid(const BasisTables &t) {
   if (t.kind != BasisKind::Sadatom) throw std::logic_error("build_sadatom_grid: sadatom basis required");
   if (t.bval.empty()) throw std::logic_error("build_sadatom_grid: basis was not built by this library");
   GridTables g;
-  g.lang = g.mang = g.nang = 1;
+  // a batch of atoms (BasisTables::batch) is laid out along the "angular point" axis: point (element, atom, radial
+  // node), and the angular table of function a = (atom, l) is the indicator of its atom -- the separable engine then
+  // produces per-atom densities and per-atom Fock blocks in one pass
+  const int nb = std::max(1, t.batch), nl = t.Nang() / nb;
+  g.lang = g.mang = 1;
+  g.nang = nb;
   g.nrad = t.nquad;
   g.Nel = t.Nel;
   g.Nang = t.Nang();
@@ -150,23 +155,30 @@ GridTables build_sadatom_grid(const BasisTables &t) {
   g.same_l_only = true;
   g.clamp_theta_kin = true;
   const double pi = std::acos(-1.0);
-  g.cth.push_back(1.0);
-  g.phi.push_back(0.0);
-  g.wang.push_back(4.0 * pi);
-  g.Y.assign((size_t)g.Nang, 1.0);
-  g.Th.assign((size_t)g.Nang, 0.0);
-  for (int a = 0; a < g.Nang; a++) g.Th[a] = std::complex<double>(0.0, std::sqrt((double)t.lval[a] * (t.lval[a] + 1)));
+  g.cth.assign(nb, 1.0);
+  g.phi.assign(nb, 0.0);
+  g.wang.assign(nb, 4.0 * pi);
+  g.Y.assign((size_t)g.Nang * nb, 0.0);
+  g.Th.assign((size_t)g.Nang * nb, 0.0);
+  for (int a = 0; a < g.Nang; a++) {
+    const int atom = a / nl;
+    g.Y[(size_t)a * nb + atom] = 1.0;
+    g.Th[(size_t)a * nb + atom] = std::complex<double>(0.0, std::sqrt((double)t.lval[a] * (t.lval[a] + 1)));
+  }
   fill_atomic_radial(t, g);
-  const size_t N = (size_t)g.Nel * g.nrad;
+  const size_t N = (size_t)g.Nel * nb * g.nrad;
   g.wtot.resize(N);
   for (int c = 0; c < 3; c++) g.scale[c].resize(N);
   g.lfac.assign(N, 1.0);
-  for (size_t p = 0; p < N; p++) {
-    g.wtot[p] = 4.0 * pi * g.wrad[p] * g.r[p] * g.r[p];
-    g.scale[0][p] = 1.0;
-    g.scale[1][p] = g.r[p];
-    g.scale[2][p] = g.r[p];
-  }
+  for (int e = 0; e < g.Nel; e++)
+    for (int ia = 0; ia < nb; ia++)
+      for (int q = 0; q < g.nrad; q++) {
+        const size_t p = ((size_t)e * nb + ia) * g.nrad + q, pr = (size_t)e * g.nrad + q;
+        g.wtot[p] = 4.0 * pi * g.wrad[pr] * g.r[pr] * g.r[pr];
+        g.scale[0][p] = 1.0;
+        g.scale[1][p] = g.r[pr];
+        g.scale[2][p] = g.r[pr];
+      }
   return g;
 }
 

@@ -52,6 +52,10 @@ struct BasisTables {
   bool pairwise() const { return !pair.empty(); }
   // basis parameters kept for bookkeeping / grid construction
   double Rhalf = 0.0;
+  // > 1: a BATCH of independent spherically averaged atoms on one radial basis (the two-electron caches do not
+  // depend on Z): angular function a = atom * (lmax + 1) + l.  Such tables serve the batched operators of the SAP
+  // workload only (radial Coulomb of many densities, radial DFT grid with one "angular point" per atom).
+  int batch = 1;
   int Z1 = 0, Z2 = 0;
   int nnodes = 0, nquad = 0;
   std::vector<double> bval;
@@ -83,6 +87,9 @@ double erfc_phi(int n, double Xi, double xi);
 // out), same radial caches as the atomic basis; exchange couples density block l_in to output
 // block l_out through the m-averaged squared Gaunt coefficient (src/sadatom/basis.cpp:209-312)
 BasisTables build_sadatom_tables(int Z, int lmax, int nelem, int nnodes, double Rmax, int igrid, double zexp, int nquad);
+// a batch of nbatch spherically averaged atoms sharing one radial basis (see BasisTables::batch)
+BasisTables build_sadatom_batch_tables(int lmax, int nbatch, int nelem, int nnodes, double Rmax, int igrid, double zexp,
+                                       int nquad);
 // range-separated caches of the spherically averaged atom (src/sadatom/basis.cpp:154-184): rs = 1 Yukawa
 // (param = lambda), rs = 2 erfc (param = mu); exchange() on them is sadatom rs_exchange (:314-420)
 BasisTables build_sadatom_rs_tables(int Z, int lmax, int nelem, int nnodes, double Rmax, int igrid, double zexp, int nquad,

@@ -82,6 +82,17 @@ double hfq_erfc_phi(int L, double Xi, double xi);
 int hfq_tables_sadatom(hfq_tables **out, int Z, int lmax, int nelem, int nnodes, double Rmax, int igrid, double zexp,
                        int nquad);
 
+/* A BATCH of nbatch spherically averaged atoms on one radial basis -- the gen_sap_table workload (one SCF per
+ * element; src/sadatom/scf.cpp:50-350 evaluates several densities concurrently, :313-350).  The radial two-electron
+ * caches do not depend on Z, so all atoms share them: angular function a = atom * (lmax + 1) + l.  A context created
+ * from these tables serves two batched, device-resident operators: hfq_coulomb_radial_batch and the radial DFT grid
+ * (hfq_grid_attach, then hfq_grid_density / hfq_grid_fxc / hfq_eval_fxc / fxc with x_func = 1): the atom index is
+ * laid out along the grid's "angular point" axis, point p = (element, atom, radial node), and matrices are
+ * BLOCK-COMPACT: the Nrad x Nrad block of function a at offset a * Nrad * (Nrad + 1) doubles, column-major, passed
+ * with leading dimension Nrad (device pointers only).  hfq_coulomb / hfq_exchange are not available on them. */
+int hfq_tables_sadatom_batch(hfq_tables **out, int lmax, int nbatch, int nelem, int nnodes, double Rmax, int igrid,
+                             double zexp, int nquad);
+
 /* Range-separated caches of the spherically averaged atom: sadatom TwoDBasis::compute_yukawa(lambda) (rs = 1)
  * or compute_erfc(mu) (rs = 2), src/sadatom/basis.cpp:154-184; hfq_exchange on a context created from these
  * tables is sadatom rs_exchange(cube) (:314-420). */
@@ -175,6 +186,12 @@ int hfq_exchange(hfq_ctx *ctx, const double *P, int64_t ldP, double *K, int64_t 
 int hfq_coulomb_device(hfq_ctx *ctx, const double *dP, int64_t ldP, double *dJ, int64_t ldJ, void *stream);
 int hfq_exchange_device(hfq_ctx *ctx, const double *dP, int64_t ldP, double *dK, int64_t ldK, int shard,
                         int nshards, void *stream);
+
+/* Radial Coulomb matrices of nb spherical densities in one launch: J_b = fac * coulomb(P_b) with the sadatom
+ * convention coulomb(P) = 4 pi J_0(P) (src/sadatom/basis.cpp:186-207; the reference's gensap builder calls it with
+ * Prad / 4 pi, src/sadatom/scf.cpp:199).  dP, dJ: nb contiguous Nrad x Nrad device matrices.  Any context over an
+ * atomic / sadatom radial basis. */
+int hfq_coulomb_radial_batch(hfq_ctx *ctx, const double *dP, double *dJ, int nb, double fac, void *stream);
 
 /* One Fock-build step as the reference's fock_builder issues it (src/diatomic/main.cpp:413-426:
  * J = coulomb(P); K = exchange(P/2) back to back): J = coulomb(P) and K = exchange(kscale * P) from a

@@ -1,0 +1,72 @@
+"""Config 5 (batched SAP potentials, gen_sap_table workload): the batched spherically averaged SCF on the GPU
+(helfem_b200/sap.py: hfq_coulomb_radial_batch + the radial grid of a batch context) against the oracle restatement of
+the reference's Fock build (oracle/scf.py::sadatom_rks, src/sadatom/scf.cpp:145-283; pinned on gensap-He-lda / -hf in
+tests/test_oracle.py), atom by atom: total energies to 1e-9 Eh, the effective-potential table to 1e-8."""
+import numpy as np
+import pytest
+
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_atom(Z, ol):
+    from oracle import sadatom as osad
+    from oracle import scf, xc
+    from helfem_b200.sap import shell_occupations
+    lmax = max(l for l in range(4) if ol[l] > 0)
+    ob = cases.oracle_atomic(Z, lmax, 0, 5)
+    rb = ob.radial
+    S = rb.assemble(lambda iel: rb.radial_integral(0, iel))
+    Vn = -Z * rb.assemble(lambda iel: rb.radial_integral(-1, iel))
+    occs = [[o for o in shell_occupations(ol[l], l, 8) if o > 0] for l in range(lmax + 1)]
+    r = scf.sadatom_rks(osad.SadatomBasis(ob, lmax), osad.SadatomDFTGrid(ob, lmax), S, rb.kinetic(), rb.kinetic_l(), Vn, occs,
+                        [xc.XC_LDA_X], exx=False)
+    return ob, lmax, r
+
+
+def test_batched_sap_scf_matches_oracle(hb, tmp_path):
+    from oracle import sadatom as osad
+    from helfem_b200 import sap
+    occ, sym = sap.ground_state_occupations()
+    zs = [1, 2, 10, 15, 36]                      # H (half-filled 1s), closed shells, P (open p shell: fractional), Kr (s, p, d)
+    batch = sap.SadatomBatchSCF(zs)
+    res = batch.run()
+    assert bool(batch.converged.all())
+    for a, Z in enumerate(zs):
+        ob, lmax, ro = _oracle_atom(Z, occ[Z])
+        assert abs(res["E"][a] - ro["E"]) < 1e-9 * max(1.0, abs(ro["E"])), (Z, res["E"][a], ro["E"])
+        assert abs(res["XC"][a] - ro["XC"]) < 1e-7 * abs(ro["XC"]) and abs(res["Coulomb"][a] - ro["Coulomb"]) < 1e-7 * abs(ro["Coulomb"])
+        assert abs(res["Nel"][a] - Z) < 1e-9
+        tab = batch.sap_table(a)
+        otab = osad.SapTable(ob, Z).table([np.asarray(P) for P in ro["Pl"]])
+        assert tab.shape == otab.shape == (5 * 75 + 1, 9)
+        scale = np.maximum(np.abs(otab).max(axis=0), 1e-300)
+        assert np.max(np.abs(tab - otab) / scale) < 1e-7, Z      # both SCFs stop at 1e-7 in the commutator
+    paths = batch.write_results(str(tmp_path))
+    first = open(paths[0]).read().splitlines()
+    assert len(first) == 376 and len(first[0]) == 9 * 25        # " %24.16e" per entry (src/general/eigen_io.h:64-101)
+    back = np.loadtxt(paths[0])
+    assert np.allclose(back, batch.sap_table(0), rtol=1e-15, atol=0)
+
+
+def test_batched_radial_coulomb_matches_single(hb):
+    """hfq_coulomb_radial_batch == 4 pi * hfq_coulomb of an lmax = 0 atomic context, density by density."""
+    import ctypes
+    import torch
+    nb = 5
+    tabs = hb.Tables.sadatom_batch(3, nb, 3)
+    basis = hb.TablesBasis(tabs)
+    single = hb.AtomicTwoDBasis(1, 0, 0, 3).compute_tei()
+    N = tabs.Nrad
+    rng = np.random.default_rng(5)
+    P = np.stack([cases.random_density(N, 2, 40 + i) * rng.uniform(0.5, 2.0) for i in range(nb)])
+    dP = torch.from_numpy(P).cuda()
+    dJ = torch.empty_like(dP)
+    hb._check(hb.lib().hfq_coulomb_radial_batch(basis._context(), dP.data_ptr(), dJ.data_ptr(), nb, 1.0, None))
+    torch.cuda.synchronize()
+    for i in range(nb):
+        ref = single.coulomb(P[i])          # atomic coulomb of an s-only density: G(0,0,0,0,0)^2 4 pi J_0 = J_0
+        assert cases.relerr(dJ[i].cpu().numpy(), 4.0 * np.pi * ref) < 1e-12
+    with pytest.raises(ValueError):
+        basis.exchange(np.zeros((basis.Nbf(), basis.Nbf())))
