@@ -145,7 +145,9 @@ class SadatomBatchSCF:
         C = self.X @ c
         return (C * self.occ[:, :, None, :]) @ C.transpose(-1, -2)
 
-    def run(self, maxit=100, conv=1e-10, errtol=1e-7, verbose=False):
+    def run(self, maxit=150, conv=1e-10, errtol=1e-7, verbose=False, damp_above=0.3):
+        """damp_above: an atom whose largest commutator element exceeds it takes a damped Roothaan step (30 % of the
+        new density) instead of the DIIS extrapolation."""
         torch = self.torch
         nb, nl, N = self.nb, self.nl, self.N
         H0 = (self.T[None, None] + self.ll1[None, :, None, None] * self.Tl[None, None]
@@ -193,10 +195,12 @@ class SadatomBatchSCF:
             except Exception:
                 c, ok = None, torch.zeros(nb, dtype=torch.bool, device=self.dev)
             Fd = F
+            far = emax > damp_above
             if c is not None:
                 mix = (torch.stack(hist_F, dim=1) * c[:, :, None, None, None]).sum(dim=1)
-                Fd = torch.where(ok[:, None, None, None], mix, F)
-            Pl = self._densities(Fd)
+                Fd = torch.where((ok & ~far)[:, None, None, None], mix, F)
+            Pn = self._densities(Fd)
+            Pl = torch.where(far[:, None, None, None], 0.7 * Pl + 0.3 * Pn, Pn)
         self.converged = done
         return {k: v.cpu().numpy() for k, v in self.energies.items()}
 

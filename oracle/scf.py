@@ -19,10 +19,12 @@ def sinvh(S):
     return X * d[:, None]
 
 
-def rhf(S, H0, coulomb, exchange, nocc_by_block, blocks, maxit=60, conv=1e-10, verbose=False):
+def rhf(S, H0, coulomb, exchange, nocc_by_block, blocks, maxit=60, conv=1e-10, verbose=False, damp_above=None):
     """Restricted closed-shell HF with fixed occupations per symmetry block.
 
     blocks: list of index arrays; nocc_by_block: doubly-occupied count each.
+    damp_above: while the largest commutator element exceeds it, the density is mixed (30 % new) instead of
+    extrapolated (a poor core-Hamiltonian guess, e.g. N2, sends plain DIIS astray).
     Returns dict of energy components (Ekin etc. need T,V passed via H0 split
     by the caller) and the density P (total, Pa+Pb).
     """
@@ -52,25 +54,19 @@ def rhf(S, H0, coulomb, exchange, nocc_by_block, blocks, maxit=60, conv=1e-10, v
         E1 = np.sum(P * H0)
         E = E1 + Ecoul + Exx
         err = F @ P @ S - S @ P @ F
-        Fs.append(F); Es.append(err)
-        Fs, Es = Fs[-8:], Es[-8:]
+        emax = np.max(np.abs(err))
         if verbose:
-            print(it, E, np.max(np.abs(err)))
-        if abs(E - Eold) < conv and np.max(np.abs(err)) < 1e-7:
+            print(it, E, emax)
+        if abs(E - Eold) < conv and emax < 1e-7:
             break
         Eold = E
-        m = len(Fs)
-        B = -np.ones((m + 1, m + 1)); B[m, m] = 0.0
-        for a in range(m):
-            for b in range(m):
-                B[a, b] = np.sum(Es[a] * Es[b])
-        rhs = np.zeros(m + 1); rhs[m] = -1.0
-        try:
-            c = np.linalg.solve(B, rhs)[:m]
-            Fd = sum(ci * Fi for ci, Fi in zip(c, Fs))
-        except np.linalg.LinAlgError:
-            Fd = F
-        P = density(Fd)
+        if damp_above is not None and emax > damp_above:
+            Fs, Es = [], []
+            P = 0.7 * P + 0.3 * density(F)
+            continue
+        Fs.append(F); Es.append(err)
+        Fs, Es = Fs[-8:], Es[-8:]
+        P = density(_diis(Fs, Es, F))
     return {"E": E, "E1": E1, "Coulomb": Ecoul, "Exx": Exx, "P": P, "J": J, "K": K, "iterations": it + 1}
 
 

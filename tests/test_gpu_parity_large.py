@@ -199,3 +199,27 @@ def test_n2_headline_size_sampled_blocks(hb):
     # blocks off the m-diagonal are exactly zero (the reference never touches them for this density)
     mv = np.repeat(T.mval, [T.Nrad - (1 if m else 0) for m in T.mval])
     assert not K[mv[:, None] != mv[None, :]].any()
+
+
+def test_n2_rhf_device_scf_matches_oracle_scf(hb):
+    """N2 RHF at the shape of the reference's diatomic-N2-hf-r case (tests/cases.json: Rbond 2.07, nelem 3,
+    lmax = 13,9, 7 doubly occupied orbitals; the case is weekly-tier and has no recorded value): the device-resident
+    SCF (helfem_b200/scf.py: GPU J, K, grid Nel, solver on the device) against the oracle SCF (numpy setup, C J/K)
+    to 1e-10 Eh (BASELINE.json north_star)."""
+    from oracle import cjk, scf
+    from helfem_b200.scf import DeviceRHF
+    ob = cases.oracle_diatomic(7, 7, 2.07, (13, 9), 3)
+    C = cjk.DiatomicCaches.from_oracle(ob)
+    cjk.use_all_cores()
+    S, T, V = ob.overlap(), ob.kinetic(), ob.nuclear()
+    blocks = cases.m_blocks(ob.mval, ob.Nrad(), True)
+    ms = sorted(set(int(m) for m in ob.mval))
+    ro = scf.rhf(S, T + V, C.coulomb, C.exchange, [5 if m == 0 else 1 for m in ms], blocks, damp_above=0.3, maxit=150)
+    basis = hb.DiatomicTwoDBasis(7, 7, 2.07, [13, 9], 3).compute_tei()
+    rd = DeviceRHF(basis, 7, Enucr=49.0 / 2.07, occ_by_m={0: 5, 1: 1, -1: 1}).run()
+    assert abs(rd["E_electronic"] - ro["E"]) < 1e-10 * abs(ro["E"]), (rd["E_electronic"], ro["E"])
+    assert abs(rd["Coulomb"] - ro["Coulomb"]) < 1e-6 and abs(rd["Exx"] - ro["Exx"]) < 1e-6
+    assert abs(rd["Nel"] - 14.0) < 1e-9
+    # Aufbau over the blocks finds the same state (1 sigma_g .. 3 sigma_g + pi_u)
+    ra = DeviceRHF(basis, 7, Enucr=49.0 / 2.07).run()
+    assert abs(ra["E_electronic"] - ro["E"]) < 1e-9 * abs(ro["E"])
