@@ -41,7 +41,7 @@ EXPORTED_SYMBOLS = [
     "hfq_tables_destroy", "hfq_create", "hfq_destroy", "hfq_nbf", "hfq_set_absm_symmetric", "hfq_coulomb",
     "hfq_exchange", "hfq_coulomb_device", "hfq_exchange_device", "hfq_last_timings", "hfq_exchange_output_pattern",
     "hfq_coulomb_output_pattern",
-    "hfq_tables_sadatom_batch", "hfq_coulomb_radial_batch", "hfq_set_host_threads", "hfq_fock_build", "hfq_fock_build_device", "hfq_comm_unique_id", "hfq_comm_init", "hfq_comm_size", "hfq_shard_assign",
+    "hfq_tables_sadatom_batch", "hfq_coulomb_radial_batch", "hfq_syev_batch", "hfq_set_host_threads", "hfq_fock_build", "hfq_fock_build_device", "hfq_comm_unique_id", "hfq_comm_init", "hfq_comm_size", "hfq_shard_assign",
     "hfq_coulomb_exchange", "hfq_coulomb_exchange_device", "hfq_grid_attach", "hfq_grid_npoints", "hfq_grid_density", "hfq_grid_fxc", "hfq_eval_fxc",
 ]
 
@@ -94,6 +94,7 @@ def lib():
     L.hfq_coulomb_exchange_device.argtypes = [vp, vp, i64, cd, vp, i64, vp, i64, ci, ci, vp]
     L.hfq_tables_sadatom_batch.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ci, cd, ci, cd, ci]
     L.hfq_coulomb_radial_batch.argtypes = [vp, vp, vp, ci, cd, vp]
+    L.hfq_syev_batch.argtypes = [vp, vp, ci, i64, vp]
     L.hfq_set_host_threads.argtypes = [ci]
     L.hfq_fock_build.argtypes = [vp, vp, i64, cd, vp, i64, vp, i64, ci, ci, vp, i64, vp, vp, cd]
     L.hfq_fock_build_device.argtypes = [vp, vp, i64, cd, vp, i64, vp, i64, ci, ci, vp, i64, vp, vp, cd, vp]

@@ -621,6 +621,18 @@ int hfq_coulomb_radial_batch(hfq_ctx *ctx, const double *dP, double *dJ, int nb,
   });
 }
 
+namespace hfq {
+void syev_batch(double *dA, double *dW, int n, int64_t nb, cudaStream_t st);
+}
+
+int hfq_syev_batch(double *dA, double *dW, int n, int64_t nb, void *stream) {
+  if (!dA || !dW || n < 1 || nb < 0) return fail(HFQ_ERR_INVALID, "hfq_syev_batch: invalid argument");
+  return guarded([&] {
+    hfq::syev_batch(dA, dW, n, nb, (cudaStream_t)stream);
+    return HFQ_OK;
+  });
+}
+
 int hfq_set_host_threads(int n) {
   if (n < 1) return fail(HFQ_ERR_INVALID, "hfq_set_host_threads: n < 1");
   omp_set_num_threads(n);

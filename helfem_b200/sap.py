@@ -98,6 +98,8 @@ class SadatomBatchSCF:
         self.Hc = torch.zeros((nb * self.nl, N + 1, N), **f64)
         self.rho = torch.zeros(self.npts, **f64)
         self.launches = 0
+        self._tab_tables = None
+        self.timing = {"eigh": 0.0, "xc": 0.0, "coulomb": 0.0, "other": 0.0}
 
     # ---- the two native batched operators -----------------------------------------------------------------------
     def xc(self, Pl):
@@ -136,14 +138,74 @@ class SadatomBatchSCF:
         self.launches += 1
         return J
 
+    def local_potential(self, v):
+        """Matrix of a local radial potential per atom: v (nb, nel_fe * nquad) at the grid's radial points ->
+        (nb, N, N) with <B_i| v |B_j>, assembled by the grid engine (used for the initial guess)."""
+        torch = self.torch
+        nb, N = self.nb, self.N
+        vp = v.view(nb, self.nel_fe, self.nquad).permute(1, 0, 2).contiguous().view(-1)   # point = (element, atom, node)
+        self.Pc.zero_()
+        nel, ekin = ctypes.c_double(), ctypes.c_double()
+        _check(lib().hfq_grid_density(self.ctx, self.Pc.data_ptr(), N, None, 0, 0, None, None, None, None, None,
+                                      ctypes.byref(nel), ctypes.byref(ekin)))
+        e = ctypes.c_double()
+        _check(lib().hfq_grid_fxc(self.ctx, 0, 1, None, vp.data_ptr(), None, None, None, self.Hc.data_ptr(), N, None, 0,
+                                  ctypes.byref(e)))
+        H = self.Hc[:, :N, :].transpose(1, 2).reshape(nb, self.nl, N, N)
+        return H[:, 0] / (4.0 * np.pi)
+
+    def radii(self):
+        """Radial quadrature points (nel_fe * nquad), element by element."""
+        if self._tab_tables is None:
+            self._tab_tables = Tables.sadatom(1, 0, self.tables.Nel)
+        z = np.zeros((self.N, self.N))
+        need = int(lib().hfq_sap_table(self._tab_tables._h, z.ctypes.data, None, 1, 0, None, 0))
+        out = np.zeros(need)
+        rows = int(lib().hfq_sap_table(self._tab_tables._h, z.ctypes.data, None, 1, 0, out.ctypes.data, need))
+        return out.reshape(9, rows)[0, 1:]
+
+    def guess_potential(self):
+        """Thomas-Fermi screened nuclear attraction (Latter's fit of the TF function), never weaker than -1/r:
+        the starting point of the SCF (the reference starts from its tabulated SAP potential, --iguess=2)."""
+        torch = self.torch
+        r = torch.tensor(self.radii(), dtype=torch.float64, device=self.dev)[None, :]
+        Z = self.Z[:, None]
+        x = r / (0.88534138 * Z ** (-1.0 / 3.0))
+        sx = x.sqrt()
+        phi = 1.0 / (1.0 + 0.02747 * sx + 1.243 * x - 0.1486 * x * sx + 0.2302 * x * x + 0.007298 * x * x * sx + 0.006944 * x ** 3)
+        return -torch.maximum(Z * phi, torch.ones_like(phi)) / r
+
     # ---- SCF -------------------------------------------------------------------------------------------------
+    def _eigh(self, Fo):
+        """Eigenvectors of the (nb, nl, N, N) symmetric matrices, ascending eigenvalues: one CTA per matrix
+        (hfq_syev_batch, cyclic Jacobi in shared memory)."""
+        torch = self.torch
+        V = Fo.contiguous().clone()
+        W = torch.empty(V.shape[:-1], dtype=torch.float64, device=self.dev)
+        _check(lib().hfq_syev_batch(V.data_ptr(), W.data_ptr(), self.N, V.shape[0] * V.shape[1],
+                                    torch.cuda.current_stream().cuda_stream))
+        self.launches += 1
+        order = torch.argsort(W, dim=-1)
+        return torch.gather(V, -1, order[..., None, :].expand_as(V))
+
     def _densities(self, F):
         """F: (nb, nl, N, N) -> per-l densities P_l = C occ C^T, C = X c (scf.cpp:119-130)."""
-        torch = self.torch
+        t0 = self._tick()
         Fo = self.X.T @ F @ self.X
-        _, c = torch.linalg.eigh(Fo)
-        C = self.X @ c
-        return (C * self.occ[:, :, None, :]) @ C.transpose(-1, -2)
+        C = self.X @ self._eigh(Fo)
+        P = (C * self.occ[:, :, None, :]) @ C.transpose(-1, -2)
+        self._tock("eigh", t0)
+        return P
+
+    def _tick(self):
+        import time
+        self.torch.cuda.synchronize()
+        return time.perf_counter()
+
+    def _tock(self, key, t0):
+        import time
+        self.torch.cuda.synchronize()
+        self.timing[key] += time.perf_counter() - t0
 
     def run(self, maxit=150, conv=1e-10, errtol=1e-7, verbose=False, damp_above=0.3):
         """damp_above: an atom whose largest commutator element exceeds it takes a damped Roothaan step (30 % of the
@@ -152,14 +214,19 @@ class SadatomBatchSCF:
         nb, nl, N = self.nb, self.nl, self.N
         H0 = (self.T[None, None] + self.ll1[None, :, None, None] * self.Tl[None, None]
               + self.Z[:, None, None, None] * self.V1[None, None])
-        Pl = self._densities(H0)
+        Vg = self.local_potential(self.guess_potential())
+        Pl = self._densities(self.T[None, None] + self.ll1[None, :, None, None] * self.Tl[None, None] + Vg[:, None])
         hist_F, hist_e = [], []
         Eold = torch.zeros(nb, dtype=torch.float64, device=self.dev)
         done = torch.zeros(nb, dtype=torch.bool, device=self.dev)
         for it in range(maxit):
             Prad = Pl.sum(dim=1)
+            t0 = self._tick()
             XC, Exc, Nel = self.xc(Pl)
+            self._tock("xc", t0)
+            t0 = self._tick()
             J = self.coulomb(Prad)
+            self._tock("coulomb", t0)
             Ekin = (Pl * self.T).sum(dim=(1, 2, 3)) + (self.ll1[None, :] * (Pl * self.Tl).sum(dim=(2, 3))).sum(dim=1)
             Enuc = self.Z * (Prad * self.V1).sum(dim=(1, 2))
             Ecoul = 0.5 * (Prad * J).sum(dim=(1, 2))
@@ -209,12 +276,18 @@ class SadatomBatchSCF:
         """effective_potential_table of atom a (src/sadatom/main.cpp:55-107): (Nel * nquad + 1) x 9."""
         z = self.zs[a]
         lmax = max(l for l in range(self.nl) if self.occ_l[a][l] > 0)
-        t = Tables.sadatom(z, lmax, self.tables.Nel)
+        if self._tab_tables is None:
+            # the table needs the radial basis only (the screening integrals are evaluated by quadrature): one
+            # set of tables serves every atom, the nuclear charge enters through the last column alone
+            self._tab_tables = Tables.sadatom(1, 0, self.tables.Nel)
+        t = self._tab_tables
         Pl = np.ascontiguousarray(self.Pl[a, :lmax + 1].transpose(-1, -2).cpu().numpy())   # column-major blocks
         need = int(lib().hfq_sap_table(t._h, Pl.ctypes.data, None, lmax + 1, 1, None, 0))
         out = np.zeros(need)
         rows = int(lib().hfq_sap_table(t._h, Pl.ctypes.data, None, lmax + 1, 1, out.ctypes.data, need))
-        return out.reshape(9, rows).T
+        tab = out.reshape(9, rows).T
+        tab[:, 8] = z - (tab[:, 5] + tab[:, 6])     # Z_eff = Z - r (V_H + V_xc), src/sadatom/main.cpp:98
+        return tab
 
     def write_results(self, directory):
         """result_<El>.dat per atom, the reference's raw-ascii layout (io::write_raw_ascii, src/general/eigen_io.h:92-101:

@@ -193,6 +193,12 @@ int hfq_exchange_device(hfq_ctx *ctx, const double *dP, int64_t ldP, double *dK,
  * atomic / sadatom radial basis. */
 int hfq_coulomb_radial_batch(hfq_ctx *ctx, const double *dP, double *dJ, int nb, double fac, void *stream);
 
+/* Batched symmetric eigensolver for small matrices on the current device (cyclic Jacobi, one CTA per matrix, n <= 118):
+ * dA = nb row-major n x n symmetric matrices, overwritten by the eigenvectors (V[i][j] = component i of vector j);
+ * dW = nb x n eigenvalues, NOT sorted.  Caller-side helper of the batched atomic SCFs (the reference leaves the
+ * eigenproblems to OpenOrbitalOptimizer / Eigen). */
+int hfq_syev_batch(double *dA, double *dW, int n, int64_t nb, void *stream);
+
 /* One Fock-build step as the reference's fock_builder issues it (src/diatomic/main.cpp:413-426:
  * J = coulomb(P); K = exchange(P/2) back to back): J = coulomb(P) and K = exchange(kscale * P) from a
  * single upload and a single packed copy of P; the host version copies J back while K is being built.
