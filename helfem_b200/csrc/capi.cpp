@@ -18,6 +18,10 @@
 #include "grid.h"
 #include "tables.h"
 
+namespace hfq {
+void syev_batch(double *dA, double *dW, int n, int64_t nb, cudaStream_t st);   // solver.cu
+}
+
 struct hfq_tables {
   hfq::BasisTables t;
 };
@@ -619,10 +623,6 @@ int hfq_coulomb_radial_batch(hfq_ctx *ctx, const double *dP, double *dJ, int nb,
     ctx->eng->coulomb_radial_batch(dP, dJ, nb, N * N, fac, stream ? (cudaStream_t)stream : ctx->eng->stream());
     return HFQ_OK;
   });
-}
-
-namespace hfq {
-void syev_batch(double *dA, double *dW, int n, int64_t nb, cudaStream_t st);
 }
 
 int hfq_syev_batch(double *dA, double *dW, int n, int64_t nb, void *stream) {

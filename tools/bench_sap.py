@@ -86,7 +86,7 @@ def main():
     line = {"metric": "SAP atoms/s (spherically averaged LDA-x SCF + effective-potential table)", "value": len(zs_all) / (t_scf + t_tab),
             "unit": "atoms/s", "n_gpus": world, "elements": len(zs_all), "scf_s": t_scf, "tables_s": t_tab, "setup_s": t_setup,
             "iterations": iters, "all_converged": conv, "scaling": "strong (elements dealt round-robin, no collective)",
-            "kernel_launches_native": batch.launches, "cpu_baseline": cpu, "results": os.path.relpath(out, ROOT),
+            "kernel_launches_native": batch.launches, "phase_seconds": batch.timing, "cpu_baseline": cpu, "results": os.path.relpath(out, ROOT),
             "E_Rn" if args.zmax >= 86 and 86 in zs else "E_last": float(res["E"][zs.index(max(zs))])}
     print(json.dumps(line))
     if world > 1:
