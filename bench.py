@@ -377,6 +377,45 @@ def main():
     ms_step = float(tms.item()) / args.steps
     value = 1e3 / ms_step
 
+    # ---- secondary figure: the DFT flavour of the grid work (density -> Slater exchange on the device -> assembly of
+    #      the XC matrix), device-resident, with the HBM model of SURVEY.md section 8d (separable evaluation)
+    vxc_dft = None
+    if world == 1:
+        dH = torch.empty_like(dP)
+        ex, ne, ek = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+
+        def vxc_call():
+            hb._check(hb.lib().hfq_eval_fxc(basis._context(), 1, 0, dP.data_ptr(), n, None, 0, dH.data_ptr(), n, None, 0,
+                                            ctypes.byref(ex), ctypes.byref(ne), ctypes.byref(ek), 1, 1e-12))
+        for _ in range(3):
+            vxc_call()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            vxc_call()
+        torch.cuda.synchronize()
+        t_vxc = (time.perf_counter() - t0) / args.steps
+        npts = lang * 75 * args.nelem
+        mv = np.asarray(T.mval)
+        coupled = int(sum((mv == m).sum() ** 2 for m in set(mv.tolist())))
+        alg_bytes = (coupled * T.Nrad ** 2 * 8          # the coupled (same-m) blocks of P
+                     + n * n * 8                         # H: the call defines the whole dense matrix
+                     + args.nelem * 75 * 15 * 8 * 2      # radial tables (value, derivative-free LDA: F only, both stages)
+                     + T.Nang * lang * 8                 # angular table
+                     + (1 + 1) * 8 * npts + 4 * 8 * npts)   # rho in / v_rho out, weights and scale factors
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        hbm = peaks.get("hbm_gbs", 6650.0)
+        vxc_dft = {"workload": "N2 LDA-exchange Vxc build on the pure-m grid (hfq_eval_fxc, x_func = 1), %d points, device-resident" % npts,
+                   "ms_per_build": 1e3 * t_vxc, "builds_per_s": 1.0 / t_vxc,
+                   "roofline": {"bound": "hbm", "achieved": alg_bytes / t_vxc / 1e9, "peak": hbm, "unit": "GB/s",
+                                "frac": alg_bytes / t_vxc / 1e9 / hbm, "alg_bytes": alg_bytes,
+                                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback of B200_PROFILING.md",
+                                "note": "separable-evaluation byte model of SURVEY.md 8d; 93 % of the bytes are the dense H the call "
+                                        "must define (10 071 of 130 321 blocks are non-zero); the chain is 10 small launches "
+                                        "(latency-bound), not a bandwidth-bound stream"},
+                   "Exc": ex.value, "Nel": ne.value}
+        del dH
+
     if args.profile_mode:
         print("profile-mode: %.2f ms/step (not a bench value)" % ms_step)
         return
@@ -489,6 +528,7 @@ def main():
                              "row ranges of its column slice of J and K and zero-fills the rest; host barrier at the end"),
                     "speculative_hits": spec_hits},
             "gpu_launches": int(acc["launches"]), "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,
+            "vxc_dft": vxc_dft,
             "clocks": sampler.summary(),
             "setup": {"host_compute_tei_s": t_setup, "device_upload_s": t_upload, "Nbf": n, "channels": T.nlm}}
     print(json.dumps(line))

@@ -508,8 +508,7 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
   // opt-in shared memory sizes
   CK(cudaFuncSetAttribute(dev::k_offdiag_mma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
   CK(cudaFuncSetAttribute(dev::k_offdiag_mma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-  CK(cudaFuncSetAttribute(dev::k_offdiag_ring<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dev::offdiag_ring_smem<1>()));
-  CK(cudaFuncSetAttribute(dev::k_offdiag_ring<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dev::offdiag_ring_smem<2>()));
+
   {
     s.tg_maxM = 0;
     for (int e = 0; e < t.Nel; e++) s.tg_maxM = std::max(s.tg_maxM, t.en[e] * t.en[e]);
@@ -1239,22 +1238,13 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
     CK(cudaEventRecord(s.ev[4], st));
     if (bt.noitems) {
       const dim3 grid(s.NB / 16, (unsigned)bt.noitems);
-      static const bool legacy = getenv("HFQ_OFFDIAG_LEGACY") && atoi(getenv("HFQ_OFFDIAG_LEGACY"));
-      if (legacy) {
-        const size_t smem = (size_t)(t.nch * 16 * (16 * 20 + 4) + t.nch * 16 * 20 + 16 * (t.nch * 16 + 4)) * sizeof(double);
-        if (t.nch == 1)
-          dev::k_offdiag_mma<1><<<grid, 256, smem, st>>>(s.bd, bt.oitems.p, bt.oentries.p, s.d_R.p, s.d_small.p,
-                                                      s.d_big.p, s.d_blk_off.p);
-        else
-          dev::k_offdiag_mma<2><<<grid, 256, smem, st>>>(s.bd, bt.oitems.p, bt.oentries.p, s.d_R.p, s.d_small.p,
-                                                      s.d_big.p, s.d_blk_off.p);
-      } else if (t.nch == 1) {
-        dev::k_offdiag_ring<1><<<grid, 512, dev::offdiag_ring_smem<1>(), st>>>(s.bd, bt.oitems.p, bt.oentries.p, s.d_R.p,
-                                                                              s.d_small.p, s.d_big.p, s.d_blk_off.p);
-      } else {
-        dev::k_offdiag_ring<2><<<grid, 512, dev::offdiag_ring_smem<2>(), st>>>(s.bd, bt.oitems.p, bt.oentries.p, s.d_R.p,
-                                                                              s.d_small.p, s.d_big.p, s.d_blk_off.p);
-      }
+      const size_t smem = (size_t)(t.nch * 16 * (16 * 20 + 4) + t.nch * 16 * 20 + 16 * (t.nch * 16 + 4)) * sizeof(double);
+      if (t.nch == 1)
+        dev::k_offdiag_mma<1><<<grid, 256, smem, st>>>(s.bd, bt.oitems.p, bt.oentries.p, s.d_R.p, s.d_small.p,
+                                                    s.d_big.p, s.d_blk_off.p);
+      else
+        dev::k_offdiag_mma<2><<<grid, 256, smem, st>>>(s.bd, bt.oitems.p, bt.oentries.p, s.d_R.p, s.d_small.p,
+                                                    s.d_big.p, s.d_blk_off.p);
       CK(cudaGetLastError());
     }
     CK(cudaEventRecord(s.ev[5], st));

@@ -150,18 +150,19 @@ __global__ void k_grid_weights(GridDev g, int flags, const double *__restrict__ 
 }
 
 // H[(a,f+r),(b,f+c)] = sum over elements containing both radial functions of
-//   Hs[e][(a,b)][(r,c)] + Hx[e][(a,b)][(r,c)] + Hx[e][(b,a)][(c,r)]        grid (Nang, Nang)
+//   Hs[e][(a,b)][(r,c)] + Hx[e][(a,b)][(r,c)] + Hx[e][(b,a)][(c,r)]
+// one CTA per COUPLED angular pair (grid NA2); the blocks of uncoupled pairs are exactly zero and are cleared by the
+// caller at memset speed (pure-m grid: 10 071 of 130 321 blocks are coupled for N2)
 __global__ void k_grid_unpack(GridDev g, const double *__restrict__ Hs, const double *__restrict__ Hx,
                               double *__restrict__ H, int64_t ld) {
-  const int a = blockIdx.x, b = blockIdx.y;
+  const int a = g.pair_a[blockIdx.x], b = g.pair_b[blockIdx.x];
   const int sa = g.ang_skip[a], sb = g.ang_skip[b];
-  const int pab = g.pair_of[a * g.Nang + b], pba = g.pair_of[b * g.Nang + a];
-  if (pab < 0 && g.skip_uncoupled) return;   // block-compact matrices (batched atoms) hold the coupled blocks only
+  const int pab = blockIdx.x, pba = g.pair_of[b * g.Nang + a];
   for (int idx = threadIdx.x; idx < g.Nrad * g.Nrad; idx += blockDim.x) {
     const int R = idx % g.Nrad, Cc = idx / g.Nrad;
     if (R < sa || Cc < sb) continue;
     double s = 0.0;
-    if (pab >= 0)
+    if (pba >= 0)
       for (int e = 0; e < g.Nel; e++) {
         const int r = R - g.efirst[e], c = Cc - g.efirst[e];
         if (r < 0 || c < 0 || r >= g.en[e] || c >= g.en[e]) continue;
@@ -620,61 +621,64 @@ void GridEngine::assemble(int flags, bool beta, bool exc, bool gga, bool vtau, b
     if (gga) { combos.push_back(1); combos.push_back(2); combos.push_back(3); }
     if (use_vtl) { combos.push_back(4); combos.push_back(5); combos.push_back(6); }
     if (vl) { combos.push_back(7); combos.push_back(8); combos.push_back(9); }
-    std::vector<dev::GemmItem> items;
-    std::vector<dev::GemmEntry> entries;
     const size_t tsz = (size_t)g.Nel * g.nang * g.NN;
-    for (int j : combos)
-      for (int e = 0; e < g.Nel; e++) {
-        dev::GemmItem it{};
-        it.C = s.d_T.p + (size_t)j * tsz + (size_t)e * g.nang * g.NN;
-        it.browoff = s.d_bo_t.p;
-        it.M = g.nang;
-        it.N = g.NN;
-        it.K = g.nrad;
-        it.ent0 = (int)entries.size();
-        const int cj = j >= 8 ? 7 : j;
-        entries.push_back(dev::GemmEntry{s.d_C.p + (size_t)cj * N + (size_t)e * g.npe,
-                                         s.d_RRT.p + ((size_t)e * NRR + rrt[j]) * g.nrad * g.NN, g.nrad});
-        it.ent1 = (int)entries.size();
-        it.accumulate = 0;
-        it.ldc = g.NN;
-        it.alpha = 1.0;
-        items.push_back(it);
-      }
-    s.gemm(items, entries, g.nang, g.NN);
-    // stage 2: Hs / Hx [e][(a,b)][(r,c)] = sum_j YY_j . T_j[e]
-    items.clear();
-    entries.clear();
-    for (int grp = 0; grp < 2; grp++)
-      for (int e = 0; e < g.Nel; e++) {
-        dev::GemmItem it{};
-        it.C = (grp ? s.d_Hx.p : s.d_Hs.p) + (size_t)e * g.NA2 * g.NN;
-        it.browoff = s.d_bo_t.p;
-        it.M = g.NA2;
-        it.N = g.NN;
-        it.K = g.nang;
-        it.ent0 = (int)entries.size();
-        for (int j : combos) {
-          const bool sym = (j == 0 || (j >= 4 && j <= 6));
-          if (sym != (grp == 0)) continue;
-          entries.push_back(dev::GemmEntry{s.d_YY.p + (size_t)yyt[j] * g.NA2 * g.nang,
-                                           s.d_T.p + (size_t)j * tsz + (size_t)e * g.nang * g.NN, g.nang});
+    // the descriptors depend only on which terms are present (not on the spin: C and T are re-used per spin)
+    const int key = (gga ? 1 : 0) | (use_vtl ? 2 : 0) | (vl ? 4 : 0);
+    s.gemm_cached(300 + key, g.nang, g.NN, [&](std::vector<dev::GemmItem> &items, std::vector<dev::GemmEntry> &entries) {
+      for (int j : combos)
+        for (int e = 0; e < g.Nel; e++) {
+          dev::GemmItem it{};
+          it.C = s.d_T.p + (size_t)j * tsz + (size_t)e * g.nang * g.NN;
+          it.browoff = s.d_bo_t.p;
+          it.M = g.nang;
+          it.N = g.NN;
+          it.K = g.nrad;
+          it.ent0 = (int)entries.size();
+          const int cj = j >= 8 ? 7 : j;
+          entries.push_back(dev::GemmEntry{s.d_C.p + (size_t)cj * N + (size_t)e * g.npe,
+                                           s.d_RRT.p + ((size_t)e * NRR + rrt[j]) * g.nrad * g.NN, g.nrad});
+          it.ent1 = (int)entries.size();
+          it.accumulate = 0;
+          it.ldc = g.NN;
+          it.alpha = 1.0;
+          items.push_back(it);
         }
-        it.ent1 = (int)entries.size();
-        it.accumulate = 0;
-        it.ldc = g.NN;
-        it.alpha = 1.0;
-        items.push_back(it);   // an item without entries writes zeros
-      }
-    s.gemm(items, entries, g.NA2, g.NN);
+    });
+    // stage 2: Hs / Hx [e][(a,b)][(r,c)] = sum_j YY_j . T_j[e]
+    s.gemm_cached(400 + key, g.NA2, g.NN, [&](std::vector<dev::GemmItem> &items, std::vector<dev::GemmEntry> &entries) {
+      for (int grp = 0; grp < 2; grp++)
+        for (int e = 0; e < g.Nel; e++) {
+          dev::GemmItem it{};
+          it.C = (grp ? s.d_Hx.p : s.d_Hs.p) + (size_t)e * g.NA2 * g.NN;
+          it.browoff = s.d_bo_t.p;
+          it.M = g.NA2;
+          it.N = g.NN;
+          it.K = g.nang;
+          it.ent0 = (int)entries.size();
+          for (int j : combos) {
+            const bool sym = (j == 0 || (j >= 4 && j <= 6));
+            if (sym != (grp == 0)) continue;
+            entries.push_back(dev::GemmEntry{s.d_YY.p + (size_t)yyt[j] * g.NA2 * g.nang,
+                                             s.d_T.p + (size_t)j * tsz + (size_t)e * g.nang * g.NN, g.nang});
+          }
+          it.ent1 = (int)entries.size();
+          it.accumulate = 0;
+          it.ldc = g.NN;
+          it.alpha = 1.0;
+          items.push_back(it);   // an item without entries writes zeros
+        }
+    });
     double *H = sp ? Hb : Ha;
     const int64_t ld = sp ? ldHb : ldHa;
+    const bool sparse = g.NA2 < g.Nang * g.Nang && !g.skip_uncoupled;   // uncoupled blocks exist and belong to the matrix
     if (is_device_pointer(H)) {   // device matrix: written in place, with the caller's leading dimension
-      k_grid_unpack<<<dim3(g.Nang, g.Nang), 256, 0, s.st>>>(g, s.d_Hs.p, s.d_Hx.p, H, ld);
+      if (sparse) CK(cudaMemset2DAsync(H, (size_t)ld * sizeof(double), 0, n * sizeof(double), n, s.st));
+      k_grid_unpack<<<g.NA2, 256, 0, s.st>>>(g, s.d_Hs.p, s.d_Hx.p, H, ld);
       CK(cudaGetLastError());
     } else {
       s.d_H.alloc(n * n);
-      k_grid_unpack<<<dim3(g.Nang, g.Nang), 256, 0, s.st>>>(g, s.d_Hs.p, s.d_Hx.p, s.d_H.p, (int64_t)n);
+      if (sparse) CK(cudaMemsetAsync(s.d_H.p, 0, n * n * sizeof(double), s.st));
+      k_grid_unpack<<<g.NA2, 256, 0, s.st>>>(g, s.d_Hs.p, s.d_Hx.p, s.d_H.p, (int64_t)n);
       CK(cudaGetLastError());
       CK(cudaMemcpy2DAsync(H, ld * sizeof(double), s.d_H.p, n * sizeof(double), n * sizeof(double), n, cudaMemcpyDefault, s.st));
     }

@@ -610,7 +610,9 @@ k_offdiag_mma(BasisDev b, const OffItem *__restrict__ items, const OffEntry *__r
   // (2*lr, 2*lr+1) of row rl = 4*ks + lc as one 16-byte load: DMMA column tile nt therefore maps to
   // the blk columns 2*n + nt.  The next chunk is fetched into registers while the current one
   // feeds the tensor pipe (nothing else hides the HBM latency of this stream; an additional
-  // prefetch.global.L2 two chunks ahead was measured and did not help: 5.57 vs 5.31 ms).
+  // prefetch.global.L2 two chunks ahead was measured and did not help: 5.57 vs 5.31 ms; neither did a variant with
+  // one 16-warp CTA per SM and a 4-deep per-warp cp.async ring in shared memory, 96 KB in flight per SM:
+  // 6.38 vs 5.59 ms, profiles/r02i -- the CTA-wide barriers between the two stages cost more than the latency).
   auto fetch = [&](int e, int q, double2 (&pf)[4]) {
     const int slot = q / NAB, ab = q % NAB, ri = warp + 8 * slot;
     const bool ok = e < it.ent1 && ri < Ni;
@@ -717,162 +719,6 @@ k_offdiag_mma(BasisDev b, const OffItem *__restrict__ items, const OffEntry *__r
         double2 v;
         v.x = kacc[slot][mt][nt][0];
         v.y = kacc[slot][mt][nt][1];
-        if (it.accumulate) {
-          const double2 o = *reinterpret_cast<const double2 *>(c);
-          v.x += o.x;
-          v.y += o.y;
-        }
-        *reinterpret_cast<double2 *>(c) = v;
-      }
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------
-// Cross-element exchange, ring variant: the same two DMMA stages as k_offdiag_mma, but one CTA of 16 warps per SM
-// (warp w owns ri = w in stage 1 and rk = w in stage 2) and the once-read R stream goes through a per-warp
-// cp.async ring of RING_D chunks in shared memory instead of one chunk of registers: RING_D - 1 chunks (2 KB
-// each) are in flight per warp -- 16 x 3 x 2 KB = 96 KB per SM against the ~45 KB that 6.5 TB/s x 1 us needs --
-// so the tensor pipe no longer waits on HBM latency (k_offdiag_mma: 47 % pipe, long_scoreboard the top stall,
-// profiles/r01f_ncu_full_summary.txt).  A lane reads back exactly the bytes it copied: no intra-warp
-// synchronisation, conflict-free 16-byte accesses.
-// Shared memory: U[NCH][16 rk][LDK] + I[NCH][16][LDI] + J[16][LDJ] + ring[16 warps][RING_D][4 ks][32 lanes] double2
-// ---------------------------------------------------------------------------
-constexpr int OFF_RING_D = 4;
-template <int NCH>
-__host__ __device__ constexpr size_t offdiag_ring_smem() {
-  return (size_t)(NCH * 16 * (16 * 20 + 4) + NCH * 16 * 20 + 16 * (NCH * 16 + 4)) * sizeof(double) +
-         (size_t)16 * OFF_RING_D * 4 * 32 * sizeof(double2);
-}
-
-template <int NCH>
-__global__ void __launch_bounds__(512, 1)
-k_offdiag_ring(BasisDev b, const OffItem *__restrict__ items, const OffEntry *__restrict__ entries,
-               const double *__restrict__ R, const double *__restrict__ dsmall, const double *__restrict__ dbig,
-               const int64_t *__restrict__ blk_off) {
-  constexpr int BT = 16, LDU = BT + 4, LDK = 16 * LDU + 4, LDI = 16 + 4, LDJ = NCH * 16 + 4, NAB = NCH * NCH, D = OFF_RING_D;
-  extern __shared__ double sm[];
-  double *sU = sm;                          // [NCH][16 rk][LDK: 16 ri x LDU]
-  double *sI = sU + NCH * 16 * LDK;         // [NCH][16 rj][LDI]
-  double *sJ = sI + NCH * 16 * LDI;         // J[rk][b*16 + rl]
-  double2 *ring = reinterpret_cast<double2 *>(sJ + 16 * LDJ);
-  const OffItem it = items[blockIdx.y];
-  const int Ni = b.en[it.ei], Nj = b.en[it.ej], fi = b.efirst[it.ei], fj = b.efirst[it.ej];
-  const int blk0 = blockIdx.x * BT;
-  if (blk0 >= it.ncol) return;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int lr = lane >> 2, lc = lane & 3;
-  const int64_t gstride = (int64_t)b.NB;
-  for (int idx = tid; idx < NCH * 16 * LDK; idx += 512) sU[idx] = 0.0;
-  for (int idx = tid; idx < NCH * 16 * LDI; idx += 512) sI[idx] = 0.0;
-  for (int idx = tid; idx < 16 * LDJ; idx += 512) sJ[idx] = 0.0;
-  double kacc[2][2][2];   // [rj tile][blk tile][frag] of rk = warp
-#pragma unroll
-  for (int q = 0; q < 8; q++) (&kacc[0][0][0])[q] = 0.0;
-
-  // chunk g = (entry, a, b): the 16 (rl) x 16 (blk) block R_ab(ri = warp, :)[blk0 .. +16); a lane copies, for k-step
-  // ks, the two columns (2 lr, 2 lr + 1) of row rl = 4 ks + lc (16 bytes): DMMA column tile nt = columns 2 n + nt
-  double2 *myring = ring + (size_t)warp * D * 4 * 32 + lane;
-  const int nchunks = (it.ent1 - it.ent0) * NAB;
-  const bool row_ok = warp < Ni;
-  auto issue = [&](int g) {
-    if (g < nchunks) {
-      const int e = it.ent0 + g / NAB, ab = g % NAB;
-      const double *row = R + ((int64_t)entries[e].rslot * NAB * b.Npix + (int64_t)ab * b.Npix +
-                               (int64_t)(fi + (row_ok ? warp : 0)) * b.Nrad + fj) * gstride + blk0 + 2 * lr;
-      double2 *dst = myring + (size_t)(g % D) * 4 * 32;
-#pragma unroll
-      for (int ks = 0; ks < 4; ks++) {
-        const int rl = ks * 4 + lc;
-        const bool ok = row_ok && rl < Nj;
-        cp_async16(dst + ks * 32, ok ? row + (int64_t)rl * gstride : R, ok ? 16 : 0);
-      }
-    }
-    cp_async_commit();
-  };
-#pragma unroll
-  for (int g = 0; g < D - 1; g++) issue(g);
-
-  int g = 0;
-  for (int e = it.ent0; e < it.ent1; e++) {
-    const OffEntry en = entries[e];
-    const double *srcI = (it.ei > it.ej ? dbig : dsmall) + blk_off[en.ilm * b.Nel + it.ei];
-    const double *srcJ = (it.ei > it.ej ? dsmall : dbig) + blk_off[en.ilm * b.Nel + it.ej];
-    __syncthreads();   // previous stage 2 finished with sI/sU
-    for (int idx = tid; idx < NCH * Ni * Ni; idx += 512) {
-      const int ch = idx / (Ni * Ni), rem = idx % (Ni * Ni), ri = rem / Ni, rj = rem % Ni;   // I(rj,ri) column-major
-      sI[(ch * 16 + rj) * LDI + ri] = srcI[idx];
-    }
-    for (int idx = tid; idx < NCH * Nj * Nj; idx += 512) {
-      const int ch = idx / (Nj * Nj), rem = idx % (Nj * Nj), rl = rem / Nj, rk = rem % Nj;   // J(rk,rl) column-major
-      sJ[rk * LDJ + ch * 16 + rl] = srcJ[idx];
-    }
-    __syncthreads();
-    // ---- stage 1: ri = warp
-#pragma unroll
-    for (int a = 0; a < NCH; a++) {
-      double c[2][2][2];
-#pragma unroll
-      for (int q = 0; q < 8; q++) (&c[0][0][0])[q] = 0.0;
-#pragma unroll
-      for (int bb = 0; bb < NCH; bb++, g++) {
-        issue(g + D - 1);
-        cp_async_wait<D - 1>();   // chunk g has landed (this lane's own copies)
-        const double2 *cur = myring + (size_t)(g % D) * 4 * 32;
-        if (row_ok) {
-#pragma unroll
-          for (int ks = 0; ks < 4; ks++) {
-            const int rl = ks * 4 + lc;
-            const double2 v = cur[ks * 32];
-            const double a0 = sJ[lr * LDJ + bb * 16 + rl], a1 = sJ[(8 + lr) * LDJ + bb * 16 + rl];
-            dmma(c[0][0][0], c[0][0][1], a0, v.x);
-            dmma(c[0][1][0], c[0][1][1], a0, v.y);
-            dmma(c[1][0][0], c[1][0][1], a1, v.x);
-            dmma(c[1][1][0], c[1][1][1], a1, v.y);
-          }
-        }
-      }
-      if (row_ok) {
-        // fragment (row lr, tile columns 2lc, 2lc+1 of tiles 0/1) = blk columns 4lc .. 4lc+3
-#pragma unroll
-        for (int mt = 0; mt < 2; mt++) {
-          double *u = sU + (a * 16 + mt * 8 + lr) * LDK + warp * LDU + 4 * lc;
-          *reinterpret_cast<double2 *>(u) = make_double2(c[mt][0][0], c[mt][1][0]);
-          *reinterpret_cast<double2 *>(u + 2) = make_double2(c[mt][0][1], c[mt][1][1]);
-        }
-      }
-    }
-    __syncthreads();
-    // ---- stage 2: rk = warp
-    if (warp < Nj) {
-#pragma unroll
-      for (int a = 0; a < NCH; a++) {
-#pragma unroll
-        for (int ks = 0; ks < 4; ks++) {
-          const int ri = ks * 4 + lc;
-          const double a0 = sI[(a * 16 + lr) * LDI + ri], a1 = sI[(a * 16 + 8 + lr) * LDI + ri];
-          const double *u = sU + (a * 16 + warp) * LDK + ri * LDU + lr;
-          const double bf0 = u[0], bf1 = u[8];
-          dmma(kacc[0][0][0], kacc[0][0][1], a0, bf0);
-          dmma(kacc[0][1][0], kacc[0][1][1], a0, bf1);
-          dmma(kacc[1][0][0], kacc[1][0][1], a1, bf0);
-          dmma(kacc[1][1][0], kacc[1][1][1], a1, bf1);
-        }
-      }
-    }
-  }
-  cp_async_wait<0>();
-  if (warp < Nj) {
-#pragma unroll
-    for (int mt = 0; mt < 2; mt++) {
-      const int rj = mt * 8 + lr;
-      if (rj >= Ni) continue;
-#pragma unroll
-      for (int nt = 0; nt < 2; nt++) {
-        double *c = it.C + (int64_t)(rj * Nj + warp) * gstride + blk0 + nt * 8 + 2 * lc;
-        double2 v;
-        v.x = kacc[mt][nt][0];
-        v.y = kacc[mt][nt][1];
         if (it.accumulate) {
           const double2 o = *reinterpret_cast<const double2 *>(c);
           v.x += o.x;
