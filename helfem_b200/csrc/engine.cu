@@ -87,6 +87,7 @@ struct Engine::Impl {
   int64_t op_stride = 0;
   std::vector<int64_t> tperm_off;   // [nlm * Nel] offset of the tiled in-element kernel A_(ilm,e)
   std::vector<int64_t> tperm_tri_off;   // the same for the rows rj <= rk only (symmetric densities)
+  int prio_hi = 0;            // highest stream priority of the device
   bool radial_only = false;   // batch tables: see the constructor
   DevBuf<int> d_bchan;        // coulomb_radial_batch: channel / prefactor per batch entry
   DevBuf<double> d_bfac;
@@ -142,8 +143,14 @@ struct Engine::Impl {
 
 Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(device) {
   CK(cudaSetDevice(device));
-  CK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  // The engine's own stream carries the host-pointer calls and, in the fused device build, the DFT-grid chain next
+  // to the caller's stream: high priority, so that its small kernels are scheduled ahead of the thousands of queued
+  // CTAs of the exchange kernels instead of behind them (the same for the Coulomb and memset side streams).
+  int prio_lo = 0, prio_hi = 0;
+  CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  CK(cudaStreamCreateWithPriority(&stream_, cudaStreamNonBlocking, prio_hi));
   Impl &s = *p_;
+  s.prio_hi = prio_hi;
   for (auto &e : s.ev) CK(cudaEventCreate(&e));
   s.t = tin;
   const BasisTables &t = s.t;
@@ -670,7 +677,7 @@ void Engine::jk_dev(const double *dP, int64_t ldP, double kscale, double *dJ, in
   const double t_pack = ms_since();
   s.packed_valid = true;
   if (!s.j_stream) {
-    CK(cudaStreamCreateWithFlags(&s.j_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithPriority(&s.j_stream, cudaStreamNonBlocking, s.prio_hi));
     CK(cudaEventCreateWithFlags(&s.ev_packed, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&s.ev_jdone, cudaEventDisableTiming));
   }
@@ -821,7 +828,7 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
   // everything outside the computed sector pairs is exactly zero: K is cleared at memset speed on a second stream
   // while the (tensor-pipe-bound) exchange kernels run; the unpack then writes the blocks that can be non-zero
   if (!s.aux_stream) {
-    CK(cudaStreamCreateWithFlags(&s.aux_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithPriority(&s.aux_stream, cudaStreamNonBlocking, s.prio_hi));
     CK(cudaEventCreateWithFlags(&s.ev_start, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&s.ev_kzero, cudaEventDisableTiming));
   }
@@ -1809,13 +1816,28 @@ void Engine::jk_spmd_host(const double *P, int64_t ldP, double kscale, double *J
     CK(cudaMemcpy2DAsync(s.d_P.p + (size_t)cb * n, n * sizeof(double), P + (int64_t)cb * ldP, ldP * sizeof(double),
                          n * sizeof(double), (size_t)(ce - cb), cudaMemcpyHostToDevice, stream_));
   comm_->all_gather_inplace(s.d_P.p, chunk * n, stream_);
-  jk_dev(s.d_P.p, (int64_t)n, kscale, s.d_O2.p, (int64_t)n, s.d_O.p, (int64_t)n, 0, 1, stream_);
-  const HostRanges hrj = host_ranges(true), hrk = host_ranges(false);
-  tm_.h2d_bytes = (double)(ce - cb) * n * sizeof(double);
-  tm_.d2h_bytes = copy_ranges_async(J, ldJ, s.d_O2.p, hrj, stream_, cb, ce) + copy_ranges_async(K, ldK, s.d_O.p, hrk, stream_, cb, ce);
-  zero_outside(J, ldJ, nbf_, hrj, cb, ce);
-  zero_outside(K, ldK, nbf_, hrk, cb, ce);
-  CK(cudaStreamSynchronize(stream_));
+  HostRanges hrj, hrk;
+  {
+    Joiner zero;   // host threads zero-fill this rank's column slice of J and K while the GPUs compute
+    plan_hook_ = [&]() {
+      hrj = host_ranges(true);
+      hrk = host_ranges(false);
+      zero.t = std::thread([&, this]() {
+        zero_outside(J, ldJ, nbf_, hrj, cb, ce);
+        zero_outside(K, ldK, nbf_, hrk, cb, ce);
+      });
+    };
+    try {
+      jk_dev(s.d_P.p, (int64_t)n, kscale, s.d_O2.p, (int64_t)n, s.d_O.p, (int64_t)n, 0, 1, stream_);
+    } catch (...) {
+      plan_hook_ = nullptr;
+      throw;
+    }
+    plan_hook_ = nullptr;
+    tm_.h2d_bytes = (double)(ce - cb) * n * sizeof(double);
+    tm_.d2h_bytes = copy_ranges_async(J, ldJ, s.d_O2.p, hrj, stream_, cb, ce) + copy_ranges_async(K, ldK, s.d_O.p, hrk, stream_, cb, ce);
+    CK(cudaStreamSynchronize(stream_));
+  }   // zero-fill thread joined here
 }
 
 const double *Engine::device_density() const { return p_->d_P.p; }

@@ -219,6 +219,7 @@ class SadatomBatchSCF:
         hist_F, hist_e = [], []
         Eold = torch.zeros(nb, dtype=torch.float64, device=self.dev)
         done = torch.zeros(nb, dtype=torch.bool, device=self.dev)
+        diis_on = torch.zeros(nb, dtype=torch.bool, device=self.dev)   # latches once an atom is close; dropped if it strays far
         for it in range(maxit):
             Prad = Pl.sum(dim=1)
             t0 = self._tick()
@@ -261,8 +262,9 @@ class SadatomBatchSCF:
                 ok = torch.isfinite(c).all(dim=1)
             except Exception:
                 c, ok = None, torch.zeros(nb, dtype=torch.bool, device=self.dev)
+            diis_on = (diis_on | (emax < damp_above)) & (emax < 10.0 * damp_above)
             Fd = F
-            far = emax > damp_above
+            far = ~diis_on
             if c is not None:
                 mix = (torch.stack(hist_F, dim=1) * c[:, :, None, None, None]).sum(dim=1)
                 Fd = torch.where((ok & ~far)[:, None, None, None], mix, F)
