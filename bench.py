@@ -325,7 +325,7 @@ def main():
     if world > 1:
         dist.barrier()
 
-    acc = {"ms_fold": 0.0, "ms_tgemm": 0.0, "ms_offdiag": 0.0, "alg_fold": 0.0, "alg_tgemm": 0.0, "alg_offdiag": 0.0,
+    acc = {"ms_pack": 0.0, "ms_unpack": 0.0, "ms_total": 0.0, "ms_fold": 0.0, "ms_tgemm": 0.0, "ms_offdiag": 0.0, "alg_fold": 0.0, "alg_tgemm": 0.0, "alg_offdiag": 0.0,
            "launches": 0.0, "launches_tgemm": 0.0, "flops_tgemm": 0.0, "n": 0}
 
     def step_device(collect=False):
@@ -486,7 +486,9 @@ def main():
                 "alg_flops_per_launch": acc["alg_tgemm"] / nl, "ms_per_launch": acc["ms_tgemm"] / nl,
                 "executed_tflops": acc["flops_tgemm"] / (acc["ms_tgemm"] * 1e-3) / 1e12 if acc["ms_tgemm"] > 0 else 0.0,
                 "step_share": {"fold_ms": acc["ms_fold"] / nst, "gemm_ms": acc["ms_tgemm"] / nst,
-                               "cross_element_ms": acc["ms_offdiag"] / nst, "step_ms": ms_step},
+                               "cross_element_ms": acc["ms_offdiag"] / nst,
+                               "norms_pack_ms": acc["ms_pack"] / nst, "reduce_gather_unpack_ms": acc["ms_unpack"] / nst,
+                               "exchange_path_ms": acc["ms_total"] / nst, "step_ms": ms_step},
                 "alg_tflops_all_kernels": (acc["alg_fold"] + acc["alg_tgemm"] + acc["alg_offdiag"]) / nst / (ms_step * 1e-3) / 1e12}
 
     cpu_baseline, parity = None, None

@@ -220,6 +220,9 @@ class SadatomBatchSCF:
         Eold = torch.zeros(nb, dtype=torch.float64, device=self.dev)
         done = torch.zeros(nb, dtype=torch.bool, device=self.dev)
         diis_on = torch.zeros(nb, dtype=torch.bool, device=self.dev)   # latches once an atom is close; dropped if it strays far
+        best = torch.full((nb,), float("inf"), dtype=torch.float64, device=self.dev)
+        restart = torch.zeros(nb, dtype=torch.long, device=self.dev)
+        hist_it = []
         for it in range(maxit):
             Prad = Pl.sum(dim=1)
             t0 = self._tick()
@@ -239,23 +242,30 @@ class SadatomBatchSCF:
             if verbose:
                 print("it %3d  not converged %3d  max err %.2e" % (it, int((~done).sum()), float(emax.max())))
             self.energies = {"E": E, "Ekin": Ekin, "Enuc": Enuc, "Coulomb": Ecoul, "XC": Exc, "Nel": Nel}
-            self.Pl, self.iterations = Pl, it + 1
+            self.Pl, self.iterations, self.last_emax = Pl, it + 1, emax
             if bool(done.all()):
                 break
             Eold = E
             # DIIS per atom, batched
             hist_F.append(F)
             hist_e.append(err.reshape(nb, -1))
-            hist_F, hist_e = hist_F[-8:], hist_e[-8:]
+            hist_F, hist_e, hist_it = hist_F[-10:], hist_e[-10:], (hist_it + [it])[-10:]
             m = len(hist_F)
             ev = torch.stack(hist_e, dim=1)                      # (nb, m, n)
             B = torch.zeros((nb, m + 1, m + 1), dtype=torch.float64, device=self.dev)
             B[:, :m, :m] = ev @ ev.transpose(1, 2)
+            # per-atom DIIS restart: entries recorded before the atom's restart iteration are priced out
+            best = torch.minimum(best, emax)
+            restart = torch.where(diis_on & (emax > 4.0 * best) & (emax > 1e-5), torch.full_like(restart, it), restart)
+            best = torch.where(restart == it, emax, best)
+            old = torch.tensor(hist_it, device=self.dev)[None, :] < restart[:, None]        # (nb, m)
+            B[:, :m, :m] += torch.diag_embed(old.to(torch.float64) * 1e30)
             B[:, m, :m] = -1.0
             B[:, :m, m] = -1.0
             rhs = torch.zeros((nb, m + 1, 1), dtype=torch.float64, device=self.dev)
             rhs[:, m] = -1.0
-            scale = B[:, :m, :m].diagonal(dim1=1, dim2=2).amax(dim=1).clamp_min(1e-300)
+            dg = B[:, :m, :m].diagonal(dim1=1, dim2=2)
+            scale = torch.where(dg < 1e29, dg, torch.zeros_like(dg)).amax(dim=1).clamp_min(1e-300)
             B[:, :m, :m] /= scale[:, None, None]
             try:
                 c = torch.linalg.solve(B, rhs)[:, :m, 0]
