@@ -6,8 +6,9 @@ import collections, csv, subprocess, sys
 def raw(path):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
-    h, v = rows[0], rows[-1]
-    d = dict(zip(h, v))
+    h, u, v = rows[0], rows[1], rows[-1]
+    d = {k: (x + " " + un if un and k != "Kernel Name" else x) for k, un, x in zip(h, u, v)}
+    num = dict(zip(h, v))
     keys = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__registers_per_thread", "launch__shared_mem_per_block",
             "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
             "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
@@ -16,7 +17,7 @@ def raw(path):
             "smsp__inst_executed.sum"]
     for k in keys:
         print("%-75s %s" % (k, d.get(k, "?")[:110]))
-    st = {k.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""): float(x) for k, x in d.items()
+    st = {k.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""): float(x) for k, x in num.items()
           if k.startswith("smsp__average_warps_issue_stalled_") and k.endswith("_per_issue_active.ratio") and x not in ("", "n/a")}
     print("stalls/issue:", ", ".join("%s %.2f" % kv for kv in sorted(st.items(), key=lambda t: -t[1])[:7]))
 
