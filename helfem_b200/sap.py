@@ -177,25 +177,47 @@ class SadatomBatchSCF:
 
     # ---- SCF -------------------------------------------------------------------------------------------------
     def _eigh(self, Fo):
-        """Eigenvectors of the (nb, nl, N, N) symmetric matrices, ascending eigenvalues: one CTA per matrix
+        """Eigenvalues (ascending) and eigenvectors of the (..., N, N) symmetric matrices: one CTA per matrix
         (hfq_syev_batch, cyclic Jacobi in shared memory)."""
         torch = self.torch
         V = Fo.contiguous().clone()
         W = torch.empty(V.shape[:-1], dtype=torch.float64, device=self.dev)
-        _check(lib().hfq_syev_batch(V.data_ptr(), W.data_ptr(), self.N, V.shape[0] * V.shape[1],
+        _check(lib().hfq_syev_batch(V.data_ptr(), W.data_ptr(), self.N, V.numel() // (self.N * self.N),
                                     torch.cuda.current_stream().cuda_stream))
         self.launches += 1
-        order = torch.argsort(W, dim=-1)
-        return torch.gather(V, -1, order[..., None, :].expand_as(V))
+        W, order = torch.sort(W, dim=-1)
+        return W, torch.gather(V, -1, order[..., None, :].expand_as(V))
 
-    def _densities(self, F):
-        """F: (nb, nl, N, N) -> per-l densities P_l = C occ C^T, C = X c (scf.cpp:119-130)."""
+    def _fermi(self, eps, ntot, kT, by_l):
+        """Occupations g_l / (1 + exp((eps - mu) / kT)) of the (na, nl, N) orbital energies, g_l = 2 (2l + 1): one
+        chemical potential per l-block holding ntot[:, l] electrons (by_l) or one per atom holding ntot.sum(1)."""
+        torch = self.torch
+        cap = (2.0 * (2.0 * torch.arange(self.nl, device=self.dev, dtype=torch.float64) + 1.0))[None, :, None]
+        red = (lambda x: x.sum(dim=2, keepdim=True)) if by_l else (lambda x: x.sum(dim=(1, 2), keepdim=True))
+        n = ntot[:, :, None] if by_l else ntot.sum(dim=1)[:, None, None]
+        lo = eps.amin(dim=2, keepdim=True) - 1.0 if by_l else eps.amin(dim=(1, 2), keepdim=True) - 1.0
+        hi = eps.amax(dim=2, keepdim=True) + 1.0 if by_l else eps.amax(dim=(1, 2), keepdim=True) + 1.0
+        for _ in range(60):
+            mu = 0.5 * (lo + hi)
+            low = red(cap * torch.sigmoid((mu - eps) / kT)) < n
+            lo, hi = torch.where(low, mu, lo), torch.where(low, hi, mu)
+        return cap * torch.sigmoid((0.5 * (lo + hi) - eps) / kT)
+
+    def _densities(self, F, idx=None, kT=0.0, auto=False):
+        """F: (na, nl, N, N) Fock matrices of the atoms idx (all if None) -> per-l densities P_l = C occ C^T, C = X c
+        (scf.cpp:119-130).  kT = 0: the frozen per-l occupations self.occ, lowest orbitals first; kT > 0:
+        Fermi-Dirac occupations at that electronic temperature, per l-block with the frozen electron counts, or
+        (auto) across the blocks with one chemical potential per atom."""
         t0 = self._tick()
         Fo = self.X.T @ F @ self.X
-        C = self.X @ self._eigh(Fo)
-        P = (C * self.occ[:, :, None, :]) @ C.transpose(-1, -2)
+        W, V = self._eigh(Fo)
+        C = self.X @ V
+        occ = self.occ if idx is None else self.occ[idx]
+        if kT > 0.0:
+            occ = self._fermi(W, occ.sum(dim=2), kT, not auto)
+        P = (C * occ[:, :, None, :]) @ C.transpose(-1, -2)
         self._tock("eigh", t0)
-        return P
+        return P, occ
 
     def _tick(self):
         import time
@@ -207,22 +229,29 @@ class SadatomBatchSCF:
         self.torch.cuda.synchronize()
         self.timing[key] += time.perf_counter() - t0
 
-    def run(self, maxit=150, conv=1e-10, errtol=1e-7, verbose=False, damp_above=0.3):
-        """damp_above: an atom whose largest commutator element exceeds it takes a damped Roothaan step (30 % of the
-        new density) instead of the DIIS extrapolation."""
+    def _solve(self, Pl, active, kT=0.0, auto=False, maxit=150, conv=1e-10, errtol=1e-7, beta=0.3, mh=8, verbose=False,
+               patience=None):
+        """Self-consistency by Pulay mixing of the per-l densities (residual = output density of the Fock matrix
+        minus input density; with thermal occupations it carries the occupation mismatch too, which the orbital
+        commutator [F, P] does not see).  Fock builds run for the whole batch; the eigenproblems, the mixing and the
+        convergence test only for the atoms in `active` (the others keep their density).  An atom whose residual
+        doubles drops its history and halves its mixing factor.  patience: give up on the stragglers when the number
+        of converged atoms has not grown for that many iterations.  Returns (Pl, converged mask of the batch)."""
         torch = self.torch
         nb, nl, N = self.nb, self.nl, self.N
+        idx = torch.nonzero(active).flatten()
+        na = int(idx.numel())
+        f64 = dict(dtype=torch.float64, device=self.dev)
         H0 = (self.T[None, None] + self.ll1[None, :, None, None] * self.Tl[None, None]
               + self.Z[:, None, None, None] * self.V1[None, None])
-        Vg = self.local_potential(self.guess_potential())
-        Pl = self._densities(self.T[None, None] + self.ll1[None, :, None, None] * self.Tl[None, None] + Vg[:, None])
-        hist_F, hist_e = [], []
-        Eold = torch.zeros(nb, dtype=torch.float64, device=self.dev)
-        done = torch.zeros(nb, dtype=torch.bool, device=self.dev)
-        diis_on = torch.zeros(nb, dtype=torch.bool, device=self.dev)   # latches once an atom is close; dropped if it strays far
-        best = torch.full((nb,), float("inf"), dtype=torch.float64, device=self.dev)
-        restart = torch.zeros(nb, dtype=torch.long, device=self.dev)
-        hist_it = []
+        hP, hR, hit = [], [], []
+        start = torch.zeros(na, dtype=torch.long, device=self.dev)
+        prev = torch.full((na,), float("inf"), **f64)
+        bet = torch.full((na,), beta, **f64)
+        Eold = torch.zeros(na, **f64)
+        done = torch.zeros(na, dtype=torch.bool, device=self.dev)
+        eye = torch.eye(mh, **f64)
+        ndone, since = 0, 0
         for it in range(maxit):
             Prad = Pl.sum(dim=1)
             t0 = self._tick()
@@ -235,52 +264,97 @@ class SadatomBatchSCF:
             Enuc = self.Z * (Prad * self.V1).sum(dim=(1, 2))
             Ecoul = 0.5 * (Prad * J).sum(dim=(1, 2))
             E = Ekin + Enuc + Ecoul + Exc
-            F = H0 + J[:, None] + XC
-            err = F @ Pl @ self.S - self.S @ Pl @ F
-            emax = err.abs().amax(dim=(1, 2, 3))
-            done = ((E - Eold).abs() < conv * E.abs().clamp_min(1.0)) & (emax < errtol)
-            if verbose:
-                print("it %3d  not converged %3d  max err %.2e" % (it, int((~done).sum()), float(emax.max())))
             self.energies = {"E": E, "Ekin": Ekin, "Enuc": Enuc, "Coulomb": Ecoul, "XC": Exc, "Nel": Nel}
-            self.Pl, self.iterations, self.last_emax = Pl, it + 1, emax
+            F = (H0 + J[:, None] + XC)[idx]
+            Pa = Pl[idx]
+            Pout, occ = self._densities(F, idx, kT, auto)
+            R = Pout - Pa
+            rmax = R.abs().amax(dim=(1, 2, 3))
+            err = F @ Pa @ self.S - self.S @ Pa @ F
+            emax = torch.maximum(err.abs().amax(dim=(1, 2, 3)), rmax)
+            Ea = E[idx]
+            done = ((Ea - Eold).abs() < conv * Ea.abs().clamp_min(1.0)) & (emax < errtol)
+            self.total_iterations += 1
+            self.last_emax[idx] = emax
+            self._last_occ = occ
+            if verbose:
+                print("it %3d  kT %.3g  not converged %3d  max err %.2e" % (it, kT, int((~done).sum()), float(emax.max())))
             if bool(done.all()):
                 break
-            Eold = E
-            # DIIS per atom, batched
-            hist_F.append(F)
-            hist_e.append(err.reshape(nb, -1))
-            hist_F, hist_e, hist_it = hist_F[-10:], hist_e[-10:], (hist_it + [it])[-10:]
-            m = len(hist_F)
-            ev = torch.stack(hist_e, dim=1)                      # (nb, m, n)
-            B = torch.zeros((nb, m + 1, m + 1), dtype=torch.float64, device=self.dev)
-            B[:, :m, :m] = ev @ ev.transpose(1, 2)
-            # per-atom DIIS restart: entries recorded before the atom's restart iteration are priced out
-            best = torch.minimum(best, emax)
-            restart = torch.where(diis_on & (emax > 4.0 * best) & (emax > 1e-5), torch.full_like(restart, it), restart)
-            best = torch.where(restart == it, emax, best)
-            old = torch.tensor(hist_it, device=self.dev)[None, :] < restart[:, None]        # (nb, m)
+            nd = int(done.sum())
+            ndone, since = (nd, 0) if nd > ndone else (ndone, since + 1)
+            if patience and ndone > 0 and since >= patience:
+                break
+            Eold = Ea
+            worse = rmax > 2.0 * prev
+            start = torch.where(worse, torch.full_like(start, it), start)
+            bet = torch.where(worse, (bet * 0.5).clamp_min(0.02), (bet * 1.1).clamp_max(beta))
+            prev = rmax
+            hP.append(Pa)
+            hR.append(R.reshape(na, -1))
+            hP, hR, hit = hP[-mh:], hR[-mh:], (hit + [it])[-mh:]
+            m = len(hP)
+            rv = torch.stack(hR, dim=1)                          # (na, m, n)
+            B = torch.zeros((na, m + 1, m + 1), **f64)
+            B[:, :m, :m] = rv @ rv.transpose(1, 2)
+            old = torch.tensor(hit, device=self.dev)[None, :] < start[:, None]       # entries before the atom's restart
             B[:, :m, :m] += torch.diag_embed(old.to(torch.float64) * 1e30)
-            B[:, m, :m] = -1.0
-            B[:, :m, m] = -1.0
-            rhs = torch.zeros((nb, m + 1, 1), dtype=torch.float64, device=self.dev)
-            rhs[:, m] = -1.0
             dg = B[:, :m, :m].diagonal(dim1=1, dim2=2)
             scale = torch.where(dg < 1e29, dg, torch.zeros_like(dg)).amax(dim=1).clamp_min(1e-300)
             B[:, :m, :m] /= scale[:, None, None]
-            try:
-                c = torch.linalg.solve(B, rhs)[:, :m, 0]
-                ok = torch.isfinite(c).all(dim=1)
-            except Exception:
-                c, ok = None, torch.zeros(nb, dtype=torch.bool, device=self.dev)
-            diis_on = (diis_on | (emax < damp_above)) & (emax < 10.0 * damp_above)
-            Fd = F
-            far = ~diis_on
-            if c is not None:
-                mix = (torch.stack(hist_F, dim=1) * c[:, :, None, None, None]).sum(dim=1)
-                Fd = torch.where((ok & ~far)[:, None, None, None], mix, F)
-            Pn = self._densities(Fd)
-            Pl = torch.where(far[:, None, None, None], 0.7 * Pl + 0.3 * Pn, Pn)
-        self.converged = done
+            B[:, :m, :m] += 1e-12 * eye[None, :m, :m]
+            B[:, m, :m] = -1.0
+            B[:, :m, m] = -1.0
+            rhs = torch.zeros((na, m + 1, 1), **f64)
+            rhs[:, m] = -1.0
+            c = torch.linalg.solve(B, rhs)[:, :m, 0]
+            ok = torch.isfinite(c).all(dim=1) & (c.abs().amax(dim=1) < 20.0)
+            last = torch.zeros(m, **f64)
+            last[-1] = 1.0
+            c = torch.where(ok[:, None], c, last[None])
+            Pm = (torch.stack(hP, dim=1) * c[:, :, None, None, None]).sum(dim=1)
+            Rm = (rv * c[:, :, None]).sum(dim=1).reshape(Pa.shape)
+            Pl = Pl.clone()
+            Pl[idx] = Pm + bet[:, None, None, None] * Rm
+        conv_mask = torch.zeros(nb, dtype=torch.bool, device=self.dev)
+        conv_mask[idx] = done
+        return Pl, conv_mask
+
+    def run(self, maxit=150, conv=1e-10, errtol=1e-7, verbose=False, refill=True, refill_kT=(0.02, 0.005)):
+        """Stage 1: SCF of every atom with its frozen per-l electron counts (self.occ_l: the reference's tabulated
+        ground-state configurations unless given).  Those are PBE configurations; with the exchange-only SAP
+        functional a few of them have no bound Aufbau solution (Gd - Tm: the 4f level of the frozen 4f^n 6s^1
+        configurations rises above zero) and cannot converge.  Stage 2 (refill): such atoms get their per-l counts
+        from a finite-temperature SCF with ONE chemical potential across the l-blocks (what the reference's
+        `--occs auto` leaves to OpenOrbitalOptimizer's occupation optimisation), annealed over refill_kT, and are then
+        converged again at zero temperature with those (fractional) counts frozen -- the reference's
+        fixed_per_l path (src/sadatom/scf.cpp:390-405).  self.refilled maps Z to the new counts."""
+        torch = self.torch
+        nb, nl, N = self.nb, self.nl, self.N
+        self.total_iterations = 0
+        self.refilled = {}
+        self.last_emax = torch.full((nb,), float("inf"), dtype=torch.float64, device=self.dev)
+        every = torch.ones(nb, dtype=torch.bool, device=self.dev)
+        Vg = self.local_potential(self.guess_potential())
+        Pl, _ = self._densities(self.T[None, None] + self.ll1[None, :, None, None] * self.Tl[None, None] + Vg[:, None])
+        Pl, done = self._solve(Pl, every, maxit=maxit, conv=conv, errtol=errtol, verbose=verbose, patience=40 if refill else None)
+        if refill and maxit >= 60 and not bool(done.all()):
+            bad = ~done
+            for kT in refill_kT:
+                Pl, _ = self._solve(Pl, bad, kT=kT, auto=True, maxit=400, conv=1e-9, errtol=1e-6, verbose=verbose)
+            counts = self._last_occ.sum(dim=2)                                # (bad atoms, nl)
+            counts = torch.where((counts - counts.round()).abs() < 1e-6, counts.round(), counts)
+            counts = counts * (self.Z[bad] / counts.sum(dim=1))[:, None]
+            occ = self.occ.clone()
+            cn = counts.cpu().numpy()
+            for k, a in enumerate(torch.nonzero(bad).flatten().tolist()):
+                for l in range(nl):
+                    occ[a, l] = torch.as_tensor(shell_occupations(cn[k, l], l, N), dtype=torch.float64, device=self.dev)
+                self.refilled[self.zs[a]] = [float(x) for x in cn[k]]
+            self.occ = occ
+            Pl, again = self._solve(Pl, bad, maxit=maxit, conv=conv, errtol=errtol, verbose=verbose)
+            done = done | again
+        self.Pl, self.converged, self.iterations = Pl, done, self.total_iterations
         return {k: v.cpu().numpy() for k, v in self.energies.items()}
 
     # ---- products --------------------------------------------------------------------------------------------
@@ -304,13 +378,17 @@ class SadatomBatchSCF:
     def write_results(self, directory):
         """result_<El>.dat per atom, the reference's raw-ascii layout (io::write_raw_ascii, src/general/eigen_io.h:92-101:
         scientific, 16 digits after the point, field width 24, one table row per line)."""
+        from concurrent.futures import ThreadPoolExecutor
         os.makedirs(directory, exist_ok=True)
-        paths = []
-        for a, z in enumerate(self.zs):
+        self.sap_table(0)      # creates the shared (read-only) table set before the threads start
+
+        def one(a):
             tab = self.sap_table(a)
-            path = os.path.join(directory, "result_%s.dat" % self.symbols[z])
+            path = os.path.join(directory, "result_%s.dat" % self.symbols[self.zs[a]])
             with open(path, "w") as f:
-                for row in tab:
-                    f.write("".join(" %24.16e" % v for v in row) + "\n")
-            paths.append(path)
-        return paths
+                f.write("".join("".join(" %24.16e" % v for v in row) + "\n" for row in tab))
+            return path
+
+        # the screening integrals are host-side post-processing (like the reference's): one atom per host thread
+        with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
+            return list(ex.map(one, range(self.nb)))

@@ -85,7 +85,9 @@ def main():
                "max_relerr_E_vs_gpu": max(errs) if errs else None}
     line = {"metric": "SAP atoms/s (spherically averaged LDA-x SCF + effective-potential table)", "value": len(zs_all) / (t_scf + t_tab),
             "unit": "atoms/s", "n_gpus": world, "elements": len(zs_all), "scf_s": t_scf, "tables_s": t_tab, "setup_s": t_setup,
-            "iterations": iters, "all_converged": conv, "scaling": "strong (elements dealt round-robin, no collective)",
+            "iterations": iters, "all_converged": conv,
+            "refilled_rank0": {str(z): [round(x, 4) for x in v] for z, v in batch.refilled.items()},
+            "refill_note": "atoms whose tabulated (PBE) frozen configuration has no bound LDA-x Aufbau solution: per-l counts from a finite-temperature SCF with one chemical potential (kT 0.02 -> 0.005 Eh), then frozen again at T = 0", "scaling": "strong (elements dealt round-robin, no collective)",
             "kernel_launches_native": batch.launches, "phase_seconds": batch.timing, "cpu_baseline": cpu, "results": os.path.relpath(out, ROOT),
             "E_Rn" if args.zmax >= 86 and 86 in zs else "E_last": float(res["E"][zs.index(max(zs))])}
     print(json.dumps(line))
