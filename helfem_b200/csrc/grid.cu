@@ -14,6 +14,7 @@
 #include <string>
 
 #include "kernels.cuh"
+#include "xc_builtin.cuh"
 
 namespace hfq {
 
@@ -211,29 +212,65 @@ __global__ void k_exc(const double *__restrict__ w, const double *__restrict__ e
   if ((threadIdx.x & 31) == 0) atomicAdd(sum, s);
 }
 
-// Slater exchange, libxc id 1 (XC_LDA_X), on the device: exc per particle and v_rho from the densities of the last
-// density call; spin-scaling relation E_x[na, nb] = (E_x[2 na] + E_x[2 nb]) / 2 for the polarised case; zero below
-// the density threshold (xc_func_set_dens_threshold, src/general/dftgrid_common.cpp:131)
-__global__ void k_lda_x(int64_t N, const double *__restrict__ ra, const double *__restrict__ rb, double thr,
-                        double *__restrict__ exc, double *__restrict__ va, double *__restrict__ vb) {
-  const double cx = -0.75 * cbrt(3.0 / 3.14159265358979323846);
+// Built-in functionals (xc_builtin.cuh: libxc ids 1, 7, 101, 130; id <= 0: none) on the device, from the densities and
+// gradients of the last density call: exc per particle, v_rho and v_sigma in libxc's conventions, summed over the
+// exchange and the correlation functional like DFTGridWorkerBase::compute_xc accumulates them; zero below the density
+// threshold (xc_func_set_dens_threshold, src/general/dftgrid_common.cpp:131).  Polarised densities: exchange only,
+// through the spin-scaling relation E_x[na, nb] = (E_x[2 na] + E_x[2 nb]) / 2 (v_sigma(ab) = 0).
+// ga / gb: gradient components [3][N] (may be null for LDAs); vsa / vsab / vsb may be null for LDAs.
+__global__ void k_xc_builtin(int64_t N, int x_func, int c_func, const double *__restrict__ ra, const double *__restrict__ rb,
+                             const double *__restrict__ ga, const double *__restrict__ gb, double thr,
+                             double *__restrict__ exc, double *__restrict__ va, double *__restrict__ vb,
+                             double *__restrict__ vsa, double *__restrict__ vsab, double *__restrict__ vsb) {
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < N; p += (int64_t)gridDim.x * blockDim.x) {
+    auto sig = [&](const double *g) {
+      if (!g) return 0.0;
+      const double a0 = g[p], a1 = g[N + p], a2 = g[2 * N + p];
+      return a0 * a0 + a1 * a1 + a2 * a2;
+    };
     if (!rb) {
       const double n = ra[p];
-      const bool ok = !(n < thr);
-      const double n13 = ok ? cbrt(n) : 0.0;
-      exc[p] = cx * n13;
-      va[p] = 4.0 / 3.0 * cx * n13;
+      double e = 0.0, vr = 0.0, vs = 0.0;
+      if (!(n < thr)) {
+        const double sg = sig(ga);
+        for (int k = 0; k < 2; k++) {
+          const int id = k ? c_func : x_func;
+          if (id <= 0) continue;
+          const xc::D2 d = xc::energy(id, n, sg);
+          e += d.v;
+          vr += d.v + n * d.n;
+          vs += n * d.s;
+        }
+      }
+      exc[p] = e;
+      va[p] = vr;
+      if (vsa) vsa[p] = vs;
     } else {
       const double na = ra[p], nb = rb[p], n = na + nb;
-      if (n < thr) {
-        exc[p] = va[p] = vb[p] = 0.0;
-        continue;
+      double e = 0.0, vra = 0.0, vrb = 0.0, vsaa = 0.0, vsbb = 0.0;
+      if (!(n < thr) && x_func > 0) {
+        if (na > 0.0) {
+          const xc::D2 d = xc::energy(x_func, 2.0 * na, 4.0 * sig(ga));
+          e += na * d.v;
+          vra = d.v + 2.0 * na * d.n;
+          vsaa = 4.0 * na * d.s;
+        }
+        if (nb > 0.0) {
+          const xc::D2 d = xc::energy(x_func, 2.0 * nb, 4.0 * sig(gb));
+          e += nb * d.v;
+          vrb = d.v + 2.0 * nb * d.n;
+          vsbb = 4.0 * nb * d.s;
+        }
+        e /= n;
       }
-      const double ca = na > 0 ? cbrt(2.0 * na) : 0.0, cb = nb > 0 ? cbrt(2.0 * nb) : 0.0;
-      exc[p] = cx * (ca * na + cb * nb) / n;
-      va[p] = 4.0 / 3.0 * cx * ca;
-      vb[p] = 4.0 / 3.0 * cx * cb;
+      exc[p] = e;
+      va[p] = vra;
+      vb[p] = vrb;
+      if (vsa) {
+        vsa[p] = vsaa;
+        vsab[p] = 0.0;
+        vsb[p] = vsbb;
+      }
     }
   }
 }
@@ -532,15 +569,24 @@ void GridEngine::density(const double *Pa, int64_t ldPa, const double *Pb, int64
 }
 
 // Built-in functionals evaluated on the device from the densities of the last density call, then the assembly:
-// x_func = 1 Slater exchange (libxc id 1), <= 0 none (H = 0; the HF drivers call eval_Fxc only to integrate Nel).
-void GridEngine::fxc_builtin(int x_func, double thr, bool beta, double *Ha, int64_t ldHa, double *Hb, int64_t ldHb,
-                             double *Exc) {
+// x_func / c_func = libxc ids 1 (Slater exchange), 101 (PBE exchange) / 7 (VWN5), 130 (PBE correlation); <= 0: none
+// (H = 0; the HF drivers call eval_Fxc only to integrate Nel).  GGAs need the gradient from the density call.
+bool GridEngine::builtin_needs_gradient(int x_func, int c_func) {
+  return (x_func > 0 && xc::is_gga(x_func)) || (c_func > 0 && xc::is_gga(c_func));
+}
+bool GridEngine::builtin_supported(int x_func, int c_func) {
+  return (x_func <= 0 || (xc::known(x_func) && xc::is_exchange(x_func))) &&
+         (c_func <= 0 || (xc::known(c_func) && !xc::is_exchange(c_func)));
+}
+
+void GridEngine::fxc_builtin(int x_func, int c_func, double thr, bool beta, double *Ha, int64_t ldHa, double *Hb,
+                             int64_t ldHb, double *Exc) {
   Impl &s = *p_;
   CK(cudaSetDevice(s.device));
   const int64_t N = s.N;
   const size_t n = (size_t)s.nbf;
   const int nspin = s.polarized ? 2 : 1;
-  if (x_func <= 0) {
+  if (x_func <= 0 && c_func <= 0) {
     auto zero = [&](double *H, int64_t ld) {
       if (!H) return;
       if (is_device_pointer(H)) {
@@ -555,11 +601,19 @@ void GridEngine::fxc_builtin(int x_func, double thr, bool beta, double *Ha, int6
     if (Exc) *Exc = 0.0;
     return;
   }
-  if (x_func != 1) throw std::logic_error("only the Slater exchange (libxc id 1) is built in");
+  if (!builtin_supported(x_func, c_func))
+    throw std::logic_error("built-in functionals: exchange 1 (Slater), 101 (PBE); correlation 7 (VWN5), 130 (PBE)");
+  if (nspin == 2 && c_func > 0)
+    throw std::logic_error("built-in correlation functionals are spin-unpolarised only: use hfq_grid_density + libxc + hfq_grid_fxc");
+  const bool gga = builtin_needs_gradient(x_func, c_func);
+  if (gga && !(s.dens_flags & GRID_GRAD)) throw std::logic_error("built-in GGA: the gradient was not computed by the density call");
   double *v = s.d_v.p;
-  k_lda_x<<<592, 256, 0, s.st>>>(N, s.dens(0, 0), nspin == 2 ? s.dens(1, 0) : nullptr, thr, v + 9 * N, v, v + N);
+  k_xc_builtin<<<592, 256, 0, s.st>>>(N, x_func, c_func, s.dens(0, 0), nspin == 2 ? s.dens(1, 0) : nullptr,
+                                      gga ? s.dens(0, 1) : nullptr, (gga && nspin == 2) ? s.dens(1, 1) : nullptr, thr,
+                                      v + 9 * N, v, v + N, gga ? v + 2 * N : nullptr, gga ? v + 3 * N : nullptr,
+                                      gga ? v + 4 * N : nullptr);
   CK(cudaGetLastError());
-  assemble(0, beta, true, false, false, false, Ha, ldHa, Hb, ldHb, Exc);
+  assemble(gga ? GRID_GRAD : 0, beta, true, gga, false, false, Ha, ldHa, Hb, ldHb, Exc);
 }
 
 void GridEngine::fxc(int flags, bool beta, const double *exc, const double *vrho, const double *vsigma, const double *vtau,

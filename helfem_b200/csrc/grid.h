@@ -63,7 +63,10 @@ class GridEngine {
   void density_launch(const double *Pa, int64_t ldPa, const double *Pb, int64_t ldPb, int flags);
   void density_collect(double *rho, double *sigma, double *tau, double *lapl, double *weights, double *Nel, double *Ekin);
   // built-in functionals on the device (x_func = 1 Slater exchange, <= 0 none) + assembly; H may be device pointers
-  void fxc_builtin(int x_func, double thr, bool beta, double *Ha, int64_t ldHa, double *Hb, int64_t ldHb, double *Exc);
+  void fxc_builtin(int x_func, int c_func, double thr, bool beta, double *Ha, int64_t ldHa, double *Hb, int64_t ldHb,
+                   double *Exc);
+  static bool builtin_supported(int x_func, int c_func);
+  static bool builtin_needs_gradient(int x_func, int c_func);
   cudaStream_t stream() const;
   // assembly from functional output (host arrays, libxc layout); uses the density kept on the device
   void fxc(int flags, bool beta, const double *exc, const double *vrho, const double *vsigma, const double *vtau,

@@ -252,8 +252,11 @@ int hfq_grid_density(hfq_ctx *ctx, const double *Pa, int64_t ldPa, const double 
 int hfq_grid_fxc(hfq_ctx *ctx, int flags, int beta, const double *exc, const double *vrho, const double *vsigma,
                  const double *vtau, const double *vlapl, double *Ha, int64_t ldHa, double *Hb, int64_t ldHb, double *Exc);
 /* DFTGrid::eval_Fxc(x_func, .., c_func, .., P[a,b] -> H[a,b], Exc, Nel, Ekin, beta, thr) for the
- * functionals built into this library (x_func = 1: Slater exchange, x_func <= 0: none -- the HF
- * drivers still call eval_Fxc to integrate Nel).  Other ids return HFQ_ERR_INVALID. */
+ * functionals built into this library and evaluated on the device (csrc/xc_builtin.cuh), libxc ids:
+ * x_func = 1 Slater exchange, 101 PBE exchange; c_func = 7 VWN5, 130 PBE correlation (correlation: restricted
+ * densities only; polarised exchange through the spin-scaling relation); <= 0: none -- the HF drivers still call
+ * eval_Fxc to integrate Nel.  These are the functionals of the reference's recorded LDA / PBE energies
+ * (tests/refs/ci.json).  Other ids return HFQ_ERR_INVALID: use hfq_grid_density + libxc + hfq_grid_fxc. */
 int hfq_eval_fxc(hfq_ctx *ctx, int x_func, int c_func, const double *Pa, int64_t ldPa, const double *Pb, int64_t ldPb,
                  double *Ha, int64_t ldHa, double *Hb, int64_t ldHb, double *Exc, double *Nel, double *Ekin, int beta,
                  double thr);
@@ -262,8 +265,8 @@ int hfq_eval_fxc(hfq_ctx *ctx, int x_func, int c_func, const double *Pa, int64_t
  * src/atomic/main.cpp:385-446): XC = eval_Fxc(x_func, c_func, P), J = coulomb(P), K = exchange(kscale * P), everything
  * device-resident.  The grid's density chain is queued first on its own stream and runs next to the J/K kernels.
  * x_func <= 0 and c_func <= 0 (Hartree-Fock: the reference still calls eval_Fxc, which then only integrates Nel):
- * dHxc may be NULL; if given it is zero-filled (the reference's XC matrix of an HF build).  x_func = 1: Slater
- * exchange evaluated on the device.  Needs hfq_grid_attach.  Exc, Nel: host scalars. */
+ * dHxc may be NULL; if given it is zero-filled (the reference's XC matrix of an HF build).  Built-in functionals
+ * (see hfq_eval_fxc) are evaluated on the device.  Needs hfq_grid_attach.  Exc, Nel: host scalars. */
 int hfq_fock_build_device(hfq_ctx *ctx, const double *dP, int64_t ldP, double kscale, double *dJ, int64_t ldJ, double *dK,
                           int64_t ldK, int x_func, int c_func, double *dHxc, int64_t ldH, double *Exc, double *Nel,
                           double thr, void *stream);

@@ -105,7 +105,71 @@ def test_eval_fxc_slater_exchange(hb):
     H0, Exc0, Nel0, _ = gg.eval_Fxc(-1, 0, P)
     assert np.all(H0 == 0.0) and Exc0 == 0.0 and abs(Nel0 - o["Nel"]) < 1e-11
     with pytest.raises(ValueError):
-        gg.eval_Fxc(101, 130, P)     # PBE is not built in: use density + libxc + fxc
+        gg.eval_Fxc(202, 231, P)     # meta-GGAs (TPSS ids) are not built in: use density + libxc + fxc
+    with pytest.raises(ValueError):
+        gg.eval_Fxc(7, 0, P)         # a correlation id in the exchange slot
+
+
+@pytest.mark.parametrize("x_func,c_func", [(1, 7), (101, 130), (101, 0), (0, 130)])
+def test_eval_fxc_builtin_functionals(hb, x_func, c_func):
+    """Functionals evaluated on the device (csrc/xc_builtin.cuh: libxc ids 1, 7, 101, 130) through eval_Fxc against
+    the oracle grid fed with the oracle's symbolically differentiated functionals (oracle/xc.py, pinned on the
+    reference's recorded LDA / PBE energies)."""
+    from oracle import xc
+    ob, basis, og, gg = _setup(hb, 4, 1, 1, 2)
+    n = ob.Nbf()
+    P = cases.random_density(n, 2, 11)
+    fids = [f for f in (x_func, c_func) if f > 0]
+    gga = any(xc.is_gga(f) for f in fids)
+    o = og.eval_density(P, None, gga)
+    exc, vrho, vsigma = xc.evaluate_sum(fids, o["rho"][:, 0], o["sigma"][:, 0] if gga else None, 1e-12)
+    Ho, _, Eo = og.eval_fxc(n, exc, vrho[:, None], vsigma[:, None] if gga else None)
+    H, Exc, Nel, Ekin = gg.eval_Fxc(x_func, c_func, P)
+    assert cases.relerr(H, Ho) < 1e-11 and abs(Exc - Eo) < 1e-12 * abs(Eo) and abs(Nel - o["Nel"]) < 1e-11 and Ekin == 0.0
+
+
+def test_eval_fxc_builtin_polarised_exchange(hb):
+    """Polarised PBE exchange through the spin-scaling relation E_x[na, nb] = (E_x[2 na] + E_x[2 nb]) / 2: the oracle
+    evaluates the unpolarised functional at (2 n_s, 4 sigma_ss) and assembles with libxc's polarised layout."""
+    from oracle import xc
+    ob, basis, og, gg = _setup(hb, 4, 1, 1, 2)
+    n = ob.Nbf()
+    Pa, Pb = cases.random_density(n, 3, 5), cases.random_density(n, 2, 6)
+    o = og.eval_density(Pa, Pb, True)
+    N = og.npoints()
+    vrho, vsigma, edens = np.zeros((N, 2)), np.zeros((N, 3)), np.zeros(N)
+    for s_, col in ((0, 0), (1, 2)):
+        e, v, vs = xc.evaluate(xc.XC_GGA_X_PBE, 2.0 * o["rho"][:, s_], 4.0 * o["sigma"][:, col], 0.0)
+        edens += o["rho"][:, s_] * e
+        vrho[:, s_], vsigma[:, col] = v, 2.0 * vs
+    tot = o["rho"].sum(axis=1)
+    ok = tot >= 1e-12
+    exc = np.where(ok, edens / np.where(ok, tot, 1.0), 0.0)
+    vrho[~ok], vsigma[~ok] = 0.0, 0.0
+    Hao, Hbo, Eo = og.eval_fxc(n, exc, vrho, vsigma)
+    (Ha, Hb), Exc, Nel, _ = gg.eval_Fxc(101, 0, Pa, Pb)
+    assert cases.relerr(Ha, Hao) < 1e-11 and cases.relerr(Hb, Hbo) < 1e-11 and abs(Exc - Eo) < 1e-12 * abs(Eo)
+    with pytest.raises(ValueError):
+        gg.eval_Fxc(101, 130, Pa, Pb)     # polarised correlation is not built in
+
+
+@pytest.mark.parametrize("method,Eref,XCref", [("lda", -2.8348356241, -0.9733148392), ("pbe", -2.8929348668, -1.0461619634)])
+def test_he_ks_energy_on_gpu(hb, method, Eref, XCref):
+    """atomic-He-lda-r / atomic-He-gga-r of the reference's tests/refs/ci.json: a Kohn-Sham SCF whose Fock build runs
+    on the GPU (J = hfq_coulomb, XC = hfq_eval_fxc with the functional evaluated on the device) lands on the recorded
+    total energy to 1e-9 Eh."""
+    from oracle import scf
+    ob, basis, og, gg = _setup(hb, 2, 0, 0, 5)
+    S, T, V = basis.tables.one_electron()
+    n = ob.Nbf()
+    xf, cf = (1, 7) if method == "lda" else (101, 130)
+
+    def vxc(P):
+        H, Exc, Nel, _ = gg.eval_Fxc(xf, cf, P)
+        return H, Exc, Nel
+
+    r = scf.rks(S, T + V, basis.coulomb, vxc, [1], [np.arange(n)])
+    assert abs(r["E"] - Eref) < 1e-9 and abs(r["XC"] - XCref) < 2e-6 and abs(r["Nel"] - 2.0) < 1e-10
 
 
 # ---------------------------------------------------------------------------------------------

@@ -174,3 +174,33 @@ def test_sap_table_matches_oracle_and_physics(hb):
     assert np.all(np.diff(vc[1:]) > -1e-9)                                    # r V_H(r) = charge inside r grows
     with pytest.raises(ValueError):
         sb.sap_table([P])                                                     # wrong number of l blocks is caught below
+
+
+def test_builtin_functionals_match_oracle(tmp_path):
+    """The functional expressions the device kernel evaluates (helfem_b200/csrc/xc_builtin.cuh: dual-number forms of
+    libxc ids 1, 7, 101, 130), compiled for the host by tests/cpp/xc_check.cpp, against the oracle's symbolically
+    differentiated restatement (oracle/xc.py, pinned on the reference's recorded LDA / PBE energies): exc, vrho, vsigma
+    over 15 decades of density and 20 of the gradient, including sigma = 0.  PBE correlation is a difference of two
+    terms that cancel at large reduced gradients, so errors are measured against the uniform-gas exchange scale."""
+    import subprocess
+    from oracle import xc
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "xc_check")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", os.path.join(root, "tests", "cpp", "xc_check.cpp"), "-o", exe])
+    rng = np.random.default_rng(3)
+    n = 10.0 ** rng.uniform(-11, 4, 600)
+    s = (10.0 ** rng.uniform(-14, 6, 600)) * n ** (8.0 / 3.0) * rng.uniform(0, 1, 600)
+    s[:30] = 0.0
+    ex, vx, _ = xc.evaluate(xc.XC_LDA_X, n)
+    for fid in (xc.XC_LDA_X, xc.XC_LDA_C_VWN, xc.XC_GGA_X_PBE, xc.XC_GGA_C_PBE):
+        inp = "".join("%d %.17e %.17e\n" % (fid, a, b) for a, b in zip(n, s))
+        out = np.array(subprocess.run([exe], input=inp, capture_output=True, text=True, check=True).stdout.split(), dtype=float)
+        out = out.reshape(-1, 3)
+        e, v, vs = xc.evaluate(fid, n, s, thr=0.0)
+        assert np.max(np.abs(out[:, 0] - e) / np.abs(ex)) < 1e-12, fid
+        assert np.max(np.abs(out[:, 1] - v) / np.abs(vx)) < 1e-12, fid
+        if vs is None:
+            assert np.all(out[:, 2] == 0.0)
+        else:   # vsigma ~ exc n / sigma: scale by the uniform-gas exchange energy density over (sigma + its natural unit)
+            scale = np.abs(ex) * n / (s + n ** (8.0 / 3.0))
+            assert np.max(np.abs(out[:, 2] - vs) / scale) < 1e-12, fid
