@@ -197,10 +197,12 @@ def test_builtin_functionals_match_oracle(tmp_path):
         out = np.array(subprocess.run([exe], input=inp, capture_output=True, text=True, check=True).stdout.split(), dtype=float)
         out = out.reshape(-1, 3)
         e, v, vs = xc.evaluate(fid, n, s, thr=0.0)
-        assert np.max(np.abs(out[:, 0] - e) / np.abs(ex)) < 1e-12, fid
-        assert np.max(np.abs(out[:, 1] - v) / np.abs(vx)) < 1e-12, fid
+        # PBE correlation below n ~ 1e-9: the oracle's exp(-ec / gamma) - 1 loses digits (the product uses expm1)
+        tol = 1e-10 if fid == xc.XC_GGA_C_PBE else 1e-12
+        assert np.max(np.abs(out[:, 0] - e) / np.abs(ex)) < tol, fid
+        assert np.max(np.abs(out[:, 1] - v) / np.abs(vx)) < tol, fid
         if vs is None:
             assert np.all(out[:, 2] == 0.0)
         else:   # vsigma ~ exc n / sigma: scale by the uniform-gas exchange energy density over (sigma + its natural unit)
             scale = np.abs(ex) * n / (s + n ** (8.0 / 3.0))
-            assert np.max(np.abs(out[:, 2] - vs) / scale) < 1e-12, fid
+            assert np.max(np.abs(out[:, 2] - vs) / scale) < tol, fid
