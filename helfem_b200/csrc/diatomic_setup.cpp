@@ -8,7 +8,10 @@
 // src/diatomic/quadrature.cpp:133-257 (nested Gauss-Chebyshev quadrature),
 // src/diatomic/quadrature.h:47-84 (Legendre value filtering).
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <memory>
 #include <set>
@@ -324,6 +327,9 @@ BasisTables build_diatomic_tables(int Z1, int Z2, double Rbond, const std::vecto
   const int nseed = std::max(t.nquad, 5);
   const double floor_rel = 256.0 * std::numeric_limits<double>::epsilon();
 
+  const bool timing = getenv("HFQ_SETUP_TIMING") != nullptr;
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_start = now();
   // ---- cross-element factors int B_i B_j sinh cosh^k {P,Q}_L^|M|(cosh mu) dmu
   const int ntask = (int)runs.size() * t.Nel;
 #pragma omp parallel for schedule(dynamic)
@@ -376,6 +382,7 @@ BasisTables build_diatomic_tables(int Z1, int Z2, double Rbond, const std::vecto
     }
   }
 
+  const double t_cross = now();
   // ---- in-element kernel: converge the rule on the hardest multipole, then
   //      build every (L,|M|) once at that order and factorise.
   int Lhard = t.lmL[0], Mhard = t.lmM[0];
@@ -408,7 +415,11 @@ BasisTables build_diatomic_tables(int Z1, int Z2, double Rbond, const std::vecto
         sign_cholesky(W, kCdThresh, b.B, b.sigma, b.rank);
       }
     }
+    if (timing) std::fprintf(stderr, "[hfq setup] element %d: nested rule order %d\n", iel, nconv);
   }
+  if (timing)
+    std::fprintf(stderr, "[hfq setup] cross-element factors %.3f s, in-element kernels + factorisation %.3f s\n",
+                 t_cross - t_start, now() - t_cross);
   return t;
 }
 

@@ -146,7 +146,7 @@ def test_eval_fxc_builtin_polarised_exchange(hb):
     ok = tot >= 1e-12
     exc = np.where(ok, edens / np.where(ok, tot, 1.0), 0.0)
     vrho[~ok], vsigma[~ok] = 0.0, 0.0
-    Hao, Hbo, Eo = og.eval_fxc(n, exc, vrho, vsigma)
+    Hao, Hbo, Eo = og.eval_fxc(n, exc, vrho, vsigma, polarized=True)
     (Ha, Hb), Exc, Nel, _ = gg.eval_Fxc(101, 0, Pa, Pb)
     assert cases.relerr(Ha, Hao) < 1e-11 and cases.relerr(Hb, Hbo) < 1e-11 and abs(Exc - Eo) < 1e-12 * abs(Eo)
     with pytest.raises(ValueError):
