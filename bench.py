@@ -287,6 +287,23 @@ def main():
     t0 = time.time()
     T = hb.Tables.diatomic(7, 7, 2.07, [args.lmax] * (args.mmax + 1), args.nelem)
     t_setup = time.time() - t0
+    tei_dev = None
+    if world == 1 and not args.profile_mode:
+        # the same setup with the in-element kernels computed on the GPU (hfq_tables_diatomic_device), timed next to
+        # the host path and compared with it channel by channel (reconstructed kernels W = B sigma B^T)
+        hb.Tables.diatomic(7, 7, 2.07, [2, 2], 1, device=local)     # CUDA context + module load outside the timing
+        t0 = time.time()
+        Td = hb.Tables.diatomic(7, 7, 2.07, [args.lmax] * (args.mmax + 1), args.nelem, device=local)
+        t_dev = time.time() - t0
+        worst = 0.0
+        for ilm in range(0, T.nlm, max(1, T.nlm // 12)):
+            for iel in range(T.Nel):
+                _, _, Bh, sh = T.block(ilm, iel)
+                _, _, Bd, sd = Td.block(ilm, iel)
+                Wh = (Bh * sh[None, :]) @ Bh.T
+                worst = max(worst, float(np.abs(Wh - (Bd * sd[None, :]) @ Bd.T).max() / np.abs(Wh).max()))
+        tei_dev = {"seconds": t_dev, "max_relerr_W_vs_host": worst, "channels_compared": len(range(0, T.nlm, max(1, T.nlm // 12))) * T.Nel}
+        del Td
     basis = hb.TablesBasis(T, device=local)
     n = T.Nbf
     P, config["density"] = make_density(args.density, T)
@@ -532,7 +549,8 @@ def main():
             "gpu_launches": int(acc["launches"]), "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,
             "vxc_dft": vxc_dft,
             "clocks": sampler.summary(),
-            "setup": {"host_compute_tei_s": t_setup, "device_upload_s": t_upload, "Nbf": n, "channels": T.nlm}}
+            "setup": {"host_compute_tei_s": t_setup, "device_compute_tei": tei_dev, "device_upload_s": t_upload, "Nbf": n,
+                      "channels": T.nlm}}
     print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -36,7 +36,7 @@ class _TablesInfo(ctypes.Structure):
 
 EXPORTED_SYMBOLS = [
     "hfq_last_error", "hfq_tables_atomic", "hfq_tables_atomic_yukawa", "hfq_tables_atomic_erfc",
-    "hfq_tables_set_pair_tensors", "hfq_sap_table", "hfq_tables_get_pair_tensor", "hfq_erfc_phi", "hfq_tables_sadatom", "hfq_tables_sadatom_rs", "hfq_tables_diatomic", "hfq_tables_from_arrays", "hfq_tables_get_info",
+    "hfq_tables_set_pair_tensors", "hfq_sap_table", "hfq_tables_get_pair_tensor", "hfq_erfc_phi", "hfq_tables_sadatom", "hfq_tables_sadatom_rs", "hfq_tables_diatomic", "hfq_tables_diatomic_device", "hfq_tables_from_arrays", "hfq_tables_get_info",
     "hfq_tables_get_ints", "hfq_tables_get_doubles", "hfq_tables_get_block", "hfq_tables_one_electron",
     "hfq_tables_destroy", "hfq_create", "hfq_destroy", "hfq_nbf", "hfq_set_absm_symmetric", "hfq_coulomb",
     "hfq_exchange", "hfq_coulomb_device", "hfq_exchange_device", "hfq_last_timings", "hfq_exchange_output_pattern",
@@ -70,6 +70,7 @@ def lib():
     L.hfq_tables_sadatom.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ci, cd, ci, cd, ci]
     L.hfq_tables_sadatom_rs.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ci, cd, ci, cd, ci, ci, cd]
     L.hfq_tables_diatomic.argtypes = [ctypes.POINTER(vp), ci, ci, cd, _c_int_p, ci, ci, ci, cd, ci, cd, ci]
+    L.hfq_tables_diatomic_device.argtypes = [ctypes.POINTER(vp), ci, ci, cd, _c_int_p, ci, ci, ci, cd, ci, cd, ci, ci]
     L.hfq_tables_from_arrays.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(_TablesDesc)]
     L.hfq_tables_get_info.argtypes = [vp, ctypes.POINTER(_TablesInfo)]
     L.hfq_tables_get_ints.argtypes = [vp, ci, vp, i64]
@@ -207,11 +208,16 @@ class Tables:
         return cls(h)
 
     @classmethod
-    def diatomic(cls, Z1, Z2, Rbond, lmax_per_m, nelem, nnodes=15, Rmax=40.0, igrid=4, zexp=1.0, nquad=0):
+    def diatomic(cls, Z1, Z2, Rbond, lmax_per_m, nelem, nnodes=15, Rmax=40.0, igrid=4, zexp=1.0, nquad=0, device=None):
+        """device: None = compute_tei on the host (OpenMP); a CUDA device index = in-element kernels on that GPU."""
         h = ctypes.c_void_p()
         lm = (ctypes.c_int * len(lmax_per_m))(*[int(x) for x in lmax_per_m])
-        _check(lib().hfq_tables_diatomic(ctypes.byref(h), Z1, Z2, Rbond, lm, len(lmax_per_m), nelem, nnodes, Rmax,
-                                         igrid, zexp, nquad))
+        if device is None:
+            _check(lib().hfq_tables_diatomic(ctypes.byref(h), Z1, Z2, Rbond, lm, len(lmax_per_m), nelem, nnodes, Rmax,
+                                             igrid, zexp, nquad))
+        else:
+            _check(lib().hfq_tables_diatomic_device(ctypes.byref(h), Z1, Z2, Rbond, lm, len(lmax_per_m), nelem, nnodes,
+                                                    Rmax, igrid, zexp, nquad, int(device)))
         return cls(h)
 
     @classmethod
@@ -466,12 +472,15 @@ class DiatomicTwoDBasis(_BasisBase):
     """helfem::diatomic::basis::TwoDBasis (src/diatomic/basis.h)."""
 
     def __init__(self, Z1, Z2, Rbond, lmax_per_m, nelem, nnodes=15, Rmax=40.0, igrid=4, zexp=1.0, nquad=0,
-                 device=0):
+                 device=0, tei_on_device=False):
+        """tei_on_device: compute_tei() evaluates the in-element two-electron kernels on the GPU `device`
+        (hfq_tables_diatomic_device) instead of the host."""
         super().__init__(device)
         self._args = (Z1, Z2, Rbond, list(lmax_per_m), nelem, nnodes, Rmax, igrid, zexp, nquad)
+        self._tei_device = device if tei_on_device else None
 
     def _make_tables(self):
-        return Tables.diatomic(*self._args)
+        return Tables.diatomic(*self._args, device=self._tei_device)
 
     def set_absm_symmetric(self, sym):
         self._absm = bool(sym)

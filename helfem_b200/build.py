@@ -12,8 +12,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhelfemqc_b200.so")
-SOURCES = ["fem.cpp", "special.cpp", "atomic_setup.cpp", "diatomic_setup.cpp", "grid_setup.cpp", "comm.cpp", "engine.cu", "grid.cu", "solver.cu", "capi.cpp"]
-HEADERS = ["fem.h", "special.h", "tables.h", "engine.h", "grid.h", "comm.h", "kernels.cuh", "xc_builtin.cuh", "../../include/helfem_b200.h"]
+SOURCES = ["fem.cpp", "special.cpp", "atomic_setup.cpp", "diatomic_setup.cpp", "grid_setup.cpp", "comm.cpp", "engine.cu", "grid.cu", "solver.cu", "tei_device.cu", "capi.cpp"]
+HEADERS = ["fem.h", "special.h", "tables.h", "engine.h", "grid.h", "comm.h", "tei_device.h", "kernels.cuh", "xc_builtin.cuh", "../../include/helfem_b200.h"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
          "-Xcompiler", "-fPIC,-fopenmp,-O3", "--expt-relaxed-constexpr"]

@@ -215,6 +215,25 @@ int hfq_tables_diatomic(hfq_tables **out, int Z1, int Z2, double Rbond, const in
   });
 }
 
+int hfq_tables_diatomic_device(hfq_tables **out, int Z1, int Z2, double Rbond, const int *lmax_per_m, int nm, int nelem,
+                               int nnodes, double Rmax, int igrid, double zexp, int nquad, int device) {
+  if (!out || !lmax_per_m || nm < 1 || nelem < 1 || nnodes < 2 || nnodes > 16 || !(Rbond > 0.0) || !(Rmax > 0.5 * Rbond) ||
+      device < 0)
+    return fail(HFQ_ERR_INVALID, "hfq_tables_diatomic_device: invalid argument");
+  for (int m = 0; m < nm; m++)
+    if (lmax_per_m[m] < m) return fail(HFQ_ERR_INVALID, "hfq_tables_diatomic_device: lmax(|m|) < |m|");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device >= ndev)
+    return fail(HFQ_ERR_CUDA, "hfq_tables_diatomic_device: no such CUDA device");
+  return guarded([&] {
+    auto *h = new hfq_tables;
+    h->t = hfq::build_diatomic_tables(Z1, Z2, Rbond, std::vector<int>(lmax_per_m, lmax_per_m + nm), nelem, nnodes,
+                                      Rmax, igrid, zexp, nquad, device);
+    *out = h;
+    return HFQ_OK;
+  });
+}
+
 int hfq_tables_from_arrays(hfq_tables **out, const hfq_tables_desc *d) {
   if (!out || !d || !d->efirst || !d->en || !d->lval || !d->mval || !d->lmL || !d->lmM || !d->pref || !d->rank ||
       !d->small_ || !d->big_ || !d->B || !d->sigma)

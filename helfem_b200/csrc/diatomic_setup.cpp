@@ -19,6 +19,7 @@
 #include "fem.h"
 #include "special.h"
 #include "tables.h"
+#include "tei_device.h"
 
 namespace hfq {
 
@@ -265,7 +266,7 @@ Mat weighted_element(const FEBasis &fe, int iel, int der, const std::vector<doub
 }  // namespace
 
 BasisTables build_diatomic_tables(int Z1, int Z2, double Rbond, const std::vector<int> &lmax_per_m, int nelem,
-                                  int nnodes, double Rmax, int igrid, double zexp, int nquad) {
+                                  int nnodes, double Rmax, int igrid, double zexp, int nquad, int device) {
   BasisTables t;
   t.kind = BasisKind::Diatomic;
   t.nch = 2;
@@ -391,6 +392,7 @@ BasisTables build_diatomic_tables(int Z1, int Z2, double Rbond, const std::vecto
       Lhard = t.lmL[i];
       Mhard = t.lmM[i];
     }
+  std::unique_ptr<TeiDevice> teidev;
   for (int iel = 0; iel < t.Nel; iel++) {
     int nconv = std::min(nseed, kOrderCap);
     std::shared_ptr<NestedRule> last;
@@ -404,6 +406,50 @@ BasisTables build_diatomic_tables(int Z1, int Z2, double Rbond, const std::vecto
         std::min(nseed, kOrderCap), kOrderCap, floor_rel, false, &nconv);
     if (!last || last->n != nconv) last = std::make_shared<NestedRule>(make_nested_rule(fe, iel, nconv));
     const NestedRule &nr = *last;
+    if (device >= 0) {
+      // every channel of the element on the GPU (tei_device.cu): the host hands over the rule's point data and the
+      // Legendre Q values at the n outer points; P at the n^2 inner points, the quadratures and the factorisations
+      // run on the device
+      if (!teidev) teidev.reset(new TeiDevice(device));
+      const int n = nr.n;
+      std::vector<double> cw((size_t)n * n), sub((size_t)n * n * nr.nbf), uw(n), bfp((size_t)nr.npair * n);
+      for (int ip = 0; ip < n; ip++) {
+        for (int q = 0; q < n; q++) cw[(size_t)ip * n + q] = nr.sublen[ip] * nr.w[q] * nr.subsh[(size_t)ip * n + q];
+        std::copy(nr.subbf[ip].a.begin(), nr.subbf[ip].a.end(), sub.begin() + (size_t)ip * n * nr.nbf);
+      }
+      for (int q = 0; q < n; q++) uw[q] = nr.mulen * nr.w[q] * nr.shmu[q];
+      for (int p = 0; p < nr.npair; p++)
+        for (int q = 0; q < n; q++) bfp[(size_t)p * n + q] = nr.bfprod(q, p);
+      TeiRuleView view;
+      view.n = n;
+      view.nbf = nr.nbf;
+      view.npair = nr.npair;
+      view.cw = cw.data();
+      view.subch = nr.subch.data();
+      view.subbf = sub.data();
+      view.uw = uw.data();
+      view.chmu = nr.chmu.data();
+      view.bfprod = bfp.data();
+      view.pi = nr.pi.data();
+      view.pj = nr.pj.data();
+      teidev->set_rule(view);
+      for (const Run &run : runs) {
+        const LegTable qo = legendre_table(run.M, run.Lhi, nr.chmu, false, true);
+        std::vector<int> Ls;
+        for (int ilm = run.lo; ilm < run.hi; ilm++) Ls.push_back(t.lmL[ilm]);
+        std::vector<TeiChannelResult> res(Ls.size());
+        teidev->run(run.M, run.Lhi, qo.Q.data(), Ls.data(), (int)Ls.size(), kCdThresh, res.data());
+        for (int ilm = run.lo; ilm < run.hi; ilm++) {
+          ChannelBlock &b = t.blocks[(size_t)ilm * t.Nel + iel];
+          TeiChannelResult &r = res[ilm - run.lo];
+          b.B = std::move(r.B);
+          b.sigma = std::move(r.sigma);
+          b.rank = r.rank;
+        }
+      }
+      if (timing) std::fprintf(stderr, "[hfq setup] element %d: nested rule order %d (device)\n", iel, nconv);
+      continue;
+    }
     for (const Run &run : runs) {
       const LegTable ps = legendre_table(run.M, run.Lhi, nr.subch, true, false);
       const LegTable qo = legendre_table(run.M, run.Lhi, nr.chmu, false, true);

@@ -399,6 +399,7 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
     for (int tri = 0; tri < 2; tri++) {
       std::vector<int64_t> &offs = tri ? s.tpair_tri_off : s.tpair_off;
       DevBuf<double> &buf = tri ? s.d_tperm_tri : s.d_tperm;
+      const int bk = tri ? dev::TP_BK_TRI : dev::TP_BK;
       offs.assign((size_t)nlm * t.Nel * t.Nel, -1);
       int64_t off = 0;
       for (int ilm = 0; ilm < nlm; ilm++)
@@ -408,7 +409,7 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
             const int Ni = t.en[ei], Nj = t.en[ej];
             const int rows = (tri && ei == ej) ? Ni * (Ni + 1) / 2 : Ni * Nj;
             offs[((size_t)ilm * t.Nel + ei) * t.Nel + ej] = off;
-            off += dev::tperm_doubles(rows, Ni * Nj);
+            off += dev::tperm_doubles(rows, Ni * Nj, bk);
           }
       std::vector<double> h((size_t)off, 0.0);
       for (int ilm = 0; ilm < nlm; ilm++)
@@ -425,7 +426,7 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
                 if (half && rj > rk) continue;
                 const int row = half ? rk * (rk + 1) / 2 + rj : rj * Nj + rk;
                 for (int col = 0; col < K; col++)
-                  h[o + dev::tperm_index(row, col, rows)] = A[((size_t)rj * Nj + rk) * K + col];
+                  h[o + dev::tperm_index(row, col, rows, bk)] = A[((size_t)rj * Nj + rk) * K + col];
               }
           }
       buf.upload(h, &dev_bytes_);
@@ -434,13 +435,14 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
   for (int tri = 0; tri < 2; tri++) {
     std::vector<int64_t> &offs = tri ? s.tperm_tri_off : s.tperm_off;
     DevBuf<double> &buf = tri ? s.d_tperm_tri : s.d_tperm;
+    const int bk = tri ? dev::TP_BK_TRI : dev::TP_BK;
     offs.assign((size_t)nlm * t.Nel, 0);
     int64_t off = 0;
     for (int ilm = 0; ilm < nlm; ilm++)
       for (int e = 0; e < t.Nel; e++) {
         const int n = t.en[e], rows = tri ? n * (n + 1) / 2 : n * n;
         offs[(size_t)ilm * t.Nel + e] = off;
-        off += dev::tperm_doubles(rows, s.nab * n * n);
+        off += dev::tperm_doubles(rows, s.nab * n * n, bk);
       }
     buf.alloc((size_t)off, &dev_bytes_);
     CK(cudaMemsetAsync(buf.p, 0, (size_t)off * sizeof(double), stream_));
@@ -449,7 +451,7 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
         const int n = t.en[e], rows = tri ? n * (n + 1) / 2 : n * n;
         dev::k_build_tperm<<<rows, 256, 0, stream_>>>(
             s.d_B.p + s.B_off[(size_t)ilm * t.Nel + e], s.d_sigma.p + s.sig_off[(size_t)ilm * t.Nel + e], n,
-            s.ranks[(size_t)ilm * t.Nel + e], t.nch, t.kind == BasisKind::Atomic ? 1 : 0, tri,
+            s.ranks[(size_t)ilm * t.Nel + e], t.nch, t.kind == BasisKind::Atomic ? 1 : 0, tri, bk,
             buf.p + offs[(size_t)ilm * t.Nel + e]);
       }
     CK(cudaGetLastError());
@@ -520,7 +522,8 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
     s.tg_maxM = 0;
     for (int e = 0; e < t.Nel; e++) s.tg_maxM = std::max(s.tg_maxM, t.en[e] * t.en[e]);
     if (s.tg_maxM > 256) throw std::runtime_error("elements with more than 16 radial functions are not supported");
-    CK(cudaFuncSetAttribute(dev::k_tgemm_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(dev::k_tgemm_ws<dev::TP_BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(dev::k_tgemm_ws<dev::TP_BK_TRI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   }
   s.d_zrow.upload(std::vector<double>(64, 0.0), &dev_bytes_);
   // opt-in shared memory of the fold kernel this basis uses (a per-device attribute: set by every engine)
@@ -727,19 +730,20 @@ void Engine::jk_dev(const double *dP, int64_t ldP, double kscale, double *dJ, in
 // ranks; the unpack (dense K, boundary removal, mirrors) then runs everywhere.
 struct ExchangeBatch {
   DevBuf<dev::FoldTask> tasks;
-  DevBuf<dev::GemmItem> gitems;
-  DevBuf<dev::GemmEntry> gentries;
+  DevBuf<dev::GemmItem> gitems;     // in-element items: first the ngitems_tri items of the symmetric-density layout
+  DevBuf<dev::GemmEntry> gentries;  // (A tiles of TP_BK_TRI columns), then the others (TP_BK) -- one launch each
   DevBuf<dev::OffItem> oitems;
   DevBuf<dev::OffEntry> oentries;
-  int ntasks = 0, ngitems = 0, noitems = 0;
+  int ntasks = 0, ngitems = 0, ngitems_tri = 0, noitems = 0;
+  int maxM_tri = 8, maxM_full = 8;
   int maxpix = 0;        // longest pixel list of a task
   int64_t totpix = 0;    // pixels folded by the batch
 };
 struct ExchangePlan {
   std::string key;
   std::vector<std::unique_ptr<ExchangeBatch>> batches;
-  std::vector<int> splist, op_src, op_tri;
-  DevBuf<int> d_op_src, d_op_tri, d_blocks;   // device copies + angular blocks (j | k << 16) that can be non-zero
+  std::vector<int> splist, op_src, op_tri, op_ldk;
+  DevBuf<int> d_op_src, d_op_tri, d_op_ldk, d_blocks;   // device copies + angular blocks (j | k << 16) that can be non-zero
   DevBuf<int64_t> d_unit_off;                 // [(active op * Nel + ei) * Nel + ej] offset in Kc or -1
   DevBuf<dev::ReduceDesc> d_reduce;
   DevBuf<int> d_pixlist;                      // pixel lists of the fold tasks (one per distinct set of owned element pairs)
@@ -894,6 +898,7 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
               ft.spp = si * ns + sl;
               ft.L = L;
               ft.rslot = 0;
+              ft.ldk = round_up(s.sec_span[sk], 2);
               ft.pix0 = ft.npix = 0;
               ft.fac = t.pref[ilm] * ((t.sign_by_M && (M & 1)) ? -1.0 : 1.0);
               w.tasks.push_back(ft);
@@ -910,6 +915,8 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
     for (int a = 0; a < nactive; a++) np->op_src[work[a].op] = a;
     np->op_tri.assign((size_t)ns * ns, 0);
     for (int a = 0; a < nactive; a++) np->op_tri[a] = work[a].tri ? 1 : 0;
+    np->op_ldk.assign((size_t)ns * ns, s.NP);
+    for (int a = 0; a < nactive; a++) np->op_ldk[a] = round_up(s.sec_span[work[a].op % ns], 2);
     // ---- units = (active output pair, element pair); ownership
     struct Unit {
       int a, ei, ej, rows, ncol;
@@ -921,7 +928,7 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
     const bool by_pair = nshards > 1 && Nel <= 8;   // else whole output pairs are dealt (regmask has 64 bits)
     for (int a = 0; a < nactive; a++) {
       const OpWork &w = work[a];
-      const int ncol = s.sec_span[w.op / ns] * s.NP;
+      const int ncol = s.sec_span[w.op / ns] * round_up(s.sec_span[w.op % ns], 2);
       const double ntask = (double)w.tasks.size();
       for (int ei = 0; ei < Nel; ei++)
         for (int ej = 0; ej < Nel; ej++) {
@@ -1017,12 +1024,14 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
     // K-split of the in-element GEMM: each (unit, 64-column tile) is cut into S chunks of its task list, each
     // chunk accumulating into its own partial buffer (partial 0 = Kc itself; the others are summed into it by
     // k_reduce_partials), so that the CTAs of a launch fill whole waves of the 148 SMs.
+    // The CTAs of a launch differ in length (task counts, partial column tiles), so among splits that fill the waves
+    // about equally well the finer one balances better: a small bonus per chunk breaks the ties towards it.
     int S = 1;
     if (own_gemm_ctas > 0) {
       double best = 0.0;
       for (int c = 1; c <= 8; c++) {
-        const double u = (double)own_gemm_ctas * c, eff = u / (std::ceil(u / 148.0) * 148.0);
-        if (eff > best + 0.02) {
+        const double u = (double)own_gemm_ctas * c, eff = u / (std::ceil(u / 148.0) * 148.0) + 0.004 * c;
+        if (eff > best) {
           best = eff;
           S = c;
         }
@@ -1066,6 +1075,7 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
       np->d_blocks.upload(blocks, &dev_bytes_);
       np->d_op_src.upload(np->op_src, &dev_bytes_);
       np->d_op_tri.upload(np->op_tri, &dev_bytes_);
+      np->d_op_ldk.upload(np->op_ldk, &dev_bytes_);
     }
     {
       size_t free_b = 0, total_b = 0;
@@ -1098,7 +1108,7 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
       std::vector<dev::GemmEntry> gentries;
       std::vector<dev::OffItem> oitems;
       std::vector<dev::OffEntry> oentries;
-      int batch_maxpix = 0;
+      int batch_maxpix = 0, batch_maxM_tri = 8, batch_maxM_full = 8;
       int64_t batch_totpix = 0;
       size_t open = 0;
       for (size_t wi = 0; wi < work.size(); wi++) open += !work[wi].own_pairs.empty() && done[wi] < work[wi].tasks.size();
@@ -1126,7 +1136,8 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
           const int ei = w.own_pairs[pi] / Nel, ej = w.own_pairs[pi] % Nel;
           const int Ni = t.en[ei], Nj = t.en[ej];
           const int64_t koff = own_off[wi][pi];
-          const int ncol = s.sec_span[w.op / ns] * s.NP;   // columns (pos_j, pos_k) with pos_j past the sector are padding
+          // dense columns (pos_j, pos_k) = pos_j * ldk + pos_k, ldk = even number of positions of the column sector
+          const int ncol = s.sec_span[w.op / ns] * round_up(s.sec_span[w.op % ns], 2);
           if (ei == ej || t.pairwise()) {
             // in-element item (tensor-core GEMM against the dense exchange-ordered kernel; for pair-tensor
             // tables (erfc) every element pair), S chunks; chunk 0 always gets work
@@ -1142,8 +1153,9 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
               gi.browoff = t.pairwise() ? s.d_browoff_P.p + s.browoff_P_first[(size_t)ei * Nel + ej]
                                         : s.d_browoff_T.p + s.browoff_T_first[ei];
               gi.M = half ? Ni * (Ni + 1) / 2 : Ni * Nj;
-              np->maxM = std::max(np->maxM, gi.M);
-              gi.N = ncol;
+              gi.ldb = w.tri ? 1 : 0;   // (unused by the kernel) layout of the item's A tiles: 1 = TP_BK_TRI
+              (w.tri ? batch_maxM_tri : batch_maxM_full) = std::max(w.tri ? batch_maxM_tri : batch_maxM_full, gi.M);
+              gi.N = round_up(ncol, 8);
               gi.K = s.nab * Ni * Nj;
               gi.ent0 = (int)gentries.size();
               for (size_t k = k0; k < k1; k++) {
@@ -1163,7 +1175,6 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
               gi.ent1 = (int)gentries.size();
               gi.accumulate = st_flag ? 1 : 0;
               st_flag = 1;
-              gi.ldb = 0;
               gi.ldc = s.NB;
               gi.alpha = 1.0;
               gitems.push_back(gi);
@@ -1185,7 +1196,7 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
             oi.ncol = ncol;
             oitems.push_back(oi);
             const double per = 2.0 * t.nch * take * ((double)Ni * Nj * t.nch * Nj + (double)Ni * Nj * Ni);
-            np->fl_off += per * s.NB;
+            np->fl_off += per * round_up(ncol, 16);
             np->al_off += per * s.sec_n[w.op / ns] * s.sec_n[w.op % ns];
           }
         }
@@ -1198,8 +1209,11 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
       // longest items first: CTAs are dispatched in block-index order, so the tail of the launch is made of
       // the cheapest items (accumulating items of one unit never share a launch, order is free)
       std::stable_sort(gitems.begin(), gitems.end(), [](const dev::GemmItem &a, const dev::GemmItem &b) {
+        if (a.ldb != b.ldb) return a.ldb > b.ldb;   // the two A layouts run as two launches
         return (double)a.M * a.N * a.K * (a.ent1 - a.ent0) > (double)b.M * b.N * b.K * (b.ent1 - b.ent0);
       });
+      int ntri = 0;
+      for (auto &gi : gitems) ntri += gi.ldb ? 1 : 0;
       auto bt = std::make_unique<ExchangeBatch>();
       bt->tasks.upload(tasks, &dev_bytes_);
       bt->gitems.upload(gitems, &dev_bytes_);
@@ -1208,6 +1222,9 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
       bt->oentries.upload(oentries, &dev_bytes_);
       bt->ntasks = (int)tasks.size();
       bt->ngitems = (int)gitems.size();
+      bt->ngitems_tri = ntri;
+      bt->maxM_tri = batch_maxM_tri;
+      bt->maxM_full = batch_maxM_full;
       bt->noitems = (int)oitems.size();
       bt->maxpix = batch_maxpix;
       bt->totpix = batch_totpix;
@@ -1234,13 +1251,26 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
     CK(cudaEventRecord(s.ev[3], st));
     if (bt.ngitems) {
       // in-element exchange: one CTA tile covers all Ni^2 rows (R rows are read once)
-      const dim3 grid(s.NB / 64, (unsigned)bt.ngitems);
-      // stages of the shared-memory ring: as many as fit in 227 KB for the largest A tile of the plan, at most 4
-      int stages = 4;
-      while (stages > 2 && dev::tgemm_ws_smem(plan->maxM, stages) > 227 * 1024) stages--;
-      dev::k_tgemm_ws<<<grid, 288, dev::tgemm_ws_smem(plan->maxM, stages), st>>>(bt.gitems.p, bt.gentries.p, s.d_zrow.p,
-                                                                                 stages, plan->maxM);
-      CK(cudaGetLastError());
+      // stages of the shared-memory ring: as many as fit in 227 KB for the largest A tile of the launch, at most 4
+      auto stages_for = [](int maxM, int bk) {
+        int stages = 4;
+        while (stages > 2 && dev::tgemm_ws_smem(maxM, stages, bk) > 227 * 1024) stages--;
+        return stages;
+      };
+      if (bt.ngitems_tri) {
+        const int ns_ = stages_for(bt.maxM_tri, dev::TP_BK_TRI);
+        dev::k_tgemm_ws<dev::TP_BK_TRI><<<dim3(s.NB / 64, (unsigned)bt.ngitems_tri), 288,
+                                         dev::tgemm_ws_smem(bt.maxM_tri, ns_, dev::TP_BK_TRI), st>>>(
+            bt.gitems.p, bt.gentries.p, s.d_zrow.p, ns_, bt.maxM_tri);
+        CK(cudaGetLastError());
+      }
+      if (bt.ngitems > bt.ngitems_tri) {
+        const int ns_ = stages_for(bt.maxM_full, dev::TP_BK);
+        dev::k_tgemm_ws<dev::TP_BK><<<dim3(s.NB / 64, (unsigned)(bt.ngitems - bt.ngitems_tri)), 288,
+                                     dev::tgemm_ws_smem(bt.maxM_full, ns_, dev::TP_BK), st>>>(
+            bt.gitems.p + bt.ngitems_tri, bt.gentries.p, s.d_zrow.p, ns_, bt.maxM_full);
+        CK(cudaGetLastError());
+      }
     }
     CK(cudaEventRecord(s.ev[4], st));
     if (bt.noitems) {
@@ -1256,9 +1286,10 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
     }
     CK(cudaEventRecord(s.ev[5], st));
     if (plan->batches.size() > 1) CK(cudaStreamSynchronize(st));   // the timing events are re-used by the next batch
-    tm_.launches += 1 + (bt.ngitems ? 1 : 0) + (bt.noitems ? 1 : 0);
+    const int ngl = (bt.ngitems_tri ? 1 : 0) + (bt.ngitems > bt.ngitems_tri ? 1 : 0);
+    tm_.launches += 1 + ngl + (bt.noitems ? 1 : 0);
     tm_.launches_fold++;
-    tm_.launches_tgemm += bt.ngitems ? 1 : 0;
+    tm_.launches_tgemm += ngl;
     tm_.launches_offdiag += bt.noitems ? 1 : 0;
     if (plan->batches.size() > 1) {
       float ms;
@@ -1280,7 +1311,7 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
   if (comm_ && plan->seg > 0) comm_->all_gather_inplace(s.d_Kc.p, (size_t)plan->seg, st);
   CK(cudaStreamWaitEvent(st, s.ev_kzero, 0));
   if (plan->nblocks) {
-    dev::UnpackDev u{plan->d_op_src.p, plan->d_op_tri.p, plan->d_blocks.p, plan->d_unit_off.p, s.d_ang_sec.p, s.d_ang_pos.p,
+    dev::UnpackDev u{plan->d_op_src.p, plan->d_op_tri.p, plan->d_op_ldk.p, plan->d_blocks.p, plan->d_unit_off.p, s.d_ang_sec.p, s.d_ang_pos.p,
                      s.kscale};
     dev::k_unpack_K<<<plan->nblocks, 256, 0, st>>>(s.bd, u, s.d_Kc.p, dK, ldK);
     CK(cudaGetLastError());

@@ -141,6 +141,8 @@ struct FoldTask {
   int spj, spk, spp;   // sector pairs of the two coupling tables and of P
   int L;               // multipole order (index into the coupling tables)
   int rslot;           // slot in the R buffer
+  int ldk;             // row stride of the folded block R[j][k] inside its NP*NP slot: the (even) number of positions
+                       // of the output column sector, so that the consumers see span_j * ldk dense columns
   int pix0, npix;      // the pixels (ri, rl) to fold: pixlist[pix0 .. pix0 + npix).  Not all of them in general: a
                        // symmetric-density diagonal output pair needs el(ri) <= el(rl) only (mirrored by the unpack),
                        // and under owner-computes sharding a rank folds the element pairs it builds
@@ -251,9 +253,10 @@ k_fold(BasisDev b, const FoldTask *__restrict__ tasks, const int *__restrict__ p
 #pragma unroll
         for (int n = 0; n < NT; n++) dmma(c[n][0], c[n][1], a, B[n * 8 * LD + kk]);
       }
-      double *out = Rdst + ((int64_t)ab * b.Npix + plist[pg + s]) * gstride + (rt * 8 + lr) * NP + 2 * lc;
+      double *out = Rdst + ((int64_t)ab * b.Npix + plist[pg + s]) * gstride + (rt * 8 + lr) * t.ldk + 2 * lc;
 #pragma unroll
       for (int n = 0; n < NT; n++) {
+        if (n * 8 + 2 * lc >= t.ldk) continue;   // column past the sector (ldk is even: both halves or none)
         double2 v;
         v.x = t.fac * c[n][0];
         v.y = t.fac * c[n][1];
@@ -365,13 +368,14 @@ k_fold_reg(BasisDev b, const FoldTask *__restrict__ tasks, const int *__restrict
               dmma(c2[rtj][rtk][0], c2[rtj][rtk][1], ga[rtj][ni].x, c1[bb][rtk][ni][0]);
               dmma(c2[rtj][rtk][0], c2[rtj][rtk][1], ga[rtj][ni].y, c1[bb][rtk][ni][1]);
             }
-        double *out = Rdst + ((int64_t)(aa * NCH + bb) * b.Npix + pix) * gstride + lr * NP + 2 * lc;
+        double *out = Rdst + ((int64_t)(aa * NCH + bb) * b.Npix + pix) * gstride + lr * t.ldk + 2 * lc;
 #pragma unroll
         for (int rtj = 0; rtj < NT; rtj++)
 #pragma unroll
           for (int rtk = 0; rtk < NT; rtk++)
-            *reinterpret_cast<double2 *>(out + rtj * 8 * NP + rtk * 8) =
-                make_double2(c2[rtj][rtk][0], c2[rtj][rtk][1]);
+            if (rtk * 8 + 2 * lc < t.ldk)   // columns past the sector are not stored (ldk is even)
+              *reinterpret_cast<double2 *>(out + rtj * 8 * t.ldk + rtk * 8) =
+                  make_double2(c2[rtj][rtk][0], c2[rtj][rtk][1]);
       }
     }
   }
@@ -515,11 +519,17 @@ k_gemm(const GemmItem *__restrict__ items, const GemmEntry *__restrict__ entries
 // are XOR-swizzled with (row & 7) so that the DMMA A-fragment reads (8 rows x 4 consecutive k)
 // hit every bank exactly twice (= the 2-wavefront minimum for 256 bytes).  Columns >= K are zero.
 // ---------------------------------------------------------------------------
-constexpr int TP_BK = 32;
-__host__ __device__ inline int64_t tperm_tile_doubles(int nn) { return (int64_t)nn * TP_BK; }
-__host__ __device__ inline int64_t tperm_doubles(int nn, int K) { return (int64_t)((K + TP_BK - 1) / TP_BK) * nn * TP_BK; }
-__host__ __device__ inline int64_t tperm_index(int row, int col, int nn) {
-  return (int64_t)(col / TP_BK) * nn * TP_BK + (int64_t)row * TP_BK + ((col % TP_BK) ^ (4 * (row & 7)));
+constexpr int TP_BK = 32;       // general layout (all M = Ni * Nj rows), swizzled
+#ifndef HFQ_TP_BK_TRI
+#define HFQ_TP_BK_TRI 36
+#endif
+constexpr int TP_BK_TRI = HFQ_TP_BK_TRI;   // symmetric-density layout (rows rj <= rk): K = nab * 15^2 = 900 = 25 chunks, no K padding;
+                                // the row stride of 36 doubles = 4 banks already spreads the 8 fragment rows over all
+                                // 32 banks, so this layout is not swizzled
+__host__ __device__ inline int64_t tperm_doubles(int nn, int K, int bk = TP_BK) { return (int64_t)((K + bk - 1) / bk) * nn * bk; }
+__host__ __device__ inline int64_t tperm_index(int row, int col, int nn, int bk = TP_BK) {
+  const int c = col % bk;
+  return (int64_t)(col / bk) * nn * bk + (int64_t)row * bk + (bk == TP_BK ? (c ^ (4 * (row & 7))) : c);
 }
 
 // ---------------------------------------------------------------------------
@@ -529,7 +539,7 @@ __host__ __device__ inline int64_t tperm_index(int row, int col, int nn) {
 // grid (rows); stored at tperm_index(row, ab*nn + ri*n + rl, rows)
 // ---------------------------------------------------------------------------
 static __global__ void k_build_tperm(const double *__restrict__ B, const double *__restrict__ sigma, int n, int rank, int nch,
-                              int out_fast, int tri, double *__restrict__ dst) {
+                              int out_fast, int tri, int bk, double *__restrict__ dst) {
   // tri: rows are the pairs rj <= rk only, row t = rk (rk + 1) / 2 + rj (symmetric densities)
   const int row = blockIdx.x, nn = n * n;
   int rj, rk;
@@ -550,7 +560,7 @@ static __global__ void k_build_tperm(const double *__restrict__ B, const double 
     double s = 0.0;
     for (int p = 0; p < rank; p++) s += sigma[p] * b1[p * ldB] * b2[p * ldB];
     const double sgn = (nch == 2 && a != bb) ? -1.0 : 1.0;
-    dst[tperm_index(row, col, nrows)] = sgn * s;
+    dst[tperm_index(row, col, nrows, bk)] = sgn * s;
   }
 }
 
@@ -776,74 +786,6 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 // smaller than the padded column count: column tiles past it are skipped.  NS = stages that fit
 // (3 for the 15-node elements).
 // ---------------------------------------------------------------------------
-// k-steps of one stage for one consumer warp of k_tgemm_ws: NRT row tiles x NCJ column tiles.
-// Fragments of k-step ks+1 are fetched while the DMMAs of ks issue.  The tile counts are template
-// parameters because a predicated-off DMMA still occupies the tensor pipe (measured: ncu r01d).
-template <int NCJ, int NRT>
-__device__ __forceinline__ void tgemm_ws_ksteps(double (&acc)[8][4][2], const double *__restrict__ as,
-                                                const double *__restrict__ bs, int lr) {
-  constexpr int BK = TP_BK, LDB_S = 68;
-  double bf[2][NCJ], af[2][NRT];
-#pragma unroll
-  for (int j = 0; j < NCJ; j++) bf[0][j] = bs[j * 8];
-#pragma unroll
-  for (int i = 0; i < NRT; i++) af[0][i] = as[i * 32 * BK + 4 * lr];
-#pragma unroll
-  for (int ks = 0; ks < BK / 4; ks++) {
-    const int cur = ks & 1, nxt = cur ^ 1;
-    if (ks + 1 < BK / 4) {
-      const int ko = 4 * ((ks + 1) ^ lr);
-#pragma unroll
-      for (int j = 0; j < NCJ; j++) bf[nxt][j] = bs[(ks + 1) * 4 * LDB_S + j * 8];
-#pragma unroll
-      for (int i = 0; i < NRT; i++) af[nxt][i] = as[i * 32 * BK + ko];
-    }
-#pragma unroll
-    for (int i = 0; i < NRT; i++)
-#pragma unroll
-      for (int j = 0; j < NCJ; j++) dmma(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
-  }
-}
-
-// Balanced variant for warps that own all 4 column tiles of their column group.  The row tiles of the item are
-// dealt to the 4 row groups in full rounds (NF tiles per warp: rg, rg + 4, ..); the REM = (row tiles mod 4)
-// left-over row tiles are cut by COLUMN tile instead: left-over tile e goes to the warp whose local column e it
-// meets, and a warp's local column j is the actual column tile (j + rg) & 3 -- so every warp runs exactly
-// NF*4 + REM DMMAs per k-step (M = 120: 15 instead of 16/16/16/12; the four scheduler partitions stay level).
-// bsj[j] = B fragment base of local column j; ax = A fragment base of the first left-over row tile.
-template <int NF, int REM>
-__device__ __forceinline__ void tgemm_ws_ksteps_bal(double (&acc)[8][4][2], double (&ex)[4][2],
-                                                    const double *__restrict__ as, const double *__restrict__ ax,
-                                                    const double *__restrict__ bs, const int (&bcol)[4], int lr) {
-  constexpr int BK = TP_BK, LDB_S = 68, NE = REM > 0 ? REM : 1, NFF = NF > 0 ? NF : 1;
-  double bf[2][4], af[2][NFF], ae[2][NE];
-#pragma unroll
-  for (int j = 0; j < 4; j++) bf[0][j] = bs[bcol[j]];
-#pragma unroll
-  for (int i = 0; i < NF; i++) af[0][i] = as[i * 32 * BK + 4 * lr];
-#pragma unroll
-  for (int e = 0; e < REM; e++) ae[0][e] = ax[e * 8 * BK + 4 * lr];
-#pragma unroll
-  for (int ks = 0; ks < BK / 4; ks++) {
-    const int cur = ks & 1, nxt = cur ^ 1;
-    if (ks + 1 < BK / 4) {
-      const int ko = 4 * ((ks + 1) ^ lr);
-#pragma unroll
-      for (int j = 0; j < 4; j++) bf[nxt][j] = bs[(ks + 1) * 4 * LDB_S + bcol[j]];
-#pragma unroll
-      for (int i = 0; i < NF; i++) af[nxt][i] = as[i * 32 * BK + ko];
-#pragma unroll
-      for (int e = 0; e < REM; e++) ae[nxt][e] = ax[e * 8 * BK + ko];
-    }
-#pragma unroll
-    for (int i = 0; i < NF; i++)
-#pragma unroll
-      for (int j = 0; j < 4; j++) dmma(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
-#pragma unroll
-    for (int e = 0; e < REM; e++) dmma(ex[e][0], ex[e][1], ae[cur][e], bf[cur][e]);
-  }
-}
-
 // The consumer loop of one warp, specialised at compile time on its tile counts (the dispatch happens once per CTA,
 // outside the stage loop, so that every variant keeps its accumulators in registers).
 //   BAL:  the warp owns 4 column tiles: NF full row tiles + REM left-over units
@@ -857,9 +799,10 @@ struct TgemmWarp {
   int nrt_tot, ncj;
 };
 
-template <int NF, int REM, bool BAL, int NCJ = 4>
+template <int BK, int NF, int REM, bool BAL, int NCJ = 4>
 __device__ __forceinline__ void tgemm_ws_consume(const TgemmWarp &w, const GemmItem &it, int bn) {
-  constexpr int BK = TP_BK, LDB_S = 68, NFF = NF > 0 ? NF : 1;
+  constexpr int LDB_S = 68, NFF = NF > 0 ? NF : 1;
+  constexpr bool SWZ = BK == TP_BK;   // A fragment of k-step ks sits at row*BK + lc + 4*ks, ks XOR lr in the swizzled layout
   double acc[NFF][4][2], ex[4][2];
 #pragma unroll
   for (int i = 0; i < NFF; i++)
@@ -875,7 +818,6 @@ __device__ __forceinline__ void tgemm_ws_consume(const TgemmWarp &w, const GemmI
   for (int step = 0; step < w.nsteps; step++) {
     mbar_wait(w.full + stage, phase);
     if (NF > 0 || REM > 0) {
-      // A fragment of k-step ks sits at row*BK + lc + 4*(ks ^ lr)   (tperm_index swizzle)
       const double *as = w.As + (size_t)stage * w.A_STAGE + (w.rg * 8 + w.lr) * BK + w.lc;
       const double *bs = w.Bs + stage * w.B_STAGE + w.lc * LDB_S + w.cg * 32 + w.lr;
       if (BAL) {
@@ -884,14 +826,14 @@ __device__ __forceinline__ void tgemm_ws_consume(const TgemmWarp &w, const GemmI
 #pragma unroll
         for (int j = 0; j < 4; j++) bf[0][j] = bs[bcol[j]];
 #pragma unroll
-        for (int i = 0; i < NF; i++) af[0][i] = as[i * 32 * BK + 4 * w.lr];
+        for (int i = 0; i < NF; i++) af[0][i] = as[i * 32 * BK + (SWZ ? 4 * w.lr : 0)];
 #pragma unroll
-        for (int e = 0; e < REM; e++) ae[0][e] = ax[e * 8 * BK + 4 * w.lr];
+        for (int e = 0; e < REM; e++) ae[0][e] = ax[e * 8 * BK + (SWZ ? 4 * w.lr : 0)];
 #pragma unroll
         for (int ks = 0; ks < BK / 4; ks++) {
           const int cur = ks & 1, nxt = cur ^ 1;
           if (ks + 1 < BK / 4) {
-            const int ko = 4 * ((ks + 1) ^ w.lr);
+            const int ko = SWZ ? 4 * ((ks + 1) ^ w.lr) : 4 * (ks + 1);
 #pragma unroll
             for (int j = 0; j < 4; j++) bf[nxt][j] = bs[(ks + 1) * 4 * LDB_S + bcol[j]];
 #pragma unroll
@@ -911,12 +853,12 @@ __device__ __forceinline__ void tgemm_ws_consume(const TgemmWarp &w, const GemmI
 #pragma unroll
         for (int j = 0; j < NCJ; j++) bf[0][j] = bs[j * 8];
 #pragma unroll
-        for (int i = 0; i < NF; i++) af[0][i] = as[i * 32 * BK + 4 * w.lr];
+        for (int i = 0; i < NF; i++) af[0][i] = as[i * 32 * BK + (SWZ ? 4 * w.lr : 0)];
 #pragma unroll
         for (int ks = 0; ks < BK / 4; ks++) {
           const int cur = ks & 1, nxt = cur ^ 1;
           if (ks + 1 < BK / 4) {
-            const int ko = 4 * ((ks + 1) ^ w.lr);
+            const int ko = SWZ ? 4 * ((ks + 1) ^ w.lr) : 4 * (ks + 1);
 #pragma unroll
             for (int j = 0; j < NCJ; j++) bf[nxt][j] = bs[(ks + 1) * 4 * LDB_S + j * 8];
 #pragma unroll
@@ -963,37 +905,38 @@ __device__ __forceinline__ void tgemm_ws_consume(const TgemmWarp &w, const GemmI
   }
 }
 
-template <int REM, bool BAL, int NCJ = 4>
+template <int BK, int REM, bool BAL, int NCJ = 4>
 __device__ __forceinline__ void tgemm_ws_dispatch_nf(const TgemmWarp &w, const GemmItem &it, int bn, int nf) {
   switch (nf) {
-    case 8: tgemm_ws_consume<8, REM, BAL, NCJ>(w, it, bn); break;
-    case 7: tgemm_ws_consume<7, REM, BAL, NCJ>(w, it, bn); break;
-    case 6: tgemm_ws_consume<6, REM, BAL, NCJ>(w, it, bn); break;
-    case 5: tgemm_ws_consume<5, REM, BAL, NCJ>(w, it, bn); break;
-    case 4: tgemm_ws_consume<4, REM, BAL, NCJ>(w, it, bn); break;
-    case 3: tgemm_ws_consume<3, REM, BAL, NCJ>(w, it, bn); break;
-    case 2: tgemm_ws_consume<2, REM, BAL, NCJ>(w, it, bn); break;
-    case 1: tgemm_ws_consume<1, REM, BAL, NCJ>(w, it, bn); break;
-    default: tgemm_ws_consume<0, REM, BAL, NCJ>(w, it, bn); break;
+    case 8: tgemm_ws_consume<BK, 8, REM, BAL, NCJ>(w, it, bn); break;
+    case 7: tgemm_ws_consume<BK, 7, REM, BAL, NCJ>(w, it, bn); break;
+    case 6: tgemm_ws_consume<BK, 6, REM, BAL, NCJ>(w, it, bn); break;
+    case 5: tgemm_ws_consume<BK, 5, REM, BAL, NCJ>(w, it, bn); break;
+    case 4: tgemm_ws_consume<BK, 4, REM, BAL, NCJ>(w, it, bn); break;
+    case 3: tgemm_ws_consume<BK, 3, REM, BAL, NCJ>(w, it, bn); break;
+    case 2: tgemm_ws_consume<BK, 2, REM, BAL, NCJ>(w, it, bn); break;
+    case 1: tgemm_ws_consume<BK, 1, REM, BAL, NCJ>(w, it, bn); break;
+    default: tgemm_ws_consume<BK, 0, REM, BAL, NCJ>(w, it, bn); break;
   }
 }
 
-__host__ __device__ inline size_t tgemm_ws_smem(int M, int ns) {
-  // ns stages of (A tile [M][TP_BK] + R tile [TP_BK][68]); slack so that the row tiles past M that
-  // the last stage's warps still read stay inside the allocation; 2*ns mbarriers
-  return ((size_t)ns * ((size_t)M * TP_BK + TP_BK * 68) + (size_t)(256 - M) * TP_BK) * sizeof(double) + 16 * ns;
+__host__ __device__ inline size_t tgemm_ws_smem(int M, int ns, int bk = TP_BK) {
+  // ns stages of (A tile [M][TP_BK] + R tile [TP_BK][68]); 8 slack rows so that the last row tile (rows up to
+  // round_up(M, 8), the furthest any consumer reads) of the last stage stays inside the allocation; 2*ns mbarriers
+  return ((size_t)ns * ((size_t)M * bk + bk * 68) + (size_t)8 * bk) * sizeof(double) + 16 * ns;
 }
 
-static __global__ void __launch_bounds__(288, 1)
+template <int BK>
+__global__ void __launch_bounds__(288, 1)
 k_tgemm_ws(const GemmItem *__restrict__ items, const GemmEntry *__restrict__ entries, const double *__restrict__ zrow,
            int NS, int maxM) {
-  constexpr int BK = TP_BK, BN = 64, NW = 8, TG_MT = 8;   // row tiles per warp (M <= 256)
+  constexpr int BN = 64, NW = 8;
   constexpr int LDB_S = BN + 4, B_STAGE = BK * LDB_S;
   extern __shared__ double sm[];
   const GemmItem it = items[blockIdx.y];
   const int A_STAGE = maxM * BK;   // stage stride (largest M of the launch); rows >= it.M hold stale data
   double *Bs = sm, *As = sm + NS * B_STAGE;
-  uint64_t *full = reinterpret_cast<uint64_t *>(As + (size_t)NS * A_STAGE + (256 - maxM) * BK), *empty = full + NS;
+  uint64_t *full = reinterpret_cast<uint64_t *>(As + (size_t)NS * A_STAGE + 8 * BK), *empty = full + NS;
   const int bn = blockIdx.x * BN;
   if (bn >= it.N) return;   // column tile holds padding only
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1023,8 +966,10 @@ k_tgemm_ws(const GemmItem *__restrict__ items, const GemmEntry *__restrict__ ent
         bulk_g2s(As + (size_t)stage * A_STAGE, e.A + (int64_t)kci * it.M * BK, abytes, full + stage);
       }
       __syncwarp();
-      const double *src = (kc + lane < it.K) ? e.B + it.browoff[kc + lane] + bn : zrow;
-      bulk_g2s(Bs + stage * B_STAGE + lane * LDB_S, src, BN * 8, full + stage);
+      for (int r = lane; r < BK; r += 32) {   // one 512-byte bulk copy per R row of the stage
+        const double *src = (kc + r < it.K) ? e.B + it.browoff[kc + r] + bn : zrow;
+        bulk_g2s(Bs + stage * B_STAGE + r * LDB_S, src, BN * 8, full + stage);
+      }
       if (++kci == nkc) {
         kci = 0;
         if (++ent < it.ent1) e = entries[ent];
@@ -1063,17 +1008,17 @@ k_tgemm_ws(const GemmItem *__restrict__ items, const GemmEntry *__restrict__ ent
   if (w.ncj == 4) {
     const int nf = w.nrt_tot >> 2;
     switch (w.nrt_tot & 3) {
-      case 3: tgemm_ws_dispatch_nf<3, true>(w, it, bn, nf); break;
-      case 2: tgemm_ws_dispatch_nf<2, true>(w, it, bn, nf); break;
-      case 1: tgemm_ws_dispatch_nf<1, true>(w, it, bn, nf); break;
-      default: tgemm_ws_dispatch_nf<0, true>(w, it, bn, nf); break;
+      case 3: tgemm_ws_dispatch_nf<BK, 3, true>(w, it, bn, nf); break;
+      case 2: tgemm_ws_dispatch_nf<BK, 2, true>(w, it, bn, nf); break;
+      case 1: tgemm_ws_dispatch_nf<BK, 1, true>(w, it, bn, nf); break;
+      default: tgemm_ws_dispatch_nf<BK, 0, true>(w, it, bn, nf); break;
     }
   } else if (w.ncj > 2) {
-    tgemm_ws_dispatch_nf<0, false, 4>(w, it, bn, (w.nrt_tot - w.rg + 3) >> 2);
+    tgemm_ws_dispatch_nf<BK, 0, false, 4>(w, it, bn, (w.nrt_tot - w.rg + 3) >> 2);
   } else if (w.ncj > 0) {
-    tgemm_ws_dispatch_nf<0, false, 2>(w, it, bn, (w.nrt_tot - w.rg + 3) >> 2);
+    tgemm_ws_dispatch_nf<BK, 0, false, 2>(w, it, bn, (w.nrt_tot - w.rg + 3) >> 2);
   } else {
-    tgemm_ws_consume<0, 0, false>(w, it, bn);
+    tgemm_ws_consume<BK, 0, 0, false>(w, it, bn);
   }
 }
 
@@ -1086,6 +1031,7 @@ k_tgemm_ws(const GemmItem *__restrict__ items, const GemmEntry *__restrict__ ent
 struct UnpackDev {
   const int *op_src;        // [ns*ns] active output pair whose units hold this block (or -1: zero)
   const int *op_tri;        // [active op] 1: symmetric storage (see below)
+  const int *op_ldk;        // [active op] column index of block (pos_j, pos_k) = pos_j * ldk + pos_k (FoldTask::ldk)
   const int *blocks;        // angular blocks (j | k << 16) whose sector pair was computed
   const int64_t *unit_off;  // [(active op * Nel + ei) * Nel + ej] offset of the unit's [rows][NB] block in Kc, -1: absent
                             // (built by another rank and not gathered: the caller sums the partial matrices)
@@ -1121,8 +1067,9 @@ static __global__ void k_unpack_K(BasisDev b, UnpackDev u, const double *__restr
   double *dst = K + b.ang_off[angj] + (int64_t)b.ang_off[angk] * ld;
   const int op = u.ang_sec[angj] * b.ns + u.ang_sec[angk];
   const int src = u.op_src[op];
-  const int blk = u.ang_pos[angj] * b.NP + u.ang_pos[angk];
-  const int blkT = u.ang_pos[angk] * b.NP + u.ang_pos[angj];
+  const int ldk = src >= 0 ? u.op_ldk[src] : b.NP;
+  const int blk = u.ang_pos[angj] * ldk + u.ang_pos[angk];
+  const int blkT = u.ang_pos[angk] * ldk + u.ang_pos[angj];
   const bool tri = src >= 0 && u.op_tri[src];
   const int64_t *uo = u.unit_off + (int64_t)(src < 0 ? 0 : src) * b.Nel * b.Nel;
   for (int idx = threadIdx.x; idx < nj * nk; idx += blockDim.x) {

@@ -96,7 +96,8 @@ BasisTables build_sadatom_rs_tables(int Z, int lmax, int nelem, int nnodes, doub
                                     int rs, double param);
 // diatomic: lmax_per_m[|m|], other arguments as src/diatomic/main.cpp:60-118
 BasisTables build_diatomic_tables(int Z1, int Z2, double Rbond, const std::vector<int> &lmax_per_m, int nelem,
-                                  int nnodes, double Rmax, int igrid, double zexp, int nquad);
+                                  int nnodes, double Rmax, int igrid, double zexp, int nquad, int device = -1);
+// device >= 0: the in-element kernels and their factorisations are computed on that GPU (tei_device.cu)
 
 // Radial effective-potential ("SAP") table of the spherically averaged atom after an SCF
 // (effective_potential_table, src/sadatom/main.cpp:55-107, with coulomb_screening / xc_screening /

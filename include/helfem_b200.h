@@ -104,6 +104,14 @@ int hfq_tables_sadatom_rs(hfq_tables **out, int Z, int lmax, int nelem, int nnod
  * lmax_per_m[|m|], |m| = 0..nm-1, is the --lmax list. */
 int hfq_tables_diatomic(hfq_tables **out, int Z1, int Z2, double Rbond, const int *lmax_per_m, int nm, int nelem,
                         int nnodes, double Rmax, int igrid, double zexp, int nquad);
+/* The same with the in-element two-electron kernels computed ON THE GPU `device` (compute_tei is the
+ * dominant non-SCF cost at large lmax): nested Gauss-Chebyshev quadratures as FP64 tensor-core GEMMs and one CTA per
+ * channel for the sign-aware pivoted Cholesky (csrc/tei_device.cu; src/diatomic/quadrature.cpp:188-257,
+ * src/diatomic/basis.cpp:1382-1537).  The tables come back to the host like those of hfq_tables_diatomic; the
+ * factors agree with the host path to round-off of the quadrature sums (reconstructed kernels to ~1e-14 of their
+ * largest element).  HFQ_ERR_CUDA without that GPU: there is no silent fallback. */
+int hfq_tables_diatomic_device(hfq_tables **out, int Z1, int Z2, double Rbond, const int *lmax_per_m, int nm, int nelem,
+                               int nnodes, double Rmax, int igrid, double zexp, int nquad, int device);
 
 /* Caller-supplied caches: lets an existing HelFEM build hand over the caches its own
  * compute_tei() produced (disjoint_L/disjoint_m1L/prim_chol, src/atomic/TwoDBasis.h:83-128;
