@@ -657,6 +657,7 @@ int hfq_syev_batch(double *dA, double *dW, int n, int64_t nb, void *stream) {
 int hfq_set_host_threads(int n) {
   if (n < 1) return fail(HFQ_ERR_INVALID, "hfq_set_host_threads: n < 1");
   omp_set_num_threads(n);
+  hfq::set_host_threads(n);
   return HFQ_OK;
 }
 

@@ -2,6 +2,7 @@
 #include "engine.h"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -1581,9 +1582,21 @@ double Engine::copy_ranges_async(double *H, int64_t ldH, const double *D, const 
   return bytes;
 }
 
+namespace {
+std::atomic<int> g_host_threads{0};
+}
+void set_host_threads(int n) { g_host_threads.store(n); }
+int host_threads() {
+  const int n = g_host_threads.load();
+  return n > 0 ? n : omp_get_max_threads();
+}
+
 void Engine::zero_outside(double *H, int64_t ldH, int n, const HostRanges &hr, int cb, int ce) {
   const bool none = (int)hr.r0.size() != n;   // no pattern: everything is zero
-  const int nthr = std::max(1, omp_get_max_threads() - 2);   // leave cores to the thread that feeds the GPU
+  // leave cores to the thread that feeds the GPU.  The count set through hfq_set_host_threads is kept in a process
+  // global: this runs in a helper std::thread, whose OpenMP ICVs start from OMP_NUM_THREADS again (torchrun exports
+  // 1), not from the omp_set_num_threads of the calling thread
+  const int nthr = std::max(1, host_threads() - 2);
   if (ce < 0) ce = n;
 #pragma omp parallel for schedule(static) num_threads(nthr)
   for (int c = cb; c < ce; c++) {

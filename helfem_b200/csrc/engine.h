@@ -119,4 +119,8 @@ class Engine {
   size_t dev_bytes_ = 0;
 };
 
+// host threads for the zero-fill / copy helpers (hfq_set_host_threads); 0 = OpenMP default
+void set_host_threads(int n);
+int host_threads();
+
 }  // namespace hfq
