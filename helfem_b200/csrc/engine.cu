@@ -987,12 +987,15 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
       np->d_unit_off.upload(uoff, &dev_bytes_);
     }
     // own units per output pair
-    int own_gemm_ctas = 0;
+    int own_gemm_ctas = 0, own_off_ctas = 0;
     for (auto &u : units)
       if (u.owner == shard) {
         OpWork &w = work[u.a];
         w.own_pairs.push_back(u.ei * Nel + u.ej);
-        if (u.ei == u.ej || t.pairwise()) own_gemm_ctas += (u.ncol + 63) / 64;
+        if (u.ei == u.ej || t.pairwise())
+          own_gemm_ctas += (u.ncol + 63) / 64;
+        else
+          own_off_ctas += (u.ncol + 15) / 16;
       }
     {
       // pixel lists: the pixels (ri, rl) of the owned element pairs of an output pair (elements overlap in their
@@ -1039,6 +1042,10 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
       }
     }
     np->S = S;
+    // chunks of the cross-element items: enough CTAs for ~8 waves of the 2 x 148 resident ones, at most S (the
+    // partial buffers are shared with the in-element items)
+    int S_off = 1;
+    if (own_off_ctas > 0) S_off = std::max(1, std::min(S, (8 * 296 + own_off_ctas - 1) / own_off_ctas));
     // partial buffers 1 .. S-1: same layout as this rank's segment of Kc
     np->part_stride = np->seg;
     if (S > 1 && s.d_Kacc.n < (size_t)(S - 1) * np->seg) s.d_Kacc.alloc((size_t)(S - 1) * np->seg, &dev_bytes_);
@@ -1183,19 +1190,26 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
               np->al_tg += 2.0 * gi.M * (double)s.sec_n[w.op / ns] * s.sec_n[w.op % ns] * (double)gi.K * (k1 - k0);
             }
           } else {
-            // cross-element item (rank-1 factors), always into Kc
-            char &st_flag = started[{wi * 4096 + (size_t)w.own_pairs[pi], 0}];
-            dev::OffItem oi{};
-            oi.C = s.d_Kc.p + koff;
-            oi.ei = ei;
-            oi.ej = ej;
-            oi.ent0 = (int)oentries.size();
-            for (size_t k = 0; k < take; k++) oentries.push_back(dev::OffEntry{(int)(t0 + k), w.ilm[ti + k]});
-            oi.ent1 = (int)oentries.size();
-            oi.accumulate = st_flag ? 1 : 0;
-            st_flag = 1;
-            oi.ncol = ncol;
-            oitems.push_back(oi);
+            // cross-element items (rank-1 factors): the task list is cut into S_off chunks with their own partial
+            // accumulators (chunk 0 = Kc itself), like the in-element items, so that a rank with few units still
+            // fills the GPU (8 GPUs: ~10 units x 13 column tiles per rank against 296 resident CTAs)
+            for (int c = 0; c < S_off; c++) {
+              const size_t k0 = (take * c + S_off - 1) / S_off, k1 = (take * (c + 1) + S_off - 1) / S_off;
+              if (k1 == k0) continue;
+              char &st_flag = started[{wi * 4096 + (size_t)w.own_pairs[pi], c}];
+              dev::OffItem oi{};
+              oi.C = c == 0 ? s.d_Kc.p + koff
+                            : s.d_Kacc.p + (size_t)(c - 1) * np->part_stride + (koff - (int64_t)shard * np->seg);
+              oi.ei = ei;
+              oi.ej = ej;
+              oi.ent0 = (int)oentries.size();
+              for (size_t k = k0; k < k1; k++) oentries.push_back(dev::OffEntry{(int)(t0 + k), w.ilm[ti + k]});
+              oi.ent1 = (int)oentries.size();
+              oi.accumulate = st_flag ? 1 : 0;
+              st_flag = 1;
+              oi.ncol = ncol;
+              oitems.push_back(oi);
+            }
             const double per = 2.0 * t.nch * take * ((double)Ni * Nj * t.nch * Nj + (double)Ni * Nj * Ni);
             np->fl_off += per * round_up(ncol, 16);
             np->al_off += per * s.sec_n[w.op / ns] * s.sec_n[w.op % ns];

@@ -175,6 +175,16 @@ __global__ void k_grid_unpack(GridDev g, const double *__restrict__ Hs, const do
   }
 }
 
+// out[i] = sum_s part[s * n + i]  (K-split partial outputs of the density GEMM; combos that were not computed are summed
+// too: they are never read)
+__global__ void k_sum_partials(const double *__restrict__ part, int nparts, int64_t n, double *__restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double v = 0.0;
+    for (int s = 0; s < nparts; s++) v += part[(size_t)s * n + i];
+    out[i] = v;
+  }
+}
+
 // interleave spin components: out[p*nc + c] = in[c][p]
 __global__ void k_interleave(const double *__restrict__ a, const double *__restrict__ b, const double *__restrict__ c,
                              int nc, int64_t N, double *__restrict__ out) {
@@ -285,7 +295,8 @@ struct GridEngine::Impl {
   int64_t N = 0;
   Buf<int> d_efirst, d_en, d_bo_q, d_bo_t, d_pa, d_pb, d_pof, d_aoff, d_askip;
   Buf<double> d_w, d_sc, d_lfac, d_RR, d_RRT, d_YY, d_YYT;
-  Buf<double> d_P, d_Pe, d_Q, d_D, d_dens, d_C, d_T, d_Hs, d_Hx, d_H, d_sums, d_io, d_v;
+  Buf<double> d_P, d_Pe, d_Q, d_D, d_Dpart, d_dens, d_C, d_T, d_Hs, d_Hx, d_H, d_sums, d_io, d_v;
+  int ksplit = 1;
   Buf<dev::GemmItem> d_items;
   Buf<dev::GemmEntry> d_entries;
   bool polarized = false, pure_m = false;
@@ -429,6 +440,11 @@ GridEngine::GridEngine(const BasisTables &t, const GridTables &g, int device, cu
   s.d_Pe.alloc((size_t)2 * Nel * NA2 * NN);
   s.d_Q.alloc((size_t)2 * Nel * NA2 * NRR * nrad);
   s.d_D.alloc((size_t)NCOMBO * s.N);
+  // stage 2 of the density contracts over all coupled angular pairs (K = NA2: 10 071 for the N2 pure-m grid) into only
+  // nang x nrad outputs per element: K is cut into ksplit chunks with their own partial outputs, so that the launch
+  // has a few hundred CTAs instead of a few dozen, and k_sum_partials adds them up
+  s.ksplit = std::max(1, std::min(16, NA2 / 512));
+  if (s.ksplit > 1) s.d_Dpart.alloc((size_t)s.ksplit * NCOMBO * s.N);
   s.d_dens.alloc((size_t)2 * 6 * s.N);
   s.d_C.alloc((size_t)NCOMBO * s.N);
   s.d_T.alloc((size_t)(NCOMBO + 2) * Nel * nang * NN);
@@ -505,27 +521,34 @@ void GridEngine::density_launch(const double *Pa, int64_t ldPa, const double *Pb
         const bool need = j == 0 || ((flags & GRID_GRAD) && j >= 1 && j <= 3) ||
                           ((flags & (GRID_TAU | GRID_LAPL)) && j >= 4 && j <= 6) || ((flags & GRID_LAPL) && j == 7);
         if (!need) continue;
-        for (int e = 0; e < g.Nel; e++) {
-          dev::GemmItem it{};
-          it.C = s.d_D.p + (size_t)j * N + (size_t)e * g.npe;
-          it.browoff = s.d_bo_q.p;
-          it.M = g.nang;
-          it.N = g.nrad;
-          it.K = g.NA2;
-          it.ent0 = (int)entries.size();
-          const double *Qe = Q + (size_t)e * g.NA2 * NRR * g.nrad;
-          entries.push_back(dev::GemmEntry{s.d_YYT.p + (size_t)yyt[j] * g.nang * g.NA2, Qe + rrt[j] * g.nrad, g.NA2});
-          if (j == 7)
-            for (int x = 8; x <= 9; x++)
-              entries.push_back(dev::GemmEntry{s.d_YYT.p + (size_t)yyt[x] * g.nang * g.NA2, Qe + rrt[x] * g.nrad, g.NA2});
-          it.ent1 = (int)entries.size();
-          it.accumulate = 0;
-          it.ldc = g.nrad;
-          it.alpha = 1.0;
-          items.push_back(it);
-        }
+        for (int e = 0; e < g.Nel; e++)
+          for (int ks = 0; ks < s.ksplit; ks++) {
+            // K chunk [k0, k1) of the coupled pairs: A columns k0.., B rows k0.. (row offsets of d_bo_q are linear in k)
+            const int k0 = (int)((int64_t)g.NA2 * ks / s.ksplit), k1 = (int)((int64_t)g.NA2 * (ks + 1) / s.ksplit);
+            dev::GemmItem it{};
+            it.C = (s.ksplit > 1 ? s.d_Dpart.p + (size_t)ks * NCOMBO * N : s.d_D.p) + (size_t)j * N + (size_t)e * g.npe;
+            it.browoff = s.d_bo_q.p;
+            it.M = g.nang;
+            it.N = g.nrad;
+            it.K = k1 - k0;
+            it.ent0 = (int)entries.size();
+            const double *Qe = Q + (size_t)e * g.NA2 * NRR * g.nrad + (size_t)k0 * NRR * g.nrad;
+            entries.push_back(dev::GemmEntry{s.d_YYT.p + (size_t)yyt[j] * g.nang * g.NA2 + k0, Qe + rrt[j] * g.nrad, g.NA2});
+            if (j == 7)
+              for (int x = 8; x <= 9; x++)
+                entries.push_back(dev::GemmEntry{s.d_YYT.p + (size_t)yyt[x] * g.nang * g.NA2 + k0, Qe + rrt[x] * g.nrad, g.NA2});
+            it.ent1 = (int)entries.size();
+            it.accumulate = 0;
+            it.ldc = g.nrad;
+            it.alpha = 1.0;
+            items.push_back(it);
+          }
       }
     });
+    if (s.ksplit > 1) {
+      k_sum_partials<<<592, 256, 0, s.st>>>(s.d_Dpart.p, s.ksplit, (int64_t)NCOMBO * N, s.d_D.p);
+      CK(cudaGetLastError());
+    }
     k_grid_points<<<592, 256, 0, s.st>>>(g, s.d_D.p, flags, s.dens(sp, 0), s.dens(sp, 1), s.dens(sp, 4), s.dens(sp, 5),
                                          s.d_sums.p);
     CK(cudaGetLastError());
