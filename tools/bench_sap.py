@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--zmax", type=int, default=86)
     ap.add_argument("--out", default=None)
     ap.add_argument("--cpu-sample", type=int, default=3, help="atoms of the CPU comparator sample (0: skip)")
+    ap.add_argument("--profile", action="store_true", help="phase timers (synchronise the device around every phase)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -43,7 +44,8 @@ def main():
     batch = sap.SadatomBatchSCF(zs, device=local)
     torch.cuda.synchronize()
     t_setup = time.perf_counter() - t0
-    batch.run(maxit=3)            # warm-up (allocations, cuSOLVER handles)
+    batch.profile = args.profile
+    batch.run(maxit=3)            # warm-up (allocations, kernel attributes)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -88,7 +90,7 @@ def main():
             "iterations": iters, "all_converged": conv,
             "refilled_rank0": {str(z): [round(x, 4) for x in v] for z, v in batch.refilled.items()},
             "refill_note": "atoms whose tabulated (PBE) frozen configuration has no bound LDA-x Aufbau solution: per-l counts from a finite-temperature SCF with one chemical potential (kT 0.02 -> 0.005 Eh), then frozen again at T = 0", "scaling": "strong (elements dealt round-robin, no collective)",
-            "kernel_launches_native": batch.launches, "phase_seconds": batch.timing, "cpu_baseline": cpu, "results": os.path.relpath(out, ROOT),
+            "kernel_launches_native": batch.launches, "phase_seconds": batch.timing if batch.profile else None, "cpu_baseline": cpu, "results": os.path.relpath(out, ROOT),
             "E_Rn" if args.zmax >= 86 and 86 in zs else "E_last": float(res["E"][zs.index(max(zs))])}
     print(json.dumps(line))
     if world > 1:
