@@ -1054,8 +1054,10 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
       for (auto &u : units)
         if (u.owner == shard) {
           const int64_t n = (int64_t)u.rows * s.NB;
+          const int nparts = ((u.ei == u.ej || t.pairwise()) ? S : S_off) - 1;
+          if (nparts < 1) continue;
           for (int64_t o = 0; o < n; o += 16384)
-            rd.push_back(dev::ReduceDesc{u.off + o, u.off - (int64_t)shard * np->seg + o, (int)std::min<int64_t>(16384, n - o)});
+            rd.push_back(dev::ReduceDesc{u.off + o, u.off - (int64_t)shard * np->seg + o, (int)std::min<int64_t>(16384, n - o), nparts});
         }
       np->nreduce = (int)rd.size();
       np->d_reduce.upload(rd, &dev_bytes_);
@@ -1319,7 +1321,7 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
   // 6. reduce the K-split partials of the own units, complete Kc over the ranks, unpack
   CK(cudaEventRecord(s.ev[6], st));
   if (S > 1 && plan->nreduce) {
-    dev::k_reduce_partials<<<plan->nreduce, 256, 0, st>>>(plan->d_reduce.p, s.d_Kc.p, s.d_Kacc.p, S - 1, plan->part_stride);
+    dev::k_reduce_partials<<<plan->nreduce, 256, 0, st>>>(plan->d_reduce.p, s.d_Kc.p, s.d_Kacc.p, plan->part_stride);
     CK(cudaGetLastError());
     tm_.launches++;
   }

@@ -1045,13 +1045,14 @@ struct UnpackDev {
 struct ReduceDesc {
   int64_t dst, src;   // offsets in doubles into Kc / the partial buffer
   int n;              // doubles
+  int nparts;         // partial buffers this unit wrote (in-element units: S - 1, cross-element units: S_off - 1)
 };
 static __global__ void k_reduce_partials(const ReduceDesc *__restrict__ descs, double *__restrict__ Kc,
-                                         const double *__restrict__ part, int nparts, int64_t cstride) {
+                                         const double *__restrict__ part, int64_t cstride) {
   const ReduceDesc d = descs[blockIdx.x];
   for (int i = threadIdx.x; i < d.n; i += blockDim.x) {
     double s = Kc[d.dst + i];
-    for (int c = 0; c < nparts; c++) s += part[d.src + (int64_t)c * cstride + i];
+    for (int c = 0; c < d.nparts; c++) s += part[d.src + (int64_t)c * cstride + i];
     Kc[d.dst + i] = s;
   }
 }
