@@ -336,13 +336,14 @@ class SadatomBatchSCF:
         conv_mask[idx] = done
         return Pl, conv_mask
 
-    def run(self, maxit=150, conv=1e-10, errtol=1e-7, verbose=False, refill=True, refill_kT=(0.02, 0.005)):
+    def run(self, maxit=150, conv=1e-10, errtol=1e-7, verbose=False, refill=True, refill_kT=(0.01, 0.005)):
         """Stage 1: SCF of every atom with its frozen per-l electron counts (self.occ_l: the reference's tabulated
         ground-state configurations unless given).  Those are PBE configurations; with the exchange-only SAP
         functional a few of them have no bound Aufbau solution (Gd - Tm: the 4f level of the frozen 4f^n 6s^1
         configurations rises above zero) and cannot converge.  Stage 2 (refill): such atoms get their per-l counts
         from a finite-temperature SCF with ONE chemical potential across the l-blocks (what the reference's
-        `--occs auto` leaves to OpenOrbitalOptimizer's occupation optimisation), annealed over refill_kT, and are then
+        `--occs auto` leaves to OpenOrbitalOptimizer's occupation optimisation), annealed over refill_kT (0.01 -> 0.005 Eh
+        reaches the same counts as 0.02 -> 0.005 in two thirds of the iterations), and are then
         converged again at zero temperature with those (fractional) counts frozen -- the reference's
         fixed_per_l path (src/sadatom/scf.cpp:390-405).  self.refilled maps Z to the new counts."""
         torch = self.torch
@@ -408,3 +409,16 @@ class SadatomBatchSCF:
         # the screening integrals are host-side post-processing (like the reference's): one atom per host thread
         with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
             return list(ex.map(one, range(self.nb)))
+
+    def write_atomdb_dump(self, path):
+        """The "Z r Zeff" rows that the reference's tools/gen_sap_table.py reads from atomdb_dump
+        (src/general/atomdb_dump.cpp) to regenerate the tabulated SAP charge of src/general/sap.cpp: for every atom of the
+        batch, in order of Z, the effective charge Z_eff(r) = Z - r (V_H + V_xc) on the common radial grid (origin +
+        quadrature points, identical for all atoms: the tool requires it).  `gen_sap_table.py sap.cpp < path` then
+        splices the table (%.14e, three per line) into the reference's source unchanged."""
+        order = sorted(range(self.nb), key=lambda a: self.zs[a])
+        with open(path, "w") as f:
+            for a in order:
+                tab = self.sap_table(a)
+                f.write("".join("%d %.16e %.16e\n" % (self.zs[a], r, z) for r, z in zip(tab[:, 0], tab[:, 8])))
+        return path

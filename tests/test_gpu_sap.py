@@ -64,6 +64,15 @@ def test_batched_sap_scf_matches_oracle(hb, tmp_path):
     assert len(first) == 376 and len(first[0]) == 9 * 25        # " %24.16e" per entry (src/general/eigen_io.h:64-101)
     back = np.loadtxt(paths[0])
     assert np.allclose(back, batch.sap_table(0), rtol=1e-15, atol=0)
+    # the rows the reference's tools/gen_sap_table.py consumes (its own consistency checks, :19-40): Z r Zeff, one
+    # block of equal length per element on one common radial grid
+    dump = np.loadtxt(batch.write_atomdb_dump(str(tmp_path / "dump.txt")))
+    Zc = dump[:, 0].astype(int)
+    nrad = int((Zc == zs[0]).sum())
+    assert nrad == 376 and dump.shape[0] == len(zs) * nrad and list(dict.fromkeys(Zc)) == sorted(zs)
+    for k in range(len(zs)):
+        assert np.array_equal(dump[k * nrad:(k + 1) * nrad, 1], dump[:nrad, 1])
+    assert abs(dump[0, 2] - zs[0]) < 1e-12 and abs(dump[nrad - 1, 2]) < 1e-6      # Z_eff(0) = Z, Z_eff(Rmax) = 0 (neutral atom)
 
 
 def test_batched_sap_scf_refills_unbound_configuration(hb):
