@@ -111,6 +111,9 @@ class SadatomBatchSCF:
         nb, nl, N = self.nb, self.nl, self.N
         angfac = 4.0 * np.pi
         self.Pc[:, :N, :] = (Pl / angfac).reshape(nb * nl, N, N).transpose(1, 2)
+        # the grid engine works on its own stream: what torch has queued (the matrix just written) must be complete;
+        # the library synchronises its stream before it returns, which orders the other direction
+        torch.cuda.current_stream().synchronize()
         nel, ekin = ctypes.c_double(), ctypes.c_double()
         _check(lib().hfq_grid_density(self.ctx, self.Pc.data_ptr(), N, None, 0, 0, self.rho.data_ptr(), None, None, None,
                                       self.w.data_ptr(), ctypes.byref(nel), ctypes.byref(ekin)))
@@ -121,6 +124,7 @@ class SadatomBatchSCF:
         exc = cx * r13
         vrho = (4.0 / 3.0) * cx * r13
         e = ctypes.c_double()
+        torch.cuda.current_stream().synchronize()      # vrho was produced on torch's stream
         _check(lib().hfq_grid_fxc(self.ctx, 0, 1, None, vrho.data_ptr(), None, None, None, self.Hc.data_ptr(), N, None, 0,
                                   ctypes.byref(e)))
         self.launches += 12
@@ -136,7 +140,9 @@ class SadatomBatchSCF:
         """J_a = coulomb(Prad_a / 4 pi) (src/sadatom/scf.cpp:199), all atoms in one launch."""
         P = (Prad / (4.0 * np.pi)).contiguous()
         J = self.torch.empty_like(P)
-        _check(lib().hfq_coulomb_radial_batch(self.ctx, P.data_ptr(), J.data_ptr(), self.nb, 1.0, None))
+        # launched on torch's current stream: ordered with the surrounding tensor operations without a synchronisation
+        _check(lib().hfq_coulomb_radial_batch(self.ctx, P.data_ptr(), J.data_ptr(), self.nb, 1.0,
+                                              self.torch.cuda.current_stream().cuda_stream))
         self.launches += 1
         return J
 
@@ -147,6 +153,7 @@ class SadatomBatchSCF:
         nb, N = self.nb, self.N
         vp = v.view(nb, self.nel_fe, self.nquad).permute(1, 0, 2).contiguous().view(-1)   # point = (element, atom, node)
         self.Pc.zero_()
+        torch.cuda.current_stream().synchronize()      # Pc and vp come from torch's stream, the grid engine has its own
         nel, ekin = ctypes.c_double(), ctypes.c_double()
         _check(lib().hfq_grid_density(self.ctx, self.Pc.data_ptr(), N, None, 0, 0, None, None, None, None, None,
                                       ctypes.byref(nel), ctypes.byref(ekin)))
