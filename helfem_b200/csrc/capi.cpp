@@ -642,6 +642,9 @@ int hfq_coulomb_radial_batch(hfq_ctx *ctx, const double *dP, double *dJ, int nb,
   return guarded([&] {
     const int64_t N = ctx->eng->tables().Nrad;
     ctx->eng->coulomb_radial_batch(dP, dJ, nb, N * N, fac, stream ? (cudaStream_t)stream : ctx->eng->stream());
+    // on the context's own stream (stream == NULL, which is also the handle of the legacy default stream that e.g.
+    // PyTorch uses) the caller has no way to order later work after the launch: complete it here
+    if (!stream && cudaStreamSynchronize(ctx->eng->stream()) != cudaSuccess) throw std::runtime_error("hfq_coulomb_radial_batch: stream synchronisation failed");
     return HFQ_OK;
   });
 }

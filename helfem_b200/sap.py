@@ -101,6 +101,7 @@ class SadatomBatchSCF:
         self._tab_tables = None
         self.timing = {"eigh": 0.0, "xc": 0.0, "coulomb": 0.0, "other": 0.0}
         self.profile = False
+        self.warm_start = os.environ.get("HFQ_SAP_WARM_START", "1") != "0"
         self._vprev = {}
 
     # ---- the two native batched operators -----------------------------------------------------------------------
@@ -113,7 +114,7 @@ class SadatomBatchSCF:
         self.Pc[:, :N, :] = (Pl / angfac).reshape(nb * nl, N, N).transpose(1, 2)
         # the grid engine works on its own stream: what torch has queued (the matrix just written) must be complete;
         # the library synchronises its stream before it returns, which orders the other direction
-        torch.cuda.current_stream().synchronize()
+        torch.cuda.synchronize()
         nel, ekin = ctypes.c_double(), ctypes.c_double()
         _check(lib().hfq_grid_density(self.ctx, self.Pc.data_ptr(), N, None, 0, 0, self.rho.data_ptr(), None, None, None,
                                       self.w.data_ptr(), ctypes.byref(nel), ctypes.byref(ekin)))
@@ -124,7 +125,7 @@ class SadatomBatchSCF:
         exc = cx * r13
         vrho = (4.0 / 3.0) * cx * r13
         e = ctypes.c_double()
-        torch.cuda.current_stream().synchronize()      # vrho was produced on torch's stream
+        torch.cuda.synchronize()      # vrho was produced on torch's stream
         _check(lib().hfq_grid_fxc(self.ctx, 0, 1, None, vrho.data_ptr(), None, None, None, self.Hc.data_ptr(), N, None, 0,
                                   ctypes.byref(e)))
         self.launches += 12
@@ -140,9 +141,11 @@ class SadatomBatchSCF:
         """J_a = coulomb(Prad_a / 4 pi) (src/sadatom/scf.cpp:199), all atoms in one launch."""
         P = (Prad / (4.0 * np.pi)).contiguous()
         J = self.torch.empty_like(P)
-        # launched on torch's current stream: ordered with the surrounding tensor operations without a synchronisation
-        _check(lib().hfq_coulomb_radial_batch(self.ctx, P.data_ptr(), J.data_ptr(), self.nb, 1.0,
-                                              self.torch.cuda.current_stream().cuda_stream))
+        # torch's default stream has the handle 0, which the C ABI reads as "the context's own stream": the call is
+        # asynchronous on that stream, so it is fenced on both sides here
+        self.torch.cuda.synchronize()
+        _check(lib().hfq_coulomb_radial_batch(self.ctx, P.data_ptr(), J.data_ptr(), self.nb, 1.0, None))
+        self.torch.cuda.synchronize()
         self.launches += 1
         return J
 
@@ -153,7 +156,7 @@ class SadatomBatchSCF:
         nb, N = self.nb, self.N
         vp = v.view(nb, self.nel_fe, self.nquad).permute(1, 0, 2).contiguous().view(-1)   # point = (element, atom, node)
         self.Pc.zero_()
-        torch.cuda.current_stream().synchronize()      # Pc and vp come from torch's stream, the grid engine has its own
+        torch.cuda.synchronize()      # Pc and vp come from torch's stream, the grid engine has its own
         nel, ekin = ctypes.c_double(), ctypes.c_double()
         _check(lib().hfq_grid_density(self.ctx, self.Pc.data_ptr(), N, None, 0, 0, None, None, None, None, None,
                                       ctypes.byref(nel), ctypes.byref(ekin)))
@@ -222,7 +225,7 @@ class SadatomBatchSCF:
         # warm start: in the eigenvector basis of the previous Fock matrices of the same atoms the new ones are nearly
         # diagonal, and the Jacobi sweeps (the latency of an SCF iteration) drop from ~10 to 2-3
         key = None if idx is None else tuple(idx.shape)
-        Vp = self._vprev.get(key)
+        Vp = self._vprev.get(key) if self.warm_start else None
         if Vp is not None and Vp.shape == Fo.shape:
             W, V = self._eigh(Vp.transpose(-1, -2) @ Fo @ Vp)
             V = Vp @ V

@@ -198,7 +198,10 @@ int hfq_exchange_device(hfq_ctx *ctx, const double *dP, int64_t ldP, double *dK,
 /* Radial Coulomb matrices of nb spherical densities in one launch: J_b = fac * coulomb(P_b) with the sadatom
  * convention coulomb(P) = 4 pi J_0(P) (src/sadatom/basis.cpp:186-207; the reference's gensap builder calls it with
  * Prad / 4 pi, src/sadatom/scf.cpp:199).  dP, dJ: nb contiguous Nrad x Nrad device matrices.  Any context over an
- * atomic / sadatom radial basis. */
+ * atomic / sadatom radial basis.  stream: a CUDA stream of the caller (the launch is asynchronous on it), or NULL = the
+ * context's own stream, in which case the call returns when the result is complete.  Note that NULL is also the
+ * handle of the legacy default stream (PyTorch's default): such callers get the synchronous form and must make sure
+ * themselves that dP is complete before the call (all *_device entry points read their inputs on the stream they run on). */
 int hfq_coulomb_radial_batch(hfq_ctx *ctx, const double *dP, double *dJ, int nb, double fac, void *stream);
 
 /* Batched symmetric eigensolver for small matrices on the current device (cyclic Jacobi, one CTA per matrix, n <= 118):
