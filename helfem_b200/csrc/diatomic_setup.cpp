@@ -506,6 +506,7 @@ void diatomic_one_electron(const BasisTables &t, std::vector<double> &S, std::ve
   const int nd = t.Ndummy(), nb = (int)pidx.size();
   std::vector<double> Sd((size_t)nd * nd, 0.0), Td((size_t)nd * nd, 0.0), Vd((size_t)nd * nd, 0.0);
   const double R3 = std::pow(t.Rhalf, 3), R2 = t.Rhalf * t.Rhalf;
+#pragma omp parallel for collapse(2) schedule(dynamic, 8)
   for (int i = 0; i < na; i++)
     for (int j = 0; j < na; j++) {
       if (t.mval[i] != t.mval[j]) continue;
@@ -529,6 +530,7 @@ void diatomic_one_electron(const BasisTables &t, std::vector<double> &S, std::ve
   S.assign((size_t)nb * nb, 0.0);
   T.assign((size_t)nb * nb, 0.0);
   V.assign((size_t)nb * nb, 0.0);
+#pragma omp parallel for schedule(static)
   for (int b = 0; b < nb; b++)
     for (int a = 0; a < nb; a++) {
       const size_t o = (size_t)pidx[a] + (size_t)pidx[b] * nd;
