@@ -61,10 +61,13 @@ k_block_norms(BasisDev b, const double *__restrict__ P, int64_t ld, const int *_
   for (int j0 = 0; j0 < nc; j0 += 32)
     for (int i0 = 0; i0 < na; i0 += 32) {
       __syncwarp();
-      // mirror tile: element (j0 + lane, i0 + k) of block (c, a) -> tm[k][lane]
-      for (int k = 0; k < 32; k++) {
+      // mirror tile: element (j0 + lane, i0 + k) of block (c, a) -> tm[k][lane].  Partial tiles (42 = 32 + 10 radial
+      // functions) loop over their own columns only; tile entries outside are never read below
+      const int k1 = min(32, na - i0), k2 = min(32, nc - j0);
+#pragma unroll 8
+      for (int k = 0; k < k1; k++) {
         const int jj = j0 + lane, ii = i0 + k;
-        const double v = (jj < nc && ii < na) ? mirr[jj + (int64_t)ii * ld] : 0.0;
+        const double v = (jj < nc) ? mirr[jj + (int64_t)ii * ld] : 0.0;
         tm[k][lane] = v;
         if (a != c) {
           s2 += v * v;
@@ -72,9 +75,10 @@ k_block_norms(BasisDev b, const double *__restrict__ P, int64_t ld, const int *_
         }
       }
       __syncwarp();
-      for (int k = 0; k < 32; k++) {   // element (i0 + lane, j0 + k) of block (a, c)
+#pragma unroll 8
+      for (int k = 0; k < k2; k++) {   // element (i0 + lane, j0 + k) of block (a, c)
         const int ii = i0 + lane, jj = j0 + k;
-        if (ii < na && jj < nc) {
+        if (ii < na) {
           const double v = base[ii + (int64_t)jj * ld];
           s1 += v * v;
           d = fmax(d, fabs(v - tm[lane][k]));
@@ -318,6 +322,11 @@ k_fold_reg(BasisDev b, const FoldTask *__restrict__ tasks, const int *__restrict
     }
   }
   __syncthreads();
+  // store pattern of a lane, fixed for the task: fragment (rtj, rtk) goes to row (rtj*8 + lr) * ldk, column rtk*8 + 2*lc
+  const int st_off = lr * t.ldk + 2 * lc, st_row = 8 * t.ldk;
+  bool st_ok[NT];
+#pragma unroll
+  for (int rtk = 0; rtk < NT; rtk++) st_ok[rtk] = rtk * 8 + 2 * lc < t.ldk;
   int buf = 0;
   for (int pos = pix0 + warp; pos < pix1; pos += 8, buf ^= 1) {
     __syncwarp();   // every lane is done reading the buffer the next prefetch overwrites
@@ -368,13 +377,13 @@ k_fold_reg(BasisDev b, const FoldTask *__restrict__ tasks, const int *__restrict
               dmma(c2[rtj][rtk][0], c2[rtj][rtk][1], ga[rtj][ni].x, c1[bb][rtk][ni][0]);
               dmma(c2[rtj][rtk][0], c2[rtj][rtk][1], ga[rtj][ni].y, c1[bb][rtk][ni][1]);
             }
-        double *out = Rdst + ((int64_t)(aa * NCH + bb) * b.Npix + pix) * gstride + lr * t.ldk + 2 * lc;
+        double *out = Rdst + ((int64_t)(aa * NCH + bb) * b.Npix + pix) * gstride + st_off;
 #pragma unroll
         for (int rtj = 0; rtj < NT; rtj++)
 #pragma unroll
           for (int rtk = 0; rtk < NT; rtk++)
-            if (rtk * 8 + 2 * lc < t.ldk)   // columns past the sector are not stored (ldk is even)
-              *reinterpret_cast<double2 *>(out + rtj * 8 * t.ldk + rtk * 8) =
+            if (st_ok[rtk])   // columns past the sector are not stored (ldk is even)
+              *reinterpret_cast<double2 *>(out + rtj * st_row + rtk * 8) =
                   make_double2(c2[rtj][rtk][0], c2[rtj][rtk][1]);
       }
     }
