@@ -806,6 +806,7 @@ struct TgemmWarp {
   int NS, A_STAGE, B_STAGE, nsteps;
   int lr, lc, cg, rg, lane;
   int nrt_tot, ncj;
+  int rs;                    // row-tile stride of the !BAL split: 4 (row groups of one column group) or 8 (all warps)
 };
 
 template <int BK, int NF, int REM, bool BAL, int NCJ = 4>
@@ -859,10 +860,11 @@ __device__ __forceinline__ void tgemm_ws_consume(const TgemmWarp &w, const GemmI
         }
       } else {
         double bf[2][NCJ], af[2][NFF];
+        const int rstep = w.rs * 8 * BK;
 #pragma unroll
         for (int j = 0; j < NCJ; j++) bf[0][j] = bs[j * 8];
 #pragma unroll
-        for (int i = 0; i < NF; i++) af[0][i] = as[i * 32 * BK + (SWZ ? 4 * w.lr : 0)];
+        for (int i = 0; i < NF; i++) af[0][i] = as[i * rstep + (SWZ ? 4 * w.lr : 0)];
 #pragma unroll
         for (int ks = 0; ks < BK / 4; ks++) {
           const int cur = ks & 1, nxt = cur ^ 1;
@@ -871,7 +873,7 @@ __device__ __forceinline__ void tgemm_ws_consume(const TgemmWarp &w, const GemmI
 #pragma unroll
             for (int j = 0; j < NCJ; j++) bf[nxt][j] = bs[(ks + 1) * 4 * LDB_S + j * 8];
 #pragma unroll
-            for (int i = 0; i < NF; i++) af[nxt][i] = as[i * 32 * BK + ko];
+            for (int i = 0; i < NF; i++) af[nxt][i] = as[i * rstep + ko];
           }
 #pragma unroll
           for (int i = 0; i < NF; i++)
@@ -901,7 +903,7 @@ __device__ __forceinline__ void tgemm_ws_consume(const TgemmWarp &w, const GemmI
   };
 #pragma unroll
   for (int i = 0; i < NF; i++) {
-    const int m = (w.rg + 4 * i) * 8 + w.lr;
+    const int m = (w.rg + (BAL ? 4 : w.rs) * i) * 8 + w.lr;
     if (m >= it.M) continue;
 #pragma unroll
     for (int j = 0; j < NCJ; j++)
@@ -1014,7 +1016,20 @@ k_tgemm_ws(const GemmItem *__restrict__ items, const GemmEntry *__restrict__ ent
   w.rg = warp & 3;
   w.nrt_tot = (it.M + 7) >> 3;
   w.ncj = min(4, ((it.N - bn) >> 3) - 4 * w.cg);   // column tiles of this warp (<= 0: idle)
-  if (w.ncj == 4) {
+  w.rs = 4;
+  const int ctiles = min(8, (it.N - bn) >> 3);     // column tiles of this CTA
+  if (ctiles <= 4) {
+    // the second column group would idle: all 8 warps share the first one, every 8th row tile each
+    w.cg = 0;
+    w.rg = warp;
+    w.rs = 8;
+    w.ncj = ctiles;
+    const int nf = (w.nrt_tot - w.rg + 7) >> 3;
+    if (ctiles > 2)
+      tgemm_ws_dispatch_nf<BK, 0, false, 4>(w, it, bn, nf);
+    else
+      tgemm_ws_dispatch_nf<BK, 0, false, 2>(w, it, bn, nf);
+  } else if (w.ncj == 4) {
     const int nf = w.nrt_tot >> 2;
     switch (w.nrt_tot & 3) {
       case 3: tgemm_ws_dispatch_nf<BK, 3, true>(w, it, bn, nf); break;
