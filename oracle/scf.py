@@ -127,8 +127,14 @@ def atomic_vxc(grid, n, func_ids, thr=1e-12):
     """vxc(P) for rks() on an oracle grid with eval_density / eval_fxc (atomic 3D, diatomic pure-m / 3D)."""
     from . import xc
     gga = any(xc.is_gga(f) for f in func_ids)
+    mgga = any(xc.is_mgga(f) for f in func_ids)
 
     def vxc(P):
+        if mgga:   # density, gradient and tau; the functional returns vtau as well (src/atomic/dftgrid.cpp:304-359)
+            d = grid.eval_density(P, None, True, True, False)
+            exc, vrho, vsigma, vtau = xc.evaluate_mgga(func_ids, d["rho"][:, 0], d["sigma"][:, 0], d["tau"][:, 0], thr)
+            Ha, _, Exc = grid.eval_fxc(n, exc, vrho[:, None], vsigma[:, None], vtau[:, None])
+            return Ha, Exc, d["Nel"]
         d = grid.eval_density(P, grad=gga)
         exc, vrho, vsigma = xc.evaluate_sum(func_ids, d["rho"][:, 0], d["sigma"][:, 0] if gga else None, thr)
         args = (exc, vrho[:, None], vsigma[:, None] if gga else None)

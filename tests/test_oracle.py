@@ -213,6 +213,7 @@ def _lda():
     (2, 1, "lda", -2.8348356241, -0.9733148392, 1.9961216725),      # atomic-He-lda-r
     (2, 1, "pbe", -2.8929348668, -1.0461619634, 2.0267367125),      # atomic-He-gga-r
     (4, 2, "lda", -14.4472094740, -2.5148562583, 7.1152581977),     # atomic-Be-lda-r
+    (2, 1, "tpss", -2.9096638609, -1.0712420321, 2.0455707136),     # atomic-He-mgga-r: pins tau and the v_tau assembly
 ])
 def test_atomic_grid_oracle_recorded_ks_energy(Z, nocc, method, Eref, XCref, Jref):
     from oracle import xc
@@ -220,7 +221,7 @@ def test_atomic_grid_oracle_recorded_ks_energy(Z, nocc, method, Eref, XCref, Jre
     ob = cases.oracle_atomic(Z, 0, 0, 5)
     S, T, V = ob.overlap(), ob.kinetic(), ob.nuclear()
     grid = AtomicDFTGrid(ob, 12, 12)                                # ldft = 4 lmax + 12, mdft = 4 mmax + 12 (main.cpp:329-330)
-    fids = _lda() if method == "lda" else [xc.XC_GGA_X_PBE, xc.XC_GGA_C_PBE]
+    fids = {"lda": _lda(), "pbe": [xc.XC_GGA_X_PBE, xc.XC_GGA_C_PBE], "tpss": [xc.XC_MGGA_X_TPSS, xc.XC_MGGA_C_TPSS]}[method]
     r = scf.rks(S, T + V, ob.coulomb, scf.atomic_vxc(grid, ob.Nbf(), fids), [nocc], [np.arange(ob.Nbf())])
     assert abs(r["E"] - Eref) < 1e-9
     assert abs(r["XC"] - XCref) < 2e-6 and abs(r["Coulomb"] - Jref) < 3e-6
