@@ -567,15 +567,16 @@ int hfq_eval_fxc(hfq_ctx *ctx, int x_func, int c_func, const double *Pa, int64_t
   }
   if (!hfq::GridEngine::builtin_supported(x_func, c_func) || (Pb && c_func > 0))
     return fail(HFQ_ERR_INVALID,
-                "hfq_eval_fxc: built in are the exchange functionals 1 (Slater), 101 (PBE) and, for restricted "
-                "densities, the correlation functionals 7 (VWN5), 130 (PBE); evaluate other functionals with libxc "
+                "hfq_eval_fxc: built in are the exchange functionals 1 (Slater), 101 (PBE), 202 (TPSS) and, for restricted "
+                "densities, the correlation functionals 7 (VWN5), 130 (PBE), 231 (TPSS); evaluate other functionals with libxc "
                 "between hfq_grid_density and hfq_grid_fxc");
   std::lock_guard<std::mutex> lk(ctx->mu);
   return guarded([&] {
     // densities, functional and assembly stay on the device; P and H may be host or device matrices
-    ctx->grid->density_launch(Pa, ldPa, Pb, ldPb, hfq::GridEngine::builtin_needs_gradient(x_func, c_func) ? hfq::GRID_GRAD : 0);
+    ctx->grid->density_launch(Pa, ldPa, Pb, ldPb, hfq::GridEngine::builtin_density_flags(x_func, c_func));
     ctx->grid->density_collect(nullptr, nullptr, nullptr, nullptr, nullptr, Nel, Ekin);
-    if (Ekin) *Ekin = 0.0;   // tau is evaluated for meta-GGAs only (src/general/dftgrid_common.cpp compute_Ekin)
+    // tau is evaluated for meta-GGAs only (src/general/dftgrid_common.cpp compute_Ekin)
+    if (Ekin && !hfq::GridEngine::builtin_needs_tau(x_func, c_func)) *Ekin = 0.0;
     ctx->grid->fxc_builtin(x_func, c_func, thr, beta != 0, Ha, ldHa, Hb, ldHb, Exc);
     return HFQ_OK;
   });
@@ -588,7 +589,7 @@ int hfq_fock_build(hfq_ctx *ctx, const double *P, int64_t ldP, double kscale, do
   const int64_t n = ctx->eng->Nbf();
   if (ldP < n || ldJ < n || ldK < n || (Hxc && ldH < n)) return fail(HFQ_ERR_INVALID, "hfq_fock_build: leading dimension smaller than Nbf");
   if (!hfq::GridEngine::builtin_supported(x_func, c_func))
-    return fail(HFQ_ERR_INVALID, "hfq_fock_build: built-in functionals are exchange 1, 101 and correlation 7, 130 (libxc ids)");
+    return fail(HFQ_ERR_INVALID, "hfq_fock_build: built-in functionals are exchange 1, 101, 202 and correlation 7, 130, 231 (libxc ids)");
   if ((x_func > 0 || c_func > 0) && !Hxc) return fail(HFQ_ERR_INVALID, "hfq_fock_build: Hxc needed for a density functional");
   std::lock_guard<std::mutex> lk(ctx->mu);
   return guarded([&] {
@@ -602,7 +603,7 @@ int hfq_fock_build(hfq_ctx *ctx, const double *P, int64_t ldP, double kscale, do
     const hfq::EngineTimings tm = ctx->eng->timings();
     double ekin = 0.0;
     ctx->grid->density_launch(ctx->eng->device_density(), n, nullptr, 0,
-                              hfq::GridEngine::builtin_needs_gradient(x_func, c_func) ? hfq::GRID_GRAD : 0);
+                              hfq::GridEngine::builtin_density_flags(x_func, c_func));
     ctx->grid->density_collect(nullptr, nullptr, nullptr, nullptr, nullptr, Nel, &ekin);
     ctx->grid->fxc_builtin(x_func, c_func, thr, true, Hxc, ldH, nullptr, 0, Exc);
     (void)tm;
@@ -619,7 +620,7 @@ int hfq_fock_build_device(hfq_ctx *ctx, const double *dP, int64_t ldP, double ks
   if (ldP < n || ldJ < n || ldK < n || (dHxc && ldH < n))
     return fail(HFQ_ERR_INVALID, "hfq_fock_build_device: leading dimension smaller than Nbf");
   if (!hfq::GridEngine::builtin_supported(x_func, c_func))
-    return fail(HFQ_ERR_INVALID, "hfq_fock_build_device: built-in functionals are exchange 1, 101 and correlation 7, 130 (libxc ids)");
+    return fail(HFQ_ERR_INVALID, "hfq_fock_build_device: built-in functionals are exchange 1, 101, 202 and correlation 7, 130, 231 (libxc ids)");
   if ((x_func > 0 || c_func > 0) && !dHxc) return fail(HFQ_ERR_INVALID, "hfq_fock_build_device: Hxc needed for a density functional");
   std::lock_guard<std::mutex> lk(ctx->mu);
   return guarded([&] {
@@ -627,7 +628,7 @@ int hfq_fock_build_device(hfq_ctx *ctx, const double *dP, int64_t ldP, double ks
     // the grid density chain (small GEMMs, bandwidth-bound) is queued first on the grid's stream and runs next to
     // the tensor-pipe-bound J/K kernels
     ctx->eng->fence_stream(st, ctx->grid->stream());   // P may still be written by earlier work on st
-    ctx->grid->density_launch(dP, ldP, nullptr, 0, hfq::GridEngine::builtin_needs_gradient(x_func, c_func) ? hfq::GRID_GRAD : 0);
+    ctx->grid->density_launch(dP, ldP, nullptr, 0, hfq::GridEngine::builtin_density_flags(x_func, c_func));
     ctx->eng->jk_dev(dP, ldP, kscale, dJ, ldJ, dK, ldK, 0, 1, st);
     double ekin = 0.0;
     ctx->grid->density_collect(nullptr, nullptr, nullptr, nullptr, nullptr, Nel, &ekin);

@@ -222,16 +222,18 @@ __global__ void k_exc(const double *__restrict__ w, const double *__restrict__ e
   if ((threadIdx.x & 31) == 0) atomicAdd(sum, s);
 }
 
-// Built-in functionals (xc_builtin.cuh: libxc ids 1, 7, 101, 130; id <= 0: none) on the device, from the densities and
-// gradients of the last density call: exc per particle, v_rho and v_sigma in libxc's conventions, summed over the
-// exchange and the correlation functional like DFTGridWorkerBase::compute_xc accumulates them; zero below the density
-// threshold (xc_func_set_dens_threshold, src/general/dftgrid_common.cpp:131).  Polarised densities: exchange only,
-// through the spin-scaling relation E_x[na, nb] = (E_x[2 na] + E_x[2 nb]) / 2 (v_sigma(ab) = 0).
-// ga / gb: gradient components [3][N] (may be null for LDAs); vsa / vsab / vsb may be null for LDAs.
+// Built-in functionals (xc_builtin.cuh: libxc ids 1, 7, 101, 130, 202, 231; id <= 0: none) on the device, from the
+// densities, gradients and kinetic energy densities of the last density call: exc per particle, v_rho, v_sigma and
+// v_tau in libxc's conventions, summed over the exchange and the correlation functional like
+// DFTGridWorkerBase::compute_xc accumulates them; zero below the density threshold (xc_func_set_dens_threshold,
+// src/general/dftgrid_common.cpp:131).  Polarised densities: exchange only, through the spin-scaling relation
+// E_x[na, nb] = (E_x[2 na] + E_x[2 nb]) / 2 (v_sigma(ab) = 0).
+// ga / gb: gradient components [3][N]; ta / tb: tau (null for LDAs / GGAs); the vs* / vt* outputs may be null likewise.
 __global__ void k_xc_builtin(int64_t N, int x_func, int c_func, const double *__restrict__ ra, const double *__restrict__ rb,
-                             const double *__restrict__ ga, const double *__restrict__ gb, double thr,
-                             double *__restrict__ exc, double *__restrict__ va, double *__restrict__ vb,
-                             double *__restrict__ vsa, double *__restrict__ vsab, double *__restrict__ vsb) {
+                             const double *__restrict__ ga, const double *__restrict__ gb, const double *__restrict__ ta,
+                             const double *__restrict__ tb, double thr, double *__restrict__ exc, double *__restrict__ va,
+                             double *__restrict__ vb, double *__restrict__ vsa, double *__restrict__ vsab,
+                             double *__restrict__ vsb, double *__restrict__ vta, double *__restrict__ vtb) {
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < N; p += (int64_t)gridDim.x * blockDim.x) {
     auto sig = [&](const double *g) {
       if (!g) return 0.0;
@@ -240,36 +242,40 @@ __global__ void k_xc_builtin(int64_t N, int x_func, int c_func, const double *__
     };
     if (!rb) {
       const double n = ra[p];
-      double e = 0.0, vr = 0.0, vs = 0.0;
+      double e = 0.0, vr = 0.0, vs = 0.0, vt = 0.0;
       if (!(n < thr)) {
-        const double sg = sig(ga);
+        const double sg = sig(ga), tt = ta ? ta[p] : 1.0;
         for (int k = 0; k < 2; k++) {
           const int id = k ? c_func : x_func;
           if (id <= 0) continue;
-          const xc::D2 d = xc::energy(id, n, sg);
+          const xc::D2 d = xc::energy(id, n, sg, tt);
           e += d.v;
           vr += d.v + n * d.n;
           vs += n * d.s;
+          vt += n * d.t;
         }
       }
       exc[p] = e;
       va[p] = vr;
       if (vsa) vsa[p] = vs;
+      if (vta) vta[p] = vt;
     } else {
       const double na = ra[p], nb = rb[p], n = na + nb;
-      double e = 0.0, vra = 0.0, vrb = 0.0, vsaa = 0.0, vsbb = 0.0;
+      double e = 0.0, vra = 0.0, vrb = 0.0, vsaa = 0.0, vsbb = 0.0, vtaa = 0.0, vtbb = 0.0;
       if (!(n < thr) && x_func > 0) {
         if (na > 0.0) {
-          const xc::D2 d = xc::energy(x_func, 2.0 * na, 4.0 * sig(ga));
+          const xc::D2 d = xc::energy(x_func, 2.0 * na, 4.0 * sig(ga), ta ? 2.0 * ta[p] : 1.0);
           e += na * d.v;
           vra = d.v + 2.0 * na * d.n;
           vsaa = 4.0 * na * d.s;
+          vtaa = 2.0 * na * d.t;
         }
         if (nb > 0.0) {
-          const xc::D2 d = xc::energy(x_func, 2.0 * nb, 4.0 * sig(gb));
+          const xc::D2 d = xc::energy(x_func, 2.0 * nb, 4.0 * sig(gb), tb ? 2.0 * tb[p] : 1.0);
           e += nb * d.v;
           vrb = d.v + 2.0 * nb * d.n;
           vsbb = 4.0 * nb * d.s;
+          vtbb = 2.0 * nb * d.t;
         }
         e /= n;
       }
@@ -280,6 +286,10 @@ __global__ void k_xc_builtin(int64_t N, int x_func, int c_func, const double *__
         vsa[p] = vsaa;
         vsab[p] = 0.0;
         vsb[p] = vsbb;
+      }
+      if (vta) {
+        vta[p] = vtaa;
+        vtb[p] = vtbb;
       }
     }
   }
@@ -592,10 +602,17 @@ void GridEngine::density(const double *Pa, int64_t ldPa, const double *Pb, int64
 }
 
 // Built-in functionals evaluated on the device from the densities of the last density call, then the assembly:
-// x_func / c_func = libxc ids 1 (Slater exchange), 101 (PBE exchange) / 7 (VWN5), 130 (PBE correlation); <= 0: none
-// (H = 0; the HF drivers call eval_Fxc only to integrate Nel).  GGAs need the gradient from the density call.
+// x_func / c_func = libxc ids 1 (Slater), 101 (PBE), 202 (TPSS) exchange / 7 (VWN5), 130 (PBE), 231 (TPSS) correlation;
+// <= 0: none (H = 0; the HF drivers call eval_Fxc only to integrate Nel).  GGAs need the gradient, meta-GGAs also tau
+// from the density call (builtin_density_flags).
 bool GridEngine::builtin_needs_gradient(int x_func, int c_func) {
   return (x_func > 0 && xc::is_gga(x_func)) || (c_func > 0 && xc::is_gga(c_func));
+}
+bool GridEngine::builtin_needs_tau(int x_func, int c_func) {
+  return (x_func > 0 && xc::is_mgga(x_func)) || (c_func > 0 && xc::is_mgga(c_func));
+}
+int GridEngine::builtin_density_flags(int x_func, int c_func) {
+  return (builtin_needs_gradient(x_func, c_func) ? GRID_GRAD : 0) | (builtin_needs_tau(x_func, c_func) ? GRID_TAU : 0);
 }
 bool GridEngine::builtin_supported(int x_func, int c_func) {
   return (x_func <= 0 || (xc::known(x_func) && xc::is_exchange(x_func))) &&
@@ -625,18 +642,20 @@ void GridEngine::fxc_builtin(int x_func, int c_func, double thr, bool beta, doub
     return;
   }
   if (!builtin_supported(x_func, c_func))
-    throw std::logic_error("built-in functionals: exchange 1 (Slater), 101 (PBE); correlation 7 (VWN5), 130 (PBE)");
+    throw std::logic_error("built-in functionals: exchange 1 (Slater), 101 (PBE), 202 (TPSS); correlation 7 (VWN5), 130 (PBE), 231 (TPSS)");
   if (nspin == 2 && c_func > 0)
     throw std::logic_error("built-in correlation functionals are spin-unpolarised only: use hfq_grid_density + libxc + hfq_grid_fxc");
-  const bool gga = builtin_needs_gradient(x_func, c_func);
+  const bool gga = builtin_needs_gradient(x_func, c_func), mgga = builtin_needs_tau(x_func, c_func);
   if (gga && !(s.dens_flags & GRID_GRAD)) throw std::logic_error("built-in GGA: the gradient was not computed by the density call");
+  if (mgga && !(s.dens_flags & GRID_TAU)) throw std::logic_error("built-in meta-GGA: tau was not computed by the density call");
   double *v = s.d_v.p;
   k_xc_builtin<<<592, 256, 0, s.st>>>(N, x_func, c_func, s.dens(0, 0), nspin == 2 ? s.dens(1, 0) : nullptr,
-                                      gga ? s.dens(0, 1) : nullptr, (gga && nspin == 2) ? s.dens(1, 1) : nullptr, thr,
+                                      gga ? s.dens(0, 1) : nullptr, (gga && nspin == 2) ? s.dens(1, 1) : nullptr,
+                                      mgga ? s.dens(0, 4) : nullptr, (mgga && nspin == 2) ? s.dens(1, 4) : nullptr, thr,
                                       v + 9 * N, v, v + N, gga ? v + 2 * N : nullptr, gga ? v + 3 * N : nullptr,
-                                      gga ? v + 4 * N : nullptr);
+                                      gga ? v + 4 * N : nullptr, mgga ? v + 5 * N : nullptr, mgga ? v + 6 * N : nullptr);
   CK(cudaGetLastError());
-  assemble(gga ? GRID_GRAD : 0, beta, true, gga, false, false, Ha, ldHa, Hb, ldHb, Exc);
+  assemble((gga ? GRID_GRAD : 0) | (mgga ? GRID_TAU : 0), beta, true, gga, mgga, false, Ha, ldHa, Hb, ldHb, Exc);
 }
 
 void GridEngine::fxc(int flags, bool beta, const double *exc, const double *vrho, const double *vsigma, const double *vtau,

@@ -67,6 +67,8 @@ class GridEngine {
                    double *Exc);
   static bool builtin_supported(int x_func, int c_func);
   static bool builtin_needs_gradient(int x_func, int c_func);
+  static bool builtin_needs_tau(int x_func, int c_func);
+  static int builtin_density_flags(int x_func, int c_func);   // GridFlags the density call must compute
   cudaStream_t stream() const;
   // assembly from functional output (host arrays, libxc layout); uses the density kept on the device
   void fxc(int flags, bool beta, const double *exc, const double *vrho, const double *vsigma, const double *vtau,

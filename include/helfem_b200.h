@@ -264,10 +264,10 @@ int hfq_grid_fxc(hfq_ctx *ctx, int flags, int beta, const double *exc, const dou
                  const double *vtau, const double *vlapl, double *Ha, int64_t ldHa, double *Hb, int64_t ldHb, double *Exc);
 /* DFTGrid::eval_Fxc(x_func, .., c_func, .., P[a,b] -> H[a,b], Exc, Nel, Ekin, beta, thr) for the
  * functionals built into this library and evaluated on the device (csrc/xc_builtin.cuh), libxc ids:
- * x_func = 1 Slater exchange, 101 PBE exchange; c_func = 7 VWN5, 130 PBE correlation (correlation: restricted
- * densities only; polarised exchange through the spin-scaling relation); <= 0: none -- the HF drivers still call
- * eval_Fxc to integrate Nel.  These are the functionals of the reference's recorded LDA / PBE energies
- * (tests/refs/ci.json).  Other ids return HFQ_ERR_INVALID: use hfq_grid_density + libxc + hfq_grid_fxc. */
+ * x_func = 1 Slater, 101 PBE, 202 TPSS exchange; c_func = 7 VWN5, 130 PBE, 231 TPSS correlation (correlation:
+ * restricted densities only; polarised exchange through the spin-scaling relation); <= 0: none -- the HF drivers still
+ * call eval_Fxc to integrate Nel.  These are the functionals of the reference's recorded LDA / PBE / TPSS energies
+ * (tests/refs/ci.json).  Ekin is returned for the meta-GGA (tau is evaluated), 0 otherwise, as in the reference.  Other ids return HFQ_ERR_INVALID: use hfq_grid_density + libxc + hfq_grid_fxc. */
 int hfq_eval_fxc(hfq_ctx *ctx, int x_func, int c_func, const double *Pa, int64_t ldPa, const double *Pb, int64_t ldPb,
                  double *Ha, int64_t ldHa, double *Hb, int64_t ldHb, double *Exc, double *Nel, double *Ekin, int beta,
                  double thr);

@@ -1,5 +1,5 @@
 // Host-side check of helfem_b200/csrc/xc_builtin.cuh (the expressions the device kernel k_xc_builtin evaluates):
-// reads "id n sigma" lines, prints exc, vrho, vsigma in libxc's conventions.  tests/test_host.py compares the
+// reads "id n sigma tau" lines, prints exc, vrho, vsigma, vtau in libxc's conventions.  tests/test_host.py compares the
 // output with the oracle's symbolic derivatives (oracle/xc.py).
 #include <cstdio>
 
@@ -7,10 +7,10 @@
 
 int main() {
   int id;
-  double n, sigma;
-  while (std::scanf("%d %lf %lf", &id, &n, &sigma) == 3) {
-    const hfq::xc::D2 e = hfq::xc::energy(id, n, sigma);
-    std::printf("%.17e %.17e %.17e\n", e.v, e.v + n * e.n, n * e.s);
+  double n, sigma, tau;
+  while (std::scanf("%d %lf %lf %lf", &id, &n, &sigma, &tau) == 4) {
+    const hfq::xc::D2 e = hfq::xc::energy(id, n, sigma, tau);
+    std::printf("%.17e %.17e %.17e %.17e\n", e.v, e.v + n * e.n, n * e.s, n * e.t);
   }
   return 0;
 }

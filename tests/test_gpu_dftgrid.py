@@ -105,7 +105,7 @@ def test_eval_fxc_slater_exchange(hb):
     H0, Exc0, Nel0, _ = gg.eval_Fxc(-1, 0, P)
     assert np.all(H0 == 0.0) and Exc0 == 0.0 and abs(Nel0 - o["Nel"]) < 1e-11
     with pytest.raises(ValueError):
-        gg.eval_Fxc(202, 231, P)     # meta-GGAs (TPSS ids) are not built in: use density + libxc + fxc
+        gg.eval_Fxc(263, 267, P)     # SCAN ids are not built in: use density + libxc + fxc
     with pytest.raises(ValueError):
         gg.eval_Fxc(7, 0, P)         # a correlation id in the exchange slot
 
@@ -126,6 +126,22 @@ def test_eval_fxc_builtin_functionals(hb, x_func, c_func):
     Ho, _, Eo = og.eval_fxc(n, exc, vrho[:, None], vsigma[:, None] if gga else None)
     H, Exc, Nel, Ekin = gg.eval_Fxc(x_func, c_func, P)
     assert cases.relerr(H, Ho) < 1e-11 and abs(Exc - Eo) < 1e-12 * abs(Eo) and abs(Nel - o["Nel"]) < 1e-11 and Ekin == 0.0
+
+
+def test_eval_fxc_builtin_tpss(hb):
+    """TPSS meta-GGA (libxc ids 202 + 231) evaluated on the device: density, gradient and tau from the grid engine, the
+    functional point-wise, v_rho / v_sigma / v_tau assembled -- against the oracle grid fed with the oracle's TPSS."""
+    from oracle import xc
+    ob, basis, og, gg = _setup(hb, 4, 1, 1, 2)
+    n = ob.Nbf()
+    P = cases.random_density(n, 2, 11)
+    o = og.eval_density(P, None, True, True, False)
+    exc, vrho, vsigma, vtau = xc.evaluate_mgga([xc.XC_MGGA_X_TPSS, xc.XC_MGGA_C_TPSS], o["rho"][:, 0], o["sigma"][:, 0],
+                                               o["tau"][:, 0], 1e-12)
+    Ho, _, Eo = og.eval_fxc(n, exc, vrho[:, None], vsigma[:, None], vtau[:, None])
+    H, Exc, Nel, Ekin = gg.eval_Fxc(202, 231, P)
+    assert cases.relerr(H, Ho) < 1e-10 and abs(Exc - Eo) < 1e-11 * abs(Eo) and abs(Nel - o["Nel"]) < 1e-11
+    assert abs(Ekin - o["Ekin"]) < 1e-10 * abs(o["Ekin"])      # tau is integrated for a meta-GGA
 
 
 def test_eval_fxc_builtin_polarised_exchange(hb):
@@ -153,16 +169,17 @@ def test_eval_fxc_builtin_polarised_exchange(hb):
         gg.eval_Fxc(101, 130, Pa, Pb)     # polarised correlation is not built in
 
 
-@pytest.mark.parametrize("method,Eref,XCref", [("lda", -2.8348356241, -0.9733148392), ("pbe", -2.8929348668, -1.0461619634)])
+@pytest.mark.parametrize("method,Eref,XCref", [("lda", -2.8348356241, -0.9733148392), ("pbe", -2.8929348668, -1.0461619634),
+                                               ("tpss", -2.9096638609, -1.0712420321)])
 def test_he_ks_energy_on_gpu(hb, method, Eref, XCref):
-    """atomic-He-lda-r / atomic-He-gga-r of the reference's tests/refs/ci.json: a Kohn-Sham SCF whose Fock build runs
+    """atomic-He-lda-r / -gga-r / -mgga-r of the reference's tests/refs/ci.json: a Kohn-Sham SCF whose Fock build runs
     on the GPU (J = hfq_coulomb, XC = hfq_eval_fxc with the functional evaluated on the device) lands on the recorded
     total energy to 1e-9 Eh."""
     from oracle import scf
     ob, basis, og, gg = _setup(hb, 2, 0, 0, 5)
     S, T, V = basis.tables.one_electron()
     n = ob.Nbf()
-    xf, cf = (1, 7) if method == "lda" else (101, 130)
+    xf, cf = {"lda": (1, 7), "pbe": (101, 130), "tpss": (202, 231)}[method]
 
     def vxc(P):
         H, Exc, Nel, _ = gg.eval_Fxc(xf, cf, P)

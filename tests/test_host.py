@@ -178,31 +178,34 @@ def test_sap_table_matches_oracle_and_physics(hb):
 
 def test_builtin_functionals_match_oracle(tmp_path):
     """The functional expressions the device kernel evaluates (helfem_b200/csrc/xc_builtin.cuh: dual-number forms of
-    libxc ids 1, 7, 101, 130), compiled for the host by tests/cpp/xc_check.cpp, against the oracle's symbolically
-    differentiated restatement (oracle/xc.py, pinned on the reference's recorded LDA / PBE energies): exc, vrho, vsigma
-    over 15 decades of density and 20 of the gradient, including sigma = 0.  PBE correlation is a difference of two
-    terms that cancel at large reduced gradients, so errors are measured against the uniform-gas exchange scale."""
+    libxc ids 1, 7, 101, 130, 202, 231), compiled for the host by tests/cpp/xc_check.cpp, against the oracle's
+    symbolically differentiated restatement (oracle/xc.py, pinned on the reference's recorded LDA / PBE / TPSS energies):
+    exc, vrho, vsigma, vtau over 12 decades of density, 13 of the gradient and tau from tau_W to 100 tau_W.  The PBE
+    and TPSS correlations are differences of terms that cancel at large reduced gradients, so energies and vrho are
+    measured against the uniform-gas exchange scale; vsigma and vtau (never near a cancellation of their own) relative."""
     import subprocess
     from oracle import xc
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     exe = str(tmp_path / "xc_check")
     subprocess.check_call(["g++", "-O2", "-std=c++17", os.path.join(root, "tests", "cpp", "xc_check.cpp"), "-o", exe])
     rng = np.random.default_rng(3)
-    n = 10.0 ** rng.uniform(-11, 4, 600)
-    s = (10.0 ** rng.uniform(-14, 6, 600)) * n ** (8.0 / 3.0) * rng.uniform(0, 1, 600)
-    s[:30] = 0.0
+    n = 10.0 ** rng.uniform(-9, 3, 500)
+    s = (10.0 ** rng.uniform(-10, 3, 500)) * n ** (8.0 / 3.0)
+    tw = s / (8.0 * n)
+    tau = tw * (1.0 + 10.0 ** rng.uniform(-3, 2, 500))
+    tau[:50] = tw[:50] * (1.0 + 1e-12)          # one-orbital regions: tau = tau_W (z = 1, the cap of the TPSS correlation)
     ex, vx, _ = xc.evaluate(xc.XC_LDA_X, n)
-    for fid in (xc.XC_LDA_X, xc.XC_LDA_C_VWN, xc.XC_GGA_X_PBE, xc.XC_GGA_C_PBE):
-        inp = "".join("%d %.17e %.17e\n" % (fid, a, b) for a, b in zip(n, s))
+    for fid in (xc.XC_LDA_X, xc.XC_LDA_C_VWN, xc.XC_GGA_X_PBE, xc.XC_GGA_C_PBE, xc.XC_MGGA_X_TPSS, xc.XC_MGGA_C_TPSS):
+        inp = "".join("%d %.17e %.17e %.17e\n" % (fid, a, b, c) for a, b, c in zip(n, s, tau))
         out = np.array(subprocess.run([exe], input=inp, capture_output=True, text=True, check=True).stdout.split(), dtype=float)
-        out = out.reshape(-1, 3)
-        e, v, vs = xc.evaluate(fid, n, s, thr=0.0)
-        # PBE correlation below n ~ 1e-9: the oracle's exp(-ec / gamma) - 1 loses digits (the product uses expm1)
-        tol = 1e-10 if fid == xc.XC_GGA_C_PBE else 1e-12
+        out = out.reshape(-1, 4)
+        e, v, vs, vt = xc.evaluate_mgga([fid], n, s, tau, thr=0.0)
+        # correlation at the lowest densities: the oracle's exp(-ec / gamma) - 1 loses digits (the product uses expm1)
+        tol = 1e-10 if fid in (xc.XC_GGA_C_PBE, xc.XC_MGGA_C_TPSS) else 1e-12
         assert np.max(np.abs(out[:, 0] - e) / np.abs(ex)) < tol, fid
         assert np.max(np.abs(out[:, 1] - v) / np.abs(vx)) < tol, fid
-        if vs is None:
-            assert np.all(out[:, 2] == 0.0)
-        else:   # vsigma ~ exc n / sigma: scale by the uniform-gas exchange energy density over (sigma + its natural unit)
-            scale = np.abs(ex) * n / (s + n ** (8.0 / 3.0))
-            assert np.max(np.abs(out[:, 2] - vs) / scale) < tol, fid
+        for col, ref in ((2, vs), (3, vt)):
+            if not np.any(ref):
+                assert np.all(out[:, col] == 0.0), (fid, col)
+            else:
+                assert np.max(np.abs(out[:, col] - ref) / np.abs(ref)) < tol, (fid, col)
