@@ -133,7 +133,10 @@ def atomic_vxc(grid, n, func_ids, thr=1e-12):
         if mgga:   # density, gradient and tau; the functional returns vtau as well (src/atomic/dftgrid.cpp:304-359)
             d = grid.eval_density(P, None, True, True, False)
             exc, vrho, vsigma, vtau = xc.evaluate_mgga(func_ids, d["rho"][:, 0], d["sigma"][:, 0], d["tau"][:, 0], thr)
-            Ha, _, Exc = grid.eval_fxc(n, exc, vrho[:, None], vsigma[:, None], vtau[:, None])
+            try:
+                Ha, _, Exc = grid.eval_fxc(n, exc, vrho[:, None], vsigma[:, None], vtau[:, None])      # AtomicDFTGrid
+            except TypeError:
+                Ha, _, Exc = grid.eval_fxc(exc, vrho[:, None], vsigma[:, None], vtau[:, None])
             return Ha, Exc, d["Nel"]
         d = grid.eval_density(P, grad=gga)
         exc, vrho, vsigma = xc.evaluate_sum(func_ids, d["rho"][:, 0], d["sigma"][:, 0] if gga else None, thr)

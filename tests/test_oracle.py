@@ -274,3 +274,17 @@ def test_tau_of_a_one_orbital_density_is_the_weizsaecker_form():
     ok = rho > 1e-8
     assert np.max(np.abs(tau[ok] - sig[ok] / (8.0 * rho[ok])) / tau[ok].max()) < 1e-8
     assert abs(d["Ekin"] - np.sum(r["P"] * T)) < 1e-9
+
+
+def test_purem_grid_oracle_documented_tpss_energy():
+    """diatomic-H2-purem-mgga-on: the reference documents -1.1804586903 Eh for H2 / TPSS on the pure-m grid (and on the
+    general 3D grid; tests/cases.json, invariant H2-purem-equals-general-mgga).  Pins tau (incl. the analytic m^2 rho_m /
+    h_phi^2 term) and the v_tau assembly of the pure-m grid oracle (src/diatomic/dftgrid_purem.cpp:212-442, :474-657)."""
+    from oracle import xc
+    from oracle.dftgrid_purem import PureMDFTGrid
+    ob = cases.oracle_diatomic(1, 1, 1.4, (4,), 3)
+    S, T, V = ob.overlap(), ob.kinetic(), ob.nuclear()
+    n = ob.Nbf()
+    vxc = scf.atomic_vxc(PureMDFTGrid(ob, 28), n, [xc.XC_MGGA_X_TPSS, xc.XC_MGGA_C_TPSS])
+    r = scf.rks(S, T + V, ob.coulomb, vxc, [1], [np.arange(n)])
+    assert abs(r["E"] + 1.0 / 1.4 - (-1.1804586903)) < 1e-9 and abs(r["Nel"] - 2.0) < 1e-10
