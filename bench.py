@@ -401,17 +401,23 @@ def main():
         dH = torch.empty_like(dP)
         ex, ne, ek = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
 
-        def vxc_call():
-            hb._check(hb.lib().hfq_eval_fxc(basis._context(), 1, 0, dP.data_ptr(), n, None, 0, dH.data_ptr(), n, None, 0,
+        def vxc_call(xf=1, cf=0):
+            hb._check(hb.lib().hfq_eval_fxc(basis._context(), xf, cf, dP.data_ptr(), n, None, 0, dH.data_ptr(), n, None, 0,
                                             ctypes.byref(ex), ctypes.byref(ne), ctypes.byref(ek), 1, 1e-12))
-        for _ in range(3):
-            vxc_call()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            vxc_call()
-        torch.cuda.synchronize()
-        t_vxc = (time.perf_counter() - t0) / args.steps
+
+        def time_vxc(xf, cf):
+            for _ in range(3):
+                vxc_call(xf, cf)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                vxc_call(xf, cf)
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t0) / args.steps, ex.value
+
+        t_pbe, exc_pbe = time_vxc(101, 130)      # GGA: density + gradient, PBE x + c on the device, v_rho and v_sigma assembled
+        t_tpss, exc_tpss = time_vxc(202, 231)    # meta-GGA: + tau and v_tau
+        t_vxc, _ = time_vxc(1, 0)
         npts = lang * 75 * args.nelem
         mv = np.asarray(T.mval)
         coupled = int(sum((mv == m).sum() ** 2 for m in set(mv.tolist())))
@@ -430,7 +436,9 @@ def main():
                                 "note": "separable-evaluation byte model of SURVEY.md 8d; 93 % of the bytes are the dense H the call "
                                         "must define (10 071 of 130 321 blocks are non-zero); the chain is 10 small launches "
                                         "(latency-bound), not a bandwidth-bound stream"},
-                   "Exc": ex.value, "Nel": ne.value}
+                   "Exc": ex.value, "Nel": ne.value,
+                   "other_functionals_ms_per_build": {"gga_x_pbe+gga_c_pbe": 1e3 * t_pbe, "mgga_x_tpss+mgga_c_tpss": 1e3 * t_tpss},
+                   "Exc_pbe": exc_pbe, "Exc_tpss": exc_tpss}
         del dH
 
     if args.profile_mode:

@@ -395,3 +395,23 @@ def test_fused_fock_build_device(hb):
     Href, eref, nref, _ = grid.eval_Fxc(1, 0, P)
     assert _rel(dH.cpu().numpy().T, Href) < 1e-13 and abs(exc - eref) < 1e-12 * abs(eref) and abs(nel - nref) < 1e-12 * nref
     assert _rel(dK.cpu().numpy().T, K) < 1e-13
+
+
+@pytest.mark.parametrize("x_func,c_func", [(101, 130), (202, 231)])
+def test_purem_eval_fxc_builtin(hb, x_func, c_func):
+    """PBE and TPSS evaluated on the device on the diatomic pure-m grid (gradient / tau incl. the analytic phi terms)
+    against the oracle grid fed with the oracle's functionals."""
+    from oracle import xc
+    ob, basis, og, gg = _setup_purem(hb, (3, 2), 2)
+    n = ob.Nbf()
+    P = cases.random_density(n, 3, 5, cases.m_blocks(ob.mval, ob.Nrad(), True))
+    mgga = x_func == 202
+    o = og.eval_density(P, None, True, mgga, False)
+    if mgga:
+        exc, vrho, vsigma, vtau = xc.evaluate_mgga([x_func, c_func], o["rho"][:, 0], o["sigma"][:, 0], o["tau"][:, 0], 1e-12)
+        Ho, _, Eo = og.eval_fxc(exc, vrho[:, None], vsigma[:, None], vtau[:, None])
+    else:
+        exc, vrho, vsigma = xc.evaluate_sum([x_func, c_func], o["rho"][:, 0], o["sigma"][:, 0], 1e-12)
+        Ho, _, Eo = og.eval_fxc(exc, vrho[:, None], vsigma[:, None])
+    H, Exc, Nel, Ekin = gg.eval_Fxc(x_func, c_func, P)
+    assert cases.relerr(H, Ho) < 1e-10 and abs(Exc - Eo) < 1e-11 * abs(Eo) and abs(Nel - o["Nel"]) < 1e-10
