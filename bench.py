@@ -544,9 +544,9 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "e2e": {"value": e2e_val, "unit": "builds/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "call": ("hfq_fock_build, dense page-locked host matrices in and out. P: the row ranges that were non-zero in "
-                             "the previous call are uploaded first and the build starts on them while the complete matrix "
-                             "follows on another stream and is compared bit-for-bit on the device (mismatch = rebuild from "
-                             "the full upload; speculative_hits counts the calls that did not need it). J, K: only the row "
+                             "the previous call are uploaded and the build starts on them, while host threads verify that "
+                             "every other element of the caller's P is exactly zero (mismatch = rebuild from the complete "
+                             "upload; speculative_hits counts the calls that did not need it). J, K: only the row "
                              "ranges of the non-zero blocks cross PCIe, the rest of the host matrices is zero-filled by host "
                              "threads while the GPU computes") if world == 1 else
                             ("hfq_fock_build with a communicator: ONE set of host matrices in POSIX shared memory, page-locked by "

@@ -1607,6 +1607,22 @@ int host_threads() {
   return n > 0 ? n : omp_get_max_threads();
 }
 
+// true if any element of the n x n column-major matrix H outside the row ranges [r0[c], r1[c]) has a non-zero bit
+// pattern (-0.0 and NaN count as non-zero: the caller then falls back to the complete upload)
+bool Engine::nonzero_outside(const double *H, int64_t ldH, int n, const std::vector<int> &r0, const std::vector<int> &r1) {
+  const int nthr = std::max(1, host_threads() - 2);
+  int found = 0;
+#pragma omp parallel for schedule(static) num_threads(nthr) reduction(| : found)
+  for (int c = 0; c < n; c++) {
+    const unsigned long long *col = reinterpret_cast<const unsigned long long *>(H + (int64_t)c * ldH);
+    unsigned long long acc = 0;
+    for (int i = 0; i < r0[c]; i++) acc |= col[i];
+    for (int i = r1[c]; i < n; i++) acc |= col[i];
+    found |= acc != 0 ? 1 : 0;
+  }
+  return found != 0;
+}
+
 void Engine::zero_outside(double *H, int64_t ldH, int n, const HostRanges &hr, int cb, int ce) {
   const bool none = (int)hr.r0.size() != n;   // no pattern: everything is zero
   // leave cores to the thread that feeds the GPU.  The count set through hfq_set_host_threads is kept in a process
@@ -1753,9 +1769,10 @@ bool Engine::fused_host(const double *P, int64_t ldP, double kscale, double *J, 
     CK(cudaEventCreateWithFlags(&s.ev_up, cudaEventDisableTiming));
     s.d_flag.alloc(1, &dev_bytes_);
   }
-  double h2d = (double)n * n * sizeof(double);
+  double h2d = spec ? 0.0 : (double)n * n * sizeof(double);
+  std::atomic<int> host_mismatch{0};
+  Joiner verify;   // joined before the function returns (declared before the scopes that may throw)
   if (spec) {
-    if (s.d_Pfull.n < n * n) s.d_Pfull.alloc(n * n, &dev_bytes_);
     CK(cudaMemsetAsync(s.d_P.p, 0, n * n * sizeof(double), stream_));
     for (size_t c0 = 0; c0 < n;) {
       size_t c1 = c0 + 1;
@@ -1768,12 +1785,10 @@ bool Engine::fused_host(const double *P, int64_t ldP, double kscale, double *J, 
       }
       c0 = c1;
     }
-    // the complete upload must queue on the copy engine BEHIND the predicted ranges
-    CK(cudaEventRecord(s.ev_up, stream_));
-    CK(cudaStreamWaitEvent(s.up_stream, s.ev_up, 0));
-    CK(cudaMemcpy2DAsync(s.d_Pfull.p, n * sizeof(double), P, ldP * sizeof(double), n * sizeof(double), n,
-                         cudaMemcpyHostToDevice, s.up_stream));
-    CK(cudaEventRecord(s.ev_up, s.up_stream));
+    // The prediction is verified on the HOST while the GPU computes: everything of P outside the uploaded row ranges
+    // must be exactly zero (bit pattern 0).  Only then is the device matrix -- zeros plus the uploaded ranges -- the
+    // caller's matrix; the scan reads P once at host-memory speed instead of sending all of it over PCIe.
+    verify.t = std::thread([&, this]() { host_mismatch.store(nonzero_outside(P, ldP, nbf_, s.pred_r0, s.pred_r1) ? 1 : 0); });
   } else {
     CK(cudaMemcpy2DAsync(s.d_P.p, n * sizeof(double), P, ldP * sizeof(double), n * sizeof(double), n,
                          cudaMemcpyHostToDevice, stream_));
@@ -1818,7 +1833,6 @@ bool Engine::fused_host(const double *P, int64_t ldP, double kscale, double *J, 
       plan_hook_ = nullptr;
       s.packed_valid = false;
       s.kscale = 1.0;
-      if (spec) cudaStreamSynchronize(s.up_stream);
       cudaStreamSynchronize(s.copy_stream);   // the J copy-back must not write into the caller's buffer after the error return
       throw;
     }
@@ -1827,20 +1841,12 @@ bool Engine::fused_host(const double *P, int64_t ldP, double kscale, double *J, 
     s.kscale = 1.0;
     tm_.h2d_bytes = h2d;
     tm_.d2h_bytes = jbytes + copy_ranges_async(K, ldK, s.d_O.p, hrk, stream_);
-    if (spec) {
-      CK(cudaMemsetAsync(s.d_flag.p, 0, sizeof(int), stream_));
-      CK(cudaStreamWaitEvent(stream_, s.ev_up, 0));
-      dev::k_any_diff<<<148 * 8, 256, 0, stream_>>>(reinterpret_cast<const unsigned long long *>(s.d_P.p),
-                                                    reinterpret_cast<const unsigned long long *>(s.d_Pfull.p), n * n,
-                                                    s.d_flag.p);
-      CK(cudaGetLastError());
-      CK(cudaMemcpyAsync(&mismatch, s.d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, stream_));
-      tm_.launches += 1;
-    }
     CK(cudaStreamSynchronize(stream_));
     CK(cudaStreamSynchronize(s.copy_stream));
     t_sync = ms_since();
   }   // zero-fill thread joined here
+  if (verify.t.joinable()) verify.t.join();
+  mismatch = host_mismatch.load();
   if (trace)
     fprintf(stderr, "[hfq] fused_host spec=%d: pack done %.1f  J done %.1f  K done %.1f  copies done %.1f  joined %.1f ms (zero-fill %.1f)\n",
             (int)spec, t_pack, t_j, t_k, t_sync, ms_since(), t_zero);

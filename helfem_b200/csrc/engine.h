@@ -102,6 +102,7 @@ class Engine {
   double copy_ranges_async(double *H, int64_t ldH, const double *D, const HostRanges &hr, cudaStream_t st, int cb = 0,
                            int ce = -1) const;   // returns bytes
   static void zero_outside(double *H, int64_t ldH, int n, const HostRanges &hr, int cb = 0, int ce = -1);
+  static bool nonzero_outside(const double *H, int64_t ldH, int n, const std::vector<int> &r0, const std::vector<int> &r1);
   bool fused_host(const double *P, int64_t ldP, double kscale, double *J, int64_t ldJ, double *K, int64_t ldK, bool spec);
   HostRanges density_ranges() const;   // bounding non-zero row range per column of the density packed last
   int spec_hits_ = 0;
