@@ -546,8 +546,9 @@ def main():
                     "call": ("hfq_fock_build, dense page-locked host matrices in and out. P: the row ranges that were non-zero in "
                              "the previous call are uploaded and the build starts on them, while host threads verify that "
                              "every other element of the caller's P is exactly zero (mismatch = rebuild from the complete "
-                             "upload; speculative_hits counts the calls that did not need it). J, K: only the row "
-                             "ranges of the non-zero blocks cross PCIe, the rest of the host matrices is zero-filled by host "
+                             "upload; speculative_hits counts the calls that did not need it). J: the complete dense matrix "
+                             "travels over the otherwise idle device-to-host link while K is being built; K: only the row "
+                             "ranges of the non-zero blocks cross PCIe, the rest of the host matrix is zero-filled by host "
                              "threads while the GPU computes") if world == 1 else
                             ("hfq_fock_build with a communicator: ONE set of host matrices in POSIX shared memory, page-locked by "
                              "every rank; each rank uploads its 1/N column slice of P over its own PCIe link, one in-place "
