@@ -343,7 +343,7 @@ def main():
         dist.barrier()
 
     acc = {"ms_pack": 0.0, "ms_unpack": 0.0, "ms_total": 0.0, "ms_fold": 0.0, "ms_tgemm": 0.0, "ms_offdiag": 0.0, "alg_fold": 0.0, "alg_tgemm": 0.0, "alg_offdiag": 0.0,
-           "launches": 0.0, "launches_tgemm": 0.0, "flops_tgemm": 0.0, "n": 0}
+           "launches": 0.0, "launches_tgemm": 0.0, "flops_tgemm": 0.0, "flops_fold": 0.0, "flops_offdiag": 0.0, "n": 0}
 
     def step_device(collect=False):
         # one Fock build: XC (HF: grid density + Nel), J = coulomb(P), K = exchange(P/2); with a communicator the
@@ -471,6 +471,17 @@ def main():
         assert ek < 1e-12 and ej < 1e-12, "host and device paths disagree: %g %g" % (ek, ej)
         assert abs(nel_h.value - nel_ref) < 1e-9 * abs(nel_ref)
 
+    per_rank = None
+    if world > 1:
+        # sharded kernels per rank (ms per build and executed Gflop): shows how level the owner-computes assignment is
+        nst_ = max(acc["n"], 1)
+        mine = torch.tensor([acc["ms_fold"] / nst_, acc["ms_tgemm"] / nst_, acc["ms_offdiag"] / nst_, acc["ms_total"] / nst_,
+                             acc["flops_fold"] / nst_ / 1e9, acc["flops_tgemm"] / nst_ / 1e9, acc["flops_offdiag"] / nst_ / 1e9],
+                            dtype=torch.float64, device="cuda")
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"columns": ["fold_ms", "gemm_ms", "cross_element_ms", "exchange_path_ms", "fold_gflop", "gemm_gflop", "cross_gflop"],
+                    "ranks": [[round(float(x), 3) for x in t.tolist()] for t in allr]}
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -556,7 +567,7 @@ def main():
                              "row ranges of its column slice of J and K and zero-fills the rest; host barrier at the end"),
                     "speculative_hits": spec_hits},
             "gpu_launches": int(acc["launches"]), "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,
-            "vxc_dft": vxc_dft,
+            "vxc_dft": vxc_dft, "per_rank": per_rank,
             "clocks": sampler.summary(),
             "setup": {"host_compute_tei_s": t_setup, "device_compute_tei": tei_dev, "device_upload_s": t_upload, "Nbf": n,
                       "channels": T.nlm}}
