@@ -834,8 +834,8 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
   // while the (tensor-pipe-bound) exchange kernels run; the unpack then writes the blocks that can be non-zero
   if (!s.aux_stream) {
     CK(cudaStreamCreateWithPriority(&s.aux_stream, cudaStreamNonBlocking, s.prio_hi));
-    CK(cudaEventCreateWithFlags(&s.ev_start, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&s.ev_kzero, cudaEventDisableTiming));
+    CK(cudaEventCreate(&s.ev_start));
+    CK(cudaEventCreate(&s.ev_kzero));
   }
   CK(cudaEventRecord(s.ev_start, st));   // earlier work on st that still reads K must finish first
   CK(cudaStreamWaitEvent(s.aux_stream, s.ev_start, 0));
@@ -1343,6 +1343,16 @@ void Engine::exchange_dev(const double *dP, int64_t ldP, double *dK, int64_t ldK
   CK(cudaEventElapsedTime(&tm_.pack, s.ev[0], s.ev[1]));
   CK(cudaEventElapsedTime(&tm_.unpack, s.ev[6], s.ev[7]));
   CK(cudaEventElapsedTime(&tm_.total, s.ev[0], s.ev[7]));
+  {
+    static const bool trace = getenv("HFQ_TRACE") && atoi(getenv("HFQ_TRACE"));
+    if (trace) {
+      float kz = 0, t6 = 0;
+      cudaEventElapsedTime(&kz, s.ev_start, s.ev_kzero);
+      cudaEventElapsedTime(&t6, s.ev[0], s.ev[6]);
+      fprintf(stderr, "[hfq] exchange_dev: K cleared on the side stream %.2f ms after the start, kernels done at %.2f ms, reduce+gather+unpack %.2f ms\n",
+              kz, t6, tm_.unpack);
+    }
+  }
   tm_.fold = ms_fold;
   tm_.tgemm = ms_tg;
   tm_.offdiag = ms_off;
