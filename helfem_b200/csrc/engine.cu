@@ -132,11 +132,8 @@ struct Engine::Impl {
     DevBuf<dev::GemmEntry> d_entries, d_uentries;
     DevBuf<int> d_blocks;
   } jplan;
-  cudaStream_t copy_stream = nullptr, up_stream = nullptr, j_stream = nullptr;
+  cudaStream_t copy_stream = nullptr, j_stream = nullptr;
   cudaEvent_t ev_packed = nullptr, ev_jdone = nullptr;
-  cudaEvent_t ev_up = nullptr;
-  DevBuf<double> d_Pfull;
-  DevBuf<int> d_flag;
   std::vector<int> pred_r0, pred_r1;   // predicted non-zero row range per column of P (from the last verified call)
   cudaEvent_t ev_j = nullptr, ev_jcopied = nullptr;
   cudaEvent_t ev[8];
@@ -1379,9 +1376,9 @@ Engine::~Engine() {
   plans_.reset();
   if (p_) {
     for (auto &e : p_->ev) cudaEventDestroy(e);
-    for (cudaEvent_t e : {p_->ev_packed, p_->ev_jdone, p_->ev_up, p_->ev_j, p_->ev_jcopied, p_->ev_start, p_->ev_kzero, p_->ev_fence})
+    for (cudaEvent_t e : {p_->ev_packed, p_->ev_jdone, p_->ev_j, p_->ev_jcopied, p_->ev_start, p_->ev_kzero, p_->ev_fence})
       if (e) cudaEventDestroy(e);
-    for (cudaStream_t st : {p_->copy_stream, p_->up_stream, p_->j_stream, p_->aux_stream})
+    for (cudaStream_t st : {p_->copy_stream, p_->j_stream, p_->aux_stream})
       if (st) cudaStreamDestroy(st);
     if (!p_->norms_host.empty()) cudaHostUnregister(p_->norms_host.data());
     if (p_->flags_host) cudaFreeHost(p_->flags_host);
@@ -1773,11 +1770,8 @@ bool Engine::fused_host(const double *P, int64_t ldP, double kscale, double *J, 
   if (s.d_O2.n < n * n) s.d_O2.alloc(n * n, &dev_bytes_);
   if (!s.copy_stream) {
     CK(cudaStreamCreateWithFlags(&s.copy_stream, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&s.up_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&s.ev_j, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&s.ev_jcopied, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&s.ev_up, cudaEventDisableTiming));
-    s.d_flag.alloc(1, &dev_bytes_);
   }
   double h2d = spec ? 0.0 : (double)n * n * sizeof(double);
   std::atomic<int> host_mismatch{0};

@@ -108,15 +108,6 @@ k_block_norms(BasisDev b, const double *__restrict__ P, int64_t ld, const int *_
   }
 }
 
-// flag = 1 if the two buffers differ in any bit (verification of a speculatively assembled density)
-static __global__ void k_any_diff(const unsigned long long *__restrict__ a, const unsigned long long *__restrict__ b, size_t n,
-                                  int *__restrict__ flag) {
-  bool diff = false;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    diff |= a[i] != b[i];
-  if (__any_sync(0xffffffffu, diff) && (threadIdx.x & 31) == 0) *flag = 1;
-}
-
 // grid (Nrad [column radial c], nactive sector pairs); splist[y] = sp index
 static __global__ void k_pack(BasisDev b, const double *__restrict__ P, int64_t ld, const int *__restrict__ splist,
                        double *__restrict__ Ppix) {
