@@ -449,7 +449,8 @@ def main():
         hJ.fill_(float("nan"))   # the call must define every element (copied blocks + host zero-fill)
         hK.fill_(float("nan"))
     barrier()
-    step_host()
+    for _ in range(max(args.warmup, 1)):   # the same W untimed steps as the device-resident leg
+        step_host()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -558,7 +559,8 @@ def main():
                              "the previous call are uploaded and the build starts on them, while host threads verify that "
                              "every other element of the caller's P is exactly zero (mismatch = rebuild from the complete "
                              "upload; speculative_hits counts the calls that did not need it). J: the complete dense matrix "
-                             "travels over the otherwise idle device-to-host link while K is being built; K: only the row "
+                             "(a share of its columns that follows the measured finish times of the two sides) travels over the "
+                             "otherwise idle device-to-host link while K is being built; K and the rest of J: only the row "
                              "ranges of the non-zero blocks cross PCIe, the rest of the host matrix is zero-filled by host "
                              "threads while the GPU computes") if world == 1 else
                             ("hfq_fock_build with a communicator: ONE set of host matrices in POSIX shared memory, page-locked by "

@@ -14,6 +14,9 @@
 #include <thread>
 
 #include <omp.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include "comm.h"
 #include "kernels.cuh"
@@ -133,6 +136,7 @@ struct Engine::Impl {
     DevBuf<int> d_blocks;
   } jplan;
   cudaStream_t copy_stream = nullptr, j_stream = nullptr;
+  double j_dense_frac = 0.5;   // share of the columns of J that a host-pointer build returns densely over PCIe
   cudaEvent_t ev_packed = nullptr, ev_jdone = nullptr;
   std::vector<int> pred_r0, pred_r1;   // predicted non-zero row range per column of P (from the last verified call)
   cudaEvent_t ev_j = nullptr, ev_jcopied = nullptr;
@@ -1630,6 +1634,23 @@ bool Engine::nonzero_outside(const double *H, int64_t ldH, int n, const std::vec
   return found != 0;
 }
 
+namespace {
+// Zero-fill with non-temporal stores: a column piece (~100 KB) is below the size from which memset switches to
+// streaming stores, so memset would read every cache line before overwriting it (read-for-ownership) and double the
+// memory traffic of what is the longest part of a host-pointer call.
+inline void stream_zero(double *p, size_t count) {
+#if defined(__SSE2__)
+  size_t i = 0;
+  while (i < count && (reinterpret_cast<uintptr_t>(p + i) & 15)) p[i++] = 0.0;
+  const __m128d z = _mm_setzero_pd();
+  for (; i + 2 <= count; i += 2) _mm_stream_pd(p + i, z);
+  for (; i < count; i++) p[i] = 0.0;
+#else
+  std::memset(p, 0, count * sizeof(double));
+#endif
+}
+}  // namespace
+
 void Engine::zero_outside(double *H, int64_t ldH, int n, const HostRanges &hr, int cb, int ce) {
   const bool none = (int)hr.r0.size() != n;   // no pattern: everything is zero
   // leave cores to the thread that feeds the GPU.  The count set through hfq_set_host_threads is kept in a process
@@ -1637,15 +1658,21 @@ void Engine::zero_outside(double *H, int64_t ldH, int n, const HostRanges &hr, i
   // 1), not from the omp_set_num_threads of the calling thread
   const int nthr = std::max(1, host_threads() - 2);
   if (ce < 0) ce = n;
-#pragma omp parallel for schedule(static) num_threads(nthr)
-  for (int c = cb; c < ce; c++) {
-    double *col = H + (int64_t)c * ldH;
-    if (none) {
-      std::memset(col, 0, (size_t)n * sizeof(double));
-      continue;
+#pragma omp parallel num_threads(nthr)
+  {
+#pragma omp for schedule(static)
+    for (int c = cb; c < ce; c++) {
+      double *col = H + (int64_t)c * ldH;
+      if (none) {
+        stream_zero(col, (size_t)n);
+        continue;
+      }
+      if (hr.r0[c] > 0) stream_zero(col, (size_t)hr.r0[c]);
+      if (hr.r1[c] < n) stream_zero(col + hr.r1[c], (size_t)(n - hr.r1[c]));
     }
-    if (hr.r0[c] > 0) std::memset(col, 0, (size_t)hr.r0[c] * sizeof(double));
-    if (hr.r1[c] < n) std::memset(col + hr.r1[c], 0, (size_t)(n - hr.r1[c]) * sizeof(double));
+#if defined(__SSE2__)
+    _mm_sfence();   // every thread orders its own streaming stores before it leaves the region
+#endif
   }
 }
 
@@ -1764,7 +1791,7 @@ bool Engine::fused_host(const double *P, int64_t ldP, double kscale, double *J, 
   static const bool trace = getenv("HFQ_TRACE") && atoi(getenv("HFQ_TRACE"));
   const auto tstart = std::chrono::steady_clock::now();
   auto ms_since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tstart).count(); };
-  double t_pack = 0, t_j = 0, t_k = 0, t_sync = 0, t_zero = 0;
+  double t_pack = 0, t_j = 0, t_k = 0, t_sync = 0, t_zero = 0, t_zero_end = 0;
   if (s.d_P.n < n * n) s.d_P.alloc(n * n, &dev_bytes_);
   if (s.d_O.n < n * n) s.d_O.alloc(n * n, &dev_bytes_);
   if (s.d_O2.n < n * n) s.d_O2.alloc(n * n, &dev_bytes_);
@@ -1830,21 +1857,24 @@ bool Engine::fused_host(const double *P, int64_t ldP, double kscale, double *J, 
           cudaGetLastError();
       }
       hrj = host_ranges(true);
-      if (j_dense) {
-        CK(cudaMemcpy2DAsync(J, (size_t)ldJ * sizeof(double), s.d_O2.p, n * sizeof(double), n * sizeof(double), n,
+      // columns [0, cj) of J travel densely, the others as row ranges + host zero-fill; the split follows the
+      // measured finish times of the two sides (PCIe rate and host-memory speed differ from host to host)
+      const int cj = j_dense ? std::min((int)n, std::max(0, (int)std::lround(s.j_dense_frac * (double)n))) : 0;
+      if (cj > 0) {
+        CK(cudaMemcpy2DAsync(J, (size_t)ldJ * sizeof(double), s.d_O2.p, n * sizeof(double), n * sizeof(double), (size_t)cj,
                              cudaMemcpyDeviceToHost, s.copy_stream));
-        jbytes = (double)n * n * sizeof(double);
-      } else {
-        jbytes = copy_ranges_async(J, ldJ, s.d_O2.p, hrj, s.copy_stream);
+        jbytes = (double)n * cj * sizeof(double);
       }
+      if (cj < (int)n) jbytes += copy_ranges_async(J, ldJ, s.d_O2.p, hrj, s.copy_stream, cj, (int)n);
       s.kscale = kscale;
-      plan_hook_ = [&, j_dense]() {
+      plan_hook_ = [&, cj]() {
         hrk = host_ranges(false);
-        zero.t = std::thread([&, j_dense]() {
+        zero.t = std::thread([&, cj]() {
           const double z0 = ms_since();
-          if (!j_dense) zero_outside(J, ldJ, nbf_, hrj);
+          if (cj < nbf_) zero_outside(J, ldJ, nbf_, hrj, cj, nbf_);
           zero_outside(K, ldK, nbf_, hrk);
           t_zero = ms_since() - z0;
+          t_zero_end = ms_since();
         });
       };
       exchange_dev(s.d_P.p, (int64_t)n, s.d_O.p, (int64_t)n, 0, 1, stream_);
@@ -1869,9 +1899,16 @@ bool Engine::fused_host(const double *P, int64_t ldP, double kscale, double *J, 
   }   // zero-fill thread joined here
   if (verify.t.joinable()) verify.t.join();
   mismatch = host_mismatch.load();
+  // steer the dense share of J: the side that finished later gives work to the other
+  if (t_zero_end > 0.0) {
+    if (t_sync > t_zero_end + 2.0)
+      s.j_dense_frac = std::max(0.0, s.j_dense_frac - 0.1);
+    else if (t_zero_end > t_sync + 2.0)
+      s.j_dense_frac = std::min(1.0, s.j_dense_frac + 0.1);
+  }
   if (trace)
-    fprintf(stderr, "[hfq] fused_host spec=%d: pack done %.1f  J done %.1f  K done %.1f  copies done %.1f  joined %.1f ms (zero-fill %.1f)\n",
-            (int)spec, t_pack, t_j, t_k, t_sync, ms_since(), t_zero);
+    fprintf(stderr, "[hfq] fused_host spec=%d: pack done %.1f  J done %.1f  K done %.1f  copies done %.1f  joined %.1f ms (zero-fill %.1f, dense share of J next %.1f)\n",
+            (int)spec, t_pack, t_j, t_k, t_sync, ms_since(), t_zero, s.j_dense_frac);
   if (mismatch) {
     s.pred_r0.clear();
     s.pred_r1.clear();
