@@ -1613,6 +1613,12 @@ namespace {
 std::atomic<int> g_host_threads{0};
 }
 void set_host_threads(int n) { g_host_threads.store(n); }
+// threads of the host-side helpers (zero-fill, verification scan): all of this process' share of the cores, minus two for
+// the threads that feed the GPU when the share is large enough (a rank of an 8-GPU job may own only 2-4 cores)
+static int helper_threads() {
+  const int ht = host_threads();
+  return std::max(1, ht > 4 ? ht - 2 : ht);
+}
 int host_threads() {
   const int n = g_host_threads.load();
   return n > 0 ? n : omp_get_max_threads();
@@ -1621,7 +1627,7 @@ int host_threads() {
 // true if any element of the n x n column-major matrix H outside the row ranges [r0[c], r1[c]) has a non-zero bit
 // pattern (-0.0 and NaN count as non-zero: the caller then falls back to the complete upload)
 bool Engine::nonzero_outside(const double *H, int64_t ldH, int n, const std::vector<int> &r0, const std::vector<int> &r1) {
-  const int nthr = std::max(1, host_threads() - 2);
+  const int nthr = helper_threads();
   int found = 0;
 #pragma omp parallel for schedule(static) num_threads(nthr) reduction(| : found)
   for (int c = 0; c < n; c++) {
@@ -1656,7 +1662,7 @@ void Engine::zero_outside(double *H, int64_t ldH, int n, const HostRanges &hr, i
   // leave cores to the thread that feeds the GPU.  The count set through hfq_set_host_threads is kept in a process
   // global: this runs in a helper std::thread, whose OpenMP ICVs start from OMP_NUM_THREADS again (torchrun exports
   // 1), not from the omp_set_num_threads of the calling thread
-  const int nthr = std::max(1, host_threads() - 2);
+  const int nthr = helper_threads();
   if (ce < 0) ce = n;
 #pragma omp parallel num_threads(nthr)
   {
