@@ -96,6 +96,35 @@ def test_no_cpu_fallback(hb):
         b.coulomb(np.zeros((b.Nbf(), b.Nbf())))
 
 
+def test_device_compute_tei_needs_its_gpu(hb):
+    """hfq_tables_diatomic_device has no host fallback: without that CUDA device it fails."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(hb.HfqError):
+        hb.Tables.diatomic(7, 7, 2.07, [2, 2], 1, device=0)
+
+
+def test_sap_occupation_tables():
+    """Host logic of the batched SAP driver: the tabulated per-l configurations (extracted from the reference's
+    pbe_ground_states, src/diatomic/twodquadrature.cpp:26-145) hold Z electrons each, shells fill by capacity with a
+    fractional remainder, and the by-element distribution deals every element to exactly one rank."""
+    from helfem_b200 import sap
+    occ, sym = sap.ground_state_occupations()
+    assert len(occ) == 118 and sym[1] == "H" and sym[86] == "Rn" and occ[10] == [4, 6, 0, 0] and occ[36] == [8, 18, 10, 0]
+    for z, ol in occ.items():
+        assert sum(ol) == z, z
+    o = sap.shell_occupations(7.5, 2, 6)            # d shells: capacity 10
+    assert list(o) == [7.5, 0, 0, 0, 0, 0]
+    o = sap.shell_occupations(24.25, 1, 6)          # p shells: capacity 6
+    assert list(o) == [6, 6, 6, 6, 0.25, 0]
+    zs = list(range(1, 87))
+    parts = [sap.elements_of_rank(zs, r, 8) for r in range(8)]
+    assert sorted(z for p in parts for z in p) == zs and max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+    # heaviest-first round-robin: the six lanthanides whose tabulated configuration needs the refill land on six ranks
+    assert len({r for r in range(8) for z in parts[r] if 64 <= z <= 69}) == 6
+
+
 def test_product_does_not_touch_the_oracle():
     pkg = os.path.join(ROOT, "helfem_b200")
     for dp, _, files in os.walk(pkg):
