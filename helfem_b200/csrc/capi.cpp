@@ -368,6 +368,10 @@ int hfq_tables_one_electron(const hfq_tables *h, double *S, double *T, double *V
   if (!h || !S || !T || !V) return fail(HFQ_ERR_INVALID, "hfq_tables_one_electron: null argument");
   if (h->t.bval.empty()) return fail(HFQ_ERR_STATE, "hfq_tables_one_electron: tables were not built by this library");
   return guarded([&] {
+    if (h->t.kind == hfq::BasisKind::Diatomic) {
+      hfq::diatomic_one_electron_into(h->t, S, T, V);
+      return HFQ_OK;
+    }
     std::vector<double> s, t, v;
     hfq::one_electron_matrices(h->t, s, t, v);
     std::memcpy(S, s.data(), s.size() * sizeof(double));

@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <memory>
 #include <set>
@@ -470,8 +471,19 @@ BasisTables build_diatomic_tables(int Z1, int Z2, double Rbond, const std::vecto
 }
 
 // One-electron matrices for the diatomic basis (basis.cpp:1032-1166).
+void diatomic_one_electron_into(const BasisTables &t, double *S, double *T, double *V);
+
 void diatomic_one_electron(const BasisTables &t, std::vector<double> &S, std::vector<double> &T,
                            std::vector<double> &V) {
+  const size_t nb = (size_t)t.Nbf();
+  S.resize(nb * nb);
+  T.resize(nb * nb);
+  V.resize(nb * nb);
+  diatomic_one_electron_into(t, S.data(), T.data(), V.data());
+}
+
+// S, T, V: caller-owned Nbf x Nbf column-major matrices; every element is defined (zero-filled in parallel first)
+void diatomic_one_electron_into(const BasisTables &t, double *S, double *T, double *V) {
   const FEBasis fe(t.nnodes, t.bval, false, true);
   const int N = t.Nrad, na = t.Nang();
   const int nseed = std::max(t.nquad, 5);
@@ -502,9 +514,20 @@ void diatomic_one_electron(const BasisTables &t, std::vector<double> &S, std::ve
   const GauntTable g(lmax + 2);
   const double pi = std::acos(-1.0);
   const double c0 = 2.0 / 3.0 * std::sqrt(pi), c2 = 4.0 / 15.0 * std::sqrt(5.0 * pi), c1 = 2.0 * std::sqrt(pi / 3.0);
+  // The blocks are written straight into the boundary-free matrices (the reference assembles them with the dummy
+  // functions and removes the boundaries afterwards, basis.cpp:1032-1166; for N2 that is 3 x 1.8 GB of intermediates
+  // of which 0.4 GB are non-zero): dense index of (angular i, radial a) = first[i] + a - skip[i], where the m != 0
+  // shells drop radial function 0.
   const std::vector<int64_t> pidx = t.pure_idx();
   const int nd = t.Ndummy(), nb = (int)pidx.size();
-  std::vector<double> Sd((size_t)nd * nd, 0.0), Td((size_t)nd * nd, 0.0), Vd((size_t)nd * nd, 0.0);
+  std::vector<int64_t> pure_of((size_t)nd, -1);
+  for (int k = 0; k < nb; k++) pure_of[pidx[k]] = k;
+#pragma omp parallel for schedule(static)
+  for (int c = 0; c < nb; c++) {
+    std::memset(S + (size_t)c * nb, 0, (size_t)nb * sizeof(double));
+    std::memset(T + (size_t)c * nb, 0, (size_t)nb * sizeof(double));
+    std::memset(V + (size_t)c * nb, 0, (size_t)nb * sizeof(double));
+  }
   const double R3 = std::pow(t.Rhalf, 3), R2 = t.Rhalf * t.Rhalf;
 #pragma omp parallel for collapse(2) schedule(dynamic, 8)
   for (int i = 0; i < na; i++)
@@ -513,30 +536,24 @@ void diatomic_one_electron(const BasisTables &t, std::vector<double> &S, std::ve
       const int li = t.lval[i], lj = t.lval[j], m = t.mval[i];
       const double cos2 = c0 * g.coeff(lj, m, 0, 0, li) + c2 * g.coeff(lj, m, 2, 0, li);
       const double cos1 = c1 * g.coeff(lj, m, 1, 0, li);
-      for (int b = 0; b < N; b++)
+      for (int b = 0; b < N; b++) {
+        const int64_t pc = pure_of[(size_t)j * N + b];
+        if (pc < 0) continue;
         for (int a = 0; a < N; a++) {
-          const size_t o = (size_t)(i * N + a) + (size_t)(j * N + b) * nd;
+          const int64_t pr = pure_of[(size_t)i * N + a];
+          if (pr < 0) continue;
+          const size_t o = (size_t)pr + (size_t)pc * nb;
           double s = -cos2 * I10(a, b), v = 0.0;
           if (li == lj) {
             s += I12(a, b);
             v += (double)(t.Z1 + t.Z2) * I11(a, b);
           }
           if (t.Z1 != t.Z2) v += (double)(t.Z2 - t.Z1) * cos1 * I10(a, b);
-          Sd[o] = R3 * s;
-          Vd[o] = -R2 * v;
-          if (i == j) Td[o] = 0.5 * t.Rhalf * (Trad(a, b) + (double)li * (li + 1) * I10(a, b) + (double)m * m * Im1(a, b));
+          S[o] = R3 * s;
+          V[o] = -R2 * v;
+          if (i == j) T[o] = 0.5 * t.Rhalf * (Trad(a, b) + (double)li * (li + 1) * I10(a, b) + (double)m * m * Im1(a, b));
         }
-    }
-  S.assign((size_t)nb * nb, 0.0);
-  T.assign((size_t)nb * nb, 0.0);
-  V.assign((size_t)nb * nb, 0.0);
-#pragma omp parallel for schedule(static)
-  for (int b = 0; b < nb; b++)
-    for (int a = 0; a < nb; a++) {
-      const size_t o = (size_t)pidx[a] + (size_t)pidx[b] * nd;
-      S[(size_t)a + (size_t)b * nb] = Sd[o];
-      T[(size_t)a + (size_t)b * nb] = Td[o];
-      V[(size_t)a + (size_t)b * nb] = Vd[o];
+      }
     }
 }
 

@@ -112,5 +112,7 @@ std::vector<double> sap_table(const BasisTables &t, const double *Pl_a, const do
 // column-major -- setup helpers so that callers/tests can run an SCF around the
 // Fock-build path (src/atomic/TwoDBasis.cpp:320-375, src/diatomic/basis.cpp:1032-1166).
 void one_electron_matrices(const BasisTables &t, std::vector<double> &S, std::vector<double> &T, std::vector<double> &V);
+// diatomic basis: straight into caller-owned Nbf x Nbf matrices (no intermediate copies)
+void diatomic_one_electron_into(const BasisTables &t, double *S, double *T, double *V);
 
 }  // namespace hfq
