@@ -34,7 +34,7 @@ class DeviceRHF:
         owner = np.repeat(mv, sizes)
         self.ms = sorted(set(int(m) for m in mv))
         f64 = dict(dtype=torch.float64, device=self.dev)
-        self.idx, self.X, self.H0b = [], [], []
+        self.idx, self.X, self.H0b, self.Sb = [], [], [], []
         for m in self.ms:
             ix = np.nonzero(owner == m)[0]
             self.idx.append(torch.from_numpy(ix).to(self.dev))
@@ -42,8 +42,8 @@ class DeviceRHF:
             d = torch.diagonal(Sb).rsqrt()
             w, U = torch.linalg.eigh(Sb * d[:, None] * d[None, :])
             self.X.append((U * w.rsqrt()[None, :]) @ U.T * d[:, None])
-            self.H0b.append(torch.tensor((T + V)[np.ix_(ix, ix)], **f64))
-        self.Sb = [torch.tensor(S[np.ix_(ix.cpu().numpy(), ix.cpu().numpy())], **f64) for ix in self.idx]
+            self.H0b.append(torch.tensor(T[np.ix_(ix, ix)] + V[np.ix_(ix, ix)], **f64))   # blocks first: T + V is 1.8 GB
+            self.Sb.append(Sb)
         del S, T, V
         # dense device matrices of the Fock build (column-major == transposed row-major; all symmetric here)
         self.P = torch.zeros((n, n), **f64)
