@@ -154,7 +154,16 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
   Impl &s = *p_;
   s.prio_hi = prio_hi;
   for (auto &e : s.ev) CK(cudaEventCreate(&e));
+  const bool timing = getenv("HFQ_SETUP_TIMING") != nullptr;
+  const auto t_ctor = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    if (!timing) return;
+    cudaDeviceSynchronize();
+    fprintf(stderr, "[hfq create] %-40s at %.3f s\n", what,
+            std::chrono::duration<double>(std::chrono::steady_clock::now() - t_ctor).count());
+  };
   s.t = tin;
+  lap("tables copied");
   const BasisTables &t = s.t;
   nbf_ = t.Nbf();
   if (t.Nel > 64) throw std::runtime_error("Engine: more than 64 radial elements not supported");
@@ -285,6 +294,7 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
       si++;
     }
   }
+  lap("sectors");
   s.mmin = *std::min_element(s.sec_m.begin(), s.sec_m.end());
   s.mmax = *std::max_element(s.sec_m.begin(), s.sec_m.end());
   s.nM = 2 * (s.mmax - s.mmin) + 1;
@@ -311,20 +321,38 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
 #pragma omp parallel for collapse(2) schedule(dynamic)
     for (int sa = 0; sa < s.ns; sa++)
       for (int sb = 0; sb < s.ns; sb++) {
-        const int sp = sa * s.ns + sb, ma = s.sec_m[sa], mb = s.sec_m[sb], M = ma - mb;
-        for (int L = std::abs(M); L < s.NL; L++) {
-          if (t.channel(L, std::abs(M)) < 0) continue;
-          bool any = false;
-          for (int ia = 0; ia < s.NP; ia++)
-            for (int ib = 0; ib < s.NP; ib++) {
-              const int anga = s.sec_ang[(size_t)sa * s.NP + ia], angb = s.sec_ang[(size_t)sb * s.NP + ib];
-              if (anga < 0 || angb < 0) continue;
-              const int la = t.lval[anga], lb = t.lval[angb];
-              if (L < std::max(std::abs(la - lb) - t.Lext, std::abs(M)) || L > la + lb + t.Lext) continue;
+        const int sp = sa * s.ns + sb, ma = s.sec_m[sa], mb = s.sec_m[sb], M = ma - mb, aM = std::abs(M);
+        std::vector<char> any(s.NL, 0);
+        // diatomic: the cos^2-modified coefficient (GauntTable::mod_coeff, src/general/gaunt.cpp:236-272) is a
+        // combination of plain coefficients of neighbouring orders,
+        //   mod(L) = c0 w0(L) q(L) + c2 sum_{Lp = max(L-2, 0, |M|)}^{L+2} w2(L, Lp) q(Lp),  q(Lp) = coeff(la, ma, lb, mb, Lp),
+        // whose weights depend on (L, M) only: they are tabulated per sector pair and q is evaluated once per order
+        // instead of up to six times (same operations in the same order as mod_coeff: identical values)
+        const double c0 = 2.0 / 3.0 * std::sqrt(std::acos(-1.0)), c2 = 4.0 / 15.0 * std::sqrt(5.0 * std::acos(-1.0));
+        std::vector<double> w0, w2, q;
+        if (t.kind == BasisKind::Diatomic) {
+          w0.assign(s.NL, 0.0);
+          w2.assign((size_t)s.NL * 5, 0.0);
+          q.assign(s.NL + 3, 0.0);
+          for (int L = aM; L < s.NL; L++) {
+            w0[L] = gt.coeff(L, M, 0, 0, L);
+            for (int Lp = std::max(std::max(L - 2, 0), aM); Lp <= L + 2; Lp++) w2[(size_t)L * 5 + (Lp - (L - 2))] = gt.coeff(Lp, M, 2, 0, L);
+          }
+        }
+        for (int ia = 0; ia < s.NP; ia++)
+          for (int ib = 0; ib < s.NP; ib++) {
+            const int anga = s.sec_ang[(size_t)sa * s.NP + ia], angb = s.sec_ang[(size_t)sb * s.NP + ib];
+            if (anga < 0 || angb < 0) continue;
+            const int la = t.lval[anga], lb = t.lval[angb];
+            const int Llo = std::max(std::abs(la - lb) - t.Lext, aM), Lhi = std::min(la + lb + t.Lext, s.NL - 1);
+            if (t.kind == BasisKind::Diatomic)
+              for (int Lp = std::max(Llo - 2, 0); Lp <= Lhi + 2; Lp++) q[Lp] = gt.coeff(la, ma, lb, mb, Lp);
+            for (int L = Llo; L <= Lhi; L++) {
+              if (t.channel(L, aM) < 0) continue;
               double *dst = &G[(((size_t)sp * s.NL + L) * t.nch) * s.NB + (size_t)ia * s.NP + ib];
               if (t.kind == BasisKind::Atomic) {
                 dst[0] = gt.coeff(la, ma, L, M, lb);
-                any |= dst[0] != 0.0;
+                any[L] |= dst[0] != 0.0;
               } else if (t.kind == BasisKind::Sadatom) {
                 // sqrt of the m-averaged squared coupling: both fold factors carry the same entry, so
                 // their product is sum_{m,m'} G(la,m,L,m-m',lb)^2 / (2 la + 1)  (src/sadatom/basis.cpp:248-259)
@@ -335,15 +363,18 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
                     tot += c * c;
                   }
                 dst[0] = std::sqrt(tot / (2 * la + 1));
-                any |= dst[0] != 0.0;
+                any[L] |= dst[0] != 0.0;
               } else {
-                dst[0] = gt.mod_coeff(la, ma, L, M, lb, mb);
+                const double cpl0 = w0[L] * q[L];
+                double cpl2 = 0.0;
+                for (int Lp = std::max(std::max(L - 2, 0), aM); Lp <= L + 2; Lp++) cpl2 += w2[(size_t)L * 5 + (Lp - (L - 2))] * q[Lp];
+                dst[0] = c0 * cpl0 + c2 * cpl2;
                 dst[s.NB] = -gt.coeff(la, ma, L, M, lb);
-                any |= dst[0] != 0.0 || dst[s.NB] != 0.0;
+                any[L] |= dst[0] != 0.0 || dst[s.NB] != 0.0;
               }
             }
-          s.G_nonzero[(size_t)sp * s.NL + L] = any;
-        }
+          }
+        for (int L = 0; L < s.NL; L++) s.G_nonzero[(size_t)sp * s.NL + L] = any[L];
       }
     s.d_G.upload(G, &dev_bytes_);
   }
@@ -392,6 +423,7 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
     s.op_stride = off;
   }
   s.d_ep_off.upload(s.ep_off, &dev_bytes_);
+  lap("coupling tables + cache upload");
   // ---- dense exchange-ordered in-element kernels, one per (multipole channel, element), stored as
   //      the pre-swizzled k-chunk tiles k_tgemm_ws bulk-copies (kernels.cuh: tperm_index)
   if (t.pairwise()) {
@@ -458,6 +490,7 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
       }
     CK(cudaGetLastError());
   }
+  lap("dense in-element kernels (k_build_tperm)");
   // ---- B-row offset tables
   {
     // T-GEMM: k' = ab*n*n + ri*n + rl -> (ab*Npix + pix(ri,rl)) * NB
@@ -530,6 +563,7 @@ Engine::Engine(const BasisTables &tin, int device) : p_(new Impl), device_(devic
   s.d_zrow.upload(std::vector<double>(64, 0.0), &dev_bytes_);
   // opt-in shared memory of the fold kernel this basis uses (a per-device attribute: set by every engine)
   launch_fold(s.NT, t.nch, s.parity, s.bd, nullptr, 0, nullptr, 0, 0, nullptr, nullptr, nullptr, stream_);
+  lap("done");
 }
 
 
