@@ -213,9 +213,12 @@ class TwoDBasis {
 
 }  // namespace diatomic
 
-// DFTGrid::eval_Fxc of the atomic / diatomic drivers for the functionals built into the library
-// (x_func = 1 Slater exchange, <= 0 none: the HF drivers still call it to integrate Nel).  For any other
-// functional use hfq_grid_density / hfq_grid_fxc around the caller's own libxc calls.
+// DFTGrid::eval_Fxc of the atomic / diatomic drivers for the functionals built into the library and evaluated on
+// the device, selected by their libxc ids like the reference's call: x_func = 1 Slater, 101 PBE, 202 TPSS exchange;
+// c_func = 7 VWN5, 130 PBE, 231 TPSS correlation (correlation: restricted densities); <= 0 none (the HF drivers still
+// call it to integrate Nel).  For any other functional use hfq_grid_density / hfq_grid_fxc around the caller's own
+// libxc calls.  The x_pars / c_pars vectors of the reference's signature are dropped:
+// none of the built-in functionals has external parameters.
 template <class Mat>
 class DFTGrid {
  public:
